@@ -1,0 +1,269 @@
+#!/usr/bin/env python
+"""Benchmark of the graphBIX hot path on B200: EM + BP on a synthetic planted-partition SBM.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[2], the single-GPU configuration the metric is quoted on):
+sbm.jl full-affinity SBM, N = 1M vertices, average degree 16, q = 8, FP64 messages.
+
+A "step" is one EM iteration of sbm.jl:342-347: one BP sweep over all K = 2E directed edges, the M-step
+(update_Crs) and update_theta.  metric = directed-edge message updates / second = K * steps / time, summed
+over ranks (weak scaling: every rank owns an independent graph of the same shape; no data-path collective).
+
+  value      device-resident: graph and messages already in HBM, K steps timed with CUDA events
+  e2e        the same metric through the public call a user of the reference makes -- EM(...) with HOST
+             buffers: graph build + H2D of links and initial messages + K iterations + free energy / CV
+             errors + D2H of PSI, gr, Crs
+  roofline   BP-sweep kernel alone (the dominant kernel): algorithmic bytes / CUDA-event time
+  cpu_baseline / --impl reference: the CPU restatement of the reference's EM() (oracle/) on the host cores,
+             on a bounded sample of the same workload (smaller N, same degree and q).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "bp_directed_edge_message_updates_per_sec"
+UNIT = "updates/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--deg", type=float, default=16.0)
+    ap.add_argument("--q", type=int, default=8)
+    ap.add_argument("--eps", type=float, default=0.1)
+    ap.add_argument("--dc", type=int, default=1)
+    ap.add_argument("--cpu-n", type=int, default=0, help="vertices of the bounded CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f"sbm.jl full-affinity SBM, planted partition N={a.n}, avg degree {a.deg:g}, q={a.q}, FP64 messages"
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(a, steps, warmup):
+    """The oracle (CPU restatement of the reference's EM loop) on a bounded sample of the workload."""
+    from graphbix_b200.synth import planted_partition, random_messages
+    try:
+        from oracle import sbm_oracle_c as OC
+        have_c = OC.available()
+    except Exception:
+        have_c = False
+    n = a.cpu_n or (200_000 if have_c else 1500)
+    links, _ = planted_partition(n, a.q, a.deg, a.eps, seed=7, connected_only=True)
+    n = int(links.max())
+    K = links.shape[0]
+    psi0 = random_messages(K, a.q, seed=8)
+    gr0 = np.ones(a.q) / a.q
+    C0 = 20 * np.eye(a.q) + 0.01 * np.ones((a.q, a.q))
+    total = steps + warmup
+    if have_c:
+        t_per_itr, cores = OC.time_em_iterations(n, a.q, links, psi0, gr0, C0, bool(a.dc), True, 0.3, warmup, steps)
+        kind_note = "C port of oracle/sbm_oracle.py (gcc -O2)"
+    else:
+        from oracle import sbm_oracle as O
+        t0 = time.perf_counter()
+        O.EM(n, a.q, links, n, (gr0, C0), bool(a.dc), warmup, True, 0.3, PSIcav0=psi0, BPconvthreshold=0.0)
+        t1 = time.perf_counter()
+        O.EM(n, a.q, links, n, (gr0, C0), bool(a.dc), total, True, 0.3, PSIcav0=psi0, BPconvthreshold=0.0)
+        t2 = time.perf_counter()
+        t_per_itr = max(((t2 - t1) - (t1 - t0)) / steps, 1e-9)
+        cores = 1
+        kind_note = "numpy/Python restatement oracle/sbm_oracle.py"
+    value = K / t_per_itr
+    sample = (f"{steps} EM iterations (sweep + update_Crs + update_theta) on a planted partition N={n}, "
+              f"avg degree {a.deg:g}, q={a.q} ({K} directed edges); {kind_note}")
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}, t_per_itr
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = min(a.steps, 5)
+    warmup = min(a.warmup, 1)
+    base, t_per_itr = cpu_reference_run(a, steps, warmup)
+    line = {"metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": t_per_itr * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": workload_name(a), "sample": base["sample"]},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from graphbix_b200.engine import EM, SbmEngine
+    from graphbix_b200.synth import planted_partition, random_messages
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for --impl ours)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    links, _ = planted_partition(a.n, a.q, a.deg, a.eps, seed=100 + rank, connected_only=False)
+    n = a.n
+    K = int(links.shape[0])
+    gr0 = np.ones(a.q) / a.q
+    C0 = 20 * np.eye(a.q) + 0.01 * np.ones((a.q, a.q))       # "uniformAssortative", sbm.jl:290-292
+
+    stream = torch.cuda.current_stream()
+    eng = SbmEngine(n, links, a.q, device=local, stream=stream)
+    eng.set_options(degreecorrection=a.dc, priorlearning=1, learningrate=0.3, itrmax=a.steps)
+    eng.init(gr0, C0, None, seed=1234 + rank)
+
+    # ---- device-resident EM iterations ----
+    eng.iterate(a.warmup, read_conv=False)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    eng.iterate(a.steps, read_conv=False)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count - l0
+    # ---- the BP sweep kernel alone (roofline) ----
+    nsweep = max(10, min(a.steps, 50))
+    eng.bp_sweeps(3)
+    torch.cuda.synchronize()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record(stream)
+    eng.bp_sweeps(nsweep)
+    s1.record(stream)
+    torch.cuda.synchronize()
+    sweep_ms = s0.elapsed_time(s1) / nsweep
+    sampler.stop_flag.set()
+    sampler.join()
+    sweep_bytes = eng.sweep_bytes
+    dev_bytes = eng.device_bytes
+    eng.close()
+
+    # ---- end to end through EM() with host buffers ----
+    psi0 = random_messages(K, a.q, seed=55 + rank)
+    barrier()
+    t0 = time.perf_counter()
+    out = EM(n, a.q, links, n, (gr0, C0), bool(a.dc), a.steps, True, 0.3, PSIcav0=psi0, BPconvthreshold=0.0,
+             device=local)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    h2d = links.nbytes + psi0.nbytes
+    d2h = out[2].nbytes + out[1].nbytes + out[0].nbytes
+
+    t = torch.tensor([ms, sweep_ms, t_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, sweep_ms, t_e2e = (float(x) for x in t.tolist())
+    value = world * K * a.steps / (ms * 1e-3)
+    e2e_value = world * K * a.steps / t_e2e
+    peak, peak_src = measured_peak_gbs()
+    achieved = sweep_bytes / (sweep_ms * 1e-3) / 1e9
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(a), "directed_edges_per_gpu": K, "degreecorrection": bool(a.dc),
+                           "priorlearning": True, "init": "uniformAssortative", "damping": 1.0,
+                           "parallelism": f"{world} independent graph(s), one per GPU",
+                           "l2_policy": f"inputs larger than L2: {dev_bytes / 1e6:.0f} MB resident per GPU vs 126 MB L2",
+                           "step": "one EM iteration = BP sweep + update_Crs + update_theta"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / a.steps,
+                        "d2h_bytes_per_step": d2h / a.steps, "seconds": t_e2e,
+                        "what": "EM() with host buffers: CSR build, H2D, steps iterations, free energy + CV, D2H"},
+                "gpu_launches": launches, "clocks": sampler.summary(),
+                "roofline": {"bound": "hbm", "kernel": "sbm_vertex_kernel<8,SWEEP> (BP sweep)", "achieved": achieved,
+                             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "peak_source": peak_src, "ms_per_launch": sweep_ms, "algorithmic_bytes": sweep_bytes,
+                             "sweep_updates_per_sec": K / (sweep_ms * 1e-3)}}
+        if not a.no_cpu_baseline and world == 1:
+            try:
+                line["cpu_baseline"], _ = cpu_reference_run(a, 2, 1)
+            except Exception as e:  # the baseline is reported, never required
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

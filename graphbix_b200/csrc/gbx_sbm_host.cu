@@ -1,0 +1,498 @@
+// libgraphbix_cuda.so -- host side of the sbm.jl EM() replacement: C ABI (include/graphbix_cuda.h), graph
+// construction (destination-major CSR of the 2E directed edges, reverse-edge index, tile schedule) and the
+// EM loop of sbm.jl:337-367 driving the per-q kernels of gbx_sbm_q.cu.  sm_100a only, no CPU path.
+//
+// Data layout in HBM (DESIGN.md has the full story)
+//   * slot e of row i holds the cavity message col[e] -> i, q doubles (64 B at q = 8), so a vertex reads its
+//     incoming messages as one contiguous run; rev[e] = slot of the opposite message i -> col[e];
+//   * two message buffers (ping-pong): a sweep reads `cur` and scatters the new messages to `nxt` at rev[e]
+//     with 256-bit stores -- a synchronous (Jacobi) sweep, deterministic by construction;
+//   * PSI (N x q), theta (N); tiles = runs of consecutive vertices with <= 256 edge slots (one CTA iteration
+//     each, one thread per slot); vertices with more than 256 edges ("hubs") get a CTA each.
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "gbx_sbm_internal.h"
+
+namespace gbx {
+
+std::string& last_error() {
+  static thread_local std::string s;
+  return s;
+}
+
+#ifndef GBX_FOR_EACH_Q
+#define GBX_FOR_EACH_Q(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
+#endif
+#define GBX_DECL(qq) const SbmOps* sbm_ops_q##qq();
+GBX_FOR_EACH_Q(GBX_DECL)
+#undef GBX_DECL
+
+static const SbmOps* ops_for(int q) {
+#define GBX_CASE(qq) \
+  if (q == qq) return sbm_ops_q##qq();
+  GBX_FOR_EACH_Q(GBX_CASE)
+#undef GBX_CASE
+  return nullptr;
+}
+
+}  // namespace gbx
+
+using namespace gbx;
+
+namespace {
+
+#define GBX_TRY(expr)            \
+  do {                           \
+    int _r = (expr);             \
+    if (_r != GBX_OK) return _r; \
+  } while (0)
+
+int fail_invalid(const char* msg) {
+  last_error() = msg;
+  return GBX_ERR_INVALID;
+}
+
+int fail_state() {
+  last_error() = "gbx_sbm_init has not been called";
+  return GBX_ERR_STATE;
+}
+
+template <typename T>
+int dev_alloc(gbx_sbm* h, T** p, size_t count) {
+  const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  GBX_CUDA_TRY(cudaMalloc((void**)p, bytes));
+  h->dev_bytes += (int64_t)bytes;
+  return GBX_OK;
+}
+
+int set_device(const gbx_sbm* h) {
+  GBX_CUDA_TRY(cudaSetDevice(h->device));
+  return GBX_OK;
+}
+
+int read_state(gbx_sbm* h) {
+  GBX_CUDA_TRY(cudaMemcpyAsync(h->h_state, h->st, sizeof(SbmState), cudaMemcpyDeviceToHost, h->stream));
+  GBX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return GBX_OK;
+}
+
+// One EM iteration, sbm.jl:343-347, with a synchronous sweep in place of BP().
+int em_iteration(gbx_sbm* h) {
+  const SbmOps* op = h->ops;
+  GBX_TRY(op->prepare(h, 0, 0));              // gr clamp, h = update_h()            sbm.jl:102
+  GBX_TRY(op->vertex_pass(h, MODE_SWEEP));    // messages, marginals, residual       sbm.jl:103-124
+  h->cur ^= 1;
+  GBX_TRY(op->reduce_vertex(h, MODE_SWEEP));
+  GBX_TRY(op->mstep(h));                      // Crs = update_Crs()                  sbm.jl:344
+  if (h->opt.degreecorrection) GBX_TRY(op->theta(h));  // theta = update_theta()     sbm.jl:345-347
+  h->itr++;
+  return GBX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gbx_version(void) { return 100; }
+
+const char* gbx_last_error(void) { return last_error().c_str(); }
+
+int gbx_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    last_error() = std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e);
+    return GBX_ERR_CUDA;
+  }
+  return n;
+}
+
+void gbx_sbm_default_options(gbx_sbm_options* opt) {
+  opt->degreecorrection = 1;
+  opt->priorlearning = 1;
+  opt->learningrate = 0.3;
+  opt->maxCrs = 0.0;
+  opt->itrmax = 256;
+  opt->bp_conv_threshold = 0.000001;
+  opt->damping = 1.0;
+  opt->check_every = 1;
+}
+
+int gbx_sbm_create(gbx_sbm** out, int device, int64_t n, int64_t K, const int64_t* links, int q) {
+  if (!out) return fail_invalid("out is NULL");
+  *out = nullptr;
+  if (q < 1 || q > MAXQ) return fail_invalid("q must be in 1..16");
+  const SbmOps* ops = ops_for(q);
+  if (!ops) return fail_invalid("this build of libgraphbix_cuda was compiled without that q");
+  if (n < 1 || K < 0 || (K > 0 && !links)) return fail_invalid("bad n_vertices / n_links / links");
+  if (n >= (int64_t)1 << 31 || K >= (int64_t)1 << 31) return fail_invalid("graph too large for 32-bit slots");
+  int ndev = gbx_device_count();
+  if (ndev < 0) return ndev;
+  if (ndev == 0) {
+    last_error() = "no CUDA device: libgraphbix_cuda has no CPU fallback";
+    return GBX_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) return fail_invalid("device out of range");
+
+  // ---- destination-major CSR on the host (counting sorts, O(K + N)) ----
+  const int64_t* src1 = links;
+  const int64_t* dst1 = links + K;
+  std::vector<int> rowptr((size_t)n + 1, 0);
+  for (int64_t k = 0; k < K; ++k) {
+    const int64_t s = src1[k], d = dst1[k];
+    if (s < 1 || s > n || d < 1 || d > n) return fail_invalid("links: vertex id out of 1..n");
+    if (s == d) return fail_invalid("links: self loop (run simplegraph first)");
+    rowptr[(size_t)d]++;
+  }
+  for (int64_t i = 0; i < n; ++i) rowptr[(size_t)i + 1] += rowptr[(size_t)i];
+  // pass 1: order links by source; pass 2: stable distribution by destination -> rows sorted by source
+  std::vector<int> by_src((size_t)K);
+  {
+    std::vector<int> cnt((size_t)n + 1, 0);
+    for (int64_t k = 0; k < K; ++k) cnt[(size_t)src1[k]]++;
+    for (int64_t i = 0; i < n; ++i) cnt[(size_t)i + 1] += cnt[(size_t)i];
+    for (int64_t k = 0; k < K; ++k) by_src[(size_t)cnt[(size_t)src1[k] - 1]++] = (int)k;
+  }
+  std::vector<int> col((size_t)K), slot_of_link((size_t)K), rev((size_t)K);
+  {
+    std::vector<int> fill(rowptr.begin(), rowptr.end() - 1);
+    for (int64_t p = 0; p < K; ++p) {
+      const int k = by_src[(size_t)p];
+      const int slot = fill[(size_t)dst1[k] - 1]++;
+      col[(size_t)slot] = (int)(src1[k] - 1);
+      slot_of_link[(size_t)k] = slot;
+    }
+  }
+  by_src.clear();
+  by_src.shrink_to_fit();
+  for (int64_t i = 0; i < n; ++i) {
+    for (int e = rowptr[(size_t)i]; e < rowptr[(size_t)i + 1]; ++e) {
+      if (e > rowptr[(size_t)i] && col[(size_t)e] == col[(size_t)e - 1])
+        return fail_invalid("links: duplicate link (run simplegraph first)");
+      const int j = col[(size_t)e];
+      const int* b = col.data() + rowptr[(size_t)j];
+      const int* en = col.data() + rowptr[(size_t)j + 1];
+      const int* it = std::lower_bound(b, en, (int)i);
+      if (it == en || *it != (int)i) return fail_invalid("links: reverse link missing (graph must be bidirected)");
+      rev[(size_t)e] = (int)(it - col.data());
+    }
+  }
+  // ---- tile schedule: runs of consecutive vertices with <= TILE_E slots and <= TV vertices; hubs apart ----
+  const int TV = tile_vertices(q);
+  std::vector<int2> tiles;
+  std::vector<int> hubs;
+  std::vector<unsigned char> lvtx((size_t)K, 0);
+  {
+    int64_t v = 0;
+    while (v < n) {
+      const int deg = rowptr[(size_t)v + 1] - rowptr[(size_t)v];
+      if (deg > TILE_E) {
+        hubs.push_back((int)v);
+        ++v;
+        continue;
+      }
+      int64_t w = v;
+      int ne = 0;
+      while (w < n && (w - v) < TV) {
+        const int d = rowptr[(size_t)w + 1] - rowptr[(size_t)w];
+        if (d > TILE_E || ne + d > TILE_E) break;
+        for (int e = rowptr[(size_t)w]; e < rowptr[(size_t)w + 1]; ++e) lvtx[(size_t)e] = (unsigned char)(w - v);
+        ne += d;
+        ++w;
+      }
+      tiles.push_back(make_int2((int)v, (int)w));
+      v = w;
+    }
+  }
+
+  gbx_sbm* h = new (std::nothrow) gbx_sbm();
+  if (!h) return fail_invalid("out of host memory");
+  h->device = device;
+  h->q = q;
+  h->n = n;
+  h->K = K;
+  h->ops = ops;
+  h->ntiles = (int)tiles.size();
+  h->nhubs = (int)hubs.size();
+  gbx_sbm_default_options(&h->opt);
+  auto body = [&]() -> int {
+    GBX_CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GBX_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+      last_error() = "libgraphbix_cuda is built for sm_100a (B200) only";
+      return GBX_ERR_CUDA;
+    }
+    h->num_sms = prop.multiProcessorCount;
+    GBX_TRY(dev_alloc(h, &h->rowptr, (size_t)n + 1));
+    GBX_TRY(dev_alloc(h, &h->col, (size_t)K));
+    GBX_TRY(dev_alloc(h, &h->rev, (size_t)K));
+    GBX_TRY(dev_alloc(h, &h->lvtx, (size_t)K));
+    GBX_TRY(dev_alloc(h, &h->slot_of_link, (size_t)K));
+    GBX_TRY(dev_alloc(h, &h->tiles, tiles.size()));
+    GBX_TRY(dev_alloc(h, &h->hubs, hubs.size()));
+    GBX_TRY(dev_alloc(h, &h->msg[0], (size_t)K * q));
+    GBX_TRY(dev_alloc(h, &h->msg[1], (size_t)K * q));
+    GBX_TRY(dev_alloc(h, &h->PSI, (size_t)n * q));
+    GBX_TRY(dev_alloc(h, &h->theta, (size_t)n));
+    GBX_TRY(dev_alloc(h, &h->st, 1));
+    GBX_TRY(dev_alloc(h, &h->params, 1));
+    GBX_CUDA_TRY(cudaMemcpy(h->rowptr, rowptr.data(), ((size_t)n + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    GBX_CUDA_TRY(cudaMemcpy(h->col, col.data(), (size_t)K * sizeof(int), cudaMemcpyHostToDevice));
+    GBX_CUDA_TRY(cudaMemcpy(h->rev, rev.data(), (size_t)K * sizeof(int), cudaMemcpyHostToDevice));
+    GBX_CUDA_TRY(cudaMemcpy(h->lvtx, lvtx.data(), (size_t)K, cudaMemcpyHostToDevice));
+    GBX_CUDA_TRY(cudaMemcpy(h->slot_of_link, slot_of_link.data(), (size_t)K * sizeof(int), cudaMemcpyHostToDevice));
+    GBX_CUDA_TRY(cudaMemcpy(h->tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    GBX_CUDA_TRY(cudaMemcpy(h->hubs, hubs.data(), hubs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    GBX_CUDA_TRY(cudaMemset(h->st, 0, sizeof(SbmState)));
+    GBX_CUDA_TRY(cudaMallocHost((void**)&h->h_state, sizeof(SbmState)));
+    // persistent grids: a whole number of CTAs per SM
+    int occ = 1, occm = 1;
+    GBX_TRY(ops->occupancy(&occ, &occm));
+    occ = std::max(occ, 1);
+    occm = std::max(occm, 1);
+    h->grid_vertex = std::max(1, std::min(h->ntiles, h->num_sms * occ));
+    const int64_t eblocks = std::max<int64_t>(1, (K + NT - 1) / NT);
+    h->grid_mstep = (int)std::min<int64_t>(eblocks, (int64_t)h->num_sms * occm);
+    h->grid_fe = (int)std::min<int64_t>(eblocks, (int64_t)h->num_sms * 2);
+    h->grid_theta = (int)std::min<int64_t>(std::max<int64_t>(1, (n + NT - 1) / NT), (int64_t)h->num_sms * 4);
+    GBX_TRY(dev_alloc(h, &h->part_vertex, (size_t)(h->grid_vertex + h->nhubs) * PSTRIDE));
+    GBX_TRY(dev_alloc(h, &h->part_mstep, (size_t)h->grid_mstep * MAXQ * MAXQ * 2));
+    GBX_TRY(dev_alloc(h, &h->part_theta, (size_t)h->grid_theta * MAXQ));
+    GBX_TRY(dev_alloc(h, &h->part_fe, (size_t)h->grid_fe * 4));
+    GBX_CUDA_TRY(cudaDeviceSynchronize());
+    return GBX_OK;
+  };
+  const int rc = body();
+  if (rc != GBX_OK) {
+    const std::string keep = last_error();
+    gbx_sbm_destroy(h);
+    last_error() = keep;
+    return rc;
+  }
+  *out = h;
+  return GBX_OK;
+}
+
+int gbx_sbm_destroy(gbx_sbm* h) {
+  if (!h) return GBX_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->rowptr);
+  cudaFree(h->col);
+  cudaFree(h->rev);
+  cudaFree(h->lvtx);
+  cudaFree(h->slot_of_link);
+  cudaFree(h->tiles);
+  cudaFree(h->hubs);
+  cudaFree(h->msg[0]);
+  cudaFree(h->msg[1]);
+  cudaFree(h->PSI);
+  cudaFree(h->theta);
+  cudaFree(h->st);
+  cudaFree(h->params);
+  cudaFree(h->part_vertex);
+  cudaFree(h->part_mstep);
+  cudaFree(h->part_theta);
+  cudaFree(h->part_fe);
+  if (h->h_state) cudaFreeHost(h->h_state);
+  delete h;
+  return GBX_OK;
+}
+
+int gbx_sbm_set_stream(gbx_sbm* h, void* s) {
+  if (!h) return fail_invalid("handle is NULL");
+  h->stream = (cudaStream_t)s;
+  return GBX_OK;
+}
+
+int gbx_sbm_set_options(gbx_sbm* h, const gbx_sbm_options* opt) {
+  if (!h || !opt) return fail_invalid("handle/options is NULL");
+  if (!(opt->damping > 0.0 && opt->damping <= 1.0)) return fail_invalid("damping must be in (0,1]");
+  if (!(opt->learningrate >= 0.0 && opt->learningrate <= 1.0)) return fail_invalid("learningrate must be in [0,1]");
+  if (opt->itrmax < 0) return fail_invalid("itrmax must be >= 0");
+  h->opt = *opt;
+  if (h->opt.check_every < 1) h->opt.check_every = 1;
+  return GBX_OK;
+}
+
+int gbx_sbm_init(gbx_sbm* h, const double* gr_init, const double* Crs_init, const double* psicav, uint64_t seed) {
+  if (!h || !Crs_init) return fail_invalid("handle/Crs_init is NULL");
+  if (h->opt.priorlearning && !gr_init) return fail_invalid("gr_init is NULL with priorlearning on");
+  GBX_TRY(set_device(h));
+  const int q = h->q;
+  SbmState s;
+  memset(&s, 0, sizeof s);
+  h->fail = 0;
+  for (int r = 0; r < q; ++r)
+    for (int t = 0; t < q; ++t) {
+      // sbm.jl:308-317; the matrix is symmetrised (every initial condition of the reference is symmetric)
+      double c = 0.5 * (Crs_init[r * q + t] + Crs_init[t * q + r]);
+      if (std::isnan(c) || std::isinf(c)) h->fail = 1;
+      else if (c < 1e-6) c = 1e-6;
+      s.C[r * q + t] = c;
+    }
+  for (int r = 0; r < q; ++r) s.gr[r] = h->opt.priorlearning ? gr_init[r] : 1.0 / q;  // sbm.jl:304-306
+  GBX_CUDA_TRY(cudaMemcpyAsync(h->st, &s, sizeof s, cudaMemcpyHostToDevice, h->stream));
+  GBX_CUDA_TRY(cudaStreamSynchronize(h->stream));  // `s` is a stack object
+  h->cur = 0;
+  h->itr = 0;
+  if (psicav) {
+    double* tmp = h->msg[1];
+    GBX_CUDA_TRY(cudaMemcpyAsync(tmp, psicav, (size_t)h->K * q * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    GBX_TRY(h->ops->permute(h, tmp, h->msg[0], 1));
+  } else {
+    GBX_TRY(h->ops->random_messages(h, seed));
+  }
+  {
+    std::vector<double> ones((size_t)h->n, 1.0);  // theta = ones(Ntot,1), sbm.jl:277
+    GBX_CUDA_TRY(cudaMemcpyAsync(h->theta, ones.data(), (size_t)h->n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    GBX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
+  if (!h->fail) {
+    // PSI = updatePSI() with h = 0, then gr = update_gr(PSI): sbm.jl:340-341
+    GBX_TRY(h->ops->prepare(h, 1, 0));
+    GBX_TRY(h->ops->vertex_pass(h, MODE_MARGINAL));
+    GBX_TRY(h->ops->reduce_vertex(h, MODE_MARGINAL));
+  }
+  GBX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->initialised = true;
+  return GBX_OK;
+}
+
+int gbx_sbm_iterate(gbx_sbm* h, int n_iters, double* bpconv_out) {
+  if (!h) return fail_invalid("handle is NULL");
+  if (!h->initialised) return fail_state();
+  GBX_TRY(set_device(h));
+  for (int i = 0; i < n_iters; ++i) GBX_TRY(em_iteration(h));
+  if (bpconv_out) {
+    GBX_TRY(read_state(h));
+    *bpconv_out = h->h_state->conv;
+  }
+  return GBX_OK;
+}
+
+int gbx_sbm_bp_sweeps(gbx_sbm* h, int n_sweeps) {
+  if (!h) return fail_invalid("handle is NULL");
+  if (!h->initialised) return fail_state();
+  GBX_TRY(set_device(h));
+  GBX_TRY(h->ops->prepare(h, 0, 0));
+  for (int i = 0; i < n_sweeps; ++i) {
+    GBX_TRY(h->ops->vertex_pass(h, MODE_SWEEP));
+    h->cur ^= 1;
+  }
+  GBX_TRY(h->ops->reduce_vertex(h, MODE_SWEEP));
+  return GBX_OK;
+}
+
+int gbx_sbm_finalize(gbx_sbm* h, gbx_sbm_result* res) {
+  if (!h || !res) return fail_invalid("handle/result is NULL");
+  if (!h->initialised) return fail_state();
+  GBX_TRY(set_device(h));
+  memset(res, 0, sizeof *res);
+  res->fail = h->fail;
+  if (!h->fail) {
+    GBX_TRY(h->ops->prepare(h, 0, 1));  // h = update_h(); gr = update_gr(PSI)   sbm.jl:364-365
+    GBX_TRY(h->ops->free_energy(h));    // freeenergy()                          sbm.jl:366
+  }
+  GBX_TRY(read_state(h));
+  const SbmState* s = h->h_state;
+  res->FE = s->result[0];
+  res->CVBayes = s->result[1];
+  res->CVGP = s->result[2];
+  res->CVGT = s->result[3];
+  res->CVMAP = s->result[4];
+  res->varCVBayes = s->result[5];
+  res->varCVGP = s->result[6];
+  res->varCVGT = s->result[7];
+  res->varCVMAP = s->result[8];
+  res->BPconv = s->conv;
+  res->max_dpsi = s->maxd;
+  res->nonfinite = s->status & 1;
+  res->itrs_done = h->itr;
+  return GBX_OK;
+}
+
+int gbx_sbm_em(gbx_sbm* h, gbx_sbm_result* res) {
+  if (!h || !res) return fail_invalid("handle/result is NULL");
+  if (!h->initialised) return fail_state();
+  GBX_TRY(set_device(h));
+  int cnv = 0, itrnum = 0;
+  if (!h->fail) {
+    for (int itr = 1; itr <= h->opt.itrmax; ++itr) {
+      GBX_TRY(em_iteration(h));
+      if (itr % h->opt.check_every == 0 || itr == h->opt.itrmax) {
+        GBX_TRY(read_state(h));
+        if (h->h_state->conv < h->opt.bp_conv_threshold) {  // sbm.jl:348-353
+          cnv = 1;
+          itrnum = itr;
+          break;
+        }
+      }
+    }
+  }
+  GBX_TRY(gbx_sbm_finalize(h, res));
+  res->cnv = cnv;
+  res->itrnum = itrnum;
+  return GBX_OK;
+}
+
+int gbx_sbm_get_state(gbx_sbm* h, double* gr, double* Crs, double* PSI, double* theta, double* hfield) {
+  if (!h) return fail_invalid("handle is NULL");
+  GBX_TRY(set_device(h));
+  GBX_TRY(read_state(h));
+  const int q = h->q;
+  if (gr) memcpy(gr, h->h_state->gr, q * sizeof(double));
+  if (Crs) memcpy(Crs, h->h_state->C, (size_t)q * q * sizeof(double));
+  if (hfield) memcpy(hfield, h->h_state->h, q * sizeof(double));
+  if (PSI) GBX_CUDA_TRY(cudaMemcpyAsync(PSI, h->PSI, (size_t)h->n * q * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (theta) GBX_CUDA_TRY(cudaMemcpyAsync(theta, h->theta, (size_t)h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  GBX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return GBX_OK;
+}
+
+int gbx_sbm_get_messages(gbx_sbm* h, double* psicav) {
+  if (!h || !psicav) return fail_invalid("handle/psicav is NULL");
+  GBX_TRY(set_device(h));
+  double* tmp = h->msg[h->cur ^ 1];  // the other buffer is scratch between sweeps
+  GBX_TRY(h->ops->permute(h, h->msg[h->cur], tmp, 0));
+  GBX_CUDA_TRY(cudaMemcpyAsync(psicav, tmp, (size_t)h->K * h->q * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  GBX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return GBX_OK;
+}
+
+int gbx_sbm_get_assignment(gbx_sbm* h, int32_t* block) {
+  if (!h || !block) return fail_invalid("handle/block is NULL");
+  GBX_TRY(set_device(h));
+  int* d = nullptr;
+  GBX_CUDA_TRY(cudaMalloc((void**)&d, (size_t)h->n * sizeof(int)));
+  int rc = h->ops->assignment(h, d);
+  cudaError_t e = cudaSuccess;
+  if (rc == GBX_OK) {
+    e = cudaMemcpyAsync(block, d, (size_t)h->n * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  }
+  cudaFree(d);
+  if (rc != GBX_OK) return rc;
+  GBX_CUDA_TRY(e);
+  return GBX_OK;
+}
+
+int64_t gbx_sbm_launch_count(const gbx_sbm* h) { return h ? h->launches : 0; }
+int64_t gbx_sbm_num_links(const gbx_sbm* h) { return h ? h->K : 0; }
+int64_t gbx_sbm_device_bytes(const gbx_sbm* h) { return h ? h->dev_bytes : 0; }
+
+double gbx_sbm_sweep_bytes(const gbx_sbm* h) {
+  if (!h) return 0.0;
+  const double q = h->q, K = (double)h->K, n = (double)h->n;
+  double per_edge = 2.0 * q * 8.0 + 4.0 + 1.0;         // message in, message out, rev, tile-local vertex id
+  if (h->opt.degreecorrection) per_edge += 4.0 + 8.0;  // col + theta of the neighbour
+  if (h->opt.damping != 1.0) per_edge += q * 8.0;      // old outgoing message
+  double per_vertex = 2.0 * q * 8.0 + 4.0;             // PSI read + write, rowptr
+  if (h->opt.degreecorrection) per_vertex += 8.0;
+  return K * per_edge + n * per_vertex;
+}
+
+}  // extern "C"

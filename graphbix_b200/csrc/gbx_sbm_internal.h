@@ -1,0 +1,87 @@
+// Internal: the host-side handle behind `gbx_sbm*` and the per-q launcher table.
+// One translation unit per q (gbx_sbm_q.cu, -DGBX_Q=<q>) fills a table; gbx_sbm_host.cu dispatches.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/graphbix_cuda.h"
+#include "gbx_common.cuh"
+
+namespace gbx {
+
+// Parameters every edge/vertex kernel reads; refreshed once per EM iteration (device -> __constant__).
+struct SbmParams {
+  double C[MAXQ * MAXQ];     // Crs, row-major with stride q
+  double logC[MAXQ * MAXQ];  // log(Crs)
+  double lgr[MAXQ];          // log(gr) after the clamp of sbm.jl:89-96
+  double h[MAXQ];            // external field, sbm.jl:70-73
+  double logN;
+};
+
+// Device-resident EM state (small; one per handle).
+struct SbmState {
+  double gr[MAXQ];
+  double C[MAXQ * MAXQ];
+  double h[MAXQ];
+  double sumPSI[MAXQ];   // sum_i PSI_i of the marginals currently in PSI
+  double Stheta[MAXQ];   // sum_i theta_i PSI_i
+  double drmean[MAXQ];   // mean degree of each MAP block (update_theta, sbm.jl:47-58)
+  double conv, maxd, sumlogZi;
+  double cvsum[4], cvmean[4], cvss[4];
+  double result[12];
+  int status;  // bit 0: non-finite / non-positive value met in a kernel
+};
+
+constexpr int PSTRIDE = 3 * MAXQ + 4;  // per-CTA partial row of the vertex kernels
+enum { MODE_SWEEP = 0, MODE_MARGINAL = 1, MODE_LOGZ = 2 };
+
+constexpr int tile_vertices(int q) { return (q <= 8) ? TILE_V : TILE_V / 2; }
+
+struct SbmOps;
+
+}  // namespace gbx
+
+struct gbx_sbm {
+  int device = 0, q = 0;
+  int64_t n = 0, K = 0;
+  cudaStream_t stream = nullptr;
+  gbx_sbm_options opt{};
+  bool initialised = false;
+  int fail = 0;
+  int64_t launches = 0, dev_bytes = 0;
+  int num_sms = 148;
+  const gbx::SbmOps* ops = nullptr;
+  // graph (device)
+  int *rowptr = nullptr, *col = nullptr, *rev = nullptr, *slot_of_link = nullptr, *hubs = nullptr;
+  unsigned char* lvtx = nullptr;  // per edge slot: index of its vertex inside its tile
+  int2* tiles = nullptr;
+  int ntiles = 0, nhubs = 0;
+  // state (device)
+  double *msg[2] = {nullptr, nullptr}, *PSI = nullptr, *theta = nullptr;
+  int cur = 0;
+  gbx::SbmState* st = nullptr;
+  gbx::SbmParams* params = nullptr;
+  double *part_vertex = nullptr, *part_mstep = nullptr, *part_theta = nullptr, *part_fe = nullptr;
+  int grid_vertex = 0, grid_mstep = 0, grid_theta = 0, grid_fe = 0;
+  gbx::SbmState* h_state = nullptr;  // pinned mirror
+  int itr = 0;
+};
+
+namespace gbx {
+
+// Launchers of one compiled q.  Each returns GBX_OK or an error code and bumps h->launches.
+struct SbmOps {
+  int q;
+  int (*vertex_pass)(gbx_sbm* h, int mode);
+  int (*reduce_vertex)(gbx_sbm* h, int mode);
+  int (*prepare)(gbx_sbm* h, int zero_h, int gr_from_sum);
+  int (*mstep)(gbx_sbm* h);
+  int (*theta)(gbx_sbm* h);
+  int (*free_energy)(gbx_sbm* h);
+  int (*permute)(gbx_sbm* h, const double* src, double* dst, int to_slots);
+  int (*random_messages)(gbx_sbm* h, uint64_t seed);
+  int (*assignment)(gbx_sbm* h, int* dev_block);
+  int (*occupancy)(int* vertex_occ, int* mstep_occ);
+};
+
+}  // namespace gbx

@@ -1,0 +1,956 @@
+// Kernels of the full-affinity SBM path (sbm.jl EM()) for ONE compile-time number of groups Q = GBX_Q.
+// The build compiles this file once per q in 1..16 (see build.py) so the q x q contraction is fully
+// unrolled with the affinity matrix as uniform-register operands from __constant__ memory.
+//
+// Kernel map (reference lines each one replaces):
+//   sbm_vertex_kernel<MODE>  BP sweep over tiled vertices           sbm.jl:83-126 (BP, logunnormalizedMessage)
+//   sbm_hub_kernel<MODE>     the same for vertices of degree > 256
+//   sbm_reduce_vertex        residual, gr update, block degree means sbm.jl:120-123, 47-58
+//   sbm_mstep_kernel         per-edge joint marginals -> Crsnew      sbm.jl:128-136
+//   sbm_reduce_mstep         Crs update + clamp                      sbm.jl:137-147
+//   sbm_theta_kernel         update_theta, S_theta for update_h      sbm.jl:47-64, 70-73
+//   sbm_prepare              gr clamp, h, logs -> __constant__       sbm.jl:89-96, 70-73
+//   sbm_fe_kernel<PASS>      log Z_ij, CV errors per edge            sbm.jl:162-200
+//   sbm_finalize             FE, CV errors, variances                sbm.jl:201-212
+#ifndef GBX_Q
+#error "compile with -DGBX_Q=<number of groups>"
+#endif
+#include "gbx_sbm_internal.h"
+
+namespace gbx {
+namespace {
+
+constexpr int Q = GBX_Q;
+constexpr int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+constexpr int QP = next_pow2(Q);     // lanes per component group (padding lanes idle when Q is not 2^k)
+constexpr int LV = 2 * QP;           // lanes per vertex in the aggregation stage: 2 edge-parities x QP
+constexpr int TV = tile_vertices(Q);
+constexpr int VPR = NT / LV;         // vertices per aggregation round
+
+constexpr double LOG_1EM8 = -18.420680743952367;  // log(10^(-8.0)), sbm.jl:42
+constexpr double INV_LN2 = 1.4426950408889634;
+constexpr double LN2 = 0.6931471805599453;
+constexpr double EXP_M500 = 7.124576406741286e-218;  // e^-500, sbm.jl:33-35
+
+__constant__ SbmParams c_P;
+
+struct VertexArgs {
+  const int* rowptr;
+  const int* col;
+  const int* rev;
+  const unsigned char* lvtx;
+  const int2* tiles;  // [ntiles] (first vertex, one past last vertex)
+  int ntiles;
+  const int* hubs;    // vertex ids with degree > TILE_E
+  const double* theta;
+  const double* cur;
+  double* nxt;
+  double* PSI;
+  double* partials;   // [(grid + nhubs)][PSTRIDE]
+  int* status;
+  double damping;
+  int dc;
+};
+
+// ---- small device helpers ---------------------------------------------------------------------
+// 2^n with saturation: 0 below the normal range, +inf above.
+__device__ __forceinline__ double pow2c(int n) {
+  if (n < -1022) return 0.0;
+  if (n > 1023) return INFINITY;
+  return pow2i(n);
+}
+// 1/x for positive normal x to ~1 ulp: MUFU.RCP64H seed + two Newton steps (no special cases needed here).
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ T group_max(T x) {
+#pragma unroll
+  for (int o = QP / 2; o > 0; o >>= 1) {
+    const T y = __shfl_xor_sync(0xffffffffu, x, o);
+    x = (y > x) ? y : x;
+  }
+  return x;
+}
+template <typename T>
+__device__ __forceinline__ T group_min(T x) {
+#pragma unroll
+  for (int o = QP / 2; o > 0; o >>= 1) {
+    const T y = __shfl_xor_sync(0xffffffffu, x, o);
+    x = (y < x) ? y : x;
+  }
+  return x;
+}
+__device__ __forceinline__ double group_sum(double x) {
+#pragma unroll
+  for (int o = QP / 2; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+// T[t] = theta_i theta_s (psi * Crs)[t]  (sbm.jl:87), rescaled by 2^-ke so that max_t T[t] is in [1,2).
+__device__ __forceinline__ void edge_transform(const double (&psi)[Q], double sc, double (&T)[Q], int& ke,
+                                               int* status) {
+  double m = 0.0;
+  bool allpos = true;
+#pragma unroll
+  for (int t = 0; t < Q; ++t) {
+    double acc = 0.0;
+#pragma unroll
+    for (int s = 0; s < Q; ++s) acc = fma(psi[s], c_P.C[s * Q + t], acc);
+    T[t] = acc * sc;
+    m = (T[t] > m) ? T[t] : m;
+    allpos = allpos && (T[t] > 0.0);  // false for NaN as well
+  }
+  bool ok;
+  ke = exponent_of(m, ok);
+  if (ok && allpos) {
+    const double s2 = pow2i(-ke);
+#pragma unroll
+    for (int t = 0; t < Q; ++t) T[t] *= s2;
+  } else {
+    ke = 0;
+    atomicOr(status, 1);
+#pragma unroll
+    for (int t = 0; t < Q; ++t) T[t] = __longlong_as_double(0x7ff8000000000000LL);  // log(<=0) in the reference
+  }
+}
+
+// Cavity message i -> j (sbm.jl:108-109) from the vertex product u and this edge's factor T, the absolute
+// clamp of normalize_logprob (sbm.jl:42) at 2^(ffrac + n) in the scaled domain, damping, scatter to rev slot.
+__device__ __forceinline__ void emit_message(const VertexArgs& a, const double* __restrict__ u, const double (&T)[Q],
+                                             double ffrac, int n, int rv) {
+  double w[Q];
+  double S = 0.0, cmin = INFINITY;
+#pragma unroll
+  for (int t = 0; t < Q; ++t) {
+    w[t] = u[t] * fast_rcp(T[t]);
+    S += w[t];
+    cmin = (w[t] < cmin) ? w[t] : cmin;
+  }
+  if (cmin < pow2c(n + 1)) {  // rare: some component is at or below the clamp floor
+    const double fl = scale2(exp2(ffrac), n);
+    S = 0.0;
+#pragma unroll
+    for (int t = 0; t < Q; ++t) {
+      w[t] = (w[t] < fl) ? fl : w[t];
+      S += w[t];
+    }
+  }
+  const double inv = 1.0 / S;
+#pragma unroll
+  for (int t = 0; t < Q; ++t) w[t] *= inv;
+  if (a.damping != 1.0) {
+    double old[Q];
+    load_vec<Q>(a.cur, rv, old);
+    const double al = a.damping, be = 1.0 - a.damping;
+#pragma unroll
+    for (int t = 0; t < Q; ++t) w[t] = be * old[t] + al * w[t];
+  }
+  store_vec<Q>(a.nxt, rv, w);
+}
+
+// Per-thread accumulators of the aggregation lanes.
+struct LaneAcc {
+  double psi = 0.0;   // sum of PSI_i(t) for this lane's component t (parity-0 lanes)
+  double res = 0.0;   // sum of per-vertex L1 changes (lane t = 0, parity 0)
+  double logz = 0.0;  // sum of log Z_i
+  double vmax = 0.0;  // max per-vertex L1 change
+};
+
+// Everything a vertex needs once lane t holds prod_t = product of its scaled edge factors and K = their exponents.
+//   true unnormalised value v_t = u_t 2^K e^xmax;  the clamp floor of sbm.jl:42 in the scaled domain is 2^f.
+// Runs on the QP lanes of a group (all lanes of the warp execute it; `valid` gates the side effects).
+template <int MODE>
+__device__ __forceinline__ void vertex_finish(const VertexArgs& a, bool valid, bool writer, int gv, int deg, int t,
+                                              double prod, int K, double& u_out, double& ffrac, int& fn,
+                                              LaneAcc& acc, double* s_dr, double* s_nr) {
+  const bool tl = t < Q;
+  const double th = (a.dc && valid) ? a.theta[gv] : 1.0;
+  const double x = tl ? (c_P.lgr[tl ? t : 0] - th * c_P.h[tl ? t : 0]) : -INFINITY;
+  const double xmax = group_max(x);
+  const double u = tl ? exp(x - xmax) * prod : 0.0;
+  u_out = u;
+  const double f = (LOG_1EM8 - xmax) * INV_LN2 - (double)K;
+  const double fi = floor(f);
+  ffrac = f - fi;
+  fn = (fi < -4000.0) ? -4000 : ((fi > 4000.0) ? 4000 : (int)fi);
+  if constexpr (MODE == MODE_LOGZ) {
+    // logsumexp(logunnormalizedMessage(i)), sbm.jl:153, with the 500 cut-off of sbm.jl:33-35
+    const double umax = group_max(u);
+    const double cut = umax * EXP_M500;
+    const double s = group_sum(tl ? ((u < cut) ? cut : u) : 0.0);
+    if (valid && writer && t == 0) {
+      acc.logz += log(s) + (double)K * LN2 + xmax;
+      if (!(s > 0.0)) atomicOr(a.status, 1);
+    }
+  } else {
+    double w = u;
+    const double umin = group_min(tl ? u : INFINITY);
+    if (umin < pow2c(fn + 1)) {  // rare
+      const double fl = scale2(exp2(ffrac), fn);
+      w = (u < fl) ? fl : u;
+    }
+    const double S = group_sum(tl ? w : 0.0);
+    const double p = w * (1.0 / S);
+    double r = 0.0;
+    if constexpr (MODE == MODE_SWEEP) {
+      const double old = (valid && tl) ? a.PSI[(size_t)gv * Q + t] : p;
+      r = fabs(p - old);
+    }
+    const double res = group_sum(tl ? r : 0.0);
+    const double pm = group_max(tl ? p : -1.0);
+    const int best = group_min((tl && p == pm) ? t : QP);  // findmax: first maximum (sbm.jl:49)
+    if (valid && writer) {
+      if (tl) {
+        a.PSI[(size_t)gv * Q + t] = p;
+        acc.psi += p;
+      }
+      if (t == 0) {
+        acc.res += res;
+        acc.vmax = fmax(acc.vmax, res);
+        if (!(S > 0.0)) atomicOr(a.status, 1);
+        if (best < Q) {
+          atomicAdd(&s_dr[best], (double)deg);  // integer-valued: exact in any order
+          atomicAdd(&s_nr[best], 1.0);
+        }
+      }
+    }
+  }
+}
+
+// Deterministic CTA reduction of the lane accumulators into this CTA's partial row.
+__device__ __forceinline__ void store_partials(const LaneAcc& acc, double* scratch /* smem, NT doubles */,
+                                               double* prow, const double* s_dr, const double* s_nr) {
+  const int tid = threadIdx.x;
+  // sumPSI[t]: parity-0 lanes with component t, in thread order
+  __syncthreads();
+  scratch[tid] = acc.psi;
+  __syncthreads();
+  if (tid < Q) {
+    double s = 0.0;
+    for (int k = tid; k < NT; k += LV) s += scratch[k];
+    prow[2 + tid] = s;
+  }
+  __syncthreads();
+  scratch[tid] = acc.res;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int k = 0; k < NT; k += LV) s += scratch[k];
+    prow[0] = s;
+  }
+  __syncthreads();
+  scratch[tid] = acc.logz;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int k = 0; k < NT; k += LV) s += scratch[k];
+    prow[1] = s;
+  }
+  __syncthreads();
+  scratch[tid] = acc.vmax;
+  __syncthreads();
+  if (tid == 0) {
+    double m = 0.0;
+    for (int k = 0; k < NT; k += LV) m = fmax(m, scratch[k]);
+    prow[2 + 3 * Q] = m;
+  }
+  if (tid < Q) {
+    prow[2 + Q + tid] = s_dr[tid];
+    prow[2 + 2 * Q + tid] = s_nr[tid];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BP sweep over the tiled (degree <= 256) vertices.
+//   stage 1  one thread per incoming edge slot: load the 8Q-byte message, T = theta theta psi*Crs, rescale
+//   stage 2  2*QP lanes per vertex: product of the T's (two edge-parities in parallel), prior, clamp floor,
+//            marginal, residual
+//   stage 3  one thread per edge slot: cavity = product / own factor, clamp, normalise, damp, scatter to rev[e]
+template <int MODE>
+__global__ void __launch_bounds__(NT, (Q <= 8) ? 3 : 2) sbm_vertex_kernel(VertexArgs a) {
+  __shared__ __align__(32) double Tsm[TILE_E * Q];
+  __shared__ __align__(32) double Usm[TV * Q];
+  __shared__ double ffS[TV];
+  __shared__ double scratch[NT];
+  __shared__ double s_dr[Q], s_nr[Q];
+  __shared__ int ksm[TILE_E];
+  __shared__ int fnS[TV];
+
+  const int tid = threadIdx.x;
+  if (tid < Q) {
+    s_dr[tid] = 0.0;
+    s_nr[tid] = 0.0;
+  }
+  LaneAcc acc;
+  const int sub = tid % LV, par = sub / QP, t = sub % QP;
+  const bool tl = t < Q;
+
+  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    const int2 tv = a.tiles[tile];
+    const int v0 = tv.x, nv = tv.y - tv.x;
+    const int e0 = a.rowptr[v0];
+    const int ne = a.rowptr[v0 + nv] - e0;
+
+    // ---- stage 1 ----
+    double T[Q];
+    int ke = 0, lv = 0, rv = 0;
+    if (tid < ne) {
+      const int e = e0 + tid;
+      double psi[Q];
+      load_vec<Q>(a.cur, e, psi);
+      lv = a.lvtx[e];
+      if constexpr (MODE == MODE_SWEEP) rv = a.rev[e];
+      double sc = 1.0;
+      if (a.dc) sc = a.theta[v0 + lv] * a.theta[a.col[e]];
+      edge_transform(psi, sc, T, ke, a.status);
+#pragma unroll
+      for (int k = 0; k < Q; ++k) Tsm[tid * Q + k] = T[k];
+      ksm[tid] = ke;
+    }
+    __syncthreads();
+
+    // ---- stage 2 ----
+    for (int vb = 0; vb < nv; vb += VPR) {
+      const int v = vb + tid / LV;
+      const bool valid = v < nv;
+      int b = 0, e = 0;
+      if (valid) {
+        b = a.rowptr[v0 + v] - e0;
+        e = a.rowptr[v0 + v + 1] - e0;
+      }
+      double prod = 1.0, prod2 = 1.0;
+      int K = 0;
+      const int tt = tl ? t : 0;
+      int k = b + par;
+      for (; k + 2 < e; k += 4) {  // two independent chains per lane
+        prod *= Tsm[k * Q + tt];
+        prod2 *= Tsm[(k + 2) * Q + tt];
+        K += ksm[k] + ksm[k + 2];
+      }
+      if (k < e) {
+        prod *= Tsm[k * Q + tt];
+        K += ksm[k];
+      }
+      prod *= prod2;
+      prod *= __shfl_xor_sync(0xffffffffu, prod, QP);  // the other edge-parity
+      K += __shfl_xor_sync(0xffffffffu, K, QP);
+      double u, ffrac;
+      int fn;
+      vertex_finish<MODE>(a, valid, par == 0, v0 + v, e - b, t, prod, K, u, ffrac, fn, acc, s_dr, s_nr);
+      if constexpr (MODE == MODE_SWEEP) {
+        if (valid && par == 0) {
+          if (tl) Usm[v * Q + t] = u;
+          if (t == 0) {
+            ffS[v] = ffrac;
+            fnS[v] = fn;
+          }
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- stage 3 ----
+    if constexpr (MODE == MODE_SWEEP) {
+      if (tid < ne) emit_message(a, &Usm[lv * Q], T, ffS[lv], fnS[lv] + ke, rv);
+    }
+  }
+  store_partials(acc, scratch, a.partials + (size_t)blockIdx.x * PSTRIDE, s_dr, s_nr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Hubs (degree > 256): one CTA per vertex, two passes over its incoming messages; the per-component
+// product is carried as (mantissa in [1,2), exponent) so any degree is safe.
+__device__ __forceinline__ void renorm(double& m, int& k) {
+  bool ok;
+  const int ex = exponent_of(m, ok);
+  if (ok) {
+    m *= pow2i(-ex);
+    k += ex;
+  } else if (m == m) {
+    m = 0.0;  // underflow: the component is negligible from here on (NaN stays NaN)
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base) {
+  __shared__ double pmS[(NT / 32) * Q];
+  __shared__ int pkS[(NT / 32) * Q];
+  __shared__ int ksS[NT / 32];
+  __shared__ double Ush[Q];
+  __shared__ double scratch[NT];
+  __shared__ double ffSh;
+  __shared__ int fnSh;
+  __shared__ double s_dr[Q], s_nr[Q];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gv = a.hubs[blockIdx.x];
+  const int e0 = a.rowptr[gv], e1 = a.rowptr[gv + 1];
+  const double th = a.dc ? a.theta[gv] : 1.0;
+  if (tid < Q) {
+    s_dr[tid] = 0.0;
+    s_nr[tid] = 0.0;
+  }
+
+  double pm[Q];
+  int pk[Q];
+#pragma unroll
+  for (int t = 0; t < Q; ++t) {
+    pm[t] = 1.0;
+    pk[t] = 0;
+  }
+  int ksum = 0;
+  for (int e = e0 + tid; e < e1; e += NT) {
+    double psi[Q], T[Q];
+    int ke;
+    load_vec<Q>(a.cur, e, psi);
+    const double sc = a.dc ? th * a.theta[a.col[e]] : 1.0;
+    edge_transform(psi, sc, T, ke, a.status);
+    ksum += ke;
+#pragma unroll
+    for (int t = 0; t < Q; ++t) {
+      pm[t] *= T[t];
+      renorm(pm[t], pk[t]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ksum += __shfl_xor_sync(0xffffffffu, ksum, o);
+#pragma unroll
+    for (int t = 0; t < Q; ++t) {
+      const double m2 = __shfl_xor_sync(0xffffffffu, pm[t], o);
+      const int k2 = __shfl_xor_sync(0xffffffffu, pk[t], o);
+      pm[t] *= m2;
+      pk[t] += k2;
+      renorm(pm[t], pk[t]);
+    }
+  }
+  if (lane == 0) {
+    ksS[warp] = ksum;
+#pragma unroll
+    for (int t = 0; t < Q; ++t) {
+      pmS[warp * Q + t] = pm[t];
+      pkS[warp * Q + t] = pk[t];
+    }
+  }
+  __syncthreads();
+
+  // warp 0 finishes the vertex: lane t < QP holds component t (same code path as the tiled kernel)
+  LaneAcc acc;
+  if (warp == 0) {
+    const int t = lane % QP;
+    const bool tl = t < Q;
+    int Ks = 0;
+    for (int w = 0; w < NT / 32; ++w) Ks += ksS[w];
+    double m = 1.0;
+    int k = 0;
+    for (int w = 0; w < NT / 32; ++w) {
+      m *= pmS[w * Q + (tl ? t : 0)];
+      k += pkS[w * Q + (tl ? t : 0)];
+      renorm(m, k);
+    }
+    const int kc = group_max((tl && m != 0.0) ? k : -(1 << 30));
+    const int kcc = (kc == -(1 << 30)) ? 0 : kc;
+    const int d = k - kcc;  // <= 0 for live components
+    const double prod = (d < -1022 || m == 0.0) ? 0.0 : m * pow2i(d > 0 ? 0 : d);
+    double u, ffrac;
+    int fn;
+    vertex_finish<MODE>(a, true, lane < QP, gv, e1 - e0, t, prod, Ks + kcc, u, ffrac, fn, acc, s_dr, s_nr);
+    if (lane < QP) {
+      if (tl) Ush[t] = u;
+      if (t == 0) {
+        ffSh = ffrac;
+        fnSh = fn;
+      }
+    }
+  }
+  __syncthreads();
+
+  if constexpr (MODE == MODE_SWEEP) {
+    for (int e = e0 + tid; e < e1; e += NT) {
+      double psi[Q], T[Q];
+      int ke;
+      load_vec<Q>(a.cur, e, psi);
+      const double sc = a.dc ? th * a.theta[a.col[e]] : 1.0;
+      edge_transform(psi, sc, T, ke, a.status);
+      emit_message(a, Ush, T, ffSh, fnSh + ke, a.rev[e]);
+    }
+  }
+  // lanes 0..QP-1 of warp 0 carry the accumulators; all other threads hold zeros
+  store_partials(acc, scratch, a.partials + (size_t)(part_base + blockIdx.x) * PSTRIDE, s_dr, s_nr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fixed-order reduction of the vertex partials, then the scalar bookkeeping of one sweep.
+__global__ void sbm_reduce_vertex(SbmState* st, const double* partials, int nrows, int mode, int prior, int dc,
+                                  double N) {
+  __shared__ double tot[PSTRIDE];
+  const int tid = threadIdx.x;
+  if (tid < 3 * Q + 3) {
+    double s = 0.0;
+    if (tid == 2 + 3 * Q) {
+      for (int r = 0; r < nrows; ++r) s = fmax(s, partials[(size_t)r * PSTRIDE + tid]);
+    } else {
+      for (int r = 0; r < nrows; ++r) s += partials[(size_t)r * PSTRIDE + tid];
+    }
+    tot[tid] = s;
+  }
+  __syncthreads();
+  if (mode == MODE_LOGZ) {
+    if (tid == 0) st->sumlogZi = tot[1];
+    return;
+  }
+  if (tid < Q) {
+    const double snew = tot[2 + tid];
+    if (mode == MODE_MARGINAL) {
+      st->gr[tid] = snew / N;                                  // gr = update_gr(PSI), sbm.jl:341
+      st->Stheta[tid] = snew;                                  // theta = 1 (sbm.jl:277)
+    } else {
+      if (prior) st->gr[tid] += (snew - st->sumPSI[tid]) / N;  // sbm.jl:120-122 summed over the sweep
+      if (!dc) st->Stheta[tid] = snew;
+    }
+    st->sumPSI[tid] = snew;
+    st->drmean[tid] = tot[2 + Q + tid] / tot[2 + 2 * Q + tid];  // sbm.jl:54-58 (NaN for an empty block, unused)
+  }
+  if (tid == 0 && mode == MODE_SWEEP) {
+    st->conv = tot[0] / N;  // sbm.jl:123
+    st->maxd = tot[2 + 3 * Q];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// M-step statistics, update_Crs() sbm.jl:128-136.  One thread per undirected edge (slot e with rev[e] < e).
+// H[s][t] (s <= t) = sum over undirected edges of (a_s b_t + a_t b_s) / Z, with a = psi_{i->j}, b = psi_{j->i},
+// Z = sum_st a_s Crs_st b_t.  Summed over both directions of every link (sbm.jl:130-136) and with Crs symmetric,
+// Crsnew = Crs .* H  (H_ss = 2 G_ss).  The upper triangle is held in registers; wide q take several passes.
+constexpr int mstep_rows(int q) {
+  int R = q;
+  while (R > 1 && R * q - R * (R - 1) / 2 > 64) --R;
+  return R;
+}
+constexpr int MS_R = mstep_rows(Q);
+constexpr int MS_NCH = (Q + MS_R - 1) / MS_R;
+constexpr int MS_STRIDE = MS_NCH * MS_R * Q;
+
+__global__ void __launch_bounds__(NT) sbm_mstep_kernel(const int* __restrict__ rev, long long K,
+                                                       const double* __restrict__ psi, double* partials,
+                                                       int* status) {
+  __shared__ double red[(NT / 32) * MS_R * Q];
+  const long long stride = (long long)gridDim.x * NT;
+#pragma unroll
+  for (int ch = 0; ch < MS_NCH; ++ch) {
+    double acc[MS_R * Q];
+#pragma unroll
+    for (int k = 0; k < MS_R * Q; ++k) acc[k] = 0.0;
+    for (long long e = (long long)blockIdx.x * NT + threadIdx.x; e < K; e += stride) {
+      const int r = rev[e];
+      if (r < e) {
+        double a[Q], b[Q];
+        load_vec<Q>(psi, e, b);  // col -> row
+        load_vec<Q>(psi, r, a);  // row -> col
+        double Z = 0.0;
+#pragma unroll
+        for (int s = 0; s < Q; ++s) {
+          double cb = 0.0;
+#pragma unroll
+          for (int t = 0; t < Q; ++t) cb = fma(c_P.C[s * Q + t], b[t], cb);
+          Z = fma(a[s], cb, Z);
+        }
+        const double invZ = 1.0 / Z;
+        if (!(invZ > 0.0) || !(invZ < INFINITY)) atomicOr(status, 1);
+#pragma unroll
+        for (int t = 0; t < Q; ++t) a[t] *= invZ;
+#pragma unroll
+        for (int rr = 0; rr < MS_R; ++rr) {
+          const int s = ch * MS_R + rr;
+          if (s < Q) {
+#pragma unroll
+            for (int t = s; t < Q; ++t) {
+              acc[rr * Q + t] = fma(a[s], b[t], acc[rr * Q + t]);
+              acc[rr * Q + t] = fma(a[t], b[s], acc[rr * Q + t]);
+            }
+          }
+        }
+      }
+    }
+    block_reduce_store<MS_R * Q>(acc, red, partials + (size_t)blockIdx.x * MS_STRIDE + ch * MS_R * Q);
+  }
+}
+
+__global__ void sbm_reduce_mstep(SbmState* st, const double* partials, int nrows, double lr, double maxCrs, double N) {
+  __shared__ double G[Q * Q];
+  const int tid = threadIdx.x;
+  if (tid < Q * Q) {
+    double s = 0.0;
+    for (int r = 0; r < nrows; ++r) s += partials[(size_t)r * MS_STRIDE + tid];
+    G[tid] = s;
+  }
+  __syncthreads();
+  if (tid < Q * Q) {
+    const int s = tid / Q, t = tid - s * Q;
+    const double Cold = st->C[tid];
+    const double Cn = Cold * (s <= t ? G[s * Q + t] : G[t * Q + s]);
+    double c = lr * Cn / (N * st->gr[s] * st->gr[t]) + (1.0 - lr) * Cold;  // sbm.jl:137
+    if (c > maxCrs) c = maxCrs; else if (c < 0.0) c = 0.0;                  // sbm.jl:138-146
+    st->C[tid] = c;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// update_theta(), sbm.jl:47-64, and S_theta = sum_i theta_i PSI_i for the next update_h().
+__global__ void __launch_bounds__(NT) sbm_theta_kernel(const SbmState* st, const int* __restrict__ rowptr, int n,
+                                                       const double* __restrict__ PSI, double* theta,
+                                                       double* partials) {
+  __shared__ double red[(NT / 32) * Q];
+  double acc[Q];
+#pragma unroll
+  for (int t = 0; t < Q; ++t) acc[t] = 0.0;
+  for (int i = blockIdx.x * NT + threadIdx.x; i < n; i += gridDim.x * NT) {
+    double p[Q];
+    load_vec<Q>(PSI, i, p);
+    int best = 0;
+    double bv = -1.0;
+#pragma unroll
+    for (int t = 0; t < Q; ++t)
+      if (p[t] > bv) {
+        bv = p[t];
+        best = t;
+      }
+    const double th = (double)(rowptr[i + 1] - rowptr[i]) / st->drmean[best];
+    theta[i] = th;
+#pragma unroll
+    for (int t = 0; t < Q; ++t) acc[t] = fma(th, p[t], acc[t]);
+  }
+  block_reduce_store<Q>(acc, red, partials + (size_t)blockIdx.x * Q);
+}
+
+__global__ void sbm_reduce_theta(SbmState* st, const double* partials, int nrows) {
+  const int tid = threadIdx.x;
+  if (tid < Q) {
+    double s = 0.0;
+    for (int r = 0; r < nrows; ++r) s += partials[(size_t)r * Q + tid];
+    st->Stheta[tid] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-iteration parameters: gr clamp (sbm.jl:89-96), h = update_h() (sbm.jl:70-73), logs; written to a
+// global staging struct that the host copies device->constant in stream order.
+__global__ void sbm_prepare(SbmState* st, SbmParams* out, double N, int zero_h, int gr_from_sum) {
+  __shared__ double g[Q];
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    double s = 0.0;
+    for (int r = 0; r < Q; ++r) {
+      double x = gr_from_sum ? st->sumPSI[r] / N : st->gr[r];  // gr = update_gr(PSI), sbm.jl:365
+      if (x != x || x < 1e-9) x = 1.0 / N;
+      g[r] = x;
+      s += x;
+    }
+    for (int r = 0; r < Q; ++r) {
+      g[r] /= s;
+      st->gr[r] = g[r];
+    }
+    out->logN = log(N);
+  }
+  __syncthreads();
+  if (tid < Q) {
+    out->lgr[tid] = log(g[tid]);
+    double hh = 0.0;
+    if (!zero_h)
+      for (int s = 0; s < Q; ++s) hh += st->Stheta[s] * st->C[s * Q + tid];
+    hh /= N;
+    st->h[tid] = hh;
+    out->h[tid] = hh;
+  }
+  for (int k = tid; k < Q * Q; k += blockDim.x) {
+    out->C[k] = st->C[k];
+    out->logC[k] = log(st->C[k]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// freeenergy(), sbm.jl:162-200: per undirected edge log Z_ij and the three Gibbs/MAP terms.
+// PASS 0 accumulates sums, PASS 1 sums of squared deviations from the means (unbiased var, sbm.jl:208-211).
+template <int PASS>
+__global__ void __launch_bounds__(NT) sbm_fe_kernel(const SbmState* st, const int* __restrict__ rev,
+                                                    const int* __restrict__ col, long long K,
+                                                    const double* __restrict__ psi, const double* __restrict__ theta,
+                                                    int dc, double* partials) {
+  __shared__ double red[(NT / 32) * 4];
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  double mean[4] = {0.0, 0.0, 0.0, 0.0};
+  if (PASS == 1)
+    for (int k = 0; k < 4; ++k) mean[k] = st->cvmean[k];
+  for (long long e = (long long)blockIdx.x * NT + threadIdx.x; e < K; e += (long long)gridDim.x * NT) {
+    const int r = rev[e];
+    if (r < e) {
+      double a[Q], b[Q];
+      load_vec<Q>(psi, e, b);  // j -> i   (i = row of e, j = col[e])
+      load_vec<Q>(psi, r, a);  // i -> j
+      double lc = -c_P.logN;
+      if (dc) lc += log(theta[col[r]]) + log(theta[col[e]]);
+      double Z0 = 0.0, W = 0.0, L1 = 0.0, G1 = 0.0;
+      int sa = 0, sb = 0;
+      double ma = -1.0, mb = -1.0;
+#pragma unroll
+      for (int s = 0; s < Q; ++s) {
+        if (a[s] > ma) { ma = a[s]; sa = s; }
+        if (b[s] > mb) { mb = b[s]; sb = s; }
+#pragma unroll
+        for (int t = 0; t < Q; ++t) {
+          const double w = a[s] * b[t];
+          const double wc = w * c_P.C[s * Q + t];
+          W += w;
+          Z0 += wc;
+          L1 += w * c_P.logC[s * Q + t];
+          G1 += wc * c_P.logC[s * Q + t];
+        }
+      }
+      double x[4];
+      x[0] = log(Z0) + lc;                // logZijs, sbm.jl:176
+      x[1] = W * lc + L1;                 // CVGPs,   sbm.jl:178-184
+      x[2] = (Z0 * lc + G1) / Z0;         // CVGTs,   sbm.jl:186-192
+      x[3] = lc + c_P.logC[sa * Q + sb];  // CVMAPs,  sbm.jl:194-198
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (PASS == 0) acc[k] += x[k];
+        else acc[k] += (x[k] - mean[k]) * (x[k] - mean[k]);
+      }
+    }
+  }
+  block_reduce_store<4>(acc, red, partials + (size_t)blockIdx.x * 4);
+}
+
+__global__ void sbm_reduce_fe(SbmState* st, const double* partials, int nrows, int pass, double L) {
+  const int tid = threadIdx.x;
+  if (tid < 4) {
+    double s = 0.0;
+    for (int r = 0; r < nrows; ++r) s += partials[(size_t)r * 4 + tid];
+    if (pass == 0) {
+      st->cvsum[tid] = s;
+      st->cvmean[tid] = s / L;
+    } else {
+      st->cvss[tid] = s;
+    }
+  }
+}
+
+__global__ void sbm_finalize(SbmState* st, double N, double L) {
+  if (threadIdx.x == 0) {
+    double ave = 0.0;
+    for (int s = 0; s < Q; ++s)
+      for (int t = 0; t < Q; ++t) ave += st->gr[s] * st->C[s * Q + t] * st->gr[t];  // sbm.jl:201
+    st->result[0] = -((st->sumlogZi - st->cvsum[0]) / N + 0.5 * ave);                 // FE, sbm.jl:203
+    for (int k = 0; k < 4; ++k) {
+      st->result[1 + k] = 1.0 - st->cvsum[k] / L;                                     // sbm.jl:204-207
+      st->result[5 + k] = st->cvss[k] / (L - 1.0);                                    // sbm.jl:208-211
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void k_permute_rows(const double* __restrict__ src, double* __restrict__ dst,
+                               const int* __restrict__ slot_of_link, long long K, int to_slots) {
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < K;
+       k += (long long)gridDim.x * blockDim.x) {
+    const long long s = slot_of_link[k];
+    double m[Q];
+    if (to_slots) {
+      load_vec<Q>(src, k, m);
+      store_vec<Q>(dst, s, m);
+    } else {
+      load_vec<Q>(src, s, m);
+      store_vec<Q>(dst, k, m);
+    }
+  }
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9e3779b97f4a7c15ULL;
+  x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ULL;
+  x = (x ^ (x >> 27)) * 0x94d049bb133111ebULL;
+  return x ^ (x >> 31);
+}
+
+// rand(1,B) normalised (sbm.jl:319-323), counter-based so the result does not depend on the launch shape.
+__global__ void k_random_messages(double* __restrict__ dst, const int* __restrict__ slot_of_link, long long K,
+                                  uint64_t seed) {
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < K;
+       k += (long long)gridDim.x * blockDim.x) {
+    double m[Q];
+    double s = 0.0;
+#pragma unroll
+    for (int t = 0; t < Q; ++t) {
+      const uint64_t r = splitmix64(seed ^ splitmix64((uint64_t)k * Q + t));
+      m[t] = ((double)(r >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+      s += m[t];
+    }
+#pragma unroll
+    for (int t = 0; t < Q; ++t) m[t] /= s;
+    store_vec<Q>(dst, slot_of_link[k], m);
+  }
+}
+
+__global__ void k_assignment(const double* __restrict__ PSI, int n, int* __restrict__ block) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double p[Q];
+    load_vec<Q>(PSI, i, p);
+    int best = 0;
+    double bv = p[0];
+#pragma unroll
+    for (int t = 1; t < Q; ++t)
+      if (p[t] > bv) {
+        bv = p[t];
+        best = t;
+      }
+    block[i] = best + 1;
+  }
+}
+
+// =============================================================================================
+// Launchers (host)
+// =============================================================================================
+VertexArgs vertex_args(gbx_sbm* h) {
+  VertexArgs a;
+  a.rowptr = h->rowptr;
+  a.col = h->col;
+  a.rev = h->rev;
+  a.lvtx = h->lvtx;
+  a.tiles = h->tiles;
+  a.ntiles = h->ntiles;
+  a.hubs = h->hubs;
+  a.theta = h->theta;
+  a.cur = h->msg[h->cur];
+  a.nxt = h->msg[h->cur ^ 1];
+  a.PSI = h->PSI;
+  a.partials = h->part_vertex;
+  a.status = &h->st->status;
+  a.damping = h->opt.damping;
+  a.dc = h->opt.degreecorrection;
+  return a;
+}
+
+template <int MODE>
+int launch_vertex_pass_t(gbx_sbm* h) {
+  VertexArgs a = vertex_args(h);
+  if (h->ntiles > 0) {
+    sbm_vertex_kernel<MODE><<<h->grid_vertex, NT, 0, h->stream>>>(a);
+    h->launches++;
+  }
+  if (h->nhubs > 0) {
+    sbm_hub_kernel<MODE><<<h->nhubs, NT, 0, h->stream>>>(a, h->grid_vertex);
+    h->launches++;
+  }
+  GBX_CUDA_TRY(cudaGetLastError());
+  return GBX_OK;
+}
+
+int op_vertex_pass(gbx_sbm* h, int mode) {
+  if (mode == MODE_SWEEP) return launch_vertex_pass_t<MODE_SWEEP>(h);
+  if (mode == MODE_MARGINAL) return launch_vertex_pass_t<MODE_MARGINAL>(h);
+  return launch_vertex_pass_t<MODE_LOGZ>(h);
+}
+
+int op_reduce_vertex(gbx_sbm* h, int mode) {
+  const int nrows = (h->ntiles > 0 ? h->grid_vertex : 0) + h->nhubs;
+  const double* base = h->part_vertex + (h->ntiles > 0 ? 0 : (size_t)h->grid_vertex * PSTRIDE);
+  sbm_reduce_vertex<<<1, 64, 0, h->stream>>>(h->st, base, nrows, mode, h->opt.priorlearning,
+                                             h->opt.degreecorrection, (double)h->n);
+  h->launches++;
+  GBX_CUDA_TRY(cudaGetLastError());
+  return GBX_OK;
+}
+
+int op_prepare(gbx_sbm* h, int zero_h, int gr_from_sum) {
+  sbm_prepare<<<1, 64, 0, h->stream>>>(h->st, h->params, (double)h->n, zero_h, gr_from_sum);
+  h->launches++;
+  GBX_CUDA_TRY(cudaGetLastError());
+  GBX_CUDA_TRY(cudaMemcpyToSymbolAsync(c_P, h->params, sizeof(SbmParams), 0, cudaMemcpyDeviceToDevice, h->stream));
+  return GBX_OK;
+}
+
+int op_mstep(gbx_sbm* h) {
+  const double maxCrs = h->opt.maxCrs > 0 ? h->opt.maxCrs : (double)h->n;
+  sbm_mstep_kernel<<<h->grid_mstep, NT, 0, h->stream>>>(h->rev, (long long)h->K, h->msg[h->cur], h->part_mstep,
+                                                        &h->st->status);
+  sbm_reduce_mstep<<<1, 256, 0, h->stream>>>(h->st, h->part_mstep, h->grid_mstep, h->opt.learningrate, maxCrs,
+                                             (double)h->n);
+  h->launches += 2;
+  GBX_CUDA_TRY(cudaGetLastError());
+  return GBX_OK;
+}
+
+int op_theta(gbx_sbm* h) {
+  sbm_theta_kernel<<<h->grid_theta, NT, 0, h->stream>>>(h->st, h->rowptr, (int)h->n, h->PSI, h->theta, h->part_theta);
+  sbm_reduce_theta<<<1, 32, 0, h->stream>>>(h->st, h->part_theta, h->grid_theta);
+  h->launches += 2;
+  GBX_CUDA_TRY(cudaGetLastError());
+  return GBX_OK;
+}
+
+int op_free_energy(gbx_sbm* h) {
+  const double L = 0.5 * (double)h->K;
+  int rc = op_vertex_pass(h, MODE_LOGZ);
+  if (rc != GBX_OK) return rc;
+  rc = op_reduce_vertex(h, MODE_LOGZ);
+  if (rc != GBX_OK) return rc;
+  sbm_fe_kernel<0><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->rev, h->col, (long long)h->K, h->msg[h->cur], h->theta,
+                                                     h->opt.degreecorrection, h->part_fe);
+  sbm_reduce_fe<<<1, 32, 0, h->stream>>>(h->st, h->part_fe, h->grid_fe, 0, L);
+  sbm_fe_kernel<1><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->rev, h->col, (long long)h->K, h->msg[h->cur], h->theta,
+                                                     h->opt.degreecorrection, h->part_fe);
+  sbm_reduce_fe<<<1, 32, 0, h->stream>>>(h->st, h->part_fe, h->grid_fe, 1, L);
+  sbm_finalize<<<1, 32, 0, h->stream>>>(h->st, (double)h->n, L);
+  h->launches += 5;
+  GBX_CUDA_TRY(cudaGetLastError());
+  return GBX_OK;
+}
+
+int grid_for(gbx_sbm* h, int64_t items) {
+  return (int)std::min<int64_t>(std::max<int64_t>(1, (items + 255) / 256), (int64_t)h->num_sms * 8);
+}
+
+int op_permute(gbx_sbm* h, const double* src, double* dst, int to_slots) {
+  k_permute_rows<<<grid_for(h, h->K), 256, 0, h->stream>>>(src, dst, h->slot_of_link, (long long)h->K, to_slots);
+  h->launches++;
+  GBX_CUDA_TRY(cudaGetLastError());
+  return GBX_OK;
+}
+
+int op_random_messages(gbx_sbm* h, uint64_t seed) {
+  k_random_messages<<<grid_for(h, h->K), 256, 0, h->stream>>>(h->msg[0], h->slot_of_link, (long long)h->K, seed);
+  h->launches++;
+  GBX_CUDA_TRY(cudaGetLastError());
+  return GBX_OK;
+}
+
+int op_assignment(gbx_sbm* h, int* dev_block) {
+  k_assignment<<<grid_for(h, h->n), 256, 0, h->stream>>>(h->PSI, (int)h->n, dev_block);
+  h->launches++;
+  GBX_CUDA_TRY(cudaGetLastError());
+  return GBX_OK;
+}
+
+int op_occupancy(int* vertex_occ, int* mstep_occ) {
+  GBX_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(vertex_occ, sbm_vertex_kernel<MODE_SWEEP>, NT, 0));
+  GBX_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(mstep_occ, sbm_mstep_kernel, NT, 0));
+  return GBX_OK;
+}
+
+const SbmOps kOps = {Q,         op_vertex_pass,     op_reduce_vertex, op_prepare,   op_mstep, op_theta, op_free_energy,
+                     op_permute, op_random_messages, op_assignment,    op_occupancy};
+
+}  // namespace
+
+#define GBX_CAT_(a, b) a##b
+#define GBX_CAT(a, b) GBX_CAT_(a, b)
+const SbmOps* GBX_CAT(sbm_ops_q, GBX_Q)() { return &kOps; }
+
+}  // namespace gbx

@@ -1,0 +1,116 @@
+/*
+ * libgraphbix_cuda.so -- C ABI of the B200 (sm_100a) implementation of graphBIX's inner loop.
+ *
+ * What it replaces in the reference (tatsuro-kawamoto/graphBIX):
+ *   gbx_sbm_*  <->  function EM(Ntot,B,links,maxCrs,initial,degreecorrection,itrmax,priorlearning,
+ *                               learningrate)                              src/sbm.jl:28-370
+ *   gbx_mod_*  <->  function EM(gr,Ntot,B,links,maxomega,itrmax,betafrac,learning,priorlearning,dc,
+ *                               learningrate)                              src/mod.jl:3-244
+ * Everything outside EM() (DocOpt CLI, edge-list parsing, simplegraph, giant component, spectral
+ * initialisation, q sweep, summary/assessment/assignment/.smap writers, PyPlot) stays in the host
+ * program; INTEGRATION.md shows the `ccall` lines a maintainer adds to sbm.jl / mod.jl.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all arrays are HOST memory unless a name ends in `_dev`;
+ *   - `links` is the reference's K x 2 Int64 matrix exactly as Julia stores it (column-major:
+ *     links[0..K) = first column, links[K..2K) = second column), 1-based vertex ids, holding BOTH
+ *     directions of every undirected edge, no self loops, no duplicates (output of `simplegraph`,
+ *     sbm.jl:414-425);
+ *   - a "message" array is double[K][q]: row k is PSIcav[sub2ind((N,N), links[k,1], links[k,2])],
+ *     the cavity message links[k,1] -> links[k,2] (sbm.jl:106-109);
+ *   - PSI is double[N][q] (row i = marginal of vertex i+1), Crs is double[q][q] (symmetric),
+ *     gr / h are double[q], theta is double[N];
+ *   - every function returns GBX_OK (0) or a negative error code; gbx_last_error() gives the text.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef GRAPHBIX_CUDA_H
+#define GRAPHBIX_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GBX_OK 0
+#define GBX_ERR_INVALID (-1)   /* bad argument / malformed links            */
+#define GBX_ERR_CUDA (-2)      /* CUDA runtime error (no device, OOM, ...)   */
+#define GBX_ERR_STATE (-3)     /* call order violated (e.g. run before init) */
+
+#define GBX_MAX_Q 16
+
+typedef struct gbx_sbm gbx_sbm; /* opaque handle: one graph + one EM state on one GPU */
+
+/* Options of EM(); defaults (gbx_sbm_default_options) are the reference's. */
+typedef struct gbx_sbm_options {
+  int degreecorrection;     /* sbm.jl:345  --dc            (default 1)                            */
+  int priorlearning;        /* sbm.jl:113  --prior         (default 1)                            */
+  double learningrate;      /* sbm.jl:137  --learning_rate (default 0.3)                          */
+  double maxCrs;            /* sbm.jl:910  maxCrs = Ntot   (<=0 means Ntot)                       */
+  int itrmax;               /* sbm.jl:342  --itrmax        (default 256)                          */
+  double bp_conv_threshold; /* sbm.jl:339  BPconvthreshold (default 1e-6)                         */
+  double damping;           /* weight of the new message in the synchronous update, (0,1];
+                               1 = undamped (default). Not in the reference (asynchronous sweep). */
+  int check_every;          /* read the residual back every n iterations (default 1)              */
+} gbx_sbm_options;
+
+/* What EM() returns besides the arrays (sbm.jl:369). */
+typedef struct gbx_sbm_result {
+  double FE, CVBayes, CVGP, CVGT, CVMAP;
+  double varCVBayes, varCVGP, varCVGT, varCVMAP;
+  int fail;        /* sbm.jl:310-312: NaN/Inf in the initial Crs                       */
+  int cnv;         /* sbm.jl:348-353                                                   */
+  int itrnum;      /* iteration at which BPconv < threshold (0 if never)               */
+  int itrs_done;   /* iterations actually run                                          */
+  int nonfinite;   /* a NaN/Inf/zero appeared in the messages ("overflow", sbm.jl:355) */
+  double BPconv;   /* last residual, sum_i sum_s |dPSI_i(s)| / N (sbm.jl:123)          */
+  double max_dpsi; /* last max_i sum_s |dPSI_i(s)|                                     */
+} gbx_sbm_result;
+
+int gbx_version(void);
+const char* gbx_last_error(void);
+int gbx_device_count(void); /* number of visible CUDA devices, or GBX_ERR_CUDA */
+
+void gbx_sbm_default_options(gbx_sbm_options* opt);
+
+/* Build the device-resident graph: destination-major CSR of the K = 2E directed edges, the
+ * reverse-edge index and the tile schedule (sbm.jl:265-275 builds `nb`, `inds` for the same use). */
+int gbx_sbm_create(gbx_sbm** out, int device, int64_t n_vertices, int64_t n_links,
+                   const int64_t* links, int q);
+int gbx_sbm_destroy(gbx_sbm* h);
+
+/* Run every later launch of this handle on `cuda_stream` (a cudaStream_t; NULL = default stream). */
+int gbx_sbm_set_stream(gbx_sbm* h, void* cuda_stream);
+int gbx_sbm_set_options(gbx_sbm* h, const gbx_sbm_options* opt);
+
+/* Initial state, sbm.jl:277-341: theta = 1, h = 0, Crs clamped below at 1e-6, messages as given
+ * (psicav == NULL: uniform random rows normalised to 1 from `seed`, sbm.jl:319-323), then
+ * PSI = updatePSI() and gr = mean(PSI).  gr_init is ignored when priorlearning == 0 (sbm.jl:304). */
+int gbx_sbm_init(gbx_sbm* h, const double* gr_init, const double* Crs_init, const double* psicav,
+                 uint64_t seed);
+
+/* The EM loop, sbm.jl:342-362, followed by sbm.jl:364-366 (h, gr, free energy and CV errors). */
+int gbx_sbm_em(gbx_sbm* h, gbx_sbm_result* res);
+
+/* Pieces of the loop, for tests and benchmarks. */
+int gbx_sbm_iterate(gbx_sbm* h, int n_iters, double* bpconv_out); /* n x (BP sweep, M-step, theta)  */
+int gbx_sbm_bp_sweeps(gbx_sbm* h, int n_sweeps);                  /* n x BP sweep kernel only        */
+int gbx_sbm_finalize(gbx_sbm* h, gbx_sbm_result* res);            /* sbm.jl:364-366                  */
+
+/* Read the state back (any pointer may be NULL). */
+int gbx_sbm_get_state(gbx_sbm* h, double* gr, double* Crs, double* PSI, double* theta, double* hfield);
+int gbx_sbm_get_messages(gbx_sbm* h, double* psicav);
+/* argmax_s PSI[i][s] + 1 (sbm.jl:983-986), computed on the device. */
+int gbx_sbm_get_assignment(gbx_sbm* h, int32_t* block);
+
+/* Introspection for benchmarks: kernels launched so far, directed edges, bytes of device memory. */
+int64_t gbx_sbm_launch_count(const gbx_sbm* h);
+int64_t gbx_sbm_num_links(const gbx_sbm* h);
+int64_t gbx_sbm_device_bytes(const gbx_sbm* h);
+/* Algorithmic HBM bytes one BP sweep moves (DESIGN.md "bytes per unit"). */
+double gbx_sbm_sweep_bytes(const gbx_sbm* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAPHBIX_CUDA_H */

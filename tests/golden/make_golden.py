@@ -1,0 +1,53 @@
+"""Generates tests/golden/sbm_em_*.npz: inputs and converged outputs of the ORACLE (oracle/sbm_oracle.py, the
+restatement of the reference's EM(), src/sbm.jl:28-370) on small planted-partition graphs.
+
+The reference itself cannot run here (no Julia), so these are oracle outputs, not reference outputs;
+they pin the oracle against regressions and let the GPU tests run without re-running the slow Python loops.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+
+from helpers import assortative_init, planted_case  # noqa: E402
+from oracle import sbm_oracle as O  # noqa: E402
+
+CASES = [
+    # name, n, q, deg, eps, seed, dc, prior, init
+    ("q2_dc_prior", 260, 2, 8.0, 0.1, 42, True, True, "assortative"),
+    ("q3_nodc_prior", 260, 3, 8.0, 0.1, 43, False, True, "assortative"),
+    ("q3_nodc_noprior", 260, 3, 8.0, 0.1, 44, False, False, "assortative"),
+    ("q4_dc_prior", 300, 4, 9.0, 0.08, 45, True, True, "assortative"),
+    ("q3_dc_noprior", 260, 3, 8.0, 0.1, 46, True, False, "assortative"),
+    ("q2_disassortative", 240, 2, 8.0, 8.0, 47, False, True, "disassortative"),
+]
+
+
+def main():
+    for name, n, q, deg, eps, seed, dc, prior, init in CASES:
+        n, links, psi0, lab = planted_case(n, q, deg, eps, seed)
+        if init == "assortative":
+            gr0, C0 = assortative_init(q)
+        else:
+            gr0, C0 = np.ones(q) / q, -9.9 * np.eye(q) + 10 * np.ones((q, q))
+        r = O.EM(n, q, links, n, (gr0, C0), dc, 4000, prior, 0.3, rng=np.random.default_rng(seed),
+                 PSIcav0=psi0, BPconvthreshold=1e-12)
+        print(name, "n", n, "K", links.shape[0], "cnv", r.cnv, "itr", r.itrs_done, "BPconv", r.BPconv, "FE", r.FE)
+        if not r.cnv:
+            print("   -> oracle did not converge, skipped")
+            continue
+        np.savez_compressed(
+            os.path.join(HERE, f"sbm_em_{name}.npz"), n=n, q=q, links=links, psi0=psi0, gr0=gr0, C0=C0,
+            dc=dc, prior=prior, lr=0.3, tol=1e-12, labels=lab, gr=r.gr, Crs=r.Crs, PSI=r.PSI, PSIcav=r.PSIcav,
+            theta=r.theta, scalars=np.array([r.FE, r.CVBayes, r.CVGP, r.CVGT, r.CVMAP, r.varCVBayes, r.varCVGP,
+                                             r.varCVGT, r.varCVMAP]), itrnum=r.itrnum)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,100 @@
+"""CUDA path vs the numpy statement of the same synchronous schedule, sweep by sweep (tight tolerances)."""
+import numpy as np
+import pytest
+
+from helpers import assortative_init, planted_case
+from sync_model import SyncSBM
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_pair(n, links, q, psi0, gr0, C0, iters, **opt):
+    from graphbix_b200.engine import SbmEngine
+    dc = opt.get("dc", True)
+    prior = opt.get("prior", True)
+    damping = opt.get("damping", 1.0)
+    ref = SyncSBM(n, links, q, gr0, C0, psi0, dc=dc, prior=prior, lr=0.3, damping=damping)
+    eng = SbmEngine(n, links, q)
+    eng.set_options(degreecorrection=int(dc), priorlearning=int(prior), learningrate=0.3, damping=damping)
+    eng.init(gr0, C0, psi0)
+    st = eng.state()
+    np.testing.assert_allclose(st["PSI"], ref.PSI, rtol=0, atol=1e-13)
+    np.testing.assert_allclose(st["gr"], ref.gr, rtol=1e-13)
+    for it in range(iters):
+        cref = ref.iterate()
+        cgpu = eng.iterate(1)
+        st = eng.state()
+        np.testing.assert_allclose(cgpu, cref, rtol=1e-9, atol=1e-16, err_msg=f"conv it={it}")
+        np.testing.assert_allclose(st["PSI"], ref.PSI, rtol=0, atol=1e-12, err_msg=f"PSI it={it}")
+        np.testing.assert_allclose(eng.messages(), ref.messages_in_link_order(), rtol=0, atol=1e-12,
+                                   err_msg=f"messages it={it}")
+        np.testing.assert_allclose(st["Crs"], ref.C, rtol=1e-11, err_msg=f"Crs it={it}")
+        np.testing.assert_allclose(st["gr"], ref.gr, rtol=1e-11, err_msg=f"gr it={it}")
+        np.testing.assert_allclose(st["h"], ref.h, rtol=1e-11, err_msg=f"h it={it}")
+        if dc:
+            np.testing.assert_allclose(st["theta"], ref.theta, rtol=1e-12, err_msg=f"theta it={it}")
+    return eng, ref
+
+
+@pytest.mark.parametrize("q", [2, 3, 8])
+@pytest.mark.parametrize("dc,prior", [(True, True), (False, True), (True, False), (False, False)])
+def test_sweeps_match_sync_model(gpu_required, q, dc, prior):
+    n, links, psi0, _ = planted_case(600, q, 9.0, 0.15, seed=q)
+    gr0, C0 = assortative_init(q)
+    eng, ref = _run_pair(n, links, q, psi0, gr0, C0, 6, dc=dc, prior=prior)
+    res = eng.finalize()
+    f = ref.finalize()
+    for k in ("FE", "CVBayes", "CVGP", "CVGT", "CVMAP", "varCVBayes", "varCVGP", "varCVGT", "varCVMAP"):
+        np.testing.assert_allclose(getattr(res, k), f[k], rtol=1e-10, err_msg=k)
+    assert res.nonfinite == 0
+
+
+def test_damped_sweeps_match_sync_model(gpu_required):
+    n, links, psi0, _ = planted_case(500, 3, 8.0, 0.1, seed=11)
+    gr0, C0 = assortative_init(3)
+    _run_pair(n, links, 3, psi0, gr0, C0, 5, damping=0.5)
+
+
+def _with_hubs(n, q, seed):
+    """Planted partition plus two hubs of degree > 256 (own kernel) and a degree-0-free tail."""
+    n0, links, psi0, lab = planted_case(n, q, 6.0, 0.1, seed=seed)
+    rng = np.random.default_rng(seed)
+    und = links[links[:, 0] < links[:, 1]]
+    extra = []
+    for hub, deg in ((1, 300), (n0 // 2, 700)):
+        nb = rng.choice(np.arange(1, n0 + 1), size=deg, replace=False)
+        extra += [(min(hub, v), max(hub, v)) for v in nb if v != hub]
+    und = np.unique(np.vstack([und, np.array(extra)]), axis=0)
+    links = np.vstack([und, und[:, ::-1]])
+    K = links.shape[0]
+    psi0 = rng.random((K, q))
+    psi0[np.arange(K), lab[links[:, 0] - 1]] += 1.0
+    psi0 /= psi0.sum(1, keepdims=True)
+    return n0, links, psi0
+
+
+@pytest.mark.parametrize("q", [2, 8])
+def test_hub_vertices(gpu_required, q):
+    n, links, psi0 = _with_hubs(1500, q, seed=5)
+    deg = np.bincount(links[:, 0])
+    assert deg.max() > 256
+    gr0, C0 = assortative_init(q)
+    _run_pair(n, links, q, psi0, gr0, C0, 4, dc=True, prior=True)
+
+
+def test_clamp_regime(gpu_required):
+    """Tiny affinities push unnormalised values below 1e-8, where the absolute clamp of sbm.jl:42 binds."""
+    q = 3
+    n, links, psi0, _ = planted_case(400, q, 10.0, 0.1, seed=21)
+    gr0 = np.ones(q) / q
+    C0 = 1e-3 * np.eye(q) + 1e-5 * np.ones((q, q))
+    from graphbix_b200.engine import SbmEngine
+    ref = SyncSBM(n, links, q, gr0, C0, psi0, dc=False, prior=True, lr=0.0)
+    eng = SbmEngine(n, links, q)
+    eng.set_options(degreecorrection=0, priorlearning=1, learningrate=0.0)
+    eng.init(gr0, C0, psi0)
+    for it in range(3):
+        ref.iterate()
+        eng.iterate(1)
+        np.testing.assert_allclose(eng.state()["PSI"], ref.PSI, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(eng.messages(), ref.messages_in_link_order(), rtol=0, atol=1e-12)
