@@ -182,7 +182,7 @@ int gbx_sbm_create(gbx_sbm** out, int device, int64_t n, int64_t K, const int64_
   }
   // ---- tile schedule: runs of consecutive vertices with <= TILE_E slots and <= TV vertices; hubs apart ----
   const int TV = tile_vertices(q);
-  std::vector<int2> tiles;
+  std::vector<int4> tiles;
   std::vector<int> hubs;
   std::vector<unsigned char> lvtx((size_t)K, 0);
   {
@@ -203,7 +203,7 @@ int gbx_sbm_create(gbx_sbm** out, int device, int64_t n, int64_t K, const int64_
         ne += d;
         ++w;
       }
-      tiles.push_back(make_int2((int)v, (int)w));
+      tiles.push_back(make_int4((int)v, (int)(w - v), rowptr[(size_t)v], ne));
       v = w;
     }
   }
@@ -231,6 +231,7 @@ int gbx_sbm_create(gbx_sbm** out, int device, int64_t n, int64_t K, const int64_
     GBX_TRY(dev_alloc(h, &h->col, (size_t)K));
     GBX_TRY(dev_alloc(h, &h->rev, (size_t)K));
     GBX_TRY(dev_alloc(h, &h->lvtx, (size_t)K));
+    GBX_TRY(dev_alloc(h, &h->escale, (size_t)K));
     GBX_TRY(dev_alloc(h, &h->slot_of_link, (size_t)K));
     GBX_TRY(dev_alloc(h, &h->tiles, tiles.size()));
     GBX_TRY(dev_alloc(h, &h->hubs, hubs.size()));
@@ -245,7 +246,7 @@ int gbx_sbm_create(gbx_sbm** out, int device, int64_t n, int64_t K, const int64_
     GBX_CUDA_TRY(cudaMemcpy(h->rev, rev.data(), (size_t)K * sizeof(int), cudaMemcpyHostToDevice));
     GBX_CUDA_TRY(cudaMemcpy(h->lvtx, lvtx.data(), (size_t)K, cudaMemcpyHostToDevice));
     GBX_CUDA_TRY(cudaMemcpy(h->slot_of_link, slot_of_link.data(), (size_t)K * sizeof(int), cudaMemcpyHostToDevice));
-    GBX_CUDA_TRY(cudaMemcpy(h->tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    GBX_CUDA_TRY(cudaMemcpy(h->tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice));
     GBX_CUDA_TRY(cudaMemcpy(h->hubs, hubs.data(), hubs.size() * sizeof(int), cudaMemcpyHostToDevice));
     GBX_CUDA_TRY(cudaMemset(h->st, 0, sizeof(SbmState)));
     GBX_CUDA_TRY(cudaMallocHost((void**)&h->h_state, sizeof(SbmState)));
@@ -284,6 +285,7 @@ int gbx_sbm_destroy(gbx_sbm* h) {
   cudaFree(h->col);
   cudaFree(h->rev);
   cudaFree(h->lvtx);
+  cudaFree(h->escale);
   cudaFree(h->slot_of_link);
   cudaFree(h->tiles);
   cudaFree(h->hubs);
@@ -347,8 +349,9 @@ int gbx_sbm_init(gbx_sbm* h, const double* gr_init, const double* Crs_init, cons
     GBX_TRY(h->ops->random_messages(h, seed));
   }
   {
-    std::vector<double> ones((size_t)h->n, 1.0);  // theta = ones(Ntot,1), sbm.jl:277
+    std::vector<double> ones((size_t)std::max<int64_t>(h->n, h->K), 1.0);  // theta = ones(Ntot,1), sbm.jl:277
     GBX_CUDA_TRY(cudaMemcpyAsync(h->theta, ones.data(), (size_t)h->n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    GBX_CUDA_TRY(cudaMemcpyAsync(h->escale, ones.data(), (size_t)h->K * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     GBX_CUDA_TRY(cudaStreamSynchronize(h->stream));
   }
   if (!h->fail) {
@@ -488,7 +491,7 @@ double gbx_sbm_sweep_bytes(const gbx_sbm* h) {
   if (!h) return 0.0;
   const double q = h->q, K = (double)h->K, n = (double)h->n;
   double per_edge = 2.0 * q * 8.0 + 4.0 + 1.0;         // message in, message out, rev, tile-local vertex id
-  if (h->opt.degreecorrection) per_edge += 4.0 + 8.0;  // col + theta of the neighbour
+  if (h->opt.degreecorrection) per_edge += 8.0;        // theta_row * theta_col of the slot
   if (h->opt.damping != 1.0) per_edge += q * 8.0;      // old outgoing message
   double per_vertex = 2.0 * q * 8.0 + 4.0;             // PSI read + write, rowptr
   if (h->opt.degreecorrection) per_vertex += 8.0;

@@ -54,7 +54,8 @@ struct gbx_sbm {
   // graph (device)
   int *rowptr = nullptr, *col = nullptr, *rev = nullptr, *slot_of_link = nullptr, *hubs = nullptr;
   unsigned char* lvtx = nullptr;  // per edge slot: index of its vertex inside its tile
-  int2* tiles = nullptr;
+  int4* tiles = nullptr;          // (first vertex, #vertices, first edge slot, #edge slots)
+  double* escale = nullptr;       // per edge slot theta_row * theta_col (all ones until update_theta runs)
   int ntiles = 0, nhubs = 0;
   // state (device)
   double *msg[2] = {nullptr, nullptr}, *PSI = nullptr, *theta = nullptr;

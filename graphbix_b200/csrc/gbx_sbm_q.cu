@@ -15,6 +15,8 @@
 #ifndef GBX_Q
 #error "compile with -DGBX_Q=<number of groups>"
 #endif
+#include <algorithm>
+
 #include "gbx_sbm_internal.h"
 
 namespace gbx {
@@ -22,10 +24,11 @@ namespace {
 
 constexpr int Q = GBX_Q;
 constexpr int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
-constexpr int QP = next_pow2(Q);     // lanes per component group (padding lanes idle when Q is not 2^k)
-constexpr int LV = 2 * QP;           // lanes per vertex in the aggregation stage: 2 edge-parities x QP
+constexpr int QP = next_pow2(Q);     // lanes per vertex in the aggregation stage (padding lanes idle when Q != 2^k)
+constexpr int LV = QP;
 constexpr int TV = tile_vertices(Q);
 constexpr int VPR = NT / LV;         // vertices per aggregation round
+constexpr int QS = Q | 1;            // row stride (doubles) of the per-edge factors in smem: odd -> no bank conflicts
 
 constexpr double LOG_1EM8 = -18.420680743952367;  // log(10^(-8.0)), sbm.jl:42
 constexpr double INV_LN2 = 1.4426950408889634;
@@ -39,7 +42,8 @@ struct VertexArgs {
   const int* col;
   const int* rev;
   const unsigned char* lvtx;
-  const int2* tiles;  // [ntiles] (first vertex, one past last vertex)
+  const double* escale;  // per edge slot: theta_row * theta_col (degree-corrected runs), refreshed with theta
+  const int4* tiles;     // [ntiles] (first vertex, #vertices, first edge slot, #edge slots)
   int ntiles;
   const int* hubs;    // vertex ids with degree > TILE_E
   const double* theta;
@@ -94,31 +98,24 @@ __device__ __forceinline__ double group_sum(double x) {
 }
 
 // T[t] = theta_i theta_s (psi * Crs)[t]  (sbm.jl:87), rescaled by 2^-ke so that max_t T[t] is in [1,2).
-__device__ __forceinline__ void edge_transform(const double (&psi)[Q], double sc, double (&T)[Q], int& ke,
-                                               int* status) {
+// A zero / NaN / Inf factor is left as it is (ke = 0): like log(0) in the reference it turns the messages that
+// depend on it into NaN, which reaches the residual and is reported as `nonfinite` ("overflow", sbm.jl:355).
+__device__ __forceinline__ void edge_transform(const double (&psi)[Q], double sc, double (&T)[Q], int& ke) {
   double m = 0.0;
-  bool allpos = true;
 #pragma unroll
   for (int t = 0; t < Q; ++t) {
     double acc = 0.0;
 #pragma unroll
     for (int s = 0; s < Q; ++s) acc = fma(psi[s], c_P.C[s * Q + t], acc);
     T[t] = acc * sc;
-    m = (T[t] > m) ? T[t] : m;
-    allpos = allpos && (T[t] > 0.0);  // false for NaN as well
+    m = fmax(m, T[t]);
   }
   bool ok;
   ke = exponent_of(m, ok);
-  if (ok && allpos) {
-    const double s2 = pow2i(-ke);
+  if (!ok) ke = 0;
+  const double s2 = pow2i(-ke);
 #pragma unroll
-    for (int t = 0; t < Q; ++t) T[t] *= s2;
-  } else {
-    ke = 0;
-    atomicOr(status, 1);
-#pragma unroll
-    for (int t = 0; t < Q; ++t) T[t] = __longlong_as_double(0x7ff8000000000000LL);  // log(<=0) in the reference
-  }
+  for (int t = 0; t < Q; ++t) T[t] *= s2;
 }
 
 // Cavity message i -> j (sbm.jl:108-109) from the vertex product u and this edge's factor T, the absolute
@@ -142,7 +139,7 @@ __device__ __forceinline__ void emit_message(const VertexArgs& a, const double* 
       S += w[t];
     }
   }
-  const double inv = 1.0 / S;
+  const double inv = fast_rcp(S);
 #pragma unroll
   for (int t = 0; t < Q; ++t) w[t] *= inv;
   if (a.damping != 1.0) {
@@ -155,23 +152,29 @@ __device__ __forceinline__ void emit_message(const VertexArgs& a, const double* 
   store_vec<Q>(a.nxt, rv, w);
 }
 
-// Per-thread accumulators of the aggregation lanes.
+// Per-thread accumulators of the aggregation lanes (lane t of a group owns component t).
 struct LaneAcc {
-  double psi = 0.0;   // sum of PSI_i(t) for this lane's component t (parity-0 lanes)
-  double res = 0.0;   // sum of per-vertex L1 changes (lane t = 0, parity 0)
-  double logz = 0.0;  // sum of log Z_i
-  double vmax = 0.0;  // max per-vertex L1 change
+  double psi = 0.0;   // sum of PSI_i(t)
+  double res = 0.0;   // sum of per-vertex L1 changes (lane t = 0)
+  double logz = 0.0;  // sum of log Z_i            (lane t = 0)
+  double vmax = 0.0;  // max per-vertex L1 change  (lane t = 0)
 };
+
+// Bits of this lane's QP-wide group inside a warp ballot.
+__device__ __forceinline__ unsigned group_bits(unsigned ballot) {
+  if constexpr (QP == 32) return ballot;
+  const unsigned lane = threadIdx.x & 31u;
+  return (ballot >> (lane & ~(unsigned)(QP - 1))) & ((1u << QP) - 1u);
+}
 
 // Everything a vertex needs once lane t holds prod_t = product of its scaled edge factors and K = their exponents.
 //   true unnormalised value v_t = u_t 2^K e^xmax;  the clamp floor of sbm.jl:42 in the scaled domain is 2^f.
 // Runs on the QP lanes of a group (all lanes of the warp execute it; `valid` gates the side effects).
 template <int MODE>
-__device__ __forceinline__ void vertex_finish(const VertexArgs& a, bool valid, bool writer, int gv, int deg, int t,
-                                              double prod, int K, double& u_out, double& ffrac, int& fn,
-                                              LaneAcc& acc, double* s_dr, double* s_nr) {
+__device__ __forceinline__ void vertex_finish(const VertexArgs& a, bool valid, int gv, int deg, int t, double th,
+                                              double old, double prod, int K, double& u_out, double& ffrac, int& fn,
+                                              LaneAcc& acc, unsigned long long* s_dr, int* s_nr) {
   const bool tl = t < Q;
-  const double th = (a.dc && valid) ? a.theta[gv] : 1.0;
   const double x = tl ? (c_P.lgr[tl ? t : 0] - th * c_P.h[tl ? t : 0]) : -INFINITY;
   const double xmax = group_max(x);
   const double u = tl ? exp(x - xmax) * prod : 0.0;
@@ -185,28 +188,22 @@ __device__ __forceinline__ void vertex_finish(const VertexArgs& a, bool valid, b
     const double umax = group_max(u);
     const double cut = umax * EXP_M500;
     const double s = group_sum(tl ? ((u < cut) ? cut : u) : 0.0);
-    if (valid && writer && t == 0) {
-      acc.logz += log(s) + (double)K * LN2 + xmax;
-      if (!(s > 0.0)) atomicOr(a.status, 1);
-    }
+    if (valid && t == 0) acc.logz += log(s) + (double)K * LN2 + xmax;
   } else {
     double w = u;
-    const double umin = group_min(tl ? u : INFINITY);
-    if (umin < pow2c(fn + 1)) {  // rare
+    const unsigned low = group_bits(__ballot_sync(0xffffffffu, tl && (u < pow2c(fn + 1))));
+    if (low) {  // rare: a component is at or below the clamp floor
       const double fl = scale2(exp2(ffrac), fn);
       w = (u < fl) ? fl : u;
     }
     const double S = group_sum(tl ? w : 0.0);
-    const double p = w * (1.0 / S);
+    const double p = w * fast_rcp(S);
     double r = 0.0;
-    if constexpr (MODE == MODE_SWEEP) {
-      const double old = (valid && tl) ? a.PSI[(size_t)gv * Q + t] : p;
-      r = fabs(p - old);
-    }
-    const double res = group_sum(tl ? r : 0.0);
+    if constexpr (MODE == MODE_SWEEP) r = tl ? fabs(p - old) : 0.0;
+    const double res = (MODE == MODE_SWEEP) ? group_sum(r) : 0.0;
     const double pm = group_max(tl ? p : -1.0);
-    const int best = group_min((tl && p == pm) ? t : QP);  // findmax: first maximum (sbm.jl:49)
-    if (valid && writer) {
+    const unsigned eq = group_bits(__ballot_sync(0xffffffffu, tl && (p == pm)));
+    if (valid) {
       if (tl) {
         a.PSI[(size_t)gv * Q + t] = p;
         acc.psi += p;
@@ -214,10 +211,10 @@ __device__ __forceinline__ void vertex_finish(const VertexArgs& a, bool valid, b
       if (t == 0) {
         acc.res += res;
         acc.vmax = fmax(acc.vmax, res);
-        if (!(S > 0.0)) atomicOr(a.status, 1);
-        if (best < Q) {
-          atomicAdd(&s_dr[best], (double)deg);  // integer-valued: exact in any order
-          atomicAdd(&s_nr[best], 1.0);
+        if (eq) {  // findmax: first maximum (sbm.jl:49); eq == 0 only when the marginal is NaN
+          const int best = __ffs(eq) - 1;
+          atomicAdd(&s_dr[best], (unsigned long long)deg);
+          atomicAdd(&s_nr[best], 1);
         }
       }
     }
@@ -226,13 +223,12 @@ __device__ __forceinline__ void vertex_finish(const VertexArgs& a, bool valid, b
 
 // Deterministic CTA reduction of the lane accumulators into this CTA's partial row.
 __device__ __forceinline__ void store_partials(const LaneAcc& acc, double* scratch /* smem, NT doubles */,
-                                               double* prow, const double* s_dr, const double* s_nr) {
+                                               double* prow, const unsigned long long* s_dr, const int* s_nr) {
   const int tid = threadIdx.x;
-  // sumPSI[t]: parity-0 lanes with component t, in thread order
   __syncthreads();
   scratch[tid] = acc.psi;
   __syncthreads();
-  if (tid < Q) {
+  if (tid < Q) {  // sumPSI[t]: lanes holding component t, in thread order
     double s = 0.0;
     for (int k = tid; k < NT; k += LV) s += scratch[k];
     prow[2 + tid] = s;
@@ -262,41 +258,41 @@ __device__ __forceinline__ void store_partials(const LaneAcc& acc, double* scrat
     prow[2 + 3 * Q] = m;
   }
   if (tid < Q) {
-    prow[2 + Q + tid] = s_dr[tid];
-    prow[2 + 2 * Q + tid] = s_nr[tid];
+    prow[2 + Q + tid] = (double)s_dr[tid];
+    prow[2 + 2 * Q + tid] = (double)s_nr[tid];
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // BP sweep over the tiled (degree <= 256) vertices.
 //   stage 1  one thread per incoming edge slot: load the 8Q-byte message, T = theta theta psi*Crs, rescale
-//   stage 2  2*QP lanes per vertex: product of the T's (two edge-parities in parallel), prior, clamp floor,
-//            marginal, residual
+//   stage 2  QP lanes per vertex: product of the T's, prior, clamp floor, marginal, residual
 //   stage 3  one thread per edge slot: cavity = product / own factor, clamp, normalise, damp, scatter to rev[e]
 template <int MODE>
 __global__ void __launch_bounds__(NT, (Q <= 8) ? 3 : 2) sbm_vertex_kernel(VertexArgs a) {
-  __shared__ __align__(32) double Tsm[TILE_E * Q];
+  __shared__ __align__(16) double Tsm[TILE_E * QS];
   __shared__ __align__(32) double Usm[TV * Q];
   __shared__ double ffS[TV];
   __shared__ double scratch[NT];
-  __shared__ double s_dr[Q], s_nr[Q];
+  __shared__ unsigned long long s_dr[Q];
+  __shared__ int s_nr[Q];
   __shared__ int ksm[TILE_E];
   __shared__ int fnS[TV];
 
   const int tid = threadIdx.x;
   if (tid < Q) {
-    s_dr[tid] = 0.0;
-    s_nr[tid] = 0.0;
+    s_dr[tid] = 0ull;
+    s_nr[tid] = 0;
   }
   LaneAcc acc;
-  const int sub = tid % LV, par = sub / QP, t = sub % QP;
+  const int t = tid % LV;
   const bool tl = t < Q;
+  const int tt = tl ? t : 0;
 
+  int4 td = (blockIdx.x < a.ntiles) ? a.tiles[blockIdx.x] : make_int4(0, 0, 0, 0);
   for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-    const int2 tv = a.tiles[tile];
-    const int v0 = tv.x, nv = tv.y - tv.x;
-    const int e0 = a.rowptr[v0];
-    const int ne = a.rowptr[v0 + nv] - e0;
+    const int v0 = td.x, nv = td.y, e0 = td.z, ne = td.w;
+    if (tile + (int)gridDim.x < a.ntiles) td = a.tiles[tile + gridDim.x];  // next descriptor, off the critical path
 
     // ---- stage 1 ----
     double T[Q];
@@ -307,11 +303,10 @@ __global__ void __launch_bounds__(NT, (Q <= 8) ? 3 : 2) sbm_vertex_kernel(Vertex
       load_vec<Q>(a.cur, e, psi);
       lv = a.lvtx[e];
       if constexpr (MODE == MODE_SWEEP) rv = a.rev[e];
-      double sc = 1.0;
-      if (a.dc) sc = a.theta[v0 + lv] * a.theta[a.col[e]];
-      edge_transform(psi, sc, T, ke, a.status);
+      const double sc = a.dc ? a.escale[e] : 1.0;
+      edge_transform(psi, sc, T, ke);
 #pragma unroll
-      for (int k = 0; k < Q; ++k) Tsm[tid * Q + k] = T[k];
+      for (int k = 0; k < Q; ++k) Tsm[tid * QS + k] = T[k];
       ksm[tid] = ke;
     }
     __syncthreads();
@@ -321,31 +316,31 @@ __global__ void __launch_bounds__(NT, (Q <= 8) ? 3 : 2) sbm_vertex_kernel(Vertex
       const int v = vb + tid / LV;
       const bool valid = v < nv;
       int b = 0, e = 0;
+      double th = 1.0, old = 0.0;
       if (valid) {
         b = a.rowptr[v0 + v] - e0;
         e = a.rowptr[v0 + v + 1] - e0;
+        if (a.dc) th = a.theta[v0 + v];
+        if (MODE == MODE_SWEEP && tl) old = a.PSI[(size_t)(v0 + v) * Q + t];
       }
       double prod = 1.0, prod2 = 1.0;
       int K = 0;
-      const int tt = tl ? t : 0;
-      int k = b + par;
-      for (; k + 2 < e; k += 4) {  // two independent chains per lane
-        prod *= Tsm[k * Q + tt];
-        prod2 *= Tsm[(k + 2) * Q + tt];
-        K += ksm[k] + ksm[k + 2];
+      int k = b;
+      for (; k + 1 < e; k += 2) {  // two independent chains
+        prod *= Tsm[k * QS + tt];
+        prod2 *= Tsm[(k + 1) * QS + tt];
+        K += ksm[k] + ksm[k + 1];
       }
       if (k < e) {
-        prod *= Tsm[k * Q + tt];
+        prod *= Tsm[k * QS + tt];
         K += ksm[k];
       }
       prod *= prod2;
-      prod *= __shfl_xor_sync(0xffffffffu, prod, QP);  // the other edge-parity
-      K += __shfl_xor_sync(0xffffffffu, K, QP);
       double u, ffrac;
       int fn;
-      vertex_finish<MODE>(a, valid, par == 0, v0 + v, e - b, t, prod, K, u, ffrac, fn, acc, s_dr, s_nr);
+      vertex_finish<MODE>(a, valid, v0 + v, e - b, t, th, old, prod, K, u, ffrac, fn, acc, s_dr, s_nr);
       if constexpr (MODE == MODE_SWEEP) {
-        if (valid && par == 0) {
+        if (valid) {
           if (tl) Usm[v * Q + t] = u;
           if (t == 0) {
             ffS[v] = ffrac;
@@ -387,15 +382,16 @@ __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base
   __shared__ double scratch[NT];
   __shared__ double ffSh;
   __shared__ int fnSh;
-  __shared__ double s_dr[Q], s_nr[Q];
+  __shared__ unsigned long long s_dr[Q];
+  __shared__ int s_nr[Q];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gv = a.hubs[blockIdx.x];
   const int e0 = a.rowptr[gv], e1 = a.rowptr[gv + 1];
   const double th = a.dc ? a.theta[gv] : 1.0;
   if (tid < Q) {
-    s_dr[tid] = 0.0;
-    s_nr[tid] = 0.0;
+    s_dr[tid] = 0ull;
+    s_nr[tid] = 0;
   }
 
   double pm[Q];
@@ -411,7 +407,7 @@ __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base
     int ke;
     load_vec<Q>(a.cur, e, psi);
     const double sc = a.dc ? th * a.theta[a.col[e]] : 1.0;
-    edge_transform(psi, sc, T, ke, a.status);
+    edge_transform(psi, sc, T, ke);
     ksum += ke;
 #pragma unroll
     for (int t = 0; t < Q; ++t) {
@@ -459,10 +455,12 @@ __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base
     const int kcc = (kc == -(1 << 30)) ? 0 : kc;
     const int d = k - kcc;  // <= 0 for live components
     const double prod = (d < -1022 || m == 0.0) ? 0.0 : m * pow2i(d > 0 ? 0 : d);
+    const bool writer = lane < QP;
+    const double old = (MODE == MODE_SWEEP && tl) ? a.PSI[(size_t)gv * Q + t] : 0.0;
     double u, ffrac;
     int fn;
-    vertex_finish<MODE>(a, true, lane < QP, gv, e1 - e0, t, prod, Ks + kcc, u, ffrac, fn, acc, s_dr, s_nr);
-    if (lane < QP) {
+    vertex_finish<MODE>(a, writer, gv, e1 - e0, t, th, old, prod, Ks + kcc, u, ffrac, fn, acc, s_dr, s_nr);
+    if (writer) {
       if (tl) Ush[t] = u;
       if (t == 0) {
         ffSh = ffrac;
@@ -478,12 +476,27 @@ __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base
       int ke;
       load_vec<Q>(a.cur, e, psi);
       const double sc = a.dc ? th * a.theta[a.col[e]] : 1.0;
-      edge_transform(psi, sc, T, ke, a.status);
+      edge_transform(psi, sc, T, ke);
       emit_message(a, Ush, T, ffSh, fnSh + ke, a.rev[e]);
     }
   }
-  // lanes 0..QP-1 of warp 0 carry the accumulators; all other threads hold zeros
+  // warp 0 carries the accumulators (LaneAcc of every other thread is zero); its group layout matches LV = QP
   store_partials(acc, scratch, a.partials + (size_t)(part_base + blockIdx.x) * PSTRIDE, s_dr, s_nr);
+}
+
+// theta_row * theta_col per tiled edge slot, refreshed after update_theta (degree-corrected runs): keeps the
+// random theta gather out of the sweep (one coalesced 8-byte read there instead of col + a dependent gather).
+__global__ void __launch_bounds__(NT) sbm_escale_kernel(const int4* __restrict__ tiles, int ntiles,
+                                                        const unsigned char* __restrict__ lvtx,
+                                                        const int* __restrict__ col, const double* __restrict__ theta,
+                                                        double* __restrict__ escale) {
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int4 td = tiles[tile];
+    if ((int)threadIdx.x < td.w) {
+      const int e = td.z + threadIdx.x;
+      escale[e] = theta[td.x + lvtx[e]] * theta[col[e]];
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -503,7 +516,10 @@ __global__ void sbm_reduce_vertex(SbmState* st, const double* partials, int nrow
   }
   __syncthreads();
   if (mode == MODE_LOGZ) {
-    if (tid == 0) st->sumlogZi = tot[1];
+    if (tid == 0) {
+      st->sumlogZi = tot[1];
+      if (!(tot[1] == tot[1])) st->status |= 1;
+    }
     return;
   }
   if (tid < Q) {
@@ -521,7 +537,9 @@ __global__ void sbm_reduce_vertex(SbmState* st, const double* partials, int nrow
   if (tid == 0 && mode == MODE_SWEEP) {
     st->conv = tot[0] / N;  // sbm.jl:123
     st->maxd = tot[2 + 3 * Q];
+    if (!(tot[0] == tot[0]) || !(tot[0] < INFINITY)) st->status |= 1;  // NaN/Inf reached the marginals
   }
+
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -823,6 +841,7 @@ VertexArgs vertex_args(gbx_sbm* h) {
   a.col = h->col;
   a.rev = h->rev;
   a.lvtx = h->lvtx;
+  a.escale = h->escale;
   a.tiles = h->tiles;
   a.ntiles = h->ntiles;
   a.hubs = h->hubs;
@@ -891,6 +910,11 @@ int op_theta(gbx_sbm* h) {
   sbm_theta_kernel<<<h->grid_theta, NT, 0, h->stream>>>(h->st, h->rowptr, (int)h->n, h->PSI, h->theta, h->part_theta);
   sbm_reduce_theta<<<1, 32, 0, h->stream>>>(h->st, h->part_theta, h->grid_theta);
   h->launches += 2;
+  if (h->ntiles > 0) {
+    sbm_escale_kernel<<<std::min(h->ntiles, h->num_sms * 8), NT, 0, h->stream>>>(h->tiles, h->ntiles, h->lvtx, h->col,
+                                                                               h->theta, h->escale);
+    h->launches++;
+  }
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
 }
