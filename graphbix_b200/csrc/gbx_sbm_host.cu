@@ -180,6 +180,10 @@ int gbx_sbm_create(gbx_sbm** out, int device, int64_t n, int64_t K, const int64_
       rev[(size_t)e] = (int)(it - col.data());
     }
   }
+  std::vector<int2> und;
+  und.reserve((size_t)K / 2);
+  for (int64_t e = 0; e < K; ++e)
+    if (rev[(size_t)e] < e) und.push_back(make_int2((int)e, rev[(size_t)e]));
   // ---- tile schedule: runs of consecutive vertices with <= TILE_E slots and <= TV vertices; hubs apart ----
   const int TV = tile_vertices(q);
   std::vector<int4> tiles;
@@ -232,6 +236,8 @@ int gbx_sbm_create(gbx_sbm** out, int device, int64_t n, int64_t K, const int64_
     GBX_TRY(dev_alloc(h, &h->rev, (size_t)K));
     GBX_TRY(dev_alloc(h, &h->lvtx, (size_t)K));
     GBX_TRY(dev_alloc(h, &h->escale, (size_t)K));
+    GBX_TRY(dev_alloc(h, &h->und, und.size()));
+    GBX_CUDA_TRY(cudaMemcpy(h->und, und.data(), und.size() * sizeof(int2), cudaMemcpyHostToDevice));
     GBX_TRY(dev_alloc(h, &h->slot_of_link, (size_t)K));
     GBX_TRY(dev_alloc(h, &h->tiles, tiles.size()));
     GBX_TRY(dev_alloc(h, &h->hubs, hubs.size()));
@@ -256,8 +262,8 @@ int gbx_sbm_create(gbx_sbm** out, int device, int64_t n, int64_t K, const int64_
     occ = std::max(occ, 1);
     occm = std::max(occm, 1);
     h->grid_vertex = std::max(1, std::min(h->ntiles, h->num_sms * occ));
-    const int64_t eblocks = std::max<int64_t>(1, (K + NT - 1) / NT);
-    h->grid_mstep = (int)std::min<int64_t>(eblocks, (int64_t)h->num_sms * occm);
+    const int64_t eblocks = std::max<int64_t>(1, (K / 2 + NT - 1) / NT);
+    h->grid_mstep = (int)std::min<int64_t>(std::max<int64_t>(1, (K / 2 + 319) / 320), (int64_t)h->num_sms * occm);
     h->grid_fe = (int)std::min<int64_t>(eblocks, (int64_t)h->num_sms * 2);
     h->grid_theta = (int)std::min<int64_t>(std::max<int64_t>(1, (n + NT - 1) / NT), (int64_t)h->num_sms * 4);
     GBX_TRY(dev_alloc(h, &h->part_vertex, (size_t)(h->grid_vertex + h->nhubs) * PSTRIDE));
@@ -286,6 +292,7 @@ int gbx_sbm_destroy(gbx_sbm* h) {
   cudaFree(h->rev);
   cudaFree(h->lvtx);
   cudaFree(h->escale);
+  cudaFree(h->und);
   cudaFree(h->slot_of_link);
   cudaFree(h->tiles);
   cudaFree(h->hubs);

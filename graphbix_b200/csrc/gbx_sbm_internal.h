@@ -56,6 +56,7 @@ struct gbx_sbm {
   unsigned char* lvtx = nullptr;  // per edge slot: index of its vertex inside its tile
   int4* tiles = nullptr;          // (first vertex, #vertices, first edge slot, #edge slots)
   double* escale = nullptr;       // per edge slot theta_row * theta_col (all ones until update_theta runs)
+  int2* und = nullptr;            // every undirected edge once: (slot e, slot rev[e]) with rev[e] < e
   int ntiles = 0, nhubs = 0;
   // state (device)
   double *msg[2] = {nullptr, nullptr}, *PSI = nullptr, *theta = nullptr;

@@ -97,6 +97,23 @@ __device__ __forceinline__ double group_sum(double x) {
   return x;
 }
 
+// Sum (or max) of column `c` of a [nrows][stride] array of per-CTA partials by one warp, in a fixed order.
+template <bool MAX = false>
+__device__ __forceinline__ double warp_column_reduce(const double* __restrict__ partials, int nrows, int stride, int c) {
+  const int lane = threadIdx.x & 31;
+  double s = 0.0;
+  for (int r = lane; r < nrows; r += 32) {
+    const double x = partials[(size_t)r * stride + c];
+    s = MAX ? fmax(s, x) : s + x;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double y = __shfl_xor_sync(0xffffffffu, s, o);
+    s = MAX ? fmax(s, y) : s + y;
+  }
+  return s;
+}
+
 // T[t] = theta_i theta_s (psi * Crs)[t]  (sbm.jl:87), rescaled by 2^-ke so that max_t T[t] is in [1,2).
 // A zero / NaN / Inf factor is left as it is (ke = 0): like log(0) in the reference it turns the messages that
 // depend on it into NaN, which reaches the residual and is reported as `nonfinite` ("overflow", sbm.jl:355).
@@ -264,19 +281,56 @@ __device__ __forceinline__ void store_partials(const LaneAcc& acc, double* scrat
 }
 
 // ---------------------------------------------------------------------------------------------
-// BP sweep over the tiled (degree <= 256) vertices.
-//   stage 1  one thread per incoming edge slot: load the 8Q-byte message, T = theta theta psi*Crs, rescale
-//   stage 2  QP lanes per vertex: product of the T's, prior, clamp floor, marginal, residual
+// BP sweep over the tiled (degree <= 256) vertices.  Persistent CTAs, software-pipelined over tiles: the global
+// loads of tile k+1 (messages, rev, local vertex id, theta scale, row bounds, old marginals) are issued before
+// the arithmetic of tile k, so HBM latency hides behind compute instead of behind occupancy.
+//   stage 1  one thread per incoming edge slot: T = theta theta psi*Crs, rescaled by 2^-ke        -> smem
+//   stage 2  QP lanes per vertex: product of the T's, prior, clamp floor, marginal, residual         -> smem
 //   stage 3  one thread per edge slot: cavity = product / own factor, clamp, normalise, damp, scatter to rev[e]
+struct EdgeRegs {   // what an edge-slot thread needs from global memory for one tile
+  double psi[Q];
+  double sc;
+  int lv, rv;
+};
+struct VertRegs {   // what an aggregation lane needs from global memory for the first round of one tile
+  double th, old;
+  int b, e;
+};
+
 template <int MODE>
-__global__ void __launch_bounds__(NT, (Q <= 8) ? 3 : 2) sbm_vertex_kernel(VertexArgs a) {
+__device__ __forceinline__ void load_edge(const VertexArgs& a, const int4& td, EdgeRegs& r) {
+  if ((int)threadIdx.x < td.w) {
+    const int e = td.z + threadIdx.x;
+    load_vec<Q>(a.cur, e, r.psi);
+    r.lv = a.lvtx[e];
+    if constexpr (MODE == MODE_SWEEP) r.rv = a.rev[e];
+    r.sc = a.dc ? a.escale[e] : 1.0;
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void load_vert(const VertexArgs& a, const int4& td, int v, int t, VertRegs& r) {
+  r.b = 0;
+  r.e = 0;
+  r.th = 1.0;
+  r.old = 0.0;
+  if (v < td.y) {
+    r.b = a.rowptr[td.x + v] - td.z;
+    r.e = a.rowptr[td.x + v + 1] - td.z;
+    if (a.dc) r.th = a.theta[td.x + v];
+    if (MODE == MODE_SWEEP && t < Q) r.old = a.PSI[(size_t)(td.x + v) * Q + t];
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NT, 2) sbm_vertex_kernel(VertexArgs a) {
   __shared__ __align__(16) double Tsm[TILE_E * QS];
   __shared__ __align__(32) double Usm[TV * Q];
   __shared__ double ffS[TV];
   __shared__ double scratch[NT];
   __shared__ unsigned long long s_dr[Q];
   __shared__ int s_nr[Q];
-  __shared__ int ksm[TILE_E];
+  __shared__ int Ksm[TV];
   __shared__ int fnS[TV];
 
   const int tid = threadIdx.x;
@@ -284,61 +338,65 @@ __global__ void __launch_bounds__(NT, (Q <= 8) ? 3 : 2) sbm_vertex_kernel(Vertex
     s_dr[tid] = 0ull;
     s_nr[tid] = 0;
   }
+  if (tid < TV) Ksm[tid] = 0;
   LaneAcc acc;
   const int t = tid % LV;
   const bool tl = t < Q;
   const int tt = tl ? t : 0;
+  const int vlane = tid / LV;                // vertex handled by this lane in an aggregation round
+  const int vwarp = (tid & ~31) / LV;        // first vertex of this warp in a round
 
-  int4 td = (blockIdx.x < a.ntiles) ? a.tiles[blockIdx.x] : make_int4(0, 0, 0, 0);
+  const int4 zero4 = make_int4(0, 0, 0, 0);
+  int4 tdN = (blockIdx.x < a.ntiles) ? a.tiles[blockIdx.x] : zero4;
+  EdgeRegs en;
+  VertRegs vn;
+  load_edge<MODE>(a, tdN, en);
+  load_vert<MODE>(a, tdN, vlane, t, vn);
+  __syncthreads();
+
   for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-    const int v0 = td.x, nv = td.y, e0 = td.z, ne = td.w;
-    if (tile + (int)gridDim.x < a.ntiles) td = a.tiles[tile + gridDim.x];  // next descriptor, off the critical path
-
-    // ---- stage 1 ----
+    const int4 td = tdN;
+    const int v0 = td.x, nv = td.y, ne = td.w;
+    // ---- stage 1: consume the prefetched registers ----
     double T[Q];
-    int ke = 0, lv = 0, rv = 0;
+    int ke = 0;
+    const int lv = en.lv, rv = en.rv;
     if (tid < ne) {
-      const int e = e0 + tid;
-      double psi[Q];
-      load_vec<Q>(a.cur, e, psi);
-      lv = a.lvtx[e];
-      if constexpr (MODE == MODE_SWEEP) rv = a.rev[e];
-      const double sc = a.dc ? a.escale[e] : 1.0;
-      edge_transform(psi, sc, T, ke);
+      edge_transform(en.psi, en.sc, T, ke);
 #pragma unroll
       for (int k = 0; k < Q; ++k) Tsm[tid * QS + k] = T[k];
-      ksm[tid] = ke;
+      atomicAdd(&Ksm[lv], ke);
     }
+    const VertRegs vc = vn;
+    // ---- issue the loads of the next tile (they complete while this tile is being computed) ----
+    const int nxt = tile + gridDim.x;
+    tdN = (nxt < a.ntiles) ? a.tiles[nxt] : zero4;
+    load_edge<MODE>(a, tdN, en);
+    load_vert<MODE>(a, tdN, vlane, t, vn);
     __syncthreads();
 
     // ---- stage 2 ----
     for (int vb = 0; vb < nv; vb += VPR) {
-      const int v = vb + tid / LV;
+      if (vb + vwarp >= nv) break;  // warp-uniform: no vertex left for this warp
+      const int v = vb + vlane;
       const bool valid = v < nv;
-      int b = 0, e = 0;
-      double th = 1.0, old = 0.0;
-      if (valid) {
-        b = a.rowptr[v0 + v] - e0;
-        e = a.rowptr[v0 + v + 1] - e0;
-        if (a.dc) th = a.theta[v0 + v];
-        if (MODE == MODE_SWEEP && tl) old = a.PSI[(size_t)(v0 + v) * Q + t];
-      }
+      VertRegs vr = vc;
+      if (vb > 0) load_vert<MODE>(a, td, v, t, vr);  // tiles with more than VPR vertices (low degrees)
+      const double* p = &Tsm[vr.b * QS + tt];
+      const double* pe = &Tsm[vr.e * QS + tt];
       double prod = 1.0, prod2 = 1.0;
-      int K = 0;
-      int k = b;
-      for (; k + 1 < e; k += 2) {  // two independent chains
-        prod *= Tsm[k * QS + tt];
-        prod2 *= Tsm[(k + 1) * QS + tt];
-        K += ksm[k] + ksm[k + 1];
+      for (; p + QS < pe; p += 2 * QS) {  // two independent chains
+        prod *= p[0];
+        prod2 *= p[QS];
       }
-      if (k < e) {
-        prod *= Tsm[k * QS + tt];
-        K += ksm[k];
-      }
+      if (p < pe) prod *= p[0];
       prod *= prod2;
+      const int K = valid ? Ksm[v] : 0;
+      __syncwarp();
+      if (valid && t == 0) Ksm[v] = 0;  // ready for the next tile
       double u, ffrac;
       int fn;
-      vertex_finish<MODE>(a, valid, v0 + v, e - b, t, th, old, prod, K, u, ffrac, fn, acc, s_dr, s_nr);
+      vertex_finish<MODE>(a, valid, v0 + v, vr.e - vr.b, t, vr.th, vr.old, prod, K, u, ffrac, fn, acc, s_dr, s_nr);
       if constexpr (MODE == MODE_SWEEP) {
         if (valid) {
           if (tl) Usm[v * Q + t] = u;
@@ -505,14 +563,10 @@ __global__ void sbm_reduce_vertex(SbmState* st, const double* partials, int nrow
                                   double N) {
   __shared__ double tot[PSTRIDE];
   const int tid = threadIdx.x;
-  if (tid < 3 * Q + 3) {
-    double s = 0.0;
-    if (tid == 2 + 3 * Q) {
-      for (int r = 0; r < nrows; ++r) s = fmax(s, partials[(size_t)r * PSTRIDE + tid]);
-    } else {
-      for (int r = 0; r < nrows; ++r) s += partials[(size_t)r * PSTRIDE + tid];
-    }
-    tot[tid] = s;
+  for (int c = tid >> 5; c < 3 * Q + 3; c += blockDim.x >> 5) {
+    const double v = (c == 2 + 3 * Q) ? warp_column_reduce<true>(partials, nrows, PSTRIDE, c)
+                                      : warp_column_reduce<false>(partials, nrows, PSTRIDE, c);
+    if ((tid & 31) == 0) tot[c] = v;
   }
   __syncthreads();
   if (mode == MODE_LOGZ) {
@@ -556,58 +610,92 @@ constexpr int MS_R = mstep_rows(Q);
 constexpr int MS_NCH = (Q + MS_R - 1) / MS_R;
 constexpr int MS_STRIDE = MS_NCH * MS_R * Q;
 
-__global__ void __launch_bounds__(NT) sbm_mstep_kernel(const int* __restrict__ rev, long long K,
-                                                       const double* __restrict__ psi, double* partials,
-                                                       int* status) {
-  __shared__ double red[(NT / 32) * MS_R * Q];
-  const long long stride = (long long)gridDim.x * NT;
+constexpr int NTM = 320;  // one CTA per SM: 36 accumulators + two edges' messages in registers per thread
+
+template <int NV>
+__device__ __forceinline__ void block_reduce_store_m(double (&v)[NV], double* red, double* dst) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double x = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) red[warp * NV + k] = x;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < NV; k += NTM) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < NTM / 32; ++w) s += red[w * NV + k];
+    dst[k] = s;
+  }
+  __syncthreads();
+}
+
+// `und` lists every undirected edge once as (slot e, slot rev[e]) with rev[e] < e.  Loads of the next edge are
+// issued before the arithmetic of the current one (two edges in flight per thread).
+__global__ void __launch_bounds__(NTM, 1) sbm_mstep_kernel(const int2* __restrict__ und, long long L,
+                                                          const double* __restrict__ psi, double* partials) {
+  __shared__ double red[(NTM / 32) * MS_R * Q];
+  const long long stride = (long long)gridDim.x * NTM;
 #pragma unroll
   for (int ch = 0; ch < MS_NCH; ++ch) {
     double acc[MS_R * Q];
 #pragma unroll
     for (int k = 0; k < MS_R * Q; ++k) acc[k] = 0.0;
-    for (long long e = (long long)blockIdx.x * NT + threadIdx.x; e < K; e += stride) {
-      const int r = rev[e];
-      if (r < e) {
-        double a[Q], b[Q];
-        load_vec<Q>(psi, e, b);  // col -> row
-        load_vec<Q>(psi, r, a);  // row -> col
-        double Z = 0.0;
+    long long i = (long long)blockIdx.x * NTM + threadIdx.x;
+    double an[Q], bn[Q];
+    if (i < L) {
+      const int2 er = und[i];
+      load_vec<Q>(psi, er.x, bn);  // col -> row
+      load_vec<Q>(psi, er.y, an);  // row -> col
+    }
+    while (i < L) {
+      double a[Q], b[Q];
 #pragma unroll
-        for (int s = 0; s < Q; ++s) {
-          double cb = 0.0;
+      for (int t = 0; t < Q; ++t) {
+        a[t] = an[t];
+        b[t] = bn[t];
+      }
+      i += stride;
+      if (i < L) {
+        const int2 er = und[i];
+        load_vec<Q>(psi, er.x, bn);
+        load_vec<Q>(psi, er.y, an);
+      }
+      double Z = 0.0;
 #pragma unroll
-          for (int t = 0; t < Q; ++t) cb = fma(c_P.C[s * Q + t], b[t], cb);
-          Z = fma(a[s], cb, Z);
-        }
-        const double invZ = 1.0 / Z;
-        if (!(invZ > 0.0) || !(invZ < INFINITY)) atomicOr(status, 1);
+      for (int s = 0; s < Q; ++s) {
+        double cb = 0.0;
 #pragma unroll
-        for (int t = 0; t < Q; ++t) a[t] *= invZ;
+        for (int t = 0; t < Q; ++t) cb = fma(c_P.C[s * Q + t], b[t], cb);
+        Z = fma(a[s], cb, Z);
+      }
+      const double invZ = 1.0 / Z;  // 0, NaN or Inf here ends up in Crs and is reported by the caller's checks
 #pragma unroll
-        for (int rr = 0; rr < MS_R; ++rr) {
-          const int s = ch * MS_R + rr;
-          if (s < Q) {
+      for (int t = 0; t < Q; ++t) a[t] *= invZ;
 #pragma unroll
-            for (int t = s; t < Q; ++t) {
-              acc[rr * Q + t] = fma(a[s], b[t], acc[rr * Q + t]);
-              acc[rr * Q + t] = fma(a[t], b[s], acc[rr * Q + t]);
-            }
+      for (int rr = 0; rr < MS_R; ++rr) {
+        const int s = ch * MS_R + rr;
+        if (s < Q) {
+#pragma unroll
+          for (int t = s; t < Q; ++t) {
+            acc[rr * Q + t] = fma(a[s], b[t], acc[rr * Q + t]);
+            acc[rr * Q + t] = fma(a[t], b[s], acc[rr * Q + t]);
           }
         }
       }
     }
-    block_reduce_store<MS_R * Q>(acc, red, partials + (size_t)blockIdx.x * MS_STRIDE + ch * MS_R * Q);
+    block_reduce_store_m<MS_R * Q>(acc, red, partials + (size_t)blockIdx.x * MS_STRIDE + ch * MS_R * Q);
   }
 }
 
 __global__ void sbm_reduce_mstep(SbmState* st, const double* partials, int nrows, double lr, double maxCrs, double N) {
   __shared__ double G[Q * Q];
   const int tid = threadIdx.x;
-  if (tid < Q * Q) {
-    double s = 0.0;
-    for (int r = 0; r < nrows; ++r) s += partials[(size_t)r * MS_STRIDE + tid];
-    G[tid] = s;
+  for (int c = tid >> 5; c < Q * Q; c += blockDim.x >> 5) {
+    const double v = warp_column_reduce(partials, nrows, MS_STRIDE, c);
+    if ((tid & 31) == 0) G[c] = v;
   }
   __syncthreads();
   if (tid < Q * Q) {
@@ -616,6 +704,7 @@ __global__ void sbm_reduce_mstep(SbmState* st, const double* partials, int nrows
     const double Cn = Cold * (s <= t ? G[s * Q + t] : G[t * Q + s]);
     double c = lr * Cn / (N * st->gr[s] * st->gr[t]) + (1.0 - lr) * Cold;  // sbm.jl:137
     if (c > maxCrs) c = maxCrs; else if (c < 0.0) c = 0.0;                  // sbm.jl:138-146
+    if (!(c == c)) st->status |= 1;
     st->C[tid] = c;
   }
 }
@@ -649,11 +738,9 @@ __global__ void __launch_bounds__(NT) sbm_theta_kernel(const SbmState* st, const
 }
 
 __global__ void sbm_reduce_theta(SbmState* st, const double* partials, int nrows) {
-  const int tid = threadIdx.x;
-  if (tid < Q) {
-    double s = 0.0;
-    for (int r = 0; r < nrows; ++r) s += partials[(size_t)r * Q + tid];
-    st->Stheta[tid] = s;
+  for (int c = threadIdx.x >> 5; c < Q; c += blockDim.x >> 5) {
+    const double v = warp_column_reduce(partials, nrows, Q, c);
+    if ((threadIdx.x & 31) == 0) st->Stheta[c] = v;
   }
 }
 
@@ -697,8 +784,8 @@ __global__ void sbm_prepare(SbmState* st, SbmParams* out, double N, int zero_h, 
 // freeenergy(), sbm.jl:162-200: per undirected edge log Z_ij and the three Gibbs/MAP terms.
 // PASS 0 accumulates sums, PASS 1 sums of squared deviations from the means (unbiased var, sbm.jl:208-211).
 template <int PASS>
-__global__ void __launch_bounds__(NT) sbm_fe_kernel(const SbmState* st, const int* __restrict__ rev,
-                                                    const int* __restrict__ col, long long K,
+__global__ void __launch_bounds__(NT) sbm_fe_kernel(const SbmState* st, const int2* __restrict__ und,
+                                                    const int* __restrict__ col, long long L,
                                                     const double* __restrict__ psi, const double* __restrict__ theta,
                                                     int dc, double* partials) {
   __shared__ double red[(NT / 32) * 4];
@@ -706,9 +793,10 @@ __global__ void __launch_bounds__(NT) sbm_fe_kernel(const SbmState* st, const in
   double mean[4] = {0.0, 0.0, 0.0, 0.0};
   if (PASS == 1)
     for (int k = 0; k < 4; ++k) mean[k] = st->cvmean[k];
-  for (long long e = (long long)blockIdx.x * NT + threadIdx.x; e < K; e += (long long)gridDim.x * NT) {
-    const int r = rev[e];
-    if (r < e) {
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < L; i += (long long)gridDim.x * NT) {
+    {
+      const int2 er = und[i];
+      const int e = er.x, r = er.y;
       double a[Q], b[Q];
       load_vec<Q>(psi, e, b);  // j -> i   (i = row of e, j = col[e])
       load_vec<Q>(psi, r, a);  // i -> j
@@ -747,15 +835,16 @@ __global__ void __launch_bounds__(NT) sbm_fe_kernel(const SbmState* st, const in
 }
 
 __global__ void sbm_reduce_fe(SbmState* st, const double* partials, int nrows, int pass, double L) {
-  const int tid = threadIdx.x;
-  if (tid < 4) {
-    double s = 0.0;
-    for (int r = 0; r < nrows; ++r) s += partials[(size_t)r * 4 + tid];
-    if (pass == 0) {
-      st->cvsum[tid] = s;
-      st->cvmean[tid] = s / L;
-    } else {
-      st->cvss[tid] = s;
+  const int c = threadIdx.x >> 5;
+  if (c < 4) {
+    const double s = warp_column_reduce(partials, nrows, 4, c);
+    if ((threadIdx.x & 31) == 0) {
+      if (pass == 0) {
+        st->cvsum[c] = s;
+        st->cvmean[c] = s / L;
+      } else {
+        st->cvss[c] = s;
+      }
     }
   }
 }
@@ -880,7 +969,7 @@ int op_vertex_pass(gbx_sbm* h, int mode) {
 int op_reduce_vertex(gbx_sbm* h, int mode) {
   const int nrows = (h->ntiles > 0 ? h->grid_vertex : 0) + h->nhubs;
   const double* base = h->part_vertex + (h->ntiles > 0 ? 0 : (size_t)h->grid_vertex * PSTRIDE);
-  sbm_reduce_vertex<<<1, 64, 0, h->stream>>>(h->st, base, nrows, mode, h->opt.priorlearning,
+  sbm_reduce_vertex<<<1, 256, 0, h->stream>>>(h->st, base, nrows, mode, h->opt.priorlearning,
                                              h->opt.degreecorrection, (double)h->n);
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
@@ -897,8 +986,7 @@ int op_prepare(gbx_sbm* h, int zero_h, int gr_from_sum) {
 
 int op_mstep(gbx_sbm* h) {
   const double maxCrs = h->opt.maxCrs > 0 ? h->opt.maxCrs : (double)h->n;
-  sbm_mstep_kernel<<<h->grid_mstep, NT, 0, h->stream>>>(h->rev, (long long)h->K, h->msg[h->cur], h->part_mstep,
-                                                        &h->st->status);
+  sbm_mstep_kernel<<<h->grid_mstep, NTM, 0, h->stream>>>(h->und, (long long)(h->K / 2), h->msg[h->cur], h->part_mstep);
   sbm_reduce_mstep<<<1, 256, 0, h->stream>>>(h->st, h->part_mstep, h->grid_mstep, h->opt.learningrate, maxCrs,
                                              (double)h->n);
   h->launches += 2;
@@ -908,7 +996,7 @@ int op_mstep(gbx_sbm* h) {
 
 int op_theta(gbx_sbm* h) {
   sbm_theta_kernel<<<h->grid_theta, NT, 0, h->stream>>>(h->st, h->rowptr, (int)h->n, h->PSI, h->theta, h->part_theta);
-  sbm_reduce_theta<<<1, 32, 0, h->stream>>>(h->st, h->part_theta, h->grid_theta);
+  sbm_reduce_theta<<<1, 256, 0, h->stream>>>(h->st, h->part_theta, h->grid_theta);
   h->launches += 2;
   if (h->ntiles > 0) {
     sbm_escale_kernel<<<std::min(h->ntiles, h->num_sms * 8), NT, 0, h->stream>>>(h->tiles, h->ntiles, h->lvtx, h->col,
@@ -925,12 +1013,12 @@ int op_free_energy(gbx_sbm* h) {
   if (rc != GBX_OK) return rc;
   rc = op_reduce_vertex(h, MODE_LOGZ);
   if (rc != GBX_OK) return rc;
-  sbm_fe_kernel<0><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->rev, h->col, (long long)h->K, h->msg[h->cur], h->theta,
+  sbm_fe_kernel<0><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->und, h->col, (long long)(h->K / 2), h->msg[h->cur], h->theta,
                                                      h->opt.degreecorrection, h->part_fe);
-  sbm_reduce_fe<<<1, 32, 0, h->stream>>>(h->st, h->part_fe, h->grid_fe, 0, L);
-  sbm_fe_kernel<1><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->rev, h->col, (long long)h->K, h->msg[h->cur], h->theta,
+  sbm_reduce_fe<<<1, 128, 0, h->stream>>>(h->st, h->part_fe, h->grid_fe, 0, L);
+  sbm_fe_kernel<1><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->und, h->col, (long long)(h->K / 2), h->msg[h->cur], h->theta,
                                                      h->opt.degreecorrection, h->part_fe);
-  sbm_reduce_fe<<<1, 32, 0, h->stream>>>(h->st, h->part_fe, h->grid_fe, 1, L);
+  sbm_reduce_fe<<<1, 128, 0, h->stream>>>(h->st, h->part_fe, h->grid_fe, 1, L);
   sbm_finalize<<<1, 32, 0, h->stream>>>(h->st, (double)h->n, L);
   h->launches += 5;
   GBX_CUDA_TRY(cudaGetLastError());
@@ -964,7 +1052,7 @@ int op_assignment(gbx_sbm* h, int* dev_block) {
 
 int op_occupancy(int* vertex_occ, int* mstep_occ) {
   GBX_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(vertex_occ, sbm_vertex_kernel<MODE_SWEEP>, NT, 0));
-  GBX_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(mstep_occ, sbm_mstep_kernel, NT, 0));
+  GBX_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(mstep_occ, sbm_mstep_kernel, NTM, 0));
   return GBX_OK;
 }
 
