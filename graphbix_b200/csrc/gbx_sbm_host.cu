@@ -10,6 +10,7 @@
 //   * PSI (N x q), theta (N); tiles = runs of consecutive vertices with <= 256 edge slots (one CTA iteration
 //     each, one thread per slot); vertices with more than 256 edges ("hubs") get a CTA each.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -212,6 +213,22 @@ int gbx_sbm_create(gbx_sbm** out, int device, int64_t n, int64_t K, const int64_
     }
   }
 
+  // ---- processing order of the group kernel: non-hub vertices by ceil(degree / QP), largest first ----
+  int qp = 1;
+  while (qp < q) qp <<= 1;
+  std::vector<int> vorder;
+  {
+    const int nclass = TILE_E / qp + 2;
+    std::vector<int> cnt((size_t)nclass + 1, 0);
+    auto cls = [&](int64_t v) { return nclass - 1 - (rowptr[(size_t)v + 1] - rowptr[(size_t)v] + qp - 1) / qp; };
+    for (int64_t v = 0; v < n; ++v)
+      if (rowptr[(size_t)v + 1] - rowptr[(size_t)v] <= TILE_E) cnt[(size_t)cls(v) + 1]++;
+    for (int c = 0; c < nclass; ++c) cnt[(size_t)c + 1] += cnt[(size_t)c];
+    vorder.resize((size_t)cnt[(size_t)nclass]);
+    for (int64_t v = 0; v < n; ++v)
+      if (rowptr[(size_t)v + 1] - rowptr[(size_t)v] <= TILE_E) vorder[(size_t)cnt[(size_t)cls(v)]++] = (int)v;
+  }
+
   gbx_sbm* h = new (std::nothrow) gbx_sbm();
   if (!h) return fail_invalid("out of host memory");
   h->device = device;
@@ -220,6 +237,11 @@ int gbx_sbm_create(gbx_sbm** out, int device, int64_t n, int64_t K, const int64_
   h->K = K;
   h->ops = ops;
   h->ntiles = (int)tiles.size();
+  h->nmain = (int)vorder.size();
+  {
+    const char* env = getenv("GBX_SWEEP");
+    h->sweep_variant = (env && std::string(env) == "group") ? 0 : 1;
+  }
   h->nhubs = (int)hubs.size();
   gbx_sbm_default_options(&h->opt);
   auto body = [&]() -> int {
@@ -240,6 +262,8 @@ int gbx_sbm_create(gbx_sbm** out, int device, int64_t n, int64_t K, const int64_
     GBX_CUDA_TRY(cudaMemcpy(h->und, und.data(), und.size() * sizeof(int2), cudaMemcpyHostToDevice));
     GBX_TRY(dev_alloc(h, &h->slot_of_link, (size_t)K));
     GBX_TRY(dev_alloc(h, &h->tiles, tiles.size()));
+    GBX_TRY(dev_alloc(h, &h->vorder, vorder.size()));
+    GBX_CUDA_TRY(cudaMemcpy(h->vorder, vorder.data(), vorder.size() * sizeof(int), cudaMemcpyHostToDevice));
     GBX_TRY(dev_alloc(h, &h->hubs, hubs.size()));
     GBX_TRY(dev_alloc(h, &h->msg[0], (size_t)K * q));
     GBX_TRY(dev_alloc(h, &h->msg[1], (size_t)K * q));
@@ -258,10 +282,14 @@ int gbx_sbm_create(gbx_sbm** out, int device, int64_t n, int64_t K, const int64_
     GBX_CUDA_TRY(cudaMallocHost((void**)&h->h_state, sizeof(SbmState)));
     // persistent grids: a whole number of CTAs per SM
     int occ = 1, occm = 1;
-    GBX_TRY(ops->occupancy(&occ, &occm));
+    GBX_TRY(ops->occupancy(h->sweep_variant, &occ, &occm));
     occ = std::max(occ, 1);
     occm = std::max(occm, 1);
-    h->grid_vertex = std::max(1, std::min(h->ntiles, h->num_sms * occ));
+    {
+      const int gpb = NT / qp;  // vertices per CTA step of the group kernel
+      const int work = h->sweep_variant == 0 ? (h->nmain + gpb - 1) / gpb : h->ntiles;
+      h->grid_vertex = std::max(1, std::min(work, h->num_sms * occ));
+    }
     const int64_t eblocks = std::max<int64_t>(1, (K / 2 + NT - 1) / NT);
     h->grid_mstep = (int)std::min<int64_t>(std::max<int64_t>(1, (K / 2 + 319) / 320), (int64_t)h->num_sms * occm);
     h->grid_fe = (int)std::min<int64_t>(eblocks, (int64_t)h->num_sms * 2);
@@ -295,6 +323,7 @@ int gbx_sbm_destroy(gbx_sbm* h) {
   cudaFree(h->und);
   cudaFree(h->slot_of_link);
   cudaFree(h->tiles);
+  cudaFree(h->vorder);
   cudaFree(h->hubs);
   cudaFree(h->msg[0]);
   cudaFree(h->msg[1]);
@@ -497,10 +526,10 @@ int64_t gbx_sbm_device_bytes(const gbx_sbm* h) { return h ? h->dev_bytes : 0; }
 double gbx_sbm_sweep_bytes(const gbx_sbm* h) {
   if (!h) return 0.0;
   const double q = h->q, K = (double)h->K, n = (double)h->n;
-  double per_edge = 2.0 * q * 8.0 + 4.0 + 1.0;         // message in, message out, rev, tile-local vertex id
-  if (h->opt.degreecorrection) per_edge += 8.0;        // theta_row * theta_col of the slot
+  double per_edge = 2.0 * q * 8.0 + 4.0;               // message in, message out, rev
+  if (h->opt.degreecorrection) per_edge += 4.0 + 8.0;  // col + theta of the neighbour
   if (h->opt.damping != 1.0) per_edge += q * 8.0;      // old outgoing message
-  double per_vertex = 2.0 * q * 8.0 + 4.0;             // PSI read + write, rowptr
+  double per_vertex = 2.0 * q * 8.0 + 4.0 + 4.0;       // PSI read + write, rowptr, processing order
   if (h->opt.degreecorrection) per_vertex += 8.0;
   return K * per_edge + n * per_vertex;
 }

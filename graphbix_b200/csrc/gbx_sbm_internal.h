@@ -57,6 +57,9 @@ struct gbx_sbm {
   int4* tiles = nullptr;          // (first vertex, #vertices, first edge slot, #edge slots)
   double* escale = nullptr;       // per edge slot theta_row * theta_col (all ones until update_theta runs)
   int2* und = nullptr;            // every undirected edge once: (slot e, slot rev[e]) with rev[e] < e
+  int* vorder = nullptr;          // non-hub vertices, grouped by ceil(degree / lanes-per-vertex), largest first
+  int nmain = 0;                  // number of non-hub vertices
+  int sweep_variant = 1;          // 1: CTA-tile kernel with cp.async staging (default), 0: warp-autonomous group kernel (GBX_SWEEP=group)
   int ntiles = 0, nhubs = 0;
   // state (device)
   double *msg[2] = {nullptr, nullptr}, *PSI = nullptr, *theta = nullptr;
@@ -83,7 +86,7 @@ struct SbmOps {
   int (*permute)(gbx_sbm* h, const double* src, double* dst, int to_slots);
   int (*random_messages)(gbx_sbm* h, uint64_t seed);
   int (*assignment)(gbx_sbm* h, int* dev_block);
-  int (*occupancy)(int* vertex_occ, int* mstep_occ);
+  int (*occupancy)(int variant, int* vertex_occ, int* mstep_occ);
 };
 
 }  // namespace gbx

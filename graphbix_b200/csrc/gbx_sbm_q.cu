@@ -45,6 +45,8 @@ struct VertexArgs {
   const double* escale;  // per edge slot: theta_row * theta_col (degree-corrected runs), refreshed with theta
   const int4* tiles;     // [ntiles] (first vertex, #vertices, first edge slot, #edge slots)
   int ntiles;
+  const int* vorder;  // non-hub vertices in processing order (grouped by ceil(degree / QP), largest first)
+  int nmain;
   const int* hubs;    // vertex ids with degree > TILE_E
   const double* theta;
   const double* cur;
@@ -281,14 +283,69 @@ __device__ __forceinline__ void store_partials(const LaneAcc& acc, double* scrat
 }
 
 // ---------------------------------------------------------------------------------------------
-// BP sweep over the tiled (degree <= 256) vertices.  Persistent CTAs, software-pipelined over tiles: the global
-// loads of tile k+1 (messages, rev, local vertex id, theta scale, row bounds, old marginals) are issued before
-// the arithmetic of tile k, so HBM latency hides behind compute instead of behind occupancy.
-//   stage 1  one thread per incoming edge slot: T = theta theta psi*Crs, rescaled by 2^-ke        -> smem
-//   stage 2  QP lanes per vertex: product of the T's, prior, clamp floor, marginal, residual         -> smem
+// BP sweep over the tiled (degree <= 256) vertices.  Persistent CTAs; the messages of tile k+1 are staged into
+// shared memory with cp.async (LDGSTS) while tile k is computed, so the HBM latency is covered by bytes in
+// flight in shared memory rather than by registers or occupancy (double buffer, 2 CTA barriers per tile).
+//   stage 1  one thread per incoming edge slot: psi row from smem, T = theta theta psi*Crs, rescaled   -> smem
+//   stage 2  QP lanes per vertex: product of the T's, prior, clamp floor, marginal, residual            -> smem
 //   stage 3  one thread per edge slot: cavity = product / own factor, clamp, normalise, damp, scatter to rev[e]
-struct EdgeRegs {   // what an edge-slot thread needs from global memory for one tile
-  double psi[Q];
+constexpr int ROWB = Q * 8;                                  // bytes of one message
+constexpr int CHB = (Q % 2 == 0) ? 16 : 8;                   // cp.async unit
+constexpr int CH = ROWB / CHB;                               // units per message
+constexpr bool SWZ = (Q == 4 || Q == 8 || Q == 16);          // power-of-two rows: rotate units to dodge bank conflicts
+constexpr int SWZ_DIV = (CH >= 8) ? 1 : 8 / CH;
+
+__device__ __forceinline__ int swz_unit(int row, int c) {
+  if constexpr (SWZ) return (c + row / SWZ_DIV) % CH;
+  return c;
+}
+
+struct SweepSmem {
+  static constexpr size_t psi_bytes = (size_t)2 * TILE_E * ROWB;
+  static constexpr size_t t_off = psi_bytes;
+  static constexpr size_t u_off = t_off + (size_t)TILE_E * QS * 8;
+  static constexpr size_t ff_off = u_off + (size_t)TV * Q * 8;
+  static constexpr size_t scratch_off = ff_off + (size_t)TV * 8;
+  static constexpr size_t dr_off = scratch_off + (size_t)NT * 8;
+  static constexpr size_t nr_off = dr_off + (size_t)Q * 8;
+  static constexpr size_t k_off = nr_off + (size_t)Q * 4;
+  static constexpr size_t fn_off = k_off + (size_t)TV * 4;
+  static constexpr size_t total = ((fn_off + (size_t)TV * 4 + 127) / 128) * 128;
+};
+
+__device__ __forceinline__ void cp_async_unit(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  if constexpr (CHB == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Stage the `ne` messages of a tile (contiguous in HBM from slot e0) into one smem buffer, coalesced.
+__device__ __forceinline__ void stage_tile(const double* __restrict__ cur, int e0, int ne, char* buf) {
+  const char* src = reinterpret_cast<const char*>(cur) + (size_t)e0 * ROWB;
+  for (int g = threadIdx.x; g < ne * CH; g += NT) {
+    const int row = g / CH, c = g - row * CH;
+    cp_async_unit(buf + row * ROWB + swz_unit(row, c) * CHB, src + (size_t)g * CHB);
+  }
+}
+
+__device__ __forceinline__ void read_staged(const char* buf, int row, double (&psi)[Q]) {
+  const char* r = buf + row * ROWB;
+  if constexpr (CHB == 16) {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const double2 v = *reinterpret_cast<const double2*>(r + swz_unit(row, c) * 16);
+      psi[2 * c] = v.x;
+      psi[2 * c + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) psi[c] = *reinterpret_cast<const double*>(r + c * 8);
+  }
+}
+
+struct EdgeRegs {   // per-slot scalars of one tile, fetched a tile ahead
   double sc;
   int lv, rv;
 };
@@ -301,7 +358,6 @@ template <int MODE>
 __device__ __forceinline__ void load_edge(const VertexArgs& a, const int4& td, EdgeRegs& r) {
   if ((int)threadIdx.x < td.w) {
     const int e = td.z + threadIdx.x;
-    load_vec<Q>(a.cur, e, r.psi);
     r.lv = a.lvtx[e];
     if constexpr (MODE == MODE_SWEEP) r.rv = a.rev[e];
     r.sc = a.dc ? a.escale[e] : 1.0;
@@ -323,15 +379,17 @@ __device__ __forceinline__ void load_vert(const VertexArgs& a, const int4& td, i
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(NT, 2) sbm_vertex_kernel(VertexArgs a) {
-  __shared__ __align__(16) double Tsm[TILE_E * QS];
-  __shared__ __align__(32) double Usm[TV * Q];
-  __shared__ double ffS[TV];
-  __shared__ double scratch[NT];
-  __shared__ unsigned long long s_dr[Q];
-  __shared__ int s_nr[Q];
-  __shared__ int Ksm[TV];
-  __shared__ int fnS[TV];
+__global__ void __launch_bounds__(NT, (Q <= 8) ? 3 : 2) sbm_vertex_kernel(VertexArgs a) {
+  extern __shared__ __align__(128) char smem[];
+  char* psiS = smem;
+  double* Tsm = reinterpret_cast<double*>(smem + SweepSmem::t_off);
+  double* Usm = reinterpret_cast<double*>(smem + SweepSmem::u_off);
+  double* ffS = reinterpret_cast<double*>(smem + SweepSmem::ff_off);
+  double* scratch = reinterpret_cast<double*>(smem + SweepSmem::scratch_off);
+  unsigned long long* s_dr = reinterpret_cast<unsigned long long*>(smem + SweepSmem::dr_off);
+  int* s_nr = reinterpret_cast<int*>(smem + SweepSmem::nr_off);
+  int* Ksm = reinterpret_cast<int*>(smem + SweepSmem::k_off);
+  int* fnS = reinterpret_cast<int*>(smem + SweepSmem::fn_off);
 
   const int tid = threadIdx.x;
   if (tid < Q) {
@@ -347,32 +405,44 @@ __global__ void __launch_bounds__(NT, 2) sbm_vertex_kernel(VertexArgs a) {
   const int vwarp = (tid & ~31) / LV;        // first vertex of this warp in a round
 
   const int4 zero4 = make_int4(0, 0, 0, 0);
-  int4 tdN = (blockIdx.x < a.ntiles) ? a.tiles[blockIdx.x] : zero4;
-  EdgeRegs en;
-  VertRegs vn;
-  load_edge<MODE>(a, tdN, en);
-  load_vert<MODE>(a, tdN, vlane, t, vn);
+  const int G = gridDim.x;
+  int4 td = (blockIdx.x < a.ntiles) ? a.tiles[blockIdx.x] : zero4;                 // tile k
+  int4 tdN = (blockIdx.x + G < a.ntiles) ? a.tiles[blockIdx.x + G] : zero4;         // tile k+1
+  EdgeRegs ec;
+  VertRegs vc;
+  ec.sc = 1.0; ec.lv = 0; ec.rv = 0;
+  stage_tile(a.cur, td.z, td.w, psiS);
+  cp_async_commit();
+  load_edge<MODE>(a, td, ec);
+  load_vert<MODE>(a, td, vlane, t, vc);
+  cp_async_wait_all();
   __syncthreads();
 
-  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-    const int4 td = tdN;
+  int buf = 0;
+  for (int tile = blockIdx.x; tile < a.ntiles; tile += G) {
     const int v0 = td.x, nv = td.y, ne = td.w;
-    // ---- stage 1: consume the prefetched registers ----
+    // ---- start the copies of tile k+1 and fetch its scalars; descriptor of tile k+2 ----
+    stage_tile(a.cur, tdN.z, tdN.w, psiS + (size_t)(buf ^ 1) * TILE_E * ROWB);
+    cp_async_commit();
+    EdgeRegs en;
+    VertRegs vn;
+    en.sc = 1.0; en.lv = 0; en.rv = 0;
+    load_edge<MODE>(a, tdN, en);
+    load_vert<MODE>(a, tdN, vlane, t, vn);
+    const int4 tdNN = (tile + 2 * G < a.ntiles) ? a.tiles[tile + 2 * G] : zero4;
+
+    // ---- stage 1 ----
     double T[Q];
     int ke = 0;
-    const int lv = en.lv, rv = en.rv;
+    const int lv = ec.lv, rv = ec.rv;
     if (tid < ne) {
-      edge_transform(en.psi, en.sc, T, ke);
+      double psi[Q];
+      read_staged(psiS + (size_t)buf * TILE_E * ROWB, tid, psi);
+      edge_transform(psi, ec.sc, T, ke);
 #pragma unroll
       for (int k = 0; k < Q; ++k) Tsm[tid * QS + k] = T[k];
       atomicAdd(&Ksm[lv], ke);
     }
-    const VertRegs vc = vn;
-    // ---- issue the loads of the next tile (they complete while this tile is being computed) ----
-    const int nxt = tile + gridDim.x;
-    tdN = (nxt < a.ntiles) ? a.tiles[nxt] : zero4;
-    load_edge<MODE>(a, tdN, en);
-    load_vert<MODE>(a, tdN, vlane, t, vn);
     __syncthreads();
 
     // ---- stage 2 ----
@@ -407,11 +477,143 @@ __global__ void __launch_bounds__(NT, 2) sbm_vertex_kernel(VertexArgs a) {
         }
       }
     }
+    cp_async_wait_all();  // tile k+1 has landed (this thread's part); the barrier publishes everybody's
     __syncthreads();
 
     // ---- stage 3 ----
     if constexpr (MODE == MODE_SWEEP) {
       if (tid < ne) emit_message(a, &Usm[lv * Q], T, ffS[lv], fnS[lv] + ke, rv);
+    }
+    td = tdN;
+    tdN = tdNN;
+    ec = en;
+    vc = vn;
+    buf ^= 1;
+  }
+  store_partials(acc, scratch, a.partials + (size_t)blockIdx.x * PSTRIDE, s_dr, s_nr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// BP sweep, warp-autonomous variant: QP lanes per vertex, no shared memory, no CTA barrier in the loop.
+//   pass 1  lane j of the group takes edge slots b+j, b+j+QP, ... of its vertex, each as a whole edge:
+//           T = theta theta psi*Crs (Q*Q DFMA with uniform operands), running product per component
+//   reduce  butterfly reduce-scatter of the partial products over the QP lanes: lane t ends with component t
+//   finish  prior, clamp floor, marginal, residual (lane t = component t), all-gather of u
+//   pass 2  the same lanes revisit their edge slots (messages now L1/L2 hits), cavity = u / T, clamp,
+//           normalise, damp, scatter to rev[e]
+// Vertices are visited in `vorder` (same ceil(degree/QP) inside a warp), so the lanes of a warp run the same
+// number of iterations.
+__device__ __forceinline__ double edge_scale(const VertexArgs& a, double th, int e) {
+  return a.dc ? th * a.theta[a.col[e]] : 1.0;
+}
+
+// T[t] = sc * (psi * Crs)[t], no rescaling.
+__device__ __forceinline__ void edge_factor(const double (&psi)[Q], double sc, double (&T)[Q]) {
+#pragma unroll
+  for (int t = 0; t < Q; ++t) {
+    double acc = 0.0;
+#pragma unroll
+    for (int s = 0; s < Q; ++s) acc = fma(psi[s], c_P.C[s * Q + t], acc);
+    T[t] = acc * sc;
+  }
+}
+
+// Divide the vector by 2^ex, ex = exponent of its largest entry; returns ex (0 if that entry is 0/NaN/Inf).
+__device__ __forceinline__ int renorm_vec(double (&P)[QP]) {
+  double m = 0.0;
+#pragma unroll
+  for (int t = 0; t < Q; ++t) m = (P[t] > m) ? P[t] : m;
+  bool ok;
+  int ex = exponent_of(m, ok);
+  if (!ok) ex = 0;
+  const double s2 = pow2i(-ex);
+#pragma unroll
+  for (int t = 0; t < Q; ++t) P[t] *= s2;
+  return ex;
+}
+
+// Multiply-reduce-scatter over the QP lanes of a group: on return lane j holds prod over lanes of P_lane[j].
+template <int W>
+__device__ __forceinline__ double reduce_scatter_mul(double (&P)[QP], int j) {
+  if constexpr (W == 1) {
+    return P[0];
+  } else {
+    constexpr int H = W / 2;
+    const bool up = (j & H) != 0;
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+      const double send = up ? P[i] : P[i + H];
+      const double keep = up ? P[i + H] : P[i];
+      P[i] = keep * __shfl_xor_sync(0xffffffffu, send, H);
+    }
+    return reduce_scatter_mul<H>(P, j);
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NT, 2) sbm_group_kernel(VertexArgs a) {
+  __shared__ double scratch[NT];
+  __shared__ unsigned long long s_dr[Q];
+  __shared__ int s_nr[Q];
+  const int tid = threadIdx.x;
+  if (tid < Q) {
+    s_dr[tid] = 0ull;
+    s_nr[tid] = 0;
+  }
+  __syncthreads();
+  LaneAcc acc;
+  const int j = tid % QP;               // lane inside the group == component owned in the finishing stage
+  const bool tl = j < Q;
+  constexpr int GPB = NT / QP;          // groups (vertices) per CTA per step
+  const int gstride = gridDim.x * GPB;
+
+  for (int base = blockIdx.x * GPB + (tid & ~31) / QP; base < a.nmain; base += gstride) {
+    const int idx = base + (tid & 31) / QP;
+    const bool valid = idx < a.nmain;
+    int gv = 0, b = 0, e = 0;
+    if (valid) {
+      gv = a.vorder[idx];
+      b = a.rowptr[gv];
+      e = a.rowptr[gv + 1];
+    }
+    const double th = (a.dc && valid) ? a.theta[gv] : 1.0;
+    const double old = (MODE == MODE_SWEEP && valid && tl) ? a.PSI[(size_t)gv * Q + j] : 0.0;
+
+    // ---- pass 1 ----
+    double P[QP];
+#pragma unroll
+    for (int t = 0; t < QP; ++t) P[t] = 1.0;
+    int K = 0, it = 0;
+    for (int k = b + j; k < e; k += QP) {
+      double psi[Q], T[Q];
+      load_vec<Q>(a.cur, k, psi);
+      edge_factor(psi, edge_scale(a, th, k), T);
+#pragma unroll
+      for (int t = 0; t < Q; ++t) P[t] *= T[t];
+      if ((++it & 3) == 0) K += renorm_vec(P);  // keeps long rows inside the double range
+    }
+    K += renorm_vec(P);
+    // ---- reduce over the group ----
+#pragma unroll
+    for (int o = QP / 2; o > 0; o >>= 1) K += __shfl_xor_sync(0xffffffffu, K, o);
+    const double prod = reduce_scatter_mul<QP>(P, j);
+
+    // ---- finish (lane j = component j) ----
+    double u, ffrac;
+    int fn;
+    vertex_finish<MODE>(a, valid, gv, e - b, j, th, old, prod, K, u, ffrac, fn, acc, s_dr, s_nr);
+
+    // ---- pass 2 ----
+    if constexpr (MODE == MODE_SWEEP) {
+      double uu[Q];
+#pragma unroll
+      for (int t = 0; t < Q; ++t) uu[t] = __shfl_sync(0xffffffffu, u, t, QP);
+      for (int k = b + j; k < e; k += QP) {
+        double psi[Q], T[Q];
+        load_vec<Q>(a.cur, k, psi);
+        edge_factor(psi, edge_scale(a, th, k), T);
+        emit_message(a, uu, T, ffrac, fn, a.rev[k]);
+      }
     }
   }
   store_partials(acc, scratch, a.partials + (size_t)blockIdx.x * PSTRIDE, s_dr, s_nr);
@@ -933,6 +1135,8 @@ VertexArgs vertex_args(gbx_sbm* h) {
   a.escale = h->escale;
   a.tiles = h->tiles;
   a.ntiles = h->ntiles;
+  a.vorder = h->vorder;
+  a.nmain = h->nmain;
   a.hubs = h->hubs;
   a.theta = h->theta;
   a.cur = h->msg[h->cur];
@@ -948,8 +1152,9 @@ VertexArgs vertex_args(gbx_sbm* h) {
 template <int MODE>
 int launch_vertex_pass_t(gbx_sbm* h) {
   VertexArgs a = vertex_args(h);
-  if (h->ntiles > 0) {
-    sbm_vertex_kernel<MODE><<<h->grid_vertex, NT, 0, h->stream>>>(a);
+  if (h->nmain > 0) {
+    if (h->sweep_variant == 0) sbm_group_kernel<MODE><<<h->grid_vertex, NT, 0, h->stream>>>(a);
+    else sbm_vertex_kernel<MODE><<<h->grid_vertex, NT, SweepSmem::total, h->stream>>>(a);
     h->launches++;
   }
   if (h->nhubs > 0) {
@@ -967,8 +1172,8 @@ int op_vertex_pass(gbx_sbm* h, int mode) {
 }
 
 int op_reduce_vertex(gbx_sbm* h, int mode) {
-  const int nrows = (h->ntiles > 0 ? h->grid_vertex : 0) + h->nhubs;
-  const double* base = h->part_vertex + (h->ntiles > 0 ? 0 : (size_t)h->grid_vertex * PSTRIDE);
+  const int nrows = (h->nmain > 0 ? h->grid_vertex : 0) + h->nhubs;
+  const double* base = h->part_vertex + (h->nmain > 0 ? 0 : (size_t)h->grid_vertex * PSTRIDE);
   sbm_reduce_vertex<<<1, 256, 0, h->stream>>>(h->st, base, nrows, mode, h->opt.priorlearning,
                                              h->opt.degreecorrection, (double)h->n);
   h->launches++;
@@ -998,7 +1203,7 @@ int op_theta(gbx_sbm* h) {
   sbm_theta_kernel<<<h->grid_theta, NT, 0, h->stream>>>(h->st, h->rowptr, (int)h->n, h->PSI, h->theta, h->part_theta);
   sbm_reduce_theta<<<1, 256, 0, h->stream>>>(h->st, h->part_theta, h->grid_theta);
   h->launches += 2;
-  if (h->ntiles > 0) {
+  if (h->ntiles > 0 && h->sweep_variant != 0) {
     sbm_escale_kernel<<<std::min(h->ntiles, h->num_sms * 8), NT, 0, h->stream>>>(h->tiles, h->ntiles, h->lvtx, h->col,
                                                                                h->theta, h->escale);
     h->launches++;
@@ -1050,8 +1255,15 @@ int op_assignment(gbx_sbm* h, int* dev_block) {
   return GBX_OK;
 }
 
-int op_occupancy(int* vertex_occ, int* mstep_occ) {
-  GBX_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(vertex_occ, sbm_vertex_kernel<MODE_SWEEP>, NT, 0));
+int op_occupancy(int variant, int* vertex_occ, int* mstep_occ) {
+  if (variant == 0)
+    GBX_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(vertex_occ, sbm_group_kernel<MODE_SWEEP>, NT, 0));
+  else {
+    GBX_CUDA_TRY(cudaFuncSetAttribute(sbm_vertex_kernel<MODE_SWEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepSmem::total));
+    GBX_CUDA_TRY(cudaFuncSetAttribute(sbm_vertex_kernel<MODE_MARGINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepSmem::total));
+    GBX_CUDA_TRY(cudaFuncSetAttribute(sbm_vertex_kernel<MODE_LOGZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepSmem::total));
+    GBX_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(vertex_occ, sbm_vertex_kernel<MODE_SWEEP>, NT, SweepSmem::total));
+  }
   GBX_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(mstep_occ, sbm_mstep_kernel, NTM, 0));
   return GBX_OK;
 }

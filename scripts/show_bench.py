@@ -1,0 +1,5 @@
+import json, sys
+d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+r = d.get("roofline", {})
+print(f"value={d['value']/1e9:.3f} G upd/s  ms/step={d['ms_per_step']:.4f}  e2e={d['e2e']['value']/1e9:.3f} G upd/s ({d['e2e'].get('seconds',0):.2f}s)  "
+      f"sweep={r.get('ms_per_launch',0)*1e3:.1f}us  {r.get('achieved',0):.0f} GB/s  frac={r.get('frac',0):.3f}  launches={d.get('gpu_launches')}  clocks={d.get('clocks')}")
