@@ -238,6 +238,7 @@ int gbx_sbm_create(gbx_sbm** out, int device, int64_t n, int64_t K, const int64_
   h->ops = ops;
   h->ntiles = (int)tiles.size();
   h->nmain = (int)vorder.size();
+  for (int64_t v = 0; v < n; ++v) h->max_degree = std::max(h->max_degree, rowptr[(size_t)v + 1] - rowptr[(size_t)v]);
   {
     const char* env = getenv("GBX_SWEEP");
     h->sweep_variant = (env && std::string(env) == "group") ? 0 : 1;
@@ -269,6 +270,9 @@ int gbx_sbm_create(gbx_sbm** out, int device, int64_t n, int64_t K, const int64_
     GBX_TRY(dev_alloc(h, &h->msg[1], (size_t)K * q));
     GBX_TRY(dev_alloc(h, &h->PSI, (size_t)n * q));
     GBX_TRY(dev_alloc(h, &h->theta, (size_t)n));
+    GBX_TRY(dev_alloc(h, &h->blk, (size_t)n));
+    GBX_TRY(dev_alloc(h, &h->prior_tab, (size_t)(1 + (TILE_E + 1) * q) * (q + 3)));
+    GBX_CUDA_TRY(cudaMemset(h->blk, 0, (size_t)n));
     GBX_TRY(dev_alloc(h, &h->st, 1));
     GBX_TRY(dev_alloc(h, &h->params, 1));
     GBX_CUDA_TRY(cudaMemcpy(h->rowptr, rowptr.data(), ((size_t)n + 1) * sizeof(int), cudaMemcpyHostToDevice));
@@ -329,6 +333,8 @@ int gbx_sbm_destroy(gbx_sbm* h) {
   cudaFree(h->msg[1]);
   cudaFree(h->PSI);
   cudaFree(h->theta);
+  cudaFree(h->blk);
+  cudaFree(h->prior_tab);
   cudaFree(h->st);
   cudaFree(h->params);
   cudaFree(h->part_vertex);
@@ -377,6 +383,7 @@ int gbx_sbm_init(gbx_sbm* h, const double* gr_init, const double* Crs_init, cons
   GBX_CUDA_TRY(cudaStreamSynchronize(h->stream));  // `s` is a stack object
   h->cur = 0;
   h->itr = 0;
+  h->theta_valid = false;
   if (psicav) {
     double* tmp = h->msg[1];
     GBX_CUDA_TRY(cudaMemcpyAsync(tmp, psicav, (size_t)h->K * q * sizeof(double), cudaMemcpyHostToDevice, h->stream));

@@ -16,6 +16,8 @@ struct SbmParams {
   double lgr[MAXQ];          // log(gr) after the clamp of sbm.jl:89-96
   double h[MAXQ];            // external field, sbm.jl:70-73
   double logN;
+  int safe_deg;              // largest degree whose plain product of edge factors cannot leave the double range
+  int pad_;
 };
 
 // Device-resident EM state (small; one per handle).
@@ -60,9 +62,12 @@ struct gbx_sbm {
   int* vorder = nullptr;          // non-hub vertices, grouped by ceil(degree / lanes-per-vertex), largest first
   int nmain = 0;                  // number of non-hub vertices
   int sweep_variant = 1;          // 1: CTA-tile kernel with cp.async staging (default), 0: warp-autonomous group kernel (GBX_SWEEP=group)
-  int ntiles = 0, nhubs = 0;
+  int ntiles = 0, nhubs = 0, max_degree = 1;
   // state (device)
   double *msg[2] = {nullptr, nullptr}, *PSI = nullptr, *theta = nullptr;
+  unsigned char* blk = nullptr;   // MAP block per vertex as of the last update_theta
+  double* prior_tab = nullptr;    // prior factors per (degree, block), rebuilt every EM iteration
+  bool theta_valid = false;       // update_theta has run since init
   int cur = 0;
   gbx::SbmState* st = nullptr;
   gbx::SbmParams* params = nullptr;

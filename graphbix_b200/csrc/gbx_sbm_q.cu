@@ -49,6 +49,9 @@ struct VertexArgs {
   int nmain;
   const int* hubs;    // vertex ids with degree > TILE_E
   const double* theta;
+  const unsigned char* blk;   // MAP block of every vertex as of the last update_theta (indexes the prior table)
+  const double* prior_tab;    // [1 + (TILE_E + 1) * Q][QT]: prior factors per (degree, block); row 0: theta = 1
+  int dc_tab;                 // theta has been updated at least once: use rows 1.. of the table
   const double* cur;
   double* nxt;
   double* PSI;
@@ -142,14 +145,16 @@ __device__ __forceinline__ void edge_transform(const double (&psi)[Q], double sc
 __device__ __forceinline__ void emit_message(const VertexArgs& a, const double* __restrict__ u, const double (&T)[Q],
                                              double ffrac, int n, int rv) {
   double w[Q];
-  double S = 0.0, cmin = INFINITY;
+  double S = 0.0;
+  bool low = false;
+  const double thr = pow2c(n + 1);
 #pragma unroll
   for (int t = 0; t < Q; ++t) {
     w[t] = u[t] * fast_rcp(T[t]);
     S += w[t];
-    cmin = (w[t] < cmin) ? w[t] : cmin;
+    low = low || (w[t] < thr);
   }
-  if (cmin < pow2c(n + 1)) {  // rare: some component is at or below the clamp floor
+  if (low) {  // rare: some component is at or below the clamp floor
     const double fl = scale2(exp2(ffrac), n);
     S = 0.0;
 #pragma unroll
@@ -186,40 +191,86 @@ __device__ __forceinline__ unsigned group_bits(unsigned ballot) {
   return (ballot >> (lane & ~(unsigned)(QP - 1))) & ((1u << QP) - 1u);
 }
 
-// Everything a vertex needs once lane t holds prod_t = product of its scaled edge factors and K = their exponents.
-//   true unnormalised value v_t = u_t 2^K e^xmax;  the clamp floor of sbm.jl:42 in the scaled domain is 2^f.
+// Prior factor of a vertex for the lane's component t, and the clamp floor of sbm.jl:42 in the scaled domain:
+//   x_t = log gr_t - theta h_t, xmax = max_t x_t, E = exp(x_t - xmax), 2^(fi + ffrac) = 1e-8 / e^xmax.
+// It depends on the vertex only through theta = degree / <degree of its MAP block>, so it is tabulated once per
+// EM iteration per (degree, block) by sbm_prior_table and read here as one coalesced row.
+constexpr int QT = Q + 3;
+struct Prior {
+  double E, ffrac, xmax;
+  int fi;
+};
+
+__device__ __forceinline__ void prior_row(double th, double* row /* QT */) {
+  double x[Q], xmax = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < Q; ++t) {
+    x[t] = c_P.lgr[t] - th * c_P.h[t];
+    xmax = fmax(xmax, x[t]);
+  }
+#pragma unroll
+  for (int t = 0; t < Q; ++t) row[t] = exp(x[t] - xmax);
+  const double f = (LOG_1EM8 - xmax) * INV_LN2;
+  const double fi = fmin(fmax(floor(f), -100000.0), 100000.0);
+  row[Q] = f - floor(f);
+  row[Q + 1] = fi;
+  row[Q + 2] = xmax;
+}
+
+__global__ void sbm_prior_table(const SbmState* st, double* tab, int dc) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nrows = dc ? 1 + (TILE_E + 1) * Q : 1;
+  if (r >= nrows) return;
+  double th = 1.0;
+  if (r > 0) {
+    const int d = (r - 1) / Q, blk = (r - 1) % Q;
+    th = (double)d / st->drmean[blk];  // the expression of sbm_theta_kernel, so theta is bit-identical
+  }
+  double row[QT];
+  prior_row(th, row);
+  for (int k = 0; k < QT; ++k) tab[(size_t)r * QT + k] = row[k];
+}
+
+template <int MODE>
+__device__ __forceinline__ Prior load_prior(const VertexArgs& a, bool valid, int gv, int deg, int t) {
+  Prior pr;
+  const int r = (a.dc_tab && valid) ? 1 + deg * Q + a.blk[gv] : 0;
+  const double* row = a.prior_tab + (size_t)r * QT;
+  pr.E = (t < Q) ? row[t] : 0.0;
+  pr.ffrac = row[Q];
+  pr.fi = (int)row[Q + 1];
+  pr.xmax = (MODE == MODE_LOGZ) ? row[Q + 2] : 0.0;
+  return pr;
+}
+
+// Everything a vertex needs once lane t holds prod_t = product of its (scaled) edge factors and K = the exponent
+// taken out of it:  true unnormalised value v_t = u_t 2^K e^xmax,  u_t = E_t prod_t;  clamp floor 2^(fn + ffrac).
 // Runs on the QP lanes of a group (all lanes of the warp execute it; `valid` gates the side effects).
 template <int MODE>
-__device__ __forceinline__ void vertex_finish(const VertexArgs& a, bool valid, int gv, int deg, int t, double th,
-                                              double old, double prod, int K, double& u_out, double& ffrac, int& fn,
+__device__ __forceinline__ void vertex_finish(const VertexArgs& a, bool valid, int gv, int deg, int t, const Prior& pr,
+                                              double old, double prod, int K, double& u_out, int& fn,
                                               LaneAcc& acc, unsigned long long* s_dr, int* s_nr) {
   const bool tl = t < Q;
-  const double x = tl ? (c_P.lgr[tl ? t : 0] - th * c_P.h[tl ? t : 0]) : -INFINITY;
-  const double xmax = group_max(x);
-  const double u = tl ? exp(x - xmax) * prod : 0.0;
+  const double u = tl ? pr.E * prod : 0.0;
   u_out = u;
-  const double f = (LOG_1EM8 - xmax) * INV_LN2 - (double)K;
-  const double fi = floor(f);
-  ffrac = f - fi;
-  fn = (fi < -4000.0) ? -4000 : ((fi > 4000.0) ? 4000 : (int)fi);
+  fn = pr.fi - K;
   if constexpr (MODE == MODE_LOGZ) {
     // logsumexp(logunnormalizedMessage(i)), sbm.jl:153, with the 500 cut-off of sbm.jl:33-35
     const double umax = group_max(u);
     const double cut = umax * EXP_M500;
     const double s = group_sum(tl ? ((u < cut) ? cut : u) : 0.0);
-    if (valid && t == 0) acc.logz += log(s) + (double)K * LN2 + xmax;
+    if (valid && t == 0) acc.logz += log(s) + (double)K * LN2 + pr.xmax;
   } else {
     double w = u;
     const unsigned low = group_bits(__ballot_sync(0xffffffffu, tl && (u < pow2c(fn + 1))));
     if (low) {  // rare: a component is at or below the clamp floor
-      const double fl = scale2(exp2(ffrac), fn);
+      const double fl = scale2(exp2(pr.ffrac), fn);
       w = (u < fl) ? fl : u;
     }
     const double S = group_sum(tl ? w : 0.0);
     const double p = w * fast_rcp(S);
-    double r = 0.0;
-    if constexpr (MODE == MODE_SWEEP) r = tl ? fabs(p - old) : 0.0;
-    const double res = (MODE == MODE_SWEEP) ? group_sum(r) : 0.0;
+    double res = 0.0;
+    if constexpr (MODE == MODE_SWEEP) res = group_sum(tl ? fabs(p - old) : 0.0);
     const double pm = group_max(tl ? p : -1.0);
     const unsigned eq = group_bits(__ballot_sync(0xffffffffu, tl && (p == pm)));
     if (valid) {
@@ -300,17 +351,29 @@ __device__ __forceinline__ int swz_unit(int row, int c) {
   return c;
 }
 
+// T[t] = sc * (psi * Crs)[t], no rescaling.
+__device__ __forceinline__ void edge_factor(const double (&psi)[Q], double sc, double (&T)[Q]) {
+#pragma unroll
+  for (int t = 0; t < Q; ++t) {
+    double acc = 0.0;
+#pragma unroll
+    for (int s = 0; s < Q; ++s) acc = fma(psi[s], c_P.C[s * Q + t], acc);
+    T[t] = acc * sc;
+  }
+}
+
 struct SweepSmem {
-  static constexpr size_t psi_bytes = (size_t)2 * TILE_E * ROWB;
-  static constexpr size_t t_off = psi_bytes;
+  static constexpr size_t psi_bytes = (size_t)2 * TILE_E * ROWB;          // staged messages, double buffered
+  static constexpr size_t sc_off = psi_bytes;                              // staged theta scales, double buffered
+  static constexpr size_t t_off = sc_off + (size_t)2 * TILE_E * 8;
   static constexpr size_t u_off = t_off + (size_t)TILE_E * QS * 8;
   static constexpr size_t ff_off = u_off + (size_t)TV * Q * 8;
   static constexpr size_t scratch_off = ff_off + (size_t)TV * 8;
   static constexpr size_t dr_off = scratch_off + (size_t)NT * 8;
   static constexpr size_t nr_off = dr_off + (size_t)Q * 8;
-  static constexpr size_t k_off = nr_off + (size_t)Q * 4;
-  static constexpr size_t fn_off = k_off + (size_t)TV * 4;
-  static constexpr size_t total = ((fn_off + (size_t)TV * 4 + 127) / 128) * 128;
+  static constexpr size_t fn_off = nr_off + (size_t)Q * 4;
+  static constexpr size_t lv_off = fn_off + (size_t)TV * 4;
+  static constexpr size_t total = ((lv_off + (size_t)TILE_E + 127) / 128) * 128;
 };
 
 __device__ __forceinline__ void cp_async_unit(void* smem_dst, const void* gsrc) {
@@ -318,16 +381,34 @@ __device__ __forceinline__ void cp_async_unit(void* smem_dst, const void* gsrc) 
   if constexpr (CHB == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
   else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// Stage the `ne` messages of a tile (contiguous in HBM from slot e0) into one smem buffer, coalesced.
-__device__ __forceinline__ void stage_tile(const double* __restrict__ cur, int e0, int ne, char* buf) {
-  const char* src = reinterpret_cast<const char*>(cur) + (size_t)e0 * ROWB;
-  for (int g = threadIdx.x; g < ne * CH; g += NT) {
-    const int row = g / CH, c = g - row * CH;
-    cp_async_unit(buf + row * ROWB + swz_unit(row, c) * CHB, src + (size_t)g * CHB);
+// Stage the `ne` messages of a tile (contiguous in HBM from slot e0), and their theta scales, into smem, coalesced:
+// unit g = i * NT + tid of the tile goes to row g / CH at a rotated position, so that stage 1 (one thread per
+// row) reads its row without bank conflicts.
+__device__ __forceinline__ void stage_tile(const VertexArgs& a, int e0, int ne, char* buf, double* scbuf) {
+  const char* src = reinterpret_cast<const char*>(a.cur) + (size_t)e0 * ROWB;
+  const int nunits = ne * CH;
+  if constexpr (NT % CH == 0) {
+    // the rotation does not depend on the round i, so the smem offset is a per-thread constant plus i * NT * CHB
+    const int row0 = threadIdx.x / CH, c = threadIdx.x % CH;
+    char* d = buf + row0 * ROWB + swz_unit(row0, c) * CHB;
+    const char* g = src + (size_t)threadIdx.x * CHB;
+#pragma unroll
+    for (int i = 0; i < CH; ++i)
+      if (i * NT + (int)threadIdx.x < nunits) cp_async_unit(d + i * NT * CHB, g + (size_t)i * NT * CHB);
+  } else {
+    for (int g = threadIdx.x; g < nunits; g += NT) {
+      const int row = g / CH, c = g - row * CH;
+      cp_async_unit(buf + row * ROWB + swz_unit(row, c) * CHB, src + (size_t)g * CHB);
+    }
   }
+  if (a.dc && (int)threadIdx.x < ne) cp_async_8(scbuf + threadIdx.x, a.escale + e0 + threadIdx.x);
 }
 
 __device__ __forceinline__ void read_staged(const char* buf, int row, double (&psi)[Q]) {
@@ -345,36 +426,15 @@ __device__ __forceinline__ void read_staged(const char* buf, int row, double (&p
   }
 }
 
-struct EdgeRegs {   // per-slot scalars of one tile, fetched a tile ahead
-  double sc;
-  int lv, rv;
-};
-struct VertRegs {   // what an aggregation lane needs from global memory for the first round of one tile
-  double th, old;
-  int b, e;
-};
-
-template <int MODE>
-__device__ __forceinline__ void load_edge(const VertexArgs& a, const int4& td, EdgeRegs& r) {
-  if ((int)threadIdx.x < td.w) {
-    const int e = td.z + threadIdx.x;
-    r.lv = a.lvtx[e];
-    if constexpr (MODE == MODE_SWEEP) r.rv = a.rev[e];
-    r.sc = a.dc ? a.escale[e] : 1.0;
-  }
-}
-
-template <int MODE>
-__device__ __forceinline__ void load_vert(const VertexArgs& a, const int4& td, int v, int t, VertRegs& r) {
-  r.b = 0;
-  r.e = 0;
-  r.th = 1.0;
-  r.old = 0.0;
-  if (v < td.y) {
-    r.b = a.rowptr[td.x + v] - td.z;
-    r.e = a.rowptr[td.x + v + 1] - td.z;
-    if (a.dc) r.th = a.theta[td.x + v];
-    if (MODE == MODE_SWEEP && t < Q) r.old = a.PSI[(size_t)(td.x + v) * Q + t];
+// Exponent bookkeeping of a running product: pull the exponent of m into k (m stays in [1,2)); a zero stays zero.
+__device__ __forceinline__ void renorm(double& m, int& k) {
+  bool ok;
+  const int ex = exponent_of(m, ok);
+  if (ok) {
+    m *= pow2i(-ex);
+    k += ex;
+  } else if (m == m && !(m > 1.0)) {
+    m = 0.0;  // underflow: the component is negligible from here on (NaN / Inf are left alone)
   }
 }
 
@@ -382,21 +442,21 @@ template <int MODE>
 __global__ void __launch_bounds__(NT, (Q <= 8) ? 3 : 2) sbm_vertex_kernel(VertexArgs a) {
   extern __shared__ __align__(128) char smem[];
   char* psiS = smem;
+  double* scS = reinterpret_cast<double*>(smem + SweepSmem::sc_off);
   double* Tsm = reinterpret_cast<double*>(smem + SweepSmem::t_off);
   double* Usm = reinterpret_cast<double*>(smem + SweepSmem::u_off);
   double* ffS = reinterpret_cast<double*>(smem + SweepSmem::ff_off);
   double* scratch = reinterpret_cast<double*>(smem + SweepSmem::scratch_off);
   unsigned long long* s_dr = reinterpret_cast<unsigned long long*>(smem + SweepSmem::dr_off);
   int* s_nr = reinterpret_cast<int*>(smem + SweepSmem::nr_off);
-  int* Ksm = reinterpret_cast<int*>(smem + SweepSmem::k_off);
   int* fnS = reinterpret_cast<int*>(smem + SweepSmem::fn_off);
+  unsigned char* lvS = reinterpret_cast<unsigned char*>(smem + SweepSmem::lv_off);
 
   const int tid = threadIdx.x;
   if (tid < Q) {
     s_dr[tid] = 0ull;
     s_nr[tid] = 0;
   }
-  if (tid < TV) Ksm[tid] = 0;
   LaneAcc acc;
   const int t = tid % LV;
   const bool tl = t < Q;
@@ -404,44 +464,49 @@ __global__ void __launch_bounds__(NT, (Q <= 8) ? 3 : 2) sbm_vertex_kernel(Vertex
   const int vlane = tid / LV;                // vertex handled by this lane in an aggregation round
   const int vwarp = (tid & ~31) / LV;        // first vertex of this warp in a round
 
-  const int4 zero4 = make_int4(0, 0, 0, 0);
   const int G = gridDim.x;
-  int4 td = (blockIdx.x < a.ntiles) ? a.tiles[blockIdx.x] : zero4;                 // tile k
-  int4 tdN = (blockIdx.x + G < a.ntiles) ? a.tiles[blockIdx.x + G] : zero4;         // tile k+1
-  EdgeRegs ec;
-  VertRegs vc;
-  ec.sc = 1.0; ec.lv = 0; ec.rv = 0;
-  stage_tile(a.cur, td.z, td.w, psiS);
+  const int last = a.ntiles - 1;
+  int4 tdN = a.tiles[min((int)blockIdx.x, last)];   // descriptor of the tile whose copies are issued next
+  stage_tile(a, tdN.z, tdN.w, psiS, scS);
   cp_async_commit();
-  load_edge<MODE>(a, td, ec);
-  load_vert<MODE>(a, td, vlane, t, vc);
+  int4 td = tdN;
+  tdN = a.tiles[min((int)blockIdx.x + G, last)];
   cp_async_wait_all();
   __syncthreads();
 
   int buf = 0;
   for (int tile = blockIdx.x; tile < a.ntiles; tile += G) {
-    const int v0 = td.x, nv = td.y, ne = td.w;
-    // ---- start the copies of tile k+1 and fetch its scalars; descriptor of tile k+2 ----
-    stage_tile(a.cur, tdN.z, tdN.w, psiS + (size_t)(buf ^ 1) * TILE_E * ROWB);
+    const int v0 = td.x, nv = td.y, e0 = td.z, ne = td.w;
+    // ---- copies of tile k+1 (other buffer), then the descriptor of tile k+2 into the same registers ----
+    const bool hasN = tile + G < a.ntiles;
+    stage_tile(a, tdN.z, hasN ? tdN.w : 0, psiS + (size_t)(buf ^ 1) * TILE_E * ROWB, scS + (buf ^ 1) * TILE_E);
     cp_async_commit();
-    EdgeRegs en;
-    VertRegs vn;
-    en.sc = 1.0; en.lv = 0; en.rv = 0;
-    load_edge<MODE>(a, tdN, en);
-    load_vert<MODE>(a, tdN, vlane, t, vn);
-    const int4 tdNN = (tile + 2 * G < a.ntiles) ? a.tiles[tile + 2 * G] : zero4;
+    const int4 tdK1 = tdN;
+    tdN = a.tiles[min(tile + 2 * G, last)];
+    // ---- this tile's small global reads, consumed one or two stages later ----
+    int rv = 0;
+    if (MODE == MODE_SWEEP && tid < ne) rv = a.rev[e0 + tid];
+    int rb = 0, re = 0;
+    double old = 0.0;
+    Prior pr;
+    {
+      const bool valid = vlane < nv;
+      if (valid) {
+        rb = a.rowptr[v0 + vlane];
+        re = a.rowptr[v0 + vlane + 1];
+        if (MODE == MODE_SWEEP && tl) old = a.PSI[(size_t)(v0 + vlane) * Q + t];
+      }
+      pr = load_prior<MODE>(a, valid, v0 + vlane, re - rb, t);
+    }
 
     // ---- stage 1 ----
     double T[Q];
-    int ke = 0;
-    const int lv = ec.lv, rv = ec.rv;
     if (tid < ne) {
       double psi[Q];
       read_staged(psiS + (size_t)buf * TILE_E * ROWB, tid, psi);
-      edge_transform(psi, ec.sc, T, ke);
+      edge_factor(psi, a.dc ? scS[buf * TILE_E + tid] : 1.0, T);
 #pragma unroll
       for (int k = 0; k < Q; ++k) Tsm[tid * QS + k] = T[k];
-      atomicAdd(&Ksm[lv], ke);
     }
     __syncthreads();
 
@@ -450,28 +515,68 @@ __global__ void __launch_bounds__(NT, (Q <= 8) ? 3 : 2) sbm_vertex_kernel(Vertex
       if (vb + vwarp >= nv) break;  // warp-uniform: no vertex left for this warp
       const int v = vb + vlane;
       const bool valid = v < nv;
-      VertRegs vr = vc;
-      if (vb > 0) load_vert<MODE>(a, td, v, t, vr);  // tiles with more than VPR vertices (low degrees)
-      const double* p = &Tsm[vr.b * QS + tt];
-      const double* pe = &Tsm[vr.e * QS + tt];
-      double prod = 1.0, prod2 = 1.0;
-      for (; p + QS < pe; p += 2 * QS) {  // two independent chains
-        prod *= p[0];
-        prod2 *= p[QS];
+      if (vb > 0) {  // tiles with more than VPR vertices (low degrees)
+        rb = re = 0;
+        old = 0.0;
+        if (valid) {
+          rb = a.rowptr[v0 + v];
+          re = a.rowptr[v0 + v + 1];
+          if (MODE == MODE_SWEEP && tl) old = a.PSI[(size_t)(v0 + v) * Q + t];
+        }
+        pr = load_prior<MODE>(a, valid, v0 + v, re - rb, t);
       }
-      if (p < pe) prod *= p[0];
-      prod *= prod2;
-      const int K = valid ? Ksm[v] : 0;
-      __syncwarp();
-      if (valid && t == 0) Ksm[v] = 0;  // ready for the next tile
-      double u, ffrac;
+      const int b = valid ? rb - e0 : 0, e = valid ? re - e0 : 0;
+      if constexpr (MODE == MODE_SWEEP) {
+        for (int k = b + t; k < e; k += LV) lvS[k] = (unsigned char)v;  // owner of every edge slot, for stage 3
+      }
+      const double* p = &Tsm[b * QS + tt];
+      const double* pe = &Tsm[e * QS + tt];
+      double m1 = 1.0, m2 = 1.0;
+      int K = 0;
+      if (e - b <= c_P.safe_deg) {
+        // the factors are bounded so that a product of this many cannot leave the double range: plain product
+        for (; p + QS < pe; p += 2 * QS) {
+          m1 *= p[0];
+          m2 *= p[QS];
+        }
+        if (p < pe) m1 *= p[0];
+        m1 *= m2;
+      } else {
+        while (p + 7 * QS < pe) {  // 8 slots per trip: two chains of 4, then pull the exponents out
+          m1 *= p[0];
+          m2 *= p[QS];
+          m1 *= p[2 * QS];
+          m2 *= p[3 * QS];
+          m1 *= p[4 * QS];
+          m2 *= p[5 * QS];
+          m1 *= p[6 * QS];
+          m2 *= p[7 * QS];
+          p += 8 * QS;
+          renorm(m1, K);
+          renorm(m2, K);
+        }
+        for (; p + QS < pe; p += 2 * QS) {
+          m1 *= p[0];
+          m2 *= p[QS];
+        }
+        if (p < pe) m1 *= p[0];
+        renorm(m1, K);
+        renorm(m2, K);
+        m1 *= m2;  // in [1,4)
+        const int Kc = group_max((tl && m1 != 0.0) ? K : -(1 << 30));
+        const int Kcc = (Kc == -(1 << 30)) ? 0 : Kc;
+        const int d = K - Kcc;  // <= 0 for live components
+        m1 = (d < -1000 || m1 == 0.0) ? 0.0 : m1 * pow2i(d > 0 ? 0 : d);
+        K = Kcc;
+      }
+      double u;
       int fn;
-      vertex_finish<MODE>(a, valid, v0 + v, vr.e - vr.b, t, vr.th, vr.old, prod, K, u, ffrac, fn, acc, s_dr, s_nr);
+      vertex_finish<MODE>(a, valid, v0 + v, e - b, t, pr, old, m1, K, u, fn, acc, s_dr, s_nr);
       if constexpr (MODE == MODE_SWEEP) {
         if (valid) {
           if (tl) Usm[v * Q + t] = u;
           if (t == 0) {
-            ffS[v] = ffrac;
+            ffS[v] = pr.ffrac;
             fnS[v] = fn;
           }
         }
@@ -482,12 +587,12 @@ __global__ void __launch_bounds__(NT, (Q <= 8) ? 3 : 2) sbm_vertex_kernel(Vertex
 
     // ---- stage 3 ----
     if constexpr (MODE == MODE_SWEEP) {
-      if (tid < ne) emit_message(a, &Usm[lv * Q], T, ffS[lv], fnS[lv] + ke, rv);
+      if (tid < ne) {
+        const int lv = lvS[tid];
+        emit_message(a, &Usm[lv * Q], T, ffS[lv], fnS[lv], rv);
+      }
     }
-    td = tdN;
-    tdN = tdNN;
-    ec = en;
-    vc = vn;
+    td = tdK1;
     buf ^= 1;
   }
   store_partials(acc, scratch, a.partials + (size_t)blockIdx.x * PSTRIDE, s_dr, s_nr);
@@ -505,17 +610,6 @@ __global__ void __launch_bounds__(NT, (Q <= 8) ? 3 : 2) sbm_vertex_kernel(Vertex
 // number of iterations.
 __device__ __forceinline__ double edge_scale(const VertexArgs& a, double th, int e) {
   return a.dc ? th * a.theta[a.col[e]] : 1.0;
-}
-
-// T[t] = sc * (psi * Crs)[t], no rescaling.
-__device__ __forceinline__ void edge_factor(const double (&psi)[Q], double sc, double (&T)[Q]) {
-#pragma unroll
-  for (int t = 0; t < Q; ++t) {
-    double acc = 0.0;
-#pragma unroll
-    for (int s = 0; s < Q; ++s) acc = fma(psi[s], c_P.C[s * Q + t], acc);
-    T[t] = acc * sc;
-  }
 }
 
 // Divide the vector by 2^ex, ex = exponent of its largest entry; returns ex (0 if that entry is 0/NaN/Inf).
@@ -578,6 +672,7 @@ __global__ void __launch_bounds__(NT, 2) sbm_group_kernel(VertexArgs a) {
     }
     const double th = (a.dc && valid) ? a.theta[gv] : 1.0;
     const double old = (MODE == MODE_SWEEP && valid && tl) ? a.PSI[(size_t)gv * Q + j] : 0.0;
+    const Prior pr = load_prior<MODE>(a, valid, gv, e - b, j);
 
     // ---- pass 1 ----
     double P[QP];
@@ -599,9 +694,10 @@ __global__ void __launch_bounds__(NT, 2) sbm_group_kernel(VertexArgs a) {
     const double prod = reduce_scatter_mul<QP>(P, j);
 
     // ---- finish (lane j = component j) ----
-    double u, ffrac;
+    double u;
     int fn;
-    vertex_finish<MODE>(a, valid, gv, e - b, j, th, old, prod, K, u, ffrac, fn, acc, s_dr, s_nr);
+    vertex_finish<MODE>(a, valid, gv, e - b, j, pr, old, prod, K, u, fn, acc, s_dr, s_nr);
+    const double ffrac = pr.ffrac;
 
     // ---- pass 2 ----
     if constexpr (MODE == MODE_SWEEP) {
@@ -622,17 +718,6 @@ __global__ void __launch_bounds__(NT, 2) sbm_group_kernel(VertexArgs a) {
 // ---------------------------------------------------------------------------------------------
 // Hubs (degree > 256): one CTA per vertex, two passes over its incoming messages; the per-component
 // product is carried as (mantissa in [1,2), exponent) so any degree is safe.
-__device__ __forceinline__ void renorm(double& m, int& k) {
-  bool ok;
-  const int ex = exponent_of(m, ok);
-  if (ok) {
-    m *= pow2i(-ex);
-    k += ex;
-  } else if (m == m) {
-    m = 0.0;  // underflow: the component is negligible from here on (NaN stays NaN)
-  }
-}
-
 template <int MODE>
 __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base) {
   __shared__ double pmS[(NT / 32) * Q];
@@ -717,9 +802,20 @@ __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base
     const double prod = (d < -1022 || m == 0.0) ? 0.0 : m * pow2i(d > 0 ? 0 : d);
     const bool writer = lane < QP;
     const double old = (MODE == MODE_SWEEP && tl) ? a.PSI[(size_t)gv * Q + t] : 0.0;
-    double u, ffrac;
+    double row[QT];
+    prior_row(th, row);  // hubs are rare: no table, the prior is evaluated in place
+    Prior pr;
+    pr.E = 0.0;
+#pragma unroll
+    for (int k = 0; k < Q; ++k)
+      if (k == t) pr.E = row[k];
+    pr.ffrac = row[Q];
+    pr.fi = (int)row[Q + 1];
+    pr.xmax = row[Q + 2];
+    double u;
     int fn;
-    vertex_finish<MODE>(a, writer, gv, e1 - e0, t, th, old, prod, Ks + kcc, u, ffrac, fn, acc, s_dr, s_nr);
+    vertex_finish<MODE>(a, writer, gv, e1 - e0, t, pr, old, prod, Ks + kcc, u, fn, acc, s_dr, s_nr);
+    const double ffrac = pr.ffrac;
     if (writer) {
       if (tl) Ush[t] = u;
       if (t == 0) {
@@ -915,7 +1011,7 @@ __global__ void sbm_reduce_mstep(SbmState* st, const double* partials, int nrows
 // update_theta(), sbm.jl:47-64, and S_theta = sum_i theta_i PSI_i for the next update_h().
 __global__ void __launch_bounds__(NT) sbm_theta_kernel(const SbmState* st, const int* __restrict__ rowptr, int n,
                                                        const double* __restrict__ PSI, double* theta,
-                                                       double* partials) {
+                                                       unsigned char* __restrict__ blk, double* partials) {
   __shared__ double red[(NT / 32) * Q];
   double acc[Q];
 #pragma unroll
@@ -933,6 +1029,7 @@ __global__ void __launch_bounds__(NT) sbm_theta_kernel(const SbmState* st, const
       }
     const double th = (double)(rowptr[i + 1] - rowptr[i]) / st->drmean[best];
     theta[i] = th;
+    blk[i] = (unsigned char)best;
 #pragma unroll
     for (int t = 0; t < Q; ++t) acc[t] = fma(th, p[t], acc[t]);
   }
@@ -949,7 +1046,8 @@ __global__ void sbm_reduce_theta(SbmState* st, const double* partials, int nrows
 // ---------------------------------------------------------------------------------------------
 // Per-iteration parameters: gr clamp (sbm.jl:89-96), h = update_h() (sbm.jl:70-73), logs; written to a
 // global staging struct that the host copies device->constant in stream order.
-__global__ void sbm_prepare(SbmState* st, SbmParams* out, double N, int zero_h, int gr_from_sum) {
+__global__ void sbm_prepare(SbmState* st, SbmParams* out, double N, int zero_h, int gr_from_sum, int dc_range,
+                            double maxdeg) {
   __shared__ double g[Q];
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -979,6 +1077,35 @@ __global__ void sbm_prepare(SbmState* st, SbmParams* out, double N, int zero_h, 
   for (int k = tid; k < Q * Q; k += blockDim.x) {
     out->C[k] = st->C[k];
     out->logC[k] = log(st->C[k]);
+  }
+  if (tid == 0) {
+    // Largest degree for which a plain product of edge factors provably stays inside the double range:
+    // factor in [thmin^2 Cmin, thmax^2 Cmax] with theta = degree / <degree of the block> in [1/dmax, maxdeg/dmin].
+    double cmin = INFINITY, cmax = 0.0;
+    for (int k = 0; k < Q * Q; ++k) {
+      cmin = fmin(cmin, st->C[k]);
+      cmax = fmax(cmax, st->C[k]);
+    }
+    double tmin = 1.0, tmax = 1.0;
+    if (dc_range) {
+      double dmin = INFINITY, dmax = 0.0;
+      for (int r = 0; r < Q; ++r) {
+        const double d = st->drmean[r];
+        if (d == d) {
+          dmin = fmin(dmin, d);
+          dmax = fmax(dmax, d);
+        }
+      }
+      if (dmax > 0.0 && dmin > 0.0) {
+        tmin = 1.0 / dmax;
+        tmax = maxdeg / dmin;
+      }
+    }
+    const double lo = fabs(log2(tmin * tmin * cmin)), hi = fabs(log2(tmax * tmax * cmax));
+    const double worst = fmax(fmax(lo, hi), 1.0);
+    int sd = 0;
+    if (worst == worst && worst < INFINITY) sd = (int)fmin(900.0 / worst, (double)TILE_E);
+    out->safe_deg = sd;
   }
 }
 
@@ -1139,6 +1266,9 @@ VertexArgs vertex_args(gbx_sbm* h) {
   a.nmain = h->nmain;
   a.hubs = h->hubs;
   a.theta = h->theta;
+  a.blk = h->blk;
+  a.prior_tab = h->prior_tab;
+  a.dc_tab = h->opt.degreecorrection && h->theta_valid;
   a.cur = h->msg[h->cur];
   a.nxt = h->msg[h->cur ^ 1];
   a.PSI = h->PSI;
@@ -1182,10 +1312,18 @@ int op_reduce_vertex(gbx_sbm* h, int mode) {
 }
 
 int op_prepare(gbx_sbm* h, int zero_h, int gr_from_sum) {
-  sbm_prepare<<<1, 64, 0, h->stream>>>(h->st, h->params, (double)h->n, zero_h, gr_from_sum);
+  const int dc_tab = h->opt.degreecorrection && h->theta_valid;
+  sbm_prepare<<<1, 64, 0, h->stream>>>(h->st, h->params, (double)h->n, zero_h, gr_from_sum, dc_tab,
+                                  (double)h->max_degree);
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
   GBX_CUDA_TRY(cudaMemcpyToSymbolAsync(c_P, h->params, sizeof(SbmParams), 0, cudaMemcpyDeviceToDevice, h->stream));
+  {
+    const int nrows = dc_tab ? 1 + (TILE_E + 1) * Q : 1;
+    sbm_prior_table<<<(nrows + 127) / 128, 128, 0, h->stream>>>(h->st, h->prior_tab, dc_tab);
+    h->launches++;
+    GBX_CUDA_TRY(cudaGetLastError());
+  }
   return GBX_OK;
 }
 
@@ -1200,7 +1338,9 @@ int op_mstep(gbx_sbm* h) {
 }
 
 int op_theta(gbx_sbm* h) {
-  sbm_theta_kernel<<<h->grid_theta, NT, 0, h->stream>>>(h->st, h->rowptr, (int)h->n, h->PSI, h->theta, h->part_theta);
+  sbm_theta_kernel<<<h->grid_theta, NT, 0, h->stream>>>(h->st, h->rowptr, (int)h->n, h->PSI, h->theta, h->blk,
+                                                        h->part_theta);
+  h->theta_valid = true;
   sbm_reduce_theta<<<1, 256, 0, h->stream>>>(h->st, h->part_theta, h->grid_theta);
   h->launches += 2;
   if (h->ntiles > 0 && h->sweep_variant != 0) {
