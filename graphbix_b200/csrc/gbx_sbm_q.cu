@@ -197,8 +197,7 @@ __device__ __forceinline__ unsigned group_bits(unsigned ballot) {
 // EM iteration per (degree, block) by sbm_prior_table and read here as one coalesced row.
 constexpr int QT = Q + 3;
 struct Prior {
-  double E, ffrac, xmax;
-  int fi;
+  double E, ffrac, xmax, fi;  // fi is an integer kept as a double so that loading it does not stall on a conversion
 };
 
 __device__ __forceinline__ void prior_row(double th, double* row /* QT */) {
@@ -238,7 +237,7 @@ __device__ __forceinline__ Prior load_prior(const VertexArgs& a, bool valid, int
   const double* row = a.prior_tab + (size_t)r * QT;
   pr.E = (t < Q) ? row[t] : 0.0;
   pr.ffrac = row[Q];
-  pr.fi = (int)row[Q + 1];
+  pr.fi = row[Q + 1];
   pr.xmax = (MODE == MODE_LOGZ) ? row[Q + 2] : 0.0;
   return pr;
 }
@@ -253,7 +252,7 @@ __device__ __forceinline__ void vertex_finish(const VertexArgs& a, bool valid, i
   const bool tl = t < Q;
   const double u = tl ? pr.E * prod : 0.0;
   u_out = u;
-  fn = pr.fi - K;
+  fn = (int)pr.fi - K;
   if constexpr (MODE == MODE_LOGZ) {
     // logsumexp(logunnormalizedMessage(i)), sbm.jl:153, with the 500 cut-off of sbm.jl:33-35
     const double umax = group_max(u);
@@ -477,12 +476,6 @@ __global__ void __launch_bounds__(NT, (Q <= 8) ? 3 : 2) sbm_vertex_kernel(Vertex
   int buf = 0;
   for (int tile = blockIdx.x; tile < a.ntiles; tile += G) {
     const int v0 = td.x, nv = td.y, e0 = td.z, ne = td.w;
-    // ---- copies of tile k+1 (other buffer), then the descriptor of tile k+2 into the same registers ----
-    const bool hasN = tile + G < a.ntiles;
-    stage_tile(a, tdN.z, hasN ? tdN.w : 0, psiS + (size_t)(buf ^ 1) * TILE_E * ROWB, scS + (buf ^ 1) * TILE_E);
-    cp_async_commit();
-    const int4 tdK1 = tdN;
-    tdN = a.tiles[min(tile + 2 * G, last)];
     // ---- this tile's small global reads, consumed one or two stages later ----
     int rv = 0;
     if (MODE == MODE_SWEEP && tid < ne) rv = a.rev[e0 + tid];
@@ -499,6 +492,12 @@ __global__ void __launch_bounds__(NT, (Q <= 8) ? 3 : 2) sbm_vertex_kernel(Vertex
       pr = load_prior<MODE>(a, valid, v0 + vlane, re - rb, t);
     }
 
+    // ---- copies of tile k+1 (other buffer), then the descriptor of tile k+2 into the same registers ----
+    const bool hasN = tile + G < a.ntiles;
+    stage_tile(a, tdN.z, hasN ? tdN.w : 0, psiS + (size_t)(buf ^ 1) * TILE_E * ROWB, scS + (buf ^ 1) * TILE_E);
+    cp_async_commit();
+    const int4 tdK1 = tdN;
+    tdN = a.tiles[min(tile + 2 * G, last)];
     // ---- stage 1 ----
     double T[Q];
     if (tid < ne) {
@@ -810,7 +809,7 @@ __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base
     for (int k = 0; k < Q; ++k)
       if (k == t) pr.E = row[k];
     pr.ffrac = row[Q];
-    pr.fi = (int)row[Q + 1];
+    pr.fi = row[Q + 1];
     pr.xmax = row[Q + 2];
     double u;
     int fn;

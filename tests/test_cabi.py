@@ -1,0 +1,60 @@
+"""CPU: the C-ABI library loads, exports every symbol include/graphbix_cuda.h declares, and fails loudly (no CPU
+fallback) when no CUDA device is present."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "graphbix_cuda.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gbx_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from graphbix_b200 import _lib
+    lib = _lib.load()
+    syms = _header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/graphbix_cuda.h but not exported"
+    assert sorted(_lib.SIGNATURES) == syms, "ctypes SIGNATURES and the header disagree"
+    assert lib.gbx_version() >= 100
+
+
+def test_struct_layouts_match_header():
+    from graphbix_b200 import _lib
+    opt = _lib.SbmOptions()
+    _lib.load().gbx_sbm_default_options(ctypes.byref(opt))
+    assert (opt.degreecorrection, opt.priorlearning, opt.itrmax, opt.check_every) == (1, 1, 256, 1)
+    assert opt.learningrate == pytest.approx(0.3) and opt.bp_conv_threshold == pytest.approx(1e-6)
+    assert opt.damping == 1.0 and opt.maxCrs == 0.0
+
+
+def test_no_cpu_fallback():
+    """Without a GPU every compute entry point must raise; nothing may quietly run on the host."""
+    from graphbix_b200 import _lib
+    lib = _lib.load()
+    if lib.gbx_device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    from graphbix_b200.engine import EM, SbmEngine
+    links = np.array([[1, 2], [2, 1]], dtype=np.int64)
+    with pytest.raises(_lib.GbxError):
+        SbmEngine(2, links, 2)
+    with pytest.raises(_lib.GbxError):
+        EM(2, 2, links, 2, "uniformAssortative", True, 4, True, 0.3)
+
+
+def test_product_does_not_import_the_oracle():
+    """oracle/ is test infrastructure: nothing under graphbix_b200/ may import or execute it."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "graphbix_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)
+                assert "oracle/" not in src and "sbm_oracle" not in src, os.path.join(dirpath, f)
