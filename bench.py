@@ -40,7 +40,7 @@ UNIT = "updates/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=1_000_000)
@@ -59,35 +59,46 @@ def workload_name(a):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md), streamed every 20 ms."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.index, self.samples, self.proc = index, [], None
+        self.marks = []  # (label, sample index) so that only samples taken under load are summarised
 
     def run(self):
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                f = [x.strip() for x in line.strip().split(",")]
                 if len(f) >= 6:
                     self.samples.append(f)
-            except Exception:
-                pass
-            self.stop_flag.wait(0.1)
+        except Exception:
+            pass
+
+    def mark(self, label):
+        self.marks.append((label, len(self.samples)))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
 
     def summary(self):
-        if not self.samples:
+        lo = dict(self.marks).get("start", 0)
+        hi = dict(self.marks).get("stop", len(self.samples))
+        sel = self.samples[lo:hi] or self.samples
+        if not sel:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        sm = sorted(float(s[0]) for s in sel if s[0].replace(".", "").isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]),
-                "reasons": reasons, "samples": len(self.samples)}
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in sel)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(sel[0][1]), "reasons": reasons,
+                "samples": len(sel)}
 
 
 def measured_peak_gbs():
@@ -186,10 +197,12 @@ def run_ours(a):
     eng.init(gr0, C0, None, seed=1234 + rank)
 
     # ---- device-resident EM iterations ----
-    eng.iterate(a.warmup, read_conv=False)
-    barrier()
     sampler = ClockSampler(local)
     sampler.start()
+    time.sleep(0.3)
+    eng.iterate(a.warmup, read_conv=False)
+    barrier()
+    sampler.mark("start")
     l0 = eng.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
@@ -208,8 +221,8 @@ def run_ours(a):
     s1.record(stream)
     torch.cuda.synchronize()
     sweep_ms = s0.elapsed_time(s1) / nsweep
-    sampler.stop_flag.set()
-    sampler.join()
+    sampler.mark("stop")
+    sampler.stop()
     sweep_bytes = eng.sweep_bytes
     dev_bytes = eng.device_bytes
     eng.close()
@@ -218,10 +231,12 @@ def run_ours(a):
     psi0 = random_messages(K, a.q, seed=55 + rank)
     barrier()
     t0 = time.perf_counter()
-    out = EM(n, a.q, links, n, (gr0, C0), bool(a.dc), a.steps, True, 0.3, PSIcav0=psi0, BPconvthreshold=0.0,
-             device=local)
+    out, eng2, res2 = EM(n, a.q, links, n, (gr0, C0), bool(a.dc), a.steps, True, 0.3, PSIcav0=psi0,
+                         BPconvthreshold=0.0, device=local, return_engine=True)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
+    e2e_parts = dict(eng2.timings)
+    eng2.close()
     h2d = links.nbytes + psi0.nbytes
     d2h = out[2].nbytes + out[1].nbytes + out[0].nbytes
 
@@ -244,7 +259,7 @@ def run_ours(a):
                            "l2_policy": f"inputs larger than L2: {dev_bytes / 1e6:.0f} MB resident per GPU vs 126 MB L2",
                            "step": "one EM iteration = BP sweep + update_Crs + update_theta"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / a.steps,
-                        "d2h_bytes_per_step": d2h / a.steps, "seconds": t_e2e,
+                        "d2h_bytes_per_step": d2h / a.steps, "seconds": t_e2e, "breakdown_s": e2e_parts,
                         "what": "EM() with host buffers: CSR build, H2D, steps iterations, free energy + CV, D2H"},
                 "gpu_launches": launches, "clocks": sampler.summary(),
                 "roofline": {"bound": "hbm", "kernel": "sbm_vertex_kernel<8,SWEEP> (BP sweep)", "achieved": achieved,

@@ -9,6 +9,7 @@ reference's argument order and returns the same 15-tuple
 from __future__ import annotations
 
 import ctypes as C
+import time
 
 import numpy as np
 
@@ -38,10 +39,13 @@ class SbmEngine:
         if links.ndim != 2 or links.shape[1] != 2:
             raise ValueError("links must be K x 2")
         self.n, self.q, self.K = int(Ntot), int(B), int(links.shape[0])
+        self.timings = {}
+        t0 = time.perf_counter()
         colmajor = np.asfortranarray(links, dtype=np.int64)  # Julia's memory layout of the K x 2 matrix
         self._h = C.c_void_p()
         check(self.lib.gbx_sbm_create(C.byref(self._h), int(device), self.n, self.K,
                                       colmajor.ctypes.data_as(C.POINTER(C.c_int64)), self.q))
+        self.timings["create"] = time.perf_counter() - t0
         self.opt = SbmOptions()
         self.lib.gbx_sbm_default_options(C.byref(self.opt))
         if stream is not None:
@@ -81,12 +85,16 @@ class SbmEngine:
         gr = _f64(gr, (self.q,)) if gr is not None else None
         Crs = _f64(Crs, (self.q, self.q))
         psicav = _f64(psicav, (self.K, self.q))
+        t0 = time.perf_counter()
         check(self.lib.gbx_sbm_init(self._h, _dp(gr), _dp(Crs), _dp(psicav), C.c_uint64(seed)))
+        self.timings["init"] = time.perf_counter() - t0
 
     # -- running ----------------------------------------------------------------------------
     def em(self) -> SbmResult:
         res = SbmResult()
+        t0 = time.perf_counter()
         check(self.lib.gbx_sbm_em(self._h, C.byref(res)))
+        self.timings["em"] = time.perf_counter() - t0
         return res
 
     def iterate(self, n: int = 1, read_conv: bool = True):
@@ -110,7 +118,9 @@ class SbmEngine:
         h = np.empty(q)
         P = np.empty((n, q)) if PSI else None
         th = np.empty(n) if theta else None
+        t0 = time.perf_counter()
         check(self.lib.gbx_sbm_get_state(self._h, _dp(gr), _dp(Crs), _dp(P), _dp(th), _dp(h)))
+        self.timings["get_state"] = time.perf_counter() - t0
         return dict(gr=gr, Crs=Crs, PSI=P, theta=th, h=h)
 
     def messages(self):

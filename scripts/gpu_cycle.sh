@@ -10,5 +10,8 @@ bench_group) GBX_SWEEP=group $B --steps 20 --warmup 3 > gpurun_out/bench_group.j
 launches) $B --steps 4 --warmup 3 > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 150 --csv --log-file gpurun_out/launches.csv $B --steps 4 --warmup 3 > gpurun_out/ncu.log 2>&1; echo "launches rc=$?" ;;
 prof_sweep) $B --steps 3 --warmup 3 > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'sbm_(group|vertex)_kernel' -s 4 -c 1 -o gpurun_out/prof_sweep -f $B --steps 3 --warmup 3 > gpurun_out/ncu_sweep.log 2>&1; echo "prof_sweep rc=$?" ;;
 prof_mstep) $B --steps 3 --warmup 3 > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:sbm_mstep_kernel -s 3 -c 1 -o gpurun_out/prof_mstep -f $B --steps 3 --warmup 3 > gpurun_out/ncu_mstep.log 2>&1; echo "prof_mstep rc=$?" ;;
+fullbench) python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo "fullbench rc=$?"; python scripts/show_bench.py gpurun_out/bench_full.json; tail -3 gpurun_out/bench_full.err ;;
+refbench) python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "refbench rc=$?"; cut -c1-400 gpurun_out/bench_ref.json ;;
+smoke) python -c "import __graft_entry__ as g; g.smoke()" ;;
 esac
 done
