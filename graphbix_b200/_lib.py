@@ -33,6 +33,20 @@ class SbmResult(C.Structure):
                 ("max_dpsi", C.c_double)]
 
 
+class ModOptions(C.Structure):
+    _fields_ = [("dc", C.c_int), ("learning", C.c_int), ("priorlearning", C.c_int), ("learningrate", C.c_double),
+                ("maxomega", C.c_double), ("itrmax", C.c_int), ("betafrac", C.c_double),
+                ("bp_conv_threshold", C.c_double), ("damping", C.c_double), ("check_every", C.c_int)]
+
+
+class ModResult(C.Structure):
+    _fields_ = [("excm", C.c_double), ("alpha", C.c_double), ("beta", C.c_double), ("omegain", C.c_double),
+                ("omegaout", C.c_double), ("FE", C.c_double), ("CVBayes", C.c_double), ("CVGP", C.c_double),
+                ("CVGT", C.c_double), ("CVMAP", C.c_double), ("varCVBayes", C.c_double), ("varCVGP", C.c_double),
+                ("varCVGT", C.c_double), ("varCVMAP", C.c_double), ("cnv", C.c_int), ("itrnum", C.c_int),
+                ("itrs_done", C.c_int), ("nonfinite", C.c_int), ("BPconv", C.c_double), ("max_dpsi", C.c_double)]
+
+
 # name -> (restype, argtypes); every symbol include/graphbix_cuda.h declares
 _P = C.c_void_p
 _D = C.POINTER(C.c_double)
@@ -57,6 +71,19 @@ SIGNATURES = {
     "gbx_sbm_num_links": (C.c_int64, [_P]),
     "gbx_sbm_device_bytes": (C.c_int64, [_P]),
     "gbx_sbm_sweep_bytes": (C.c_double, [_P]),
+    "gbx_mod_default_options": (None, [C.POINTER(ModOptions)]),
+    "gbx_mod_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.c_int]),
+    "gbx_mod_destroy": (C.c_int, [_P]),
+    "gbx_mod_set_stream": (C.c_int, [_P, _P]),
+    "gbx_mod_set_options": (C.c_int, [_P, C.POINTER(ModOptions)]),
+    "gbx_mod_init": (C.c_int, [_P, _D, _D, C.c_uint64]),
+    "gbx_mod_em": (C.c_int, [_P, C.POINTER(ModResult)]),
+    "gbx_mod_iterate": (C.c_int, [_P, C.c_int, _D]),
+    "gbx_mod_finalize": (C.c_int, [_P, C.POINTER(ModResult)]),
+    "gbx_mod_get_state": (C.c_int, [_P, _D, _D, _D, _D]),
+    "gbx_mod_get_messages": (C.c_int, [_P, _D]),
+    "gbx_mod_get_assignment": (C.c_int, [_P, C.POINTER(C.c_int32)]),
+    "gbx_mod_launch_count": (C.c_int64, [_P]),
 }
 
 _lib = None

@@ -50,9 +50,10 @@ def build(qs=None, force=False, verbose=False):
         return OUT
     jobs = []
     for q in qs:
-        o = os.path.join(OBJ, f"gbx_sbm_q{q}.o")
-        jobs.append((o, [NVCC, *FLAGS, f"-DGBX_Q={q}", "-c", os.path.join(HERE, "gbx_sbm_q.cu"), "-o", o]
-                     + (["-Xptxas", "-v"] if verbose else [])))
+        for model, tag in ((0, "sbm"), (1, "mod")):
+            o = os.path.join(OBJ, f"gbx_{tag}_q{q}.o")
+            jobs.append((o, [NVCC, *FLAGS, f"-DGBX_Q={q}", f"-DGBX_MODEL={model}", "-c",
+                             os.path.join(HERE, "gbx_sbm_q.cu"), "-o", o] + (["-Xptxas", "-v"] if verbose else [])))
     foreach = "-DGBX_FOR_EACH_Q(X)=" + " ".join(f"X({q})" for q in qs)
     ho = os.path.join(OBJ, "gbx_sbm_host.o")
     jobs.append((ho, [NVCC, *FLAGS, foreach, "-c", os.path.join(HERE, "gbx_sbm_host.cu"), "-o", ho]))

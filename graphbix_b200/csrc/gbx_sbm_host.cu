@@ -10,6 +10,7 @@
 //   * PSI (N x q), theta (N); tiles = runs of consecutive vertices with <= 256 edge slots (one CTA iteration
 //     each, one thread per slot); vertices with more than 256 edges ("hubs") get a CTA each.
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -27,13 +28,15 @@ std::string& last_error() {
 #ifndef GBX_FOR_EACH_Q
 #define GBX_FOR_EACH_Q(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
 #endif
-#define GBX_DECL(qq) const SbmOps* sbm_ops_q##qq();
+#define GBX_DECL(qq)              \
+  const SbmOps* sbm_ops_q##qq(); \
+  const SbmOps* mod_ops_q##qq();
 GBX_FOR_EACH_Q(GBX_DECL)
 #undef GBX_DECL
 
-static const SbmOps* ops_for(int q) {
+static const SbmOps* ops_for(int model, int q) {
 #define GBX_CASE(qq) \
-  if (q == qq) return sbm_ops_q##qq();
+  if (q == qq) return model == 1 ? mod_ops_q##qq() : sbm_ops_q##qq();
   GBX_FOR_EACH_Q(GBX_CASE)
 #undef GBX_CASE
   return nullptr;
@@ -122,11 +125,11 @@ void gbx_sbm_default_options(gbx_sbm_options* opt) {
   opt->check_every = 1;
 }
 
-int gbx_sbm_create(gbx_sbm** out, int device, int64_t n, int64_t K, const int64_t* links, int q) {
+static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t K, const int64_t* links, int q) {
   if (!out) return fail_invalid("out is NULL");
   *out = nullptr;
   if (q < 1 || q > MAXQ) return fail_invalid("q must be in 1..16");
-  const SbmOps* ops = ops_for(q);
+  const SbmOps* ops = ops_for(model, q);
   if (!ops) return fail_invalid("this build of libgraphbix_cuda was compiled without that q");
   if (n < 1 || K < 0 || (K > 0 && !links)) return fail_invalid("bad n_vertices / n_links / links");
   if (n >= (int64_t)1 << 31 || K >= (int64_t)1 << 31) return fail_invalid("graph too large for 32-bit slots");
@@ -241,7 +244,21 @@ int gbx_sbm_create(gbx_sbm** out, int device, int64_t n, int64_t K, const int64_
   for (int64_t v = 0; v < n; ++v) h->max_degree = std::max(h->max_degree, rowptr[(size_t)v + 1] - rowptr[(size_t)v]);
   {
     const char* env = getenv("GBX_SWEEP");
-    h->sweep_variant = (env && std::string(env) == "group") ? 0 : 1;
+    h->sweep_variant = (env && std::string(env) == "group" && model == 0) ? 0 : 1;
+  }
+  h->model = model;
+  gbx_mod_default_options(&h->mopt);
+  {
+    // mod.jl:155 constshift = sum_i d_i log d_i / L and mod.jl:185 excm, from the true degrees
+    double sdl = 0.0, sd2 = 0.0, sd = 0.0;
+    for (int64_t v = 0; v < n; ++v) {
+      const double d = (double)(rowptr[(size_t)v + 1] - rowptr[(size_t)v]);
+      if (d > 0) sdl += d * std::log(d);
+      sd2 += d * d;
+      sd += d;
+    }
+    h->constshift = K > 0 ? sdl / (0.5 * (double)K) : 0.0;
+    h->excm = sd > 0 ? sd2 / sd - 1.0 : 0.0;  // (d'd)/(N mean(d)) - 1
   }
   h->nhubs = (int)hubs.size();
   gbx_sbm_default_options(&h->opt);
@@ -316,6 +333,10 @@ int gbx_sbm_create(gbx_sbm** out, int device, int64_t n, int64_t K, const int64_
   return GBX_OK;
 }
 
+int gbx_sbm_create(gbx_sbm** out, int device, int64_t n, int64_t K, const int64_t* links, int q) {
+  return graph_create(0, out, device, n, K, links, q);
+}
+
 int gbx_sbm_destroy(gbx_sbm* h) {
   if (!h) return GBX_OK;
   cudaSetDevice(h->device);
@@ -364,6 +385,7 @@ int gbx_sbm_set_options(gbx_sbm* h, const gbx_sbm_options* opt) {
 
 int gbx_sbm_init(gbx_sbm* h, const double* gr_init, const double* Crs_init, const double* psicav, uint64_t seed) {
   if (!h || !Crs_init) return fail_invalid("handle/Crs_init is NULL");
+  if (h->model != 0) return fail_invalid("not a gbx_sbm handle");
   if (h->opt.priorlearning && !gr_init) return fail_invalid("gr_init is NULL with priorlearning on");
   GBX_TRY(set_device(h));
   const int q = h->q;
@@ -540,5 +562,165 @@ double gbx_sbm_sweep_bytes(const gbx_sbm* h) {
   if (h->opt.degreecorrection) per_vertex += 8.0;
   return K * per_edge + n * per_vertex;
 }
+
+// ---------------------------------------------------------------------------------------------
+// mod.jl
+// ---------------------------------------------------------------------------------------------
+void gbx_mod_default_options(gbx_mod_options* opt) {
+  opt->dc = 1;
+  opt->learning = 1;
+  opt->priorlearning = 0;
+  opt->learningrate = 0.3;
+  opt->maxomega = 1.0;
+  opt->itrmax = 256;
+  opt->betafrac = 0.0;
+  opt->bp_conv_threshold = 0.000001;
+  opt->damping = 1.0;
+  opt->check_every = 1;
+}
+
+int gbx_mod_create(gbx_mod** out, int device, int64_t n, int64_t K, const int64_t* links, int q) {
+  return graph_create(1, out, device, n, K, links, q);
+}
+int gbx_mod_destroy(gbx_mod* h) { return gbx_sbm_destroy(h); }
+int gbx_mod_set_stream(gbx_mod* h, void* s) { return gbx_sbm_set_stream(h, s); }
+
+int gbx_mod_set_options(gbx_mod* h, const gbx_mod_options* opt) {
+  if (!h || !opt) return fail_invalid("handle/options is NULL");
+  if (h->model != 1) return fail_invalid("not a gbx_mod handle");
+  if (!(opt->damping > 0.0 && opt->damping <= 1.0)) return fail_invalid("damping must be in (0,1]");
+  if (!(opt->learningrate >= 0.0 && opt->learningrate <= 1.0)) return fail_invalid("learningrate must be in [0,1]");
+  if (opt->itrmax < 0) return fail_invalid("itrmax must be >= 0");
+  h->mopt = *opt;
+  if (h->mopt.check_every < 1) h->mopt.check_every = 1;
+  return GBX_OK;
+}
+
+int gbx_mod_init(gbx_mod* h, const double* gr, const double* psicav, uint64_t seed) {
+  if (!h || !gr) return fail_invalid("handle/gr is NULL");
+  if (h->model != 1) return fail_invalid("not a gbx_mod handle");
+  GBX_TRY(set_device(h));
+  const int q = h->q;
+  SbmState s;
+  memset(&s, 0, sizeof s);
+  for (int r = 0; r < q; ++r) s.gr[r] = gr[r];
+  // mod.jl:185-196
+  const double excm = h->excm, B = (double)q;
+  const double beta0 = std::log(1.0 + B / (excm - 1.0));
+  const double betaast = std::log(1.0 + B / (std::sqrt(excm) - 1.0));
+  s.alpha = 1.0 / (double)h->K;
+  s.beta = betaast - h->mopt.betafrac * (betaast - beta0);
+  s.omegain = std::exp(s.beta) * s.alpha * s.beta / (std::exp(s.beta) - 1.0);
+  s.omegaout = s.alpha * s.beta / (std::exp(s.beta) - 1.0);
+  GBX_CUDA_TRY(cudaMemcpyAsync(h->st, &s, sizeof s, cudaMemcpyHostToDevice, h->stream));
+  GBX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->cur = 0;
+  h->itr = 0;
+  h->fail = 0;
+  if (psicav) {
+    double* tmp = h->msg[1];
+    GBX_CUDA_TRY(cudaMemcpyAsync(tmp, psicav, (size_t)h->K * q * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    GBX_TRY(h->ops->permute(h, tmp, h->msg[0], 1));
+  } else {
+    GBX_TRY(h->ops->random_messages(h, seed));
+  }
+  // h = zeros(1,B); PSI = updatePSI(): mod.jl:204-206
+  GBX_TRY(h->ops->prepare(h, 1, 0));
+  GBX_TRY(h->ops->vertex_pass(h, MODE_MARGINAL));
+  GBX_TRY(h->ops->reduce_vertex(h, MODE_MARGINAL));
+  GBX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->initialised = true;
+  return GBX_OK;
+}
+
+static int mod_iteration(gbx_sbm* h) {
+  const SbmOps* op = h->ops;
+  GBX_TRY(op->prepare(h, 0, 0));              // h = update_h()                       mod.jl:56
+  GBX_TRY(op->vertex_pass(h, MODE_SWEEP));    // messages, marginals, residual        mod.jl:57-73
+  h->cur ^= 1;
+  GBX_TRY(op->reduce_vertex(h, MODE_SWEEP));  // conv; gr = update_gr(PSI)            mod.jl:221-223
+  if (h->mopt.learning) GBX_TRY(op->mstep(h));  // omegas, alpha, beta                mod.jl:224-229
+  h->itr++;
+  return GBX_OK;
+}
+
+int gbx_mod_iterate(gbx_mod* h, int n_iters, double* bpconv_out) {
+  if (!h) return fail_invalid("handle is NULL");
+  if (!h->initialised || h->model != 1) return fail_state();
+  GBX_TRY(set_device(h));
+  for (int i = 0; i < n_iters; ++i) GBX_TRY(mod_iteration(h));
+  if (bpconv_out) {
+    GBX_TRY(read_state(h));
+    *bpconv_out = h->h_state->conv;
+  }
+  return GBX_OK;
+}
+
+int gbx_mod_finalize(gbx_mod* h, gbx_mod_result* res) {
+  if (!h || !res) return fail_invalid("handle/result is NULL");
+  if (!h->initialised || h->model != 1) return fail_state();
+  GBX_TRY(set_device(h));
+  memset(res, 0, sizeof *res);
+  GBX_TRY(h->ops->prepare(h, 0, 0));   // h = update_h()   mod.jl:240
+  GBX_TRY(h->ops->free_energy(h));     // freeenergy()     mod.jl:241
+  GBX_TRY(read_state(h));
+  const SbmState* s = h->h_state;
+  res->excm = h->excm;
+  res->alpha = s->alpha;
+  res->beta = s->beta;
+  res->omegain = s->omegain;
+  res->omegaout = s->omegaout;
+  res->FE = s->result[0];
+  res->CVBayes = s->result[1];
+  res->CVGP = s->result[2];
+  res->CVGT = s->result[3];
+  res->CVMAP = s->result[4];
+  res->varCVBayes = s->result[5];
+  res->varCVGP = s->result[6];
+  res->varCVGT = s->result[7];
+  res->varCVMAP = s->result[8];
+  res->BPconv = s->conv;
+  res->max_dpsi = s->maxd;
+  res->nonfinite = s->status & 1;
+  res->itrs_done = h->itr;
+  return GBX_OK;
+}
+
+int gbx_mod_em(gbx_mod* h, gbx_mod_result* res) {
+  if (!h || !res) return fail_invalid("handle/result is NULL");
+  if (!h->initialised || h->model != 1) return fail_state();
+  GBX_TRY(set_device(h));
+  int cnv = 0, itrnum = 0;
+  for (int itr = 1; itr <= h->mopt.itrmax; ++itr) {
+    GBX_TRY(mod_iteration(h));
+    if (itr % h->mopt.check_every == 0 || itr == h->mopt.itrmax) {
+      GBX_TRY(read_state(h));
+      if (h->h_state->conv < h->mopt.bp_conv_threshold) {  // mod.jl:230-234
+        cnv = 1;
+        itrnum = itr;
+        break;
+      }
+    }
+  }
+  GBX_TRY(gbx_mod_finalize(h, res));
+  res->cnv = cnv;
+  res->itrnum = itrnum;
+  return GBX_OK;
+}
+
+int gbx_mod_get_state(gbx_mod* h, double* gr, double* PSI, double* hfield, double* params) {
+  if (!h) return fail_invalid("handle is NULL");
+  GBX_TRY(gbx_sbm_get_state(h, gr, nullptr, PSI, nullptr, hfield));
+  if (params) {
+    params[0] = h->h_state->alpha;
+    params[1] = h->h_state->beta;
+    params[2] = h->h_state->omegain;
+    params[3] = h->h_state->omegaout;
+  }
+  return GBX_OK;
+}
+int gbx_mod_get_messages(gbx_mod* h, double* psicav) { return gbx_sbm_get_messages(h, psicav); }
+int gbx_mod_get_assignment(gbx_mod* h, int32_t* block) { return gbx_sbm_get_assignment(h, block); }
+int64_t gbx_mod_launch_count(const gbx_mod* h) { return gbx_sbm_launch_count(h); }
 
 }  // extern "C"

@@ -16,6 +16,7 @@ struct SbmParams {
   double lgr[MAXQ];          // log(gr) after the clamp of sbm.jl:89-96
   double h[MAXQ];            // external field, sbm.jl:70-73
   double logN;
+  double eb1;                // e^beta - 1 (mod.jl)
   int safe_deg;              // largest degree whose plain product of edge factors cannot leave the double range
   int pad_;
 };
@@ -31,10 +32,13 @@ struct SbmState {
   double conv, maxd, sumlogZi;
   double cvsum[4], cvmean[4], cvss[4];
   double result[12];
+  // mod.jl (community-restricted SBM) scalars
+  double omegain, omegaout, alpha, beta, hn2;
+  double cv5sum[5], cv5mean[5], cv5ss[5];
   int status;  // bit 0: non-finite / non-positive value met in a kernel
 };
 
-constexpr int PSTRIDE = 3 * MAXQ + 4;  // per-CTA partial row of the vertex kernels
+constexpr int PSTRIDE = 4 * MAXQ + 4;  // per-CTA partial row of the vertex kernels
 enum { MODE_SWEEP = 0, MODE_MARGINAL = 1, MODE_LOGZ = 2 };
 
 constexpr int tile_vertices(int q) { return (q <= 8) ? TILE_V : TILE_V / 2; }
@@ -48,6 +52,10 @@ struct gbx_sbm {
   int64_t n = 0, K = 0;
   cudaStream_t stream = nullptr;
   gbx_sbm_options opt{};
+  int model = 0;                  // 0: sbm.jl, 1: mod.jl (same handle type behind gbx_mod*)
+  gbx_mod_options mopt{};
+  double constshift = 0.0;        // sum_i d_i log d_i / L (mod.jl:155), 0 without degree correction
+  double excm = 0.0;              // mean excess degree (mod.jl:185)
   bool initialised = false;
   int fail = 0;
   int64_t launches = 0, dev_bytes = 0;

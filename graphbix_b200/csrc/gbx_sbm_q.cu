@@ -22,6 +22,11 @@
 namespace gbx {
 namespace {
 
+#ifndef GBX_MODEL
+#define GBX_MODEL 0
+#endif
+constexpr int MODEL = GBX_MODEL;  // 0: full-affinity SBM (sbm.jl), 1: community-restricted SBM (mod.jl)
+constexpr int MODEL_SBM = 0, MODEL_MOD = 1;
 constexpr int Q = GBX_Q;
 constexpr int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 constexpr int QP = next_pow2(Q);     // lanes per vertex in the aggregation stage (padding lanes idle when Q != 2^k)
@@ -126,10 +131,14 @@ __device__ __forceinline__ void edge_transform(const double (&psi)[Q], double sc
   double m = 0.0;
 #pragma unroll
   for (int t = 0; t < Q; ++t) {
-    double acc = 0.0;
+    if constexpr (MODEL == MODEL_MOD) {
+      T[t] = fma(psi[t], c_P.eb1, 1.0);  // 1 + psi (e^beta - 1), mod.jl:42
+    } else {
+      double acc = 0.0;
 #pragma unroll
-    for (int s = 0; s < Q; ++s) acc = fma(psi[s], c_P.C[s * Q + t], acc);
-    T[t] = acc * sc;
+      for (int s = 0; s < Q; ++s) acc = fma(psi[s], c_P.C[s * Q + t], acc);
+      T[t] = acc * sc;
+    }
     m = fmax(m, T[t]);
   }
   bool ok;
@@ -179,6 +188,7 @@ __device__ __forceinline__ void emit_message(const VertexArgs& a, const double* 
 // Per-thread accumulators of the aggregation lanes (lane t of a group owns component t).
 struct LaneAcc {
   double psi = 0.0;   // sum of PSI_i(t)
+  double dpsi = 0.0;  // sum of degree_i PSI_i(t)  (h of mod.jl:22-24)
   double res = 0.0;   // sum of per-vertex L1 changes (lane t = 0)
   double logz = 0.0;  // sum of log Z_i            (lane t = 0)
   double vmax = 0.0;  // max per-vertex L1 change  (lane t = 0)
@@ -223,7 +233,8 @@ __global__ void sbm_prior_table(const SbmState* st, double* tab, int dc) {
   double th = 1.0;
   if (r > 0) {
     const int d = (r - 1) / Q, blk = (r - 1) % Q;
-    th = (double)d / st->drmean[blk];  // the expression of sbm_theta_kernel, so theta is bit-identical
+    if constexpr (MODEL == MODEL_MOD) th = (double)d;  // mod.jl:48: the field is alpha beta d_i h
+    else th = (double)d / st->drmean[blk];             // the expression of sbm_theta_kernel: bit-identical theta
   }
   double row[QT];
   prior_row(th, row);
@@ -276,6 +287,7 @@ __device__ __forceinline__ void vertex_finish(const VertexArgs& a, bool valid, i
       if (tl) {
         a.PSI[(size_t)gv * Q + t] = p;
         acc.psi += p;
+        if constexpr (MODEL == MODEL_MOD) acc.dpsi += (double)deg * p;
       }
       if (t == 0) {
         acc.res += res;
@@ -330,6 +342,16 @@ __device__ __forceinline__ void store_partials(const LaneAcc& acc, double* scrat
     prow[2 + Q + tid] = (double)s_dr[tid];
     prow[2 + 2 * Q + tid] = (double)s_nr[tid];
   }
+  if constexpr (MODEL == MODEL_MOD) {
+    __syncthreads();
+    scratch[tid] = acc.dpsi;
+    __syncthreads();
+    if (tid < Q) {
+      double s = 0.0;
+      for (int k = tid; k < NT; k += LV) s += scratch[k];
+      prow[3 + 3 * Q + tid] = s;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -354,10 +376,14 @@ __device__ __forceinline__ int swz_unit(int row, int c) {
 __device__ __forceinline__ void edge_factor(const double (&psi)[Q], double sc, double (&T)[Q]) {
 #pragma unroll
   for (int t = 0; t < Q; ++t) {
-    double acc = 0.0;
+    if constexpr (MODEL == MODEL_MOD) {
+      T[t] = fma(psi[t], c_P.eb1, 1.0);  // 1 + psi (e^beta - 1), mod.jl:42
+    } else {
+      double acc = 0.0;
 #pragma unroll
-    for (int s = 0; s < Q; ++s) acc = fma(psi[s], c_P.C[s * Q + t], acc);
-    T[t] = acc * sc;
+      for (int s = 0; s < Q; ++s) acc = fma(psi[s], c_P.C[s * Q + t], acc);
+      T[t] = acc * sc;
+    }
   }
 }
 
@@ -407,7 +433,7 @@ __device__ __forceinline__ void stage_tile(const VertexArgs& a, int e0, int ne, 
       cp_async_unit(buf + row * ROWB + swz_unit(row, c) * CHB, src + (size_t)g * CHB);
     }
   }
-  if (a.dc && (int)threadIdx.x < ne) cp_async_8(scbuf + threadIdx.x, a.escale + e0 + threadIdx.x);
+  if (MODEL == MODEL_SBM && a.dc && (int)threadIdx.x < ne) cp_async_8(scbuf + threadIdx.x, a.escale + e0 + threadIdx.x);
 }
 
 __device__ __forceinline__ void read_staged(const char* buf, int row, double (&psi)[Q]) {
@@ -503,7 +529,7 @@ __global__ void __launch_bounds__(NT, (Q <= 8) ? 3 : 2) sbm_vertex_kernel(Vertex
     if (tid < ne) {
       double psi[Q];
       read_staged(psiS + (size_t)buf * TILE_E * ROWB, tid, psi);
-      edge_factor(psi, a.dc ? scS[buf * TILE_E + tid] : 1.0, T);
+      edge_factor(psi, (MODEL == MODEL_SBM && a.dc) ? scS[buf * TILE_E + tid] : 1.0, T);
 #pragma unroll
       for (int k = 0; k < Q; ++k) Tsm[tid * QS + k] = T[k];
     }
@@ -732,7 +758,8 @@ __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gv = a.hubs[blockIdx.x];
   const int e0 = a.rowptr[gv], e1 = a.rowptr[gv + 1];
-  const double th = a.dc ? a.theta[gv] : 1.0;
+  // theta of the prior: sbm.jl degree correction factor, or the degree itself in mod.jl:48
+  const double th = !a.dc ? 1.0 : (MODEL == MODEL_MOD ? (double)(e1 - e0) : a.theta[gv]);
   if (tid < Q) {
     s_dr[tid] = 0ull;
     s_nr[tid] = 0;
@@ -750,7 +777,7 @@ __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base
     double psi[Q], T[Q];
     int ke;
     load_vec<Q>(a.cur, e, psi);
-    const double sc = a.dc ? th * a.theta[a.col[e]] : 1.0;
+    const double sc = (MODEL == MODEL_SBM && a.dc) ? th * a.theta[a.col[e]] : 1.0;
     edge_transform(psi, sc, T, ke);
     ksum += ke;
 #pragma unroll
@@ -830,7 +857,7 @@ __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base
       double psi[Q], T[Q];
       int ke;
       load_vec<Q>(a.cur, e, psi);
-      const double sc = a.dc ? th * a.theta[a.col[e]] : 1.0;
+      const double sc = (MODEL == MODEL_SBM && a.dc) ? th * a.theta[a.col[e]] : 1.0;
       edge_transform(psi, sc, T, ke);
       emit_message(a, Ush, T, ffSh, fnSh + ke, a.rev[e]);
     }
@@ -1267,14 +1294,14 @@ VertexArgs vertex_args(gbx_sbm* h) {
   a.theta = h->theta;
   a.blk = h->blk;
   a.prior_tab = h->prior_tab;
-  a.dc_tab = h->opt.degreecorrection && h->theta_valid;
+  a.dc_tab = (MODEL == MODEL_MOD) ? h->mopt.dc : (h->opt.degreecorrection && h->theta_valid);
   a.cur = h->msg[h->cur];
   a.nxt = h->msg[h->cur ^ 1];
   a.PSI = h->PSI;
   a.partials = h->part_vertex;
   a.status = &h->st->status;
-  a.damping = h->opt.damping;
-  a.dc = h->opt.degreecorrection;
+  a.damping = (MODEL == MODEL_MOD) ? h->mopt.damping : h->opt.damping;
+  a.dc = (MODEL == MODEL_MOD) ? h->mopt.dc : h->opt.degreecorrection;
   return a;
 }
 
@@ -1282,7 +1309,7 @@ template <int MODE>
 int launch_vertex_pass_t(gbx_sbm* h) {
   VertexArgs a = vertex_args(h);
   if (h->nmain > 0) {
-    if (h->sweep_variant == 0) sbm_group_kernel<MODE><<<h->grid_vertex, NT, 0, h->stream>>>(a);
+    if (MODEL == MODEL_SBM && h->sweep_variant == 0) sbm_group_kernel<MODE><<<h->grid_vertex, NT, 0, h->stream>>>(a);
     else sbm_vertex_kernel<MODE><<<h->grid_vertex, NT, SweepSmem::total, h->stream>>>(a);
     h->launches++;
   }
@@ -1407,13 +1434,250 @@ int op_occupancy(int variant, int* vertex_occ, int* mstep_occ) {
   return GBX_OK;
 }
 
+#if GBX_MODEL == 1
+// =============================================================================================
+// mod.jl: SBM restricted to community structure (omega_in on the diagonal, omega_out off it), src/mod.jl:3-244.
+// The sweep reuses sbm_vertex_kernel / sbm_hub_kernel (edge factor 1 + psi (e^beta - 1), prior field
+// alpha beta d_i h); below are the scalar bookkeeping, the omega M-step and the free energy of that model.
+// =============================================================================================
+__global__ void mod_reduce_vertex(SbmState* st, const double* partials, int nrows, int mode, int prior, int dc,
+                                  double N) {
+  __shared__ double tot[PSTRIDE];
+  const int tid = threadIdx.x;
+  for (int c = tid >> 5; c < 4 * Q + 3; c += blockDim.x >> 5) {
+    const double v = (c == 2 + 3 * Q) ? warp_column_reduce<true>(partials, nrows, PSTRIDE, c)
+                                      : warp_column_reduce<false>(partials, nrows, PSTRIDE, c);
+    if ((tid & 31) == 0) tot[c] = v;
+  }
+  __syncthreads();
+  if (mode == MODE_LOGZ) {
+    if (tid == 0) {
+      st->sumlogZi = tot[1];
+      if (!(tot[1] == tot[1])) st->status |= 1;
+    }
+    return;
+  }
+  if (tid < Q) {
+    const double snew = tot[2 + tid];
+    st->sumPSI[tid] = snew;
+    st->Stheta[tid] = dc ? tot[3 + 3 * Q + tid] : snew;            // degrees' * PSI, mod.jl:22-24 (ones without dc)
+    if (mode == MODE_SWEEP && prior) st->gr[tid] = snew / N;        // gr = update_gr(PSI), mod.jl:221-223
+  }
+  if (tid == 0 && mode == MODE_SWEEP) {
+    st->conv = tot[0] / N;  // mod.jl:72
+    st->maxd = tot[2 + 3 * Q];
+    if (!(tot[0] == tot[0]) || !(tot[0] < INFINITY)) st->status |= 1;
+  }
+}
+
+__global__ void mod_prepare(SbmState* st, SbmParams* out, double N, int zero_h) {
+  const int tid = threadIdx.x;
+  if (tid < Q) {
+    out->lgr[tid] = log(st->gr[tid]);
+    const double hh = zero_h ? 0.0 : st->Stheta[tid];  // h = update_h(), mod.jl:56 (zeros before the first sweep)
+    st->h[tid] = hh;
+    out->h[tid] = st->alpha * st->beta * hh;            // the prior field is alpha beta d_i h, mod.jl:46-48
+  }
+  if (tid == 0) {
+    out->logN = log(N);
+    const double eb1 = exp(st->beta) - 1.0;             // written as in mod.jl:42
+    out->eb1 = eb1;
+    double hn2 = 0.0;
+    for (int t = 0; t < Q; ++t) {
+      const double hh = zero_h ? 0.0 : st->Stheta[t];
+      hn2 += hh * hh;
+    }
+    st->hn2 = hn2;
+    // edge factors lie in [1, 1 + eb1] (or [1 + eb1, 1] for beta < 0): bound for the plain-product path
+    const double worst = fmax(fabs(log2(1.0 + eb1)), 1e-3);
+    out->safe_deg = (worst == worst && worst < INFINITY) ? (int)fmin(900.0 / worst, (double)TILE_E) : 0;
+  }
+}
+
+// update_omega(), mod.jl:77-88: omegainnew = sum over undirected edges of omega_in s / ((omega_in - omega_out) s + omega_out)
+__global__ void __launch_bounds__(NT) mod_mstep_kernel(const SbmState* st, const int2* __restrict__ und, long long L,
+                                                       const double* __restrict__ psi, double* partials) {
+  __shared__ double red[NT / 32];
+  const double oin = st->omegain, oout = st->omegaout;
+  double acc[1] = {0.0};
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < L; i += (long long)gridDim.x * NT) {
+    const int2 er = und[i];
+    double a[Q], b[Q];
+    load_vec<Q>(psi, er.x, b);
+    load_vec<Q>(psi, er.y, a);
+    double s = 0.0;
+#pragma unroll
+    for (int t = 0; t < Q; ++t) s = fma(a[t], b[t], s);
+    acc[0] += oin * s / ((oin - oout) * s + oout);
+  }
+  block_reduce_store<1>(acc, red, partials + blockIdx.x);
+}
+
+// mod.jl:89-105 and 224-229: new omegas, clamps, learning-rate mix, update_alphabeta
+__global__ void mod_reduce_mstep(SbmState* st, const double* partials, int nrows, double lr, double maxomega,
+                                 double N, double K, int dc) {
+  if (threadIdx.x >= 32) return;
+  const double omegainnew = warp_column_reduce(partials, nrows, 1, 0);
+  if (threadIdx.x == 0) {
+    double dn = 0.0;
+    for (int t = 0; t < Q; ++t) dn += st->Stheta[t] * st->Stheta[t];  // norm(update_h())^2 of the new marginals
+    double oin = 2.0 * omegainnew / dn;
+    double oout = 2.0 * (0.5 * K - omegainnew) / ((dc ? K * K : N * N) - dn);
+    if (oin > maxomega) oin = maxomega;
+    else if (oin < 0.0) oin = 0.0;
+    else if (oout < 0.0) oout = 0.0;
+    st->omegain = lr * oin + (1.0 - lr) * st->omegain;
+    st->omegaout = lr * oout + (1.0 - lr) * st->omegaout;
+    st->beta = log(st->omegain / st->omegaout);                      // update_alphabeta, mod.jl:108-112
+    st->alpha = (st->omegain - st->omegaout) / st->beta;
+    if (!(st->beta == st->beta) || !(st->alpha == st->alpha)) st->status |= 1;
+  }
+}
+
+// freeenergy(), mod.jl:127-153.  x0 = logZij, x1 = CVBP, x2 = CVGP, x3 = CVGT, x4 = CVMAP per undirected edge.
+template <int PASS>
+__global__ void __launch_bounds__(NT) mod_fe_kernel(const SbmState* st, const int2* __restrict__ und,
+                                                    const int* __restrict__ col, const int* __restrict__ rowptr,
+                                                    long long L, const double* __restrict__ psi, int dc,
+                                                    double* partials) {
+  __shared__ double red[(NT / 32) * 5];
+  double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  double mean[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  if (PASS == 1)
+    for (int k = 0; k < 5; ++k) mean[k] = st->cv5mean[k];
+  const double oin = st->omegain, oout = st->omegaout, beta = st->beta;
+  const double loin = log(oin), loout = log(oout);
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < L; i += (long long)gridDim.x * NT) {
+    const int2 er = und[i];
+    double a[Q], b[Q];
+    load_vec<Q>(psi, er.x, b);
+    load_vec<Q>(psi, er.y, a);
+    double di = 1.0, dj = 1.0;
+    if (dc) {
+      const int vi = col[er.y], vj = col[er.x];
+      di = (double)(rowptr[vi + 1] - rowptr[vi]);
+      dj = (double)(rowptr[vj + 1] - rowptr[vj]);
+    }
+    double s = 0.0;
+    int sa = 0, sb = 0;
+#pragma unroll
+    for (int t = 0; t < Q; ++t) {
+      s = fma(a[t], b[t], s);
+      if (a[t] > a[sa]) sa = t;
+      if (b[t] > b[sb]) sb = t;
+    }
+    double x[5];
+    x[0] = log(1.0 + c_P.eb1 * s);
+    x[1] = x[0] + log(di) + loout + log(dj);
+    x[2] = beta * s;
+    x[3] = di * dj * (oout * loout + (oin * loin - oout * loout) * s) / exp(x[1]);
+    x[4] = (sa == sb) ? loin : loout;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      if (PASS == 0) acc[k] += x[k];
+      else acc[k] += (x[k] - mean[k]) * (x[k] - mean[k]);
+    }
+  }
+  block_reduce_store<5>(acc, red, partials + (size_t)blockIdx.x * 5);
+}
+
+__global__ void mod_reduce_fe(SbmState* st, const double* partials, int nrows, int pass, double L) {
+  const int c = threadIdx.x >> 5;
+  if (c < 5) {
+    const double s = warp_column_reduce(partials, nrows, 5, c);
+    if ((threadIdx.x & 31) == 0) {
+      if (pass == 0) {
+        st->cv5sum[c] = s;
+        st->cv5mean[c] = s / L;
+      } else {
+        st->cv5ss[c] = s;
+      }
+    }
+  }
+}
+
+__global__ void mod_finalize(SbmState* st, double N, double L, double constshift) {
+  if (threadIdx.x == 0) {
+    const double al = st->alpha, be = st->beta, oout = st->omegaout;
+    st->result[0] = -(st->sumlogZi - st->cv5sum[0] + 0.5 * al * be * st->hn2) / (be * N) -
+                    (L / N) * (2.0 * L * oout + log(oout) + constshift) / be;          // FE, mod.jl:158
+    st->result[1] = -st->cv5sum[1] / L + 1.0;                                        // CVBayes, mod.jl:159
+    st->result[2] = -st->cv5sum[2] / L - log(oout) + 1.0 - constshift;               // CVGP,    mod.jl:160
+    st->result[3] = -st->cv5sum[3] / L + 1.0 - constshift;                           // CVGT,    mod.jl:161
+    st->result[4] = -st->cv5sum[4] / L + 1.0 - constshift;                           // CVMAP,   mod.jl:162
+    st->result[5] = st->cv5ss[0] / (L - 1.0);                                        // var(logZijs), mod.jl:163
+    st->result[6] = st->cv5ss[2] / (L - 1.0);
+    st->result[7] = st->cv5ss[3] / (L - 1.0);
+    st->result[8] = st->cv5ss[4] / (L - 1.0);
+  }
+}
+
+int mop_reduce_vertex(gbx_sbm* h, int mode) {
+  const int nrows = (h->nmain > 0 ? h->grid_vertex : 0) + h->nhubs;
+  const double* base = h->part_vertex + (h->nmain > 0 ? 0 : (size_t)h->grid_vertex * PSTRIDE);
+  mod_reduce_vertex<<<1, 256, 0, h->stream>>>(h->st, base, nrows, mode, h->mopt.priorlearning, h->mopt.dc, (double)h->n);
+  h->launches++;
+  GBX_CUDA_TRY(cudaGetLastError());
+  return GBX_OK;
+}
+
+int mop_prepare(gbx_sbm* h, int zero_h, int) {
+  mod_prepare<<<1, 32, 0, h->stream>>>(h->st, h->params, (double)h->n, zero_h);
+  h->launches++;
+  GBX_CUDA_TRY(cudaGetLastError());
+  GBX_CUDA_TRY(cudaMemcpyToSymbolAsync(c_P, h->params, sizeof(SbmParams), 0, cudaMemcpyDeviceToDevice, h->stream));
+  const int dc_tab = h->mopt.dc;
+  const int nrows = dc_tab ? 1 + (TILE_E + 1) * Q : 1;
+  sbm_prior_table<<<(nrows + 127) / 128, 128, 0, h->stream>>>(h->st, h->prior_tab, dc_tab);
+  h->launches++;
+  GBX_CUDA_TRY(cudaGetLastError());
+  return GBX_OK;
+}
+
+int mop_mstep(gbx_sbm* h) {
+  mod_mstep_kernel<<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->und, (long long)(h->K / 2), h->msg[h->cur], h->part_fe);
+  mod_reduce_mstep<<<1, 32, 0, h->stream>>>(h->st, h->part_fe, h->grid_fe, h->mopt.learningrate, h->mopt.maxomega,
+                                            (double)h->n, (double)h->K, h->mopt.dc);
+  h->launches += 2;
+  GBX_CUDA_TRY(cudaGetLastError());
+  return GBX_OK;
+}
+
+int mop_theta(gbx_sbm*) { return GBX_OK; }
+
+int mop_free_energy(gbx_sbm* h) {
+  const double L = 0.5 * (double)h->K;
+  int rc = op_vertex_pass(h, MODE_LOGZ);
+  if (rc != GBX_OK) return rc;
+  rc = mop_reduce_vertex(h, MODE_LOGZ);
+  if (rc != GBX_OK) return rc;
+  mod_fe_kernel<0><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->und, h->col, h->rowptr, (long long)(h->K / 2),
+                                                     h->msg[h->cur], h->mopt.dc, h->part_fe);
+  mod_reduce_fe<<<1, 160, 0, h->stream>>>(h->st, h->part_fe, h->grid_fe, 0, L);
+  mod_fe_kernel<1><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->und, h->col, h->rowptr, (long long)(h->K / 2),
+                                                     h->msg[h->cur], h->mopt.dc, h->part_fe);
+  mod_reduce_fe<<<1, 160, 0, h->stream>>>(h->st, h->part_fe, h->grid_fe, 1, L);
+  mod_finalize<<<1, 32, 0, h->stream>>>(h->st, (double)h->n, L, h->mopt.dc ? h->constshift : 0.0);  // degrees = ones without dc (mod.jl:189-191)
+  h->launches += 5;
+  GBX_CUDA_TRY(cudaGetLastError());
+  return GBX_OK;
+}
+
+const SbmOps kOps = {Q,          op_vertex_pass,     mop_reduce_vertex, mop_prepare,  mop_mstep, mop_theta, mop_free_energy,
+                     op_permute, op_random_messages, op_assignment,     op_occupancy};
+#else
 const SbmOps kOps = {Q,         op_vertex_pass,     op_reduce_vertex, op_prepare,   op_mstep, op_theta, op_free_energy,
                      op_permute, op_random_messages, op_assignment,    op_occupancy};
+#endif
 
 }  // namespace
 
 #define GBX_CAT_(a, b) a##b
 #define GBX_CAT(a, b) GBX_CAT_(a, b)
+#if GBX_MODEL == 1
+const SbmOps* GBX_CAT(mod_ops_q, GBX_Q)() { return &kOps; }
+#else
 const SbmOps* GBX_CAT(sbm_ops_q, GBX_Q)() { return &kOps; }
+#endif
 
 }  // namespace gbx

@@ -14,7 +14,7 @@ import time
 import numpy as np
 
 from . import _lib
-from ._lib import SbmOptions, SbmResult, check
+from ._lib import ModOptions, ModResult, SbmOptions, SbmResult, check
 
 
 def _dp(a):
@@ -189,4 +189,104 @@ def EM(Ntot, B, links, maxCrs, initial, degreecorrection, itrmax, priorlearning,
         return out, eng, res
     if engine is None:
         eng.close()
+    return out
+
+
+# =================================================================================================
+# mod.jl: SBM restricted to community structure
+# =================================================================================================
+class ModEngine:
+    """One graph + one EM state of mod.jl's model resident on one GPU (C ABI gbx_mod_*)."""
+
+    def __init__(self, Ntot: int, links, B: int, device: int = 0, stream=None):
+        self.lib = _lib.load()
+        links = np.asarray(links)
+        if links.ndim != 2 or links.shape[1] != 2:
+            raise ValueError("links must be K x 2")
+        self.n, self.q, self.K = int(Ntot), int(B), int(links.shape[0])
+        colmajor = np.asfortranarray(links, dtype=np.int64)
+        self._h = C.c_void_p()
+        check(self.lib.gbx_mod_create(C.byref(self._h), int(device), self.n, self.K,
+                                      colmajor.ctypes.data_as(C.POINTER(C.c_int64)), self.q))
+        self.opt = ModOptions()
+        self.lib.gbx_mod_default_options(C.byref(self.opt))
+        if stream is not None:
+            ptr = getattr(stream, "cuda_stream", stream)
+            check(self.lib.gbx_mod_set_stream(self._h, C.c_void_p(int(ptr) if ptr else 0)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.gbx_mod_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_options(self, **kw):
+        for k, v in kw.items():
+            if not hasattr(self.opt, k):
+                raise TypeError(f"unknown option {k!r}")
+            setattr(self.opt, k, v)
+        check(self.lib.gbx_mod_set_options(self._h, C.byref(self.opt)))
+
+    def init(self, gr, psicav=None, seed: int = 0):
+        gr = _f64(gr, (self.q,))
+        psicav = _f64(psicav, (self.K, self.q))
+        check(self.lib.gbx_mod_init(self._h, _dp(gr), _dp(psicav), C.c_uint64(seed)))
+
+    def em(self) -> ModResult:
+        res = ModResult()
+        check(self.lib.gbx_mod_em(self._h, C.byref(res)))
+        return res
+
+    def iterate(self, n: int = 1, read_conv: bool = True):
+        conv = C.c_double(float("nan"))
+        check(self.lib.gbx_mod_iterate(self._h, int(n), C.byref(conv) if read_conv else None))
+        return conv.value
+
+    def finalize(self) -> ModResult:
+        res = ModResult()
+        check(self.lib.gbx_mod_finalize(self._h, C.byref(res)))
+        return res
+
+    def state(self):
+        q, n = self.q, self.n
+        gr, h, P, par = np.empty(q), np.empty(q), np.empty((n, q)), np.empty(4)
+        check(self.lib.gbx_mod_get_state(self._h, _dp(gr), _dp(P), _dp(h), _dp(par)))
+        return dict(gr=gr, PSI=P, h=h, alpha=par[0], beta=par[1], omegain=par[2], omegaout=par[3])
+
+    def messages(self):
+        m = np.empty((self.K, self.q))
+        check(self.lib.gbx_mod_get_messages(self._h, _dp(m)))
+        return m
+
+    def assignment(self):
+        b = np.empty(self.n, dtype=np.int32)
+        check(self.lib.gbx_mod_get_assignment(self._h, b.ctypes.data_as(C.POINTER(C.c_int32))))
+        return b
+
+    @property
+    def launch_count(self):
+        return int(self.lib.gbx_mod_launch_count(self._h))
+
+
+def EM_mod(gr, Ntot, B, links, maxomega, itrmax, betafrac, learning, priorlearning, dc, learningrate, *,
+           PSIcav0=None, seed=0, BPconvthreshold=0.000001, damping=1.0, device=0, return_engine=False):
+    """Drop-in for mod.jl's EM(), mod.jl:3.  Returns the reference's 17-tuple
+    (excm,alpha,beta,omegain,omegaout,PSI,FE,CVBayes,CVGP,CVGT,CVMAP,varCVBayes,varCVGP,varCVGT,varCVMAP,cnv,itrnum)."""
+    eng = ModEngine(Ntot, links, B, device=device)
+    eng.set_options(dc=int(bool(dc)), learning=int(bool(learning)), priorlearning=int(bool(priorlearning)),
+                    learningrate=float(learningrate), maxomega=float(maxomega), itrmax=int(itrmax),
+                    betafrac=float(betafrac), bp_conv_threshold=float(BPconvthreshold), damping=float(damping))
+    eng.init(gr, PSIcav0, seed=seed)
+    r = eng.em()
+    st = eng.state()
+    out = (r.excm, r.alpha, r.beta, r.omegain, r.omegaout, st["PSI"], r.FE, r.CVBayes, r.CVGP, r.CVGT, r.CVMAP,
+           r.varCVBayes, r.varCVGP, r.varCVGT, r.varCVMAP, bool(r.cnv), int(r.itrnum))
+    if return_engine:
+        return out, eng, r
+    eng.close()
     return out

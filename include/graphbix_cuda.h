@@ -110,6 +110,53 @@ int64_t gbx_sbm_device_bytes(const gbx_sbm* h);
 /* Algorithmic HBM bytes one BP sweep moves (DESIGN.md "bytes per unit"). */
 double gbx_sbm_sweep_bytes(const gbx_sbm* h);
 
+/* ------------------------------------------------------------------------------------------------
+ * mod.jl: SBM restricted to community structure (omega_in / omega_out).
+ *   gbx_mod_*  <->  function EM(gr,Ntot,B,links,maxomega,itrmax,betafrac,learning,priorlearning,dc,learningrate)
+ *                                                                                src/mod.jl:3-244
+ * Same graph conventions as above (`links`, message rows, PSI layout).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct gbx_sbm gbx_mod; /* opaque handle (the same device-resident graph object) */
+
+typedef struct gbx_mod_options {
+  int dc;                   /* mod.jl:189  --dc            (default 1)                          */
+  int learning;             /* mod.jl:224  --learning      (default 1)                          */
+  int priorlearning;        /* mod.jl:221  --prior         (default 0)                          */
+  double learningrate;      /* mod.jl:226  --learningrate  (default 0.3)                        */
+  double maxomega;          /* mod.jl:810  maxomega = 1                                         */
+  int itrmax;               /* mod.jl:219  --itrmax        (default 256)                        */
+  double betafrac;          /* mod.jl:194  position between beta* and beta0 (driver: 0, +0.1 per retry) */
+  double bp_conv_threshold; /* mod.jl:218  BPconvthreshold (default 1e-6)                       */
+  double damping;           /* synchronous-update damping, (0,1]; 1 = undamped (default)        */
+  int check_every;          /* read the residual back every n iterations (default 1)            */
+} gbx_mod_options;
+
+/* What EM() returns besides PSI (mod.jl:243). */
+typedef struct gbx_mod_result {
+  double excm, alpha, beta, omegain, omegaout;
+  double FE, CVBayes, CVGP, CVGT, CVMAP;
+  double varCVBayes, varCVGP, varCVGT, varCVMAP;
+  int cnv, itrnum, itrs_done, nonfinite;
+  double BPconv, max_dpsi;
+} gbx_mod_result;
+
+void gbx_mod_default_options(gbx_mod_options* opt);
+int gbx_mod_create(gbx_mod** out, int device, int64_t n_vertices, int64_t n_links, const int64_t* links, int q);
+int gbx_mod_destroy(gbx_mod* h);
+int gbx_mod_set_stream(gbx_mod* h, void* cuda_stream);
+int gbx_mod_set_options(gbx_mod* h, const gbx_mod_options* opt);
+/* Initial state, mod.jl:171-207: excm, beta from betafrac, alpha = 1/K, omegas, messages as given (NULL: random
+ * from `seed`), h = 0, PSI = updatePSI().  `gr` is the prior the driver passes in (mod.jl:807: ones(1,B)/B). */
+int gbx_mod_init(gbx_mod* h, const double* gr, const double* psicav, uint64_t seed);
+int gbx_mod_em(gbx_mod* h, gbx_mod_result* res);                  /* mod.jl:219-241 */
+int gbx_mod_iterate(gbx_mod* h, int n_iters, double* bpconv_out); /* n x (BP sweep, gr, omega update) */
+int gbx_mod_finalize(gbx_mod* h, gbx_mod_result* res);            /* mod.jl:240-241 */
+/* gr[q], PSI[N][q], hfield[q] (= degrees' * PSI), params[4] = {alpha, beta, omegain, omegaout}; any may be NULL */
+int gbx_mod_get_state(gbx_mod* h, double* gr, double* PSI, double* hfield, double* params);
+int gbx_mod_get_messages(gbx_mod* h, double* psicav);
+int gbx_mod_get_assignment(gbx_mod* h, int32_t* block);
+int64_t gbx_mod_launch_count(const gbx_mod* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,34 @@ CASES = [
 ]
 
 
+MOD_CASES = [
+    # name, n, q, deg, eps, seed, dc, learning, prior
+    ("q2_dc_learn", 260, 2, 8.0, 0.1, 62, True, True, False),
+    ("q3_nodc_learn_prior", 260, 3, 8.0, 0.1, 63, False, True, True),
+    ("q3_dc_learn", 260, 3, 8.0, 0.1, 63, True, True, False),
+    ("q4_dc_nolearn", 260, 4, 8.0, 0.1, 64, True, False, False),
+]
+
+
+def main_mod():
+    from oracle import mod_oracle as M
+    for name, n, q, deg, eps, seed, dc, learning, prior in MOD_CASES:
+        n, links, psi0, lab = planted_case(n, q, deg, eps, seed)
+        gr = np.ones(q) / q
+        r = M.EM(gr, n, q, links, 1, 4000, 0.0, learning, prior, dc, 0.3, rng=np.random.default_rng(seed),
+                 PSIcav0=psi0, BPconvthreshold=1e-12)
+        print("mod", name, "n", n, "K", links.shape[0], "cnv", r.cnv, "itr", r.itrs_done, "FE", r.FE)
+        if not r.cnv:
+            print("   -> oracle did not converge, skipped")
+            continue
+        np.savez_compressed(
+            os.path.join(HERE, f"mod_em_{name}.npz"), n=n, q=q, links=links, psi0=psi0, gr0=gr, dc=dc,
+            learning=learning, prior=prior, lr=0.3, tol=1e-12, PSI=r.PSI, PSIcav=r.PSIcav, gr=r.gr,
+            params=np.array([r.excm, r.alpha, r.beta, r.omegain, r.omegaout]),
+            scalars=np.array([r.FE, r.CVBayes, r.CVGP, r.CVGT, r.CVMAP, r.varCVBayes, r.varCVGP, r.varCVGT,
+                              r.varCVMAP]), itrnum=r.itrnum)
+
+
 def main():
     for name, n, q, deg, eps, seed, dc, prior, init in CASES:
         n, links, psi0, lab = planted_case(n, q, deg, eps, seed)
@@ -50,4 +78,10 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "mod" in sys.argv[1:]:
+        main_mod()
+    elif "sbm" in sys.argv[1:]:
+        main()
+    else:
+        main()
+        main_mod()
