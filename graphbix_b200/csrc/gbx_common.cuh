@@ -9,9 +9,12 @@
 
 namespace gbx {
 
-constexpr int NT = 256;      // threads per CTA == directed-edge slots per tile
-constexpr int TILE_E = NT;   // a tile is a run of consecutive vertices with <= TILE_E incoming edges
-constexpr int TILE_V = 128;  // ... and <= TILE_V vertices
+#ifndef GBX_NT
+#define GBX_NT 128
+#endif
+constexpr int NT = GBX_NT;         // threads per CTA == directed-edge slots per tile
+constexpr int TILE_E = NT;         // a tile is a run of consecutive vertices with <= TILE_E incoming edges
+constexpr int TILE_V = NT / 2;     // ... and <= TILE_V vertices
 constexpr int MAXQ = 16;
 
 // ---- error plumbing -------------------------------------------------------------------------

@@ -287,9 +287,9 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
     GBX_TRY(dev_alloc(h, &h->msg[1], (size_t)K * q));
     GBX_TRY(dev_alloc(h, &h->PSI, (size_t)n * q));
     GBX_TRY(dev_alloc(h, &h->theta, (size_t)n));
-    GBX_TRY(dev_alloc(h, &h->blk, (size_t)n));
+    GBX_TRY(dev_alloc(h, &h->pidx, (size_t)n));
     GBX_TRY(dev_alloc(h, &h->prior_tab, (size_t)(1 + (TILE_E + 1) * q) * (q + 3)));
-    GBX_CUDA_TRY(cudaMemset(h->blk, 0, (size_t)n));
+    GBX_CUDA_TRY(cudaMemset(h->pidx, 0, (size_t)n * sizeof(int)));
     GBX_TRY(dev_alloc(h, &h->st, 1));
     GBX_TRY(dev_alloc(h, &h->params, 1));
     GBX_CUDA_TRY(cudaMemcpy(h->rowptr, rowptr.data(), ((size_t)n + 1) * sizeof(int), cudaMemcpyHostToDevice));
@@ -354,7 +354,7 @@ int gbx_sbm_destroy(gbx_sbm* h) {
   cudaFree(h->msg[1]);
   cudaFree(h->PSI);
   cudaFree(h->theta);
-  cudaFree(h->blk);
+  cudaFree(h->pidx);
   cudaFree(h->prior_tab);
   cudaFree(h->st);
   cudaFree(h->params);
@@ -406,6 +406,7 @@ int gbx_sbm_init(gbx_sbm* h, const double* gr_init, const double* Crs_init, cons
   h->cur = 0;
   h->itr = 0;
   h->theta_valid = false;
+  GBX_TRY(h->ops->init_model(h));  // theta = 1: row 0 of the prior table
   if (psicav) {
     double* tmp = h->msg[1];
     GBX_CUDA_TRY(cudaMemcpyAsync(tmp, psicav, (size_t)h->K * q * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -617,6 +618,7 @@ int gbx_mod_init(gbx_mod* h, const double* gr, const double* psicav, uint64_t se
   h->cur = 0;
   h->itr = 0;
   h->fail = 0;
+  GBX_TRY(h->ops->init_model(h));  // prior-table row per vertex: by degree when degree corrected
   if (psicav) {
     double* tmp = h->msg[1];
     GBX_CUDA_TRY(cudaMemcpyAsync(tmp, psicav, (size_t)h->K * q * sizeof(double), cudaMemcpyHostToDevice, h->stream));

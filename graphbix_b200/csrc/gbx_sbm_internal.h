@@ -41,7 +41,7 @@ struct SbmState {
 constexpr int PSTRIDE = 4 * MAXQ + 4;  // per-CTA partial row of the vertex kernels
 enum { MODE_SWEEP = 0, MODE_MARGINAL = 1, MODE_LOGZ = 2 };
 
-constexpr int tile_vertices(int q) { return (q <= 8) ? TILE_V : TILE_V / 2; }
+constexpr int tile_vertices(int q) { return (q <= 8) ? TILE_V / 2 : TILE_V / 4; }
 
 struct SbmOps;
 
@@ -73,7 +73,7 @@ struct gbx_sbm {
   int ntiles = 0, nhubs = 0, max_degree = 1;
   // state (device)
   double *msg[2] = {nullptr, nullptr}, *PSI = nullptr, *theta = nullptr;
-  unsigned char* blk = nullptr;   // MAP block per vertex as of the last update_theta
+  int* pidx = nullptr;            // per vertex: row of the prior table (1 + degree * q + MAP block; 0: theta = 1)
   double* prior_tab = nullptr;    // prior factors per (degree, block), rebuilt every EM iteration
   bool theta_valid = false;       // update_theta has run since init
   int cur = 0;
@@ -100,6 +100,7 @@ struct SbmOps {
   int (*random_messages)(gbx_sbm* h, uint64_t seed);
   int (*assignment)(gbx_sbm* h, int* dev_block);
   int (*occupancy)(int variant, int* vertex_occ, int* mstep_occ);
+  int (*init_model)(gbx_sbm* h);  // per-vertex prior-table rows of the initial state
 };
 
 }  // namespace gbx

@@ -54,9 +54,8 @@ struct VertexArgs {
   int nmain;
   const int* hubs;    // vertex ids with degree > TILE_E
   const double* theta;
-  const unsigned char* blk;   // MAP block of every vertex as of the last update_theta (indexes the prior table)
+  const int* pidx;            // per vertex: row of the prior table, 1 + degree * Q + MAP block (0: theta = 1)
   const double* prior_tab;    // [1 + (TILE_E + 1) * Q][QT]: prior factors per (degree, block); row 0: theta = 1
-  int dc_tab;                 // theta has been updated at least once: use rows 1.. of the table
   const double* cur;
   double* nxt;
   double* PSI;
@@ -242,9 +241,8 @@ __global__ void sbm_prior_table(const SbmState* st, double* tab, int dc) {
 }
 
 template <int MODE>
-__device__ __forceinline__ Prior load_prior(const VertexArgs& a, bool valid, int gv, int deg, int t) {
+__device__ __forceinline__ Prior load_prior(const VertexArgs& a, int r, int t) {
   Prior pr;
-  const int r = (a.dc_tab && valid) ? 1 + deg * Q + a.blk[gv] : 0;
   const double* row = a.prior_tab + (size_t)r * QT;
   pr.E = (t < Q) ? row[t] : 0.0;
   pr.ffrac = row[Q];
@@ -387,10 +385,18 @@ __device__ __forceinline__ void edge_factor(const double (&psi)[Q], double sc, d
   }
 }
 
+// Per-tile inputs staged by cp.async, double buffered: nothing in the tile loop waits on a global load.
+struct StageBuf {
+  static constexpr size_t psi_off = 0;                                   // ne messages (rotated units)
+  static constexpr size_t sc_off = psi_off + (size_t)TILE_E * ROWB;      // ne theta scales
+  static constexpr size_t rev_off = sc_off + (size_t)TILE_E * 8;         // ne reverse slots
+  static constexpr size_t old_off = rev_off + (size_t)TILE_E * 4;        // nv old marginals
+  static constexpr size_t rp_off = old_off + (size_t)TV * ROWB;          // nv + 1 row pointers
+  static constexpr size_t pi_off = rp_off + (size_t)(TV + 4) * 4;        // nv prior-table rows
+  static constexpr size_t bytes = ((pi_off + (size_t)TV * 4 + 15) / 16) * 16;
+};
 struct SweepSmem {
-  static constexpr size_t psi_bytes = (size_t)2 * TILE_E * ROWB;          // staged messages, double buffered
-  static constexpr size_t sc_off = psi_bytes;                              // staged theta scales, double buffered
-  static constexpr size_t t_off = sc_off + (size_t)2 * TILE_E * 8;
+  static constexpr size_t t_off = 2 * StageBuf::bytes;
   static constexpr size_t u_off = t_off + (size_t)TILE_E * QS * 8;
   static constexpr size_t ff_off = u_off + (size_t)TV * Q * 8;
   static constexpr size_t scratch_off = ff_off + (size_t)TV * 8;
@@ -410,34 +416,49 @@ __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// Stage the `ne` messages of a tile (contiguous in HBM from slot e0), and their theta scales, into smem, coalesced:
-// unit g = i * NT + tid of the tile goes to row g / CH at a rotated position, so that stage 1 (one thread per
-// row) reads its row without bank conflicts.
-__device__ __forceinline__ void stage_tile(const VertexArgs& a, int e0, int ne, char* buf, double* scbuf) {
+// Stage everything tile `td` = (v0, nv, e0, ne) needs from HBM into one buffer, coalesced.  Message unit
+// g = i * NT + tid goes to row g / CH at a rotated position so that stage 1 (one thread per row) reads its row
+// without bank conflicts; the rotation does not depend on the round i, so the offset is a per-thread constant.
+template <int MODE>
+__device__ __forceinline__ void stage_tile(const VertexArgs& a, const int4& td, char* buf) {
+  const int tid = threadIdx.x;
+  const int v0 = td.x, nv = td.y, e0 = td.z, ne = td.w;
   const char* src = reinterpret_cast<const char*>(a.cur) + (size_t)e0 * ROWB;
   const int nunits = ne * CH;
   if constexpr (NT % CH == 0) {
-    // the rotation does not depend on the round i, so the smem offset is a per-thread constant plus i * NT * CHB
-    const int row0 = threadIdx.x / CH, c = threadIdx.x % CH;
-    char* d = buf + row0 * ROWB + swz_unit(row0, c) * CHB;
-    const char* g = src + (size_t)threadIdx.x * CHB;
+    const int row0 = tid / CH, c = tid % CH;
+    char* d = buf + StageBuf::psi_off + row0 * ROWB + swz_unit(row0, c) * CHB;
+    const char* g = src + (size_t)tid * CHB;
 #pragma unroll
     for (int i = 0; i < CH; ++i)
-      if (i * NT + (int)threadIdx.x < nunits) cp_async_unit(d + i * NT * CHB, g + (size_t)i * NT * CHB);
+      if (i * NT + tid < nunits) cp_async_unit(d + i * NT * CHB, g + (size_t)i * NT * CHB);
   } else {
-    for (int g = threadIdx.x; g < nunits; g += NT) {
+    for (int g = tid; g < nunits; g += NT) {
       const int row = g / CH, c = g - row * CH;
-      cp_async_unit(buf + row * ROWB + swz_unit(row, c) * CHB, src + (size_t)g * CHB);
+      cp_async_unit(buf + StageBuf::psi_off + row * ROWB + swz_unit(row, c) * CHB, src + (size_t)g * CHB);
     }
   }
-  if (MODEL == MODEL_SBM && a.dc && (int)threadIdx.x < ne) cp_async_8(scbuf + threadIdx.x, a.escale + e0 + threadIdx.x);
+  if (tid < ne) {
+    if (MODEL == MODEL_SBM && a.dc) cp_async_8(buf + StageBuf::sc_off + tid * 8, a.escale + e0 + tid);
+    if (MODE == MODE_SWEEP) cp_async_4(buf + StageBuf::rev_off + tid * 4, a.rev + e0 + tid);
+  }
+  if (tid <= nv) cp_async_4(buf + StageBuf::rp_off + tid * 4, a.rowptr + v0 + tid);
+  if (tid < nv) cp_async_4(buf + StageBuf::pi_off + tid * 4, a.pidx + v0 + tid);
+  if (MODE == MODE_SWEEP) {
+    const char* osrc = reinterpret_cast<const char*>(a.PSI) + (size_t)v0 * ROWB;
+    for (int g = tid; g < nv * CH; g += NT) cp_async_unit(buf + StageBuf::old_off + g * CHB, osrc + (size_t)g * CHB);
+  }
 }
 
 __device__ __forceinline__ void read_staged(const char* buf, int row, double (&psi)[Q]) {
-  const char* r = buf + row * ROWB;
+  const char* r = buf + StageBuf::psi_off + row * ROWB;
   if constexpr (CHB == 16) {
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
@@ -464,10 +485,8 @@ __device__ __forceinline__ void renorm(double& m, int& k) {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(NT, (Q <= 8) ? 3 : 2) sbm_vertex_kernel(VertexArgs a) {
+__global__ void __launch_bounds__(NT, ((Q <= 8) ? 3 : 2) * (256 / NT)) sbm_vertex_kernel(VertexArgs a) {
   extern __shared__ __align__(128) char smem[];
-  char* psiS = smem;
-  double* scS = reinterpret_cast<double*>(smem + SweepSmem::sc_off);
   double* Tsm = reinterpret_cast<double*>(smem + SweepSmem::t_off);
   double* Usm = reinterpret_cast<double*>(smem + SweepSmem::u_off);
   double* ffS = reinterpret_cast<double*>(smem + SweepSmem::ff_off);
@@ -492,7 +511,7 @@ __global__ void __launch_bounds__(NT, (Q <= 8) ? 3 : 2) sbm_vertex_kernel(Vertex
   const int G = gridDim.x;
   const int last = a.ntiles - 1;
   int4 tdN = a.tiles[min((int)blockIdx.x, last)];   // descriptor of the tile whose copies are issued next
-  stage_tile(a, tdN.z, tdN.w, psiS, scS);
+  stage_tile<MODE>(a, tdN, smem);
   cp_async_commit();
   int4 td = tdN;
   tdN = a.tiles[min((int)blockIdx.x + G, last)];
@@ -502,34 +521,29 @@ __global__ void __launch_bounds__(NT, (Q <= 8) ? 3 : 2) sbm_vertex_kernel(Vertex
   int buf = 0;
   for (int tile = blockIdx.x; tile < a.ntiles; tile += G) {
     const int v0 = td.x, nv = td.y, e0 = td.z, ne = td.w;
-    // ---- this tile's small global reads, consumed one or two stages later ----
-    int rv = 0;
-    if (MODE == MODE_SWEEP && tid < ne) rv = a.rev[e0 + tid];
-    int rb = 0, re = 0;
-    double old = 0.0;
-    Prior pr;
+    const char* cb = smem + (size_t)buf * StageBuf::bytes;
+    const int* rpS = reinterpret_cast<const int*>(cb + StageBuf::rp_off);
+    const int* piS = reinterpret_cast<const int*>(cb + StageBuf::pi_off);
+    const double* oldS = reinterpret_cast<const double*>(cb + StageBuf::old_off);
+    // ---- copies of tile k+1 into the other buffer, then the descriptor of tile k+2 into the same registers ----
     {
-      const bool valid = vlane < nv;
-      if (valid) {
-        rb = a.rowptr[v0 + vlane];
-        re = a.rowptr[v0 + vlane + 1];
-        if (MODE == MODE_SWEEP && tl) old = a.PSI[(size_t)(v0 + vlane) * Q + t];
-      }
-      pr = load_prior<MODE>(a, valid, v0 + vlane, re - rb, t);
+      int4 tn = tdN;
+      if (tile + G >= a.ntiles) tn.y = tn.w = -1;  // nothing to stage
+      stage_tile<MODE>(a, tn, smem + (size_t)(buf ^ 1) * StageBuf::bytes);
+      cp_async_commit();
     }
-
-    // ---- copies of tile k+1 (other buffer), then the descriptor of tile k+2 into the same registers ----
-    const bool hasN = tile + G < a.ntiles;
-    stage_tile(a, tdN.z, hasN ? tdN.w : 0, psiS + (size_t)(buf ^ 1) * TILE_E * ROWB, scS + (buf ^ 1) * TILE_E);
-    cp_async_commit();
     const int4 tdK1 = tdN;
     tdN = a.tiles[min(tile + 2 * G, last)];
+    // ---- prior factors of this tile's first round of vertices (an L2-resident table row per vertex) ----
+    Prior pr = load_prior<MODE>(a, (vlane < nv) ? piS[vlane] : 0, t);
+
     // ---- stage 1 ----
     double T[Q];
     if (tid < ne) {
       double psi[Q];
-      read_staged(psiS + (size_t)buf * TILE_E * ROWB, tid, psi);
-      edge_factor(psi, (MODEL == MODEL_SBM && a.dc) ? scS[buf * TILE_E + tid] : 1.0, T);
+      read_staged(cb, tid, psi);
+      const double sc = (MODEL == MODEL_SBM && a.dc) ? reinterpret_cast<const double*>(cb + StageBuf::sc_off)[tid] : 1.0;
+      edge_factor(psi, sc, T);
 #pragma unroll
       for (int k = 0; k < Q; ++k) Tsm[tid * QS + k] = T[k];
     }
@@ -540,17 +554,9 @@ __global__ void __launch_bounds__(NT, (Q <= 8) ? 3 : 2) sbm_vertex_kernel(Vertex
       if (vb + vwarp >= nv) break;  // warp-uniform: no vertex left for this warp
       const int v = vb + vlane;
       const bool valid = v < nv;
-      if (vb > 0) {  // tiles with more than VPR vertices (low degrees)
-        rb = re = 0;
-        old = 0.0;
-        if (valid) {
-          rb = a.rowptr[v0 + v];
-          re = a.rowptr[v0 + v + 1];
-          if (MODE == MODE_SWEEP && tl) old = a.PSI[(size_t)(v0 + v) * Q + t];
-        }
-        pr = load_prior<MODE>(a, valid, v0 + v, re - rb, t);
-      }
-      const int b = valid ? rb - e0 : 0, e = valid ? re - e0 : 0;
+      if (vb > 0) pr = load_prior<MODE>(a, valid ? piS[v] : 0, t);  // tiles with more than VPR vertices
+      const int b = valid ? rpS[v] - e0 : 0, e = valid ? rpS[v + 1] - e0 : 0;
+      const double old = (MODE == MODE_SWEEP && valid && tl) ? oldS[v * Q + t] : 0.0;
       if constexpr (MODE == MODE_SWEEP) {
         for (int k = b + t; k < e; k += LV) lvS[k] = (unsigned char)v;  // owner of every edge slot, for stage 3
       }
@@ -614,6 +620,7 @@ __global__ void __launch_bounds__(NT, (Q <= 8) ? 3 : 2) sbm_vertex_kernel(Vertex
     if constexpr (MODE == MODE_SWEEP) {
       if (tid < ne) {
         const int lv = lvS[tid];
+        const int rv = reinterpret_cast<const int*>(cb + StageBuf::rev_off)[tid];
         emit_message(a, &Usm[lv * Q], T, ffS[lv], fnS[lv], rv);
       }
     }
@@ -670,7 +677,7 @@ __device__ __forceinline__ double reduce_scatter_mul(double (&P)[QP], int j) {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(NT, 2) sbm_group_kernel(VertexArgs a) {
+__global__ void __launch_bounds__(NT, 2 * (256 / NT)) sbm_group_kernel(VertexArgs a) {
   __shared__ double scratch[NT];
   __shared__ unsigned long long s_dr[Q];
   __shared__ int s_nr[Q];
@@ -697,7 +704,7 @@ __global__ void __launch_bounds__(NT, 2) sbm_group_kernel(VertexArgs a) {
     }
     const double th = (a.dc && valid) ? a.theta[gv] : 1.0;
     const double old = (MODE == MODE_SWEEP && valid && tl) ? a.PSI[(size_t)gv * Q + j] : 0.0;
-    const Prior pr = load_prior<MODE>(a, valid, gv, e - b, j);
+    const Prior pr = load_prior<MODE>(a, valid ? a.pidx[gv] : 0, j);
 
     // ---- pass 1 ----
     double P[QP];
@@ -1037,7 +1044,7 @@ __global__ void sbm_reduce_mstep(SbmState* st, const double* partials, int nrows
 // update_theta(), sbm.jl:47-64, and S_theta = sum_i theta_i PSI_i for the next update_h().
 __global__ void __launch_bounds__(NT) sbm_theta_kernel(const SbmState* st, const int* __restrict__ rowptr, int n,
                                                        const double* __restrict__ PSI, double* theta,
-                                                       unsigned char* __restrict__ blk, double* partials) {
+                                                       int* __restrict__ pidx, double* partials) {
   __shared__ double red[(NT / 32) * Q];
   double acc[Q];
 #pragma unroll
@@ -1055,7 +1062,8 @@ __global__ void __launch_bounds__(NT) sbm_theta_kernel(const SbmState* st, const
       }
     const double th = (double)(rowptr[i + 1] - rowptr[i]) / st->drmean[best];
     theta[i] = th;
-    blk[i] = (unsigned char)best;
+    const int deg = rowptr[i + 1] - rowptr[i];
+    pidx[i] = (deg <= TILE_E) ? 1 + deg * Q + best : 0;  // row of the prior table (hubs evaluate the prior in place)
 #pragma unroll
     for (int t = 0; t < Q; ++t) acc[t] = fma(th, p[t], acc[t]);
   }
@@ -1276,6 +1284,15 @@ __global__ void k_assignment(const double* __restrict__ PSI, int n, int* __restr
   }
 }
 
+// Row of the prior table per vertex at init: theta = 1 (row 0) for sbm.jl; 1 + degree * Q for mod.jl with
+// degree correction (the field alpha beta d_i h depends on the vertex through its degree only, mod.jl:48).
+__global__ void k_init_pidx(const int* __restrict__ rowptr, int n, int by_degree, int* __restrict__ pidx) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int deg = rowptr[i + 1] - rowptr[i];
+    pidx[i] = (by_degree && deg <= TILE_E) ? 1 + deg * Q : 0;
+  }
+}
+
 // =============================================================================================
 // Launchers (host)
 // =============================================================================================
@@ -1292,9 +1309,8 @@ VertexArgs vertex_args(gbx_sbm* h) {
   a.nmain = h->nmain;
   a.hubs = h->hubs;
   a.theta = h->theta;
-  a.blk = h->blk;
+  a.pidx = h->pidx;
   a.prior_tab = h->prior_tab;
-  a.dc_tab = (MODEL == MODEL_MOD) ? h->mopt.dc : (h->opt.degreecorrection && h->theta_valid);
   a.cur = h->msg[h->cur];
   a.nxt = h->msg[h->cur ^ 1];
   a.PSI = h->PSI;
@@ -1364,7 +1380,7 @@ int op_mstep(gbx_sbm* h) {
 }
 
 int op_theta(gbx_sbm* h) {
-  sbm_theta_kernel<<<h->grid_theta, NT, 0, h->stream>>>(h->st, h->rowptr, (int)h->n, h->PSI, h->theta, h->blk,
+  sbm_theta_kernel<<<h->grid_theta, NT, 0, h->stream>>>(h->st, h->rowptr, (int)h->n, h->PSI, h->theta, h->pidx,
                                                         h->part_theta);
   h->theta_valid = true;
   sbm_reduce_theta<<<1, 256, 0, h->stream>>>(h->st, h->part_theta, h->grid_theta);
@@ -1416,6 +1432,14 @@ int op_random_messages(gbx_sbm* h, uint64_t seed) {
 
 int op_assignment(gbx_sbm* h, int* dev_block) {
   k_assignment<<<grid_for(h, h->n), 256, 0, h->stream>>>(h->PSI, (int)h->n, dev_block);
+  h->launches++;
+  GBX_CUDA_TRY(cudaGetLastError());
+  return GBX_OK;
+}
+
+int op_init_model(gbx_sbm* h) {
+  const int by_degree = (MODEL == MODEL_MOD) && h->mopt.dc;
+  k_init_pidx<<<grid_for(h, h->n), 256, 0, h->stream>>>(h->rowptr, (int)h->n, by_degree, h->pidx);
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
@@ -1663,11 +1687,11 @@ int mop_free_energy(gbx_sbm* h) {
   return GBX_OK;
 }
 
-const SbmOps kOps = {Q,          op_vertex_pass,     mop_reduce_vertex, mop_prepare,  mop_mstep, mop_theta, mop_free_energy,
-                     op_permute, op_random_messages, op_assignment,     op_occupancy};
+const SbmOps kOps = {Q,          op_vertex_pass,     mop_reduce_vertex, mop_prepare,  mop_mstep,     mop_theta, mop_free_energy,
+                     op_permute, op_random_messages, op_assignment,     op_occupancy, op_init_model};
 #else
-const SbmOps kOps = {Q,         op_vertex_pass,     op_reduce_vertex, op_prepare,   op_mstep, op_theta, op_free_energy,
-                     op_permute, op_random_messages, op_assignment,    op_occupancy};
+const SbmOps kOps = {Q,         op_vertex_pass,     op_reduce_vertex, op_prepare,   op_mstep,     op_theta, op_free_energy,
+                     op_permute, op_random_messages, op_assignment,    op_occupancy, op_init_model};
 #endif
 
 }  // namespace
