@@ -44,6 +44,10 @@ static const SbmOps* ops_for(int model, int q) {
 
 }  // namespace gbx
 
+namespace gbx {
+int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* rowptr_host);
+}
+
 using namespace gbx;
 
 namespace {
@@ -141,58 +145,42 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
   }
   if (device < 0 || device >= ndev) return fail_invalid("device out of range");
 
-  // ---- destination-major CSR on the host (counting sorts, O(K + N)) ----
-  const int64_t* src1 = links;
-  const int64_t* dst1 = links + K;
-  std::vector<int> rowptr((size_t)n + 1, 0);
-  for (int64_t k = 0; k < K; ++k) {
-    const int64_t s = src1[k], d = dst1[k];
-    if (s < 1 || s > n || d < 1 || d > n) return fail_invalid("links: vertex id out of 1..n");
-    if (s == d) return fail_invalid("links: self loop (run simplegraph first)");
-    rowptr[(size_t)d]++;
-  }
-  for (int64_t i = 0; i < n; ++i) rowptr[(size_t)i + 1] += rowptr[(size_t)i];
-  // pass 1: order links by source; pass 2: stable distribution by destination -> rows sorted by source
-  std::vector<int> by_src((size_t)K);
+  // ---- handle + device-side graph construction (gbx_graph_build.cu) ----
+  gbx_sbm* h = new (std::nothrow) gbx_sbm();
+  if (!h) return fail_invalid("out of host memory");
+  h->device = device;
+  h->q = q;
+  h->n = n;
+  h->K = K;
+  h->ops = ops;
+  std::vector<int> rowptr;
   {
-    std::vector<int> cnt((size_t)n + 1, 0);
-    for (int64_t k = 0; k < K; ++k) cnt[(size_t)src1[k]]++;
-    for (int64_t i = 0; i < n; ++i) cnt[(size_t)i + 1] += cnt[(size_t)i];
-    for (int64_t k = 0; k < K; ++k) by_src[(size_t)cnt[(size_t)src1[k] - 1]++] = (int)k;
-  }
-  std::vector<int> col((size_t)K), slot_of_link((size_t)K), rev((size_t)K);
-  {
-    std::vector<int> fill(rowptr.begin(), rowptr.end() - 1);
-    for (int64_t p = 0; p < K; ++p) {
-      const int k = by_src[(size_t)p];
-      const int slot = fill[(size_t)dst1[k] - 1]++;
-      col[(size_t)slot] = (int)(src1[k] - 1);
-      slot_of_link[(size_t)k] = slot;
+    cudaDeviceProp prop;
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce == cudaSuccess) ce = cudaGetDeviceProperties(&prop, device);
+    if (ce != cudaSuccess) {
+      last_error() = std::string("cudaSetDevice/cudaGetDeviceProperties: ") + cudaGetErrorString(ce);
+      delete h;
+      return GBX_ERR_CUDA;
+    }
+    if (prop.major < 10) {
+      last_error() = "libgraphbix_cuda is built for sm_100a (B200) only";
+      delete h;
+      return GBX_ERR_CUDA;
+    }
+    h->num_sms = prop.multiProcessorCount;
+    const int rcb = build_graph_device(h, links, &rowptr);
+    if (rcb != GBX_OK) {
+      const std::string keep = last_error();
+      gbx_sbm_destroy(h);
+      last_error() = keep;
+      return rcb;
     }
   }
-  by_src.clear();
-  by_src.shrink_to_fit();
-  for (int64_t i = 0; i < n; ++i) {
-    for (int e = rowptr[(size_t)i]; e < rowptr[(size_t)i + 1]; ++e) {
-      if (e > rowptr[(size_t)i] && col[(size_t)e] == col[(size_t)e - 1])
-        return fail_invalid("links: duplicate link (run simplegraph first)");
-      const int j = col[(size_t)e];
-      const int* b = col.data() + rowptr[(size_t)j];
-      const int* en = col.data() + rowptr[(size_t)j + 1];
-      const int* it = std::lower_bound(b, en, (int)i);
-      if (it == en || *it != (int)i) return fail_invalid("links: reverse link missing (graph must be bidirected)");
-      rev[(size_t)e] = (int)(it - col.data());
-    }
-  }
-  std::vector<int2> und;
-  und.reserve((size_t)K / 2);
-  for (int64_t e = 0; e < K; ++e)
-    if (rev[(size_t)e] < e) und.push_back(make_int2((int)e, rev[(size_t)e]));
   // ---- tile schedule: runs of consecutive vertices with <= TILE_E slots and <= TV vertices; hubs apart ----
   const int TV = tile_vertices(q);
   std::vector<int4> tiles;
   std::vector<int> hubs;
-  std::vector<unsigned char> lvtx((size_t)K, 0);
   {
     int64_t v = 0;
     while (v < n) {
@@ -207,7 +195,6 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
       while (w < n && (w - v) < TV) {
         const int d = rowptr[(size_t)w + 1] - rowptr[(size_t)w];
         if (d > TILE_E || ne + d > TILE_E) break;
-        for (int e = rowptr[(size_t)w]; e < rowptr[(size_t)w + 1]; ++e) lvtx[(size_t)e] = (unsigned char)(w - v);
         ne += d;
         ++w;
       }
@@ -232,13 +219,6 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
       if (rowptr[(size_t)v + 1] - rowptr[(size_t)v] <= TILE_E) vorder[(size_t)cnt[(size_t)cls(v)]++] = (int)v;
   }
 
-  gbx_sbm* h = new (std::nothrow) gbx_sbm();
-  if (!h) return fail_invalid("out of host memory");
-  h->device = device;
-  h->q = q;
-  h->n = n;
-  h->K = K;
-  h->ops = ops;
   h->ntiles = (int)tiles.size();
   h->nmain = (int)vorder.size();
   for (int64_t v = 0; v < n; ++v) h->max_degree = std::max(h->max_degree, rowptr[(size_t)v + 1] - rowptr[(size_t)v]);
@@ -263,22 +243,7 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
   h->nhubs = (int)hubs.size();
   gbx_sbm_default_options(&h->opt);
   auto body = [&]() -> int {
-    GBX_CUDA_TRY(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    GBX_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) {
-      last_error() = "libgraphbix_cuda is built for sm_100a (B200) only";
-      return GBX_ERR_CUDA;
-    }
-    h->num_sms = prop.multiProcessorCount;
-    GBX_TRY(dev_alloc(h, &h->rowptr, (size_t)n + 1));
-    GBX_TRY(dev_alloc(h, &h->col, (size_t)K));
-    GBX_TRY(dev_alloc(h, &h->rev, (size_t)K));
-    GBX_TRY(dev_alloc(h, &h->lvtx, (size_t)K));
     GBX_TRY(dev_alloc(h, &h->escale, (size_t)K));
-    GBX_TRY(dev_alloc(h, &h->und, und.size()));
-    GBX_CUDA_TRY(cudaMemcpy(h->und, und.data(), und.size() * sizeof(int2), cudaMemcpyHostToDevice));
-    GBX_TRY(dev_alloc(h, &h->slot_of_link, (size_t)K));
     GBX_TRY(dev_alloc(h, &h->tiles, tiles.size()));
     GBX_TRY(dev_alloc(h, &h->vorder, vorder.size()));
     GBX_CUDA_TRY(cudaMemcpy(h->vorder, vorder.data(), vorder.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -292,11 +257,6 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
     GBX_CUDA_TRY(cudaMemset(h->pidx, 0, (size_t)n * sizeof(int)));
     GBX_TRY(dev_alloc(h, &h->st, 1));
     GBX_TRY(dev_alloc(h, &h->params, 1));
-    GBX_CUDA_TRY(cudaMemcpy(h->rowptr, rowptr.data(), ((size_t)n + 1) * sizeof(int), cudaMemcpyHostToDevice));
-    GBX_CUDA_TRY(cudaMemcpy(h->col, col.data(), (size_t)K * sizeof(int), cudaMemcpyHostToDevice));
-    GBX_CUDA_TRY(cudaMemcpy(h->rev, rev.data(), (size_t)K * sizeof(int), cudaMemcpyHostToDevice));
-    GBX_CUDA_TRY(cudaMemcpy(h->lvtx, lvtx.data(), (size_t)K, cudaMemcpyHostToDevice));
-    GBX_CUDA_TRY(cudaMemcpy(h->slot_of_link, slot_of_link.data(), (size_t)K * sizeof(int), cudaMemcpyHostToDevice));
     GBX_CUDA_TRY(cudaMemcpy(h->tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice));
     GBX_CUDA_TRY(cudaMemcpy(h->hubs, hubs.data(), hubs.size() * sizeof(int), cudaMemcpyHostToDevice));
     GBX_CUDA_TRY(cudaMemset(h->st, 0, sizeof(SbmState)));
@@ -343,7 +303,7 @@ int gbx_sbm_destroy(gbx_sbm* h) {
   cudaFree(h->rowptr);
   cudaFree(h->col);
   cudaFree(h->rev);
-  cudaFree(h->lvtx);
+  cudaFree(h->erow);
   cudaFree(h->escale);
   cudaFree(h->und);
   cudaFree(h->slot_of_link);

@@ -63,7 +63,7 @@ struct gbx_sbm {
   const gbx::SbmOps* ops = nullptr;
   // graph (device)
   int *rowptr = nullptr, *col = nullptr, *rev = nullptr, *slot_of_link = nullptr, *hubs = nullptr;
-  unsigned char* lvtx = nullptr;  // per edge slot: index of its vertex inside its tile
+  int* erow = nullptr;            // per edge slot: its row (destination vertex)
   int4* tiles = nullptr;          // (first vertex, #vertices, first edge slot, #edge slots)
   double* escale = nullptr;       // per edge slot theta_row * theta_col (all ones until update_theta runs)
   int2* und = nullptr;            // every undirected edge once: (slot e, slot rev[e]) with rev[e] < e

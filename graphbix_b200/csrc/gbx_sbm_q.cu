@@ -46,7 +46,6 @@ struct VertexArgs {
   const int* rowptr;
   const int* col;
   const int* rev;
-  const unsigned char* lvtx;
   const double* escale;  // per edge slot: theta_row * theta_col (degree-corrected runs), refreshed with theta
   const int4* tiles;     // [ntiles] (first vertex, #vertices, first edge slot, #edge slots)
   int ntiles;
@@ -873,19 +872,13 @@ __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base
   store_partials(acc, scratch, a.partials + (size_t)(part_base + blockIdx.x) * PSTRIDE, s_dr, s_nr);
 }
 
-// theta_row * theta_col per tiled edge slot, refreshed after update_theta (degree-corrected runs): keeps the
-// random theta gather out of the sweep (one coalesced 8-byte read there instead of col + a dependent gather).
-__global__ void __launch_bounds__(NT) sbm_escale_kernel(const int4* __restrict__ tiles, int ntiles,
-                                                        const unsigned char* __restrict__ lvtx,
-                                                        const int* __restrict__ col, const double* __restrict__ theta,
-                                                        double* __restrict__ escale) {
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int4 td = tiles[tile];
-    if ((int)threadIdx.x < td.w) {
-      const int e = td.z + threadIdx.x;
-      escale[e] = theta[td.x + lvtx[e]] * theta[col[e]];
-    }
-  }
+// theta_row * theta_col per edge slot, refreshed after update_theta (degree-corrected runs): keeps the random
+// theta gather out of the sweep (one staged 8-byte value per slot there instead of col + a dependent gather).
+__global__ void __launch_bounds__(256) sbm_escale_kernel(const int* __restrict__ erow, const int* __restrict__ col,
+                                                         long long K, const double* __restrict__ theta,
+                                                         double* __restrict__ escale) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < K; e += (long long)gridDim.x * blockDim.x)
+    escale[e] = theta[erow[e]] * theta[col[e]];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -975,12 +968,16 @@ __global__ void __launch_bounds__(NTM, 1) sbm_mstep_kernel(const int2* __restric
 #pragma unroll
     for (int k = 0; k < MS_R * Q; ++k) acc[k] = 0.0;
     long long i = (long long)blockIdx.x * NTM + threadIdx.x;
+    // software pipeline: slot pair of edge i + 2*stride and messages of edge i + stride are in flight while edge i
+    // is being accumulated
     double an[Q], bn[Q];
+    int2 ern = make_int2(0, 0);
     if (i < L) {
       const int2 er = und[i];
       load_vec<Q>(psi, er.x, bn);  // col -> row
       load_vec<Q>(psi, er.y, an);  // row -> col
     }
+    if (i + stride < L) ern = und[i + stride];
     while (i < L) {
       double a[Q], b[Q];
 #pragma unroll
@@ -990,7 +987,8 @@ __global__ void __launch_bounds__(NTM, 1) sbm_mstep_kernel(const int2* __restric
       }
       i += stride;
       if (i < L) {
-        const int2 er = und[i];
+        const int2 er = ern;
+        if (i + stride < L) ern = und[i + stride];
         load_vec<Q>(psi, er.x, bn);
         load_vec<Q>(psi, er.y, an);
       }
@@ -1296,12 +1294,15 @@ __global__ void k_init_pidx(const int* __restrict__ rowptr, int n, int by_degree
 // =============================================================================================
 // Launchers (host)
 // =============================================================================================
+int grid_for(gbx_sbm* h, int64_t items) {
+  return (int)std::min<int64_t>(std::max<int64_t>(1, (items + 255) / 256), (int64_t)h->num_sms * 8);
+}
+
 VertexArgs vertex_args(gbx_sbm* h) {
   VertexArgs a;
   a.rowptr = h->rowptr;
   a.col = h->col;
   a.rev = h->rev;
-  a.lvtx = h->lvtx;
   a.escale = h->escale;
   a.tiles = h->tiles;
   a.ntiles = h->ntiles;
@@ -1386,8 +1387,7 @@ int op_theta(gbx_sbm* h) {
   sbm_reduce_theta<<<1, 256, 0, h->stream>>>(h->st, h->part_theta, h->grid_theta);
   h->launches += 2;
   if (h->ntiles > 0 && h->sweep_variant != 0) {
-    sbm_escale_kernel<<<std::min(h->ntiles, h->num_sms * 8), NT, 0, h->stream>>>(h->tiles, h->ntiles, h->lvtx, h->col,
-                                                                               h->theta, h->escale);
+    sbm_escale_kernel<<<grid_for(h, h->K), 256, 0, h->stream>>>(h->erow, h->col, (long long)h->K, h->theta, h->escale);
     h->launches++;
   }
   GBX_CUDA_TRY(cudaGetLastError());
@@ -1412,9 +1412,6 @@ int op_free_energy(gbx_sbm* h) {
   return GBX_OK;
 }
 
-int grid_for(gbx_sbm* h, int64_t items) {
-  return (int)std::min<int64_t>(std::max<int64_t>(1, (items + 255) / 256), (int64_t)h->num_sms * 8);
-}
 
 int op_permute(gbx_sbm* h, const double* src, double* dst, int to_slots) {
   k_permute_rows<<<grid_for(h, h->K), 256, 0, h->stream>>>(src, dst, h->slot_of_link, (long long)h->K, to_slots);
