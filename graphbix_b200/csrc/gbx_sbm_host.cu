@@ -203,29 +203,8 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
     }
   }
 
-  // ---- processing order of the group kernel: non-hub vertices by ceil(degree / QP), largest first ----
-  int qp = 1;
-  while (qp < q) qp <<= 1;
-  std::vector<int> vorder;
-  {
-    const int nclass = TILE_E / qp + 2;
-    std::vector<int> cnt((size_t)nclass + 1, 0);
-    auto cls = [&](int64_t v) { return nclass - 1 - (rowptr[(size_t)v + 1] - rowptr[(size_t)v] + qp - 1) / qp; };
-    for (int64_t v = 0; v < n; ++v)
-      if (rowptr[(size_t)v + 1] - rowptr[(size_t)v] <= TILE_E) cnt[(size_t)cls(v) + 1]++;
-    for (int c = 0; c < nclass; ++c) cnt[(size_t)c + 1] += cnt[(size_t)c];
-    vorder.resize((size_t)cnt[(size_t)nclass]);
-    for (int64_t v = 0; v < n; ++v)
-      if (rowptr[(size_t)v + 1] - rowptr[(size_t)v] <= TILE_E) vorder[(size_t)cnt[(size_t)cls(v)]++] = (int)v;
-  }
-
   h->ntiles = (int)tiles.size();
-  h->nmain = (int)vorder.size();
   for (int64_t v = 0; v < n; ++v) h->max_degree = std::max(h->max_degree, rowptr[(size_t)v + 1] - rowptr[(size_t)v]);
-  {
-    const char* env = getenv("GBX_SWEEP");
-    h->sweep_variant = (env && std::string(env) == "group" && model == 0) ? 0 : 1;
-  }
   h->model = model;
   gbx_mod_default_options(&h->mopt);
   {
@@ -245,8 +224,6 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
   auto body = [&]() -> int {
     GBX_TRY(dev_alloc(h, &h->escale, (size_t)K));
     GBX_TRY(dev_alloc(h, &h->tiles, tiles.size()));
-    GBX_TRY(dev_alloc(h, &h->vorder, vorder.size()));
-    GBX_CUDA_TRY(cudaMemcpy(h->vorder, vorder.data(), vorder.size() * sizeof(int), cudaMemcpyHostToDevice));
     GBX_TRY(dev_alloc(h, &h->hubs, hubs.size()));
     GBX_TRY(dev_alloc(h, &h->msg[0], (size_t)K * q));
     GBX_TRY(dev_alloc(h, &h->msg[1], (size_t)K * q));
@@ -263,20 +240,16 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
     GBX_CUDA_TRY(cudaMallocHost((void**)&h->h_state, sizeof(SbmState)));
     // persistent grids: a whole number of CTAs per SM
     int occ = 1, occm = 1;
-    GBX_TRY(ops->occupancy(h->sweep_variant, &occ, &occm));
+    GBX_TRY(ops->occupancy(1, &occ, &occm));
     occ = std::max(occ, 1);
     occm = std::max(occm, 1);
-    {
-      const int gpb = NT / qp;  // vertices per CTA step of the group kernel
-      const int work = h->sweep_variant == 0 ? (h->nmain + gpb - 1) / gpb : h->ntiles;
-      h->grid_vertex = std::max(1, std::min(work, h->num_sms * occ));
-    }
+    h->grid_vertex = std::max(1, std::min(h->ntiles, h->num_sms * occ));
     const int64_t eblocks = std::max<int64_t>(1, (K / 2 + NT - 1) / NT);
-    h->grid_mstep = (int)std::min<int64_t>(std::max<int64_t>(1, (K / 2 + 319) / 320), (int64_t)h->num_sms * occm);
+    h->grid_mstep = h->grid_vertex + h->nhubs;  // M-step statistics: one row per sweep CTA
     h->grid_fe = (int)std::min<int64_t>(eblocks, (int64_t)h->num_sms * 2);
     h->grid_theta = (int)std::min<int64_t>(std::max<int64_t>(1, (n + NT - 1) / NT), (int64_t)h->num_sms * 4);
     GBX_TRY(dev_alloc(h, &h->part_vertex, (size_t)(h->grid_vertex + h->nhubs) * PSTRIDE));
-    GBX_TRY(dev_alloc(h, &h->part_mstep, (size_t)h->grid_mstep * MAXQ * MAXQ * 2));
+    GBX_TRY(dev_alloc(h, &h->part_mstep, (size_t)h->grid_mstep * q * q));
     GBX_TRY(dev_alloc(h, &h->part_theta, (size_t)h->grid_theta * MAXQ));
     GBX_TRY(dev_alloc(h, &h->part_fe, (size_t)h->grid_fe * 4));
     GBX_CUDA_TRY(cudaDeviceSynchronize());
@@ -308,7 +281,6 @@ int gbx_sbm_destroy(gbx_sbm* h) {
   cudaFree(h->und);
   cudaFree(h->slot_of_link);
   cudaFree(h->tiles);
-  cudaFree(h->vorder);
   cudaFree(h->hubs);
   cudaFree(h->msg[0]);
   cudaFree(h->msg[1]);

@@ -17,6 +17,7 @@ struct SbmParams {
   double h[MAXQ];            // external field, sbm.jl:70-73
   double logN;
   double eb1;                // e^beta - 1 (mod.jl)
+  double oin, oout;          // omega_in, omega_out (mod.jl)
   int safe_deg;              // largest degree whose plain product of edge factors cannot leave the double range
   int pad_;
 };
@@ -33,7 +34,7 @@ struct SbmState {
   double cvsum[4], cvmean[4], cvss[4];
   double result[12];
   // mod.jl (community-restricted SBM) scalars
-  double omegain, omegaout, alpha, beta, hn2;
+  double omegain, omegaout, alpha, beta, hn2, omegainnew2;
   double cv5sum[5], cv5mean[5], cv5ss[5];
   int status;  // bit 0: non-finite / non-positive value met in a kernel
 };
@@ -67,9 +68,6 @@ struct gbx_sbm {
   int4* tiles = nullptr;          // (first vertex, #vertices, first edge slot, #edge slots)
   double* escale = nullptr;       // per edge slot theta_row * theta_col (all ones until update_theta runs)
   int2* und = nullptr;            // every undirected edge once: (slot e, slot rev[e]) with rev[e] < e
-  int* vorder = nullptr;          // non-hub vertices, grouped by ceil(degree / lanes-per-vertex), largest first
-  int nmain = 0;                  // number of non-hub vertices
-  int sweep_variant = 1;          // 1: CTA-tile kernel with cp.async staging (default), 0: warp-autonomous group kernel (GBX_SWEEP=group)
   int ntiles = 0, nhubs = 0, max_degree = 1;
   // state (device)
   double *msg[2] = {nullptr, nullptr}, *PSI = nullptr, *theta = nullptr;

@@ -49,8 +49,6 @@ struct VertexArgs {
   const double* escale;  // per edge slot: theta_row * theta_col (degree-corrected runs), refreshed with theta
   const int4* tiles;     // [ntiles] (first vertex, #vertices, first edge slot, #edge slots)
   int ntiles;
-  const int* vorder;  // non-hub vertices in processing order (grouped by ceil(degree / QP), largest first)
-  int nmain;
   const int* hubs;    // vertex ids with degree > TILE_E
   const double* theta;
   const int* pidx;            // per vertex: row of the prior table, 1 + degree * Q + MAP block (0: theta = 1)
@@ -59,6 +57,7 @@ struct VertexArgs {
   double* nxt;
   double* PSI;
   double* partials;   // [(grid + nhubs)][PSTRIDE]
+  double* mpart;      // [(grid + nhubs)][Q * Q]: M-step statistics (sbm.jl) per CTA
   int* status;
   double damping;
   int dc;
@@ -150,8 +149,7 @@ __device__ __forceinline__ void edge_transform(const double (&psi)[Q], double sc
 // Cavity message i -> j (sbm.jl:108-109) from the vertex product u and this edge's factor T, the absolute
 // clamp of normalize_logprob (sbm.jl:42) at 2^(ffrac + n) in the scaled domain, damping, scatter to rev slot.
 __device__ __forceinline__ void emit_message(const VertexArgs& a, const double* __restrict__ u, const double (&T)[Q],
-                                             double ffrac, int n, int rv) {
-  double w[Q];
+                                             double ffrac, int n, int rv, double (&w)[Q]) {
   double S = 0.0;
   bool low = false;
   const double thr = pow2c(n + 1);
@@ -183,10 +181,76 @@ __device__ __forceinline__ void emit_message(const VertexArgs& a, const double* 
   store_vec<Q>(a.nxt, rv, w);
 }
 
+// ---- M-step statistics fused into the sweep ------------------------------------------------------------
+// update_Crs (sbm.jl:128-136) needs G[s][t] = sum over directed links (i,j) of a_s b_t / Z with a = psi_{i->j},
+// b = psi_{j->i}, Z = sum_st a_s Crs_st b_t.  The thread that emits psi_{i->j} holds both (its new output and the
+// message it consumed), so the statistics are accumulated right there -- the new outgoing message paired with the
+// previous incoming one; at the fixed point that is the reference's pairing -- and the 1 GB re-read of a separate
+// M-step pass disappears.  The accumulation sum_e a(e) (x) b(e) is a (q x E) x (E x q) product: it runs as FP64
+// DMMA m8n8k4 over groups of 4 edge slots, operands exchanged through the warp's own rows of shared memory, the
+// q x q accumulator living in two registers per lane per 8x8 block for the whole kernel.
+constexpr int MB = (Q + 7) / 8;  // 8x8 blocks per dimension
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+struct MstepAcc {
+  double c[MB * MB * 2];
+};
+
+// Called by a full warp.  arow: the warp's 32 rows (stride QS doubles) holding a/Z of its 32 edge slots;
+// bget(r, comp): component `comp` of the message consumed by the warp's r-th slot; nrows = how many are real.
+template <typename BGet>
+__device__ __forceinline__ void mstep_accumulate(MstepAcc& g, const double* arow, BGet bget, int nrows) {
+  const int lane = threadIdx.x & 31;
+  const int k = lane & 3, cidx = lane >> 2;
+#pragma unroll
+  for (int grp = 0; grp < 8; ++grp) {
+    const int r = 4 * grp + k;
+    const bool live = r < nrows;
+    double av[MB], bv[MB];
+#pragma unroll
+    for (int m = 0; m < MB; ++m) {
+      const int comp = m * 8 + cidx;
+      av[m] = (live && comp < Q) ? arow[r * QS + comp] : 0.0;
+      bv[m] = (live && comp < Q) ? bget(r, comp) : 0.0;
+    }
+#pragma unroll
+    for (int m = 0; m < MB; ++m)
+#pragma unroll
+      for (int n = 0; n < MB; ++n) dmma884(g.c[(m * MB + n) * 2], g.c[(m * MB + n) * 2 + 1], av[m], bv[n]);
+  }
+}
+
+// Fixed-order reduction of the per-warp q x q accumulators into this CTA's row of the M-step partials.
+__device__ __forceinline__ void store_mstep_partials(const MstepAcc& g, double* scratch /* smem, >= 64 * MB * MB */,
+                                                     double* mrow) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int w = 0; w < NT / 32; ++w) {
+    __syncthreads();
+    if (warp == w) {
+#pragma unroll
+      for (int m = 0; m < MB; ++m)
+#pragma unroll
+        for (int n = 0; n < MB; ++n)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int row = m * 8 + (lane >> 2), col = n * 8 + (lane & 3) * 2 + j;
+            const int idx = row * (8 * MB) + col;
+            scratch[idx] = (w == 0 ? 0.0 : scratch[idx]) + g.c[(m * MB + n) * 2 + j];
+          }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Q * Q; i += NT) mrow[i] = scratch[(i / Q) * (8 * MB) + (i % Q)];
+}
+
 // Per-thread accumulators of the aggregation lanes (lane t of a group owns component t).
 struct LaneAcc {
   double psi = 0.0;   // sum of PSI_i(t)
   double dpsi = 0.0;  // sum of degree_i PSI_i(t)  (h of mod.jl:22-24)
+  double mod = 0.0;   // sum over this thread's edge slots of the omega_in statistic (mod.jl:86-87)
   double res = 0.0;   // sum of per-vertex L1 changes (lane t = 0)
   double logz = 0.0;  // sum of log Z_i            (lane t = 0)
   double vmax = 0.0;  // max per-vertex L1 change  (lane t = 0)
@@ -348,6 +412,14 @@ __device__ __forceinline__ void store_partials(const LaneAcc& acc, double* scrat
       for (int k = tid; k < NT; k += LV) s += scratch[k];
       prow[3 + 3 * Q + tid] = s;
     }
+    __syncthreads();
+    scratch[tid] = acc.mod;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int k = 0; k < NT; ++k) s += scratch[k];
+      prow[3 + 4 * Q] = s;
+    }
   }
 }
 
@@ -399,7 +471,7 @@ struct SweepSmem {
   static constexpr size_t u_off = t_off + (size_t)TILE_E * QS * 8;
   static constexpr size_t ff_off = u_off + (size_t)TV * Q * 8;
   static constexpr size_t scratch_off = ff_off + (size_t)TV * 8;
-  static constexpr size_t dr_off = scratch_off + (size_t)NT * 8;
+  static constexpr size_t dr_off = scratch_off + (size_t)(NT > 64 * MB * MB ? NT : 64 * MB * MB) * 8;
   static constexpr size_t nr_off = dr_off + (size_t)Q * 8;
   static constexpr size_t fn_off = nr_off + (size_t)Q * 4;
   static constexpr size_t lv_off = fn_off + (size_t)TV * 4;
@@ -501,6 +573,9 @@ __global__ void __launch_bounds__(NT, ((Q <= 8) ? 3 : 2) * (256 / NT)) sbm_verte
     s_nr[tid] = 0;
   }
   LaneAcc acc;
+  MstepAcc macc;
+#pragma unroll
+  for (int k = 0; k < MB * MB * 2; ++k) macc.c[k] = 0.0;
   const int t = tid % LV;
   const bool tl = t < Q;
   const int tt = tl ? t : 0;
@@ -617,133 +692,56 @@ __global__ void __launch_bounds__(NT, ((Q <= 8) ? 3 : 2) * (256 / NT)) sbm_verte
 
     // ---- stage 3 ----
     if constexpr (MODE == MODE_SWEEP) {
+      double mod_term = 0.0;
       if (tid < ne) {
         const int lv = lvS[tid];
         const int rv = reinterpret_cast<const int*>(cb + StageBuf::rev_off)[tid];
-        emit_message(a, &Usm[lv * Q], T, ffS[lv], fnS[lv], rv);
+        double w[Q];
+        emit_message(a, &Usm[lv * Q], T, ffS[lv], fnS[lv], rv, w);
+        if constexpr (MODEL == MODEL_SBM) {
+          // a / Z for the M-step: Z = sum_s a_s (Crs b)_s = sum_s w_s T_s / sc
+          const double sc = a.dc ? reinterpret_cast<const double*>(cb + StageBuf::sc_off)[tid] : 1.0;
+          double z = 0.0;
+#pragma unroll
+          for (int k = 0; k < Q; ++k) z = fma(w[k], T[k], z);
+          const double kz = sc * fast_rcp(z);
+#pragma unroll
+          for (int k = 0; k < Q; ++k) Tsm[tid * QS + k] = w[k] * kz;   // this thread's own row: free since stage 2
+        } else {
+          // mod.jl:86-87: s = psi_{i->j} . psi_{j->i};  omega_in s / ((omega_in - omega_out) s + omega_out)
+          double psi[Q];
+          read_staged(cb, tid, psi);
+          double sdot = 0.0;
+#pragma unroll
+          for (int k = 0; k < Q; ++k) sdot = fma(w[k], psi[k], sdot);
+          mod_term = c_P.oin * sdot / ((c_P.oin - c_P.oout) * sdot + c_P.oout);
+        }
+      }
+      if constexpr (MODEL == MODEL_SBM) {
+        __syncwarp();
+        const int wbase = tid & ~31;
+        const char* pb = cb + StageBuf::psi_off;
+        mstep_accumulate(macc, &Tsm[wbase * QS],
+                         [&](int r, int comp) {
+                           const int row = wbase + r;
+                           if constexpr (CHB == 16)
+                             return *reinterpret_cast<const double*>(pb + row * ROWB + swz_unit(row, comp >> 1) * 16 +
+                                                                     (comp & 1) * 8);
+                           else
+                             return *reinterpret_cast<const double*>(pb + row * ROWB + comp * 8);
+                         },
+                         ne - wbase);
+        __syncwarp();
+      } else {
+        acc.mod += mod_term;
       }
     }
     td = tdK1;
     buf ^= 1;
   }
   store_partials(acc, scratch, a.partials + (size_t)blockIdx.x * PSTRIDE, s_dr, s_nr);
-}
-
-// ---------------------------------------------------------------------------------------------
-// BP sweep, warp-autonomous variant: QP lanes per vertex, no shared memory, no CTA barrier in the loop.
-//   pass 1  lane j of the group takes edge slots b+j, b+j+QP, ... of its vertex, each as a whole edge:
-//           T = theta theta psi*Crs (Q*Q DFMA with uniform operands), running product per component
-//   reduce  butterfly reduce-scatter of the partial products over the QP lanes: lane t ends with component t
-//   finish  prior, clamp floor, marginal, residual (lane t = component t), all-gather of u
-//   pass 2  the same lanes revisit their edge slots (messages now L1/L2 hits), cavity = u / T, clamp,
-//           normalise, damp, scatter to rev[e]
-// Vertices are visited in `vorder` (same ceil(degree/QP) inside a warp), so the lanes of a warp run the same
-// number of iterations.
-__device__ __forceinline__ double edge_scale(const VertexArgs& a, double th, int e) {
-  return a.dc ? th * a.theta[a.col[e]] : 1.0;
-}
-
-// Divide the vector by 2^ex, ex = exponent of its largest entry; returns ex (0 if that entry is 0/NaN/Inf).
-__device__ __forceinline__ int renorm_vec(double (&P)[QP]) {
-  double m = 0.0;
-#pragma unroll
-  for (int t = 0; t < Q; ++t) m = (P[t] > m) ? P[t] : m;
-  bool ok;
-  int ex = exponent_of(m, ok);
-  if (!ok) ex = 0;
-  const double s2 = pow2i(-ex);
-#pragma unroll
-  for (int t = 0; t < Q; ++t) P[t] *= s2;
-  return ex;
-}
-
-// Multiply-reduce-scatter over the QP lanes of a group: on return lane j holds prod over lanes of P_lane[j].
-template <int W>
-__device__ __forceinline__ double reduce_scatter_mul(double (&P)[QP], int j) {
-  if constexpr (W == 1) {
-    return P[0];
-  } else {
-    constexpr int H = W / 2;
-    const bool up = (j & H) != 0;
-#pragma unroll
-    for (int i = 0; i < H; ++i) {
-      const double send = up ? P[i] : P[i + H];
-      const double keep = up ? P[i + H] : P[i];
-      P[i] = keep * __shfl_xor_sync(0xffffffffu, send, H);
-    }
-    return reduce_scatter_mul<H>(P, j);
-  }
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(NT, 2 * (256 / NT)) sbm_group_kernel(VertexArgs a) {
-  __shared__ double scratch[NT];
-  __shared__ unsigned long long s_dr[Q];
-  __shared__ int s_nr[Q];
-  const int tid = threadIdx.x;
-  if (tid < Q) {
-    s_dr[tid] = 0ull;
-    s_nr[tid] = 0;
-  }
-  __syncthreads();
-  LaneAcc acc;
-  const int j = tid % QP;               // lane inside the group == component owned in the finishing stage
-  const bool tl = j < Q;
-  constexpr int GPB = NT / QP;          // groups (vertices) per CTA per step
-  const int gstride = gridDim.x * GPB;
-
-  for (int base = blockIdx.x * GPB + (tid & ~31) / QP; base < a.nmain; base += gstride) {
-    const int idx = base + (tid & 31) / QP;
-    const bool valid = idx < a.nmain;
-    int gv = 0, b = 0, e = 0;
-    if (valid) {
-      gv = a.vorder[idx];
-      b = a.rowptr[gv];
-      e = a.rowptr[gv + 1];
-    }
-    const double th = (a.dc && valid) ? a.theta[gv] : 1.0;
-    const double old = (MODE == MODE_SWEEP && valid && tl) ? a.PSI[(size_t)gv * Q + j] : 0.0;
-    const Prior pr = load_prior<MODE>(a, valid ? a.pidx[gv] : 0, j);
-
-    // ---- pass 1 ----
-    double P[QP];
-#pragma unroll
-    for (int t = 0; t < QP; ++t) P[t] = 1.0;
-    int K = 0, it = 0;
-    for (int k = b + j; k < e; k += QP) {
-      double psi[Q], T[Q];
-      load_vec<Q>(a.cur, k, psi);
-      edge_factor(psi, edge_scale(a, th, k), T);
-#pragma unroll
-      for (int t = 0; t < Q; ++t) P[t] *= T[t];
-      if ((++it & 3) == 0) K += renorm_vec(P);  // keeps long rows inside the double range
-    }
-    K += renorm_vec(P);
-    // ---- reduce over the group ----
-#pragma unroll
-    for (int o = QP / 2; o > 0; o >>= 1) K += __shfl_xor_sync(0xffffffffu, K, o);
-    const double prod = reduce_scatter_mul<QP>(P, j);
-
-    // ---- finish (lane j = component j) ----
-    double u;
-    int fn;
-    vertex_finish<MODE>(a, valid, gv, e - b, j, pr, old, prod, K, u, fn, acc, s_dr, s_nr);
-    const double ffrac = pr.ffrac;
-
-    // ---- pass 2 ----
-    if constexpr (MODE == MODE_SWEEP) {
-      double uu[Q];
-#pragma unroll
-      for (int t = 0; t < Q; ++t) uu[t] = __shfl_sync(0xffffffffu, u, t, QP);
-      for (int k = b + j; k < e; k += QP) {
-        double psi[Q], T[Q];
-        load_vec<Q>(a.cur, k, psi);
-        edge_factor(psi, edge_scale(a, th, k), T);
-        emit_message(a, uu, T, ffrac, fn, a.rev[k]);
-      }
-    }
-  }
-  store_partials(acc, scratch, a.partials + (size_t)blockIdx.x * PSTRIDE, s_dr, s_nr);
+  if constexpr (MODE == MODE_SWEEP && MODEL == MODEL_SBM)
+    store_mstep_partials(macc, scratch, a.mpart + (size_t)blockIdx.x * Q * Q);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -755,7 +753,9 @@ __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base
   __shared__ int pkS[(NT / 32) * Q];
   __shared__ int ksS[NT / 32];
   __shared__ double Ush[Q];
-  __shared__ double scratch[NT];
+  __shared__ double scratch[(NT > 64 * MB * MB) ? NT : 64 * MB * MB];
+  __shared__ double rowA[(MODEL == MODEL_SBM && MODE == MODE_SWEEP) ? NT * QS : 1];   // a / Z of the warp's 32 slots
+  __shared__ double rowB[(MODEL == MODEL_SBM && MODE == MODE_SWEEP) ? NT * QS : 1];   // consumed messages
   __shared__ double ffSh;
   __shared__ int fnSh;
   __shared__ unsigned long long s_dr[Q];
@@ -771,6 +771,7 @@ __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base
     s_nr[tid] = 0;
   }
 
+  double macc_mod = 0.0;
   double pm[Q];
   int pk[Q];
 #pragma unroll
@@ -858,18 +859,54 @@ __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base
   }
   __syncthreads();
 
+  MstepAcc macc;
+#pragma unroll
+  for (int k = 0; k < MB * MB * 2; ++k) macc.c[k] = 0.0;
   if constexpr (MODE == MODE_SWEEP) {
-    for (int e = e0 + tid; e < e1; e += NT) {
-      double psi[Q], T[Q];
-      int ke;
-      load_vec<Q>(a.cur, e, psi);
-      const double sc = (MODEL == MODEL_SBM && a.dc) ? th * a.theta[a.col[e]] : 1.0;
-      edge_transform(psi, sc, T, ke);
-      emit_message(a, Ush, T, ffSh, fnSh + ke, a.rev[e]);
+    for (int base = e0; base < e1; base += NT) {  // uniform trip count: the M-step accumulation is warp-wide
+      const int e = base + tid;
+      double mod_term = 0.0;
+      if (e < e1) {
+        double psi[Q], T[Q], w[Q];
+        int ke;
+        load_vec<Q>(a.cur, e, psi);
+        const double sc = (MODEL == MODEL_SBM && a.dc) ? th * a.theta[a.col[e]] : 1.0;
+        edge_transform(psi, sc, T, ke);
+        emit_message(a, Ush, T, ffSh, fnSh + ke, a.rev[e], w);
+        if constexpr (MODEL == MODEL_SBM) {
+          double z = 0.0;
+#pragma unroll
+          for (int k = 0; k < Q; ++k) z = fma(w[k], T[k], z);
+          const double kz = sc * pow2i(-ke) * fast_rcp(z);  // T carries the extra factor 2^-ke here
+#pragma unroll
+          for (int k = 0; k < Q; ++k) {
+            rowA[tid * QS + k] = w[k] * kz;
+            rowB[tid * QS + k] = psi[k];
+          }
+        } else {
+          double sdot = 0.0;
+#pragma unroll
+          for (int k = 0; k < Q; ++k) sdot = fma(w[k], psi[k], sdot);
+          mod_term = c_P.oin * sdot / ((c_P.oin - c_P.oout) * sdot + c_P.oout);
+        }
+      }
+      if constexpr (MODEL == MODEL_SBM) {
+        __syncwarp();
+        const int wbase = tid & ~31;
+        const double* bb = &rowB[wbase * QS];
+        mstep_accumulate(macc, &rowA[wbase * QS], [&](int r, int comp) { return bb[r * QS + comp]; },
+                         e1 - base - wbase);
+        __syncwarp();
+      } else {
+        macc_mod += mod_term;
+      }
     }
   }
-  // warp 0 carries the accumulators (LaneAcc of every other thread is zero); its group layout matches LV = QP
+  // warp 0 carries the vertex accumulators (LaneAcc of every other thread is zero); its group layout matches LV = QP
+  acc.mod = macc_mod;
   store_partials(acc, scratch, a.partials + (size_t)(part_base + blockIdx.x) * PSTRIDE, s_dr, s_nr);
+  if constexpr (MODE == MODE_SWEEP && MODEL == MODEL_SBM)
+    store_mstep_partials(macc, scratch, a.mpart + (size_t)(part_base + blockIdx.x) * Q * Q);
 }
 
 // theta_row * theta_col per edge slot, refreshed after update_theta (degree-corrected runs): keeps the random
@@ -921,116 +958,19 @@ __global__ void sbm_reduce_vertex(SbmState* st, const double* partials, int nrow
 }
 
 // ---------------------------------------------------------------------------------------------
-// M-step statistics, update_Crs() sbm.jl:128-136.  One thread per undirected edge (slot e with rev[e] < e).
-// H[s][t] (s <= t) = sum over undirected edges of (a_s b_t + a_t b_s) / Z, with a = psi_{i->j}, b = psi_{j->i},
-// Z = sum_st a_s Crs_st b_t.  Summed over both directions of every link (sbm.jl:130-136) and with Crs symmetric,
-// Crsnew = Crs .* H  (H_ss = 2 G_ss).  The upper triangle is held in registers; wide q take several passes.
-constexpr int mstep_rows(int q) {
-  int R = q;
-  while (R > 1 && R * q - R * (R - 1) / 2 > 64) --R;
-  return R;
-}
-constexpr int MS_R = mstep_rows(Q);
-constexpr int MS_NCH = (Q + MS_R - 1) / MS_R;
-constexpr int MS_STRIDE = MS_NCH * MS_R * Q;
-
-constexpr int NTM = 320;  // one CTA per SM: 36 accumulators + two edges' messages in registers per thread
-
-template <int NV>
-__device__ __forceinline__ void block_reduce_store_m(double (&v)[NV], double* red, double* dst) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    double x = v[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    if (lane == 0) red[warp * NV + k] = x;
-  }
-  __syncthreads();
-  for (int k = threadIdx.x; k < NV; k += NTM) {
-    double s = 0.0;
-#pragma unroll
-    for (int w = 0; w < NTM / 32; ++w) s += red[w * NV + k];
-    dst[k] = s;
-  }
-  __syncthreads();
-}
-
-// `und` lists every undirected edge once as (slot e, slot rev[e]) with rev[e] < e.  Loads of the next edge are
-// issued before the arithmetic of the current one (two edges in flight per thread).
-__global__ void __launch_bounds__(NTM, 1) sbm_mstep_kernel(const int2* __restrict__ und, long long L,
-                                                          const double* __restrict__ psi, double* partials) {
-  __shared__ double red[(NTM / 32) * MS_R * Q];
-  const long long stride = (long long)gridDim.x * NTM;
-#pragma unroll
-  for (int ch = 0; ch < MS_NCH; ++ch) {
-    double acc[MS_R * Q];
-#pragma unroll
-    for (int k = 0; k < MS_R * Q; ++k) acc[k] = 0.0;
-    long long i = (long long)blockIdx.x * NTM + threadIdx.x;
-    // software pipeline: slot pair of edge i + 2*stride and messages of edge i + stride are in flight while edge i
-    // is being accumulated
-    double an[Q], bn[Q];
-    int2 ern = make_int2(0, 0);
-    if (i < L) {
-      const int2 er = und[i];
-      load_vec<Q>(psi, er.x, bn);  // col -> row
-      load_vec<Q>(psi, er.y, an);  // row -> col
-    }
-    if (i + stride < L) ern = und[i + stride];
-    while (i < L) {
-      double a[Q], b[Q];
-#pragma unroll
-      for (int t = 0; t < Q; ++t) {
-        a[t] = an[t];
-        b[t] = bn[t];
-      }
-      i += stride;
-      if (i < L) {
-        const int2 er = ern;
-        if (i + stride < L) ern = und[i + stride];
-        load_vec<Q>(psi, er.x, bn);
-        load_vec<Q>(psi, er.y, an);
-      }
-      double Z = 0.0;
-#pragma unroll
-      for (int s = 0; s < Q; ++s) {
-        double cb = 0.0;
-#pragma unroll
-        for (int t = 0; t < Q; ++t) cb = fma(c_P.C[s * Q + t], b[t], cb);
-        Z = fma(a[s], cb, Z);
-      }
-      const double invZ = 1.0 / Z;  // 0, NaN or Inf here ends up in Crs and is reported by the caller's checks
-#pragma unroll
-      for (int t = 0; t < Q; ++t) a[t] *= invZ;
-#pragma unroll
-      for (int rr = 0; rr < MS_R; ++rr) {
-        const int s = ch * MS_R + rr;
-        if (s < Q) {
-#pragma unroll
-          for (int t = s; t < Q; ++t) {
-            acc[rr * Q + t] = fma(a[s], b[t], acc[rr * Q + t]);
-            acc[rr * Q + t] = fma(a[t], b[s], acc[rr * Q + t]);
-          }
-        }
-      }
-    }
-    block_reduce_store_m<MS_R * Q>(acc, red, partials + (size_t)blockIdx.x * MS_STRIDE + ch * MS_R * Q);
-  }
-}
-
+// update_Crs(), sbm.jl:137-147, from the statistics the sweep accumulated (G summed over all directed links).
 __global__ void sbm_reduce_mstep(SbmState* st, const double* partials, int nrows, double lr, double maxCrs, double N) {
   __shared__ double G[Q * Q];
   const int tid = threadIdx.x;
   for (int c = tid >> 5; c < Q * Q; c += blockDim.x >> 5) {
-    const double v = warp_column_reduce(partials, nrows, MS_STRIDE, c);
+    const double v = warp_column_reduce(partials, nrows, Q * Q, c);
     if ((tid & 31) == 0) G[c] = v;
   }
   __syncthreads();
   if (tid < Q * Q) {
     const int s = tid / Q, t = tid - s * Q;
     const double Cold = st->C[tid];
-    const double Cn = Cold * (s <= t ? G[s * Q + t] : G[t * Q + s]);
+    const double Cn = Cold * 0.5 * (G[s * Q + t] + G[t * Q + s]);  // Crsnew is symmetric (both directions of every link)
     double c = lr * Cn / (N * st->gr[s] * st->gr[t]) + (1.0 - lr) * Cold;  // sbm.jl:137
     if (c > maxCrs) c = maxCrs; else if (c < 0.0) c = 0.0;                  // sbm.jl:138-146
     if (!(c == c)) st->status |= 1;
@@ -1306,8 +1246,6 @@ VertexArgs vertex_args(gbx_sbm* h) {
   a.escale = h->escale;
   a.tiles = h->tiles;
   a.ntiles = h->ntiles;
-  a.vorder = h->vorder;
-  a.nmain = h->nmain;
   a.hubs = h->hubs;
   a.theta = h->theta;
   a.pidx = h->pidx;
@@ -1316,6 +1254,7 @@ VertexArgs vertex_args(gbx_sbm* h) {
   a.nxt = h->msg[h->cur ^ 1];
   a.PSI = h->PSI;
   a.partials = h->part_vertex;
+  a.mpart = h->part_mstep;
   a.status = &h->st->status;
   a.damping = (MODEL == MODEL_MOD) ? h->mopt.damping : h->opt.damping;
   a.dc = (MODEL == MODEL_MOD) ? h->mopt.dc : h->opt.degreecorrection;
@@ -1325,9 +1264,8 @@ VertexArgs vertex_args(gbx_sbm* h) {
 template <int MODE>
 int launch_vertex_pass_t(gbx_sbm* h) {
   VertexArgs a = vertex_args(h);
-  if (h->nmain > 0) {
-    if (MODEL == MODEL_SBM && h->sweep_variant == 0) sbm_group_kernel<MODE><<<h->grid_vertex, NT, 0, h->stream>>>(a);
-    else sbm_vertex_kernel<MODE><<<h->grid_vertex, NT, SweepSmem::total, h->stream>>>(a);
+  if (h->ntiles > 0) {
+    sbm_vertex_kernel<MODE><<<h->grid_vertex, NT, SweepSmem::total, h->stream>>>(a);
     h->launches++;
   }
   if (h->nhubs > 0) {
@@ -1345,8 +1283,8 @@ int op_vertex_pass(gbx_sbm* h, int mode) {
 }
 
 int op_reduce_vertex(gbx_sbm* h, int mode) {
-  const int nrows = (h->nmain > 0 ? h->grid_vertex : 0) + h->nhubs;
-  const double* base = h->part_vertex + (h->nmain > 0 ? 0 : (size_t)h->grid_vertex * PSTRIDE);
+  const int nrows = (h->ntiles > 0 ? h->grid_vertex : 0) + h->nhubs;
+  const double* base = h->part_vertex + (h->ntiles > 0 ? 0 : (size_t)h->grid_vertex * PSTRIDE);
   sbm_reduce_vertex<<<1, 256, 0, h->stream>>>(h->st, base, nrows, mode, h->opt.priorlearning,
                                              h->opt.degreecorrection, (double)h->n);
   h->launches++;
@@ -1372,10 +1310,10 @@ int op_prepare(gbx_sbm* h, int zero_h, int gr_from_sum) {
 
 int op_mstep(gbx_sbm* h) {
   const double maxCrs = h->opt.maxCrs > 0 ? h->opt.maxCrs : (double)h->n;
-  sbm_mstep_kernel<<<h->grid_mstep, NTM, 0, h->stream>>>(h->und, (long long)(h->K / 2), h->msg[h->cur], h->part_mstep);
-  sbm_reduce_mstep<<<1, 256, 0, h->stream>>>(h->st, h->part_mstep, h->grid_mstep, h->opt.learningrate, maxCrs,
-                                             (double)h->n);
-  h->launches += 2;
+  const int nrows = (h->ntiles > 0 ? h->grid_vertex : 0) + h->nhubs;
+  const double* base = h->part_mstep + (h->ntiles > 0 ? 0 : (size_t)h->grid_vertex * Q * Q);
+  sbm_reduce_mstep<<<1, 256, 0, h->stream>>>(h->st, base, nrows, h->opt.learningrate, maxCrs, (double)h->n);
+  h->launches += 1;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
 }
@@ -1386,7 +1324,7 @@ int op_theta(gbx_sbm* h) {
   h->theta_valid = true;
   sbm_reduce_theta<<<1, 256, 0, h->stream>>>(h->st, h->part_theta, h->grid_theta);
   h->launches += 2;
-  if (h->ntiles > 0 && h->sweep_variant != 0) {
+  if (h->ntiles > 0) {
     sbm_escale_kernel<<<grid_for(h, h->K), 256, 0, h->stream>>>(h->erow, h->col, (long long)h->K, h->theta, h->escale);
     h->launches++;
   }
@@ -1443,15 +1381,14 @@ int op_init_model(gbx_sbm* h) {
 }
 
 int op_occupancy(int variant, int* vertex_occ, int* mstep_occ) {
-  if (variant == 0)
-    GBX_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(vertex_occ, sbm_group_kernel<MODE_SWEEP>, NT, 0));
-  else {
+  (void)variant;
+  {
     GBX_CUDA_TRY(cudaFuncSetAttribute(sbm_vertex_kernel<MODE_SWEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepSmem::total));
     GBX_CUDA_TRY(cudaFuncSetAttribute(sbm_vertex_kernel<MODE_MARGINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepSmem::total));
     GBX_CUDA_TRY(cudaFuncSetAttribute(sbm_vertex_kernel<MODE_LOGZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepSmem::total));
     GBX_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(vertex_occ, sbm_vertex_kernel<MODE_SWEEP>, NT, SweepSmem::total));
   }
-  GBX_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(mstep_occ, sbm_mstep_kernel, NTM, 0));
+  *mstep_occ = 1;
   return GBX_OK;
 }
 
@@ -1465,7 +1402,7 @@ __global__ void mod_reduce_vertex(SbmState* st, const double* partials, int nrow
                                   double N) {
   __shared__ double tot[PSTRIDE];
   const int tid = threadIdx.x;
-  for (int c = tid >> 5; c < 4 * Q + 3; c += blockDim.x >> 5) {
+  for (int c = tid >> 5; c < 4 * Q + 4; c += blockDim.x >> 5) {
     const double v = (c == 2 + 3 * Q) ? warp_column_reduce<true>(partials, nrows, PSTRIDE, c)
                                       : warp_column_reduce<false>(partials, nrows, PSTRIDE, c);
     if ((tid & 31) == 0) tot[c] = v;
@@ -1478,6 +1415,7 @@ __global__ void mod_reduce_vertex(SbmState* st, const double* partials, int nrow
     }
     return;
   }
+  if (tid == 0 && mode == MODE_SWEEP) st->omegainnew2 = tot[3 + 4 * Q];
   if (tid < Q) {
     const double snew = tot[2 + tid];
     st->sumPSI[tid] = snew;
@@ -1503,6 +1441,8 @@ __global__ void mod_prepare(SbmState* st, SbmParams* out, double N, int zero_h) 
     out->logN = log(N);
     const double eb1 = exp(st->beta) - 1.0;             // written as in mod.jl:42
     out->eb1 = eb1;
+    out->oin = st->omegain;
+    out->oout = st->omegaout;
     double hn2 = 0.0;
     for (int t = 0; t < Q; ++t) {
       const double hh = zero_h ? 0.0 : st->Stheta[t];
@@ -1515,31 +1455,12 @@ __global__ void mod_prepare(SbmState* st, SbmParams* out, double N, int zero_h) 
   }
 }
 
-// update_omega(), mod.jl:77-88: omegainnew = sum over undirected edges of omega_in s / ((omega_in - omega_out) s + omega_out)
-__global__ void __launch_bounds__(NT) mod_mstep_kernel(const SbmState* st, const int2* __restrict__ und, long long L,
-                                                       const double* __restrict__ psi, double* partials) {
-  __shared__ double red[NT / 32];
-  const double oin = st->omegain, oout = st->omegaout;
-  double acc[1] = {0.0};
-  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < L; i += (long long)gridDim.x * NT) {
-    const int2 er = und[i];
-    double a[Q], b[Q];
-    load_vec<Q>(psi, er.x, b);
-    load_vec<Q>(psi, er.y, a);
-    double s = 0.0;
-#pragma unroll
-    for (int t = 0; t < Q; ++t) s = fma(a[t], b[t], s);
-    acc[0] += oin * s / ((oin - oout) * s + oout);
-  }
-  block_reduce_store<1>(acc, red, partials + blockIdx.x);
-}
-
 // mod.jl:89-105 and 224-229: new omegas, clamps, learning-rate mix, update_alphabeta
-__global__ void mod_reduce_mstep(SbmState* st, const double* partials, int nrows, double lr, double maxomega,
-                                 double N, double K, int dc) {
-  if (threadIdx.x >= 32) return;
-  const double omegainnew = warp_column_reduce(partials, nrows, 1, 0);
+// The statistic sum_e omega_in s_e / ((omega_in - omega_out) s_e + omega_out) (mod.jl:86-87) is accumulated by the
+// sweep over ALL directed slots (new outgoing message . previous incoming one), i.e. twice per undirected edge.
+__global__ void mod_reduce_mstep(SbmState* st, double lr, double maxomega, double N, double K, int dc) {
   if (threadIdx.x == 0) {
+    const double omegainnew = 0.5 * st->omegainnew2;
     double dn = 0.0;
     for (int t = 0; t < Q; ++t) dn += st->Stheta[t] * st->Stheta[t];  // norm(update_h())^2 of the new marginals
     double oin = 2.0 * omegainnew / dn;
@@ -1634,8 +1555,8 @@ __global__ void mod_finalize(SbmState* st, double N, double L, double constshift
 }
 
 int mop_reduce_vertex(gbx_sbm* h, int mode) {
-  const int nrows = (h->nmain > 0 ? h->grid_vertex : 0) + h->nhubs;
-  const double* base = h->part_vertex + (h->nmain > 0 ? 0 : (size_t)h->grid_vertex * PSTRIDE);
+  const int nrows = (h->ntiles > 0 ? h->grid_vertex : 0) + h->nhubs;
+  const double* base = h->part_vertex + (h->ntiles > 0 ? 0 : (size_t)h->grid_vertex * PSTRIDE);
   mod_reduce_vertex<<<1, 256, 0, h->stream>>>(h->st, base, nrows, mode, h->mopt.priorlearning, h->mopt.dc, (double)h->n);
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
@@ -1656,10 +1577,9 @@ int mop_prepare(gbx_sbm* h, int zero_h, int) {
 }
 
 int mop_mstep(gbx_sbm* h) {
-  mod_mstep_kernel<<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->und, (long long)(h->K / 2), h->msg[h->cur], h->part_fe);
-  mod_reduce_mstep<<<1, 32, 0, h->stream>>>(h->st, h->part_fe, h->grid_fe, h->mopt.learningrate, h->mopt.maxomega,
-                                            (double)h->n, (double)h->K, h->mopt.dc);
-  h->launches += 2;
+  mod_reduce_mstep<<<1, 32, 0, h->stream>>>(h->st, h->mopt.learningrate, h->mopt.maxomega, (double)h->n, (double)h->K,
+                                            h->mopt.dc);
+  h->launches += 1;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
 }

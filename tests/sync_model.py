@@ -14,7 +14,7 @@ One EM iteration (mirrors sbm.jl:342-347 with a Jacobi sweep in place of `BP()`)
         PSI'_i = normalize_logprob(logPSI_i)                                        (sbm.jl:117-118)
     conv = sum |PSI' - PSI| / N                         (sbm.jl:123)
     gr  += mean(PSI') - mean(PSI)   if priorlearning    (sbm.jl:120-122)
-    Crs <- update_Crs()                                 (sbm.jl:128-148)
+    Crs <- update_Crs()                                 (sbm.jl:128-148; new outgoing x previous incoming message)
     theta <- update_theta() if degreecorrection         (sbm.jl:47-64)
 """
 from __future__ import annotations
@@ -82,12 +82,16 @@ def sweep(g, psi, theta, C, gr, h, damping=1.0):
     return new, _normalize_logprob_rows(logPSI), logPSI
 
 
-def update_Crs(g, psi, theta, C, gr, n, maxCrs, lr):
-    a = psi[g["rev"]]          # message row -> col   (PSIcav[indij] with i = row)
-    b = psi                    # message col -> row
+def update_Crs(g, psi_new, psi_old, theta, C, gr, n, maxCrs, lr):
+    """sbm.jl:128-148 on the pairs the sweep has in hand: for the link (i, j) handled at slot e (row i, col j) the
+    NEW message i -> j (just emitted, stored at rev[e]) and the message j -> i it was computed from.  Summed over
+    all directed links and symmetrised (with all-new messages the sum is symmetric by itself); same fixed point."""
+    a = psi_new[g["rev"]]      # message row -> col   (PSIcav[indij] with i = row)
+    b = psi_old                # message col -> row
     w = (theta[g["row"]] * theta[g["col"]])[:, None, None] * a[:, :, None] * b[:, None, :] * C[None]
     w = w / w.sum(axis=(1, 2), keepdims=True)
     Cn = w.sum(axis=0)
+    Cn = 0.5 * (Cn + Cn.T)
     C2 = lr * Cn / (n * np.outer(gr, gr)) + (1 - lr) * C
     return np.clip(C2, 0.0, maxCrs)
 
@@ -131,8 +135,9 @@ class SyncSBM:
         self.conv = float(np.abs(PSI - self.PSI).sum() / self.n)
         if self.prior:
             self.gr = self.gr + (PSI.mean(axis=0) - self.PSI.mean(axis=0))
+        old = self.psi
         self.psi, self.PSI = psi, PSI
-        self.C = update_Crs(self.g, self.psi, self.theta, self.C, self.gr, self.n, self.maxCrs, self.lr)
+        self.C = update_Crs(self.g, self.psi, old, self.theta, self.C, self.gr, self.n, self.maxCrs, self.lr)
         if self.dc:
             self.theta = update_theta(self.PSI, self.degrees)
         self.itr += 1

@@ -70,14 +70,16 @@ class SyncMOD:
         self.h = self.update_h()
         psi, PSI = self._sweep(self.psi, self.damping)
         self.conv = float(np.abs(PSI - self.PSI).sum() / self.n)
+        old = self.psi
         self.psi, self.PSI = psi, PSI
         if self.prior:
             self.gr = self.PSI.mean(axis=0)
         if self.learning:
-            sel = g["row"] > g["col"]
-            s = (self.psi[g["rev"]][sel] * self.psi[sel]).sum(axis=1)
+            # mod.jl:79-88 on the pairs the sweep has in hand: new message row -> col with the message col -> row it
+            # was computed from, over all directed slots, i.e. twice per undirected edge (hence the 0.5)
+            s = (self.psi[g["rev"]] * old).sum(axis=1)
             oin, oout = self.omegain, self.omegaout
-            omegainnew = float(np.sum(oin * s / ((oin - oout) * s + oout)))
+            omegainnew = 0.5 * float(np.sum(oin * s / ((oin - oout) * s + oout)))
             dn = float(np.linalg.norm(self.update_h()) ** 2)
             oin_n = 2 * omegainnew / dn
             oout_n = 2 * (0.5 * self.K - omegainnew) / ((self.K ** 2 if self.dc else self.n ** 2) - dn)
