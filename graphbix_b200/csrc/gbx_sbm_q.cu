@@ -200,27 +200,33 @@ struct MstepAcc {
 };
 
 // Called by a full warp.  arow: the warp's 32 rows (stride QS doubles) holding a/Z of its 32 edge slots;
-// bget(r, comp): component `comp` of the message consumed by the warp's r-th slot; nrows = how many are real.
-template <typename BGet>
-__device__ __forceinline__ void mstep_accumulate(MstepAcc& g, const double* arow, BGet bget, int nrows) {
+// bget(grp, k, comp): component `comp` of the message consumed by the warp's slot 4*grp + k; nrows = real rows.
+template <bool FULL, typename BGet>
+__device__ __forceinline__ void mstep_accumulate_impl(MstepAcc& g, const double* arow, BGet bget, int nrows) {
   const int lane = threadIdx.x & 31;
   const int k = lane & 3, cidx = lane >> 2;
+  const double* pa = arow + k * QS + cidx;
 #pragma unroll
   for (int grp = 0; grp < 8; ++grp) {
-    const int r = 4 * grp + k;
-    const bool live = r < nrows;
+    const bool live = FULL || (4 * grp + k < nrows);
     double av[MB], bv[MB];
 #pragma unroll
     for (int m = 0; m < MB; ++m) {
       const int comp = m * 8 + cidx;
-      av[m] = (live && comp < Q) ? arow[r * QS + comp] : 0.0;
-      bv[m] = (live && comp < Q) ? bget(r, comp) : 0.0;
+      const bool ok = live && (Q % 8 == 0 || comp < Q);
+      av[m] = ok ? pa[grp * 4 * QS + m * 8] : 0.0;
+      bv[m] = ok ? bget(grp, k, comp) : 0.0;
     }
 #pragma unroll
     for (int m = 0; m < MB; ++m)
 #pragma unroll
       for (int n = 0; n < MB; ++n) dmma884(g.c[(m * MB + n) * 2], g.c[(m * MB + n) * 2 + 1], av[m], bv[n]);
   }
+}
+template <typename BGet>
+__device__ __forceinline__ void mstep_accumulate(MstepAcc& g, const double* arow, BGet bget, int nrows) {
+  if (nrows >= 32) mstep_accumulate_impl<true>(g, arow, bget, 32);
+  else if (nrows > 0) mstep_accumulate_impl<false>(g, arow, bget, nrows);
 }
 
 // Fixed-order reduction of the per-warp q x q accumulators into this CTA's row of the M-step partials.
@@ -353,7 +359,7 @@ __device__ __forceinline__ void vertex_finish(const VertexArgs& a, bool valid, i
       if (t == 0) {
         acc.res += res;
         acc.vmax = fmax(acc.vmax, res);
-        if (eq) {  // findmax: first maximum (sbm.jl:49); eq == 0 only when the marginal is NaN
+        if (MODEL == MODEL_SBM && a.dc && eq) {  // update_theta statistics: findmax, first maximum (sbm.jl:49)
           const int best = __ffs(eq) - 1;
           atomicAdd(&s_dr[best], (unsigned long long)deg);
           atomicAdd(&s_nr[best], 1);
@@ -479,7 +485,7 @@ struct SweepSmem {
 };
 
 __device__ __forceinline__ void cp_async_unit(void* smem_dst, const void* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);  // folds to base + offset after inlining
   if constexpr (CHB == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
   else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
 }
@@ -721,16 +727,29 @@ __global__ void __launch_bounds__(NT, ((Q <= 8) ? 3 : 2) * (256 / NT)) sbm_verte
         __syncwarp();
         const int wbase = tid & ~31;
         const char* pb = cb + StageBuf::psi_off;
-        mstep_accumulate(macc, &Tsm[wbase * QS],
-                         [&](int r, int comp) {
-                           const int row = wbase + r;
-                           if constexpr (CHB == 16)
-                             return *reinterpret_cast<const double*>(pb + row * ROWB + swz_unit(row, comp >> 1) * 16 +
-                                                                     (comp & 1) * 8);
-                           else
-                             return *reinterpret_cast<const double*>(pb + row * ROWB + comp * 8);
-                         },
-                         ne - wbase);
+        const char* pw = pb + wbase * ROWB;  // this warp's 32 staged rows
+        if constexpr (SWZ && CH == 4) {
+          // rotated layout: unit (c + row/2) % 4 of row wbase + 4 grp + k; wbase/2 and 2 grp only flip bit 1
+          const int kk = tid & 3, cc = (tid & 31) >> 2;
+          const int p0 = ((cc >> 1) + (kk >> 1)) & 3;
+          const int off0 = kk * ROWB + p0 * 16 + (cc & 1) * 8, off1 = kk * ROWB + (p0 ^ 2) * 16 + (cc & 1) * 8;
+          mstep_accumulate(macc, &Tsm[wbase * QS],
+                           [&](int grp, int, int) {
+                             return *reinterpret_cast<const double*>(pw + grp * 4 * ROWB + ((grp & 1) ? off1 : off0));
+                           },
+                           ne - wbase);
+        } else {
+          mstep_accumulate(macc, &Tsm[wbase * QS],
+                           [&](int grp, int k, int comp) {
+                             const int row = wbase + 4 * grp + k;
+                             if constexpr (CHB == 16)
+                               return *reinterpret_cast<const double*>(pb + row * ROWB + swz_unit(row, comp >> 1) * 16 +
+                                                                       (comp & 1) * 8);
+                             else
+                               return *reinterpret_cast<const double*>(pb + row * ROWB + comp * 8);
+                           },
+                           ne - wbase);
+        }
         __syncwarp();
       } else {
         acc.mod += mod_term;
@@ -894,7 +913,7 @@ __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base
         __syncwarp();
         const int wbase = tid & ~31;
         const double* bb = &rowB[wbase * QS];
-        mstep_accumulate(macc, &rowA[wbase * QS], [&](int r, int comp) { return bb[r * QS + comp]; },
+        mstep_accumulate(macc, &rowA[wbase * QS], [&](int grp, int k, int comp) { return bb[(4 * grp + k) * QS + comp]; },
                          e1 - base - wbase);
         __syncwarp();
       } else {
