@@ -229,9 +229,13 @@ def run_ours(a):
 
     # ---- end to end through EM() with host buffers ----
     psi0 = random_messages(K, a.q, seed=55 + rank)
+    # the call's host inputs live in pinned memory (links exactly as Julia would hand them over: column-major)
+    links_pin = torch.from_numpy(np.asfortranarray(links)).pin_memory()
+    psi0_pin = torch.from_numpy(psi0).pin_memory()
+    links_h, psi0_h = links_pin.numpy(), psi0_pin.numpy()
     barrier()
     t0 = time.perf_counter()
-    out, eng2, res2 = EM(n, a.q, links, n, (gr0, C0), bool(a.dc), a.steps, True, 0.3, PSIcav0=psi0,
+    out, eng2, res2 = EM(n, a.q, links_h, n, (gr0, C0), bool(a.dc), a.steps, True, 0.3, PSIcav0=psi0_h,
                          BPconvthreshold=0.0, device=local, return_engine=True)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0

@@ -87,15 +87,33 @@ int read_state(gbx_sbm* h) {
   return GBX_OK;
 }
 
+// freeenergy(): sum_i log Z_i, then two passes over the undirected edges (sums, then squared deviations).
+int free_energy_steps(gbx_sbm* h) {
+  const SbmOps* op = h->ops;
+  GBX_TRY(op->vertex_pass(h, MODE_LOGZ));
+  GBX_TRY(op->local_totals(h, MODE_LOGZ));
+  GBX_TRY(op->apply_totals(h, MODE_LOGZ));
+  for (int pass = 0; pass < 2; ++pass) {
+    GBX_TRY(op->fe_local(h, pass));
+    GBX_TRY(op->fe_apply(h, pass));
+  }
+  GBX_TRY(op->fe_final(h));
+  return GBX_OK;
+}
+
 // One EM iteration, sbm.jl:343-347, with a synchronous sweep in place of BP().
 int em_iteration(gbx_sbm* h) {
   const SbmOps* op = h->ops;
-  GBX_TRY(op->prepare(h, 0, 0));              // gr clamp, h = update_h()            sbm.jl:102
-  GBX_TRY(op->vertex_pass(h, MODE_SWEEP));    // messages, marginals, residual       sbm.jl:103-124
+  GBX_TRY(op->prepare(h, 0, 0));              // gr clamp, h = update_h()                        sbm.jl:102
+  GBX_TRY(op->vertex_pass(h, MODE_SWEEP));    // messages, marginals, residual, M-step statistics sbm.jl:103-136
   h->cur ^= 1;
-  GBX_TRY(op->reduce_vertex(h, MODE_SWEEP));
-  GBX_TRY(op->mstep(h));                      // Crs = update_Crs()                  sbm.jl:344
-  if (h->opt.degreecorrection) GBX_TRY(op->theta(h));  // theta = update_theta()     sbm.jl:345-347
+  GBX_TRY(op->local_totals(h, MODE_SWEEP));
+  GBX_TRY(op->apply_totals(h, MODE_SWEEP));   // BPconv, gr, Crs = update_Crs()                  sbm.jl:120-123, 137-147
+  if (h->opt.degreecorrection) {              // theta = update_theta()                          sbm.jl:345-347
+    GBX_TRY(op->theta_local(h));
+    GBX_TRY(op->theta_apply(h));
+    GBX_TRY(op->escale(h));
+  }
   h->itr++;
   return GBX_OK;
 }
@@ -152,6 +170,9 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
   h->q = q;
   h->n = n;
   h->K = K;
+  h->n_global = n;
+  h->K_global = K;
+  h->n_und = K / 2;
   h->ops = ops;
   std::vector<int> rowptr;
   {
@@ -228,7 +249,17 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
     GBX_TRY(dev_alloc(h, &h->msg[0], (size_t)K * q));
     GBX_TRY(dev_alloc(h, &h->msg[1], (size_t)K * q));
     GBX_TRY(dev_alloc(h, &h->PSI, (size_t)n * q));
-    GBX_TRY(dev_alloc(h, &h->theta, (size_t)n));
+    GBX_TRY(dev_alloc(h, &h->theta, (size_t)h->n_global));
+    GBX_TRY(dev_alloc(h, &h->totals, (size_t)TOT_MAX));
+    GBX_TRY(dev_alloc(h, &h->maxd_dev, 1));
+    GBX_TRY(dev_alloc(h, &h->deg_global, (size_t)h->n_global));
+    {
+      std::vector<double> dg((size_t)h->n_global);
+      for (int64_t v = 0; v < h->n_global; ++v) dg[(size_t)v] = (double)(rowptr[(size_t)v + 1] - rowptr[(size_t)v]);
+      GBX_CUDA_TRY(cudaMemcpy(h->deg_global, dg.data(), dg.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    h->msgp[0][0] = h->msg[0];
+    h->msgp[1][0] = h->msg[1];
     GBX_TRY(dev_alloc(h, &h->pidx, (size_t)n));
     GBX_TRY(dev_alloc(h, &h->prior_tab, (size_t)(1 + (TILE_E + 1) * q) * (q + 3)));
     GBX_CUDA_TRY(cudaMemset(h->pidx, 0, (size_t)n * sizeof(int)));
@@ -285,7 +316,10 @@ int gbx_sbm_destroy(gbx_sbm* h) {
   cudaFree(h->msg[0]);
   cudaFree(h->msg[1]);
   cudaFree(h->PSI);
-  cudaFree(h->theta);
+  if (h->theta_owned) cudaFree(h->theta);
+  if (h->totals_owned) cudaFree(h->totals);
+  cudaFree(h->maxd_dev);
+  cudaFree(h->deg_global);
   cudaFree(h->pidx);
   cudaFree(h->prior_tab);
   cudaFree(h->st);
@@ -347,8 +381,8 @@ int gbx_sbm_init(gbx_sbm* h, const double* gr_init, const double* Crs_init, cons
     GBX_TRY(h->ops->random_messages(h, seed));
   }
   {
-    std::vector<double> ones((size_t)std::max<int64_t>(h->n, h->K), 1.0);  // theta = ones(Ntot,1), sbm.jl:277
-    GBX_CUDA_TRY(cudaMemcpyAsync(h->theta, ones.data(), (size_t)h->n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    std::vector<double> ones((size_t)std::max<int64_t>(h->n_global, h->K), 1.0);  // theta = ones(Ntot,1), sbm.jl:277
+    GBX_CUDA_TRY(cudaMemcpyAsync(h->theta, ones.data(), (size_t)h->n_global * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     GBX_CUDA_TRY(cudaMemcpyAsync(h->escale, ones.data(), (size_t)h->K * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     GBX_CUDA_TRY(cudaStreamSynchronize(h->stream));
   }
@@ -356,7 +390,8 @@ int gbx_sbm_init(gbx_sbm* h, const double* gr_init, const double* Crs_init, cons
     // PSI = updatePSI() with h = 0, then gr = update_gr(PSI): sbm.jl:340-341
     GBX_TRY(h->ops->prepare(h, 1, 0));
     GBX_TRY(h->ops->vertex_pass(h, MODE_MARGINAL));
-    GBX_TRY(h->ops->reduce_vertex(h, MODE_MARGINAL));
+    GBX_TRY(h->ops->local_totals(h, MODE_MARGINAL));
+    GBX_TRY(h->ops->apply_totals(h, MODE_MARGINAL));
   }
   GBX_CUDA_TRY(cudaStreamSynchronize(h->stream));
   h->initialised = true;
@@ -384,7 +419,6 @@ int gbx_sbm_bp_sweeps(gbx_sbm* h, int n_sweeps) {
     GBX_TRY(h->ops->vertex_pass(h, MODE_SWEEP));
     h->cur ^= 1;
   }
-  GBX_TRY(h->ops->reduce_vertex(h, MODE_SWEEP));
   return GBX_OK;
 }
 
@@ -396,7 +430,7 @@ int gbx_sbm_finalize(gbx_sbm* h, gbx_sbm_result* res) {
   res->fail = h->fail;
   if (!h->fail) {
     GBX_TRY(h->ops->prepare(h, 0, 1));  // h = update_h(); gr = update_gr(PSI)   sbm.jl:364-365
-    GBX_TRY(h->ops->free_energy(h));    // freeenergy()                          sbm.jl:366
+    GBX_TRY(free_energy_steps(h));      // freeenergy()                          sbm.jl:366
   }
   GBX_TRY(read_state(h));
   const SbmState* s = h->h_state;
@@ -561,7 +595,8 @@ int gbx_mod_init(gbx_mod* h, const double* gr, const double* psicav, uint64_t se
   // h = zeros(1,B); PSI = updatePSI(): mod.jl:204-206
   GBX_TRY(h->ops->prepare(h, 1, 0));
   GBX_TRY(h->ops->vertex_pass(h, MODE_MARGINAL));
-  GBX_TRY(h->ops->reduce_vertex(h, MODE_MARGINAL));
+  GBX_TRY(h->ops->local_totals(h, MODE_MARGINAL));
+  GBX_TRY(h->ops->apply_totals(h, MODE_MARGINAL));
   GBX_CUDA_TRY(cudaStreamSynchronize(h->stream));
   h->initialised = true;
   return GBX_OK;
@@ -569,11 +604,11 @@ int gbx_mod_init(gbx_mod* h, const double* gr, const double* psicav, uint64_t se
 
 static int mod_iteration(gbx_sbm* h) {
   const SbmOps* op = h->ops;
-  GBX_TRY(op->prepare(h, 0, 0));              // h = update_h()                       mod.jl:56
-  GBX_TRY(op->vertex_pass(h, MODE_SWEEP));    // messages, marginals, residual        mod.jl:57-73
+  GBX_TRY(op->prepare(h, 0, 0));              // h = update_h()                                    mod.jl:56
+  GBX_TRY(op->vertex_pass(h, MODE_SWEEP));    // messages, marginals, residual, omega statistic     mod.jl:57-88
   h->cur ^= 1;
-  GBX_TRY(op->reduce_vertex(h, MODE_SWEEP));  // conv; gr = update_gr(PSI)            mod.jl:221-223
-  if (h->mopt.learning) GBX_TRY(op->mstep(h));  // omegas, alpha, beta                mod.jl:224-229
+  GBX_TRY(op->local_totals(h, MODE_SWEEP));
+  GBX_TRY(op->apply_totals(h, MODE_SWEEP));   // conv; gr = update_gr(PSI); omegas, alpha, beta     mod.jl:221-229
   h->itr++;
   return GBX_OK;
 }
@@ -596,7 +631,7 @@ int gbx_mod_finalize(gbx_mod* h, gbx_mod_result* res) {
   GBX_TRY(set_device(h));
   memset(res, 0, sizeof *res);
   GBX_TRY(h->ops->prepare(h, 0, 0));   // h = update_h()   mod.jl:240
-  GBX_TRY(h->ops->free_energy(h));     // freeenergy()     mod.jl:241
+  GBX_TRY(free_energy_steps(h));       // freeenergy()     mod.jl:241
   GBX_TRY(read_state(h));
   const SbmState* s = h->h_state;
   res->excm = h->excm;

@@ -39,7 +39,11 @@ struct SbmState {
   int status;  // bit 0: non-finite / non-positive value met in a kernel
 };
 
-constexpr int PSTRIDE = 4 * MAXQ + 4;  // per-CTA partial row of the vertex kernels
+constexpr int PSTRIDE = 4 * MAXQ + 4;
+constexpr int MAXPEER = 8;                       // ranks of one partitioned run (one NVLink domain)
+constexpr int REV_SHIFT = 28;                    // rev[e] = owner << 28 | slot in the owner's buffer
+constexpr int REV_MASK = (1 << REV_SHIFT) - 1;
+constexpr int TOT_MAX = 4 + 4 * MAXQ + MAXQ * MAXQ;  // doubles in a totals vector  // per-CTA partial row of the vertex kernels
 enum { MODE_SWEEP = 0, MODE_MARGINAL = 1, MODE_LOGZ = 2 };
 
 constexpr int tile_vertices(int q) { return (q <= 8) ? TILE_V / 2 : TILE_V / 4; }
@@ -50,7 +54,11 @@ struct SbmOps;
 
 struct gbx_sbm {
   int device = 0, q = 0;
-  int64_t n = 0, K = 0;
+  int64_t n = 0, K = 0;           // vertices / directed-edge slots owned by this handle (all of them when world == 1)
+  int64_t n_global = 0, K_global = 0;
+  int rank = 0, world = 1;
+  int64_t vbeg = 0, sbeg = 0;     // first global vertex / first global slot of this rank
+  int64_t vbeg_all[gbx::MAXPEER + 1] = {0}, sbeg_all[gbx::MAXPEER + 1] = {0};
   cudaStream_t stream = nullptr;
   gbx_sbm_options opt{};
   int model = 0;                  // 0: sbm.jl, 1: mod.jl (same handle type behind gbx_mod*)
@@ -69,8 +77,16 @@ struct gbx_sbm {
   double* escale = nullptr;       // per edge slot theta_row * theta_col (all ones until update_theta runs)
   int2* und = nullptr;            // every undirected edge once: (slot e, slot rev[e]) with rev[e] < e
   int ntiles = 0, nhubs = 0, max_degree = 1;
+  int64_t n_und = 0;              // entries of `und` (undirected edges whose larger slot is on this rank)
+  double* deg_global = nullptr;   // degree of every vertex, by global id
   // state (device)
-  double *msg[2] = {nullptr, nullptr}, *PSI = nullptr, *theta = nullptr;
+  double *msg[2] = {nullptr, nullptr}, *PSI = nullptr;
+  double* msgp[2][gbx::MAXPEER] = {};   // both message buffers of every rank (peer-mapped; [b][rank] == msg[b])
+  double* theta = nullptr;              // indexed by GLOBAL vertex id (all ranks' values after the all-gather)
+  bool theta_owned = true;              // false: the caller provided the buffer (partitioned runs)
+  double* totals = nullptr;             // per-pass totals vector (device); caller-provided in partitioned runs
+  bool totals_owned = true;
+  double* maxd_dev = nullptr;
   int* pidx = nullptr;            // per vertex: row of the prior table (1 + degree * q + MAP block; 0: theta = 1)
   double* prior_tab = nullptr;    // prior factors per (degree, block), rebuilt every EM iteration
   bool theta_valid = false;       // update_theta has run since init
@@ -88,12 +104,16 @@ namespace gbx {
 // Launchers of one compiled q.  Each returns GBX_OK or an error code and bumps h->launches.
 struct SbmOps {
   int q;
-  int (*vertex_pass)(gbx_sbm* h, int mode);
-  int (*reduce_vertex)(gbx_sbm* h, int mode);
+  int (*vertex_pass)(gbx_sbm* h, int mode);      // sweep / marginals / log Z_i over this rank's vertices
+  int (*local_totals)(gbx_sbm* h, int mode);     // CTA partial rows -> h->totals (this rank)
+  int (*apply_totals)(gbx_sbm* h, int mode);     // (all-reduced) totals -> residual, gr, Crs / omegas, ...
   int (*prepare)(gbx_sbm* h, int zero_h, int gr_from_sum);
-  int (*mstep)(gbx_sbm* h);
-  int (*theta)(gbx_sbm* h);
-  int (*free_energy)(gbx_sbm* h);
+  int (*theta_local)(gbx_sbm* h);                // update_theta on this rank's vertices; S_theta partial -> totals
+  int (*theta_apply)(gbx_sbm* h);                // totals -> S_theta
+  int (*escale)(gbx_sbm* h);                     // theta_row * theta_col per slot (needs every rank's theta)
+  int (*fe_local)(gbx_sbm* h, int pass);         // per-edge free-energy terms -> totals
+  int (*fe_apply)(gbx_sbm* h, int pass);
+  int (*fe_final)(gbx_sbm* h);
   int (*permute)(gbx_sbm* h, const double* src, double* dst, int to_slots);
   int (*random_messages)(gbx_sbm* h, uint64_t seed);
   int (*assignment)(gbx_sbm* h, int* dev_block);

@@ -42,6 +42,10 @@ constexpr double EXP_M500 = 7.124576406741286e-218;  // e^-500, sbm.jl:33-35
 
 __constant__ SbmParams c_P;
 
+// rev[e] packs (owner rank, slot inside the owner's buffer); one rank: owner 0.
+__device__ __forceinline__ int rev_owner(int rv) { return (int)((unsigned)rv >> REV_SHIFT); }
+__device__ __forceinline__ int rev_slot(int rv) { return rv & REV_MASK; }
+
 struct VertexArgs {
   const int* rowptr;
   const int* col;
@@ -51,10 +55,12 @@ struct VertexArgs {
   int ntiles;
   const int* hubs;    // vertex ids with degree > TILE_E
   const double* theta;
+  long long vbeg;             // global id of this rank's first vertex (theta, col and erow use global ids)
   const int* pidx;            // per vertex: row of the prior table, 1 + degree * Q + MAP block (0: theta = 1)
   const double* prior_tab;    // [1 + (TILE_E + 1) * Q][QT]: prior factors per (degree, block); row 0: theta = 1
-  const double* cur;
-  double* nxt;
+  const double* cur;            // this rank's current message buffer (the tile loop streams it)
+  const double* curp[MAXPEER];  // ... and every rank's (peer-mapped over NVLink): old outgoing messages for damping
+  double* nxtp[MAXPEER];        // every rank's next buffer: a new message is stored straight into its owner's rows
   double* PSI;
   double* partials;   // [(grid + nhubs)][PSTRIDE]
   double* mpart;      // [(grid + nhubs)][Q * Q]: M-step statistics (sbm.jl) per CTA
@@ -171,14 +177,15 @@ __device__ __forceinline__ void emit_message(const VertexArgs& a, const double* 
   const double inv = fast_rcp(S);
 #pragma unroll
   for (int t = 0; t < Q; ++t) w[t] *= inv;
+  const int owner = rev_owner(rv), slot = rev_slot(rv);
   if (a.damping != 1.0) {
     double old[Q];
-    load_vec<Q>(a.cur, rv, old);
+    load_vec<Q>(a.curp[owner], slot, old);
     const double al = a.damping, be = 1.0 - a.damping;
 #pragma unroll
     for (int t = 0; t < Q; ++t) w[t] = be * old[t] + al * w[t];
   }
-  store_vec<Q>(a.nxt, rv, w);
+  store_vec<Q>(a.nxtp[owner], slot, w);
 }
 
 // ---- M-step statistics fused into the sweep ------------------------------------------------------------
@@ -784,7 +791,7 @@ __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base
   const int gv = a.hubs[blockIdx.x];
   const int e0 = a.rowptr[gv], e1 = a.rowptr[gv + 1];
   // theta of the prior: sbm.jl degree correction factor, or the degree itself in mod.jl:48
-  const double th = !a.dc ? 1.0 : (MODEL == MODEL_MOD ? (double)(e1 - e0) : a.theta[gv]);
+  const double th = !a.dc ? 1.0 : (MODEL == MODEL_MOD ? (double)(e1 - e0) : a.theta[a.vbeg + gv]);
   if (tid < Q) {
     s_dr[tid] = 0ull;
     s_nr[tid] = 0;
@@ -938,17 +945,42 @@ __global__ void __launch_bounds__(256) sbm_escale_kernel(const int* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fixed-order reduction of the vertex partials, then the scalar bookkeeping of one sweep.
-__global__ void sbm_reduce_vertex(SbmState* st, const double* partials, int nrows, int mode, int prior, int dc,
-                                  double N) {
-  __shared__ double tot[PSTRIDE];
-  const int tid = threadIdx.x;
-  for (int c = tid >> 5; c < 3 * Q + 3; c += blockDim.x >> 5) {
-    const double v = (c == 2 + 3 * Q) ? warp_column_reduce<true>(partials, nrows, PSTRIDE, c)
-                                      : warp_column_reduce<false>(partials, nrows, PSTRIDE, c);
-    if ((tid & 31) == 0) tot[c] = v;
+// Totals of one vertex pass.  Every CTA left a partial row; `sbm_local_totals` reduces them in a fixed order
+// into one vector per rank, the ranks of a partitioned run all-reduce that vector (NCCL, host side), and
+// `sbm_apply_totals` does the scalar bookkeeping of the sweep from the global sums.
+//   [0] residual  [1] sum log Z_i  [2,2+Q) sum PSI  [2+Q,2+2Q) degree sum per MAP block  [2+2Q,2+3Q) block sizes
+//   [2+3Q,2+4Q) sum degree*PSI (mod.jl)  [2+4Q] omega_in statistic (mod.jl)  [3+4Q] unused  [4+4Q, +Q*Q) G (M-step)
+constexpr int TOT_G = 4 + 4 * Q;
+constexpr int TOT_LEN = TOT_G + Q * Q;
+
+__global__ void sbm_local_totals(const double* __restrict__ pv, int nrows, const double* __restrict__ pm, int with_g,
+                                 double* __restrict__ totals, double* __restrict__ maxd_out) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int ncol = 4 * Q + 4 + (with_g ? Q * Q : 0);
+  for (int c = tid >> 5; c < ncol; c += blockDim.x >> 5) {
+    double v;
+    if (c < 4 * Q + 4) {
+      // partial-row columns: 0,1 | 2..2+3Q | maxd at 2+3Q | dpsi at 3+3Q.. | mod stat at 3+4Q
+      if (c < 2 + 3 * Q) v = warp_column_reduce<false>(pv, nrows, PSTRIDE, c);
+      else if (c < 2 + 4 * Q) v = (MODEL == MODEL_MOD) ? warp_column_reduce<false>(pv, nrows, PSTRIDE, c + 1) : 0.0;
+      else if (c == 2 + 4 * Q) v = (MODEL == MODEL_MOD) ? warp_column_reduce<false>(pv, nrows, PSTRIDE, 3 + 4 * Q) : 0.0;
+      else v = 0.0;
+    } else {
+      v = warp_column_reduce<false>(pm, nrows, Q * Q, c - (4 * Q + 4));
+    }
+    if (lane == 0) totals[c] = v;
   }
-  __syncthreads();
+  if ((tid >> 5) == 0) {  // the largest per-vertex change is a max, kept out of the summed vector
+    const double m = warp_column_reduce<true>(pv, nrows, PSTRIDE, 2 + 3 * Q);
+    if (lane == 0) *maxd_out = m;
+  }
+}
+
+#if GBX_MODEL == 0
+// sbm.jl:120-123 (residual, gr), 47-58 (block degree means), 137-147 (update_Crs) from the global totals.
+__global__ void sbm_apply_totals(SbmState* st, const double* __restrict__ tot, const double* maxd, int mode, int prior,
+                                 int dc, double N, double lr, double maxCrs) {
+  const int tid = threadIdx.x;
   if (mode == MODE_LOGZ) {
     if (tid == 0) {
       st->sumlogZi = tot[1];
@@ -956,46 +988,41 @@ __global__ void sbm_reduce_vertex(SbmState* st, const double* partials, int nrow
     }
     return;
   }
+  __shared__ double g[Q];
   if (tid < Q) {
     const double snew = tot[2 + tid];
+    double gnew = st->gr[tid];
     if (mode == MODE_MARGINAL) {
-      st->gr[tid] = snew / N;                                  // gr = update_gr(PSI), sbm.jl:341
-      st->Stheta[tid] = snew;                                  // theta = 1 (sbm.jl:277)
+      gnew = snew / N;                                          // gr = update_gr(PSI), sbm.jl:341
+      st->Stheta[tid] = snew;                                   // theta = 1 (sbm.jl:277)
     } else {
-      if (prior) st->gr[tid] += (snew - st->sumPSI[tid]) / N;  // sbm.jl:120-122 summed over the sweep
+      if (prior) gnew += (snew - st->sumPSI[tid]) / N;          // sbm.jl:120-122 summed over the sweep
       if (!dc) st->Stheta[tid] = snew;
     }
+    st->gr[tid] = gnew;
+    g[tid] = gnew;
     st->sumPSI[tid] = snew;
     st->drmean[tid] = tot[2 + Q + tid] / tot[2 + 2 * Q + tid];  // sbm.jl:54-58 (NaN for an empty block, unused)
   }
   if (tid == 0 && mode == MODE_SWEEP) {
     st->conv = tot[0] / N;  // sbm.jl:123
-    st->maxd = tot[2 + 3 * Q];
+    st->maxd = *maxd;
     if (!(tot[0] == tot[0]) || !(tot[0] < INFINITY)) st->status |= 1;  // NaN/Inf reached the marginals
   }
-
-}
-
-// ---------------------------------------------------------------------------------------------
-// update_Crs(), sbm.jl:137-147, from the statistics the sweep accumulated (G summed over all directed links).
-__global__ void sbm_reduce_mstep(SbmState* st, const double* partials, int nrows, double lr, double maxCrs, double N) {
-  __shared__ double G[Q * Q];
-  const int tid = threadIdx.x;
-  for (int c = tid >> 5; c < Q * Q; c += blockDim.x >> 5) {
-    const double v = warp_column_reduce(partials, nrows, Q * Q, c);
-    if ((tid & 31) == 0) G[c] = v;
-  }
   __syncthreads();
-  if (tid < Q * Q) {
+  if (mode == MODE_SWEEP && tid < Q * Q) {
+    // update_Crs(), sbm.jl:137-147, from the statistics the sweep accumulated (G over all directed links)
     const int s = tid / Q, t = tid - s * Q;
+    const double* G = tot + TOT_G;
     const double Cold = st->C[tid];
-    const double Cn = Cold * 0.5 * (G[s * Q + t] + G[t * Q + s]);  // Crsnew is symmetric (both directions of every link)
-    double c = lr * Cn / (N * st->gr[s] * st->gr[t]) + (1.0 - lr) * Cold;  // sbm.jl:137
-    if (c > maxCrs) c = maxCrs; else if (c < 0.0) c = 0.0;                  // sbm.jl:138-146
+    const double Cn = Cold * 0.5 * (G[s * Q + t] + G[t * Q + s]);  // Crsnew is symmetric (both directions of a link)
+    double c = lr * Cn / (N * g[s] * g[t]) + (1.0 - lr) * Cold;    // sbm.jl:137
+    if (c > maxCrs) c = maxCrs; else if (c < 0.0) c = 0.0;          // sbm.jl:138-146
     if (!(c == c)) st->status |= 1;
     st->C[tid] = c;
   }
 }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // update_theta(), sbm.jl:47-64, and S_theta = sum_i theta_i PSI_i for the next update_h().
@@ -1027,11 +1054,16 @@ __global__ void __launch_bounds__(NT) sbm_theta_kernel(const SbmState* st, const
   block_reduce_store<Q>(acc, red, partials + (size_t)blockIdx.x * Q);
 }
 
-__global__ void sbm_reduce_theta(SbmState* st, const double* partials, int nrows) {
-  for (int c = threadIdx.x >> 5; c < Q; c += blockDim.x >> 5) {
-    const double v = warp_column_reduce(partials, nrows, Q, c);
-    if ((threadIdx.x & 31) == 0) st->Stheta[c] = v;
+// partial rows -> totals[0..ncol) (local), then apply after the ranks' all-reduce
+__global__ void k_local_columns(const double* __restrict__ partials, int nrows, int ncol, double* __restrict__ totals) {
+  for (int c = threadIdx.x >> 5; c < ncol; c += blockDim.x >> 5) {
+    const double v = warp_column_reduce(partials, nrows, ncol, c);
+    if ((threadIdx.x & 31) == 0) totals[c] = v;
   }
+}
+
+__global__ void sbm_apply_theta(SbmState* st, const double* __restrict__ totals) {
+  if (threadIdx.x < Q) st->Stheta[threadIdx.x] = totals[threadIdx.x];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1103,11 +1135,15 @@ __global__ void sbm_prepare(SbmState* st, SbmParams* out, double N, int zero_h, 
 // ---------------------------------------------------------------------------------------------
 // freeenergy(), sbm.jl:162-200: per undirected edge log Z_ij and the three Gibbs/MAP terms.
 // PASS 0 accumulates sums, PASS 1 sums of squared deviations from the means (unbiased var, sbm.jl:208-211).
+struct PeerCur {
+  const double* p[MAXPEER];
+};
+
 template <int PASS>
 __global__ void __launch_bounds__(NT) sbm_fe_kernel(const SbmState* st, const int2* __restrict__ und,
-                                                    const int* __restrict__ col, long long L,
-                                                    const double* __restrict__ psi, const double* __restrict__ theta,
-                                                    int dc, double* partials) {
+                                                    const int* __restrict__ col, const int* __restrict__ erow,
+                                                    long long L, const double* __restrict__ psi, PeerCur peers,
+                                                    const double* __restrict__ theta, int dc, double* partials) {
   __shared__ double red[(NT / 32) * 4];
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   double mean[4] = {0.0, 0.0, 0.0, 0.0};
@@ -1118,10 +1154,10 @@ __global__ void __launch_bounds__(NT) sbm_fe_kernel(const SbmState* st, const in
       const int2 er = und[i];
       const int e = er.x, r = er.y;
       double a[Q], b[Q];
-      load_vec<Q>(psi, e, b);  // j -> i   (i = row of e, j = col[e])
-      load_vec<Q>(psi, r, a);  // i -> j
+      load_vec<Q>(psi, e, b);                                   // j -> i   (i = row of e, j = col[e])
+      load_vec<Q>(peers.p[rev_owner(r)], rev_slot(r), a);       // i -> j   (in the row of j, possibly on a peer)
       double lc = -c_P.logN;
-      if (dc) lc += log(theta[col[r]]) + log(theta[col[e]]);
+      if (dc) lc += log(theta[erow[e]]) + log(theta[col[e]]);
       double Z0 = 0.0, W = 0.0, L1 = 0.0, G1 = 0.0;
       int sa = 0, sb = 0;
       double ma = -1.0, mb = -1.0;
@@ -1154,17 +1190,14 @@ __global__ void __launch_bounds__(NT) sbm_fe_kernel(const SbmState* st, const in
   block_reduce_store<4>(acc, red, partials + (size_t)blockIdx.x * 4);
 }
 
-__global__ void sbm_reduce_fe(SbmState* st, const double* partials, int nrows, int pass, double L) {
-  const int c = threadIdx.x >> 5;
+__global__ void sbm_apply_fe(SbmState* st, const double* __restrict__ totals, int pass, double L) {
+  const int c = threadIdx.x;
   if (c < 4) {
-    const double s = warp_column_reduce(partials, nrows, 4, c);
-    if ((threadIdx.x & 31) == 0) {
-      if (pass == 0) {
-        st->cvsum[c] = s;
-        st->cvmean[c] = s / L;
-      } else {
-        st->cvss[c] = s;
-      }
+    if (pass == 0) {
+      st->cvsum[c] = totals[c];
+      st->cvmean[c] = totals[c] / L;
+    } else {
+      st->cvss[c] = totals[c];
     }
   }
 }
@@ -1267,10 +1300,14 @@ VertexArgs vertex_args(gbx_sbm* h) {
   a.ntiles = h->ntiles;
   a.hubs = h->hubs;
   a.theta = h->theta;
+  a.vbeg = h->vbeg;
   a.pidx = h->pidx;
   a.prior_tab = h->prior_tab;
   a.cur = h->msg[h->cur];
-  a.nxt = h->msg[h->cur ^ 1];
+  for (int r = 0; r < MAXPEER; ++r) {
+    a.curp[r] = h->msgp[h->cur][r];
+    a.nxtp[r] = h->msgp[h->cur ^ 1][r];
+  }
   a.PSI = h->PSI;
   a.partials = h->part_vertex;
   a.mpart = h->part_mstep;
@@ -1301,11 +1338,22 @@ int op_vertex_pass(gbx_sbm* h, int mode) {
   return launch_vertex_pass_t<MODE_LOGZ>(h);
 }
 
-int op_reduce_vertex(gbx_sbm* h, int mode) {
-  const int nrows = (h->ntiles > 0 ? h->grid_vertex : 0) + h->nhubs;
-  const double* base = h->part_vertex + (h->ntiles > 0 ? 0 : (size_t)h->grid_vertex * PSTRIDE);
-  sbm_reduce_vertex<<<1, 256, 0, h->stream>>>(h->st, base, nrows, mode, h->opt.priorlearning,
-                                             h->opt.degreecorrection, (double)h->n);
+int vertex_rows(const gbx_sbm* h) { return (h->ntiles > 0 ? h->grid_vertex : 0) + h->nhubs; }
+
+int op_local_totals(gbx_sbm* h, int mode) {
+  const size_t skip = h->ntiles > 0 ? 0 : (size_t)h->grid_vertex;
+  sbm_local_totals<<<1, 512, 0, h->stream>>>(h->part_vertex + skip * PSTRIDE, vertex_rows(h), h->part_mstep + skip * Q * Q,
+                                             (MODEL == MODEL_SBM && mode == MODE_SWEEP) ? 1 : 0, h->totals, h->maxd_dev);
+  h->launches++;
+  GBX_CUDA_TRY(cudaGetLastError());
+  return GBX_OK;
+}
+
+#if GBX_MODEL == 0
+int op_apply_totals(gbx_sbm* h, int mode) {
+  const double maxCrs = h->opt.maxCrs > 0 ? h->opt.maxCrs : (double)h->n_global;
+  sbm_apply_totals<<<1, 256, 0, h->stream>>>(h->st, h->totals, h->maxd_dev, mode, h->opt.priorlearning,
+                                             h->opt.degreecorrection, (double)h->n_global, h->opt.learningrate, maxCrs);
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
@@ -1313,8 +1361,8 @@ int op_reduce_vertex(gbx_sbm* h, int mode) {
 
 int op_prepare(gbx_sbm* h, int zero_h, int gr_from_sum) {
   const int dc_tab = h->opt.degreecorrection && h->theta_valid;
-  sbm_prepare<<<1, 64, 0, h->stream>>>(h->st, h->params, (double)h->n, zero_h, gr_from_sum, dc_tab,
-                                  (double)h->max_degree);
+  sbm_prepare<<<1, 64, 0, h->stream>>>(h->st, h->params, (double)h->n_global, zero_h, gr_from_sum, dc_tab,
+                                       (double)h->max_degree);
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
   GBX_CUDA_TRY(cudaMemcpyToSymbolAsync(c_P, h->params, sizeof(SbmParams), 0, cudaMemcpyDeviceToDevice, h->stream));
@@ -1327,48 +1375,65 @@ int op_prepare(gbx_sbm* h, int zero_h, int gr_from_sum) {
   return GBX_OK;
 }
 
-int op_mstep(gbx_sbm* h) {
-  const double maxCrs = h->opt.maxCrs > 0 ? h->opt.maxCrs : (double)h->n;
-  const int nrows = (h->ntiles > 0 ? h->grid_vertex : 0) + h->nhubs;
-  const double* base = h->part_mstep + (h->ntiles > 0 ? 0 : (size_t)h->grid_vertex * Q * Q);
-  sbm_reduce_mstep<<<1, 256, 0, h->stream>>>(h->st, base, nrows, h->opt.learningrate, maxCrs, (double)h->n);
-  h->launches += 1;
-  GBX_CUDA_TRY(cudaGetLastError());
-  return GBX_OK;
-}
-
-int op_theta(gbx_sbm* h) {
-  sbm_theta_kernel<<<h->grid_theta, NT, 0, h->stream>>>(h->st, h->rowptr, (int)h->n, h->PSI, h->theta, h->pidx,
+int op_theta_local(gbx_sbm* h) {
+  sbm_theta_kernel<<<h->grid_theta, NT, 0, h->stream>>>(h->st, h->rowptr, (int)h->n, h->PSI, h->theta + h->vbeg, h->pidx,
                                                         h->part_theta);
   h->theta_valid = true;
-  sbm_reduce_theta<<<1, 256, 0, h->stream>>>(h->st, h->part_theta, h->grid_theta);
+  k_local_columns<<<1, 256, 0, h->stream>>>(h->part_theta, h->grid_theta, Q, h->totals);
   h->launches += 2;
-  if (h->ntiles > 0) {
+  GBX_CUDA_TRY(cudaGetLastError());
+  return GBX_OK;
+}
+
+int op_theta_apply(gbx_sbm* h) {
+  sbm_apply_theta<<<1, 32, 0, h->stream>>>(h->st, h->totals);
+  h->launches++;
+  GBX_CUDA_TRY(cudaGetLastError());
+  return GBX_OK;
+}
+
+int op_escale(gbx_sbm* h) {
+  if (h->K > 0) {
     sbm_escale_kernel<<<grid_for(h, h->K), 256, 0, h->stream>>>(h->erow, h->col, (long long)h->K, h->theta, h->escale);
     h->launches++;
+    GBX_CUDA_TRY(cudaGetLastError());
   }
+  return GBX_OK;
+}
+
+PeerCur peer_cur(const gbx_sbm* h) {
+  PeerCur p;
+  for (int r = 0; r < MAXPEER; ++r) p.p[r] = h->msgp[h->cur][r];
+  return p;
+}
+
+int op_fe_local(gbx_sbm* h, int pass) {
+  if (pass == 0)
+    sbm_fe_kernel<0><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->und, h->col, h->erow, (long long)h->n_und, h->msg[h->cur],
+                                                       peer_cur(h), h->theta, h->opt.degreecorrection, h->part_fe);
+  else
+    sbm_fe_kernel<1><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->und, h->col, h->erow, (long long)h->n_und, h->msg[h->cur],
+                                                       peer_cur(h), h->theta, h->opt.degreecorrection, h->part_fe);
+  k_local_columns<<<1, 128, 0, h->stream>>>(h->part_fe, h->grid_fe, 4, h->totals);
+  h->launches += 2;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
 }
 
-int op_free_energy(gbx_sbm* h) {
-  const double L = 0.5 * (double)h->K;
-  int rc = op_vertex_pass(h, MODE_LOGZ);
-  if (rc != GBX_OK) return rc;
-  rc = op_reduce_vertex(h, MODE_LOGZ);
-  if (rc != GBX_OK) return rc;
-  sbm_fe_kernel<0><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->und, h->col, (long long)(h->K / 2), h->msg[h->cur], h->theta,
-                                                     h->opt.degreecorrection, h->part_fe);
-  sbm_reduce_fe<<<1, 128, 0, h->stream>>>(h->st, h->part_fe, h->grid_fe, 0, L);
-  sbm_fe_kernel<1><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->und, h->col, (long long)(h->K / 2), h->msg[h->cur], h->theta,
-                                                     h->opt.degreecorrection, h->part_fe);
-  sbm_reduce_fe<<<1, 128, 0, h->stream>>>(h->st, h->part_fe, h->grid_fe, 1, L);
-  sbm_finalize<<<1, 32, 0, h->stream>>>(h->st, (double)h->n, L);
-  h->launches += 5;
+int op_fe_apply(gbx_sbm* h, int pass) {
+  sbm_apply_fe<<<1, 32, 0, h->stream>>>(h->st, h->totals, pass, 0.5 * (double)h->K_global);
+  h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
 }
 
+int op_fe_final(gbx_sbm* h) {
+  sbm_finalize<<<1, 32, 0, h->stream>>>(h->st, (double)h->n_global, 0.5 * (double)h->K_global);
+  h->launches++;
+  GBX_CUDA_TRY(cudaGetLastError());
+  return GBX_OK;
+}
+#endif
 
 int op_permute(gbx_sbm* h, const double* src, double* dst, int to_slots) {
   k_permute_rows<<<grid_for(h, h->K), 256, 0, h->stream>>>(src, dst, h->slot_of_link, (long long)h->K, to_slots);
@@ -1417,16 +1482,10 @@ int op_occupancy(int variant, int* vertex_occ, int* mstep_occ) {
 // The sweep reuses sbm_vertex_kernel / sbm_hub_kernel (edge factor 1 + psi (e^beta - 1), prior field
 // alpha beta d_i h); below are the scalar bookkeeping, the omega M-step and the free energy of that model.
 // =============================================================================================
-__global__ void mod_reduce_vertex(SbmState* st, const double* partials, int nrows, int mode, int prior, int dc,
-                                  double N) {
-  __shared__ double tot[PSTRIDE];
+// mod.jl:72 (residual), 22-24 (h numerator), 221-223 (gr), 77-112 and 224-229 (omegas, alpha, beta) from the totals.
+__global__ void mod_apply_totals(SbmState* st, const double* __restrict__ tot, const double* maxd, int mode, int prior,
+                                 int dc, int learning, double N, double K, double lr, double maxomega) {
   const int tid = threadIdx.x;
-  for (int c = tid >> 5; c < 4 * Q + 4; c += blockDim.x >> 5) {
-    const double v = (c == 2 + 3 * Q) ? warp_column_reduce<true>(partials, nrows, PSTRIDE, c)
-                                      : warp_column_reduce<false>(partials, nrows, PSTRIDE, c);
-    if ((tid & 31) == 0) tot[c] = v;
-  }
-  __syncthreads();
   if (mode == MODE_LOGZ) {
     if (tid == 0) {
       st->sumlogZi = tot[1];
@@ -1434,17 +1493,36 @@ __global__ void mod_reduce_vertex(SbmState* st, const double* partials, int nrow
     }
     return;
   }
-  if (tid == 0 && mode == MODE_SWEEP) st->omegainnew2 = tot[3 + 4 * Q];
+  __shared__ double hs[Q];
   if (tid < Q) {
     const double snew = tot[2 + tid];
     st->sumPSI[tid] = snew;
-    st->Stheta[tid] = dc ? tot[3 + 3 * Q + tid] : snew;            // degrees' * PSI, mod.jl:22-24 (ones without dc)
-    if (mode == MODE_SWEEP && prior) st->gr[tid] = snew / N;        // gr = update_gr(PSI), mod.jl:221-223
+    hs[tid] = dc ? tot[2 + 3 * Q + tid] : snew;                     // degrees' * PSI, mod.jl:22-24 (ones without dc)
+    st->Stheta[tid] = hs[tid];
+    if (mode == MODE_SWEEP && prior) st->gr[tid] = snew / N;         // gr = update_gr(PSI), mod.jl:221-223
   }
+  __syncthreads();
   if (tid == 0 && mode == MODE_SWEEP) {
     st->conv = tot[0] / N;  // mod.jl:72
-    st->maxd = tot[2 + 3 * Q];
+    st->maxd = *maxd;
     if (!(tot[0] == tot[0]) || !(tot[0] < INFINITY)) st->status |= 1;
+    if (learning) {
+      // The statistic sum_e omega_in s_e / ((omega_in - omega_out) s_e + omega_out) (mod.jl:86-87) was accumulated by
+      // the sweep over ALL directed slots (new outgoing message . previous incoming one): twice per undirected edge.
+      const double omegainnew = 0.5 * tot[2 + 4 * Q];
+      double dn = 0.0;
+      for (int t = 0; t < Q; ++t) dn += hs[t] * hs[t];                // norm(update_h())^2 of the new marginals
+      double oin = 2.0 * omegainnew / dn;
+      double oout = 2.0 * (0.5 * K - omegainnew) / ((dc ? K * K : N * N) - dn);
+      if (oin > maxomega) oin = maxomega;                             // mod.jl:97-103
+      else if (oin < 0.0) oin = 0.0;
+      else if (oout < 0.0) oout = 0.0;
+      st->omegain = lr * oin + (1.0 - lr) * st->omegain;              // mod.jl:226-227
+      st->omegaout = lr * oout + (1.0 - lr) * st->omegaout;
+      st->beta = log(st->omegain / st->omegaout);                     // update_alphabeta, mod.jl:108-112
+      st->alpha = (st->omegain - st->omegaout) / st->beta;
+      if (!(st->beta == st->beta) || !(st->alpha == st->alpha)) st->status |= 1;
+    }
   }
 }
 
@@ -1474,32 +1552,12 @@ __global__ void mod_prepare(SbmState* st, SbmParams* out, double N, int zero_h) 
   }
 }
 
-// mod.jl:89-105 and 224-229: new omegas, clamps, learning-rate mix, update_alphabeta
-// The statistic sum_e omega_in s_e / ((omega_in - omega_out) s_e + omega_out) (mod.jl:86-87) is accumulated by the
-// sweep over ALL directed slots (new outgoing message . previous incoming one), i.e. twice per undirected edge.
-__global__ void mod_reduce_mstep(SbmState* st, double lr, double maxomega, double N, double K, int dc) {
-  if (threadIdx.x == 0) {
-    const double omegainnew = 0.5 * st->omegainnew2;
-    double dn = 0.0;
-    for (int t = 0; t < Q; ++t) dn += st->Stheta[t] * st->Stheta[t];  // norm(update_h())^2 of the new marginals
-    double oin = 2.0 * omegainnew / dn;
-    double oout = 2.0 * (0.5 * K - omegainnew) / ((dc ? K * K : N * N) - dn);
-    if (oin > maxomega) oin = maxomega;
-    else if (oin < 0.0) oin = 0.0;
-    else if (oout < 0.0) oout = 0.0;
-    st->omegain = lr * oin + (1.0 - lr) * st->omegain;
-    st->omegaout = lr * oout + (1.0 - lr) * st->omegaout;
-    st->beta = log(st->omegain / st->omegaout);                      // update_alphabeta, mod.jl:108-112
-    st->alpha = (st->omegain - st->omegaout) / st->beta;
-    if (!(st->beta == st->beta) || !(st->alpha == st->alpha)) st->status |= 1;
-  }
-}
-
 // freeenergy(), mod.jl:127-153.  x0 = logZij, x1 = CVBP, x2 = CVGP, x3 = CVGT, x4 = CVMAP per undirected edge.
 template <int PASS>
 __global__ void __launch_bounds__(NT) mod_fe_kernel(const SbmState* st, const int2* __restrict__ und,
-                                                    const int* __restrict__ col, const int* __restrict__ rowptr,
-                                                    long long L, const double* __restrict__ psi, int dc,
+                                                    const int* __restrict__ col, const int* __restrict__ erow,
+                                                    const double* __restrict__ degs, long long L,
+                                                    const double* __restrict__ psi, PeerCur peers, int dc,
                                                     double* partials) {
   __shared__ double red[(NT / 32) * 5];
   double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
@@ -1512,12 +1570,11 @@ __global__ void __launch_bounds__(NT) mod_fe_kernel(const SbmState* st, const in
     const int2 er = und[i];
     double a[Q], b[Q];
     load_vec<Q>(psi, er.x, b);
-    load_vec<Q>(psi, er.y, a);
+    load_vec<Q>(peers.p[rev_owner(er.y)], rev_slot(er.y), a);
     double di = 1.0, dj = 1.0;
-    if (dc) {
-      const int vi = col[er.y], vj = col[er.x];
-      di = (double)(rowptr[vi + 1] - rowptr[vi]);
-      dj = (double)(rowptr[vj + 1] - rowptr[vj]);
+    if (dc) {  // degrees of both endpoints: `degs` is indexed by global vertex id (every rank's, like theta)
+      di = degs[erow[er.x]];
+      dj = degs[col[er.x]];
     }
     double s = 0.0;
     int sa = 0, sb = 0;
@@ -1542,17 +1599,14 @@ __global__ void __launch_bounds__(NT) mod_fe_kernel(const SbmState* st, const in
   block_reduce_store<5>(acc, red, partials + (size_t)blockIdx.x * 5);
 }
 
-__global__ void mod_reduce_fe(SbmState* st, const double* partials, int nrows, int pass, double L) {
-  const int c = threadIdx.x >> 5;
+__global__ void mod_apply_fe(SbmState* st, const double* __restrict__ totals, int pass, double L) {
+  const int c = threadIdx.x;
   if (c < 5) {
-    const double s = warp_column_reduce(partials, nrows, 5, c);
-    if ((threadIdx.x & 31) == 0) {
-      if (pass == 0) {
-        st->cv5sum[c] = s;
-        st->cv5mean[c] = s / L;
-      } else {
-        st->cv5ss[c] = s;
-      }
+    if (pass == 0) {
+      st->cv5sum[c] = totals[c];
+      st->cv5mean[c] = totals[c] / L;
+    } else {
+      st->cv5ss[c] = totals[c];
     }
   }
 }
@@ -1573,17 +1627,17 @@ __global__ void mod_finalize(SbmState* st, double N, double L, double constshift
   }
 }
 
-int mop_reduce_vertex(gbx_sbm* h, int mode) {
-  const int nrows = (h->ntiles > 0 ? h->grid_vertex : 0) + h->nhubs;
-  const double* base = h->part_vertex + (h->ntiles > 0 ? 0 : (size_t)h->grid_vertex * PSTRIDE);
-  mod_reduce_vertex<<<1, 256, 0, h->stream>>>(h->st, base, nrows, mode, h->mopt.priorlearning, h->mopt.dc, (double)h->n);
+int mop_apply_totals(gbx_sbm* h, int mode) {
+  mod_apply_totals<<<1, 64, 0, h->stream>>>(h->st, h->totals, h->maxd_dev, mode, h->mopt.priorlearning, h->mopt.dc,
+                                            h->mopt.learning, (double)h->n_global, (double)h->K_global,
+                                            h->mopt.learningrate, h->mopt.maxomega);
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
 }
 
 int mop_prepare(gbx_sbm* h, int zero_h, int) {
-  mod_prepare<<<1, 32, 0, h->stream>>>(h->st, h->params, (double)h->n, zero_h);
+  mod_prepare<<<1, 32, 0, h->stream>>>(h->st, h->params, (double)h->n_global, zero_h);
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
   GBX_CUDA_TRY(cudaMemcpyToSymbolAsync(c_P, h->params, sizeof(SbmParams), 0, cudaMemcpyDeviceToDevice, h->stream));
@@ -1595,39 +1649,50 @@ int mop_prepare(gbx_sbm* h, int zero_h, int) {
   return GBX_OK;
 }
 
-int mop_mstep(gbx_sbm* h) {
-  mod_reduce_mstep<<<1, 32, 0, h->stream>>>(h->st, h->mopt.learningrate, h->mopt.maxomega, (double)h->n, (double)h->K,
-                                            h->mopt.dc);
-  h->launches += 1;
+int mop_noop(gbx_sbm*) { return GBX_OK; }
+
+PeerCur peer_cur(const gbx_sbm* h) {
+  PeerCur p;
+  for (int r = 0; r < MAXPEER; ++r) p.p[r] = h->msgp[h->cur][r];
+  return p;
+}
+
+int mop_fe_local(gbx_sbm* h, int pass) {
+  if (pass == 0)
+    mod_fe_kernel<0><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->und, h->col, h->erow, h->deg_global, (long long)h->n_und,
+                                                       h->msg[h->cur], peer_cur(h), h->mopt.dc, h->part_fe);
+  else
+    mod_fe_kernel<1><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->und, h->col, h->erow, h->deg_global, (long long)h->n_und,
+                                                       h->msg[h->cur], peer_cur(h), h->mopt.dc, h->part_fe);
+  k_local_columns<<<1, 160, 0, h->stream>>>(h->part_fe, h->grid_fe, 5, h->totals);
+  h->launches += 2;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
 }
 
-int mop_theta(gbx_sbm*) { return GBX_OK; }
-
-int mop_free_energy(gbx_sbm* h) {
-  const double L = 0.5 * (double)h->K;
-  int rc = op_vertex_pass(h, MODE_LOGZ);
-  if (rc != GBX_OK) return rc;
-  rc = mop_reduce_vertex(h, MODE_LOGZ);
-  if (rc != GBX_OK) return rc;
-  mod_fe_kernel<0><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->und, h->col, h->rowptr, (long long)(h->K / 2),
-                                                     h->msg[h->cur], h->mopt.dc, h->part_fe);
-  mod_reduce_fe<<<1, 160, 0, h->stream>>>(h->st, h->part_fe, h->grid_fe, 0, L);
-  mod_fe_kernel<1><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->und, h->col, h->rowptr, (long long)(h->K / 2),
-                                                     h->msg[h->cur], h->mopt.dc, h->part_fe);
-  mod_reduce_fe<<<1, 160, 0, h->stream>>>(h->st, h->part_fe, h->grid_fe, 1, L);
-  mod_finalize<<<1, 32, 0, h->stream>>>(h->st, (double)h->n, L, h->mopt.dc ? h->constshift : 0.0);  // degrees = ones without dc (mod.jl:189-191)
-  h->launches += 5;
+int mop_fe_apply(gbx_sbm* h, int pass) {
+  mod_apply_fe<<<1, 32, 0, h->stream>>>(h->st, h->totals, pass, 0.5 * (double)h->K_global);
+  h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
 }
 
-const SbmOps kOps = {Q,          op_vertex_pass,     mop_reduce_vertex, mop_prepare,  mop_mstep,     mop_theta, mop_free_energy,
-                     op_permute, op_random_messages, op_assignment,     op_occupancy, op_init_model};
+int mop_fe_final(gbx_sbm* h) {
+  // degrees = ones without dc (mod.jl:189-191), hence constshift = 0 then
+  mod_finalize<<<1, 32, 0, h->stream>>>(h->st, (double)h->n_global, 0.5 * (double)h->K_global,
+                                        h->mopt.dc ? h->constshift : 0.0);
+  h->launches++;
+  GBX_CUDA_TRY(cudaGetLastError());
+  return GBX_OK;
+}
+
+const SbmOps kOps = {Q,          op_vertex_pass, op_local_totals, mop_apply_totals,   mop_prepare,   mop_noop,     mop_noop,
+                     mop_noop,   mop_fe_local,   mop_fe_apply,    mop_fe_final,       op_permute,    op_random_messages,
+                     op_assignment, op_occupancy, op_init_model};
 #else
-const SbmOps kOps = {Q,         op_vertex_pass,     op_reduce_vertex, op_prepare,   op_mstep,     op_theta, op_free_energy,
-                     op_permute, op_random_messages, op_assignment,    op_occupancy, op_init_model};
+const SbmOps kOps = {Q,          op_vertex_pass, op_local_totals, op_apply_totals,    op_prepare,    op_theta_local, op_theta_apply,
+                     op_escale,  op_fe_local,    op_fe_apply,     op_fe_final,        op_permute,    op_random_messages,
+                     op_assignment, op_occupancy, op_init_model};
 #endif
 
 }  // namespace
