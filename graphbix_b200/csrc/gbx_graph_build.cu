@@ -6,7 +6,10 @@
 //   rev[e]            =   slot of the opposite message
 //   erow[e]           =   i (row of the slot)
 //   slot_of_link[k]   =   slot of links[k]              (import / export of messages in `links` order)
-//   und[u]            =   (e, rev[e]) with rev[e] < e   (every undirected edge once, in slot order)
+//
+// A partitioned run (`world` ranks, one GPU each) splits the vertices into `world` equal contiguous ranges; because
+// the CSR is destination-major, a rank's rows are one contiguous range of the global slot space, so its local slot
+// is the global slot minus a base and rev[e] becomes (owner rank << 28 | slot in the owner's buffer).
 //
 // One 64-bit radix sort (CUB) of (destination, source) keys; everything else is a map or a scan.
 #include <cub/cub.cuh>
@@ -67,57 +70,40 @@ __global__ void k_rev(const int* __restrict__ rowptr, const int* __restrict__ co
   }
 }
 
-__global__ void k_flags(const int* __restrict__ rev, long long K, char* flags) {
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < K; e += (long long)gridDim.x * blockDim.x)
-    flags[e] = rev[e] < e;
-}
+struct PartBases {
+  long long sbeg[MAXPEER + 1];
+};
 
-__global__ void k_und(const int* __restrict__ sel, const int* __restrict__ rev, long long L, int2* und) {
-  for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < L; u += (long long)gridDim.x * blockDim.x) {
-    const int e = sel[u];
-    und[u] = make_int2(e, rev[e]);
+// Local slice of the global structure: slots [sbeg, sbeg + Kl) of rank `rank`.
+__global__ void k_slice(const int* __restrict__ gcol, const int* __restrict__ grev, const int* __restrict__ gerow,
+                        long long sbeg, long long Kl, long long chunk, PartBases pb, int* col, int* rev, int* erow) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < Kl; e += (long long)gridDim.x * blockDim.x) {
+    const long long ge = sbeg + e;
+    const int j = gcol[ge];
+    const int owner = (int)(j / chunk);
+    col[e] = j;
+    erow[e] = gerow[ge];
+    rev[e] = (owner << REV_SHIFT) | (int)(grev[ge] - pb.sbeg[owner]);
   }
 }
 
 }  // namespace
 
-// Fills h->rowptr/col/rev/erow/slot_of_link/und (device) and rowptr_host.  Returns GBX_OK or an error code.
-int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* rowptr_host) {
-  const long long n = h->n, K = h->K;
+// Builds the global structure on the device, then keeps this rank's slice in the handle: h->rowptr (local, rebased),
+// h->col / h->erow (global vertex ids), h->rev (packed owner/slot), h->slot_of_link (global slot of every link) and
+// the partition bases.  rowptr_global receives the global row pointers.  Sets h->n, h->K, h->vbeg, h->sbeg.
+int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* rowptr_global) {
+  const long long n = h->n_global, K = h->K_global;
   cudaStream_t st = h->stream;
-  auto alloc = [&](void** p, size_t bytes, bool keep) -> int {
-    GBX_CUDA_TRY(cudaMalloc(p, bytes ? bytes : 1));
-    if (keep) h->dev_bytes += (int64_t)bytes;
-    return GBX_OK;
-  };
-#define GBX_A(ptr, count, keep)                                                          \
-  do {                                                                                   \
-    int _rc = alloc((void**)&(ptr), (size_t)(count) * sizeof(*(ptr)), keep);             \
-    if (_rc != GBX_OK) return _rc;                                                       \
-  } while (0)
-  GBX_A(h->rowptr, n + 1, true);
-  GBX_A(h->col, K, true);
-  GBX_A(h->rev, K, true);
-  GBX_A(h->erow, K, true);
-  GBX_A(h->slot_of_link, K, true);
-  GBX_A(h->und, K / 2 + 1, true);
-
+  int *g_rowptr = nullptr, *g_col = nullptr, *g_rev = nullptr, *g_erow = nullptr;
   int64_t* d_links = nullptr;
   unsigned long long *keys = nullptr, *keys2 = nullptr;
-  int *vals = nullptr, *vals2 = nullptr, *deg = nullptr, *err = nullptr, *sel = nullptr, *nsel = nullptr;
-  char* flags = nullptr;
+  int *vals = nullptr, *vals2 = nullptr, *deg = nullptr, *err = nullptr;
   void* tmp = nullptr;
-  GBX_A(d_links, 2 * K, false);
-  GBX_A(keys, K, false);
-  GBX_A(keys2, K, false);
-  GBX_A(vals, K, false);
-  GBX_A(vals2, K, false);
-  GBX_A(deg, n + 1, false);
-  GBX_A(err, 1, false);
-  GBX_A(nsel, 1, false);
   auto cleanup = [&]() {
+    cudaFree(g_rowptr); cudaFree(g_col); cudaFree(g_rev); cudaFree(g_erow);
     cudaFree(d_links); cudaFree(keys); cudaFree(keys2); cudaFree(vals); cudaFree(vals2); cudaFree(deg);
-    cudaFree(err); cudaFree(sel); cudaFree(nsel); cudaFree(flags); cudaFree(tmp);
+    cudaFree(err); cudaFree(tmp);
   };
   auto fail = [&](int rc) { cleanup(); return rc; };
 #define GBX_C(expr)                                                                      \
@@ -128,38 +114,44 @@ int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* 
       return fail(GBX_ERR_CUDA);                                                         \
     }                                                                                    \
   } while (0)
+#define GBX_T(ptr, count) GBX_C(cudaMalloc((void**)&(ptr), std::max<size_t>((size_t)(count), 1) * sizeof(*(ptr))))
+  GBX_T(g_rowptr, n + 1);
+  GBX_T(g_col, K);
+  GBX_T(g_rev, K);
+  GBX_T(g_erow, K);
+  GBX_C(cudaMalloc((void**)&h->slot_of_link, std::max<size_t>((size_t)K, 1) * sizeof(int)));
+  h->dev_bytes += (int64_t)K * sizeof(int);
+  GBX_T(d_links, 2 * K);
+  GBX_T(keys, K);
+  GBX_T(keys2, K);
+  GBX_T(vals, K);
+  GBX_T(vals2, K);
+  GBX_T(deg, n + 1);
+  GBX_T(err, 1);
   const int grid = h->num_sms * 8;
   GBX_C(cudaMemcpyAsync(d_links, links_host, (size_t)2 * K * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   GBX_C(cudaMemsetAsync(deg, 0, (size_t)(n + 1) * sizeof(int), st));
   GBX_C(cudaMemsetAsync(err, 0, sizeof(int), st));
   if (K > 0) k_keys<<<grid, 256, 0, st>>>(d_links, K, n, keys, vals, deg, err);
-  // rowptr = exclusive scan of the in-degrees
-  size_t tb1 = 0, tb2 = 0, tb3 = 0;
+  size_t tb1 = 0, tb2 = 0;
   int bits = 32;
   while ((1ll << (bits - 32)) < n && bits < 64) ++bits;
-  cub::DeviceScan::ExclusiveSum(nullptr, tb1, deg, h->rowptr, (int)(n + 1), st);
+  cub::DeviceScan::ExclusiveSum(nullptr, tb1, deg, g_rowptr, (int)(n + 1), st);
   cub::DeviceRadixSort::SortPairs(nullptr, tb2, keys, keys2, vals, vals2, (int)K, 0, bits, st);
-  GBX_C(cudaMalloc((void**)&flags, (size_t)K + 1));
-  GBX_C(cudaMalloc((void**)&sel, ((size_t)K / 2 + 1) * sizeof(int)));
-  cub::DeviceSelect::Flagged(nullptr, tb3, cub::CountingInputIterator<int>(0), flags, sel, nsel, (int)K, st);
-  const size_t tb = std::max(tb1, std::max(tb2, tb3));
+  const size_t tb = std::max(tb1, tb2);
   GBX_C(cudaMalloc(&tmp, tb ? tb : 1));
   size_t t = tb;
-  GBX_C(cub::DeviceScan::ExclusiveSum(tmp, t, deg, h->rowptr, (int)(n + 1), st));
+  GBX_C(cub::DeviceScan::ExclusiveSum(tmp, t, deg, g_rowptr, (int)(n + 1), st));
   if (K > 0) {
     t = tb;
     GBX_C(cub::DeviceRadixSort::SortPairs(tmp, t, keys, keys2, vals, vals2, (int)K, 0, bits, st));
-    k_slots<<<grid, 256, 0, st>>>(keys2, vals2, K, h->col, h->erow, h->slot_of_link, err);
-    k_rev<<<grid, 256, 0, st>>>(h->rowptr, h->col, h->erow, K, h->rev, err);
-    k_flags<<<grid, 256, 0, st>>>(h->rev, K, flags);
-    t = tb;
-    GBX_C(cub::DeviceSelect::Flagged(tmp, t, cub::CountingInputIterator<int>(0), flags, sel, nsel, (int)K, st));
+    k_slots<<<grid, 256, 0, st>>>(keys2, vals2, K, g_col, g_erow, h->slot_of_link, err);
+    k_rev<<<grid, 256, 0, st>>>(g_rowptr, g_col, g_erow, K, g_rev, err);
   }
-  int herr = 0, hn = 0;
-  rowptr_host->resize((size_t)n + 1);
+  int herr = 0;
+  rowptr_global->resize((size_t)n + 1);
   GBX_C(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
-  if (K > 0) GBX_C(cudaMemcpyAsync(&hn, nsel, sizeof(int), cudaMemcpyDeviceToHost, st));
-  GBX_C(cudaMemcpyAsync(rowptr_host->data(), h->rowptr, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+  GBX_C(cudaMemcpyAsync(rowptr_global->data(), g_rowptr, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
   GBX_C(cudaStreamSynchronize(st));
   GBX_C(cudaGetLastError());
   if (herr & ERR_RANGE) { last_error() = "links: vertex id out of 1..n"; return fail(GBX_ERR_INVALID); }
@@ -169,13 +161,44 @@ int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* 
     last_error() = "links: reverse link missing (graph must be bidirected)";
     return fail(GBX_ERR_INVALID);
   }
-  if (2ll * hn != K) { last_error() = "links: odd number of directed links"; return fail(GBX_ERR_INVALID); }
-  if (K > 0) k_und<<<grid, 256, 0, st>>>(sel, h->rev, K / 2, h->und);
-  GBX_C(cudaStreamSynchronize(st));
+  // ---- this rank's slice ----
+  const long long chunk = (n + h->world - 1) / h->world;
+  PartBases pb;
+  for (int r = 0; r <= MAXPEER; ++r) {
+    const long long v = std::min<long long>(n, (long long)std::min(r, h->world) * chunk);
+    h->vbeg_all[r] = v;
+    h->sbeg_all[r] = (*rowptr_global)[(size_t)v];
+    pb.sbeg[r] = h->sbeg_all[r];
+  }
+  h->vbeg = h->vbeg_all[h->rank];
+  h->sbeg = h->sbeg_all[h->rank];
+  h->n = h->vbeg_all[h->rank + 1] - h->vbeg;
+  h->K = h->sbeg_all[h->rank + 1] - h->sbeg;
+  for (int r = 0; r < h->world; ++r)
+    if (h->sbeg_all[r + 1] - h->sbeg_all[r] > (long long)REV_MASK) {
+      last_error() = "too many edge slots on one rank (limit 2^28)";
+      return fail(GBX_ERR_INVALID);
+    }
+  auto keep = [&](void** p, size_t bytes) -> cudaError_t {
+    h->dev_bytes += (int64_t)bytes;
+    return cudaMalloc(p, bytes ? bytes : 1);
+  };
+  GBX_C(keep((void**)&h->rowptr, (size_t)(h->n + 1) * sizeof(int)));
+  GBX_C(keep((void**)&h->col, (size_t)h->K * sizeof(int)));
+  GBX_C(keep((void**)&h->rev, (size_t)h->K * sizeof(int)));
+  GBX_C(keep((void**)&h->erow, (size_t)h->K * sizeof(int)));
+  {
+    std::vector<int> rl((size_t)h->n + 1);
+    for (long long i = 0; i <= h->n; ++i) rl[(size_t)i] = (*rowptr_global)[(size_t)(h->vbeg + i)] - (int)h->sbeg;
+    GBX_C(cudaMemcpyAsync(h->rowptr, rl.data(), rl.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (h->K > 0) k_slice<<<grid, 256, 0, st>>>(g_col, g_rev, g_erow, h->sbeg, h->K, chunk, pb, h->col, h->rev, h->erow);
+    GBX_C(cudaStreamSynchronize(st));
+  }
+  GBX_C(cudaGetLastError());
   cleanup();
-  h->launches += 6;
+  h->launches += 5;
   return GBX_OK;
-#undef GBX_A
+#undef GBX_T
 #undef GBX_C
 }
 

@@ -87,6 +87,25 @@ int read_state(gbx_sbm* h) {
   return GBX_OK;
 }
 
+// Initial messages into buffer 0: from the caller's K_global x q array in `links` order, or drawn on the device.
+int load_messages(gbx_sbm* h, const double* psicav, uint64_t seed) {
+  if (!psicav) return h->ops->random_messages(h, seed);
+  const size_t bytes = (size_t)h->K_global * h->q * sizeof(double);
+  double* tmp = h->msg[1];  // scratch before the first sweep (large enough on a single rank)
+  bool own = false;
+  if (h->world > 1) {
+    GBX_CUDA_TRY(cudaMalloc((void**)&tmp, bytes ? bytes : 1));
+    own = true;
+  }
+  cudaError_t e = cudaMemcpyAsync(tmp, psicav, bytes, cudaMemcpyHostToDevice, h->stream);
+  int rc = GBX_OK;
+  if (e == cudaSuccess) rc = h->ops->permute(h, tmp, h->msg[0], 1);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (own) cudaFree(tmp);
+  GBX_CUDA_TRY(e);
+  return rc;
+}
+
 // freeenergy(): sum_i log Z_i, then two passes over the undirected edges (sums, then squared deviations).
 int free_energy_steps(gbx_sbm* h) {
   const SbmOps* op = h->ops;
@@ -147,7 +166,8 @@ void gbx_sbm_default_options(gbx_sbm_options* opt) {
   opt->check_every = 1;
 }
 
-static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t K, const int64_t* links, int q) {
+static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t K, const int64_t* links, int q,
+                        int rank = 0, int world = 1) {
   if (!out) return fail_invalid("out is NULL");
   *out = nullptr;
   if (q < 1 || q > MAXQ) return fail_invalid("q must be in 1..16");
@@ -155,6 +175,7 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
   if (!ops) return fail_invalid("this build of libgraphbix_cuda was compiled without that q");
   if (n < 1 || K < 0 || (K > 0 && !links)) return fail_invalid("bad n_vertices / n_links / links");
   if (n >= (int64_t)1 << 31 || K >= (int64_t)1 << 31) return fail_invalid("graph too large for 32-bit slots");
+  if (world < 1 || world > MAXPEER || rank < 0 || rank >= world) return fail_invalid("bad rank / world (at most 8 ranks)");
   int ndev = gbx_device_count();
   if (ndev < 0) return ndev;
   if (ndev == 0) {
@@ -172,9 +193,11 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
   h->K = K;
   h->n_global = n;
   h->K_global = K;
-  h->n_und = K / 2;
+  h->rank = rank;
+  h->world = world;
   h->ops = ops;
-  std::vector<int> rowptr;
+  std::vector<int> rowptr_g;   // global row pointers
+  std::vector<int> rowptr;     // this rank's (rebased)
   {
     cudaDeviceProp prop;
     cudaError_t ce = cudaSetDevice(device);
@@ -190,7 +213,7 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
       return GBX_ERR_CUDA;
     }
     h->num_sms = prop.multiProcessorCount;
-    const int rcb = build_graph_device(h, links, &rowptr);
+    const int rcb = build_graph_device(h, links, &rowptr_g);
     if (rcb != GBX_OK) {
       const std::string keep = last_error();
       gbx_sbm_destroy(h);
@@ -198,6 +221,10 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
       return rcb;
     }
   }
+  n = h->n;  // from here on: this rank's vertices and slots
+  K = h->K;
+  rowptr.resize((size_t)n + 1);
+  for (int64_t i = 0; i <= n; ++i) rowptr[(size_t)i] = rowptr_g[(size_t)(h->vbeg + i)] - (int)h->sbeg;
   // ---- tile schedule: runs of consecutive vertices with <= TILE_E slots and <= TV vertices; hubs apart ----
   const int TV = tile_vertices(q);
   std::vector<int4> tiles;
@@ -225,19 +252,19 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
   }
 
   h->ntiles = (int)tiles.size();
-  for (int64_t v = 0; v < n; ++v) h->max_degree = std::max(h->max_degree, rowptr[(size_t)v + 1] - rowptr[(size_t)v]);
+  for (int64_t v = 0; v < h->n_global; ++v) h->max_degree = std::max(h->max_degree, rowptr_g[(size_t)v + 1] - rowptr_g[(size_t)v]);
   h->model = model;
   gbx_mod_default_options(&h->mopt);
   {
     // mod.jl:155 constshift = sum_i d_i log d_i / L and mod.jl:185 excm, from the true degrees
     double sdl = 0.0, sd2 = 0.0, sd = 0.0;
-    for (int64_t v = 0; v < n; ++v) {
-      const double d = (double)(rowptr[(size_t)v + 1] - rowptr[(size_t)v]);
+    for (int64_t v = 0; v < h->n_global; ++v) {
+      const double d = (double)(rowptr_g[(size_t)v + 1] - rowptr_g[(size_t)v]);
       if (d > 0) sdl += d * std::log(d);
       sd2 += d * d;
       sd += d;
     }
-    h->constshift = K > 0 ? sdl / (0.5 * (double)K) : 0.0;
+    h->constshift = h->K_global > 0 ? sdl / (0.5 * (double)h->K_global) : 0.0;
     h->excm = sd > 0 ? sd2 / sd - 1.0 : 0.0;  // (d'd)/(N mean(d)) - 1
   }
   h->nhubs = (int)hubs.size();
@@ -249,17 +276,17 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
     GBX_TRY(dev_alloc(h, &h->msg[0], (size_t)K * q));
     GBX_TRY(dev_alloc(h, &h->msg[1], (size_t)K * q));
     GBX_TRY(dev_alloc(h, &h->PSI, (size_t)n * q));
-    GBX_TRY(dev_alloc(h, &h->theta, (size_t)h->n_global));
+    GBX_TRY(dev_alloc(h, &h->theta, (size_t)h->n_global + MAXPEER));
     GBX_TRY(dev_alloc(h, &h->totals, (size_t)TOT_MAX));
     GBX_TRY(dev_alloc(h, &h->maxd_dev, 1));
     GBX_TRY(dev_alloc(h, &h->deg_global, (size_t)h->n_global));
     {
       std::vector<double> dg((size_t)h->n_global);
-      for (int64_t v = 0; v < h->n_global; ++v) dg[(size_t)v] = (double)(rowptr[(size_t)v + 1] - rowptr[(size_t)v]);
+      for (int64_t v = 0; v < h->n_global; ++v) dg[(size_t)v] = (double)(rowptr_g[(size_t)v + 1] - rowptr_g[(size_t)v]);
       GBX_CUDA_TRY(cudaMemcpy(h->deg_global, dg.data(), dg.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
-    h->msgp[0][0] = h->msg[0];
-    h->msgp[1][0] = h->msg[1];
+    h->msgp[0][h->rank] = h->msg[0];
+    h->msgp[1][h->rank] = h->msg[1];
     GBX_TRY(dev_alloc(h, &h->pidx, (size_t)n));
     GBX_TRY(dev_alloc(h, &h->prior_tab, (size_t)(1 + (TILE_E + 1) * q) * (q + 3)));
     GBX_CUDA_TRY(cudaMemset(h->pidx, 0, (size_t)n * sizeof(int)));
@@ -282,7 +309,7 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
     GBX_TRY(dev_alloc(h, &h->part_vertex, (size_t)(h->grid_vertex + h->nhubs) * PSTRIDE));
     GBX_TRY(dev_alloc(h, &h->part_mstep, (size_t)h->grid_mstep * q * q));
     GBX_TRY(dev_alloc(h, &h->part_theta, (size_t)h->grid_theta * MAXQ));
-    GBX_TRY(dev_alloc(h, &h->part_fe, (size_t)h->grid_fe * 4));
+    GBX_TRY(dev_alloc(h, &h->part_fe, (size_t)h->grid_fe * 8));
     GBX_CUDA_TRY(cudaDeviceSynchronize());
     return GBX_OK;
   };
@@ -304,12 +331,14 @@ int gbx_sbm_create(gbx_sbm** out, int device, int64_t n, int64_t K, const int64_
 int gbx_sbm_destroy(gbx_sbm* h) {
   if (!h) return GBX_OK;
   cudaSetDevice(h->device);
+  for (int b = 0; b < 2; ++b)
+    for (int r = 0; r < MAXPEER; ++r)
+      if (h->ipc_open[b][r]) cudaIpcCloseMemHandle(h->msgp[b][r]);
   cudaFree(h->rowptr);
   cudaFree(h->col);
   cudaFree(h->rev);
   cudaFree(h->erow);
   cudaFree(h->escale);
-  cudaFree(h->und);
   cudaFree(h->slot_of_link);
   cudaFree(h->tiles);
   cudaFree(h->hubs);
@@ -373,21 +402,16 @@ int gbx_sbm_init(gbx_sbm* h, const double* gr_init, const double* Crs_init, cons
   h->itr = 0;
   h->theta_valid = false;
   GBX_TRY(h->ops->init_model(h));  // theta = 1: row 0 of the prior table
-  if (psicav) {
-    double* tmp = h->msg[1];
-    GBX_CUDA_TRY(cudaMemcpyAsync(tmp, psicav, (size_t)h->K * q * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    GBX_TRY(h->ops->permute(h, tmp, h->msg[0], 1));
-  } else {
-    GBX_TRY(h->ops->random_messages(h, seed));
-  }
+  GBX_TRY(load_messages(h, psicav, seed));
   {
     std::vector<double> ones((size_t)std::max<int64_t>(h->n_global, h->K), 1.0);  // theta = ones(Ntot,1), sbm.jl:277
     GBX_CUDA_TRY(cudaMemcpyAsync(h->theta, ones.data(), (size_t)h->n_global * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     GBX_CUDA_TRY(cudaMemcpyAsync(h->escale, ones.data(), (size_t)h->K * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     GBX_CUDA_TRY(cudaStreamSynchronize(h->stream));
   }
-  if (!h->fail) {
+  if (!h->fail && h->world == 1) {
     // PSI = updatePSI() with h = 0, then gr = update_gr(PSI): sbm.jl:340-341
+    // (a partitioned run does this through gbx_sbm_step so that the ranks can all-reduce the totals in between)
     GBX_TRY(h->ops->prepare(h, 1, 0));
     GBX_TRY(h->ops->vertex_pass(h, MODE_MARGINAL));
     GBX_TRY(h->ops->local_totals(h, MODE_MARGINAL));
@@ -401,6 +425,7 @@ int gbx_sbm_init(gbx_sbm* h, const double* gr_init, const double* Crs_init, cons
 int gbx_sbm_iterate(gbx_sbm* h, int n_iters, double* bpconv_out) {
   if (!h) return fail_invalid("handle is NULL");
   if (!h->initialised) return fail_state();
+  if (h->world > 1 && n_iters > 0) return fail_invalid("partitioned handle: drive the loop with gbx_sbm_step");
   GBX_TRY(set_device(h));
   for (int i = 0; i < n_iters; ++i) GBX_TRY(em_iteration(h));
   if (bpconv_out) {
@@ -426,12 +451,13 @@ int gbx_sbm_finalize(gbx_sbm* h, gbx_sbm_result* res) {
   if (!h || !res) return fail_invalid("handle/result is NULL");
   if (!h->initialised) return fail_state();
   GBX_TRY(set_device(h));
-  memset(res, 0, sizeof *res);
-  res->fail = h->fail;
-  if (!h->fail) {
+  if (!h->fail && h->world == 1) {
     GBX_TRY(h->ops->prepare(h, 0, 1));  // h = update_h(); gr = update_gr(PSI)   sbm.jl:364-365
     GBX_TRY(free_energy_steps(h));      // freeenergy()                          sbm.jl:366
   }
+  // (a partitioned run has driven the same steps through gbx_sbm_step, with the ranks' all-reduces in between)
+  memset(res, 0, sizeof *res);
+  res->fail = h->fail;
   GBX_TRY(read_state(h));
   const SbmState* s = h->h_state;
   res->FE = s->result[0];
@@ -453,6 +479,7 @@ int gbx_sbm_finalize(gbx_sbm* h, gbx_sbm_result* res) {
 int gbx_sbm_em(gbx_sbm* h, gbx_sbm_result* res) {
   if (!h || !res) return fail_invalid("handle/result is NULL");
   if (!h->initialised) return fail_state();
+  if (h->world > 1) return fail_invalid("partitioned handle: drive the loop with gbx_sbm_step (see engine_dist.py)");
   GBX_TRY(set_device(h));
   int cnv = 0, itrnum = 0;
   if (!h->fail) {
@@ -483,7 +510,7 @@ int gbx_sbm_get_state(gbx_sbm* h, double* gr, double* Crs, double* PSI, double* 
   if (Crs) memcpy(Crs, h->h_state->C, (size_t)q * q * sizeof(double));
   if (hfield) memcpy(hfield, h->h_state->h, q * sizeof(double));
   if (PSI) GBX_CUDA_TRY(cudaMemcpyAsync(PSI, h->PSI, (size_t)h->n * q * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  if (theta) GBX_CUDA_TRY(cudaMemcpyAsync(theta, h->theta, (size_t)h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (theta) GBX_CUDA_TRY(cudaMemcpyAsync(theta, h->theta + h->vbeg, (size_t)h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   GBX_CUDA_TRY(cudaStreamSynchronize(h->stream));
   return GBX_OK;
 }
@@ -491,10 +518,21 @@ int gbx_sbm_get_state(gbx_sbm* h, double* gr, double* Crs, double* PSI, double* 
 int gbx_sbm_get_messages(gbx_sbm* h, double* psicav) {
   if (!h || !psicav) return fail_invalid("handle/psicav is NULL");
   GBX_TRY(set_device(h));
-  double* tmp = h->msg[h->cur ^ 1];  // the other buffer is scratch between sweeps
-  GBX_TRY(h->ops->permute(h, h->msg[h->cur], tmp, 0));
-  GBX_CUDA_TRY(cudaMemcpyAsync(psicav, tmp, (size_t)h->K * h->q * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  GBX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  // link order, K_global rows; on a partitioned run the rows of links owned by other ranks come back as zeros
+  const size_t bytes = (size_t)h->K_global * h->q * sizeof(double);
+  double* tmp = h->msg[h->cur ^ 1];  // the other buffer is scratch between sweeps (single rank)
+  bool own = false;
+  if (h->world > 1) {
+    GBX_CUDA_TRY(cudaMalloc((void**)&tmp, bytes ? bytes : 1));
+    own = true;
+  }
+  int rc = h->ops->permute(h, h->msg[h->cur], tmp, 0);
+  cudaError_t e = cudaSuccess;
+  if (rc == GBX_OK) e = cudaMemcpyAsync(psicav, tmp, bytes, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (own) cudaFree(tmp);
+  if (rc != GBX_OK) return rc;
+  GBX_CUDA_TRY(e);
   return GBX_OK;
 }
 
@@ -575,7 +613,7 @@ int gbx_mod_init(gbx_mod* h, const double* gr, const double* psicav, uint64_t se
   const double excm = h->excm, B = (double)q;
   const double beta0 = std::log(1.0 + B / (excm - 1.0));
   const double betaast = std::log(1.0 + B / (std::sqrt(excm) - 1.0));
-  s.alpha = 1.0 / (double)h->K;
+  s.alpha = 1.0 / (double)h->K_global;
   s.beta = betaast - h->mopt.betafrac * (betaast - beta0);
   s.omegain = std::exp(s.beta) * s.alpha * s.beta / (std::exp(s.beta) - 1.0);
   s.omegaout = s.alpha * s.beta / (std::exp(s.beta) - 1.0);
@@ -585,18 +623,14 @@ int gbx_mod_init(gbx_mod* h, const double* gr, const double* psicav, uint64_t se
   h->itr = 0;
   h->fail = 0;
   GBX_TRY(h->ops->init_model(h));  // prior-table row per vertex: by degree when degree corrected
-  if (psicav) {
-    double* tmp = h->msg[1];
-    GBX_CUDA_TRY(cudaMemcpyAsync(tmp, psicav, (size_t)h->K * q * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    GBX_TRY(h->ops->permute(h, tmp, h->msg[0], 1));
-  } else {
-    GBX_TRY(h->ops->random_messages(h, seed));
+  GBX_TRY(load_messages(h, psicav, seed));
+  if (h->world == 1) {
+    // h = zeros(1,B); PSI = updatePSI(): mod.jl:204-206
+    GBX_TRY(h->ops->prepare(h, 1, 0));
+    GBX_TRY(h->ops->vertex_pass(h, MODE_MARGINAL));
+    GBX_TRY(h->ops->local_totals(h, MODE_MARGINAL));
+    GBX_TRY(h->ops->apply_totals(h, MODE_MARGINAL));
   }
-  // h = zeros(1,B); PSI = updatePSI(): mod.jl:204-206
-  GBX_TRY(h->ops->prepare(h, 1, 0));
-  GBX_TRY(h->ops->vertex_pass(h, MODE_MARGINAL));
-  GBX_TRY(h->ops->local_totals(h, MODE_MARGINAL));
-  GBX_TRY(h->ops->apply_totals(h, MODE_MARGINAL));
   GBX_CUDA_TRY(cudaStreamSynchronize(h->stream));
   h->initialised = true;
   return GBX_OK;
@@ -616,6 +650,7 @@ static int mod_iteration(gbx_sbm* h) {
 int gbx_mod_iterate(gbx_mod* h, int n_iters, double* bpconv_out) {
   if (!h) return fail_invalid("handle is NULL");
   if (!h->initialised || h->model != 1) return fail_state();
+  if (h->world > 1 && n_iters > 0) return fail_invalid("partitioned handle: drive the loop with gbx_sbm_step");
   GBX_TRY(set_device(h));
   for (int i = 0; i < n_iters; ++i) GBX_TRY(mod_iteration(h));
   if (bpconv_out) {
@@ -630,8 +665,10 @@ int gbx_mod_finalize(gbx_mod* h, gbx_mod_result* res) {
   if (!h->initialised || h->model != 1) return fail_state();
   GBX_TRY(set_device(h));
   memset(res, 0, sizeof *res);
-  GBX_TRY(h->ops->prepare(h, 0, 0));   // h = update_h()   mod.jl:240
-  GBX_TRY(free_energy_steps(h));       // freeenergy()     mod.jl:241
+  if (h->world == 1) {
+    GBX_TRY(h->ops->prepare(h, 0, 0));   // h = update_h()   mod.jl:240
+    GBX_TRY(free_energy_steps(h));       // freeenergy()     mod.jl:241
+  }
   GBX_TRY(read_state(h));
   const SbmState* s = h->h_state;
   res->excm = h->excm;
@@ -658,6 +695,7 @@ int gbx_mod_finalize(gbx_mod* h, gbx_mod_result* res) {
 int gbx_mod_em(gbx_mod* h, gbx_mod_result* res) {
   if (!h || !res) return fail_invalid("handle/result is NULL");
   if (!h->initialised || h->model != 1) return fail_state();
+  if (h->world > 1) return fail_invalid("partitioned handle: drive the loop with gbx_sbm_step");
   GBX_TRY(set_device(h));
   int cnv = 0, itrnum = 0;
   for (int itr = 1; itr <= h->mopt.itrmax; ++itr) {
@@ -691,5 +729,101 @@ int gbx_mod_get_state(gbx_mod* h, double* gr, double* PSI, double* hfield, doubl
 int gbx_mod_get_messages(gbx_mod* h, double* psicav) { return gbx_sbm_get_messages(h, psicav); }
 int gbx_mod_get_assignment(gbx_mod* h, int32_t* block) { return gbx_sbm_get_assignment(h, block); }
 int64_t gbx_mod_launch_count(const gbx_mod* h) { return gbx_sbm_launch_count(h); }
+
+// ---------------------------------------------------------------------------------------------
+// Vertex-partitioned runs: one process per GPU, rank r owns the vertices [r*ceil(n/world), ...) and their rows.
+// ---------------------------------------------------------------------------------------------
+int gbx_sbm_create_part(gbx_sbm** out, int device, int64_t n, int64_t K, const int64_t* links, int q, int rank,
+                        int world) {
+  return graph_create(0, out, device, n, K, links, q, rank, world);
+}
+int gbx_mod_create_part(gbx_mod** out, int device, int64_t n, int64_t K, const int64_t* links, int q, int rank,
+                        int world) {
+  return graph_create(1, out, device, n, K, links, q, rank, world);
+}
+
+int gbx_sbm_part_info(const gbx_sbm* h, int64_t* info) {
+  if (!h || !info) return fail_invalid("handle/info is NULL");
+  info[0] = h->vbeg;
+  info[1] = h->n;
+  info[2] = h->sbeg;
+  info[3] = h->K;
+  info[4] = TOT_MAX;
+  info[5] = (h->n_global + h->world - 1) / h->world;  // vertices per rank (the last rank may own fewer)
+  info[6] = h->rank;
+  info[7] = h->world;
+  return GBX_OK;
+}
+
+int gbx_sbm_ipc_export(gbx_sbm* h, int which, unsigned char* handle64) {
+  if (!h || !handle64 || which < 0 || which > 1) return fail_invalid("bad arguments");
+  GBX_TRY(set_device(h));
+  cudaIpcMemHandle_t mh;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  GBX_CUDA_TRY(cudaIpcGetMemHandle(&mh, h->msg[which]));
+  memcpy(handle64, &mh, 64);
+  return GBX_OK;
+}
+
+int gbx_sbm_ipc_import(gbx_sbm* h, int which, int rank, const unsigned char* handle64) {
+  if (!h || !handle64 || which < 0 || which > 1 || rank < 0 || rank >= h->world) return fail_invalid("bad arguments");
+  if (rank == h->rank) return GBX_OK;
+  GBX_TRY(set_device(h));
+  cudaIpcMemHandle_t mh;
+  memcpy(&mh, handle64, 64);
+  void* p = nullptr;
+  GBX_CUDA_TRY(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+  h->msgp[which][rank] = (double*)p;
+  h->ipc_open[which][rank] = true;
+  return GBX_OK;
+}
+
+int gbx_sbm_part_set_buffers(gbx_sbm* h, void* totals_dev, void* theta_dev) {
+  if (!h) return fail_invalid("handle is NULL");
+  if (totals_dev) {
+    if (h->totals_owned) cudaFree(h->totals);
+    h->totals = (double*)totals_dev;
+    h->totals_owned = false;
+  }
+  if (theta_dev) {
+    if (h->theta_owned) cudaFree(h->theta);
+    h->theta = (double*)theta_dev;
+    h->theta_owned = false;
+  }
+  return GBX_OK;
+}
+
+int gbx_sbm_step(gbx_sbm* h, int step, int arg) {
+  if (!h) return fail_invalid("handle is NULL");
+  if (!h->initialised) return fail_state();
+  GBX_TRY(set_device(h));
+  const SbmOps* op = h->ops;
+  switch (step) {
+    case GBX_STEP_PREPARE: return op->prepare(h, arg & 1, (arg >> 1) & 1);
+    case GBX_STEP_VERTEX_PASS: {
+      GBX_TRY(op->vertex_pass(h, arg));
+      if (arg == MODE_SWEEP) h->cur ^= 1;
+      return GBX_OK;
+    }
+    case GBX_STEP_LOCAL_TOTALS: return op->local_totals(h, arg);
+    case GBX_STEP_APPLY_TOTALS: return op->apply_totals(h, arg);
+    case GBX_STEP_THETA_LOCAL: return op->theta_local(h);
+    case GBX_STEP_THETA_APPLY: return op->theta_apply(h);
+    case GBX_STEP_ESCALE: return op->escale(h);
+    case GBX_STEP_FE_LOCAL: return op->fe_local(h, arg);
+    case GBX_STEP_FE_APPLY: return op->fe_apply(h, arg);
+    case GBX_STEP_FE_FINAL: return op->fe_final(h);
+    case GBX_STEP_COUNT_ITERATION: h->itr++; return GBX_OK;
+    default: return fail_invalid("unknown step");
+  }
+}
+
+int gbx_sbm_read_residual(gbx_sbm* h, double* bpconv) {
+  if (!h || !bpconv) return fail_invalid("handle/bpconv is NULL");
+  GBX_TRY(set_device(h));
+  GBX_TRY(read_state(h));
+  *bpconv = h->h_state->conv;
+  return GBX_OK;
+}
 
 }  // extern "C"

@@ -75,13 +75,12 @@ struct gbx_sbm {
   int* erow = nullptr;            // per edge slot: its row (destination vertex)
   int4* tiles = nullptr;          // (first vertex, #vertices, first edge slot, #edge slots)
   double* escale = nullptr;       // per edge slot theta_row * theta_col (all ones until update_theta runs)
-  int2* und = nullptr;            // every undirected edge once: (slot e, slot rev[e]) with rev[e] < e
   int ntiles = 0, nhubs = 0, max_degree = 1;
-  int64_t n_und = 0;              // entries of `und` (undirected edges whose larger slot is on this rank)
   double* deg_global = nullptr;   // degree of every vertex, by global id
   // state (device)
   double *msg[2] = {nullptr, nullptr}, *PSI = nullptr;
   double* msgp[2][gbx::MAXPEER] = {};   // both message buffers of every rank (peer-mapped; [b][rank] == msg[b])
+  bool ipc_open[2][gbx::MAXPEER] = {};
   double* theta = nullptr;              // indexed by GLOBAL vertex id (all ranks' values after the all-gather)
   bool theta_owned = true;              // false: the caller provided the buffer (partitioned runs)
   double* totals = nullptr;             // per-pass totals vector (device); caller-provided in partitioned runs

@@ -1140,19 +1140,20 @@ struct PeerCur {
 };
 
 template <int PASS>
-__global__ void __launch_bounds__(NT) sbm_fe_kernel(const SbmState* st, const int2* __restrict__ und,
+__global__ void __launch_bounds__(NT) sbm_fe_kernel(const SbmState* st, const int* __restrict__ rev,
                                                     const int* __restrict__ col, const int* __restrict__ erow,
                                                     long long L, const double* __restrict__ psi, PeerCur peers,
-                                                    const double* __restrict__ theta, int dc, double* partials) {
+                                                    const double* __restrict__ theta, int dc, int rank,
+                                                    double* partials) {
   __shared__ double red[(NT / 32) * 4];
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   double mean[4] = {0.0, 0.0, 0.0, 0.0};
   if (PASS == 1)
     for (int k = 0; k < 4; ++k) mean[k] = st->cvmean[k];
   for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < L; i += (long long)gridDim.x * NT) {
-    {
-      const int2 er = und[i];
-      const int e = er.x, r = er.y;
+    const int e = (int)i, r = rev[i];
+    // every undirected edge once: at the larger of its two global slots (the `i < j -> continue` of sbm.jl:166)
+    if (rev_owner(r) < rank || (rev_owner(r) == rank && rev_slot(r) < e)) {
       double a[Q], b[Q];
       load_vec<Q>(psi, e, b);                                   // j -> i   (i = row of e, j = col[e])
       load_vec<Q>(peers.p[rev_owner(r)], rev_slot(r), a);       // i -> j   (in the row of j, possibly on a peer)
@@ -1216,17 +1217,27 @@ __global__ void sbm_finalize(SbmState* st, double N, double L) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Messages between `links` order (all K_global links) and this rank's slots [sbeg, sbeg + Kl).
+//   to_slots: dst (local slots) <- src (link order);  otherwise dst (link order, zeros for links of other ranks) <- src
 __global__ void k_permute_rows(const double* __restrict__ src, double* __restrict__ dst,
-                               const int* __restrict__ slot_of_link, long long K, int to_slots) {
+                               const int* __restrict__ slot_of_link, long long K, int to_slots, long long sbeg,
+                               long long Kl) {
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < K;
        k += (long long)gridDim.x * blockDim.x) {
-    const long long s = slot_of_link[k];
+    const long long s = (long long)slot_of_link[k] - sbeg;
+    const bool local = s >= 0 && s < Kl;
     double m[Q];
     if (to_slots) {
+      if (!local) continue;
       load_vec<Q>(src, k, m);
       store_vec<Q>(dst, s, m);
     } else {
-      load_vec<Q>(src, s, m);
+      if (local) {
+        load_vec<Q>(src, s, m);
+      } else {
+#pragma unroll
+        for (int t = 0; t < Q; ++t) m[t] = 0.0;
+      }
       store_vec<Q>(dst, k, m);
     }
   }
@@ -1241,9 +1252,11 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 
 // rand(1,B) normalised (sbm.jl:319-323), counter-based so the result does not depend on the launch shape.
 __global__ void k_random_messages(double* __restrict__ dst, const int* __restrict__ slot_of_link, long long K,
-                                  uint64_t seed) {
+                                  uint64_t seed, long long sbeg, long long Kl) {
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < K;
        k += (long long)gridDim.x * blockDim.x) {
+    const long long slot = (long long)slot_of_link[k] - sbeg;
+    if (slot < 0 || slot >= Kl) continue;  // keyed by the global link index: the same draw whatever the partition
     double m[Q];
     double s = 0.0;
 #pragma unroll
@@ -1254,7 +1267,7 @@ __global__ void k_random_messages(double* __restrict__ dst, const int* __restric
     }
 #pragma unroll
     for (int t = 0; t < Q; ++t) m[t] /= s;
-    store_vec<Q>(dst, slot_of_link[k], m);
+    store_vec<Q>(dst, slot, m);
   }
 }
 
@@ -1409,11 +1422,11 @@ PeerCur peer_cur(const gbx_sbm* h) {
 
 int op_fe_local(gbx_sbm* h, int pass) {
   if (pass == 0)
-    sbm_fe_kernel<0><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->und, h->col, h->erow, (long long)h->n_und, h->msg[h->cur],
-                                                       peer_cur(h), h->theta, h->opt.degreecorrection, h->part_fe);
+    sbm_fe_kernel<0><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->rev, h->col, h->erow, (long long)h->K, h->msg[h->cur],
+                                                       peer_cur(h), h->theta, h->opt.degreecorrection, h->rank, h->part_fe);
   else
-    sbm_fe_kernel<1><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->und, h->col, h->erow, (long long)h->n_und, h->msg[h->cur],
-                                                       peer_cur(h), h->theta, h->opt.degreecorrection, h->part_fe);
+    sbm_fe_kernel<1><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->rev, h->col, h->erow, (long long)h->K, h->msg[h->cur],
+                                                       peer_cur(h), h->theta, h->opt.degreecorrection, h->rank, h->part_fe);
   k_local_columns<<<1, 128, 0, h->stream>>>(h->part_fe, h->grid_fe, 4, h->totals);
   h->launches += 2;
   GBX_CUDA_TRY(cudaGetLastError());
@@ -1436,14 +1449,16 @@ int op_fe_final(gbx_sbm* h) {
 #endif
 
 int op_permute(gbx_sbm* h, const double* src, double* dst, int to_slots) {
-  k_permute_rows<<<grid_for(h, h->K), 256, 0, h->stream>>>(src, dst, h->slot_of_link, (long long)h->K, to_slots);
+  k_permute_rows<<<grid_for(h, h->K_global), 256, 0, h->stream>>>(src, dst, h->slot_of_link, (long long)h->K_global, to_slots,
+                                                                 (long long)h->sbeg, (long long)h->K);
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
 }
 
 int op_random_messages(gbx_sbm* h, uint64_t seed) {
-  k_random_messages<<<grid_for(h, h->K), 256, 0, h->stream>>>(h->msg[0], h->slot_of_link, (long long)h->K, seed);
+  k_random_messages<<<grid_for(h, h->K_global), 256, 0, h->stream>>>(h->msg[0], h->slot_of_link, (long long)h->K_global, seed,
+                                                                    (long long)h->sbeg, (long long)h->K);
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
@@ -1554,10 +1569,10 @@ __global__ void mod_prepare(SbmState* st, SbmParams* out, double N, int zero_h) 
 
 // freeenergy(), mod.jl:127-153.  x0 = logZij, x1 = CVBP, x2 = CVGP, x3 = CVGT, x4 = CVMAP per undirected edge.
 template <int PASS>
-__global__ void __launch_bounds__(NT) mod_fe_kernel(const SbmState* st, const int2* __restrict__ und,
+__global__ void __launch_bounds__(NT) mod_fe_kernel(const SbmState* st, const int* __restrict__ rev,
                                                     const int* __restrict__ col, const int* __restrict__ erow,
                                                     const double* __restrict__ degs, long long L,
-                                                    const double* __restrict__ psi, PeerCur peers, int dc,
+                                                    const double* __restrict__ psi, PeerCur peers, int dc, int rank,
                                                     double* partials) {
   __shared__ double red[(NT / 32) * 5];
   double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
@@ -1567,7 +1582,8 @@ __global__ void __launch_bounds__(NT) mod_fe_kernel(const SbmState* st, const in
   const double oin = st->omegain, oout = st->omegaout, beta = st->beta;
   const double loin = log(oin), loout = log(oout);
   for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < L; i += (long long)gridDim.x * NT) {
-    const int2 er = und[i];
+    const int2 er = make_int2((int)i, rev[i]);
+    if (!(rev_owner(er.y) < rank || (rev_owner(er.y) == rank && rev_slot(er.y) < er.x))) continue;  // each edge once
     double a[Q], b[Q];
     load_vec<Q>(psi, er.x, b);
     load_vec<Q>(peers.p[rev_owner(er.y)], rev_slot(er.y), a);
@@ -1659,11 +1675,11 @@ PeerCur peer_cur(const gbx_sbm* h) {
 
 int mop_fe_local(gbx_sbm* h, int pass) {
   if (pass == 0)
-    mod_fe_kernel<0><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->und, h->col, h->erow, h->deg_global, (long long)h->n_und,
-                                                       h->msg[h->cur], peer_cur(h), h->mopt.dc, h->part_fe);
+    mod_fe_kernel<0><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->rev, h->col, h->erow, h->deg_global, (long long)h->K,
+                                                       h->msg[h->cur], peer_cur(h), h->mopt.dc, h->rank, h->part_fe);
   else
-    mod_fe_kernel<1><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->und, h->col, h->erow, h->deg_global, (long long)h->n_und,
-                                                       h->msg[h->cur], peer_cur(h), h->mopt.dc, h->part_fe);
+    mod_fe_kernel<1><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->rev, h->col, h->erow, h->deg_global, (long long)h->K,
+                                                       h->msg[h->cur], peer_cur(h), h->mopt.dc, h->rank, h->part_fe);
   k_local_columns<<<1, 160, 0, h->stream>>>(h->part_fe, h->grid_fe, 5, h->totals);
   h->launches += 2;
   GBX_CUDA_TRY(cudaGetLastError());

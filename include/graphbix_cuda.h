@@ -157,6 +157,43 @@ int gbx_mod_get_messages(gbx_mod* h, double* psicav);
 int gbx_mod_get_assignment(gbx_mod* h, int32_t* block);
 int64_t gbx_mod_launch_count(const gbx_mod* h);
 
+/* ------------------------------------------------------------------------------------------------
+ * Vertex-partitioned runs (BASELINE.json configs[3]): one process per GPU of one NVLink domain, <= 8 ranks.
+ * Rank r owns the vertices [r*c, min(n,(r+1)*c)), c = ceil(n/world), and the rows of their incoming messages.
+ * New messages into rows of another rank are stored straight into that rank's buffer over NVLink (peer pointers
+ * exchanged once with gbx_sbm_ipc_*); the only per-iteration collectives are the all-reduce of the totals vector
+ * and, with degree correction, the all-gather of theta -- issued by the host (torch.distributed / NCCL) between
+ * gbx_sbm_step calls.  graphbix_b200/engine_dist.py is the reference driver.  gbx_mod handles work the same way.
+ * ------------------------------------------------------------------------------------------------ */
+enum {
+  GBX_STEP_PREPARE = 0,          /* arg bit 0: h = 0 (initial marginals); bit 1: gr = update_gr(PSI) first   */
+  GBX_STEP_VERTEX_PASS = 1,      /* arg 0: BP sweep (+ M-step statistics), 1: marginals only, 2: sum log Z_i  */
+  GBX_STEP_LOCAL_TOTALS = 2,     /* arg = mode of the pass; fills this rank's totals vector                   */
+  GBX_STEP_APPLY_TOTALS = 3,     /* after the all-reduce (sum) of the totals vector                           */
+  GBX_STEP_THETA_LOCAL = 4,      /* update_theta on this rank's vertices; S_theta partial -> totals[0..q)      */
+  GBX_STEP_THETA_APPLY = 5,      /* after the all-reduce of totals[0..q)                                      */
+  GBX_STEP_ESCALE = 6,           /* after the all-gather of theta                                             */
+  GBX_STEP_FE_LOCAL = 7,         /* arg = pass (0 sums, 1 squared deviations) -> totals[0..5)                 */
+  GBX_STEP_FE_APPLY = 8,
+  GBX_STEP_FE_FINAL = 9,
+  GBX_STEP_COUNT_ITERATION = 10
+};
+int gbx_sbm_create_part(gbx_sbm** out, int device, int64_t n_vertices, int64_t n_links, const int64_t* links, int q,
+                        int rank, int world);
+int gbx_mod_create_part(gbx_mod** out, int device, int64_t n_vertices, int64_t n_links, const int64_t* links, int q,
+                        int rank, int world);
+/* info[0..8) = first owned vertex, owned vertices, first owned slot, owned slots, length of the totals vector,
+ * vertices per rank c, rank, world */
+int gbx_sbm_part_info(const gbx_sbm* h, int64_t* info);
+/* cudaIpcMemHandle_t (64 bytes) of message buffer `which` (0/1); every rank imports every other rank's two. */
+int gbx_sbm_ipc_export(gbx_sbm* h, int which, unsigned char* handle64);
+int gbx_sbm_ipc_import(gbx_sbm* h, int which, int rank, const unsigned char* handle64);
+/* Device buffers owned by the caller that the collectives run on: totals (info[4] doubles) and theta
+ * (world * c doubles, indexed by global vertex id; rank r's update_theta writes [r*c, ...)). */
+int gbx_sbm_part_set_buffers(gbx_sbm* h, void* totals_dev, void* theta_dev);
+int gbx_sbm_step(gbx_sbm* h, int step, int arg);
+int gbx_sbm_read_residual(gbx_sbm* h, double* bpconv);
+
 #ifdef __cplusplus
 }
 #endif

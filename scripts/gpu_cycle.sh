@@ -12,6 +12,7 @@ prof_sweep) $B --steps 3 --warmup 3 > gpurun_out/plain.log 2>&1 && ncu --set ful
 prof_mstep) $B --steps 3 --warmup 3 > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:sbm_mstep_kernel -s 3 -c 1 -o gpurun_out/prof_mstep -f $B --steps 3 --warmup 3 > gpurun_out/ncu_mstep.log 2>&1; echo "prof_mstep rc=$?" ;;
 fullbench) python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo "fullbench rc=$?"; python scripts/show_bench.py gpurun_out/bench_full.json; tail -3 gpurun_out/bench_full.err ;;
 refbench) python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "refbench rc=$?"; cut -c1-400 gpurun_out/bench_ref.json ;;
+part) python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29517 tests/dist_check_part.py > gpurun_out/part.log 2>&1; echo "part rc=$?"; grep -v 'OMP_NUM_THREADS\|^\*\*\*\*\|^frame\|^$' gpurun_out/part.log | head -40 ;;
 smoke) python -c "import __graft_entry__ as g; g.smoke()" ;;
 esac
 done
