@@ -50,6 +50,15 @@ def parse_args():
     ap.add_argument("--dc", type=int, default=1)
     ap.add_argument("--cpu-n", type=int, default=0, help="vertices of the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="independent", choices=["independent", "partitioned"],
+                    help="N > 1: one independent graph per GPU (default; a partitioned leg is reported beside it), or "
+                         "ONE graph vertex-partitioned over the GPUs as the headline")
+    ap.add_argument("--part-n", type=int, default=0, help="vertices of the partitioned graph (0 = gpus * n)")
+    ap.add_argument("--part-deg", type=float, default=0.0, help="average degree of the partitioned graph (0 = deg)")
+    ap.add_argument("--part-shuffle", type=int, default=1,
+                    help="1: random vertex numbering (a contiguous partition cuts (P-1)/P of the links); "
+                         "0: vertices numbered group by group (the partition follows the planted groups)")
+    ap.add_argument("--no-partitioned-leg", action="store_true")
     return ap.parse_args()
 
 
@@ -165,6 +174,66 @@ def run_reference(a):
 
 
 # ------------------------------------------------------------------------------------------------
+def run_partitioned(a, torch, dist, world, rank, local):
+    """ONE graph, vertex-partitioned over the ranks (BASELINE.json configs[3]): every sweep stores the messages for
+    vertices of other ranks into their HBM over NVLink; totals all-reduced, theta all-gathered (NCCL) per iteration."""
+    from graphbix_b200.engine_dist import PartEngine
+    from graphbix_b200.synth import planted_partition_device
+    dev = torch.device("cuda", local)
+    n = a.part_n or world * a.n
+    deg = a.part_deg or a.deg
+    t0 = time.perf_counter()
+    if rank == 0:
+        links, _ = planted_partition_device(n, a.q, deg, a.eps, seed=4242, device=dev, shuffle=bool(a.part_shuffle))
+        kk = torch.tensor([links.shape[1]], dtype=torch.int64, device=dev)
+    else:
+        kk = torch.zeros(1, dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(kk, 0)
+    K = int(kk.item())
+    if rank != 0:
+        links = torch.empty((2, K), dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(links, 0)
+    torch.cuda.synchronize()
+    chunk = (n + world - 1) // world
+    cut = float((((links[0] - 1) // chunk) != ((links[1] - 1) // chunk)).double().mean().item())
+    t_gen = time.perf_counter() - t0
+    torch.cuda.empty_cache()
+    t0 = time.perf_counter()
+    eng = PartEngine(n, links, a.q)
+    del links
+    torch.cuda.empty_cache()
+    t_build = time.perf_counter() - t0
+    eng.set_options(degreecorrection=a.dc, priorlearning=1, learningrate=0.3, itrmax=a.steps)
+    gr0 = np.ones(a.q) / a.q
+    C0 = 20 * np.eye(a.q) + 0.01 * np.ones((a.q, a.q))
+    eng.init(gr0, C0, None, seed=99)
+    eng.iterate(a.warmup)
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    eng.iterate(a.steps)
+    ev1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    resid = eng.residual()
+    slots = eng.K
+    eng.close()
+    return {"value": K * a.steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / a.steps, "n_vertices": n,
+            "avg_degree": deg, "directed_edges": K, "directed_edges_rank0": slots, "cut_fraction": cut,
+            "vertex_numbering": "random" if a.part_shuffle else "by planted group",
+            "generate_s": t_gen, "build_s": t_build, "residual_after": resid,
+            "what": ("one graph vertex-partitioned over the GPUs: peer stores of boundary messages over NVLink inside "
+                     "the sweep kernel, NCCL all-reduce of the totals and all-gather of theta per iteration")}
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -177,8 +246,10 @@ def run_ours(a):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for --impl ours)")
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world > 1 or a.mode == "partitioned":
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29541")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), rank=rank, world_size=world)
 
     def barrier():
         if world > 1:
@@ -252,6 +323,9 @@ def run_ours(a):
     e2e_value = world * K * a.steps / t_e2e
     peak, peak_src = measured_peak_gbs()
     achieved = sweep_bytes / (sweep_ms * 1e-3) / 1e9
+    part = None
+    if (world > 1 and not a.no_partitioned_leg) or a.mode == "partitioned":
+        part = run_partitioned(a, torch, dist, world, rank, local)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -270,13 +344,20 @@ def run_ours(a):
                              "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                              "peak_source": peak_src, "ms_per_launch": sweep_ms, "algorithmic_bytes": sweep_bytes,
                              "sweep_updates_per_sec": K / (sweep_ms * 1e-3)}}
+        if part is not None:
+            line["partitioned"] = part
+            if a.mode == "partitioned":
+                line["independent"] = {"value": value, "ms_per_step": ms / a.steps}
+                line["value"], line["ms_per_step"] = part["value"], part["ms_per_step"]
+                line["scaling"] = "weak" if part["n_vertices"] == world * a.n else "strong"
+                line["config"]["parallelism"] = f"one graph of {part['n_vertices']} vertices partitioned over {world} GPU(s)"
         if not a.no_cpu_baseline and world == 1:
             try:
                 line["cpu_baseline"], _ = cpu_reference_run(a, 2, 1)
             except Exception as e:  # the baseline is reported, never required
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
         print(json.dumps(line))
-    if world > 1:
+    if dist.is_initialized():
         dist.destroy_process_group()
 
 

@@ -83,7 +83,7 @@ __global__ void k_slice(const int* __restrict__ gcol, const int* __restrict__ gr
     const int owner = (int)(j / chunk);
     col[e] = j;
     erow[e] = gerow[ge];
-    rev[e] = (owner << REV_SHIFT) | (int)(grev[ge] - pb.sbeg[owner]);
+    rev[e] = (int)(((unsigned)owner << REV_SHIFT) | (unsigned)(grev[ge] - pb.sbeg[owner]));
   }
 }
 
@@ -121,7 +121,19 @@ int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* 
   GBX_T(g_erow, K);
   GBX_C(cudaMalloc((void**)&h->slot_of_link, std::max<size_t>((size_t)K, 1) * sizeof(int)));
   h->dev_bytes += (int64_t)K * sizeof(int);
-  GBX_T(d_links, 2 * K);
+  // `links` may already live on this device (a partitioned run whose edge list was generated or received there)
+  const int64_t* links = nullptr;
+  {
+    cudaPointerAttributes at;
+    if (links_host && cudaPointerGetAttributes(&at, links_host) == cudaSuccess && at.type == cudaMemoryTypeDevice &&
+        at.device == h->device)
+      links = links_host;
+    cudaGetLastError();
+  }
+  if (!links) {
+    GBX_T(d_links, 2 * K);
+    links = d_links;
+  }
   GBX_T(keys, K);
   GBX_T(keys2, K);
   GBX_T(vals, K);
@@ -129,10 +141,11 @@ int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* 
   GBX_T(deg, n + 1);
   GBX_T(err, 1);
   const int grid = h->num_sms * 8;
-  GBX_C(cudaMemcpyAsync(d_links, links_host, (size_t)2 * K * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  if (links == d_links)
+    GBX_C(cudaMemcpyAsync(d_links, links_host, (size_t)2 * K * sizeof(int64_t), cudaMemcpyDefault, st));
   GBX_C(cudaMemsetAsync(deg, 0, (size_t)(n + 1) * sizeof(int), st));
   GBX_C(cudaMemsetAsync(err, 0, sizeof(int), st));
-  if (K > 0) k_keys<<<grid, 256, 0, st>>>(d_links, K, n, keys, vals, deg, err);
+  if (K > 0) k_keys<<<grid, 256, 0, st>>>(links, K, n, keys, vals, deg, err);
   size_t tb1 = 0, tb2 = 0;
   int bits = 32;
   while ((1ll << (bits - 32)) < n && bits < 64) ++bits;
@@ -154,6 +167,9 @@ int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* 
   GBX_C(cudaMemcpyAsync(rowptr_global->data(), g_rowptr, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
   GBX_C(cudaStreamSynchronize(st));
   GBX_C(cudaGetLastError());
+  // the sort workspace is the peak of the build: give it back before the per-rank arrays are allocated
+  cudaFree(d_links); cudaFree(keys); cudaFree(keys2); cudaFree(vals); cudaFree(vals2); cudaFree(deg); cudaFree(tmp);
+  d_links = nullptr; keys = keys2 = nullptr; vals = vals2 = deg = nullptr; tmp = nullptr;
   if (herr & ERR_RANGE) { last_error() = "links: vertex id out of 1..n"; return fail(GBX_ERR_INVALID); }
   if (herr & ERR_SELF) { last_error() = "links: self loop (run simplegraph first)"; return fail(GBX_ERR_INVALID); }
   if (herr & ERR_DUP) { last_error() = "links: duplicate link (run simplegraph first)"; return fail(GBX_ERR_INVALID); }
@@ -176,7 +192,7 @@ int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* 
   h->K = h->sbeg_all[h->rank + 1] - h->sbeg;
   for (int r = 0; r < h->world; ++r)
     if (h->sbeg_all[r + 1] - h->sbeg_all[r] > (long long)REV_MASK) {
-      last_error() = "too many edge slots on one rank (limit 2^28)";
+      last_error() = "too many edge slots on one rank (limit 2^29)";
       return fail(GBX_ERR_INVALID);
     }
   auto keep = [&](void** p, size_t bytes) -> cudaError_t {

@@ -41,7 +41,7 @@ struct SbmState {
 
 constexpr int PSTRIDE = 4 * MAXQ + 4;
 constexpr int MAXPEER = 8;                       // ranks of one partitioned run (one NVLink domain)
-constexpr int REV_SHIFT = 28;                    // rev[e] = owner << 28 | slot in the owner's buffer
+constexpr int REV_SHIFT = 29;                    // rev[e] = owner << 29 | slot in the owner's buffer (3 + 29 bits)
 constexpr int REV_MASK = (1 << REV_SHIFT) - 1;
 constexpr int TOT_MAX = 4 + 4 * MAXQ + MAXQ * MAXQ;  // doubles in a totals vector  // per-CTA partial row of the vertex kernels
 enum { MODE_SWEEP = 0, MODE_MARGINAL = 1, MODE_LOGZ = 2 };

@@ -86,27 +86,36 @@ __device__ __forceinline__ double fast_rcp(double x) {
   r = fma(r, e, r);
   return r;
 }
+// The QP lanes that share a vertex.  Groups of one warp may sit in different branches (plain product vs exponent-
+// tracked product, by degree), so group shuffles name only their own lanes.
+__device__ __forceinline__ unsigned group_mask() {
+  if constexpr (QP >= 32) return 0xffffffffu;
+  else return ((1u << QP) - 1u) << ((threadIdx.x & 31) & ~(QP - 1));
+}
 template <typename T>
 __device__ __forceinline__ T group_max(T x) {
+  const unsigned gm = group_mask();
 #pragma unroll
   for (int o = QP / 2; o > 0; o >>= 1) {
-    const T y = __shfl_xor_sync(0xffffffffu, x, o);
+    const T y = __shfl_xor_sync(gm, x, o);
     x = (y > x) ? y : x;
   }
   return x;
 }
 template <typename T>
 __device__ __forceinline__ T group_min(T x) {
+  const unsigned gm = group_mask();
 #pragma unroll
   for (int o = QP / 2; o > 0; o >>= 1) {
-    const T y = __shfl_xor_sync(0xffffffffu, x, o);
+    const T y = __shfl_xor_sync(gm, x, o);
     x = (y < x) ? y : x;
   }
   return x;
 }
 __device__ __forceinline__ double group_sum(double x) {
+  const unsigned gm = group_mask();
 #pragma unroll
-  for (int o = QP / 2; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  for (int o = QP / 2; o > 0; o >>= 1) x += __shfl_xor_sync(gm, x, o);
   return x;
 }
 
@@ -346,7 +355,7 @@ __device__ __forceinline__ void vertex_finish(const VertexArgs& a, bool valid, i
     if (valid && t == 0) acc.logz += log(s) + (double)K * LN2 + pr.xmax;
   } else {
     double w = u;
-    const unsigned low = group_bits(__ballot_sync(0xffffffffu, tl && (u < pow2c(fn + 1))));
+    const unsigned low = group_bits(__ballot_sync(group_mask(), tl && (u < pow2c(fn + 1))));
     if (low) {  // rare: a component is at or below the clamp floor
       const double fl = scale2(exp2(pr.ffrac), fn);
       w = (u < fl) ? fl : u;
@@ -356,7 +365,7 @@ __device__ __forceinline__ void vertex_finish(const VertexArgs& a, bool valid, i
     double res = 0.0;
     if constexpr (MODE == MODE_SWEEP) res = group_sum(tl ? fabs(p - old) : 0.0);
     const double pm = group_max(tl ? p : -1.0);
-    const unsigned eq = group_bits(__ballot_sync(0xffffffffu, tl && (p == pm)));
+    const unsigned eq = group_bits(__ballot_sync(group_mask(), tl && (p == pm)));
     if (valid) {
       if (tl) {
         a.PSI[(size_t)gv * Q + t] = p;

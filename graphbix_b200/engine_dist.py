@@ -36,13 +36,23 @@ class PartEngine:
         self.local = int(os.environ.get("LOCAL_RANK", self.rank))
         torch.cuda.set_device(self.local)
         self.model = model
-        links = np.asarray(links)
-        self.n_global, self.q, self.K_global = int(Ntot), int(B), int(links.shape[0])
-        colmajor = np.asfortranarray(links, dtype=np.int64)
+        self._debug = bool(int(os.environ.get("GBX_PART_SYNC", "0")))   # synchronise after every step (debugging)
+        if torch.is_tensor(links):
+            # edge list already on this GPU: a (2, K) int64 tensor = the K x 2 `links` matrix in column-major order
+            assert links.is_cuda and links.dtype == torch.int64 and links.dim() == 2 and links.shape[0] == 2
+            links = links.contiguous()
+            self.K_global = int(links.shape[1])
+            ptr = C.cast(C.c_void_p(links.data_ptr()), C.POINTER(C.c_int64))
+            torch.cuda.synchronize()
+        else:
+            links = np.asarray(links)
+            self.K_global = int(links.shape[0])
+            colmajor = np.asfortranarray(links, dtype=np.int64)
+            ptr = colmajor.ctypes.data_as(C.POINTER(C.c_int64))
+        self.n_global, self.q = int(Ntot), int(B)
         create = self.lib.gbx_sbm_create_part if model == "sbm" else self.lib.gbx_mod_create_part
         self._h = C.c_void_p()
-        check(create(C.byref(self._h), self.local, self.n_global, self.K_global,
-                     colmajor.ctypes.data_as(C.POINTER(C.c_int64)), self.q, self.rank, self.world))
+        check(create(C.byref(self._h), self.local, self.n_global, self.K_global, ptr, self.q, self.rank, self.world))
         info = (C.c_int64 * 8)()
         check(self.lib.gbx_sbm_part_info(self._h, info))
         self.vbeg, self.n, self.sbeg, self.K, self.tot_len, self.chunk = (int(info[i]) for i in range(6))
@@ -86,12 +96,21 @@ class PartEngine:
         fn = self.lib.gbx_sbm_set_options if self.model == "sbm" else self.lib.gbx_mod_set_options
         check(fn(self._h, C.byref(self.opt)))
 
+    def _sync(self, what):
+        if self._debug:
+            try:
+                self.torch.cuda.synchronize()
+            except Exception as e:
+                raise RuntimeError(f"rank {self.rank}: device error after {what}: {e}") from e
+
     def _step(self, step, arg=0):
         check(self.lib.gbx_sbm_step(self._h, step, arg))
+        self._sync(f"gbx_sbm_step({step}, {arg})")
 
     def _allreduce(self, count=None):
         t = self.totals if count is None else self.totals[:count]
         self.dist.all_reduce(t)
+        self._sync("all_reduce")
 
     def _pass(self, mode):
         self._step(STEP_VERTEX_PASS, mode)
@@ -105,7 +124,7 @@ class PartEngine:
 
     def init(self, gr, Crs=None, psicav=None, seed: int = 0):
         gr = _f64(gr, (self.q,))
-        psicav = _f64(psicav, (self.K_global, self.q))
+        psicav = _f64(psicav, (self.K_global, self.q))   # None: drawn on the device from `seed` (same on every rank)
         self.theta.fill_(1.0)
         if self.model == "sbm":
             Crs = _f64(Crs, (self.q, self.q))
@@ -126,6 +145,7 @@ class PartEngine:
                 self._step(STEP_THETA_APPLY)
                 mine = self.theta[r * c:(r + 1) * c].clone()
                 self.dist.all_gather_into_tensor(self.theta, mine)
+                self._sync("all_gather(theta)")
                 self._step(STEP_ESCALE)
             self._step(STEP_COUNT_ITERATION)
 

@@ -68,3 +68,56 @@ def random_messages(n_links: int, q: int, seed: int = 0) -> np.ndarray:
     rng = np.random.default_rng(seed)
     m = rng.random((n_links, q))
     return m / m.sum(axis=1, keepdims=True)
+
+
+def planted_partition_device(n: int, q: int, avg_degree: float, epsilon: float = 0.1, seed: int = 0,
+                             device="cuda", shuffle: bool = False):
+    """The same ensemble as `planted_partition`, drawn with torch on a GPU for graphs too large to generate on the
+    host in reasonable time (N = 50M, degree 20: 10^9 directed links).  The number of edge draws is fixed at
+    n * avg_degree / 2 (instead of Poisson counts per block pair) and each draw is within-group with probability
+    1 / (1 + (q-1) epsilon).  `shuffle` renumbers the vertices at random, so that a contiguous vertex partition cuts
+    (P-1)/P of the links (worst case) instead of following the planted groups.
+
+    Returns (links_cm, labels): links_cm is a (2, K) int64 CUDA tensor = the K x 2 `links` matrix in column-major
+    order (1-based, both directions, no self loops or multi-edges); labels is an (n,) int64 CUDA tensor."""
+    import torch
+    dev = torch.device(device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(int(seed))
+    m = int(n * avg_degree / 2)
+    p_in = 1.0 / (1.0 + (q - 1) * epsilon)
+    u = torch.randint(0, n, (m,), generator=g, device=dev, dtype=torch.int64)
+    gv = u * q // n
+    if q > 1:
+        other = torch.rand(m, generator=g, device=dev) >= p_in
+        shift = torch.randint(1, q, (m,), generator=g, device=dev, dtype=torch.int64)
+        gv = torch.where(other, (gv + shift) % q, gv)
+        del other, shift
+    start = (gv * n + q - 1) // q            # first vertex with label gv under labels = i * q // n
+    size = ((gv + 1) * n + q - 1) // q - start
+    del gv
+    v = start + (torch.rand(m, generator=g, device=dev, dtype=torch.float64) * size).to(torch.int64).clamp_(max=n)
+    v = torch.minimum(v, start + size - 1)
+    del start, size
+    keep = u != v
+    lo, hi = torch.minimum(u, v)[keep], torch.maximum(u, v)[keep]
+    del u, v, keep
+    key = torch.unique(lo * n + hi)
+    del lo, hi
+    lo, hi = key // n, key % n
+    del key
+    labels = torch.arange(n, device=dev, dtype=torch.int64) * q // n
+    if shuffle:
+        perm = torch.randperm(n, generator=g, device=dev)
+        lo, hi = perm[lo], perm[hi]
+        newlab = torch.empty_like(labels)
+        newlab[perm] = labels
+        labels = newlab
+        del perm
+    E = lo.numel()
+    links = torch.empty((2, 2 * E), dtype=torch.int64, device=dev)
+    links[0, :E] = lo + 1
+    links[1, :E] = hi + 1
+    links[0, E:] = hi + 1
+    links[1, E:] = lo + 1
+    return links, labels

@@ -164,6 +164,8 @@ int64_t gbx_mod_launch_count(const gbx_mod* h);
  * exchanged once with gbx_sbm_ipc_*); the only per-iteration collectives are the all-reduce of the totals vector
  * and, with degree correction, the all-gather of theta -- issued by the host (torch.distributed / NCCL) between
  * gbx_sbm_step calls.  graphbix_b200/engine_dist.py is the reference driver.  gbx_mod handles work the same way.
+ * Every rank passes the same `links`; it may be a host pointer or a pointer into this device's memory (an edge list
+ * generated on, or broadcast to, the GPU is used in place).  At most 2^29 directed links per rank.
  * ------------------------------------------------------------------------------------------------ */
 enum {
   GBX_STEP_PREPARE = 0,          /* arg bit 0: h = 0 (initial marginals); bit 1: gr = update_gr(PSI) first   */

@@ -98,3 +98,26 @@ def test_clamp_regime(gpu_required):
         eng.iterate(1)
         np.testing.assert_allclose(eng.state()["PSI"], ref.PSI, rtol=0, atol=1e-12)
         np.testing.assert_allclose(eng.messages(), ref.messages_in_link_order(), rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("q", [2, 3, 8])
+@pytest.mark.parametrize("log2c", [20, 30, 45])
+def test_mixed_plain_and_exponent_tracked_products(gpu_required, q, log2c):
+    """The aggregation multiplies a vertex's edge factors directly when degree <= 900 / max|log2 factor| and tracks
+    exponents otherwise.  With affinities around 2^log2c and degrees spread over 10..55 both kinds of vertex share
+    warps (lanes of one warp in different branches)."""
+    n, links, psi0, _ = planted_case(700, q, 30.0, 0.2, seed=40 + q)
+    deg = np.bincount(links[:, 0])
+    assert deg.min() < 900 / log2c < deg.max() or log2c == 20
+    gr0 = np.ones(q) / q
+    C0 = (2.0 ** log2c) * np.eye(q) + 1.0
+    from graphbix_b200.engine import SbmEngine
+    ref = SyncSBM(n, links, q, gr0, C0, psi0, dc=False, prior=True, lr=0.0, maxCrs=2.0 ** 60)
+    eng = SbmEngine(n, links, q)
+    eng.set_options(degreecorrection=0, priorlearning=1, learningrate=0.0, maxCrs=2.0 ** 60)
+    eng.init(gr0, C0, psi0)
+    for it in range(4):
+        ref.iterate()
+        eng.iterate(1)
+        np.testing.assert_allclose(eng.state()["PSI"], ref.PSI, rtol=0, atol=1e-12, err_msg=f"PSI it={it}")
+        np.testing.assert_allclose(eng.messages(), ref.messages_in_link_order(), rtol=0, atol=1e-12)
