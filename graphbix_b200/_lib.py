@@ -92,12 +92,13 @@ SIGNATURES = {
     "gbx_sbm_ipc_export": (C.c_int, [_P, C.c_int, C.POINTER(C.c_ubyte)]),
     "gbx_sbm_ipc_import": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]),
     "gbx_sbm_part_set_buffers": (C.c_int, [_P, _P, _P]),
+    "gbx_sbm_part_set_exchange": (C.c_int, [_P, C.c_int]),
     "gbx_sbm_step": (C.c_int, [_P, C.c_int, C.c_int]),
     "gbx_sbm_read_residual": (C.c_int, [_P, _D]),
 }
 
 STEP_PREPARE, STEP_VERTEX_PASS, STEP_LOCAL_TOTALS, STEP_APPLY_TOTALS, STEP_THETA_LOCAL, STEP_THETA_APPLY, \
-    STEP_ESCALE, STEP_FE_LOCAL, STEP_FE_APPLY, STEP_FE_FINAL, STEP_COUNT_ITERATION = range(11)
+    STEP_ESCALE, STEP_FE_LOCAL, STEP_FE_APPLY, STEP_FE_FINAL, STEP_COUNT_ITERATION, STEP_UNPACK = range(12)
 MODE_SWEEP, MODE_MARGINAL, MODE_LOGZ = 0, 1, 2
 
 _lib = None

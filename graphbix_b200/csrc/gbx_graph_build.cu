@@ -92,7 +92,7 @@ __global__ void k_slice(const int* __restrict__ gcol, const int* __restrict__ gr
 // Builds the global structure on the device, then keeps this rank's slice in the handle: h->rowptr (local, rebased),
 // h->col / h->erow (global vertex ids), h->rev (packed owner/slot), h->slot_of_link (global slot of every link) and
 // the partition bases.  rowptr_global receives the global row pointers.  Sets h->n, h->K, h->vbeg, h->sbeg.
-int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* rowptr_global) {
+int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* rowptr_global, GlobalGraph* keep_global) {
   const long long n = h->n_global, K = h->K_global;
   cudaStream_t st = h->stream;
   int *g_rowptr = nullptr, *g_col = nullptr, *g_rev = nullptr, *g_erow = nullptr;
@@ -211,10 +211,195 @@ int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* 
     GBX_C(cudaStreamSynchronize(st));
   }
   GBX_C(cudaGetLastError());
+  if (keep_global && h->world > 1) {  // the exchange plan (below) reads the global columns and reverse slots
+    keep_global->col = g_col;
+    keep_global->rev = g_rev;
+    g_col = g_rev = nullptr;
+  }
   cleanup();
   h->launches += 5;
   return GBX_OK;
 #undef GBX_T
+#undef GBX_C
+}
+
+void free_global(GlobalGraph* g) {
+  if (!g) return;
+  cudaFree(g->col);
+  cudaFree(g->rev);
+  g->col = g->rev = nullptr;
+}
+
+// ---- plan of the packed boundary exchange (see gbx_sbm_internal.h) -------------------------------------------------
+namespace {
+
+struct ColOwnedBy {  // local slot e: is its column (the vertex the new message goes to) owned by `owner`?
+  const int* col;
+  long long chunk;
+  int owner;
+  __device__ bool operator()(int e) const { return col[e] / chunk == owner; }
+};
+struct IncomingSlot {  // global slot ge outside my rows whose column is mine: its message lands in one of my rows
+  const int* gcol;
+  long long chunk, my_beg, my_end;
+  int me;
+  __device__ bool operator()(int ge) const { return (ge < my_beg || ge >= my_end) && gcol[ge] / chunk == me; }
+};
+
+__global__ void k_set_rev_pack(const int* __restrict__ sel, long long cnt, int owner, int* rev_pack) {
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < cnt; k += (long long)gridDim.x * blockDim.x)
+    rev_pack[sel[k]] = (int)(((unsigned)owner << REV_SHIFT) | (unsigned)k);
+}
+__global__ void k_unpack_slots(const int* __restrict__ selg, long long cnt, const int* __restrict__ grev, long long sbeg_me,
+                               int* unpack_slot) {
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < cnt; k += (long long)gridDim.x * blockDim.x)
+    unpack_slot[k] = (int)(grev[selg[k]] - sbeg_me);
+}
+struct Bounds {
+  long long b[MAXPEER + 2];
+  int nb;
+};
+// out[g][o] = number of slots in [b[g], b[g+1]) whose column is owned by o
+__global__ void k_group_owner_hist(const int* __restrict__ col, Bounds bd, long long chunk, unsigned long long* out) {
+  __shared__ unsigned int sh[(MAXPEER + 1) * MAXPEER];
+  for (int i = threadIdx.x; i < (MAXPEER + 1) * MAXPEER; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const long long n = bd.b[bd.nb];
+  for (long long e = bd.b[0] + (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    int g = 0;
+    while (g + 1 < bd.nb && e >= bd.b[g + 1]) ++g;
+    atomicAdd(&sh[g * MAXPEER + (int)(col[e] / chunk)], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (MAXPEER + 1) * MAXPEER; i += blockDim.x)
+    if (sh[i]) atomicAdd(&out[i], (unsigned long long)sh[i]);
+}
+
+}  // namespace
+
+int build_exchange_plan(gbx_sbm* h, const GlobalGraph& g, const std::vector<int4>& tiles) {
+  if (h->world <= 1) return GBX_OK;
+  const long long n = h->n_global, chunk = (n + h->world - 1) / h->world;
+  const long long Kl = h->K, Kg = h->K_global;
+  const int me = h->rank, P = h->world;
+  cudaStream_t st = h->stream;
+  int *sel = nullptr, *dnum = nullptr;
+  unsigned long long* dh = nullptr;
+  void* tmp = nullptr;
+  auto cleanup = [&]() { cudaFree(sel); cudaFree(dnum); cudaFree(dh); cudaFree(tmp); };
+  auto fail = [&](int rc) { cleanup(); return rc; };
+#define GBX_C(expr)                                                                      \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      last_error() = std::string(#expr) + " -> " + cudaGetErrorString(_e);               \
+      return fail(GBX_ERR_CUDA);                                                         \
+    }                                                                                    \
+  } while (0)
+  const int grid = h->num_sms * 8;
+  const size_t HB = (size_t)(MAXPEER + 1) * MAXPEER;
+  GBX_C(cudaMalloc((void**)&dh, HB * sizeof(unsigned long long)));
+  GBX_C(cudaMalloc((void**)&dnum, sizeof(int)));
+  std::vector<unsigned long long> hh(HB);
+  // counts between every pair of ranks: cnt[s][o] = slots in rows of s whose column is owned by o
+  long long cnt[MAXPEER][MAXPEER] = {};
+  {
+    Bounds bd;
+    bd.nb = P;
+    for (int r = 0; r <= P; ++r) bd.b[r] = h->sbeg_all[r];
+    GBX_C(cudaMemsetAsync(dh, 0, HB * sizeof(unsigned long long), st));
+    if (Kg > 0) k_group_owner_hist<<<grid, 256, 0, st>>>(g.col, bd, chunk, dh);
+    GBX_C(cudaMemcpyAsync(hh.data(), dh, HB * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    GBX_C(cudaStreamSynchronize(st));
+    for (int s = 0; s < P; ++s)
+      for (int o = 0; o < P; ++o) cnt[s][o] = (long long)hh[(size_t)s * MAXPEER + o];
+  }
+  h->send_off[0] = 0;
+  for (int o = 0; o < P; ++o) h->send_off[o + 1] = h->send_off[o] + (o == me ? 0 : cnt[me][o]);
+  for (int o = P; o < MAXPEER; ++o) h->send_off[o + 1] = h->send_off[o];
+  h->send_total = h->send_off[P];
+  for (int o = 0; o < P; ++o) {
+    long long off = 0;
+    for (int s = 0; s < me; ++s)
+      if (s != o) off += cnt[s][o];
+    h->my_off_at[o] = off;
+  }
+  // pieces of the sweep: equal runs of tiles, at least one full grid each
+  const int ntiles = (int)tiles.size();
+  int nch = h->nchunks < 1 ? 1 : (h->nchunks > MAXCHUNK ? MAXCHUNK : h->nchunks);
+  while (nch > 1 && ntiles / nch < h->num_sms * 8) --nch;
+  h->nchunks = nch;
+  Bounds cb;
+  cb.nb = nch;
+  for (int c = 0; c <= nch; ++c) {
+    h->chunk_tile[c] = (int)((long long)ntiles * c / nch);
+    cb.b[c] = (c == 0) ? 0 : (c == nch ? Kl : (long long)tiles[(size_t)h->chunk_tile[c]].z);
+  }
+  {
+    GBX_C(cudaMemsetAsync(dh, 0, HB * sizeof(unsigned long long), st));
+    if (Kl > 0) k_group_owner_hist<<<grid, 256, 0, st>>>(h->col, cb, chunk, dh);
+    GBX_C(cudaMemcpyAsync(hh.data(), dh, HB * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    GBX_C(cudaStreamSynchronize(st));
+    for (int o = 0; o < MAXPEER; ++o) {
+      long long acc = 0;
+      for (int c = 0; c <= nch; ++c) {
+        h->chunk_send[c][o] = acc;
+        if (c < nch) acc += (long long)hh[(size_t)c * MAXPEER + o];
+      }
+    }
+  }
+  auto keep = [&](void** p, size_t bytes) -> cudaError_t {
+    h->dev_bytes += (int64_t)bytes;
+    return cudaMalloc(p, bytes ? bytes : 1);
+  };
+  const size_t rowb = (size_t)h->q * sizeof(double);
+  GBX_C(keep((void**)&h->rev_pack, (size_t)Kl * sizeof(int)));
+  GBX_C(keep((void**)&h->unpack_slot, (size_t)h->send_total * sizeof(int)));
+  GBX_C(keep((void**)&h->sendbuf, (size_t)h->send_total * rowb));
+  GBX_C(keep((void**)&h->recvbuf[0], (size_t)h->send_total * rowb));
+  GBX_C(keep((void**)&h->recvbuf[1], (size_t)h->send_total * rowb));
+  h->recvp[0][me] = h->recvbuf[0];
+  h->recvp[1][me] = h->recvbuf[1];
+  GBX_C(cudaMemcpyAsync(h->rev_pack, h->rev, (size_t)Kl * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  // send positions: the k-th local slot (in slot order) whose column belongs to o goes to row k of the run for o
+  long long maxsel = h->send_total;
+  for (int o = 0; o < P; ++o)
+    if (o != me) maxsel = std::max(maxsel, cnt[me][o]);
+  GBX_C(cudaMalloc((void**)&sel, std::max<size_t>((size_t)maxsel, 1) * sizeof(int)));
+  size_t tb = 0, tb2 = 0;
+  cub::CountingInputIterator<int> ids(0);
+  cub::DeviceSelect::If(nullptr, tb, ids, sel, dnum, (int)Kl, ColOwnedBy{h->col, chunk, 0}, st);
+  cub::DeviceSelect::If(nullptr, tb2, ids, sel, dnum, (int)Kg, IncomingSlot{g.col, chunk, h->sbeg, h->sbeg + Kl, me}, st);
+  tb = std::max(tb, tb2);
+  GBX_C(cudaMalloc(&tmp, tb ? tb : 1));
+  for (int o = 0; o < P; ++o) {
+    if (o == me || cnt[me][o] == 0) continue;
+    size_t t = tb;
+    GBX_C(cub::DeviceSelect::If(tmp, t, ids, sel, dnum, (int)Kl, ColOwnedBy{h->col, chunk, o}, st));
+    k_set_rev_pack<<<grid, 256, 0, st>>>(sel, cnt[me][o], o, h->rev_pack);
+  }
+  // receive side: rows arrive grouped by sender (ascending rank), each group in the sender's slot order; the global
+  // slots outside my rows whose column is mine, in slot order, are exactly that sequence
+  if (h->send_total > 0) {
+    size_t t = tb;
+    GBX_C(cub::DeviceSelect::If(tmp, t, ids, sel, dnum, (int)Kg, IncomingSlot{g.col, chunk, h->sbeg, h->sbeg + Kl, me}, st));
+    int got = 0;
+    GBX_C(cudaMemcpyAsync(&got, dnum, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GBX_C(cudaStreamSynchronize(st));
+    if ((long long)got != h->send_total) {
+      last_error() = "exchange plan: incoming and outgoing boundary counts differ (graph not symmetric?)";
+      return fail(GBX_ERR_INVALID);
+    }
+    k_unpack_slots<<<grid, 256, 0, st>>>(sel, h->send_total, g.rev, h->sbeg, h->unpack_slot);
+  }
+  GBX_C(cudaStreamSynchronize(st));
+  GBX_C(cudaGetLastError());
+  GBX_C(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (int c = 0; c < MAXCHUNK; ++c) GBX_C(cudaEventCreateWithFlags(&h->ev_piece[c], cudaEventDisableTiming));
+  GBX_C(cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming));
+  cleanup();
+  h->launches += 2 + P;
+  return GBX_OK;
 #undef GBX_C
 }
 

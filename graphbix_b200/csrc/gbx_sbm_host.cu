@@ -45,7 +45,9 @@ static const SbmOps* ops_for(int model, int q) {
 }  // namespace gbx
 
 namespace gbx {
-int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* rowptr_host);
+int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* rowptr_host, GlobalGraph* keep_global);
+void free_global(GlobalGraph* g);
+int build_exchange_plan(gbx_sbm* h, const GlobalGraph& g, const std::vector<int4>& tiles);
 }
 
 using namespace gbx;
@@ -198,6 +200,7 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
   h->ops = ops;
   std::vector<int> rowptr_g;   // global row pointers
   std::vector<int> rowptr;     // this rank's (rebased)
+  GlobalGraph gg;              // global columns / reverse slots, alive until the exchange plan is built
   {
     cudaDeviceProp prop;
     cudaError_t ce = cudaSetDevice(device);
@@ -213,7 +216,7 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
       return GBX_ERR_CUDA;
     }
     h->num_sms = prop.multiProcessorCount;
-    const int rcb = build_graph_device(h, links, &rowptr_g);
+    const int rcb = build_graph_device(h, links, &rowptr_g, &gg);
     if (rcb != GBX_OK) {
       const std::string keep = last_error();
       gbx_sbm_destroy(h);
@@ -252,6 +255,19 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
   }
 
   h->ntiles = (int)tiles.size();
+  if (world > 1) {
+    h->nchunks = 4;
+    if (const char* e = getenv("GBX_EXCHANGE_PIECES")) h->nchunks = atoi(e);
+    const int rcp = build_exchange_plan(h, gg, tiles);
+    free_global(&gg);
+    if (rcp != GBX_OK) {
+      const std::string keep = last_error();
+      gbx_sbm_destroy(h);
+      last_error() = keep;
+      return rcp;
+    }
+    h->exchange = 1;
+  }
   for (int64_t v = 0; v < h->n_global; ++v) h->max_degree = std::max(h->max_degree, rowptr_g[(size_t)v + 1] - rowptr_g[(size_t)v]);
   h->model = model;
   gbx_mod_default_options(&h->mopt);
@@ -306,7 +322,8 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
     h->grid_mstep = h->grid_vertex + h->nhubs;  // M-step statistics: one row per sweep CTA
     h->grid_fe = (int)std::min<int64_t>(eblocks, (int64_t)h->num_sms * 2);
     h->grid_theta = (int)std::min<int64_t>(std::max<int64_t>(1, (n + NT - 1) / NT), (int64_t)h->num_sms * 4);
-    GBX_TRY(dev_alloc(h, &h->part_vertex, (size_t)(h->grid_vertex + h->nhubs) * PSTRIDE));
+    h->grid_mstep = h->grid_vertex * h->nchunks + h->nhubs;  // one row per sweep CTA of every piece
+    GBX_TRY(dev_alloc(h, &h->part_vertex, (size_t)h->grid_mstep * PSTRIDE));
     GBX_TRY(dev_alloc(h, &h->part_mstep, (size_t)h->grid_mstep * q * q));
     GBX_TRY(dev_alloc(h, &h->part_theta, (size_t)h->grid_theta * MAXQ));
     GBX_TRY(dev_alloc(h, &h->part_fe, (size_t)h->grid_fe * 8));
@@ -332,8 +349,19 @@ int gbx_sbm_destroy(gbx_sbm* h) {
   if (!h) return GBX_OK;
   cudaSetDevice(h->device);
   for (int b = 0; b < 2; ++b)
-    for (int r = 0; r < MAXPEER; ++r)
+    for (int r = 0; r < MAXPEER; ++r) {
       if (h->ipc_open[b][r]) cudaIpcCloseMemHandle(h->msgp[b][r]);
+      if (h->ipc_open_recv[b][r]) cudaIpcCloseMemHandle(h->recvp[b][r]);
+    }
+  cudaFree(h->rev_pack);
+  cudaFree(h->unpack_slot);
+  cudaFree(h->sendbuf);
+  cudaFree(h->recvbuf[0]);
+  cudaFree(h->recvbuf[1]);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (int c = 0; c < MAXCHUNK; ++c)
+    if (h->ev_piece[c]) cudaEventDestroy(h->ev_piece[c]);
+  if (h->ev_copied) cudaEventDestroy(h->ev_copied);
   cudaFree(h->rowptr);
   cudaFree(h->col);
   cudaFree(h->rev);
@@ -756,25 +784,31 @@ int gbx_sbm_part_info(const gbx_sbm* h, int64_t* info) {
 }
 
 int gbx_sbm_ipc_export(gbx_sbm* h, int which, unsigned char* handle64) {
-  if (!h || !handle64 || which < 0 || which > 1) return fail_invalid("bad arguments");
+  if (!h || !handle64 || which < 0 || which > 3) return fail_invalid("bad arguments");
+  if (which >= 2 && !h->recvbuf[which - 2]) return fail_invalid("no receive buffers (single-rank handle)");
   GBX_TRY(set_device(h));
   cudaIpcMemHandle_t mh;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-  GBX_CUDA_TRY(cudaIpcGetMemHandle(&mh, h->msg[which]));
+  GBX_CUDA_TRY(cudaIpcGetMemHandle(&mh, which < 2 ? h->msg[which] : h->recvbuf[which - 2]));
   memcpy(handle64, &mh, 64);
   return GBX_OK;
 }
 
 int gbx_sbm_ipc_import(gbx_sbm* h, int which, int rank, const unsigned char* handle64) {
-  if (!h || !handle64 || which < 0 || which > 1 || rank < 0 || rank >= h->world) return fail_invalid("bad arguments");
+  if (!h || !handle64 || which < 0 || which > 3 || rank < 0 || rank >= h->world) return fail_invalid("bad arguments");
   if (rank == h->rank) return GBX_OK;
   GBX_TRY(set_device(h));
   cudaIpcMemHandle_t mh;
   memcpy(&mh, handle64, 64);
   void* p = nullptr;
   GBX_CUDA_TRY(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
-  h->msgp[which][rank] = (double*)p;
-  h->ipc_open[which][rank] = true;
+  if (which < 2) {
+    h->msgp[which][rank] = (double*)p;
+    h->ipc_open[which][rank] = true;
+  } else {
+    h->recvp[which - 2][rank] = (double*)p;
+    h->ipc_open_recv[which - 2][rank] = true;
+  }
   return GBX_OK;
 }
 
@@ -790,6 +824,15 @@ int gbx_sbm_part_set_buffers(gbx_sbm* h, void* totals_dev, void* theta_dev) {
     h->theta = (double*)theta_dev;
     h->theta_owned = false;
   }
+  return GBX_OK;
+}
+
+int gbx_sbm_part_set_exchange(gbx_sbm* h, int mode) {
+  if (!h) return fail_invalid("handle is NULL");
+  if (mode != 0 && mode != 1) return fail_invalid("exchange mode must be 0 (direct peer stores) or 1 (packed)");
+  if (mode == 1 && h->world > 1 && !h->rev_pack) return fail_invalid("no exchange plan");
+  if (h->pending_unpack) return fail_state();
+  h->exchange = h->world > 1 ? mode : 0;
   return GBX_OK;
 }
 
@@ -814,6 +857,7 @@ int gbx_sbm_step(gbx_sbm* h, int step, int arg) {
     case GBX_STEP_FE_APPLY: return op->fe_apply(h, arg);
     case GBX_STEP_FE_FINAL: return op->fe_final(h);
     case GBX_STEP_COUNT_ITERATION: h->itr++; return GBX_OK;
+    case GBX_STEP_UNPACK: return op->unpack(h);
     default: return fail_invalid("unknown step");
   }
 }

@@ -43,12 +43,19 @@ constexpr int PSTRIDE = 4 * MAXQ + 4;
 constexpr int MAXPEER = 8;                       // ranks of one partitioned run (one NVLink domain)
 constexpr int REV_SHIFT = 29;                    // rev[e] = owner << 29 | slot in the owner's buffer (3 + 29 bits)
 constexpr int REV_MASK = (1 << REV_SHIFT) - 1;
+constexpr int MAXCHUNK = 8;                      // a partitioned sweep is launched in <= 8 pieces so that copies overlap it
 constexpr int TOT_MAX = 4 + 4 * MAXQ + MAXQ * MAXQ;  // doubles in a totals vector  // per-CTA partial row of the vertex kernels
 enum { MODE_SWEEP = 0, MODE_MARGINAL = 1, MODE_LOGZ = 2 };
 
 constexpr int tile_vertices(int q) { return (q <= 8) ? TILE_V / 2 : TILE_V / 4; }
 
 struct SbmOps;
+
+// Device copies of the global columns / reverse slots, kept between the graph build and the exchange plan.
+struct GlobalGraph {
+  int* col = nullptr;
+  int* rev = nullptr;
+};
 
 }  // namespace gbx
 
@@ -96,6 +103,31 @@ struct gbx_sbm {
   int grid_vertex = 0, grid_mstep = 0, grid_theta = 0, grid_fe = 0;
   gbx::SbmState* h_state = nullptr;  // pinned mirror
   int itr = 0;
+  // ---- packed boundary exchange of a partitioned run (exchange == 1) -------------------------------------------
+  // The sweep stores a message for a row of rank o at the next position of this rank's send run for o (positions
+  // follow this rank's slot order, so the stores are nearly sequential); the runs are pushed to o's receive buffer
+  // by the copy engine while later pieces of the sweep run; after the all-reduce of the totals (the barrier that
+  // says every rank's copies have landed) o scatters the received rows into its message buffer.  Random 64-B peer
+  // stores reach 300-420 GB/s on NVLink 5, contiguous copies 700-770 GB/s (profiles/r01_p2p_probe.txt).
+  int exchange = 0;                    // 0: direct peer stores from the sweep, 1: pack + bulk copy + unpack
+  int* rev_pack = nullptr;             // rev[] with remote slots replaced by (owner, position in the send run)
+  double* sendbuf = nullptr;           // [send_total][q]
+  double* recvbuf[2] = {nullptr, nullptr};   // [send_total][q] each: one per sweep parity (run of rank s at recv_off[s])
+  double* recvp[2][gbx::MAXPEER] = {};       // every rank's receive buffers (peer-mapped)
+  bool ipc_open_recv[2][gbx::MAXPEER] = {};
+  int* unpack_slot = nullptr;          // [send_total]: local slot of every received row
+  int64_t send_total = 0;
+  int64_t send_off[gbx::MAXPEER + 1] = {0};  // start of the run for rank o in sendbuf, and of the run from o in recvbuf
+  int64_t my_off_at[gbx::MAXPEER] = {0};     // start of this rank's run in rank o's recvbuf
+  int nchunks = 1;
+  int chunk_tile[gbx::MAXCHUNK + 1] = {0};
+  int64_t chunk_send[gbx::MAXCHUNK + 1][gbx::MAXPEER] = {};  // rows of the run for o written by pieces < c
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_piece[gbx::MAXCHUNK] = {};
+  cudaEvent_t ev_copied = nullptr;
+  int sweep_rows = 0, sweep_row0 = 0;  // partial rows written by the last vertex pass (count, first row)
+  int xparity = 0;                     // receive buffer the next sweep pushes into
+  bool pending_unpack = false;         // the last sweep was packed and its rows have not been scattered yet
 };
 
 namespace gbx {
@@ -118,6 +150,7 @@ struct SbmOps {
   int (*assignment)(gbx_sbm* h, int* dev_block);
   int (*occupancy)(int variant, int* vertex_occ, int* mstep_occ);
   int (*init_model)(gbx_sbm* h);  // per-vertex prior-table rows of the initial state
+  int (*unpack)(gbx_sbm* h);      // packed exchange: received rows -> message buffer
 };
 
 }  // namespace gbx

@@ -86,36 +86,29 @@ __device__ __forceinline__ double fast_rcp(double x) {
   r = fma(r, e, r);
   return r;
 }
-// The QP lanes that share a vertex.  Groups of one warp may sit in different branches (plain product vs exponent-
-// tracked product, by degree), so group shuffles name only their own lanes.
-__device__ __forceinline__ unsigned group_mask() {
-  if constexpr (QP >= 32) return 0xffffffffu;
-  else return ((1u << QP) - 1u) << ((threadIdx.x & 31) & ~(QP - 1));
-}
+// Reductions over the QP lanes that share a vertex.  They name all 32 lanes, so every call site must be reached by
+// the whole warp (the aggregation stage keeps its branches warp-uniform with a vote for that reason).
 template <typename T>
 __device__ __forceinline__ T group_max(T x) {
-  const unsigned gm = group_mask();
 #pragma unroll
   for (int o = QP / 2; o > 0; o >>= 1) {
-    const T y = __shfl_xor_sync(gm, x, o);
+    const T y = __shfl_xor_sync(0xffffffffu, x, o);
     x = (y > x) ? y : x;
   }
   return x;
 }
 template <typename T>
 __device__ __forceinline__ T group_min(T x) {
-  const unsigned gm = group_mask();
 #pragma unroll
   for (int o = QP / 2; o > 0; o >>= 1) {
-    const T y = __shfl_xor_sync(gm, x, o);
+    const T y = __shfl_xor_sync(0xffffffffu, x, o);
     x = (y < x) ? y : x;
   }
   return x;
 }
 __device__ __forceinline__ double group_sum(double x) {
-  const unsigned gm = group_mask();
 #pragma unroll
-  for (int o = QP / 2; o > 0; o >>= 1) x += __shfl_xor_sync(gm, x, o);
+  for (int o = QP / 2; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
   return x;
 }
 
@@ -355,7 +348,7 @@ __device__ __forceinline__ void vertex_finish(const VertexArgs& a, bool valid, i
     if (valid && t == 0) acc.logz += log(s) + (double)K * LN2 + pr.xmax;
   } else {
     double w = u;
-    const unsigned low = group_bits(__ballot_sync(group_mask(), tl && (u < pow2c(fn + 1))));
+    const unsigned low = group_bits(__ballot_sync(0xffffffffu, tl && (u < pow2c(fn + 1))));
     if (low) {  // rare: a component is at or below the clamp floor
       const double fl = scale2(exp2(pr.ffrac), fn);
       w = (u < fl) ? fl : u;
@@ -365,7 +358,7 @@ __device__ __forceinline__ void vertex_finish(const VertexArgs& a, bool valid, i
     double res = 0.0;
     if constexpr (MODE == MODE_SWEEP) res = group_sum(tl ? fabs(p - old) : 0.0);
     const double pm = group_max(tl ? p : -1.0);
-    const unsigned eq = group_bits(__ballot_sync(group_mask(), tl && (p == pm)));
+    const unsigned eq = group_bits(__ballot_sync(0xffffffffu, tl && (p == pm)));
     if (valid) {
       if (tl) {
         a.PSI[(size_t)gv * Q + t] = p;
@@ -516,26 +509,43 @@ __device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// Stage everything tile `td` = (v0, nv, e0, ne) needs from HBM into one buffer, coalesced.  Message unit
-// g = i * NT + tid goes to row g / CH at a rotated position so that stage 1 (one thread per row) reads its row
-// without bank conflicts; the rotation does not depend on the round i, so the offset is a per-thread constant.
+// Stage everything tile `td` = (v0, nv, e0, ne) needs from HBM into one buffer, coalesced.  Every warp copies the
+// messages of its own 32 edge slots (lane l, round i: unit 32 i + l of the warp's 32 * CH units), because stage 3 of
+// a warp still reads them (M-step operands) when a faster warp is already staging the tile after next into the same
+// buffer: with warp-private rows that overwrite is ordered by the warp's own program order.  Units sit at a rotated
+// position inside their row so that stage 1 (one thread per row) reads without bank conflicts; for CH | 32 the
+// rotation does not depend on the round, so the offset is a per-thread constant.
 template <int MODE>
 __device__ __forceinline__ void stage_tile(const VertexArgs& a, const int4& td, char* buf) {
   const int tid = threadIdx.x;
   const int v0 = td.x, nv = td.y, e0 = td.z, ne = td.w;
   const char* src = reinterpret_cast<const char*>(a.cur) + (size_t)e0 * ROWB;
   const int nunits = ne * CH;
-  if constexpr (NT % CH == 0) {
-    const int row0 = tid / CH, c = tid % CH;
-    char* d = buf + StageBuf::psi_off + row0 * ROWB + swz_unit(row0, c) * CHB;
-    const char* g = src + (size_t)tid * CHB;
+  const int lane = tid & 31, wrow = tid & ~31;  // first row of this warp
+  if constexpr (32 % CH == 0) {
+    constexpr int RPR = 32 / CH;  // rows per round
+    const int row0 = wrow + lane / CH, c = lane % CH;
+    const int u0 = wrow * CH + lane;
+    const char* g = src + (size_t)u0 * CHB;
+    if constexpr (!SWZ || (RPR / SWZ_DIV) % CH == 0) {
+      char* d = buf + StageBuf::psi_off + row0 * ROWB + swz_unit(row0, c) * CHB;
 #pragma unroll
-    for (int i = 0; i < CH; ++i)
-      if (i * NT + tid < nunits) cp_async_unit(d + i * NT * CHB, g + (size_t)i * NT * CHB);
+      for (int i = 0; i < CH; ++i)
+        if (u0 + i * 32 < nunits) cp_async_unit(d + i * 32 * CHB, g + (size_t)i * 32 * CHB);
+    } else {
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        const int row = row0 + i * RPR;
+        if (u0 + i * 32 < nunits)
+          cp_async_unit(buf + StageBuf::psi_off + row * ROWB + swz_unit(row, c) * CHB, g + (size_t)i * 32 * CHB);
+      }
+    }
   } else {
-    for (int g = tid; g < nunits; g += NT) {
-      const int row = g / CH, c = g - row * CH;
-      cp_async_unit(buf + StageBuf::psi_off + row * ROWB + swz_unit(row, c) * CHB, src + (size_t)g * CHB);
+    for (int k = lane; k < 32 * CH; k += 32) {
+      const int u = wrow * CH + k;
+      if (u >= nunits) break;
+      const int row = u / CH, c = u - row * CH;
+      cp_async_unit(buf + StageBuf::psi_off + row * ROWB + swz_unit(row, c) * CHB, src + (size_t)u * CHB);
     }
   }
   if (tid < ne) {
@@ -660,7 +670,9 @@ __global__ void __launch_bounds__(NT, ((Q <= 8) ? 3 : 2) * (256 / NT)) sbm_verte
       const double* pe = &Tsm[e * QS + tt];
       double m1 = 1.0, m2 = 1.0;
       int K = 0;
-      if (e - b <= c_P.safe_deg) {
+      // Warp-uniform choice (the group reductions below use full-warp shuffles): both branches give bit-identical
+      // products, the second one only adds exact power-of-two rescaling.
+      if (!__any_sync(0xffffffffu, e - b > c_P.safe_deg)) {
         // the factors are bounded so that a product of this many cannot leave the double range: plain product
         for (; p + QS < pe; p += 2 * QS) {
           m1 *= p[0];
@@ -1350,21 +1362,103 @@ int launch_vertex_pass_t(gbx_sbm* h) {
     sbm_hub_kernel<MODE><<<h->nhubs, NT, 0, h->stream>>>(a, h->grid_vertex);
     h->launches++;
   }
+  h->sweep_rows = (h->ntiles > 0 ? h->grid_vertex : 0) + h->nhubs;
+  h->sweep_row0 = h->ntiles > 0 ? 0 : h->grid_vertex;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
 }
 
+// Partitioned sweep with the packed exchange: the messages for rows of rank o go to this rank's send run for o
+// (rev_pack holds the positions), hubs first, then the tiles in `nchunks` pieces; when a piece is done its part of
+// every run is pushed to the owner's receive buffer by the copy engine while the next piece computes.
+int launch_packed_sweep(gbx_sbm* h) {
+  VertexArgs a = vertex_args(h);
+  a.rev = h->rev_pack;
+  for (int o = 0; o < h->world; ++o)
+    if (o != h->rank) a.nxtp[o] = h->sendbuf + (size_t)h->send_off[o] * Q;
+  const int G = h->grid_vertex, NC = h->nchunks;
+  if (h->nhubs > 0) {
+    sbm_hub_kernel<MODE_SWEEP><<<h->nhubs, NT, 0, h->stream>>>(a, NC * G);
+    h->launches++;
+  }
+  const size_t rowb = (size_t)Q * sizeof(double);
+  double* const* dst = h->recvp[h->xparity];
+  for (int c = 0; c < NC; ++c) {
+    VertexArgs ac = a;
+    ac.tiles = a.tiles + h->chunk_tile[c];
+    ac.ntiles = h->chunk_tile[c + 1] - h->chunk_tile[c];
+    ac.partials = a.partials + (size_t)c * G * PSTRIDE;
+    ac.mpart = a.mpart + (size_t)c * G * Q * Q;
+    if (ac.ntiles > 0) {
+      sbm_vertex_kernel<MODE_SWEEP><<<G, NT, SweepSmem::total, h->stream>>>(ac);
+      h->launches++;
+    } else {
+      GBX_CUDA_TRY(cudaMemsetAsync(ac.partials, 0, (size_t)G * PSTRIDE * sizeof(double), h->stream));
+      GBX_CUDA_TRY(cudaMemsetAsync(ac.mpart, 0, (size_t)G * Q * Q * sizeof(double), h->stream));
+    }
+    GBX_CUDA_TRY(cudaEventRecord(h->ev_piece[c], h->stream));
+    GBX_CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_piece[c], 0));
+    for (int o = 0; o < h->world; ++o) {
+      if (o == h->rank) continue;
+      const long long b = h->chunk_send[c][o], e = h->chunk_send[c + 1][o];
+      if (e <= b) continue;
+      GBX_CUDA_TRY(cudaMemcpyAsync(dst[o] + (size_t)(h->my_off_at[o] + b) * Q,
+                                   h->sendbuf + (size_t)(h->send_off[o] + b) * Q, (size_t)(e - b) * rowb,
+                                   cudaMemcpyDeviceToDevice, h->copy_stream));
+    }
+  }
+  GBX_CUDA_TRY(cudaEventRecord(h->ev_copied, h->copy_stream));
+  GBX_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_copied, 0));  // the totals (and the all-reduce) follow the copies
+  h->sweep_rows = NC * G + h->nhubs;
+  h->sweep_row0 = 0;
+  h->pending_unpack = true;
+  GBX_CUDA_TRY(cudaGetLastError());
+  return GBX_OK;
+}
+
+// Rows received from the other ranks (parity of the last sweep) -> their slots of the (new) current message buffer.
+__global__ void k_unpack(const double* __restrict__ recv, const int* __restrict__ slot, long long rows, double* __restrict__ msg) {
+  constexpr int U = (Q % 2 == 0) ? Q / 2 : Q;  // 16-B units per row when the row is a whole number of them
+  const long long total = rows * U;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / U;
+    const int c = (int)(i - r * U);
+    const long long s = slot[r];
+    if constexpr (Q % 2 == 0)
+      reinterpret_cast<double2*>(msg)[s * U + c] = reinterpret_cast<const double2*>(recv)[i];
+    else
+      msg[s * U + c] = recv[i];
+  }
+}
+
+int op_unpack(gbx_sbm* h) {
+  if (!h->pending_unpack) return GBX_OK;
+  h->pending_unpack = false;
+  const int parity = h->xparity;
+  h->xparity ^= 1;
+  if (h->send_total > 0) {
+    // called after the sweep's buffer swap: h->cur is the buffer the sweep wrote
+    k_unpack<<<grid_for(h, h->send_total * ((Q % 2 == 0) ? Q / 2 : Q)), 256, 0, h->stream>>>(
+        h->recvbuf[parity], h->unpack_slot, (long long)h->send_total, h->msg[h->cur]);
+    h->launches++;
+    GBX_CUDA_TRY(cudaGetLastError());
+  }
+  return GBX_OK;
+}
+
 int op_vertex_pass(gbx_sbm* h, int mode) {
-  if (mode == MODE_SWEEP) return launch_vertex_pass_t<MODE_SWEEP>(h);
+  if (mode == MODE_SWEEP) {
+    const double damping = (MODEL == MODEL_MOD) ? h->mopt.damping : h->opt.damping;
+    if (h->world > 1 && h->exchange == 1 && damping == 1.0) return launch_packed_sweep(h);
+    return launch_vertex_pass_t<MODE_SWEEP>(h);
+  }
   if (mode == MODE_MARGINAL) return launch_vertex_pass_t<MODE_MARGINAL>(h);
   return launch_vertex_pass_t<MODE_LOGZ>(h);
 }
 
-int vertex_rows(const gbx_sbm* h) { return (h->ntiles > 0 ? h->grid_vertex : 0) + h->nhubs; }
-
 int op_local_totals(gbx_sbm* h, int mode) {
-  const size_t skip = h->ntiles > 0 ? 0 : (size_t)h->grid_vertex;
-  sbm_local_totals<<<1, 512, 0, h->stream>>>(h->part_vertex + skip * PSTRIDE, vertex_rows(h), h->part_mstep + skip * Q * Q,
+  const size_t skip = (size_t)h->sweep_row0;  // rows of the last vertex pass (a packed sweep has one set per piece)
+  sbm_local_totals<<<1, 512, 0, h->stream>>>(h->part_vertex + skip * PSTRIDE, h->sweep_rows, h->part_mstep + skip * Q * Q,
                                              (MODEL == MODEL_SBM && mode == MODE_SWEEP) ? 1 : 0, h->totals, h->maxd_dev);
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
@@ -1713,11 +1807,11 @@ int mop_fe_final(gbx_sbm* h) {
 
 const SbmOps kOps = {Q,          op_vertex_pass, op_local_totals, mop_apply_totals,   mop_prepare,   mop_noop,     mop_noop,
                      mop_noop,   mop_fe_local,   mop_fe_apply,    mop_fe_final,       op_permute,    op_random_messages,
-                     op_assignment, op_occupancy, op_init_model};
+                     op_assignment, op_occupancy, op_init_model, op_unpack};
 #else
 const SbmOps kOps = {Q,          op_vertex_pass, op_local_totals, op_apply_totals,    op_prepare,    op_theta_local, op_theta_apply,
                      op_escale,  op_fe_local,    op_fe_apply,     op_fe_final,        op_permute,    op_random_messages,
-                     op_assignment, op_occupancy, op_init_model};
+                     op_assignment, op_occupancy, op_init_model, op_unpack};
 #endif
 
 }  // namespace

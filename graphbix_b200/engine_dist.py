@@ -1,8 +1,10 @@
 """Vertex-partitioned EM + BP across the GPUs of one NVLink domain (BASELINE.json configs[3]): one process per GPU.
 
 Rank r owns a contiguous range of vertices and the rows of their incoming messages.  During a sweep each rank
-stores the new messages for rows of other ranks straight into the owner's buffer over NVLink (peer pointers,
-exchanged once here through CUDA IPC handles); the only per-iteration collectives are the all-reduce of the totals
+packs the new messages for rows of other ranks into per-destination runs that the copy engine pushes into the
+owner's receive buffer over NVLink while the sweep continues (peer pointers, exchanged once here through CUDA IPC
+handles), and the owner scatters them into its rows after the all-reduce (`set_exchange(0)`: 64-B peer stores straight
+from the sweep kernel instead); the only per-iteration collectives are the all-reduce of the totals
 vector (residual, sum PSI, block degree sums, M-step statistics: 4 + 4q + q^2 doubles) and, with degree correction,
 the all-reduce of S_theta (q doubles) and the all-gather of theta (N doubles).  torch.distributed (NCCL) is the
 plumbing for those; the kernels are the same as on one GPU (C ABI: gbx_sbm_create_part, gbx_sbm_step, ...).
@@ -19,7 +21,7 @@ import numpy as np
 from . import _lib
 from ._lib import (MODE_LOGZ, MODE_MARGINAL, MODE_SWEEP, STEP_APPLY_TOTALS, STEP_COUNT_ITERATION, STEP_ESCALE,
                    STEP_FE_APPLY, STEP_FE_FINAL, STEP_FE_LOCAL, STEP_LOCAL_TOTALS, STEP_PREPARE, STEP_THETA_APPLY,
-                   STEP_THETA_LOCAL, STEP_VERTEX_PASS, ModOptions, ModResult, SbmOptions, SbmResult, check)
+                   STEP_THETA_LOCAL, STEP_UNPACK, STEP_VERTEX_PASS, ModOptions, ModResult, SbmOptions, SbmResult, check)
 from .engine import _dp, _f64
 
 
@@ -62,8 +64,8 @@ class PartEngine:
         check(self.lib.gbx_sbm_part_set_buffers(self._h, C.c_void_p(self.totals.data_ptr()),
                                                 C.c_void_p(self.theta.data_ptr())))
         check(self.lib.gbx_sbm_set_stream(self._h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        # peer pointers of both message buffers of every rank
-        for which in (0, 1):
+        # peer pointers of both message buffers and both receive buffers of every rank
+        for which in (0, 1, 2, 3):
             buf = (C.c_ubyte * 64)()
             check(self.lib.gbx_sbm_ipc_export(self._h, which, buf))
             handles = [None] * self.world
@@ -112,10 +114,17 @@ class PartEngine:
         self.dist.all_reduce(t)
         self._sync("all_reduce")
 
+    def set_exchange(self, mode: int):
+        """1 (default): boundary messages packed, pushed by the copy engine, unpacked after the all-reduce;
+        0: stored one by one into the owner's buffer from the sweep kernel."""
+        check(self.lib.gbx_sbm_part_set_exchange(self._h, int(mode)))
+
     def _pass(self, mode):
         self._step(STEP_VERTEX_PASS, mode)
         self._step(STEP_LOCAL_TOTALS, mode)
-        self._allreduce()
+        self._allreduce()                   # also the barrier after which every rank's boundary rows have arrived
+        if mode == MODE_SWEEP:
+            self._step(STEP_UNPACK)
         self._step(STEP_APPLY_TOTALS, mode)
 
     @property

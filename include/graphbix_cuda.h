@@ -178,7 +178,9 @@ enum {
   GBX_STEP_FE_LOCAL = 7,         /* arg = pass (0 sums, 1 squared deviations) -> totals[0..5)                 */
   GBX_STEP_FE_APPLY = 8,
   GBX_STEP_FE_FINAL = 9,
-  GBX_STEP_COUNT_ITERATION = 10
+  GBX_STEP_COUNT_ITERATION = 10,
+  GBX_STEP_UNPACK = 11           /* packed exchange: after the all-reduce that follows a sweep, scatter the rows  */
+                                 /* received from the other ranks into the message buffer (no-op otherwise)       */
 };
 int gbx_sbm_create_part(gbx_sbm** out, int device, int64_t n_vertices, int64_t n_links, const int64_t* links, int q,
                         int rank, int world);
@@ -187,12 +189,19 @@ int gbx_mod_create_part(gbx_mod** out, int device, int64_t n_vertices, int64_t n
 /* info[0..8) = first owned vertex, owned vertices, first owned slot, owned slots, length of the totals vector,
  * vertices per rank c, rank, world */
 int gbx_sbm_part_info(const gbx_sbm* h, int64_t* info);
-/* cudaIpcMemHandle_t (64 bytes) of message buffer `which` (0/1); every rank imports every other rank's two. */
+/* cudaIpcMemHandle_t (64 bytes) of message buffer `which` (0/1) or receive buffer `which - 2` (2/3); every rank
+ * imports every other rank's four. */
 int gbx_sbm_ipc_export(gbx_sbm* h, int which, unsigned char* handle64);
 int gbx_sbm_ipc_import(gbx_sbm* h, int which, int rank, const unsigned char* handle64);
 /* Device buffers owned by the caller that the collectives run on: totals (info[4] doubles) and theta
  * (world * c doubles, indexed by global vertex id; rank r's update_theta writes [r*c, ...)). */
 int gbx_sbm_part_set_buffers(gbx_sbm* h, void* totals_dev, void* theta_dev);
+/* How boundary messages travel.  1 (default for world > 1): the sweep packs them into per-destination send runs in
+ * this rank's slot order, the copy engine pushes the runs over NVLink while later pieces of the sweep run, and
+ * GBX_STEP_UNPACK scatters the received rows after the all-reduce.  0: the sweep stores each message straight into
+ * the owner's buffer (64-B peer stores; slower on NVLink, see profiles/r01_p2p_probe.txt).  Damped sweeps
+ * (damping != 1) always use 0 because the previous outgoing message lives on the owner. */
+int gbx_sbm_part_set_exchange(gbx_sbm* h, int mode);
 int gbx_sbm_step(gbx_sbm* h, int step, int arg);
 int gbx_sbm_read_residual(gbx_sbm* h, double* bpconv);
 

@@ -121,3 +121,13 @@ def test_mixed_plain_and_exponent_tracked_products(gpu_required, q, log2c):
         eng.iterate(1)
         np.testing.assert_allclose(eng.state()["PSI"], ref.PSI, rtol=0, atol=1e-12, err_msg=f"PSI it={it}")
         np.testing.assert_allclose(eng.messages(), ref.messages_in_link_order(), rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("q", [2, 3, 4, 6, 8, 16])
+@pytest.mark.parametrize("dc", [True, False])
+def test_several_tiles_per_cta(gpu_required, q, dc):
+    """More tiles than resident CTAs: every CTA walks several tiles through its double-buffered staging, and its
+    M-step accumulators and partial sums carry over from tile to tile."""
+    n, links, psi0, _ = planted_case(24000 if q < 16 else 16000, q, 10.0, 0.15, seed=70 + q)
+    gr0, C0 = assortative_init(q)
+    _run_pair(n, links, q, psi0, gr0, C0, 3, dc=dc, prior=True)
