@@ -58,6 +58,8 @@ def parse_args():
     ap.add_argument("--part-shuffle", type=int, default=1,
                     help="1: random vertex numbering (a contiguous partition cuts (P-1)/P of the links); "
                          "0: vertices numbered group by group (the partition follows the planted groups)")
+    ap.add_argument("--part-exchange", type=int, default=1,
+                    help="1: packed boundary exchange (copy engine pushes, unpack); 0: 64-B peer stores from the sweep")
     ap.add_argument("--no-partitioned-leg", action="store_true")
     return ap.parse_args()
 
@@ -197,7 +199,11 @@ def run_partitioned(a, torch, dist, world, rank, local):
         dist.broadcast(links, 0)
     torch.cuda.synchronize()
     chunk = (n + world - 1) // world
-    cut = float((((links[0] - 1) // chunk) != ((links[1] - 1) // chunk)).double().mean().item())
+    ncut = 0
+    for b in range(0, K, 1 << 26):   # in slices: at 10^9 links whole-array temporaries would cost 8 GB each
+        sl = links[:, b:b + (1 << 26)]
+        ncut += int((((sl[0] - 1) // chunk) != ((sl[1] - 1) // chunk)).sum().item())
+    cut = ncut / max(K, 1)
     t_gen = time.perf_counter() - t0
     torch.cuda.empty_cache()
     t0 = time.perf_counter()
@@ -206,6 +212,7 @@ def run_partitioned(a, torch, dist, world, rank, local):
     torch.cuda.empty_cache()
     t_build = time.perf_counter() - t0
     eng.set_options(degreecorrection=a.dc, priorlearning=1, learningrate=0.3, itrmax=a.steps)
+    eng.set_exchange(a.part_exchange)
     gr0 = np.ones(a.q) / a.q
     C0 = 20 * np.eye(a.q) + 0.01 * np.ones((a.q, a.q))
     eng.init(gr0, C0, None, seed=99)
@@ -225,13 +232,19 @@ def run_partitioned(a, torch, dist, world, rank, local):
     ms = float(t.item())
     resid = eng.residual()
     slots = eng.K
+    prof = eng.profile_summary()
+    if prof and rank == 0:
+        print("partitioned step profile (ms per iteration, incl. warm-up iterations):",
+              {k: round(v / (a.steps + a.warmup), 4) for k, v in prof.items()}, file=sys.stderr)
     eng.close()
     return {"value": K * a.steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / a.steps, "n_vertices": n,
             "avg_degree": deg, "directed_edges": K, "directed_edges_rank0": slots, "cut_fraction": cut,
             "vertex_numbering": "random" if a.part_shuffle else "by planted group",
+            "exchange": "packed runs pushed by the copy engine, unpacked by the owner" if a.part_exchange else
+                        "64-B peer stores from the sweep kernel",
             "generate_s": t_gen, "build_s": t_build, "residual_after": resid,
-            "what": ("one graph vertex-partitioned over the GPUs: peer stores of boundary messages over NVLink inside "
-                     "the sweep kernel, NCCL all-reduce of the totals and all-gather of theta per iteration")}
+            "what": ("one graph vertex-partitioned over the GPUs: boundary messages cross NVLink every sweep, NCCL "
+                     "all-reduce of the totals and all-gather of theta per iteration")}
 
 
 def run_ours(a):

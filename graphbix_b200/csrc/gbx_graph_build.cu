@@ -395,8 +395,12 @@ int build_exchange_plan(gbx_sbm* h, const GlobalGraph& g, const std::vector<int4
   GBX_C(cudaStreamSynchronize(st));
   GBX_C(cudaGetLastError());
   GBX_C(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  h->peer_stream[1] = h->copy_stream;
+  for (int k = 2; k < P; ++k) GBX_C(cudaStreamCreateWithFlags(&h->peer_stream[k], cudaStreamNonBlocking));
+  for (int k = 1; k < P; ++k) GBX_C(cudaEventCreateWithFlags(&h->ev_peer[k], cudaEventDisableTiming));
   for (int c = 0; c < MAXCHUNK; ++c) GBX_C(cudaEventCreateWithFlags(&h->ev_piece[c], cudaEventDisableTiming));
   GBX_C(cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming));
+  GBX_C(cudaEventCreateWithFlags(&h->ev_unpacked, cudaEventDisableTiming));
   cleanup();
   h->launches += 2 + P;
   return GBX_OK;

@@ -78,8 +78,14 @@ int dev_alloc(gbx_sbm* h, T** p, size_t count) {
   return GBX_OK;
 }
 
-int set_device(const gbx_sbm* h) {
+// Every C-ABI entry starts here.  `join` (default): the main stream first waits for an unpack of boundary rows that
+// may still run on the copy stream; the steps that never touch the messages skip that so they overlap with it.
+int set_device(gbx_sbm* h, bool join = true) {
   GBX_CUDA_TRY(cudaSetDevice(h->device));
+  if (join && h->unpack_inflight) {
+    GBX_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_unpacked, 0));
+    h->unpack_inflight = false;
+  }
   return GBX_OK;
 }
 
@@ -256,7 +262,9 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
 
   h->ntiles = (int)tiles.size();
   if (world > 1) {
-    h->nchunks = 4;
+    // pieces of a packed sweep: the exposed copy tail is 1/pieces of the boundary traffic, but many small all-to-all
+    // copies run slower through the switch than a few large ones (measured: 2 GPUs best with 8, 8 GPUs with 2)
+    h->nchunks = std::max(2, std::min((int)MAXCHUNK, 16 / world));
     if (const char* e = getenv("GBX_EXCHANGE_PIECES")) h->nchunks = atoi(e);
     const int rcp = build_exchange_plan(h, gg, tiles);
     free_global(&gg);
@@ -358,10 +366,15 @@ int gbx_sbm_destroy(gbx_sbm* h) {
   cudaFree(h->sendbuf);
   cudaFree(h->recvbuf[0]);
   cudaFree(h->recvbuf[1]);
+  for (int k = 2; k < MAXPEER; ++k)
+    if (h->peer_stream[k]) cudaStreamDestroy(h->peer_stream[k]);
+  for (int k = 0; k < MAXPEER; ++k)
+    if (h->ev_peer[k]) cudaEventDestroy(h->ev_peer[k]);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (int c = 0; c < MAXCHUNK; ++c)
     if (h->ev_piece[c]) cudaEventDestroy(h->ev_piece[c]);
   if (h->ev_copied) cudaEventDestroy(h->ev_copied);
+  if (h->ev_unpacked) cudaEventDestroy(h->ev_unpacked);
   cudaFree(h->rowptr);
   cudaFree(h->col);
   cudaFree(h->rev);
@@ -839,7 +852,10 @@ int gbx_sbm_part_set_exchange(gbx_sbm* h, int mode) {
 int gbx_sbm_step(gbx_sbm* h, int step, int arg) {
   if (!h) return fail_invalid("handle is NULL");
   if (!h->initialised) return fail_state();
-  GBX_TRY(set_device(h));
+  const bool no_messages = step == GBX_STEP_PREPARE || step == GBX_STEP_APPLY_TOTALS || step == GBX_STEP_THETA_LOCAL ||
+                           step == GBX_STEP_THETA_APPLY || step == GBX_STEP_ESCALE || step == GBX_STEP_COUNT_ITERATION ||
+                           step == GBX_STEP_UNPACK;
+  GBX_TRY(set_device(h, !no_messages));
   const SbmOps* op = h->ops;
   switch (step) {
     case GBX_STEP_PREPARE: return op->prepare(h, arg & 1, (arg >> 1) & 1);

@@ -122,9 +122,12 @@ struct gbx_sbm {
   int nchunks = 1;
   int chunk_tile[gbx::MAXCHUNK + 1] = {0};
   int64_t chunk_send[gbx::MAXCHUNK + 1][gbx::MAXPEER] = {};  // rows of the run for o written by pieces < c
-  cudaStream_t copy_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;                 // unpack + the copies to rank (me + 1) % world
+  cudaStream_t peer_stream[gbx::MAXPEER] = {};        // [k]: copies to rank (me + k) % world, k >= 2 (own copy engine queue)
+  cudaEvent_t ev_peer[gbx::MAXPEER] = {};
   cudaEvent_t ev_piece[gbx::MAXCHUNK] = {};
-  cudaEvent_t ev_copied = nullptr;
+  cudaEvent_t ev_copied = nullptr, ev_unpacked = nullptr;
+  bool unpack_inflight = false;        // k_unpack is running on the copy stream; join before touching messages
   int sweep_rows = 0, sweep_row0 = 0;  // partial rows written by the last vertex pass (count, first row)
   int xparity = 0;                     // receive buffer the next sweep pushes into
   bool pending_unpack = false;         // the last sweep was packed and its rows have not been scattered yet

@@ -974,26 +974,46 @@ __global__ void __launch_bounds__(256) sbm_escale_kernel(const int* __restrict__
 constexpr int TOT_G = 4 + 4 * Q;
 constexpr int TOT_LEN = TOT_G + Q * Q;
 
-__global__ void sbm_local_totals(const double* __restrict__ pv, int nrows, const double* __restrict__ pm, int with_g,
-                                 double* __restrict__ totals, double* __restrict__ maxd_out) {
-  const int tid = threadIdx.x, lane = tid & 31;
+__global__ void __launch_bounds__(256) sbm_local_totals(const double* __restrict__ pv, int nrows,
+                                                        const double* __restrict__ pm, int with_g,
+                                                        double* __restrict__ totals, double* __restrict__ maxd_out) {
+  // One block per column of the totals vector (the last block: the max column); fixed summation order.
+  __shared__ double red[256];
+  const int tid = threadIdx.x;
   const int ncol = 4 * Q + 4 + (with_g ? Q * Q : 0);
-  for (int c = tid >> 5; c < ncol; c += blockDim.x >> 5) {
-    double v;
-    if (c < 4 * Q + 4) {
-      // partial-row columns: 0,1 | 2..2+3Q | maxd at 2+3Q | dpsi at 3+3Q.. | mod stat at 3+4Q
-      if (c < 2 + 3 * Q) v = warp_column_reduce<false>(pv, nrows, PSTRIDE, c);
-      else if (c < 2 + 4 * Q) v = (MODEL == MODEL_MOD) ? warp_column_reduce<false>(pv, nrows, PSTRIDE, c + 1) : 0.0;
-      else if (c == 2 + 4 * Q) v = (MODEL == MODEL_MOD) ? warp_column_reduce<false>(pv, nrows, PSTRIDE, 3 + 4 * Q) : 0.0;
-      else v = 0.0;
-    } else {
-      v = warp_column_reduce<false>(pm, nrows, Q * Q, c - (4 * Q + 4));
-    }
-    if (lane == 0) totals[c] = v;
+  const int c = blockIdx.x;
+  const bool is_max = (c == ncol);
+  const double* src = nullptr;
+  int stride = PSTRIDE, col = 0;
+  if (is_max) {
+    src = pv;
+    col = 2 + 3 * Q;
+  } else if (c < 4 * Q + 4) {
+    // partial-row columns: 0,1 | 2..2+3Q | maxd at 2+3Q | dpsi at 3+3Q.. | mod stat at 3+4Q
+    if (c < 2 + 3 * Q) { src = pv; col = c; }
+    else if (c < 2 + 4 * Q) { if (MODEL == MODEL_MOD) { src = pv; col = c + 1; } }
+    else if (c == 2 + 4 * Q) { if (MODEL == MODEL_MOD) { src = pv; col = 3 + 4 * Q; } }
+  } else {
+    src = pm;
+    stride = Q * Q;
+    col = c - (4 * Q + 4);
   }
-  if ((tid >> 5) == 0) {  // the largest per-vertex change is a max, kept out of the summed vector
-    const double m = warp_column_reduce<true>(pv, nrows, PSTRIDE, 2 + 3 * Q);
-    if (lane == 0) *maxd_out = m;
+  double v = 0.0;
+  if (src) {
+    for (int r = tid; r < nrows; r += 256) {
+      const double x = src[(size_t)r * stride + col];
+      v = is_max ? fmax(v, x) : v + x;
+    }
+  }
+  red[tid] = v;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) red[tid] = is_max ? fmax(red[tid], red[tid + o]) : red[tid] + red[tid + o];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    if (is_max) *maxd_out = red[0];
+    else totals[c] = red[0];
   }
 }
 
@@ -1397,18 +1417,21 @@ int launch_packed_sweep(gbx_sbm* h) {
       GBX_CUDA_TRY(cudaMemsetAsync(ac.mpart, 0, (size_t)G * Q * Q * sizeof(double), h->stream));
     }
     GBX_CUDA_TRY(cudaEventRecord(h->ev_piece[c], h->stream));
-    GBX_CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_piece[c], 0));
-    for (int o = 0; o < h->world; ++o) {
-      if (o == h->rank) continue;
+    // one queue per destination, destinations in rotated order: at any moment the ranks push to different owners
+    for (int k = 1; k < h->world; ++k) {
+      const int o = (h->rank + k) % h->world;
       const long long b = h->chunk_send[c][o], e = h->chunk_send[c + 1][o];
       if (e <= b) continue;
+      GBX_CUDA_TRY(cudaStreamWaitEvent(h->peer_stream[k], h->ev_piece[c], 0));
       GBX_CUDA_TRY(cudaMemcpyAsync(dst[o] + (size_t)(h->my_off_at[o] + b) * Q,
                                    h->sendbuf + (size_t)(h->send_off[o] + b) * Q, (size_t)(e - b) * rowb,
-                                   cudaMemcpyDeviceToDevice, h->copy_stream));
+                                   cudaMemcpyDeviceToDevice, h->peer_stream[k]));
     }
   }
-  GBX_CUDA_TRY(cudaEventRecord(h->ev_copied, h->copy_stream));
-  GBX_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_copied, 0));  // the totals (and the all-reduce) follow the copies
+  for (int k = 1; k < h->world; ++k) {  // the totals (and the all-reduce) follow the copies
+    GBX_CUDA_TRY(cudaEventRecord(h->ev_peer[k], h->peer_stream[k]));
+    GBX_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_peer[k], 0));
+  }
   h->sweep_rows = NC * G + h->nhubs;
   h->sweep_row0 = 0;
   h->pending_unpack = true;
@@ -1431,6 +1454,8 @@ __global__ void k_unpack(const double* __restrict__ recv, const int* __restrict_
   }
 }
 
+// Runs on the copy stream, next to the small kernels and collectives that follow the sweep on the main stream; every
+// entry point that touches the messages joins it first (join_unpack in gbx_sbm_host.cu).
 int op_unpack(gbx_sbm* h) {
   if (!h->pending_unpack) return GBX_OK;
   h->pending_unpack = false;
@@ -1438,10 +1463,14 @@ int op_unpack(gbx_sbm* h) {
   h->xparity ^= 1;
   if (h->send_total > 0) {
     // called after the sweep's buffer swap: h->cur is the buffer the sweep wrote
-    k_unpack<<<grid_for(h, h->send_total * ((Q % 2 == 0) ? Q / 2 : Q)), 256, 0, h->stream>>>(
+    GBX_CUDA_TRY(cudaEventRecord(h->ev_piece[0], h->stream));  // after the all-reduce: every rank's rows have landed
+    GBX_CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_piece[0], 0));
+    k_unpack<<<grid_for(h, h->send_total * ((Q % 2 == 0) ? Q / 2 : Q)), 256, 0, h->copy_stream>>>(
         h->recvbuf[parity], h->unpack_slot, (long long)h->send_total, h->msg[h->cur]);
     h->launches++;
     GBX_CUDA_TRY(cudaGetLastError());
+    GBX_CUDA_TRY(cudaEventRecord(h->ev_unpacked, h->copy_stream));
+    h->unpack_inflight = true;
   }
   return GBX_OK;
 }
@@ -1458,8 +1487,9 @@ int op_vertex_pass(gbx_sbm* h, int mode) {
 
 int op_local_totals(gbx_sbm* h, int mode) {
   const size_t skip = (size_t)h->sweep_row0;  // rows of the last vertex pass (a packed sweep has one set per piece)
-  sbm_local_totals<<<1, 512, 0, h->stream>>>(h->part_vertex + skip * PSTRIDE, h->sweep_rows, h->part_mstep + skip * Q * Q,
-                                             (MODEL == MODEL_SBM && mode == MODE_SWEEP) ? 1 : 0, h->totals, h->maxd_dev);
+  const int with_g = (MODEL == MODEL_SBM && mode == MODE_SWEEP) ? 1 : 0;
+  sbm_local_totals<<<4 * Q + 4 + (with_g ? Q * Q : 0) + 1, 256, 0, h->stream>>>(
+      h->part_vertex + skip * PSTRIDE, h->sweep_rows, h->part_mstep + skip * Q * Q, with_g, h->totals, h->maxd_dev);
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;

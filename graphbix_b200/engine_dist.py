@@ -39,6 +39,7 @@ class PartEngine:
         torch.cuda.set_device(self.local)
         self.model = model
         self._debug = bool(int(os.environ.get("GBX_PART_SYNC", "0")))   # synchronise after every step (debugging)
+        self._profile = [] if int(os.environ.get("GBX_PART_PROFILE", "0")) else None
         if torch.is_tensor(links):
             # edge list already on this GPU: a (2, K) int64 tensor = the K x 2 `links` matrix in column-major order
             assert links.is_cuda and links.dtype == torch.int64 and links.dim() == 2 and links.shape[0] == 2
@@ -98,7 +99,25 @@ class PartEngine:
         fn = self.lib.gbx_sbm_set_options if self.model == "sbm" else self.lib.gbx_mod_set_options
         check(fn(self._h, C.byref(self.opt)))
 
+    def _tick(self, label):
+        """GBX_PART_PROFILE=1: CUDA events between the steps of an iteration (profile_summary() adds them up)."""
+        if self._profile is not None:
+            ev = self.torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._profile.append((label, ev))
+
+    def profile_summary(self):
+        if not self._profile:
+            return {}
+        self.torch.cuda.synchronize()
+        out = {}
+        for (_, e0), (label, e1) in zip(self._profile[:-1], self._profile[1:]):
+            out[label] = out.get(label, 0.0) + e0.elapsed_time(e1)
+        self._profile = []
+        return out
+
     def _sync(self, what):
+        self._tick(what)
         if self._debug:
             try:
                 self.torch.cuda.synchronize()
@@ -153,10 +172,12 @@ class PartEngine:
                 self._allreduce(q)
                 self._step(STEP_THETA_APPLY)
                 mine = self.theta[r * c:(r + 1) * c].clone()
+                self._tick("clone(theta)")
                 self.dist.all_gather_into_tensor(self.theta, mine)
                 self._sync("all_gather(theta)")
                 self._step(STEP_ESCALE)
             self._step(STEP_COUNT_ITERATION)
+            self._tick("iteration end")
 
     def residual(self) -> float:
         v = C.c_double()

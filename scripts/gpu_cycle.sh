@@ -14,7 +14,7 @@ fullbench) python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full
 refbench) python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "refbench rc=$?"; cut -c1-400 gpurun_out/bench_ref.json ;;
 part) python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29517 tests/dist_check_part.py > gpurun_out/part.log 2>&1; echo "part rc=$?"; grep -v 'OMP_NUM_THREADS\|^\*\*\*\*\|^frame\|^$' gpurun_out/part.log | tail -45 ;;
 benchN) python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus ${NGPU:-2} --steps ${STEPS:-50} --warmup 5 ${BARGS:-} > gpurun_out/bench_n${NGPU:-2}${TAG:-}.json 2> gpurun_out/bench_n${NGPU:-2}${TAG:-}.err; echo "benchN rc=$?"; python scripts/show_bench.py gpurun_out/bench_n${NGPU:-2}${TAG:-}.json; grep -v 'OMP_NUM_THREADS\|^\*\*\*\*\|^$' gpurun_out/bench_n${NGPU:-2}${TAG:-}.err | tail -15 ;;
-partrun) python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29521 scripts/part_run.py --steps ${STEPS:-50} --warmup 5 ${BARGS:-} > gpurun_out/partrun${TAG:-}.json 2> gpurun_out/partrun${TAG:-}.err; echo "partrun rc=$?"; cut -c1-900 gpurun_out/partrun${TAG:-}.json; grep -v 'OMP_NUM_THREADS\|^\*\*\*\*\|^$' gpurun_out/partrun${TAG:-}.err | grep -i "error\|rank" | head -12 | cut -c1-300 ;;
+partrun) python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29521 scripts/part_run.py --warmup 5 --steps ${STEPS:-50} ${BARGS:-} > gpurun_out/partrun${TAG:-}.json 2> gpurun_out/partrun${TAG:-}.err; echo "partrun rc=$?"; cut -c1-900 gpurun_out/partrun${TAG:-}.json; grep -v 'OMP_NUM_THREADS\|^\*\*\*\*\|^$' gpurun_out/partrun${TAG:-}.err | grep -i "error\|rank" | head -12 | cut -c1-300 ;;
 smoke) python -c "import __graft_entry__ as g; g.smoke()" ;;
 esac
 done

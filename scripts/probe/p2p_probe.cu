@@ -117,6 +117,24 @@ int main() {
     report("(f) pack: random 64-B gather -> contiguous local", timeit([&] { k_pack<<<grid, 256>>>((double2*)src, (double2*)loc, perm, n); }));
     report("(g) unpack: contiguous -> random 64-B scatter local", timeit([&] { k_rowT<4><<<grid, 256>>>((double2*)src, (double2*)loc, perm, n); }));
   }
+  {
+    // (k) rows in order, (l) runs of 64 rows (4 KB, one tile's boundary messages) at random places, rows in order inside
+    std::vector<int> pk(n), pl(n);
+    std::iota(pk.begin(), pk.end(), 0);
+    const int RUN = 64;
+    std::vector<int> runs(n / RUN);
+    std::iota(runs.begin(), runs.end(), 0);
+    std::shuffle(runs.begin(), runs.end(), rng);
+    for (long long i = 0; i < n; ++i) pl[i] = runs[i / RUN] * RUN + (int)(i % RUN);
+    int *permk, *perml;
+    CK(cudaMalloc(&permk, n * 4));
+    CK(cudaMalloc(&perml, n * 4));
+    CK(cudaMemcpy(permk, pk.data(), n * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(perml, pl.data(), n * 4, cudaMemcpyHostToDevice));
+    report("(k) rows in order, 1 thread/row (2 x v4.f64) -> peer", timeit([&] { k_row1<<<148 * 16, 256>>>(src, peer, permk, n); }));
+    report("(l) 4-KB runs at random places, 1 thread/row -> peer", timeit([&] { k_row1<<<148 * 16, 256>>>(src, peer, perml, n); }));
+    report("(k') rows in order, 1 thread/row -> local", timeit([&] { k_row1<<<148 * 16, 256>>>(src, loc, permk, n); }));
+  }
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   // both directions at once (what a sweep does): GPU1 -> GPU0 concurrently
