@@ -122,6 +122,19 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def recorded_traffic(a):
+    """DRAM bytes per launch of the sweep kernel from the committed ncu capture (profiles/sweep_traffic.json), if it
+    was taken on this workload; None otherwise (ncu cannot run inside a timed bench)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "sweep_traffic.json")))
+        w = t["workload"]
+        if (w["n"], float(w["deg"]), w["q"], w["dc"]) == (a.n, float(a.deg), a.q, a.dc):
+            return float(t["dram_bytes_per_launch"]), t["source"]
+    except Exception:
+        pass
+    return None, None
+
+
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_run(a, steps, warmup):
     """The oracle (CPU restatement of the reference's EM loop) on a bounded sample of the workload."""
@@ -336,6 +349,7 @@ def run_ours(a):
     e2e_value = world * K * a.steps / t_e2e
     peak, peak_src = measured_peak_gbs()
     achieved = sweep_bytes / (sweep_ms * 1e-3) / 1e9
+    traffic, traffic_src = recorded_traffic(a)
     part = None
     if (world > 1 and not a.no_partitioned_leg) or a.mode == "partitioned":
         part = run_partitioned(a, torch, dist, world, rank, local)
@@ -354,8 +368,8 @@ def run_ours(a):
                         "what": "EM() with host buffers: CSR build, H2D, steps iterations, free energy + CV, D2H"},
                 "gpu_launches": launches, "clocks": sampler.summary(),
                 "roofline": {"bound": "hbm", "kernel": "sbm_vertex_kernel<8,SWEEP> (BP sweep)", "achieved": achieved,
-                             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                             "peak_source": peak_src, "ms_per_launch": sweep_ms, "algorithmic_bytes": sweep_bytes,
+                             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                             "traffic_source": traffic_src, "peak_source": peak_src, "ms_per_launch": sweep_ms, "algorithmic_bytes": sweep_bytes,
                              "sweep_updates_per_sec": K / (sweep_ms * 1e-3)}}
         if part is not None:
             line["partitioned"] = part
