@@ -61,6 +61,7 @@ def parse_args():
     ap.add_argument("--part-exchange", type=int, default=1,
                     help="1: packed boundary exchange (copy engine pushes, unpack); 0: 64-B peer stores from the sweep")
     ap.add_argument("--no-partitioned-leg", action="store_true")
+    ap.add_argument("--no-convergence-leg", action="store_true")
     return ap.parse_args()
 
 
@@ -260,6 +261,48 @@ def run_partitioned(a, torch, dist, world, rank, local):
                      "all-reduce of the totals and all-gather of theta per iteration")}
 
 
+def run_convergence(a, torch, dist, world, rank, local):
+    """Second half of BASELINE.json's metric, on configs[1]: mod.jl community-restricted SBM on a planted partition
+    N = 100k, average degree 10, q = 2..10, one q per GPU (dealt round-robin), each EM() run to BPconv < 1e-6 through
+    the public call with host buffers.  Reports iterations and seconds per q."""
+    from graphbix_b200.engine import EM_mod
+    from graphbix_b200.parallel import my_share
+    from graphbix_b200.synth import planted_partition
+    n, deg, qtrue = 100_000, 10.0, 4
+    links, _ = planted_partition(n, qtrue, deg, 0.1, seed=31, connected_only=True)
+    n = int(links.max())
+    qs = list(range(2, 11))
+    mine = []
+    torch.cuda.synchronize()
+    t_all = time.perf_counter()
+    for pos, q in my_share(qs, rank, world):
+        # the first call of a q in a process also loads that q's kernels (CUDA lazy module loading): reported apart
+        t0 = time.perf_counter()
+        EM_mod(np.ones(q) / q, n, q, links, 1, 256, 0.0, True, True, False, 0.3, seed=5 + q, device=local)
+        torch.cuda.synchronize()
+        first = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        out, eng, _ = EM_mod(np.ones(q) / q, n, q, links, 1, 256, 0.0, True, True, False, 0.3, seed=5 + q, device=local,
+                             return_engine=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        mine.append({"q": q, "iterations": int(out[16]), "converged": bool(out[15]), "seconds": dt,
+                     "seconds_first_call": first, "seconds_em_loop": eng.timings.get("em"),
+                     "seconds_graph_build": eng.timings.get("create"), "CVBayes": float(out[7]), "FE": float(out[6])})
+        eng.close()
+    wall = time.perf_counter() - t_all
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        mine = sorted((x for part in gathered for x in part), key=lambda x: x["q"])
+        t = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t.item())
+    return {"workload": f"mod.jl EM() to BPconv < 1e-6, planted partition N={n} (giant component of 100000), avg degree "
+                        f"{deg:g}, 4 planted groups, q = 2..10, one q per GPU round-robin",
+            "seconds_total": wall, "directed_edges": int(links.shape[0]), "runs": mine}
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -352,7 +395,22 @@ def run_ours(a):
     traffic, traffic_src = recorded_traffic(a)
     part = None
     if (world > 1 and not a.no_partitioned_leg) or a.mode == "partitioned":
-        part = run_partitioned(a, torch, dist, world, rank, local)
+        if a.mode == "partitioned":
+            part = run_partitioned(a, torch, dist, world, rank, local)
+        else:
+            # an extra next to the headline: a failure here (every rank fails alike: same code, same sizes) must not
+            # cost the independent-graphs line
+            try:
+                part = run_partitioned(a, torch, dist, world, rank, local)
+            except Exception as e:  # noqa: BLE001
+                part = {"error": f"{type(e).__name__}: {e}"[:400]}
+
+    conv = None
+    if not a.no_convergence_leg:
+        try:
+            conv = run_convergence(a, torch, dist, world, rank, local)
+        except Exception as e:  # noqa: BLE001
+            conv = {"error": f"{type(e).__name__}: {e}"[:400]}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -371,6 +429,8 @@ def run_ours(a):
                              "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                              "traffic_source": traffic_src, "peak_source": peak_src, "ms_per_launch": sweep_ms, "algorithmic_bytes": sweep_bytes,
                              "sweep_updates_per_sec": K / (sweep_ms * 1e-3)}}
+        if conv is not None:
+            line["em_convergence"] = conv
         if part is not None:
             line["partitioned"] = part
             if a.mode == "partitioned":

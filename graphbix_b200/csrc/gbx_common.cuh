@@ -73,6 +73,30 @@ __device__ __forceinline__ void store_vec(double* __restrict__ base, long long i
   }
 }
 
+// Message rows: Q components in a row of QM >= Q doubles (pads are stored as zeros, ignored on load).
+template <int Q, int QM>
+__device__ __forceinline__ void load_msg(const double* __restrict__ base, long long idx, double (&m)[Q]) {
+  if constexpr (QM == Q) {
+    load_vec<Q>(base, idx, m);
+  } else {
+    double t[QM];
+    load_vec<QM>(base, idx, t);
+#pragma unroll
+    for (int k = 0; k < Q; ++k) m[k] = t[k];
+  }
+}
+template <int Q, int QM>
+__device__ __forceinline__ void store_msg(double* __restrict__ base, long long idx, const double (&m)[Q]) {
+  if constexpr (QM == Q) {
+    store_vec<Q>(base, idx, m);
+  } else {
+    double t[QM];
+#pragma unroll
+    for (int k = 0; k < QM; ++k) t[k] = (k < Q) ? m[k] : 0.0;
+    store_vec<QM>(base, idx, t);
+  }
+}
+
 // ---- power-of-two scaling (exact) -------------------------------------------------------------
 // Unbiased exponent of a positive normal double; `ok` is cleared for 0, subnormal, Inf, NaN, negative.
 __device__ __forceinline__ int exponent_of(double m, bool& ok) {

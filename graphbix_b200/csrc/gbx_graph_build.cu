@@ -352,7 +352,7 @@ int build_exchange_plan(gbx_sbm* h, const GlobalGraph& g, const std::vector<int4
     h->dev_bytes += (int64_t)bytes;
     return cudaMalloc(p, bytes ? bytes : 1);
   };
-  const size_t rowb = (size_t)h->q * sizeof(double);
+  const size_t rowb = (size_t)h->qm * sizeof(double);
   GBX_C(keep((void**)&h->rev_pack, (size_t)Kl * sizeof(int)));
   GBX_C(keep((void**)&h->unpack_slot, (size_t)h->send_total * sizeof(int)));
   GBX_C(keep((void**)&h->sendbuf, (size_t)h->send_total * rowb));

@@ -197,6 +197,7 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
   if (!h) return fail_invalid("out of host memory");
   h->device = device;
   h->q = q;
+  h->qm = msg_stride(q);
   h->n = n;
   h->K = K;
   h->n_global = n;
@@ -297,8 +298,8 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
     GBX_TRY(dev_alloc(h, &h->escale, (size_t)K));
     GBX_TRY(dev_alloc(h, &h->tiles, tiles.size()));
     GBX_TRY(dev_alloc(h, &h->hubs, hubs.size()));
-    GBX_TRY(dev_alloc(h, &h->msg[0], (size_t)K * q));
-    GBX_TRY(dev_alloc(h, &h->msg[1], (size_t)K * q));
+    GBX_TRY(dev_alloc(h, &h->msg[0], (size_t)K * h->qm));
+    GBX_TRY(dev_alloc(h, &h->msg[1], (size_t)K * h->qm));
     GBX_TRY(dev_alloc(h, &h->PSI, (size_t)n * q));
     GBX_TRY(dev_alloc(h, &h->theta, (size_t)h->n_global + MAXPEER));
     GBX_TRY(dev_alloc(h, &h->totals, (size_t)TOT_MAX));

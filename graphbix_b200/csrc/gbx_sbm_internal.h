@@ -47,6 +47,15 @@ constexpr int MAXCHUNK = 8;                      // a partitioned sweep is launc
 constexpr int TOT_MAX = 4 + 4 * MAXQ + MAXQ * MAXQ;  // doubles in a totals vector  // per-CTA partial row of the vertex kernels
 enum { MODE_SWEEP = 0, MODE_MARGINAL = 1, MODE_LOGZ = 2 };
 
+// Doubles between consecutive messages in the message / send / receive buffers.  Rows are padded to a whole number of
+// 32-byte sectors (q = 3 -> 4, 5..7 -> 8, 9..11 -> 12, 13..15 -> 16; pads are written as zeros): a 40-byte row stored
+// at a random place touches sectors it shares with its neighbours, and partial-sector writes cost a read-modify-write
+// in HBM (q = 5 ran 1.7x slower than q = 8 unpadded).  q <= 2 stays packed.
+#ifndef GBX_PAD_SMALL_Q
+#define GBX_PAD_SMALL_Q 0
+#endif
+constexpr int msg_stride(int q) { return (q <= 2 && !GBX_PAD_SMALL_Q) ? q : (q + 3) / 4 * 4; }
+
 constexpr int tile_vertices(int q) { return (q <= 8) ? TILE_V / 2 : TILE_V / 4; }
 
 struct SbmOps;
@@ -61,6 +70,7 @@ struct GlobalGraph {
 
 struct gbx_sbm {
   int device = 0, q = 0;
+  int qm = 0;                     // gbx::msg_stride(q): doubles per message row in msg / sendbuf / recvbuf
   int64_t n = 0, K = 0;           // vertices / directed-edge slots owned by this handle (all of them when world == 1)
   int64_t n_global = 0, K_global = 0;
   int rank = 0, world = 1;

@@ -29,6 +29,7 @@ constexpr int MODEL = GBX_MODEL;  // 0: full-affinity SBM (sbm.jl), 1: community
 constexpr int MODEL_SBM = 0, MODEL_MOD = 1;
 constexpr int Q = GBX_Q;
 constexpr int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+constexpr int QM = msg_stride(Q);    // doubles per message row (padded to whole 32-B sectors)
 constexpr int QP = next_pow2(Q);     // lanes per vertex in the aggregation stage (padding lanes idle when Q != 2^k)
 constexpr int LV = QP;
 constexpr int TV = tile_vertices(Q);
@@ -182,12 +183,12 @@ __device__ __forceinline__ void emit_message(const VertexArgs& a, const double* 
   const int owner = rev_owner(rv), slot = rev_slot(rv);
   if (a.damping != 1.0) {
     double old[Q];
-    load_vec<Q>(a.curp[owner], slot, old);
+    load_msg<Q, QM>(a.curp[owner], slot, old);
     const double al = a.damping, be = 1.0 - a.damping;
 #pragma unroll
     for (int t = 0; t < Q; ++t) w[t] = be * old[t] + al * w[t];
   }
-  store_vec<Q>(a.nxtp[owner], slot, w);
+  store_msg<Q, QM>(a.nxtp[owner], slot, w);
 }
 
 // ---- M-step statistics fused into the sweep ------------------------------------------------------------
@@ -445,10 +446,13 @@ __device__ __forceinline__ void store_partials(const LaneAcc& acc, double* scrat
 //   stage 1  one thread per incoming edge slot: psi row from smem, T = theta theta psi*Crs, rescaled   -> smem
 //   stage 2  QP lanes per vertex: product of the T's, prior, clamp floor, marginal, residual            -> smem
 //   stage 3  one thread per edge slot: cavity = product / own factor, clamp, normalise, damp, scatter to rev[e]
-constexpr int ROWB = Q * 8;                                  // bytes of one message
-constexpr int CHB = (Q % 2 == 0) ? 16 : 8;                   // cp.async unit
-constexpr int CH = ROWB / CHB;                               // units per message
-constexpr bool SWZ = (Q == 4 || Q == 8 || Q == 16);          // power-of-two rows: rotate units to dodge bank conflicts
+constexpr int ROWB = QM * 8;                                 // bytes of one message row (padded)
+constexpr int CHB = (QM % 2 == 0) ? 16 : 8;                  // cp.async unit
+constexpr int CH = ROWB / CHB;                               // units per message row
+constexpr bool SWZ = (QM == 4 || QM == 8 || QM == 16);       // power-of-two rows: rotate units to dodge bank conflicts
+constexpr int PROWB = Q * 8;                                 // bytes of one row of PSI (not padded)
+constexpr int PCHB = (Q % 2 == 0) ? 16 : 8;
+constexpr int PCH = PROWB / PCHB;
 constexpr int SWZ_DIV = (CH >= 8) ? 1 : 8 / CH;
 
 __device__ __forceinline__ int swz_unit(int row, int c) {
@@ -496,6 +500,11 @@ struct SweepSmem {
 __device__ __forceinline__ void cp_async_unit(void* smem_dst, const void* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);  // folds to base + offset after inlining
   if constexpr (CHB == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_punit(void* smem_dst, const void* gsrc) {  // a unit of a PSI row
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  if constexpr (PCHB == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
   else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
@@ -555,8 +564,8 @@ __device__ __forceinline__ void stage_tile(const VertexArgs& a, const int4& td, 
   if (tid <= nv) cp_async_4(buf + StageBuf::rp_off + tid * 4, a.rowptr + v0 + tid);
   if (tid < nv) cp_async_4(buf + StageBuf::pi_off + tid * 4, a.pidx + v0 + tid);
   if (MODE == MODE_SWEEP) {
-    const char* osrc = reinterpret_cast<const char*>(a.PSI) + (size_t)v0 * ROWB;
-    for (int g = tid; g < nv * CH; g += NT) cp_async_unit(buf + StageBuf::old_off + g * CHB, osrc + (size_t)g * CHB);
+    const char* osrc = reinterpret_cast<const char*>(a.PSI) + (size_t)v0 * PROWB;
+    for (int g = tid; g < nv * PCH; g += NT) cp_async_punit(buf + StageBuf::old_off + g * PCHB, osrc + (size_t)g * PCHB);
   }
 }
 
@@ -564,10 +573,10 @@ __device__ __forceinline__ void read_staged(const char* buf, int row, double (&p
   const char* r = buf + StageBuf::psi_off + row * ROWB;
   if constexpr (CHB == 16) {
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
+    for (int c = 0; c < (Q + 1) / 2; ++c) {  // the units that hold components (the rest of a padded row is zeros)
       const double2 v = *reinterpret_cast<const double2*>(r + swz_unit(row, c) * 16);
       psi[2 * c] = v.x;
-      psi[2 * c + 1] = v.y;
+      if (2 * c + 1 < Q) psi[2 * c + 1] = v.y;
     }
   } else {
 #pragma unroll
@@ -830,7 +839,7 @@ __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base
   for (int e = e0 + tid; e < e1; e += NT) {
     double psi[Q], T[Q];
     int ke;
-    load_vec<Q>(a.cur, e, psi);
+    load_msg<Q, QM>(a.cur, e, psi);
     const double sc = (MODEL == MODEL_SBM && a.dc) ? th * a.theta[a.col[e]] : 1.0;
     edge_transform(psi, sc, T, ke);
     ksum += ke;
@@ -916,7 +925,7 @@ __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base
       if (e < e1) {
         double psi[Q], T[Q], w[Q];
         int ke;
-        load_vec<Q>(a.cur, e, psi);
+        load_msg<Q, QM>(a.cur, e, psi);
         const double sc = (MODEL == MODEL_SBM && a.dc) ? th * a.theta[a.col[e]] : 1.0;
         edge_transform(psi, sc, T, ke);
         emit_message(a, Ush, T, ffSh, fnSh + ke, a.rev[e], w);
@@ -1196,8 +1205,8 @@ __global__ void __launch_bounds__(NT) sbm_fe_kernel(const SbmState* st, const in
     // every undirected edge once: at the larger of its two global slots (the `i < j -> continue` of sbm.jl:166)
     if (rev_owner(r) < rank || (rev_owner(r) == rank && rev_slot(r) < e)) {
       double a[Q], b[Q];
-      load_vec<Q>(psi, e, b);                                   // j -> i   (i = row of e, j = col[e])
-      load_vec<Q>(peers.p[rev_owner(r)], rev_slot(r), a);       // i -> j   (in the row of j, possibly on a peer)
+      load_msg<Q, QM>(psi, e, b);                               // j -> i   (i = row of e, j = col[e])
+      load_msg<Q, QM>(peers.p[rev_owner(r)], rev_slot(r), a);   // i -> j   (in the row of j, possibly on a peer)
       double lc = -c_P.logN;
       if (dc) lc += log(theta[erow[e]]) + log(theta[col[e]]);
       double Z0 = 0.0, W = 0.0, L1 = 0.0, G1 = 0.0;
@@ -1271,10 +1280,10 @@ __global__ void k_permute_rows(const double* __restrict__ src, double* __restric
     if (to_slots) {
       if (!local) continue;
       load_vec<Q>(src, k, m);
-      store_vec<Q>(dst, s, m);
+      store_msg<Q, QM>(dst, s, m);
     } else {
       if (local) {
-        load_vec<Q>(src, s, m);
+        load_msg<Q, QM>(src, s, m);
       } else {
 #pragma unroll
         for (int t = 0; t < Q; ++t) m[t] = 0.0;
@@ -1308,7 +1317,7 @@ __global__ void k_random_messages(double* __restrict__ dst, const int* __restric
     }
 #pragma unroll
     for (int t = 0; t < Q; ++t) m[t] /= s;
-    store_vec<Q>(dst, slot, m);
+    store_msg<Q, QM>(dst, slot, m);
   }
 }
 
@@ -1395,13 +1404,13 @@ int launch_packed_sweep(gbx_sbm* h) {
   VertexArgs a = vertex_args(h);
   a.rev = h->rev_pack;
   for (int o = 0; o < h->world; ++o)
-    if (o != h->rank) a.nxtp[o] = h->sendbuf + (size_t)h->send_off[o] * Q;
+    if (o != h->rank) a.nxtp[o] = h->sendbuf + (size_t)h->send_off[o] * QM;
   const int G = h->grid_vertex, NC = h->nchunks;
   if (h->nhubs > 0) {
     sbm_hub_kernel<MODE_SWEEP><<<h->nhubs, NT, 0, h->stream>>>(a, NC * G);
     h->launches++;
   }
-  const size_t rowb = (size_t)Q * sizeof(double);
+  const size_t rowb = (size_t)QM * sizeof(double);
   double* const* dst = h->recvp[h->xparity];
   for (int c = 0; c < NC; ++c) {
     VertexArgs ac = a;
@@ -1423,8 +1432,8 @@ int launch_packed_sweep(gbx_sbm* h) {
       const long long b = h->chunk_send[c][o], e = h->chunk_send[c + 1][o];
       if (e <= b) continue;
       GBX_CUDA_TRY(cudaStreamWaitEvent(h->peer_stream[k], h->ev_piece[c], 0));
-      GBX_CUDA_TRY(cudaMemcpyAsync(dst[o] + (size_t)(h->my_off_at[o] + b) * Q,
-                                   h->sendbuf + (size_t)(h->send_off[o] + b) * Q, (size_t)(e - b) * rowb,
+      GBX_CUDA_TRY(cudaMemcpyAsync(dst[o] + (size_t)(h->my_off_at[o] + b) * QM,
+                                   h->sendbuf + (size_t)(h->send_off[o] + b) * QM, (size_t)(e - b) * rowb,
                                    cudaMemcpyDeviceToDevice, h->peer_stream[k]));
     }
   }
@@ -1441,13 +1450,13 @@ int launch_packed_sweep(gbx_sbm* h) {
 
 // Rows received from the other ranks (parity of the last sweep) -> their slots of the (new) current message buffer.
 __global__ void k_unpack(const double* __restrict__ recv, const int* __restrict__ slot, long long rows, double* __restrict__ msg) {
-  constexpr int U = (Q % 2 == 0) ? Q / 2 : Q;  // 16-B units per row when the row is a whole number of them
+  constexpr int U = (QM % 2 == 0) ? QM / 2 : QM;  // 16-B units per (padded) row when it is a whole number of them
   const long long total = rows * U;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / U;
     const int c = (int)(i - r * U);
     const long long s = slot[r];
-    if constexpr (Q % 2 == 0)
+    if constexpr (QM % 2 == 0)
       reinterpret_cast<double2*>(msg)[s * U + c] = reinterpret_cast<const double2*>(recv)[i];
     else
       msg[s * U + c] = recv[i];
@@ -1465,7 +1474,7 @@ int op_unpack(gbx_sbm* h) {
     // called after the sweep's buffer swap: h->cur is the buffer the sweep wrote
     GBX_CUDA_TRY(cudaEventRecord(h->ev_piece[0], h->stream));  // after the all-reduce: every rank's rows have landed
     GBX_CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_piece[0], 0));
-    k_unpack<<<grid_for(h, h->send_total * ((Q % 2 == 0) ? Q / 2 : Q)), 256, 0, h->copy_stream>>>(
+    k_unpack<<<grid_for(h, h->send_total * ((QM % 2 == 0) ? QM / 2 : QM)), 256, 0, h->copy_stream>>>(
         h->recvbuf[parity], h->unpack_slot, (long long)h->send_total, h->msg[h->cur]);
     h->launches++;
     GBX_CUDA_TRY(cudaGetLastError());
@@ -1718,8 +1727,8 @@ __global__ void __launch_bounds__(NT) mod_fe_kernel(const SbmState* st, const in
     const int2 er = make_int2((int)i, rev[i]);
     if (!(rev_owner(er.y) < rank || (rev_owner(er.y) == rank && rev_slot(er.y) < er.x))) continue;  // each edge once
     double a[Q], b[Q];
-    load_vec<Q>(psi, er.x, b);
-    load_vec<Q>(peers.p[rev_owner(er.y)], rev_slot(er.y), a);
+    load_msg<Q, QM>(psi, er.x, b);
+    load_msg<Q, QM>(peers.p[rev_owner(er.y)], rev_slot(er.y), a);
     double di = 1.0, dj = 1.0;
     if (dc) {  // degrees of both endpoints: `degs` is indexed by global vertex id (every rank's, like theta)
       di = degs[erow[er.x]];

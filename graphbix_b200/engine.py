@@ -206,8 +206,11 @@ class ModEngine:
         self.n, self.q, self.K = int(Ntot), int(B), int(links.shape[0])
         colmajor = np.asfortranarray(links, dtype=np.int64)
         self._h = C.c_void_p()
+        self.timings = {}
+        t0 = time.perf_counter()
         check(self.lib.gbx_mod_create(C.byref(self._h), int(device), self.n, self.K,
                                       colmajor.ctypes.data_as(C.POINTER(C.c_int64)), self.q))
+        self.timings["create"] = time.perf_counter() - t0
         self.opt = ModOptions()
         self.lib.gbx_mod_default_options(C.byref(self.opt))
         if stream is not None:
@@ -235,11 +238,15 @@ class ModEngine:
     def init(self, gr, psicav=None, seed: int = 0):
         gr = _f64(gr, (self.q,))
         psicav = _f64(psicav, (self.K, self.q))
+        t0 = time.perf_counter()
         check(self.lib.gbx_mod_init(self._h, _dp(gr), _dp(psicav), C.c_uint64(seed)))
+        self.timings["init"] = time.perf_counter() - t0
 
     def em(self) -> ModResult:
         res = ModResult()
+        t0 = time.perf_counter()
         check(self.lib.gbx_mod_em(self._h, C.byref(res)))
+        self.timings["em"] = time.perf_counter() - t0
         return res
 
     def iterate(self, n: int = 1, read_conv: bool = True):
@@ -255,7 +262,9 @@ class ModEngine:
     def state(self):
         q, n = self.q, self.n
         gr, h, P, par = np.empty(q), np.empty(q), np.empty((n, q)), np.empty(4)
+        t0 = time.perf_counter()
         check(self.lib.gbx_mod_get_state(self._h, _dp(gr), _dp(P), _dp(h), _dp(par)))
+        self.timings["get_state"] = time.perf_counter() - t0
         return dict(gr=gr, PSI=P, h=h, alpha=par[0], beta=par[1], omegain=par[2], omegaout=par[3])
 
     def messages(self):
