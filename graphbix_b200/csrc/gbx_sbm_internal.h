@@ -48,13 +48,10 @@ constexpr int TOT_MAX = 4 + 4 * MAXQ + MAXQ * MAXQ;  // doubles in a totals vect
 enum { MODE_SWEEP = 0, MODE_MARGINAL = 1, MODE_LOGZ = 2 };
 
 // Doubles between consecutive messages in the message / send / receive buffers.  Rows are padded to a whole number of
-// 32-byte sectors (q = 3 -> 4, 5..7 -> 8, 9..11 -> 12, 13..15 -> 16; pads are written as zeros): a 40-byte row stored
-// at a random place touches sectors it shares with its neighbours, and partial-sector writes cost a read-modify-write
-// in HBM (q = 5 ran 1.7x slower than q = 8 unpadded).  q <= 2 stays packed.
-#ifndef GBX_PAD_SMALL_Q
-#define GBX_PAD_SMALL_Q 0
-#endif
-constexpr int msg_stride(int q) { return (q <= 2 && !GBX_PAD_SMALL_Q) ? q : (q + 3) / 4 * 4; }
+// 32-byte sectors (q = 1..3 -> 4, 5..7 -> 8, 9..11 -> 12, 13..15 -> 16; pads are written as zeros): a 40-byte row
+// stored at a random place touches sectors it shares with its neighbours, and partial-sector writes cost a
+// read-modify-write in HBM (unpadded, q = 5 ran 1.7x slower than q = 8 and q = 2 slower than q = 4).
+constexpr int msg_stride(int q) { return (q + 3) / 4 * 4; }
 
 constexpr int tile_vertices(int q) { return (q <= 8) ? TILE_V / 2 : TILE_V / 4; }
 
