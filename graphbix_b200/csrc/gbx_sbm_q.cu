@@ -1066,7 +1066,7 @@ __global__ void sbm_apply_totals(SbmState* st, const double* __restrict__ tot, c
     const double* G = tot + TOT_G;
     const double Cold = st->C[tid];
     const double Cn = Cold * 0.5 * (G[s * Q + t] + G[t * Q + s]);  // Crsnew is symmetric (both directions of a link)
-    double c = lr * Cn / (N * g[s] * g[t]) + (1.0 - lr) * Cold;    // sbm.jl:137
+    double c = lr * Cn / (N * (g[s] * g[t])) + (1.0 - lr) * Cold;  // sbm.jl:137; (g g) first: bitwise symmetric in s, t
     if (c > maxCrs) c = maxCrs; else if (c < 0.0) c = 0.0;          // sbm.jl:138-146
     if (!(c == c)) st->status |= 1;
     st->C[tid] = c;
