@@ -368,20 +368,20 @@ def run_ours(a):
     eng.close()
 
     # ---- end to end through EM() with host buffers ----
-    psi0 = random_messages(K, a.q, seed=55 + rank)
-    # the call's host inputs live in pinned memory (links exactly as Julia would hand them over: column-major)
+    # The call a user of the reference makes: EM(Ntot, B, links, ...) -- the initial messages are drawn inside, as in
+    # sbm.jl:319-323 (here on the device from a seed), so the host inputs are `links` (pinned, column-major as Julia
+    # hands it over) and the outputs PSI, gr, Crs and the scalars.
     links_pin = torch.from_numpy(np.asfortranarray(links)).pin_memory()
-    psi0_pin = torch.from_numpy(psi0).pin_memory()
-    links_h, psi0_h = links_pin.numpy(), psi0_pin.numpy()
+    links_h = links_pin.numpy()
     barrier()
     t0 = time.perf_counter()
-    out, eng2, res2 = EM(n, a.q, links_h, n, (gr0, C0), bool(a.dc), a.steps, True, 0.3, PSIcav0=psi0_h,
+    out, eng2, res2 = EM(n, a.q, links_h, n, (gr0, C0), bool(a.dc), a.steps, True, 0.3, seed=55 + rank,
                          BPconvthreshold=0.0, device=local, return_engine=True)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     e2e_parts = dict(eng2.timings)
     eng2.close()
-    h2d = links.nbytes + psi0.nbytes
+    h2d = links.nbytes
     d2h = out[2].nbytes + out[1].nbytes + out[0].nbytes
 
     t = torch.tensor([ms, sweep_ms, t_e2e], dtype=torch.float64, device="cuda")
@@ -423,7 +423,7 @@ def run_ours(a):
                            "step": "one EM iteration = BP sweep + update_Crs + update_theta"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / a.steps,
                         "d2h_bytes_per_step": d2h / a.steps, "seconds": t_e2e, "breakdown_s": e2e_parts,
-                        "what": "EM() with host buffers: CSR build, H2D, steps iterations, free energy + CV, D2H"},
+                        "what": "EM() with host buffers: H2D of links, CSR build, random initial messages (device), steps iterations, free energy + CV, D2H of PSI / gr / Crs"},
                 "gpu_launches": launches, "clocks": sampler.summary(),
                 "roofline": {"bound": "hbm", "kernel": "sbm_vertex_kernel<8,SWEEP> (BP sweep)", "achieved": achieved,
                              "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

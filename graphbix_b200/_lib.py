@@ -93,6 +93,8 @@ SIGNATURES = {
     "gbx_sbm_ipc_import": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]),
     "gbx_sbm_part_set_buffers": (C.c_int, [_P, _P, _P]),
     "gbx_sbm_part_set_exchange": (C.c_int, [_P, C.c_int]),
+    "gbx_trim_cache": (C.c_int, []),
+    "gbx_cached_bytes": (C.c_int64, [C.c_int]),
     "gbx_sbm_step": (C.c_int, [_P, C.c_int, C.c_int]),
     "gbx_sbm_read_residual": (C.c_int, [_P, _D]),
 }

@@ -100,10 +100,12 @@ int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* 
   unsigned long long *keys = nullptr, *keys2 = nullptr;
   int *vals = nullptr, *vals2 = nullptr, *deg = nullptr, *err = nullptr;
   void* tmp = nullptr;
+  const int dv = h->device;
+  const bool pooled = h->world == 1;
   auto cleanup = [&]() {
-    cudaFree(g_rowptr); cudaFree(g_col); cudaFree(g_rev); cudaFree(g_erow);
-    cudaFree(d_links); cudaFree(keys); cudaFree(keys2); cudaFree(vals); cudaFree(vals2); cudaFree(deg);
-    cudaFree(err); cudaFree(tmp);
+    dev_free(dv, g_rowptr); dev_free(dv, g_col); dev_free(dv, g_rev); dev_free(dv, g_erow);
+    dev_free(dv, d_links); dev_free(dv, keys); dev_free(dv, keys2); dev_free(dv, vals); dev_free(dv, vals2);
+    dev_free(dv, deg); dev_free(dv, err); dev_free(dv, tmp);
   };
   auto fail = [&](int rc) { cleanup(); return rc; };
 #define GBX_C(expr)                                                                      \
@@ -114,12 +116,12 @@ int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* 
       return fail(GBX_ERR_CUDA);                                                         \
     }                                                                                    \
   } while (0)
-#define GBX_T(ptr, count) GBX_C(cudaMalloc((void**)&(ptr), std::max<size_t>((size_t)(count), 1) * sizeof(*(ptr))))
+#define GBX_T(ptr, count) GBX_C(dev_malloc(dv, (void**)&(ptr), std::max<size_t>((size_t)(count), 1) * sizeof(*(ptr)), pooled))
   GBX_T(g_rowptr, n + 1);
   GBX_T(g_col, K);
   GBX_T(g_rev, K);
   GBX_T(g_erow, K);
-  GBX_C(cudaMalloc((void**)&h->slot_of_link, std::max<size_t>((size_t)K, 1) * sizeof(int)));
+  GBX_C(dev_malloc(dv, (void**)&h->slot_of_link, std::max<size_t>((size_t)K, 1) * sizeof(int), pooled));
   h->dev_bytes += (int64_t)K * sizeof(int);
   // `links` may already live on this device (a partitioned run whose edge list was generated or received there)
   const int64_t* links = nullptr;
@@ -152,7 +154,7 @@ int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* 
   cub::DeviceScan::ExclusiveSum(nullptr, tb1, deg, g_rowptr, (int)(n + 1), st);
   cub::DeviceRadixSort::SortPairs(nullptr, tb2, keys, keys2, vals, vals2, (int)K, 0, bits, st);
   const size_t tb = std::max(tb1, tb2);
-  GBX_C(cudaMalloc(&tmp, tb ? tb : 1));
+  GBX_C(dev_malloc(dv, &tmp, tb ? tb : 1, pooled));
   size_t t = tb;
   GBX_C(cub::DeviceScan::ExclusiveSum(tmp, t, deg, g_rowptr, (int)(n + 1), st));
   if (K > 0) {
@@ -168,7 +170,8 @@ int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* 
   GBX_C(cudaStreamSynchronize(st));
   GBX_C(cudaGetLastError());
   // the sort workspace is the peak of the build: give it back before the per-rank arrays are allocated
-  cudaFree(d_links); cudaFree(keys); cudaFree(keys2); cudaFree(vals); cudaFree(vals2); cudaFree(deg); cudaFree(tmp);
+  dev_free(dv, d_links); dev_free(dv, keys); dev_free(dv, keys2); dev_free(dv, vals); dev_free(dv, vals2);
+  dev_free(dv, deg); dev_free(dv, tmp);
   d_links = nullptr; keys = keys2 = nullptr; vals = vals2 = deg = nullptr; tmp = nullptr;
   if (herr & ERR_RANGE) { last_error() = "links: vertex id out of 1..n"; return fail(GBX_ERR_INVALID); }
   if (herr & ERR_SELF) { last_error() = "links: self loop (run simplegraph first)"; return fail(GBX_ERR_INVALID); }
@@ -197,7 +200,7 @@ int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* 
     }
   auto keep = [&](void** p, size_t bytes) -> cudaError_t {
     h->dev_bytes += (int64_t)bytes;
-    return cudaMalloc(p, bytes ? bytes : 1);
+    return dev_malloc(dv, p, bytes ? bytes : 1, pooled);
   };
   GBX_C(keep((void**)&h->rowptr, (size_t)(h->n + 1) * sizeof(int)));
   GBX_C(keep((void**)&h->col, (size_t)h->K * sizeof(int)));
@@ -225,7 +228,7 @@ int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* 
 
 void free_global(GlobalGraph* g) {
   if (!g) return;
-  cudaFree(g->col);
+  cudaFree(g->col);  // only kept for partitioned handles, which never use the block cache
   cudaFree(g->rev);
   g->col = g->rev = nullptr;
 }

@@ -10,6 +10,8 @@
 //   * PSI (N x q), theta (N); tiles = runs of consecutive vertices with <= 256 edge slots (one CTA iteration
 //     each, one thread per slot); vertices with more than 256 edges ("hubs") get a CTA each.
 #include <algorithm>
+#include <chrono>
+#include <mutex>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -73,7 +75,7 @@ int fail_state() {
 template <typename T>
 int dev_alloc(gbx_sbm* h, T** p, size_t count) {
   const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-  GBX_CUDA_TRY(cudaMalloc((void**)p, bytes));
+  GBX_CUDA_TRY(dev_malloc(h->device, (void**)p, bytes, h->world == 1));
   h->dev_bytes += (int64_t)bytes;
   return GBX_OK;
 }
@@ -174,8 +176,43 @@ void gbx_sbm_default_options(gbx_sbm_options* opt) {
   opt->check_every = 1;
 }
 
+// Pinned mirrors of SbmState are recycled too (cudaMallocHost costs about a millisecond).
+static std::mutex g_pin_mutex;
+static std::vector<SbmState*> g_pin_free;
+static cudaError_t pinned_state_alloc(SbmState** p) {
+  {
+    std::lock_guard<std::mutex> g(g_pin_mutex);
+    if (!g_pin_free.empty()) {
+      *p = g_pin_free.back();
+      g_pin_free.pop_back();
+      return cudaSuccess;
+    }
+  }
+  return cudaMallocHost((void**)p, sizeof(SbmState));
+}
+static void pinned_state_free(SbmState* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> g(g_pin_mutex);
+  if (g_pin_free.size() < 64) g_pin_free.push_back(p);
+  else cudaFreeHost(p);
+}
+
+// GBX_TIMING=1: host wall time of the phases of gbx_*_create on stderr.
+struct PhaseTimer {
+  bool on = getenv("GBX_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!on) return;
+    cudaDeviceSynchronize();
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[gbx create] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+    t = now;
+  }
+};
+
 static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t K, const int64_t* links, int q,
                         int rank = 0, int world = 1) {
+  PhaseTimer pt;
   if (!out) return fail_invalid("out is NULL");
   *out = nullptr;
   if (q < 1 || q > MAXQ) return fail_invalid("q must be in 1..16");
@@ -209,21 +246,24 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
   std::vector<int> rowptr;     // this rank's (rebased)
   GlobalGraph gg;              // global columns / reverse slots, alive until the exchange plan is built
   {
-    cudaDeviceProp prop;
+    int major = 0, sms = 0;
     cudaError_t ce = cudaSetDevice(device);
-    if (ce == cudaSuccess) ce = cudaGetDeviceProperties(&prop, device);
+    if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (ce != cudaSuccess) {
-      last_error() = std::string("cudaSetDevice/cudaGetDeviceProperties: ") + cudaGetErrorString(ce);
+      last_error() = std::string("cudaSetDevice/cudaDeviceGetAttribute: ") + cudaGetErrorString(ce);
       delete h;
       return GBX_ERR_CUDA;
     }
-    if (prop.major < 10) {
+    if (major < 10) {
       last_error() = "libgraphbix_cuda is built for sm_100a (B200) only";
       delete h;
       return GBX_ERR_CUDA;
     }
-    h->num_sms = prop.multiProcessorCount;
+    h->num_sms = sms;
+    pt.lap("device properties");
     const int rcb = build_graph_device(h, links, &rowptr_g, &gg);
+    pt.lap("build_graph_device");
     if (rcb != GBX_OK) {
       const std::string keep = last_error();
       gbx_sbm_destroy(h);
@@ -262,6 +302,7 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
   }
 
   h->ntiles = (int)tiles.size();
+  pt.lap("tile schedule (host)");
   if (world > 1) {
     // pieces of a packed sweep: the exposed copy tail is 1/pieces of the boundary traffic, but many small all-to-all
     // copies run slower through the switch than a few large ones (measured: 2 GPUs best with 8, 8 GPUs with 2)
@@ -293,6 +334,7 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
     h->excm = sd > 0 ? sd2 / sd - 1.0 : 0.0;  // (d'd)/(N mean(d)) - 1
   }
   h->nhubs = (int)hubs.size();
+  pt.lap("degree statistics (host)");
   gbx_sbm_default_options(&h->opt);
   auto body = [&]() -> int {
     GBX_TRY(dev_alloc(h, &h->escale, (size_t)K));
@@ -320,7 +362,7 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
     GBX_CUDA_TRY(cudaMemcpy(h->tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice));
     GBX_CUDA_TRY(cudaMemcpy(h->hubs, hubs.data(), hubs.size() * sizeof(int), cudaMemcpyHostToDevice));
     GBX_CUDA_TRY(cudaMemset(h->st, 0, sizeof(SbmState)));
-    GBX_CUDA_TRY(cudaMallocHost((void**)&h->h_state, sizeof(SbmState)));
+    GBX_CUDA_TRY(pinned_state_alloc(&h->h_state));
     // persistent grids: a whole number of CTAs per SM
     int occ = 1, occm = 1;
     GBX_TRY(ops->occupancy(1, &occ, &occm));
@@ -340,6 +382,7 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
     return GBX_OK;
   };
   const int rc = body();
+  pt.lap("allocations + uploads");
   if (rc != GBX_OK) {
     const std::string keep = last_error();
     gbx_sbm_destroy(h);
@@ -354,19 +397,28 @@ int gbx_sbm_create(gbx_sbm** out, int device, int64_t n, int64_t K, const int64_
   return graph_create(0, out, device, n, K, links, q);
 }
 
+int gbx_trim_cache(void) {
+  pool_trim(-1);
+  return GBX_OK;
+}
+int64_t gbx_cached_bytes(int device) { return pool_cached_bytes(device); }
+
 int gbx_sbm_destroy(gbx_sbm* h) {
   if (!h) return GBX_OK;
   cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);  // blocks go back to the cache: nothing of this handle may still be running
+  for (int k = 1; k < MAXPEER; ++k)
+    if (h->peer_stream[k]) cudaStreamSynchronize(h->peer_stream[k]);
   for (int b = 0; b < 2; ++b)
     for (int r = 0; r < MAXPEER; ++r) {
       if (h->ipc_open[b][r]) cudaIpcCloseMemHandle(h->msgp[b][r]);
       if (h->ipc_open_recv[b][r]) cudaIpcCloseMemHandle(h->recvp[b][r]);
     }
-  cudaFree(h->rev_pack);
-  cudaFree(h->unpack_slot);
-  cudaFree(h->sendbuf);
-  cudaFree(h->recvbuf[0]);
-  cudaFree(h->recvbuf[1]);
+  dev_free(h->device, h->rev_pack);
+  dev_free(h->device, h->unpack_slot);
+  dev_free(h->device, h->sendbuf);
+  dev_free(h->device, h->recvbuf[0]);
+  dev_free(h->device, h->recvbuf[1]);
   for (int k = 2; k < MAXPEER; ++k)
     if (h->peer_stream[k]) cudaStreamDestroy(h->peer_stream[k]);
   for (int k = 0; k < MAXPEER; ++k)
@@ -376,30 +428,30 @@ int gbx_sbm_destroy(gbx_sbm* h) {
     if (h->ev_piece[c]) cudaEventDestroy(h->ev_piece[c]);
   if (h->ev_copied) cudaEventDestroy(h->ev_copied);
   if (h->ev_unpacked) cudaEventDestroy(h->ev_unpacked);
-  cudaFree(h->rowptr);
-  cudaFree(h->col);
-  cudaFree(h->rev);
-  cudaFree(h->erow);
-  cudaFree(h->escale);
-  cudaFree(h->slot_of_link);
-  cudaFree(h->tiles);
-  cudaFree(h->hubs);
-  cudaFree(h->msg[0]);
-  cudaFree(h->msg[1]);
-  cudaFree(h->PSI);
-  if (h->theta_owned) cudaFree(h->theta);
-  if (h->totals_owned) cudaFree(h->totals);
-  cudaFree(h->maxd_dev);
-  cudaFree(h->deg_global);
-  cudaFree(h->pidx);
-  cudaFree(h->prior_tab);
-  cudaFree(h->st);
-  cudaFree(h->params);
-  cudaFree(h->part_vertex);
-  cudaFree(h->part_mstep);
-  cudaFree(h->part_theta);
-  cudaFree(h->part_fe);
-  if (h->h_state) cudaFreeHost(h->h_state);
+  dev_free(h->device, h->rowptr);
+  dev_free(h->device, h->col);
+  dev_free(h->device, h->rev);
+  dev_free(h->device, h->erow);
+  dev_free(h->device, h->escale);
+  dev_free(h->device, h->slot_of_link);
+  dev_free(h->device, h->tiles);
+  dev_free(h->device, h->hubs);
+  dev_free(h->device, h->msg[0]);
+  dev_free(h->device, h->msg[1]);
+  dev_free(h->device, h->PSI);
+  if (h->theta_owned) dev_free(h->device, h->theta);
+  if (h->totals_owned) dev_free(h->device, h->totals);
+  dev_free(h->device, h->maxd_dev);
+  dev_free(h->device, h->deg_global);
+  dev_free(h->device, h->pidx);
+  dev_free(h->device, h->prior_tab);
+  dev_free(h->device, h->st);
+  dev_free(h->device, h->params);
+  dev_free(h->device, h->part_vertex);
+  dev_free(h->device, h->part_mstep);
+  dev_free(h->device, h->part_theta);
+  dev_free(h->device, h->part_fe);
+  pinned_state_free(h->h_state);
   delete h;
   return GBX_OK;
 }

@@ -57,6 +57,12 @@ constexpr int tile_vertices(int q) { return (q <= 8) ? TILE_V / 2 : TILE_V / 4; 
 
 struct SbmOps;
 
+// gbx_pool.cu: device-memory block cache shared by the handles of a process.
+cudaError_t dev_malloc(int device, void** p, size_t bytes, bool pooled);
+void dev_free(int device, void* p);
+void pool_trim(int device);              // device < 0: every device
+int64_t pool_cached_bytes(int device);
+
 // Device copies of the global columns / reverse slots, kept between the graph build and the exchange plan.
 struct GlobalGraph {
   int* col = nullptr;

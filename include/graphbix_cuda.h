@@ -71,6 +71,12 @@ int gbx_version(void);
 const char* gbx_last_error(void);
 int gbx_device_count(void); /* number of visible CUDA devices, or GBX_ERR_CUDA */
 
+/* Device buffers of destroyed handles are kept for the next handle (the hosts call EM() once per q, initial condition
+ * and sample on the same graph, sbm.jl:912-943); gbx_trim_cache() gives them back to the driver.  Environment:
+ * GBX_POOL=0 disables the cache, GBX_POOL_MB=<n> caps it (default: a quarter of the device memory). */
+int gbx_trim_cache(void);
+int64_t gbx_cached_bytes(int device);
+
 void gbx_sbm_default_options(gbx_sbm_options* opt);
 
 /* Build the device-resident graph: destination-major CSR of the K = 2E directed edges, the
