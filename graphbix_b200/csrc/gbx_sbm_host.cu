@@ -131,13 +131,27 @@ int free_energy_steps(gbx_sbm* h) {
 }
 
 // One EM iteration, sbm.jl:343-347, with a synchronous sweep in place of BP().
-int em_iteration(gbx_sbm* h) {
+// The residual is final after apply_totals: its copy to the pinned mirror is queued there, before update_theta, so
+// that it has long arrived when the host asks for it (wait_residual) and the GPU never idles on the convergence test.
+int queue_residual(gbx_sbm* h) {
+  GBX_CUDA_TRY(cudaMemcpyAsync(&h->h_state->conv, &h->st->conv, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  GBX_CUDA_TRY(cudaEventRecord(h->ev_conv, h->stream));
+  return GBX_OK;
+}
+int wait_residual(gbx_sbm* h, double* conv) {
+  GBX_CUDA_TRY(cudaEventSynchronize(h->ev_conv));
+  *conv = h->h_state->conv;
+  return GBX_OK;
+}
+
+int em_iteration(gbx_sbm* h, bool want_residual = false) {
   const SbmOps* op = h->ops;
   GBX_TRY(op->prepare(h, 0, 0));              // gr clamp, h = update_h()                        sbm.jl:102
   GBX_TRY(op->vertex_pass(h, MODE_SWEEP));    // messages, marginals, residual, M-step statistics sbm.jl:103-136
   h->cur ^= 1;
   GBX_TRY(op->local_totals(h, MODE_SWEEP));
   GBX_TRY(op->apply_totals(h, MODE_SWEEP));   // BPconv, gr, Crs = update_Crs()                  sbm.jl:120-123, 137-147
+  if (want_residual) GBX_TRY(queue_residual(h));
   if (h->opt.degreecorrection) {              // theta = update_theta()                          sbm.jl:345-347
     GBX_TRY(op->theta_local(h));
     GBX_TRY(op->theta_apply(h));
@@ -363,6 +377,7 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
     GBX_CUDA_TRY(cudaMemcpy(h->hubs, hubs.data(), hubs.size() * sizeof(int), cudaMemcpyHostToDevice));
     GBX_CUDA_TRY(cudaMemset(h->st, 0, sizeof(SbmState)));
     GBX_CUDA_TRY(pinned_state_alloc(&h->h_state));
+    GBX_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_conv, cudaEventDisableTiming));
     // persistent grids: a whole number of CTAs per SM
     int occ = 1, occm = 1;
     GBX_TRY(ops->occupancy(1, &occ, &occm));
@@ -427,6 +442,7 @@ int gbx_sbm_destroy(gbx_sbm* h) {
   for (int c = 0; c < MAXCHUNK; ++c)
     if (h->ev_piece[c]) cudaEventDestroy(h->ev_piece[c]);
   if (h->ev_copied) cudaEventDestroy(h->ev_copied);
+  if (h->ev_conv) cudaEventDestroy(h->ev_conv);
   if (h->ev_unpacked) cudaEventDestroy(h->ev_unpacked);
   dev_free(h->device, h->rowptr);
   dev_free(h->device, h->col);
@@ -578,10 +594,12 @@ int gbx_sbm_em(gbx_sbm* h, gbx_sbm_result* res) {
   int cnv = 0, itrnum = 0;
   if (!h->fail) {
     for (int itr = 1; itr <= h->opt.itrmax; ++itr) {
-      GBX_TRY(em_iteration(h));
-      if (itr % h->opt.check_every == 0 || itr == h->opt.itrmax) {
-        GBX_TRY(read_state(h));
-        if (h->h_state->conv < h->opt.bp_conv_threshold) {  // sbm.jl:348-353
+      const bool check = itr % h->opt.check_every == 0 || itr == h->opt.itrmax;
+      GBX_TRY(em_iteration(h, check));
+      if (check) {
+        double conv;
+        GBX_TRY(wait_residual(h, &conv));
+        if (conv < h->opt.bp_conv_threshold) {  // sbm.jl:348-353
           cnv = 1;
           itrnum = itr;
           break;
@@ -730,13 +748,14 @@ int gbx_mod_init(gbx_mod* h, const double* gr, const double* psicav, uint64_t se
   return GBX_OK;
 }
 
-static int mod_iteration(gbx_sbm* h) {
+static int mod_iteration(gbx_sbm* h, bool want_residual = false) {
   const SbmOps* op = h->ops;
   GBX_TRY(op->prepare(h, 0, 0));              // h = update_h()                                    mod.jl:56
   GBX_TRY(op->vertex_pass(h, MODE_SWEEP));    // messages, marginals, residual, omega statistic     mod.jl:57-88
   h->cur ^= 1;
   GBX_TRY(op->local_totals(h, MODE_SWEEP));
   GBX_TRY(op->apply_totals(h, MODE_SWEEP));   // conv; gr = update_gr(PSI); omegas, alpha, beta     mod.jl:221-229
+  if (want_residual) GBX_TRY(queue_residual(h));
   h->itr++;
   return GBX_OK;
 }
@@ -793,10 +812,12 @@ int gbx_mod_em(gbx_mod* h, gbx_mod_result* res) {
   GBX_TRY(set_device(h));
   int cnv = 0, itrnum = 0;
   for (int itr = 1; itr <= h->mopt.itrmax; ++itr) {
-    GBX_TRY(mod_iteration(h));
-    if (itr % h->mopt.check_every == 0 || itr == h->mopt.itrmax) {
-      GBX_TRY(read_state(h));
-      if (h->h_state->conv < h->mopt.bp_conv_threshold) {  // mod.jl:230-234
+    const bool check = itr % h->mopt.check_every == 0 || itr == h->mopt.itrmax;
+    GBX_TRY(mod_iteration(h, check));
+    if (check) {
+      double conv;
+      GBX_TRY(wait_residual(h, &conv));
+      if (conv < h->mopt.bp_conv_threshold) {  // mod.jl:230-234
         cnv = 1;
         itrnum = itr;
         break;

@@ -115,6 +115,7 @@ struct gbx_sbm {
   double *part_vertex = nullptr, *part_mstep = nullptr, *part_theta = nullptr, *part_fe = nullptr;
   int grid_vertex = 0, grid_mstep = 0, grid_theta = 0, grid_fe = 0;
   gbx::SbmState* h_state = nullptr;  // pinned mirror
+  cudaEvent_t ev_conv = nullptr;     // the residual of the last iteration has reached h_state->conv
   int itr = 0;
   // ---- packed boundary exchange of a partitioned run (exchange == 1) -------------------------------------------
   // The sweep stores a message for a row of rank o at the next position of this rank's send run for o (positions
