@@ -211,6 +211,18 @@ static void pinned_state_free(SbmState* p) {
   else cudaFreeHost(p);
 }
 
+__global__ void k_fill(double* __restrict__ p, long long n, double v) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+static int fill_async(gbx_sbm* h, double* p, int64_t n, double v) {
+  if (n <= 0) return GBX_OK;
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)h->num_sms * 8);
+  k_fill<<<grid, 256, 0, h->stream>>>(p, (long long)n, v);
+  h->launches++;
+  GBX_CUDA_TRY(cudaGetLastError());
+  return GBX_OK;
+}
+
 // GBX_TIMING=1: host wall time of the phases of gbx_*_create on stderr.
 struct PhaseTimer {
   bool on = getenv("GBX_TIMING") != nullptr;
@@ -336,9 +348,9 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
   h->model = model;
   gbx_mod_default_options(&h->mopt);
   {
-    // mod.jl:155 constshift = sum_i d_i log d_i / L and mod.jl:185 excm, from the true degrees
+    // mod.jl:155 constshift = sum_i d_i log d_i / L and mod.jl:185 excm, from the true degrees (mod.jl handles only)
     double sdl = 0.0, sd2 = 0.0, sd = 0.0;
-    for (int64_t v = 0; v < h->n_global; ++v) {
+    for (int64_t v = 0; model == 1 && v < h->n_global; ++v) {
       const double d = (double)(rowptr_g[(size_t)v + 1] - rowptr_g[(size_t)v]);
       if (d > 0) sdl += d * std::log(d);
       sd2 += d * d;
@@ -360,8 +372,8 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
     GBX_TRY(dev_alloc(h, &h->theta, (size_t)h->n_global + MAXPEER));
     GBX_TRY(dev_alloc(h, &h->totals, (size_t)TOT_MAX));
     GBX_TRY(dev_alloc(h, &h->maxd_dev, 1));
-    GBX_TRY(dev_alloc(h, &h->deg_global, (size_t)h->n_global));
-    {
+    if (model == 1) {  // degree of every vertex by global id: the field of mod.jl's sweep and free energy
+      GBX_TRY(dev_alloc(h, &h->deg_global, (size_t)h->n_global));
       std::vector<double> dg((size_t)h->n_global);
       for (int64_t v = 0; v < h->n_global; ++v) dg[(size_t)v] = (double)(rowptr_g[(size_t)v + 1] - rowptr_g[(size_t)v]);
       GBX_CUDA_TRY(cudaMemcpy(h->deg_global, dg.data(), dg.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -514,10 +526,8 @@ int gbx_sbm_init(gbx_sbm* h, const double* gr_init, const double* Crs_init, cons
   GBX_TRY(h->ops->init_model(h));  // theta = 1: row 0 of the prior table
   GBX_TRY(load_messages(h, psicav, seed));
   {
-    std::vector<double> ones((size_t)std::max<int64_t>(h->n_global, h->K), 1.0);  // theta = ones(Ntot,1), sbm.jl:277
-    GBX_CUDA_TRY(cudaMemcpyAsync(h->theta, ones.data(), (size_t)h->n_global * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    GBX_CUDA_TRY(cudaMemcpyAsync(h->escale, ones.data(), (size_t)h->K * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    GBX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    GBX_TRY(fill_async(h, h->theta, h->n_global, 1.0));  // theta = ones(Ntot,1), sbm.jl:277
+    GBX_TRY(fill_async(h, h->escale, h->K, 1.0));
   }
   if (!h->fail && h->world == 1) {
     // PSI = updatePSI() with h = 0, then gr = update_gr(PSI): sbm.jl:340-341
@@ -595,10 +605,16 @@ int gbx_sbm_em(gbx_sbm* h, gbx_sbm_result* res) {
   if (!h->fail) {
     for (int itr = 1; itr <= h->opt.itrmax; ++itr) {
       const bool check = itr % h->opt.check_every == 0 || itr == h->opt.itrmax;
-      GBX_TRY(em_iteration(h, check));
+      static const bool early = getenv("GBX_EARLY_RESIDUAL") ? atoi(getenv("GBX_EARLY_RESIDUAL")) != 0 : true;
+      GBX_TRY(em_iteration(h, check && early));
       if (check) {
         double conv;
-        GBX_TRY(wait_residual(h, &conv));
+        if (early) {
+          GBX_TRY(wait_residual(h, &conv));
+        } else {
+          GBX_TRY(read_state(h));
+          conv = h->h_state->conv;
+        }
         if (conv < h->opt.bp_conv_threshold) {  // sbm.jl:348-353
           cnv = 1;
           itrnum = itr;

@@ -14,3 +14,8 @@ if c and "error" in c:
     print("convergence leg failed:", c["error"])
 elif c:
     print(f"em_convergence: total {c['seconds_total']:.2f}s :", " ".join(f"q{r['q']}:{r['iterations']}it/{r['seconds']*1e3:.0f}ms{'' if r['converged'] else '(!)'}" for r in c["runs"]))
+b = d.get("batched_graphs")
+if b and "error" in b:
+    print("batch leg failed:", b["error"])
+elif b:
+    print(f"batched_graphs: {b['graphs']} graphs in {b['seconds']:.2f}s = {b['graphs_per_sec']:.1f} graphs/s  converged {b['converged_fraction']:.2f}  mean it {b['mean_iterations']:.0f}  overlap {b['overlap_by_epsilon']}")
