@@ -3,15 +3,17 @@
 // unrolled with the affinity matrix as uniform-register operands from __constant__ memory.
 //
 // Kernel map (reference lines each one replaces):
-//   sbm_vertex_kernel<MODE>  BP sweep over tiled vertices           sbm.jl:83-126 (BP, logunnormalizedMessage)
-//   sbm_hub_kernel<MODE>     the same for vertices of degree > 256
-//   sbm_reduce_vertex        residual, gr update, block degree means sbm.jl:120-123, 47-58
-//   sbm_mstep_kernel         per-edge joint marginals -> Crsnew      sbm.jl:128-136
-//   sbm_reduce_mstep         Crs update + clamp                      sbm.jl:137-147
-//   sbm_theta_kernel         update_theta, S_theta for update_h      sbm.jl:47-64, 70-73
-//   sbm_prepare              gr clamp, h, logs -> __constant__       sbm.jl:89-96, 70-73
-//   sbm_fe_kernel<PASS>      log Z_ij, CV errors per edge            sbm.jl:162-200
-//   sbm_finalize             FE, CV errors, variances                sbm.jl:201-212
+//   sbm_vertex_kernel<MODE>  BP sweep over tiled vertices + M-step statistics   sbm.jl:83-136 (mod.jl:38-88)
+//   sbm_hub_kernel<MODE>     the same for vertices of degree > 128 (one CTA per vertex)
+//   sbm_local_totals         per-CTA partial rows -> this rank's totals vector (one block per column, fixed order)
+//   sbm_apply_totals         residual, gr, block degree means, Crs update + clamp sbm.jl:120-123, 47-58, 137-147
+//   sbm_theta_kernel         update_theta, S_theta for update_h                  sbm.jl:47-64, 70-73
+//   sbm_escale_kernel        theta_row * theta_col per edge slot
+//   sbm_prepare / sbm_prior_table   gr clamp, h, logs -> __constant__; prior factors per (degree, block) sbm.jl:89-96, 70-73
+//   sbm_fe_kernel<PASS>      log Z_ij, CV errors per edge                        sbm.jl:162-200
+//   sbm_finalize             FE, CV errors, variances                            sbm.jl:201-212
+//   k_unpack                 partitioned runs: received boundary rows -> message buffer
+//   mod_*                    the scalar bookkeeping and free energy of mod.jl's model (GBX_MODEL == 1)
 #ifndef GBX_Q
 #error "compile with -DGBX_Q=<number of groups>"
 #endif
