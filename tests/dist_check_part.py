@@ -22,7 +22,8 @@ def main():
     ok = True
     # (vertices, q, degree correction, exchange mode, hubs): 120k vertices -> the packed sweep runs in several pieces
     cases = ((4000, 3, True, 1, False), (4000, 8, True, 1, False), (4000, 8, False, 0, False), (4000, 8, True, 0, False),
-             (3000, 8, True, 1, True), (120000, 8, True, 1, False), (120000, 2, False, 1, False))
+             (3000, 8, True, 1, True), (3000, 5, True, 1, True), (4000, 5, False, 0, False),
+             (120000, 8, True, 1, False), (120000, 2, False, 1, False))
     if os.environ.get("GBX_PART_CASES"):
         import ast
         cases = ast.literal_eval(os.environ["GBX_PART_CASES"])

@@ -73,7 +73,7 @@ def _with_hubs(n, q, seed):
     return n0, links, psi0
 
 
-@pytest.mark.parametrize("q", [2, 8])
+@pytest.mark.parametrize("q", [2, 5, 8, 16])
 def test_hub_vertices(gpu_required, q):
     n, links, psi0 = _with_hubs(1500, q, seed=5)
     deg = np.bincount(links[:, 0])
@@ -82,16 +82,17 @@ def test_hub_vertices(gpu_required, q):
     _run_pair(n, links, q, psi0, gr0, C0, 4, dc=True, prior=True)
 
 
-def test_clamp_regime(gpu_required):
-    """Tiny affinities push unnormalised values below 1e-8, where the absolute clamp of sbm.jl:42 binds."""
-    q = 3
+@pytest.mark.parametrize("q,dc", [(3, False), (3, True), (5, True), (8, True)])
+def test_clamp_regime(gpu_required, q, dc):
+    """Tiny affinities push unnormalised values below 1e-8, where the absolute clamp of sbm.jl:42 binds (with degree
+    correction the theta factors move the true magnitudes the clamp is applied to)."""
     n, links, psi0, _ = planted_case(400, q, 10.0, 0.1, seed=21)
     gr0 = np.ones(q) / q
     C0 = 1e-3 * np.eye(q) + 1e-5 * np.ones((q, q))
     from graphbix_b200.engine import SbmEngine
-    ref = SyncSBM(n, links, q, gr0, C0, psi0, dc=False, prior=True, lr=0.0)
+    ref = SyncSBM(n, links, q, gr0, C0, psi0, dc=dc, prior=True, lr=0.0)
     eng = SbmEngine(n, links, q)
-    eng.set_options(degreecorrection=0, priorlearning=1, learningrate=0.0)
+    eng.set_options(degreecorrection=int(dc), priorlearning=1, learningrate=0.0)
     eng.init(gr0, C0, psi0)
     for it in range(3):
         ref.iterate()
