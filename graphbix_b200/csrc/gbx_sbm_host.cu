@@ -237,7 +237,7 @@ struct PhaseTimer {
 };
 
 static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t K, const int64_t* links, int q,
-                        int rank = 0, int world = 1) {
+                        int rank = 0, int world = 1, bool stepped = false) {
   PhaseTimer pt;
   if (!out) return fail_invalid("out is NULL");
   *out = nullptr;
@@ -267,6 +267,7 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
   h->K_global = K;
   h->rank = rank;
   h->world = world;
+  h->stepped = stepped;
   h->ops = ops;
   std::vector<int> rowptr_g;   // global row pointers
   std::vector<int> rowptr;     // this rank's (rebased)
@@ -529,7 +530,7 @@ int gbx_sbm_init(gbx_sbm* h, const double* gr_init, const double* Crs_init, cons
     GBX_TRY(fill_async(h, h->theta, h->n_global, 1.0));  // theta = ones(Ntot,1), sbm.jl:277
     GBX_TRY(fill_async(h, h->escale, h->K, 1.0));
   }
-  if (!h->fail && h->world == 1) {
+  if (!h->fail && !h->stepped) {
     // PSI = updatePSI() with h = 0, then gr = update_gr(PSI): sbm.jl:340-341
     // (a partitioned run does this through gbx_sbm_step so that the ranks can all-reduce the totals in between)
     GBX_TRY(h->ops->prepare(h, 1, 0));
@@ -545,7 +546,7 @@ int gbx_sbm_init(gbx_sbm* h, const double* gr_init, const double* Crs_init, cons
 int gbx_sbm_iterate(gbx_sbm* h, int n_iters, double* bpconv_out) {
   if (!h) return fail_invalid("handle is NULL");
   if (!h->initialised) return fail_state();
-  if (h->world > 1 && n_iters > 0) return fail_invalid("partitioned handle: drive the loop with gbx_sbm_step");
+  if (h->stepped && n_iters > 0) return fail_invalid("partitioned handle: drive the loop with gbx_sbm_step");
   GBX_TRY(set_device(h));
   for (int i = 0; i < n_iters; ++i) GBX_TRY(em_iteration(h));
   if (bpconv_out) {
@@ -571,7 +572,7 @@ int gbx_sbm_finalize(gbx_sbm* h, gbx_sbm_result* res) {
   if (!h || !res) return fail_invalid("handle/result is NULL");
   if (!h->initialised) return fail_state();
   GBX_TRY(set_device(h));
-  if (!h->fail && h->world == 1) {
+  if (!h->fail && !h->stepped) {
     GBX_TRY(h->ops->prepare(h, 0, 1));  // h = update_h(); gr = update_gr(PSI)   sbm.jl:364-365
     GBX_TRY(free_energy_steps(h));      // freeenergy()                          sbm.jl:366
   }
@@ -599,7 +600,7 @@ int gbx_sbm_finalize(gbx_sbm* h, gbx_sbm_result* res) {
 int gbx_sbm_em(gbx_sbm* h, gbx_sbm_result* res) {
   if (!h || !res) return fail_invalid("handle/result is NULL");
   if (!h->initialised) return fail_state();
-  if (h->world > 1) return fail_invalid("partitioned handle: drive the loop with gbx_sbm_step (see engine_dist.py)");
+  if (h->stepped) return fail_invalid("partitioned handle: drive the loop with gbx_sbm_step (see engine_dist.py)");
   GBX_TRY(set_device(h));
   int cnv = 0, itrnum = 0;
   if (!h->fail) {
@@ -752,7 +753,7 @@ int gbx_mod_init(gbx_mod* h, const double* gr, const double* psicav, uint64_t se
   h->fail = 0;
   GBX_TRY(h->ops->init_model(h));  // prior-table row per vertex: by degree when degree corrected
   GBX_TRY(load_messages(h, psicav, seed));
-  if (h->world == 1) {
+  if (!h->stepped) {
     // h = zeros(1,B); PSI = updatePSI(): mod.jl:204-206
     GBX_TRY(h->ops->prepare(h, 1, 0));
     GBX_TRY(h->ops->vertex_pass(h, MODE_MARGINAL));
@@ -779,7 +780,7 @@ static int mod_iteration(gbx_sbm* h, bool want_residual = false) {
 int gbx_mod_iterate(gbx_mod* h, int n_iters, double* bpconv_out) {
   if (!h) return fail_invalid("handle is NULL");
   if (!h->initialised || h->model != 1) return fail_state();
-  if (h->world > 1 && n_iters > 0) return fail_invalid("partitioned handle: drive the loop with gbx_sbm_step");
+  if (h->stepped && n_iters > 0) return fail_invalid("partitioned handle: drive the loop with gbx_sbm_step");
   GBX_TRY(set_device(h));
   for (int i = 0; i < n_iters; ++i) GBX_TRY(mod_iteration(h));
   if (bpconv_out) {
@@ -794,7 +795,7 @@ int gbx_mod_finalize(gbx_mod* h, gbx_mod_result* res) {
   if (!h->initialised || h->model != 1) return fail_state();
   GBX_TRY(set_device(h));
   memset(res, 0, sizeof *res);
-  if (h->world == 1) {
+  if (!h->stepped) {
     GBX_TRY(h->ops->prepare(h, 0, 0));   // h = update_h()   mod.jl:240
     GBX_TRY(free_energy_steps(h));       // freeenergy()     mod.jl:241
   }
@@ -824,7 +825,7 @@ int gbx_mod_finalize(gbx_mod* h, gbx_mod_result* res) {
 int gbx_mod_em(gbx_mod* h, gbx_mod_result* res) {
   if (!h || !res) return fail_invalid("handle/result is NULL");
   if (!h->initialised || h->model != 1) return fail_state();
-  if (h->world > 1) return fail_invalid("partitioned handle: drive the loop with gbx_sbm_step");
+  if (h->stepped) return fail_invalid("partitioned handle: drive the loop with gbx_sbm_step");
   GBX_TRY(set_device(h));
   int cnv = 0, itrnum = 0;
   for (int itr = 1; itr <= h->mopt.itrmax; ++itr) {
@@ -866,11 +867,11 @@ int64_t gbx_mod_launch_count(const gbx_mod* h) { return gbx_sbm_launch_count(h);
 // ---------------------------------------------------------------------------------------------
 int gbx_sbm_create_part(gbx_sbm** out, int device, int64_t n, int64_t K, const int64_t* links, int q, int rank,
                         int world) {
-  return graph_create(0, out, device, n, K, links, q, rank, world);
+  return graph_create(0, out, device, n, K, links, q, rank, world, true);
 }
 int gbx_mod_create_part(gbx_mod** out, int device, int64_t n, int64_t K, const int64_t* links, int q, int rank,
                         int world) {
-  return graph_create(1, out, device, n, K, links, q, rank, world);
+  return graph_create(1, out, device, n, K, links, q, rank, world, true);
 }
 
 int gbx_sbm_part_info(const gbx_sbm* h, int64_t* info) {

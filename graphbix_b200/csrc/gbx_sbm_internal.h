@@ -77,6 +77,7 @@ struct gbx_sbm {
   int64_t n = 0, K = 0;           // vertices / directed-edge slots owned by this handle (all of them when world == 1)
   int64_t n_global = 0, K_global = 0;
   int rank = 0, world = 1;
+  bool stepped = false;           // created by gbx_*_create_part: the host drives every step (gbx_sbm_step)
   int64_t vbeg = 0, sbeg = 0;     // first global vertex / first global slot of this rank
   int64_t vbeg_all[gbx::MAXPEER + 1] = {0}, sbeg_all[gbx::MAXPEER + 1] = {0};
   cudaStream_t stream = nullptr;

@@ -66,7 +66,7 @@ class PartEngine:
                                                 C.c_void_p(self.theta.data_ptr())))
         check(self.lib.gbx_sbm_set_stream(self._h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         # peer pointers of both message buffers and both receive buffers of every rank
-        for which in (0, 1, 2, 3):
+        for which in ((0, 1, 2, 3) if self.world > 1 else ()):
             buf = (C.c_ubyte * 64)()
             check(self.lib.gbx_sbm_ipc_export(self._h, which, buf))
             handles = [None] * self.world
@@ -171,9 +171,8 @@ class PartEngine:
                 self._step(STEP_THETA_LOCAL)
                 self._allreduce(q)
                 self._step(STEP_THETA_APPLY)
-                mine = self.theta[r * c:(r + 1) * c].clone()
-                self._tick("clone(theta)")
-                self.dist.all_gather_into_tensor(self.theta, mine)
+                # in place: this rank's slice of the output is its input (NCCL's in-place all-gather layout)
+                self.dist.all_gather_into_tensor(self.theta, self.theta[r * c:(r + 1) * c])
                 self._sync("all_gather(theta)")
                 self._step(STEP_ESCALE)
             self._step(STEP_COUNT_ITERATION)
