@@ -253,7 +253,14 @@ def run_partitioned(a, torch, dist, world, rank, local):
         print("partitioned step profile (ms per iteration, incl. warm-up iterations):",
               {k: round(v / (a.steps + a.warmup), 4) for k, v in prof.items()}, file=sys.stderr)
     eng.close()
+    qm = (a.q + 3) // 4 * 4                      # message rows are padded to whole 32-B sectors
+    boundary = cut * K / world * qm * 8          # bytes that leave (and enter) each GPU per sweep, on average
     return {"value": K * a.steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / a.steps, "n_vertices": n,
+            "boundary_bytes_per_gpu_per_step": boundary,
+            "nvlink_egress_gbs_if_exchange_alone": boundary / (ms / a.steps * 1e-3) / 1e9,
+            "nvlink_note": ("lower bound of the link rate the exchange sustains (whole iteration time in the denominator); "
+                            "NCCL all-to-all alone moves this volume at 586 GB/s per GPU on 8 B200 "
+                            "(profiles/r01_a2a_probe_8gpu.txt)"),
             "avg_degree": deg, "directed_edges": K, "directed_edges_rank0": slots, "cut_fraction": cut,
             "vertex_numbering": "random" if a.part_shuffle else "by planted group",
             "exchange": "packed runs pushed by the copy engine, unpacked by the owner" if a.part_exchange else
