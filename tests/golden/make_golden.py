@@ -1,4 +1,4 @@
-"""Generates tests/golden/sbm_em_*.npz: inputs and converged outputs of the ORACLE (oracle/sbm_oracle.py, the
+"""Generates tests/golden/{sbm,mod,lsbm}_em_*.npz: inputs and converged outputs of the ORACLE (oracle/sbm_oracle.py, the
 restatement of the reference's EM(), src/sbm.jl:28-370) on small planted-partition graphs.
 
 The reference itself cannot run here (no Julia), so these are oracle outputs, not reference outputs;
@@ -57,6 +57,41 @@ def main_mod():
                               r.varCVMAP]), itrnum=r.itrnum)
 
 
+LABELED_CASES = [
+    # name, n, B, mean degree per label, kind per label, seed, dc
+    ("B2_G2_dc", 240, 2, [5.0, 4.0], ["a", "d"], 3, True),
+    ("B2_G2_nodc", 240, 2, [5.0, 4.0], ["a", "d"], 4, False),
+    ("B3_G2_dc", 300, 3, [6.0, 4.0], ["a", "a"], 5, True),
+]
+
+
+def main_labeled():
+    """Fixtures for the labeled SBM of the reference's notebook (DESIGN.md row (f'); its CUDA path is the next row)."""
+    from oracle import labeled_oracle as L
+    for name, n, B, cs, kinds, seed, dc in LABELED_CASES:
+        links, lab = L.labeled_planted_partition(n, B, cs, kinds, eps=0.08, seed=seed)
+        n = int(links[:, :2].max())
+        G = len(cs)
+        und = links[links[:, 0] < links[:, 1]]
+        Larray = [int((und[:, 2] == a + 1).sum()) for a in range(G)]
+        rng = np.random.default_rng(seed + 100)
+        K = len(links)
+        psi0 = rng.random((K, B)) * 0.5
+        psi0[np.arange(K), lab[links[:, 0] - 1]] += 1.0
+        psi0 /= psi0.sum(1, keepdims=True)
+        aff0 = L.initial_affinity(n, K, Larray, B, G, dc, 0, kinds, 1 / B)
+        r = L.EM(n, Larray, B, G, links, 4000, 1e-12, True, True, dc, 0.3, 0, kinds, 1 / B, rng=rng, PSIcav0=psi0)
+        print("labeled", name, "n", n, "K", K, "cnv", r.cnv, "itr", r.itrs_done, "FE", r.FE)
+        if not r.cnv:
+            print("   -> oracle did not converge, skipped")
+            continue
+        np.savez_compressed(
+            os.path.join(HERE, f"lsbm_em_{name}.npz"), n=n, B=B, G=G, links=links, Larray=np.array(Larray), psi0=psi0,
+            affinity0=aff0, dc=dc, lr=0.3, tol=1e-12, labels=lab, gr=r.gr, affinity=r.affinity, PSI=r.PSI,
+            PSIcav=r.PSIcav, scalars=np.array([r.FE, r.CVBayes, r.CVGP, r.CVGT, r.CVMAP, r.varCVBayes, r.varCVGP,
+                                               r.varCVGT, r.varCVMAP]), itrnum=r.itrnum)
+
+
 def main():
     for name, n, q, deg, eps, seed, dc, prior, init in CASES:
         n, links, psi0, lab = planted_case(n, q, deg, eps, seed)
@@ -78,7 +113,9 @@ def main():
 
 
 if __name__ == "__main__":
-    if "mod" in sys.argv[1:]:
+    if "labeled" in sys.argv[1:]:
+        main_labeled()
+    elif "mod" in sys.argv[1:]:
         main_mod()
     elif "sbm" in sys.argv[1:]:
         main()
