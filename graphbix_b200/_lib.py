@@ -47,6 +47,18 @@ class ModResult(C.Structure):
                 ("itrs_done", C.c_int), ("nonfinite", C.c_int), ("BPconv", C.c_double), ("max_dpsi", C.c_double)]
 
 
+class LsbmOptions(C.Structure):
+    _fields_ = [("dc", C.c_int), ("learning", C.c_int), ("priorlearning", C.c_int), ("learningrate", C.c_double),
+                ("itrmax", C.c_int), ("bp_conv_threshold", C.c_double), ("REDfrac", C.c_double), ("damping", C.c_double)]
+
+
+class LsbmResult(C.Structure):
+    _fields_ = [("FE", C.c_double), ("CVBayes", C.c_double), ("CVGP", C.c_double), ("CVGT", C.c_double),
+                ("CVMAP", C.c_double), ("varCVBayes", C.c_double), ("varCVGP", C.c_double), ("varCVGT", C.c_double),
+                ("varCVMAP", C.c_double), ("cnv", C.c_int), ("itrnum", C.c_int), ("itrs_done", C.c_int),
+                ("nonfinite", C.c_int), ("BPconv", C.c_double)]
+
+
 # name -> (restype, argtypes); every symbol include/graphbix_cuda.h declares
 _P = C.c_void_p
 _D = C.POINTER(C.c_double)
@@ -93,6 +105,18 @@ SIGNATURES = {
     "gbx_sbm_ipc_import": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]),
     "gbx_sbm_part_set_buffers": (C.c_int, [_P, _P, _P]),
     "gbx_sbm_part_set_exchange": (C.c_int, [_P, C.c_int]),
+    "gbx_lsbm_default_options": (None, [C.POINTER(LsbmOptions)]),
+    "gbx_lsbm_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.c_int, C.c_int]),
+    "gbx_lsbm_destroy": (C.c_int, [_P]),
+    "gbx_lsbm_set_stream": (C.c_int, [_P, C.c_void_p]),
+    "gbx_lsbm_set_options": (C.c_int, [_P, C.POINTER(LsbmOptions)]),
+    "gbx_lsbm_init": (C.c_int, [_P, _D, _D, _D]),
+    "gbx_lsbm_em": (C.c_int, [_P, C.POINTER(LsbmResult)]),
+    "gbx_lsbm_iterate": (C.c_int, [_P, C.c_int, _D]),
+    "gbx_lsbm_finalize": (C.c_int, [_P, C.POINTER(LsbmResult)]),
+    "gbx_lsbm_get_state": (C.c_int, [_P, _D, _D, _D, _D]),
+    "gbx_lsbm_get_messages": (C.c_int, [_P, _D]),
+    "gbx_lsbm_launch_count": (C.c_int64, [_P]),
     "gbx_trim_cache": (C.c_int, []),
     "gbx_cached_bytes": (C.c_int64, [C.c_int]),
     "gbx_sbm_step": (C.c_int, [_P, C.c_int, C.c_int]),

@@ -42,7 +42,7 @@ def _run(cmd):
 def build(qs=None, force=False, verbose=False):
     qs = sorted(set(qs or ALL_Q))
     os.makedirs(OBJ, exist_ok=True)
-    srcs = [os.path.join(HERE, f) for f in ("gbx_sbm_q.cu", "gbx_sbm_host.cu", "gbx_graph_build.cu", "gbx_pool.cu", "gbx_common.cuh",
+    srcs = [os.path.join(HERE, f) for f in ("gbx_sbm_q.cu", "gbx_sbm_host.cu", "gbx_graph_build.cu", "gbx_pool.cu", "gbx_lsbm.cu", "gbx_common.cuh",
                                             "gbx_sbm_internal.h")]
     srcs.append(os.path.join(os.path.dirname(PKG), "include", "graphbix_cuda.h"))
     stamp = os.path.join(OBJ, "stamp.txt")
@@ -62,6 +62,8 @@ def build(qs=None, force=False, verbose=False):
     jobs.append((go, [NVCC, *FLAGS, "-c", os.path.join(HERE, "gbx_graph_build.cu"), "-o", go]))
     po = os.path.join(OBJ, "gbx_pool.o")
     jobs.append((po, [NVCC, *FLAGS, "-c", os.path.join(HERE, "gbx_pool.cu"), "-o", po]))
+    lo = os.path.join(OBJ, "gbx_lsbm.o")
+    jobs.append((lo, [NVCC, *FLAGS, "-c", os.path.join(HERE, "gbx_lsbm.cu"), "-o", lo]))
     logs = []
     with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
         for out in ex.map(lambda j: _run(j[1]), jobs):

@@ -164,6 +164,52 @@ int gbx_mod_get_assignment(gbx_mod* h, int32_t* block);
 int64_t gbx_mod_launch_count(const gbx_mod* h);
 
 /* ------------------------------------------------------------------------------------------------
+ * Labeled SBM (edge labels alpha = 1..n_labels, one affinity matrix and one degree sequence per label):
+ *   gbx_lsbm_*  <->  function EM(Ntot,Larray,B,G,links,itrmax,BPconvthreshold,learning,priorlearning,dc,learningrate,
+ *                                REDfrac,assortativity,Omega)   src/labeled_sbm/labeled-sbmBIX_0.2.3.8_Julia0.6.2.ipynb
+ * `links3` is the notebook's K x 3 Int64 matrix (i, j, label) in column-major order, both directions of every edge with
+ * the same label (`labeledsimplegraph`).  The initial affinity matrices (notebook EM, "initial state": from Larray,
+ * assortativity and Omega) and the random initial messages are computed by the host and handed over; affinity is
+ * double[n_labels][q][q].  First CUDA path of this model: correct and parity-tested, not yet tuned (gbx_lsbm.cu).
+ * ------------------------------------------------------------------------------------------------ */
+#define GBX_MAX_LABELS 4
+typedef struct gbx_lsbm gbx_lsbm;
+
+typedef struct gbx_lsbm_options {
+  int dc;                   /* degree correction: degrees[i,alpha] = alpha-labelled links at i, else all ones (default 1) */
+  int learning;             /* update the affinity matrices (default 1)                                                   */
+  int priorlearning;        /* update gr (default 1)                                                                      */
+  double learningrate;      /* default 0.3                                                                                */
+  int itrmax;               /* default 512                                                                                */
+  double bp_conv_threshold; /* default 1e-6                                                                               */
+  double REDfrac;           /* != 0: the last label holds the randomly discarded edges, its matrix stays flat at 1/K      */
+  double damping;           /* synchronous-update damping, (0,1]; 1 = undamped (default)                                  */
+} gbx_lsbm_options;
+
+typedef struct gbx_lsbm_result {
+  double FE, CVBayes, CVGP, CVGT, CVMAP;
+  double varCVBayes, varCVGP, varCVGT, varCVMAP;
+  int cnv, itrnum, itrs_done, nonfinite;
+  double BPconv;
+} gbx_lsbm_result;
+
+void gbx_lsbm_default_options(gbx_lsbm_options* opt);
+int gbx_lsbm_create(gbx_lsbm** out, int device, int64_t n_vertices, int64_t n_links, const int64_t* links3, int q,
+                    int n_labels);
+int gbx_lsbm_destroy(gbx_lsbm* h);
+int gbx_lsbm_set_stream(gbx_lsbm* h, void* cuda_stream);
+int gbx_lsbm_set_options(gbx_lsbm* h, const gbx_lsbm_options* opt);
+/* gr[q], affinity[n_labels][q][q], psicav[K][q] (rows in `links3` order); then PSI = updatePSI(), h = update_h(). */
+int gbx_lsbm_init(gbx_lsbm* h, const double* gr, const double* affinity, const double* psicav);
+int gbx_lsbm_em(gbx_lsbm* h, gbx_lsbm_result* res);                  /* the main loop + freeenergy()          */
+int gbx_lsbm_iterate(gbx_lsbm* h, int n_iters, double* bpconv_out);  /* n x (update_h, BP sweep, gr, affinity) */
+int gbx_lsbm_finalize(gbx_lsbm* h, gbx_lsbm_result* res);            /* freeenergy()                          */
+/* gr[q], affinity[n_labels][q][q], PSI[N][q], hfield[n_labels][q]; any may be NULL */
+int gbx_lsbm_get_state(gbx_lsbm* h, double* gr, double* affinity, double* PSI, double* hfield);
+int gbx_lsbm_get_messages(gbx_lsbm* h, double* psicav);
+int64_t gbx_lsbm_launch_count(const gbx_lsbm* h);
+
+/* ------------------------------------------------------------------------------------------------
  * Vertex-partitioned runs (BASELINE.json configs[3]): one process per GPU of one NVLink domain, <= 8 ranks.
  * Rank r owns the vertices [r*c, min(n,(r+1)*c)), c = ceil(n/world), and the rows of their incoming messages.
  * New messages into rows of another rank are stored straight into that rank's buffer over NVLink (peer pointers

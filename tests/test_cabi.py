@@ -34,6 +34,11 @@ def test_struct_layouts_match_header():
     assert (opt.degreecorrection, opt.priorlearning, opt.itrmax, opt.check_every) == (1, 1, 256, 1)
     assert opt.learningrate == pytest.approx(0.3) and opt.bp_conv_threshold == pytest.approx(1e-6)
     assert opt.damping == 1.0 and opt.maxCrs == 0.0
+    lopt = _lib.LsbmOptions()
+    _lib.load().gbx_lsbm_default_options(ctypes.byref(lopt))
+    assert (lopt.dc, lopt.learning, lopt.priorlearning, lopt.itrmax) == (1, 1, 1, 512)
+    assert lopt.learningrate == pytest.approx(0.3) and lopt.bp_conv_threshold == pytest.approx(1e-6)
+    assert lopt.REDfrac == 0.0 and lopt.damping == 1.0
 
 
 def test_no_cpu_fallback():

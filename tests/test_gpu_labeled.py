@@ -1,0 +1,82 @@
+"""Labeled SBM (the reference's notebook model; gbx_lsbm_* / graphbix_b200.labeled): the CUDA path against the numpy
+statement of its synchronous schedule sweep by sweep, and against the oracle's fixed points (tests/golden/lsbm_em_*.npz,
+asynchronous schedule) with north_star's tolerances."""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from sync_model_labeled import SyncLabeled
+
+pytestmark = pytest.mark.gpu
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "lsbm_em_*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[8:-4] for p in GOLDEN])
+@pytest.mark.parametrize("red", [False, True])
+def test_labeled_sweeps_match_sync_model(gpu_required, path, red):
+    from graphbix_b200.labeled import LabeledEngine
+    g = np.load(path)
+    n, B, G, dc = int(g["n"]), int(g["B"]), int(g["G"]), bool(g["dc"])
+    gr0 = np.ones(B) / B
+    ref = SyncLabeled(n, g["links"], B, G, gr0, g["affinity0"], g["psi0"], dc=dc, red=red)
+    eng = LabeledEngine(n, g["links"], B, G)
+    eng.set_options(dc=int(dc), REDfrac=0.5 if red else 0.0)
+    eng.init(gr0, g["affinity0"], g["psi0"])
+    st = eng.state()
+    np.testing.assert_allclose(st["PSI"], ref.PSI, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(st["h"], ref.h, rtol=1e-11)
+    for it in range(6):
+        cref = ref.iterate()
+        cgpu = eng.iterate(1)
+        st = eng.state()
+        np.testing.assert_allclose(cgpu, cref, rtol=1e-8, atol=1e-15, err_msg=f"conv it={it}")
+        np.testing.assert_allclose(st["PSI"], ref.PSI, rtol=0, atol=1e-12, err_msg=f"PSI it={it}")
+        np.testing.assert_allclose(eng.messages(), ref.psi, rtol=0, atol=1e-12, err_msg=f"messages it={it}")
+        np.testing.assert_allclose(st["gr"], ref.gr, rtol=1e-11, err_msg=f"gr it={it}")
+        np.testing.assert_allclose(st["affinity"], ref.aff, rtol=1e-10, err_msg=f"affinity it={it}")
+    res = eng.finalize()
+    f = ref.finalize()
+    for k in ("FE", "CVBayes", "CVGP", "CVGT", "CVMAP", "varCVBayes", "varCVGP", "varCVGT", "varCVMAP"):
+        np.testing.assert_allclose(getattr(res, k), f[k], rtol=1e-9, err_msg=k)
+    assert res.nonfinite == 0
+    eng.close()
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[8:-4] for p in GOLDEN])
+def test_labeled_fixed_point_matches_oracle(gpu_required, path):
+    from graphbix_b200.labeled import EM_labeled
+    g = np.load(path)
+    n, B, G, dc = int(g["n"]), int(g["B"]), int(g["G"]), bool(g["dc"])
+    out = EM_labeled(n, list(g["Larray"]), B, G, g["links"], 4000, float(g["tol"]), True, True, dc, float(g["lr"]), 0,
+                     ["a", "d"], 1 / B, PSIcav0=g["psi0"], affinity0=g["affinity0"])
+    gr, aff, PSI = out[0], out[1], out[2]
+    assert out[12], "CUDA path did not converge"
+    assert np.abs(PSI - g["PSI"]).max() < 1e-6                          # marginals: 1e-6 max-abs per vertex
+    np.testing.assert_allclose(gr, g["gr"], rtol=1e-6)
+    np.testing.assert_allclose(aff, g["affinity"], rtol=1e-6)
+    np.testing.assert_allclose(np.array(out[3:12]), g["scalars"], rtol=1e-5)     # FE, CV errors, variances
+    assert np.array_equal(np.argmax(PSI, axis=1), np.argmax(g["PSI"], axis=1))    # identical assignments
+
+
+def test_labeled_input_checks(gpu_required):
+    from graphbix_b200 import _lib
+    lib = _lib.load()
+
+    def create(links3, G):
+        h = C.c_void_p()
+        a = np.asfortranarray(np.array(links3, dtype=np.int64))
+        rc = lib.gbx_lsbm_create(C.byref(h), 0, 3, a.shape[0], a.ctypes.data_as(C.POINTER(C.c_int64)), 2, G)
+        msg = lib.gbx_last_error().decode() if rc else ""
+        if rc == 0:
+            lib.gbx_lsbm_destroy(h)
+        return rc, msg
+
+    assert create([(1, 2, 1), (2, 1, 1), (2, 3, 2), (3, 2, 2)], 2)[0] == 0
+    rc, msg = create([(1, 2, 1), (2, 1, 1), (2, 3, 3), (3, 2, 3)], 2)
+    assert rc == -1 and "label" in msg
+    rc, msg = create([(1, 2, 1), (2, 1, 2)], 2)
+    assert rc == -1 and "directions" in msg
+    assert create([(1, 2, 1), (2, 1, 1)], 5)[0] == -1                  # more labels than GBX_MAX_LABELS
