@@ -63,6 +63,8 @@ def parse_args():
     ap.add_argument("--no-partitioned-leg", action="store_true")
     ap.add_argument("--no-convergence-leg", action="store_true")
     ap.add_argument("--no-batch-leg", action="store_true")
+    ap.add_argument("--no-labeled-leg", action="store_true")
+    ap.add_argument("--labeled-graphs", type=int, default=32, help="graphs per GPU of the labeled-SBM leg")
     ap.add_argument("--batch-graphs", type=int, default=128, help="graphs per GPU of the batched-graphs leg")
     return ap.parse_args()
 
@@ -359,6 +361,77 @@ def run_batch(a, torch, dist, world, rank, local):
             "mean_iterations": float(np.mean([x[2] if x[3] else 256 for x in res]))}
 
 
+def run_labeled(a, torch, dist, world, rank, local):
+    """BASELINE.json configs[4]: the labeled SBM of the reference's notebook on independent N = 10k graphs (two labels:
+    one assortative with mean degree 5, one disassortative with mean degree 3; 2 groups), a sweep over epsilon, dealt to
+    the GPUs round-robin, one EM() per graph through graphbix_b200.labeled.EM_labeled.  The CUDA path of this model is
+    the first correct one (log domain, thread per vertex), so this is a baseline to improve, not a tuned number.  Also
+    times the sweep on one large labeled graph (N = 1M, two labels of mean degree 8 each, q = 8)."""
+    from graphbix_b200.labeled import EM_labeled, LabeledEngine, initial_affinity
+    from graphbix_b200.parallel import my_share
+    from graphbix_b200.synth import labeled_planted_partition
+    n, B, G = 10_000, 2, 2
+    eps_list = [0.05, 0.15, 0.25, 0.35, 0.45, 0.55, 0.65, 0.75]
+    per_eps = max(1, a.labeled_graphs // len(eps_list))
+    tasks = [(e, s) for e in eps_list for s in range(per_eps * world)]
+    graphs = []
+    for pos, (eps, s) in my_share(tasks, rank, world):
+        links, lab = labeled_planted_partition(n, B, [5.0, 3.0], ["a", "d"], eps, seed=977 * s + int(eps * 100))
+        und = links[links[:, 0] < links[:, 1]]
+        graphs.append((pos, eps, links, lab, [int((und[:, 2] == k + 1).sum()) for k in range(G)]))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    res = []
+    for pos, eps, links, lab, Larray in graphs:
+        out = EM_labeled(n, Larray, B, G, links, 512, 1e-6, True, True, True, 0.3, 0, ["a", "d"], 1 / B,
+                         rng=np.random.default_rng(pos), device=local)
+        agree = float((np.argmax(out[2], axis=1) == lab).mean())
+        res.append((eps, (max(agree, 1 - agree) - 0.5) / 0.5, int(out[13]), bool(out[12])))
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, res)
+        res = [x for part in gathered for x in part]
+    dt = float(t.item())
+    by_eps = {}
+    for eps, ov, it, cnv in res:
+        by_eps.setdefault(round(eps, 2), []).append(ov)
+    out = {"workload": f"{len(tasks)} independent labeled graphs N={n}, labels: assortative c=5 + disassortative c=3, "
+                       f"q={B}, EM_labeled() with degree correction, itrmax 512, epsilon 0.05..0.75, {world} GPU(s)",
+           "graphs": len(tasks), "seconds": dt, "graphs_per_sec": len(tasks) / dt,
+           "overlap_by_epsilon": {str(k): round(float(np.mean(v)), 3) for k, v in sorted(by_eps.items())},
+           "converged_fraction": float(np.mean([x[3] for x in res])),
+           "mean_iterations": float(np.mean([x[2] if x[3] else 512 for x in res]))}
+    if rank == 0:   # device-resident rate of the (untuned) labeled sweep on one large graph
+        nb, q = 1_000_000, 8
+        links, _ = labeled_planted_partition(nb, q, [8.0, 8.0], ["a", "d"], 0.1, seed=5)
+        K = links.shape[0]
+        und = links[links[:, 0] < links[:, 1]]
+        Larray = [int((und[:, 2] == k + 1).sum()) for k in range(G)]
+        eng = LabeledEngine(nb, links, q, G, device=local, stream=torch.cuda.current_stream())
+        rng = np.random.default_rng(3)
+        psi0 = rng.random((K, q))
+        psi0 /= psi0.sum(axis=1, keepdims=True)
+        eng.init(np.ones(q) / q, initial_affinity(nb, K, Larray, q, G, True, 0, ["a", "d"], 1 / q), psi0)
+        eng.iterate(2, read_conv=False)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.iterate(5, read_conv=False)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        eng.close()
+        out["large_graph"] = {"n_vertices": nb, "directed_edges": K, "q": q, "labels": G, "ms_per_em_iteration": ms,
+                              "updates_per_sec": K / (ms * 1e-3)}
+    return out
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -477,6 +550,13 @@ def run_ours(a):
         except Exception as e:  # noqa: BLE001
             batch = {"error": f"{type(e).__name__}: {e}"[:400]}
 
+    labeled = None
+    if not a.no_labeled_leg:
+        try:
+            labeled = run_labeled(a, torch, dist, world, rank, local)
+        except Exception as e:  # noqa: BLE001
+            labeled = {"error": f"{type(e).__name__}: {e}"[:400]}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -498,6 +578,8 @@ def run_ours(a):
             line["em_convergence"] = conv
         if batch is not None:
             line["batched_graphs"] = batch
+        if labeled is not None:
+            line["labeled_graphs"] = labeled
         if part is not None:
             line["partitioned"] = part
             if a.mode == "partitioned":

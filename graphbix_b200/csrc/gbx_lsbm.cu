@@ -118,18 +118,21 @@ __global__ void k_lsbm_degrees(const int* __restrict__ rowptr, const unsigned ch
 }
 
 // ---- the sweep ----------------------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(256) k_lsbm_vertex(int n, int q, int G, const int* __restrict__ rowptr,
+// QT > 0: q known at compile time (loops unrolled, per-thread vectors in registers); QT == 0: any q <= 16.
+template <int MODE, int QT>
+__global__ void __launch_bounds__(256) k_lsbm_vertex(int n, int qrt, int G, const int* __restrict__ rowptr,
                                                      const int* __restrict__ col, const int* __restrict__ rev,
                                                      const unsigned char* __restrict__ lab, const double* __restrict__ deg,
                                                      const double* __restrict__ cur, double* __restrict__ nxt,
                                                      double* __restrict__ PSI, LParams* P, double N, double damping) {
   __shared__ double red[256];
+  const int q = QT > 0 ? QT : qrt;
+  constexpr int QA = QT > 0 ? QT : MAXQ;
   double acc = 0.0;  // residual (sweep) or sum of log Z_i
   for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
     const int i = i0 + threadIdx.x;
     if (i >= n) continue;
-    double x[MAXQ], w[MAXQ], term[MAXQ];
+    double x[QA], w[QA], term[QA];
     for (int t = 0; t < q; ++t) {
       double ext = 0.0;
       for (int a = 0; a < G; ++a) ext += deg[(size_t)i * G + a] * P->h[a][t];
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(256) k_lsbm_vertex(int n, int q, int G, const 
         const double dd = deg[(size_t)i * G + a] * deg[(size_t)col[e] * G + a];
         const double* psi = cur + (size_t)e * q;
         const double* A = P->aff[a];
-        double cav[MAXQ], m[MAXQ];
+        double cav[QA], m[QA];
         for (int t = 0; t < q; ++t) {
           double s = 0.0;
           for (int r = 0; r < q; ++r) s += psi[r] * A[r * q + t];
@@ -194,7 +197,8 @@ __global__ void __launch_bounds__(256) k_lsbm_denom(int n, int q, int G, const d
   for (int k = threadIdx.x; k < (LMAXG + 1) * MAXQ; k += blockDim.x) sh[k] = 0.0;
   __syncthreads();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    for (int t = 0; t < q; ++t) {
+    for (int t0 = 0; t0 < q; ++t0) {
+      const int t = (t0 + (int)threadIdx.x) % q;   // rotated: the lanes of a warp add to different addresses
       const double p = PSI[(size_t)i * q + t];
       atomicAdd(&sh[LMAXG * MAXQ + t], p);
       for (int a = 0; a < G; ++a) atomicAdd(&sh[a * MAXQ + t], deg[(size_t)i * G + a] * p);
@@ -231,8 +235,12 @@ __global__ void __launch_bounds__(256) k_lsbm_mstep(long long K, int q, int G, c
     for (int r = 0; r < q; ++r)
       for (int s = 0; s < q; ++s) sum += mij[r] * mji[s] * A[r * q + s];
     const double inv = 1.0 / sum;
-    for (int r = 0; r < q; ++r)
-      for (int s = 0; s < q; ++s) atomicAdd(&sh[(a * q + r) * q + s], mij[r] * mji[s] * A[r * q + s] * inv);
+    const int qq = q * q;
+    for (int k0 = 0; k0 < qq; ++k0) {
+      const int k = (k0 + (int)threadIdx.x) % qq;  // rotated: the lanes of a warp add to different addresses
+      const int r = k / q, s = k - r * q;
+      atomicAdd(&sh[a * qq + k], mij[r] * mji[s] * A[k] * inv);
+    }
   }
   __syncthreads();
   for (int k = threadIdx.x; k < G * q * q; k += blockDim.x) {
@@ -372,6 +380,12 @@ int l_sync_state(gbx_lsbm* h) {
   return GBX_OK;
 }
 
+int l_read_conv(gbx_lsbm* h) {  // the residual alone: 8 bytes instead of the whole parameter block
+  GBX_CUDA_TRY(cudaMemcpyAsync(&h->hP->conv, &h->P->conv, sizeof(double), cudaMemcpyDeviceToHost, h->g.stream));
+  GBX_CUDA_TRY(cudaStreamSynchronize(h->g.stream));
+  return GBX_OK;
+}
+
 int l_denom(gbx_lsbm* h) {
   k_lsbm_zero<<<1, 256, 0, h->g.stream>>>(h->P, 1);
   k_lsbm_denom<<<h->grid_v, 256, 0, h->g.stream>>>((int)h->g.n, h->q, h->G, h->deg, h->PSI, h->P);
@@ -380,14 +394,26 @@ int l_denom(gbx_lsbm* h) {
   return GBX_OK;
 }
 
-template <int MODE>
-int l_vertex(gbx_lsbm* h) {
-  k_lsbm_vertex<MODE><<<h->grid_v, 256, 0, h->g.stream>>>((int)h->g.n, h->q, h->G, h->g.rowptr, h->g.col, h->g.rev, h->lab,
-                                                          h->deg, h->msg[h->cur], h->msg[h->cur ^ 1], h->PSI, h->P,
-                                                          (double)h->g.n, h->opt.damping);
+template <int MODE, int QT>
+int l_vertex_q(gbx_lsbm* h) {
+  k_lsbm_vertex<MODE, QT><<<h->grid_v, 256, 0, h->g.stream>>>((int)h->g.n, h->q, h->G, h->g.rowptr, h->g.col, h->g.rev,
+                                                              h->lab, h->deg, h->msg[h->cur], h->msg[h->cur ^ 1], h->PSI,
+                                                              h->P, (double)h->g.n, h->opt.damping);
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
+}
+template <int MODE>
+int l_vertex(gbx_lsbm* h) {
+  switch (h->q) {
+    case 2: return l_vertex_q<MODE, 2>(h);
+    case 3: return l_vertex_q<MODE, 3>(h);
+    case 4: return l_vertex_q<MODE, 4>(h);
+    case 5: return l_vertex_q<MODE, 5>(h);
+    case 6: return l_vertex_q<MODE, 6>(h);
+    case 8: return l_vertex_q<MODE, 8>(h);
+    default: return l_vertex_q<MODE, 0>(h);
+  }
 }
 
 // one pass of the notebook's main loop: h = update_h(); BP(); gr and affinity updates
@@ -594,7 +620,7 @@ int gbx_lsbm_iterate(gbx_lsbm* h, int n_iters, double* bpconv_out) {
   GBX_CUDA_TRY(cudaSetDevice(h->g.device));
   for (int i = 0; i < n_iters; ++i) L_TRY(l_iteration(h));
   if (bpconv_out) {
-    L_TRY(l_sync_state(h));
+    L_TRY(l_read_conv(h));
     *bpconv_out = h->hP->conv;
   }
   return GBX_OK;
@@ -651,7 +677,7 @@ int gbx_lsbm_em(gbx_lsbm* h, gbx_lsbm_result* res) {
   for (int itr = 1; itr <= h->opt.itrmax; ++itr) {
     L_TRY(l_iteration(h));
     done = itr;
-    L_TRY(l_sync_state(h));
+    L_TRY(l_read_conv(h));
     if (h->hP->conv < h->opt.bp_conv_threshold) {
       cnv = 1;
       itrnum = itr;

@@ -121,3 +121,36 @@ def planted_partition_device(n: int, q: int, avg_degree: float, epsilon: float =
     links[0, E:] = hi + 1
     links[1, E:] = lo + 1
     return links, labels
+
+
+def labeled_planted_partition(n: int, B: int, c_by_label, kinds, epsilon: float = 0.1, seed: int = 0):
+    """Labeled planted partition in the spirit of the reference's `labeledSBMedgelist_Nblock=[300,300,300]_c=[5,3]_...`
+    sample: B equal groups; label alpha (1-based in the output) has mean degree c_by_label[alpha] and is assortative
+    ('a': c_out = epsilon c_in) or disassortative ('d': c_in = epsilon c_out).  A vertex pair carries at most one label.
+    Returns (links K x 3 int64 with both directions of every edge, planted labels 0..B-1)."""
+    rng = np.random.default_rng(seed)
+    lab = (np.arange(n) * B // n).astype(np.int64)
+    starts = (np.arange(B + 1) * n + B - 1) // B
+    los, his, als = [], [], []
+    for a, (c, kind) in enumerate(zip(c_by_label, kinds)):
+        w_in, w_out = (1.0, epsilon) if kind == "a" else (epsilon, 1.0)
+        p_in = w_in / (w_in + (B - 1) * w_out) if B > 1 else 1.0
+        m = int(rng.poisson(c * n / 2))
+        u = rng.integers(0, n, size=m)
+        gv = lab[u].copy()
+        if B > 1:
+            other = rng.random(m) >= p_in
+            gv[other] = (gv[other] + rng.integers(1, B, size=int(other.sum()))) % B
+        v = starts[gv] + (rng.random(m) * (starts[gv + 1] - starts[gv])).astype(np.int64)
+        v = np.minimum(v, starts[gv + 1] - 1)
+        keep = u != v
+        los.append(np.minimum(u, v)[keep])
+        his.append(np.maximum(u, v)[keep])
+        als.append(np.full(int(keep.sum()), a + 1, dtype=np.int64))
+    lo, hi, al = np.concatenate(los), np.concatenate(his), np.concatenate(als)
+    _, first = np.unique(lo * n + hi, return_index=True)
+    lo, hi, al = lo[first], hi[first], al[first]
+    links = np.empty((2 * lo.size, 3), dtype=np.int64)
+    links[: lo.size] = np.column_stack([lo + 1, hi + 1, al])
+    links[lo.size:] = np.column_stack([hi + 1, lo + 1, al])
+    return links, lab

@@ -1,7 +1,7 @@
 # usage (on the GPU box, through gpurun): bash scripts/gpu_cycle.sh [tests] [bench] [fullbench] [refbench] [launches] [prof_sweep] [part] [partrun] [benchN] [smoke]
 mkdir -p gpurun_out
 B="python bench.py --no-cpu-baseline"
-BP="$B --no-convergence-leg --no-batch-leg"   # profiler runs: the headline path only
+BP="$B --no-convergence-leg --no-batch-leg --no-labeled-leg"   # profiler runs: the headline path only
 for what in "$@"; do
 case $what in
 tests) python -m pytest tests -m gpu -x -q 2>&1 | tail -15 ;;
