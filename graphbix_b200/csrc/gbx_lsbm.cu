@@ -258,35 +258,81 @@ __global__ void __launch_bounds__(256) k_lsbm_denom(int n, int q, int G, const d
 }
 
 // affinitynew[alpha] += PSIij / sum(PSIij), once per undirected link (i < j); the factor degrees * degrees * Ntot of
-// the notebook's PSIij cancels in the normalisation.
-__global__ void __launch_bounds__(256) k_lsbm_mstep(long long K, int q, int G, const int* __restrict__ erow,
-                                                    const int* __restrict__ col, const int* __restrict__ rev,
-                                                    const unsigned char* __restrict__ lab, const double* __restrict__ cur,
-                                                    LParams* P) {
+// the notebook's PSIij cancels in the normalisation, and affinity[alpha][r,s] is the same for every link of a label:
+//     affinitynew[alpha][r,s] = affinity[alpha][r,s] * sum_links (psi_{i->j}[r] / Z_link) psi_{j->i}[s],
+// a sum of outer products.  A warp takes 32 slots at a time: every lane normalises its link and parks the two vectors
+// in shared memory, then every lane accumulates the (r,s) entries it owns over the 32 links in registers.
+constexpr int MSTEP_THREADS = 128;
+__global__ void __launch_bounds__(MSTEP_THREADS) k_lsbm_mstep(long long K, int q, int G, const int* __restrict__ erow,
+                                                              const int* __restrict__ col, const int* __restrict__ rev,
+                                                              const unsigned char* __restrict__ lab,
+                                                              const double* __restrict__ cur, LParams* P) {
+  extern __shared__ double dyn[];                       // [warps][32][2 q]
   __shared__ double sh[LMAXG * MAXQ * MAXQ];
-  for (int k = threadIdx.x; k < G * q * q; k += blockDim.x) sh[k] = 0.0;
+  __shared__ unsigned char labS[MSTEP_THREADS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, qq = q * q;
+  double* rows = dyn + (size_t)warp * 32 * 2 * q;
+  for (int k = threadIdx.x; k < G * qq; k += blockDim.x) sh[k] = 0.0;
   __syncthreads();
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < K; e += (long long)gridDim.x * blockDim.x) {
-    if (erow[e] >= col[e]) continue;                       // row i < column j
-    const int a = lab[e];
-    const double* A = P->aff[a];
-    const double* mij = cur + (size_t)rev[e] * q;          // i -> j
-    const double* mji = cur + (size_t)e * q;               // j -> i
-    double sum = 0.0;
-    for (int r = 0; r < q; ++r)
-      for (int s = 0; s < q; ++s) sum += mij[r] * mji[s] * A[r * q + s];
-    const double inv = 1.0 / sum;
-    const int qq = q * q;
-    for (int k0 = 0; k0 < qq; ++k0) {
-      const int k = (k0 + (int)threadIdx.x) % qq;  // rotated: the lanes of a warp add to different addresses
-      const int r = k / q, s = k - r * q;
-      atomicAdd(&sh[a * qq + k], mij[r] * mji[s] * A[k] * inv);
+  constexpr int EPL = (MAXQ * MAXQ + 31) / 32;         // entries (r,s) a lane may own
+  double acc[LMAXG][EPL];
+#pragma unroll
+  for (int g = 0; g < LMAXG; ++g)
+#pragma unroll
+    for (int m = 0; m < EPL; ++m) acc[g][m] = 0.0;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long chunks = (K + 31) / 32;
+  for (long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < chunks; c += nwarps) {
+    const long long e = c * 32 + lane;
+    unsigned char L = 255;
+    if (e < K && erow[e] < col[e]) {                    // row i < column j: every undirected link once
+      L = lab[e];
+      const double* A = P->aff[L];
+      const double* mij = cur + (size_t)rev[e] * q;     // i -> j
+      const double* mji = cur + (size_t)e * q;          // j -> i
+      double Z = 0.0;
+      for (int r = 0; r < q; ++r) {
+        double t = 0.0;
+        for (int s2 = 0; s2 < q; ++s2) t += mji[s2] * A[r * q + s2];
+        Z += mij[r] * t;
+      }
+      const double inv = 1.0 / Z;
+      for (int r = 0; r < q; ++r) {
+        rows[(lane * 2) * q + r] = mij[r] * inv;
+        rows[(lane * 2 + 1) * q + r] = mji[r];
+      }
     }
+    labS[threadIdx.x] = L;
+    __syncwarp();
+    for (int j = 0; j < 32; ++j) {
+      const unsigned char Lj = labS[(warp << 5) + j];   // the same for every lane
+      if (Lj == 255) continue;
+      const double* aj = rows + (size_t)(j * 2) * q;
+      const double* bj = aj + q;
+#pragma unroll
+      for (int m = 0; m < EPL; ++m) {
+        const int k = lane + 32 * m;
+        if (k < qq) {
+          const double v = aj[k / q] * bj[k % q];
+#pragma unroll
+          for (int g = 0; g < LMAXG; ++g)
+            if (Lj == g) acc[g][m] += v;
+        }
+      }
+    }
+    __syncwarp();
   }
+#pragma unroll
+  for (int g = 0; g < LMAXG; ++g)
+#pragma unroll
+    for (int m = 0; m < EPL; ++m) {
+      const int k = lane + 32 * m;
+      if (g < G && k < qq && acc[g][m] != 0.0) atomicAdd(&sh[g * qq + k], acc[g][m]);
+    }
   __syncthreads();
-  for (int k = threadIdx.x; k < G * q * q; k += blockDim.x) {
-    const int a = k / (q * q), rs = k % (q * q);
-    if (sh[k] != 0.0) atomicAdd(&P->Gnew[a][(rs / q) * q + (rs % q)], sh[k]);
+  for (int k = threadIdx.x; k < G * qq; k += blockDim.x) {
+    const int g = k / qq, rs = k % qq;
+    if (sh[k] != 0.0) atomicAdd(&P->Gnew[g][rs], sh[k] * P->aff[g][rs]);
   }
 }
 
@@ -480,8 +526,10 @@ int l_iteration(gbx_lsbm* h) {
   h->cur ^= 1;
   L_TRY(l_denom(h));                                            // from the new marginals
   if (h->opt.learning && h->g.K > 0) {
-    k_lsbm_mstep<<<h->grid_e, 256, 0, st>>>((long long)h->g.K, h->q, h->G, h->g.erow, h->g.col, h->g.rev, h->lab,
-                                            h->msg[h->cur], h->P);
+    const int mgrid = (int)std::min<int64_t>(std::max<int64_t>(1, (h->g.K + MSTEP_THREADS - 1) / MSTEP_THREADS),
+                                             (int64_t)h->g.num_sms * 8);
+    k_lsbm_mstep<<<mgrid, MSTEP_THREADS, (size_t)(MSTEP_THREADS / 32) * 32 * 2 * h->q * sizeof(double), st>>>(
+        (long long)h->g.K, h->q, h->G, h->g.erow, h->g.col, h->g.rev, h->lab, h->msg[h->cur], h->P);
     h->launches++;
   }
   k_lsbm_post<<<1, 256, 0, st>>>(h->P, h->q, h->G, (double)h->g.n, (double)h->g.K, h->opt.learningrate,
