@@ -90,6 +90,24 @@ __device__ __forceinline__ double block_sum(double v, double* red) {  // 256 thr
   return r;
 }
 
+// Message rows: 256/128-bit accesses when q is a compile-time constant (gbx_common.cuh), scalar otherwise.
+template <int QT, int QA>
+__device__ __forceinline__ void row_load(const double* __restrict__ base, long long idx, int q, double (&m)[QA]) {
+  if constexpr (QT > 0) {
+    load_vec<QT>(base, idx, m);
+  } else {
+    for (int t = 0; t < q; ++t) m[t] = base[idx * q + t];
+  }
+}
+template <int QT, int QA>
+__device__ __forceinline__ void row_store(double* __restrict__ base, long long idx, int q, const double (&m)[QA]) {
+  if constexpr (QT > 0) {
+    store_vec<QT>(base, idx, m);
+  } else {
+    for (int t = 0; t < q; ++t) base[idx * q + t] = m[t];
+  }
+}
+
 __global__ void k_lab_slots(const int64_t* __restrict__ lab_link, const int* __restrict__ slot_of_link, long long K, int G,
                             unsigned char* __restrict__ lab, int* err) {
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < K; k += (long long)gridDim.x * blockDim.x) {
@@ -147,7 +165,8 @@ __global__ void __launch_bounds__(256) k_lsbm_vertex(int n, int qrt, int G, cons
       if (e < e1) {
         const int a = lab[e];
         const double dd = deg[(size_t)i * G + a] * deg[(size_t)col[e] * G + a];
-        const double* psi = cur + (size_t)e * q;
+        double psi[QA];
+        row_load<QT, QA>(cur, e, q, psi);
         const double* A = P->aff[a];
 #pragma unroll
         for (int t = 0; t < QA; ++t) {
@@ -195,7 +214,8 @@ __global__ void __launch_bounds__(256) k_lsbm_vertex(int n, int qrt, int G, cons
           if (!single) {
             const int a = lab[e];
             const double dd = deg[(size_t)i * G + a] * deg[(size_t)col[e] * G + a];
-            const double* psi = cur + (size_t)e * q;
+            double psi[QA];
+            row_load<QT, QA>(cur, e, q, psi);
             const double* A = P->aff[a];
 #pragma unroll
             for (int t = 0; t < QA; ++t) {
@@ -213,12 +233,13 @@ __global__ void __launch_bounds__(256) k_lsbm_vertex(int n, int qrt, int G, cons
           for (int t = 0; t < QA; ++t)
             if (t < q) cav[t] = x[t] - term[t];
           normalize_logprob(cav, q, m);
-          double* dst = nxt + (size_t)rev[e] * q;
+          const long long rv = rev[e];
           if (damping != 1.0) {
-            const double* old = cur + (size_t)rev[e] * q;
+            double old[QA];
+            row_load<QT, QA>(cur, rv, q, old);
             for (int t = 0; t < q; ++t) m[t] = (1.0 - damping) * old[t] + damping * m[t];
           }
-          for (int t = 0; t < q; ++t) dst[t] = m[t];
+          row_store<QT, QA>(nxt, rv, q, m);
         }
       }
     }
