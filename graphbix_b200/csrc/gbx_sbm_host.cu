@@ -161,6 +161,57 @@ int em_iteration(gbx_sbm* h, bool want_residual = false) {
   return GBX_OK;
 }
 
+int mod_iteration(gbx_sbm* h, bool want_residual);
+
+// The loop of EM() (sbm.jl:342-362, mod.jl:219-235).  Large graphs: one iteration at a time, the residual read back
+// early (queue_residual).  Small graphs are launch bound, so `batch` iterations are queued before the host looks:
+// sbm_apply_totals records the first iteration whose residual is below the threshold in SbmState::done_at and every
+// kernel of a later iteration returns at once, which leaves the state exactly as the reference's `break` would.
+int em_loop(gbx_sbm* h, int itrmax, int check_every, double thr, bool mod, int* cnv, int* itrnum) {
+  int batch = h->K < (int64_t)2000000 ? 8 : 1;
+  if (const char* e = getenv("GBX_EM_BATCH")) batch = std::max(1, atoi(e));
+  batch = std::max(batch, std::max(1, check_every));
+  GBX_CUDA_TRY(cudaMemsetAsync(&h->st->done_at, 0, sizeof(int), h->stream));
+  const int itr0 = h->itr;  // iterations run before this call (gbx_sbm_iterate): stamps keep growing
+  h->cur_thr = thr;
+  int rc = GBX_OK, itr = 0;
+  while (itr < itrmax && rc == GBX_OK) {
+    const int nb = std::min(batch, itrmax - itr);
+    for (int b = 1; b <= nb && rc == GBX_OK; ++b) {
+      h->cur_it = itr0 + itr + b;
+      rc = mod ? mod_iteration(h, nb == 1) : em_iteration(h, nb == 1);
+    }
+    if (rc != GBX_OK) break;
+    itr += nb;
+    double conv;
+    int done_at = 0;
+    if (nb == 1) {
+      rc = wait_residual(h, &conv);
+      if (rc == GBX_OK && conv < thr) done_at = itr0 + itr;
+    } else {
+      cudaError_t ce = cudaMemcpyAsync(&h->h_state->done_at, &h->st->done_at, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+      if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+      if (ce != cudaSuccess) {
+        last_error() = std::string("em_loop: ") + cudaGetErrorString(ce);
+        rc = GBX_ERR_CUDA;
+        break;
+      }
+      done_at = h->h_state->done_at;
+    }
+    if (done_at != 0) {
+      const int extra = itr0 + itr - done_at;   // queued iterations that found the flag set and did nothing
+      if (extra & 1) h->cur ^= 1;               // ... but the host flipped the message buffers for each of them
+      h->itr = done_at;
+      *cnv = 1;
+      *itrnum = done_at - itr0;
+      break;
+    }
+  }
+  h->cur_it = 0;
+  h->cur_thr = -1.0;
+  return rc;
+}
+
 }  // namespace
 
 extern "C" {
@@ -603,27 +654,7 @@ int gbx_sbm_em(gbx_sbm* h, gbx_sbm_result* res) {
   if (h->stepped) return fail_invalid("partitioned handle: drive the loop with gbx_sbm_step (see engine_dist.py)");
   GBX_TRY(set_device(h));
   int cnv = 0, itrnum = 0;
-  if (!h->fail) {
-    for (int itr = 1; itr <= h->opt.itrmax; ++itr) {
-      const bool check = itr % h->opt.check_every == 0 || itr == h->opt.itrmax;
-      static const bool early = getenv("GBX_EARLY_RESIDUAL") ? atoi(getenv("GBX_EARLY_RESIDUAL")) != 0 : true;
-      GBX_TRY(em_iteration(h, check && early));
-      if (check) {
-        double conv;
-        if (early) {
-          GBX_TRY(wait_residual(h, &conv));
-        } else {
-          GBX_TRY(read_state(h));
-          conv = h->h_state->conv;
-        }
-        if (conv < h->opt.bp_conv_threshold) {  // sbm.jl:348-353
-          cnv = 1;
-          itrnum = itr;
-          break;
-        }
-      }
-    }
-  }
+  if (!h->fail) GBX_TRY(em_loop(h, h->opt.itrmax, h->opt.check_every, h->opt.bp_conv_threshold, false, &cnv, &itrnum));
   GBX_TRY(gbx_sbm_finalize(h, res));
   res->cnv = cnv;
   res->itrnum = itrnum;
@@ -765,7 +796,10 @@ int gbx_mod_init(gbx_mod* h, const double* gr, const double* psicav, uint64_t se
   return GBX_OK;
 }
 
-static int mod_iteration(gbx_sbm* h, bool want_residual = false) {
+}  // extern "C"
+
+namespace {
+int mod_iteration(gbx_sbm* h, bool want_residual) {
   const SbmOps* op = h->ops;
   GBX_TRY(op->prepare(h, 0, 0));              // h = update_h()                                    mod.jl:56
   GBX_TRY(op->vertex_pass(h, MODE_SWEEP));    // messages, marginals, residual, omega statistic     mod.jl:57-88
@@ -776,13 +810,16 @@ static int mod_iteration(gbx_sbm* h, bool want_residual = false) {
   h->itr++;
   return GBX_OK;
 }
+}  // namespace
+
+extern "C" {
 
 int gbx_mod_iterate(gbx_mod* h, int n_iters, double* bpconv_out) {
   if (!h) return fail_invalid("handle is NULL");
   if (!h->initialised || h->model != 1) return fail_state();
   if (h->stepped && n_iters > 0) return fail_invalid("partitioned handle: drive the loop with gbx_sbm_step");
   GBX_TRY(set_device(h));
-  for (int i = 0; i < n_iters; ++i) GBX_TRY(mod_iteration(h));
+  for (int i = 0; i < n_iters; ++i) GBX_TRY(mod_iteration(h, false));
   if (bpconv_out) {
     GBX_TRY(read_state(h));
     *bpconv_out = h->h_state->conv;
@@ -828,19 +865,7 @@ int gbx_mod_em(gbx_mod* h, gbx_mod_result* res) {
   if (h->stepped) return fail_invalid("partitioned handle: drive the loop with gbx_sbm_step");
   GBX_TRY(set_device(h));
   int cnv = 0, itrnum = 0;
-  for (int itr = 1; itr <= h->mopt.itrmax; ++itr) {
-    const bool check = itr % h->mopt.check_every == 0 || itr == h->mopt.itrmax;
-    GBX_TRY(mod_iteration(h, check));
-    if (check) {
-      double conv;
-      GBX_TRY(wait_residual(h, &conv));
-      if (conv < h->mopt.bp_conv_threshold) {  // mod.jl:230-234
-        cnv = 1;
-        itrnum = itr;
-        break;
-      }
-    }
-  }
+  GBX_TRY(em_loop(h, h->mopt.itrmax, h->mopt.check_every, h->mopt.bp_conv_threshold, true, &cnv, &itrnum));
   GBX_TRY(gbx_mod_finalize(h, res));
   res->cnv = cnv;
   res->itrnum = itrnum;

@@ -37,6 +37,9 @@ struct SbmState {
   double omegain, omegaout, alpha, beta, hn2, omegainnew2;
   double cv5sum[5], cv5mean[5], cv5ss[5];
   int status;  // bit 0: non-finite / non-positive value met in a kernel
+  int done_at; // EM iteration whose residual fell below the threshold (0: not yet).  The kernels of LATER iterations
+               // return at once, so the host may queue several iterations before it reads the residual back and the
+               // state still is exactly that of the converged iteration (sbm.jl:348-353 breaks after update_theta).
 };
 
 constexpr int PSTRIDE = 4 * MAXQ + 4;
@@ -116,6 +119,8 @@ struct gbx_sbm {
   double *part_vertex = nullptr, *part_mstep = nullptr, *part_theta = nullptr, *part_fe = nullptr;
   int grid_vertex = 0, grid_mstep = 0, grid_theta = 0, grid_fe = 0;
   gbx::SbmState* h_state = nullptr;  // pinned mirror
+  int cur_it = 0;                    // iteration the launchers stamp their kernels with (0: never skip)
+  double cur_thr = -1.0;             // residual threshold sbm_apply_totals tests (< 0: never converged)
   cudaEvent_t ev_conv = nullptr;     // the residual of the last iteration has reached h_state->conv
   int itr = 0;
   // ---- packed boundary exchange of a partitioned run (exchange == 1) -------------------------------------------

@@ -68,11 +68,21 @@ struct VertexArgs {
   double* partials;   // [(grid + nhubs)][PSTRIDE]
   double* mpart;      // [(grid + nhubs)][Q * Q]: M-step statistics (sbm.jl) per CTA
   int* status;
+  const SbmState* st;   // for skip_iteration
+  int it;
   double damping;
   int dc;
 };
 
 // ---- small device helpers ---------------------------------------------------------------------
+// True when an earlier EM iteration has already converged (SbmState::done_at): this launch belongs to an iteration the
+// host queued ahead of reading the residual and must not touch anything.  it == 0: unconditional launch.
+__device__ __forceinline__ bool skip_iteration(const SbmState* st, int it) {
+  if (it == 0) return false;
+  const int d = *reinterpret_cast<const volatile int*>(&st->done_at);
+  return d != 0 && d < it;
+}
+
 // 2^n with saturation: 0 below the normal range, +inf above.
 __device__ __forceinline__ double pow2c(int n) {
   if (n < -1022) return 0.0;
@@ -306,7 +316,8 @@ __device__ __forceinline__ void prior_row(double th, double* row /* QT */) {
   row[Q + 2] = xmax;
 }
 
-__global__ void sbm_prior_table(const SbmState* st, double* tab, int dc) {
+__global__ void sbm_prior_table(const SbmState* st, double* tab, int dc, int it) {
+  if (skip_iteration(st, it)) return;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const int nrows = dc ? 1 + (TILE_E + 1) * Q : 1;
   if (r >= nrows) return;
@@ -611,6 +622,7 @@ __global__ void __launch_bounds__(NT, ((Q <= 8) ? 3 : 2) * (256 / NT)) sbm_verte
   unsigned char* lvS = reinterpret_cast<unsigned char*>(smem + SweepSmem::lv_off);
 
   const int tid = threadIdx.x;
+  if (MODE == MODE_SWEEP && skip_iteration(a.st, a.it)) return;
   if (tid < Q) {
     s_dr[tid] = 0ull;
     s_nr[tid] = 0;
@@ -820,6 +832,7 @@ __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base
   __shared__ int s_nr[Q];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (MODE == MODE_SWEEP && skip_iteration(a.st, a.it)) return;
   const int gv = a.hubs[blockIdx.x];
   const int e0 = a.rowptr[gv], e1 = a.rowptr[gv + 1];
   // theta of the prior: sbm.jl degree correction factor, or the degree itself in mod.jl:48
@@ -971,7 +984,8 @@ __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base
 // theta gather out of the sweep (one staged 8-byte value per slot there instead of col + a dependent gather).
 __global__ void __launch_bounds__(256) sbm_escale_kernel(const int* __restrict__ erow, const int* __restrict__ col,
                                                          long long K, const double* __restrict__ theta,
-                                                         double* __restrict__ escale) {
+                                                         double* __restrict__ escale, const SbmState* st, int it) {
+  if (skip_iteration(st, it)) return;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < K; e += (long long)gridDim.x * blockDim.x)
     escale[e] = theta[erow[e]] * theta[col[e]];
 }
@@ -987,8 +1001,10 @@ constexpr int TOT_LEN = TOT_G + Q * Q;
 
 __global__ void __launch_bounds__(256) sbm_local_totals(const double* __restrict__ pv, int nrows,
                                                         const double* __restrict__ pm, int with_g,
-                                                        double* __restrict__ totals, double* __restrict__ maxd_out) {
+                                                        double* __restrict__ totals, double* __restrict__ maxd_out,
+                                                        const SbmState* st, int it) {
   // One block per column of the totals vector (the last block: the max column); fixed summation order.
+  if (skip_iteration(st, it)) return;
   __shared__ double red[256];
   const int tid = threadIdx.x;
   const int ncol = 4 * Q + 4 + (with_g ? Q * Q : 0);
@@ -1031,8 +1047,9 @@ __global__ void __launch_bounds__(256) sbm_local_totals(const double* __restrict
 #if GBX_MODEL == 0
 // sbm.jl:120-123 (residual, gr), 47-58 (block degree means), 137-147 (update_Crs) from the global totals.
 __global__ void sbm_apply_totals(SbmState* st, const double* __restrict__ tot, const double* maxd, int mode, int prior,
-                                 int dc, double N, double lr, double maxCrs) {
+                                 int dc, double N, double lr, double maxCrs, int it, double thr) {
   const int tid = threadIdx.x;
+  if (skip_iteration(st, it)) return;
   if (mode == MODE_LOGZ) {
     if (tid == 0) {
       st->sumlogZi = tot[1];
@@ -1058,6 +1075,7 @@ __global__ void sbm_apply_totals(SbmState* st, const double* __restrict__ tot, c
   }
   if (tid == 0 && mode == MODE_SWEEP) {
     st->conv = tot[0] / N;  // sbm.jl:123
+    if (it != 0 && st->done_at == 0 && st->conv < thr) st->done_at = it;   // sbm.jl:348-353, acted on from it + 1
     st->maxd = *maxd;
     if (!(tot[0] == tot[0]) || !(tot[0] < INFINITY)) st->status |= 1;  // NaN/Inf reached the marginals
   }
@@ -1080,8 +1098,9 @@ __global__ void sbm_apply_totals(SbmState* st, const double* __restrict__ tot, c
 // update_theta(), sbm.jl:47-64, and S_theta = sum_i theta_i PSI_i for the next update_h().
 __global__ void __launch_bounds__(NT) sbm_theta_kernel(const SbmState* st, const int* __restrict__ rowptr, int n,
                                                        const double* __restrict__ PSI, double* theta,
-                                                       int* __restrict__ pidx, double* partials) {
+                                                       int* __restrict__ pidx, double* partials, int it) {
   __shared__ double red[(NT / 32) * Q];
+  if (skip_iteration(st, it)) return;
   double acc[Q];
 #pragma unroll
   for (int t = 0; t < Q; ++t) acc[t] = 0.0;
@@ -1107,14 +1126,17 @@ __global__ void __launch_bounds__(NT) sbm_theta_kernel(const SbmState* st, const
 }
 
 // partial rows -> totals[0..ncol) (local), then apply after the ranks' all-reduce
-__global__ void k_local_columns(const double* __restrict__ partials, int nrows, int ncol, double* __restrict__ totals) {
+__global__ void k_local_columns(const double* __restrict__ partials, int nrows, int ncol, double* __restrict__ totals,
+                                const SbmState* st = nullptr, int it = 0) {
+  if (st && skip_iteration(st, it)) return;
   for (int c = threadIdx.x >> 5; c < ncol; c += blockDim.x >> 5) {
     const double v = warp_column_reduce(partials, nrows, ncol, c);
     if ((threadIdx.x & 31) == 0) totals[c] = v;
   }
 }
 
-__global__ void sbm_apply_theta(SbmState* st, const double* __restrict__ totals) {
+__global__ void sbm_apply_theta(SbmState* st, const double* __restrict__ totals, int it) {
+  if (skip_iteration(st, it)) return;
   if (threadIdx.x < Q) st->Stheta[threadIdx.x] = totals[threadIdx.x];
 }
 
@@ -1122,7 +1144,8 @@ __global__ void sbm_apply_theta(SbmState* st, const double* __restrict__ totals)
 // Per-iteration parameters: gr clamp (sbm.jl:89-96), h = update_h() (sbm.jl:70-73), logs; written to a
 // global staging struct that the host copies device->constant in stream order.
 __global__ void sbm_prepare(SbmState* st, SbmParams* out, double N, int zero_h, int gr_from_sum, int dc_range,
-                            double maxdeg) {
+                            double maxdeg, int it) {
+  if (skip_iteration(st, it)) return;
   __shared__ double g[Q];
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -1377,6 +1400,8 @@ VertexArgs vertex_args(gbx_sbm* h) {
   a.partials = h->part_vertex;
   a.mpart = h->part_mstep;
   a.status = &h->st->status;
+  a.st = h->st;
+  a.it = h->cur_it;
   a.damping = (MODEL == MODEL_MOD) ? h->mopt.damping : h->opt.damping;
   a.dc = (MODEL == MODEL_MOD) ? h->mopt.dc : h->opt.degreecorrection;
   return a;
@@ -1500,7 +1525,7 @@ int op_local_totals(gbx_sbm* h, int mode) {
   const size_t skip = (size_t)h->sweep_row0;  // rows of the last vertex pass (a packed sweep has one set per piece)
   const int with_g = (MODEL == MODEL_SBM && mode == MODE_SWEEP) ? 1 : 0;
   sbm_local_totals<<<4 * Q + 4 + (with_g ? Q * Q : 0) + 1, 256, 0, h->stream>>>(
-      h->part_vertex + skip * PSTRIDE, h->sweep_rows, h->part_mstep + skip * Q * Q, with_g, h->totals, h->maxd_dev);
+      h->part_vertex + skip * PSTRIDE, h->sweep_rows, h->part_mstep + skip * Q * Q, with_g, h->totals, h->maxd_dev, h->st, h->cur_it);
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
@@ -1510,7 +1535,8 @@ int op_local_totals(gbx_sbm* h, int mode) {
 int op_apply_totals(gbx_sbm* h, int mode) {
   const double maxCrs = h->opt.maxCrs > 0 ? h->opt.maxCrs : (double)h->n_global;
   sbm_apply_totals<<<1, 256, 0, h->stream>>>(h->st, h->totals, h->maxd_dev, mode, h->opt.priorlearning,
-                                             h->opt.degreecorrection, (double)h->n_global, h->opt.learningrate, maxCrs);
+                                             h->opt.degreecorrection, (double)h->n_global, h->opt.learningrate, maxCrs, h->cur_it,
+                                             h->cur_thr);
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
@@ -1519,13 +1545,13 @@ int op_apply_totals(gbx_sbm* h, int mode) {
 int op_prepare(gbx_sbm* h, int zero_h, int gr_from_sum) {
   const int dc_tab = h->opt.degreecorrection && h->theta_valid;
   sbm_prepare<<<1, 64, 0, h->stream>>>(h->st, h->params, (double)h->n_global, zero_h, gr_from_sum, dc_tab,
-                                       (double)h->max_degree);
+                                       (double)h->max_degree, h->cur_it);
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
   GBX_CUDA_TRY(cudaMemcpyToSymbolAsync(c_P, h->params, sizeof(SbmParams), 0, cudaMemcpyDeviceToDevice, h->stream));
   {
     const int nrows = dc_tab ? 1 + (TILE_E + 1) * Q : 1;
-    sbm_prior_table<<<(nrows + 127) / 128, 128, 0, h->stream>>>(h->st, h->prior_tab, dc_tab);
+    sbm_prior_table<<<(nrows + 127) / 128, 128, 0, h->stream>>>(h->st, h->prior_tab, dc_tab, h->cur_it);
     h->launches++;
     GBX_CUDA_TRY(cudaGetLastError());
   }
@@ -1534,16 +1560,16 @@ int op_prepare(gbx_sbm* h, int zero_h, int gr_from_sum) {
 
 int op_theta_local(gbx_sbm* h) {
   sbm_theta_kernel<<<h->grid_theta, NT, 0, h->stream>>>(h->st, h->rowptr, (int)h->n, h->PSI, h->theta + h->vbeg, h->pidx,
-                                                        h->part_theta);
+                                                        h->part_theta, h->cur_it);
   h->theta_valid = true;
-  k_local_columns<<<1, 256, 0, h->stream>>>(h->part_theta, h->grid_theta, Q, h->totals);
+  k_local_columns<<<1, 256, 0, h->stream>>>(h->part_theta, h->grid_theta, Q, h->totals, h->st, h->cur_it);
   h->launches += 2;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
 }
 
 int op_theta_apply(gbx_sbm* h) {
-  sbm_apply_theta<<<1, 32, 0, h->stream>>>(h->st, h->totals);
+  sbm_apply_theta<<<1, 32, 0, h->stream>>>(h->st, h->totals, h->cur_it);
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
@@ -1551,7 +1577,7 @@ int op_theta_apply(gbx_sbm* h) {
 
 int op_escale(gbx_sbm* h) {
   if (h->K > 0) {
-    sbm_escale_kernel<<<grid_for(h, h->K), 256, 0, h->stream>>>(h->erow, h->col, (long long)h->K, h->theta, h->escale);
+    sbm_escale_kernel<<<grid_for(h, h->K), 256, 0, h->stream>>>(h->erow, h->col, (long long)h->K, h->theta, h->escale, h->st, h->cur_it);
     h->launches++;
     GBX_CUDA_TRY(cudaGetLastError());
   }
@@ -1643,8 +1669,9 @@ int op_occupancy(int variant, int* vertex_occ, int* mstep_occ) {
 // =============================================================================================
 // mod.jl:72 (residual), 22-24 (h numerator), 221-223 (gr), 77-112 and 224-229 (omegas, alpha, beta) from the totals.
 __global__ void mod_apply_totals(SbmState* st, const double* __restrict__ tot, const double* maxd, int mode, int prior,
-                                 int dc, int learning, double N, double K, double lr, double maxomega) {
+                                 int dc, int learning, double N, double K, double lr, double maxomega, int it, double thr) {
   const int tid = threadIdx.x;
+  if (skip_iteration(st, it)) return;
   if (mode == MODE_LOGZ) {
     if (tid == 0) {
       st->sumlogZi = tot[1];
@@ -1663,6 +1690,7 @@ __global__ void mod_apply_totals(SbmState* st, const double* __restrict__ tot, c
   __syncthreads();
   if (tid == 0 && mode == MODE_SWEEP) {
     st->conv = tot[0] / N;  // mod.jl:72
+    if (it != 0 && st->done_at == 0 && st->conv < thr) st->done_at = it;   // mod.jl:230-234, acted on from it + 1
     st->maxd = *maxd;
     if (!(tot[0] == tot[0]) || !(tot[0] < INFINITY)) st->status |= 1;
     if (learning) {
@@ -1685,7 +1713,8 @@ __global__ void mod_apply_totals(SbmState* st, const double* __restrict__ tot, c
   }
 }
 
-__global__ void mod_prepare(SbmState* st, SbmParams* out, double N, int zero_h) {
+__global__ void mod_prepare(SbmState* st, SbmParams* out, double N, int zero_h, int it) {
+  if (skip_iteration(st, it)) return;
   const int tid = threadIdx.x;
   if (tid < Q) {
     out->lgr[tid] = log(st->gr[tid]);
@@ -1790,20 +1819,20 @@ __global__ void mod_finalize(SbmState* st, double N, double L, double constshift
 int mop_apply_totals(gbx_sbm* h, int mode) {
   mod_apply_totals<<<1, 64, 0, h->stream>>>(h->st, h->totals, h->maxd_dev, mode, h->mopt.priorlearning, h->mopt.dc,
                                             h->mopt.learning, (double)h->n_global, (double)h->K_global,
-                                            h->mopt.learningrate, h->mopt.maxomega);
+                                            h->mopt.learningrate, h->mopt.maxomega, h->cur_it, h->cur_thr);
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
 }
 
 int mop_prepare(gbx_sbm* h, int zero_h, int) {
-  mod_prepare<<<1, 32, 0, h->stream>>>(h->st, h->params, (double)h->n_global, zero_h);
+  mod_prepare<<<1, 32, 0, h->stream>>>(h->st, h->params, (double)h->n_global, zero_h, h->cur_it);
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
   GBX_CUDA_TRY(cudaMemcpyToSymbolAsync(c_P, h->params, sizeof(SbmParams), 0, cudaMemcpyDeviceToDevice, h->stream));
   const int dc_tab = h->mopt.dc;
   const int nrows = dc_tab ? 1 + (TILE_E + 1) * Q : 1;
-  sbm_prior_table<<<(nrows + 127) / 128, 128, 0, h->stream>>>(h->st, h->prior_tab, dc_tab);
+  sbm_prior_table<<<(nrows + 127) / 128, 128, 0, h->stream>>>(h->st, h->prior_tab, dc_tab, h->cur_it);
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
