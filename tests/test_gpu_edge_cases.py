@@ -103,3 +103,26 @@ def test_extreme_q(gpu_required, q):
         np.testing.assert_allclose(eng.state()["PSI"], ref.PSI, rtol=0, atol=1e-12)
         np.testing.assert_allclose(eng.messages(), ref.messages_in_link_order(), rtol=0, atol=1e-12)
     eng.close()
+
+
+@pytest.mark.parametrize("model", ["sbm", "mod"])
+def test_queued_iterations_stop_exactly_where_the_one_by_one_loop_stops(gpu_required, monkeypatch, model):
+    """Small graphs queue 8 EM iterations before the host reads the residual; the device freezes the state at the
+    converging iteration.  Same itrnum and bit-identical state as the loop that synchronises every iteration."""
+    from graphbix_b200.engine import EM, EM_mod
+    q = 3
+    n, links, psi0, _ = planted_case(500, q, 8.0, 0.1, seed=31)
+    gr0, C0 = assortative_init(q)
+    outs = []
+    for batch in ("1", "8", "5"):
+        monkeypatch.setenv("GBX_EM_BATCH", batch)
+        if model == "sbm":
+            out = EM(n, q, links, n, (gr0, C0), False, 300, True, 0.3, PSIcav0=psi0)
+            outs.append((out[14], out[13], out[2], out[1], np.array(out[3:12])))
+        else:
+            out = EM_mod(np.ones(q) / q, n, q, links, 1, 300, 0.0, True, True, False, 0.3, PSIcav0=psi0)
+            outs.append((out[16], out[15], out[5], np.array([out[1], out[2], out[3], out[4]]), np.array(out[6:15])))
+    assert outs[0][1] and 1 < outs[0][0] < 300
+    for o in outs[1:]:
+        assert o[0] == outs[0][0] and o[1] == outs[0][1]
+        assert np.array_equal(o[2], outs[0][2]) and np.array_equal(o[3], outs[0][3]) and np.array_equal(o[4], outs[0][4])
