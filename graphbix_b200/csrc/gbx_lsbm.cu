@@ -39,6 +39,8 @@ struct LParams {
   double fesum[4], femean[4], fess[4];
   double result[9];
   int status;                        // bit 0: non-finite value seen; bit 1: the two directions of a link differ in label
+  int done_at;                       // EM iteration whose residual fell below the threshold (0: not yet); kernels stamped
+                                     // with a later iteration return at once (the host queues several iterations)
 };
 
 #define L_TRY(expr)              \
@@ -53,6 +55,11 @@ int l_invalid(const char* msg) {
 }
 
 // ---- small device helpers -----------------------------------------------------------------------------------------
+__device__ __forceinline__ bool l_skip(const LParams* P, int it) {   // see LParams::done_at; it == 0: never skip
+  if (it == 0) return false;
+  const int d = *reinterpret_cast<const volatile int*>(&P->done_at);
+  return d != 0 && d < it;
+}
 // normalize_logprob (notebook): clamp at log(1e-8), then exp(x - logsumexp(x)) with logsumexp's 500 cut-off.
 __device__ __forceinline__ void normalize_logprob(const double* x, int q, double* p) {
   double m = -INFINITY;
@@ -145,8 +152,10 @@ __global__ void __launch_bounds__(256) k_lsbm_vertex(int n, int qrt, int G, cons
                                                      const int* __restrict__ col, const int* __restrict__ rev,
                                                      const unsigned char* __restrict__ lab, const double* __restrict__ deg,
                                                      const double* __restrict__ cur, double* __restrict__ nxt,
-                                                     double* __restrict__ PSI, LParams* P, double N, double damping) {
+                                                     double* __restrict__ PSI, LParams* P, double N, double damping,
+                                                     int it) {
   __shared__ double red[256];
+  if (MODE == LMODE_SWEEP && l_skip(P, it)) return;
   const int q = QT > 0 ? QT : qrt;
   constexpr int QA = QT > 0 ? QT : MAXQ;
   constexpr int GPB = 256 / LPV;                        // vertices per block and round
@@ -254,8 +263,9 @@ __global__ void __launch_bounds__(256) k_lsbm_vertex(int n, int qrt, int G, cons
 
 // denom[alpha, t] = sum_i degrees[i, alpha] PSI[i, t] and sum_i PSI[i, t]
 __global__ void __launch_bounds__(256) k_lsbm_denom(int n, int q, int G, const double* __restrict__ deg,
-                                                    const double* __restrict__ PSI, LParams* P) {
+                                                    const double* __restrict__ PSI, LParams* P, int it) {
   __shared__ double sh[(LMAXG + 1) * MAXQ];
+  if (l_skip(P, it)) return;
   for (int k = threadIdx.x; k < (LMAXG + 1) * MAXQ; k += blockDim.x) sh[k] = 0.0;
   __syncthreads();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -287,8 +297,9 @@ constexpr int MSTEP_THREADS = 128;
 __global__ void __launch_bounds__(MSTEP_THREADS) k_lsbm_mstep(long long K, int q, int G, const int* __restrict__ erow,
                                                               const int* __restrict__ col, const int* __restrict__ rev,
                                                               const unsigned char* __restrict__ lab,
-                                                              const double* __restrict__ cur, LParams* P) {
-  extern __shared__ double dyn[];                       // [warps][32][2 q]
+                                                              const double* __restrict__ cur, LParams* P, int it) {
+  extern __shared__ double dyn[];
+  if (l_skip(P, it)) return;                       // [warps][32][2 q]
   __shared__ double sh[LMAXG * MAXQ * MAXQ];
   __shared__ unsigned char labS[MSTEP_THREADS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, qq = q * q;
@@ -357,8 +368,9 @@ __global__ void __launch_bounds__(MSTEP_THREADS) k_lsbm_mstep(long long K, int q
   }
 }
 
-__global__ void k_lsbm_zero(LParams* P, int what) {  // what bit 0: denom / sumPSI / Gnew, bit 1: conv, bit 2: free energy sums
+__global__ void k_lsbm_zero(LParams* P, int what, int it) {  // what bit 0: denom / sumPSI / Gnew, bit 1: conv, bit 2: free energy sums
   const int tid = threadIdx.x;
+  if (l_skip(P, it)) return;
   if (what & 1) {
     for (int k = tid; k < LMAXG * MAXQ; k += blockDim.x) P->denom[k / MAXQ][k % MAXQ] = 0.0;
     for (int k = tid; k < MAXQ; k += blockDim.x) P->sumPSI[k] = 0.0;
@@ -372,8 +384,10 @@ __global__ void k_lsbm_zero(LParams* P, int what) {  // what bit 0: denom / sumP
 }
 
 // h[alpha, :] = sum_i degrees[i, alpha] (PSI * affinity[alpha])[i, :] = denom[alpha, :] * affinity[alpha]   (update_h)
-__global__ void k_lsbm_pre(LParams* P, int q, int G) {
+__global__ void k_lsbm_pre(LParams* P, int q, int G, int it) {
   const int tid = threadIdx.x;
+  if (l_skip(P, it)) return;
+  if (tid == 0) P->conv = 0.0;   // the sweep that follows accumulates its residual here
   if (tid < G * q) {
     const int a = tid / q, t = tid % q;
     double s = 0.0;
@@ -383,8 +397,11 @@ __global__ void k_lsbm_pre(LParams* P, int q, int G) {
 }
 
 // gr = lr * update_gr(PSI) + (1 - lr) * gr; affinity = lr * update_affinity() + (1 - lr) * affinity   (EM main loop)
-__global__ void k_lsbm_post(LParams* P, int q, int G, double N, double K, double lr, int prior, int learning, int red) {
+__global__ void k_lsbm_post(LParams* P, int q, int G, double N, double K, double lr, int prior, int learning, int red,
+                            int it, double thr) {
   const int tid = threadIdx.x;
+  if (l_skip(P, it)) return;
+  if (tid == 0 && it != 0 && P->done_at == 0 && P->conv < thr) P->done_at = it;   // acted on from iteration it + 1
   if (prior && tid < q) P->gr[tid] = lr * (P->sumPSI[tid] / N) + (1.0 - lr) * P->gr[tid];
   if (learning) {
     for (int k = tid; k < G * q * q; k += blockDim.x) {
@@ -478,6 +495,9 @@ struct gbx_lsbm {
   bool initialised = false;
   int64_t launches = 0;
   int grid_v = 1, grid_e = 1, grid_w = 1;
+  int itr = 0;               // EM iterations run since init
+  int cur_it = 0;            // stamp of the iteration being queued (0: never skip)
+  double cur_thr = -1.0;     // residual threshold k_lsbm_post tests (< 0: never converged)
 };
 
 namespace {
@@ -495,8 +515,8 @@ int l_read_conv(gbx_lsbm* h) {  // the residual alone: 8 bytes instead of the wh
 }
 
 int l_denom(gbx_lsbm* h) {
-  k_lsbm_zero<<<1, 256, 0, h->g.stream>>>(h->P, 1);
-  k_lsbm_denom<<<h->grid_v, 256, 0, h->g.stream>>>((int)h->g.n, h->q, h->G, h->deg, h->PSI, h->P);
+  k_lsbm_zero<<<1, 256, 0, h->g.stream>>>(h->P, 1, h->cur_it);
+  k_lsbm_denom<<<h->grid_v, 256, 0, h->g.stream>>>((int)h->g.n, h->q, h->G, h->deg, h->PSI, h->P, h->cur_it);
   h->launches += 2;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
@@ -508,7 +528,7 @@ int l_vertex_ql(gbx_lsbm* h) {
   const int grid = (int)std::min<int64_t>(std::max<int64_t>(1, (h->g.n + gpb - 1) / gpb), (int64_t)h->g.num_sms * 8);
   k_lsbm_vertex<MODE, QT, LPV><<<grid, 256, 0, h->g.stream>>>((int)h->g.n, h->q, h->G, h->g.rowptr, h->g.col, h->g.rev,
                                                               h->lab, h->deg, h->msg[h->cur], h->msg[h->cur ^ 1], h->PSI,
-                                                              h->P, (double)h->g.n, h->opt.damping);
+                                                              h->P, (double)h->g.n, h->opt.damping, h->cur_it);
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
@@ -536,13 +556,13 @@ int l_vertex(gbx_lsbm* h) {
   }
 }
 
-// one pass of the notebook's main loop: h = update_h(); BP(); gr and affinity updates
+// one pass of the notebook's main loop: h = update_h(); BP(); gr and affinity updates.  denom (sum_i degrees PSI) of the
+// current marginals is already there: from init or from the end of the previous pass.
 int l_iteration(gbx_lsbm* h) {
   cudaStream_t st = h->g.stream;
-  L_TRY(l_denom(h));                                            // from the current marginals
-  k_lsbm_pre<<<1, 64, 0, st>>>(h->P, h->q, h->G);               // h = update_h()
-  k_lsbm_zero<<<1, 32, 0, st>>>(h->P, 2);
-  h->launches += 2;
+  const int it = h->cur_it;
+  k_lsbm_pre<<<1, 64, 0, st>>>(h->P, h->q, h->G, it);           // h = update_h(); residual := 0
+  h->launches++;
   L_TRY(l_vertex<LMODE_SWEEP>(h));                              // (BPconv, PSI) = BP()
   h->cur ^= 1;
   L_TRY(l_denom(h));                                            // from the new marginals
@@ -550,12 +570,13 @@ int l_iteration(gbx_lsbm* h) {
     const int mgrid = (int)std::min<int64_t>(std::max<int64_t>(1, (h->g.K + MSTEP_THREADS - 1) / MSTEP_THREADS),
                                              (int64_t)h->g.num_sms * 8);
     k_lsbm_mstep<<<mgrid, MSTEP_THREADS, (size_t)(MSTEP_THREADS / 32) * 32 * 2 * h->q * sizeof(double), st>>>(
-        (long long)h->g.K, h->q, h->G, h->g.erow, h->g.col, h->g.rev, h->lab, h->msg[h->cur], h->P);
+        (long long)h->g.K, h->q, h->G, h->g.erow, h->g.col, h->g.rev, h->lab, h->msg[h->cur], h->P, it);
     h->launches++;
   }
   k_lsbm_post<<<1, 256, 0, st>>>(h->P, h->q, h->G, (double)h->g.n, (double)h->g.K, h->opt.learningrate,
-                                 h->opt.priorlearning, h->opt.learning, h->opt.REDfrac != 0.0);
+                                 h->opt.priorlearning, h->opt.learning, h->opt.REDfrac != 0.0, it, h->cur_thr);
   h->launches++;
+  h->itr++;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
 }
@@ -713,6 +734,7 @@ int gbx_lsbm_init(gbx_lsbm* h, const double* gr, const double* affinity, const d
   GBX_CUDA_TRY(cudaMemcpyAsync(h->P, s, sizeof(LParams), cudaMemcpyHostToDevice, st));
   GBX_CUDA_TRY(cudaStreamSynchronize(st));
   h->cur = 0;
+  h->itr = 0;
   const int64_t K = h->g.K;
   if (K > 0) {
     // the other message buffer is scratch before the first sweep
@@ -726,7 +748,7 @@ int gbx_lsbm_init(gbx_lsbm* h, const double* gr, const double* affinity, const d
   // h = zeros(G,B); PSI = updatePSI(); h = update_h()   (notebook EM, "initial state")
   L_TRY(l_vertex<LMODE_MARGINAL>(h));
   L_TRY(l_denom(h));
-  k_lsbm_pre<<<1, 64, 0, st>>>(h->P, q, G);
+  k_lsbm_pre<<<1, 64, 0, st>>>(h->P, q, G, 0);
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
   GBX_CUDA_TRY(cudaStreamSynchronize(st));
@@ -758,7 +780,7 @@ int gbx_lsbm_finalize(gbx_lsbm* h, gbx_lsbm_result* res) {
   GBX_CUDA_TRY(cudaSetDevice(h->g.device));
   cudaStream_t st = h->g.stream;
   const double L = 0.5 * (double)h->g.K, N = (double)h->g.n;
-  k_lsbm_zero<<<1, 32, 0, st>>>(h->P, 4);
+  k_lsbm_zero<<<1, 32, 0, st>>>(h->P, 4, 0);
   h->launches++;
   L_TRY(l_vertex<LMODE_LOGZ>(h));
   if (h->g.K > 0) {
@@ -796,17 +818,43 @@ int gbx_lsbm_em(gbx_lsbm* h, gbx_lsbm_result* res) {
     return GBX_ERR_STATE;
   }
   GBX_CUDA_TRY(cudaSetDevice(h->g.device));
+  // Small graphs are launch bound: queue `batch` iterations, then read the iteration k_lsbm_post recorded as converged
+  // (kernels of later iterations returned at once, so the state is the one the notebook's `break` leaves).
   int cnv = 0, itrnum = 0, done = 0;
-  for (int itr = 1; itr <= h->opt.itrmax; ++itr) {
-    L_TRY(l_iteration(h));
-    done = itr;
-    L_TRY(l_read_conv(h));
-    if (h->hP->conv < h->opt.bp_conv_threshold) {
+  int batch = h->g.K < (int64_t)2000000 ? 8 : 1;
+  if (const char* e = getenv("GBX_EM_BATCH")) batch = std::max(1, atoi(e));
+  GBX_CUDA_TRY(cudaMemsetAsync(&h->P->done_at, 0, sizeof(int), h->g.stream));
+  const int itr0 = h->itr;
+  h->cur_thr = h->opt.bp_conv_threshold;
+  int rc = GBX_OK;
+  while (done < h->opt.itrmax && rc == GBX_OK) {
+    const int nb = std::min(batch, h->opt.itrmax - done);
+    for (int b = 1; b <= nb && rc == GBX_OK; ++b) {
+      h->cur_it = itr0 + done + b;
+      rc = l_iteration(h);
+    }
+    if (rc != GBX_OK) break;
+    done += nb;
+    cudaError_t ce = cudaMemcpyAsync(&h->hP->done_at, &h->P->done_at, sizeof(int), cudaMemcpyDeviceToHost, h->g.stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->g.stream);
+    if (ce != cudaSuccess) {
+      last_error() = std::string("gbx_lsbm_em: ") + cudaGetErrorString(ce);
+      rc = GBX_ERR_CUDA;
+      break;
+    }
+    const int done_at = h->hP->done_at;
+    if (done_at != 0) {
+      if ((itr0 + done - done_at) & 1) h->cur ^= 1;   // queued passes that did nothing still flipped the buffers
+      h->itr = done_at;
       cnv = 1;
-      itrnum = itr;
+      itrnum = done_at - itr0;
+      done = itrnum;
       break;
     }
   }
+  h->cur_it = 0;
+  h->cur_thr = -1.0;
+  L_TRY(rc);
   L_TRY(gbx_lsbm_finalize(h, res));
   res->cnv = cnv;
   res->itrnum = itrnum;

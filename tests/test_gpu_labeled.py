@@ -80,3 +80,22 @@ def test_labeled_input_checks(gpu_required):
     rc, msg = create([(1, 2, 1), (2, 1, 2)], 2)
     assert rc == -1 and "directions" in msg
     assert create([(1, 2, 1), (2, 1, 1)], 5)[0] == -1                  # more labels than GBX_MAX_LABELS
+
+
+def test_labeled_queued_iterations_are_exact(gpu_required, monkeypatch):
+    """gbx_lsbm_em queues 8 iterations on small graphs; the device freezes the state at the converging one."""
+    from graphbix_b200.labeled import EM_labeled
+    g = np.load(GOLDEN[0])
+    n, B, G, dc = int(g["n"]), int(g["B"]), int(g["G"]), bool(g["dc"])
+    outs = []
+    for batch in ("1", "8", "3"):
+        monkeypatch.setenv("GBX_EM_BATCH", batch)
+        outs.append(EM_labeled(n, list(g["Larray"]), B, G, g["links"], 2000, 1e-9, True, True, dc, 0.3, 0, ["a", "d"], 1 / B,
+                               PSIcav0=g["psi0"], affinity0=g["affinity0"]))
+    assert outs[0][12] and 1 < outs[0][13] < 2000
+    for o in outs[1:]:
+        assert o[13] == outs[0][13] and o[12]
+        # shared-memory atomics make the sums order dependent: equal to rounding, not bit for bit
+        np.testing.assert_allclose(o[2], outs[0][2], rtol=0, atol=1e-13)
+        np.testing.assert_allclose(o[1], outs[0][1], rtol=1e-12)
+        np.testing.assert_allclose(o[3:12], outs[0][3:12], rtol=1e-11)
