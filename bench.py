@@ -469,6 +469,7 @@ def run_ours(a):
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
+    eng.iterate(30, read_conv=False)          # bring the clocks up before the W warm-up steps the caller asked for
     eng.iterate(a.warmup, read_conv=False)
     barrier()
     sampler.mark("start")
