@@ -99,3 +99,23 @@ def test_labeled_queued_iterations_are_exact(gpu_required, monkeypatch):
         np.testing.assert_allclose(o[2], outs[0][2], rtol=0, atol=1e-13)
         np.testing.assert_allclose(o[1], outs[0][1], rtol=1e-12)
         np.testing.assert_allclose(o[3:12], outs[0][3:12], rtol=1e-11)
+
+
+def test_labeled_main_program_mirror(gpu_required, tmp_path):
+    """graphbix_b200.labeled_main: the notebook's MAIN on a planted two-label graph; q* = 2 and the planted groups."""
+    from graphbix_b200.labeled_main import run
+    from graphbix_b200.synth import labeled_planted_partition
+    links, lab = labeled_planted_partition(400, 2, [6.0, 4.0], ["d", "a"], 0.05, seed=8)
+    und = links[links[:, 0] < links[:, 1]]
+    path = tmp_path / "edges.txt"
+    path.write_text("".join(f"{i} {j} {a}\n" for i, j, a in und))
+    out = run(str(path), "t", Barray=[2, 3], samples=2, dc=True, REDfrac=0.0, assortativity=["d", "a"], seed=3,
+              outdir=str(tmp_path), log=lambda *a: None)
+    for f in ("summary_t.txt", "assessment_t.txt", "assignment_t.txt"):
+        assert (tmp_path / f).stat().st_size > 0
+    assert "q* = " in (tmp_path / "summary_t.txt").read_text()
+    assert out["CV"]["Bayes"][0, 0] < 1.2 * out["CV"]["Bayes"][1, 0]
+    a = np.loadtxt(tmp_path / "assignment_t.txt", dtype=np.int64)
+    ids, block2 = a[:, 0], a[:, 1]
+    agree = (block2 - 1 == lab[ids - 1]).mean()
+    assert max(agree, 1 - agree) > 0.9
