@@ -142,6 +142,17 @@ __global__ void k_lsbm_degrees(const int* __restrict__ rowptr, const unsigned ch
   }
 }
 
+// degrees[i, alpha] degrees[j, alpha] Ntot of every slot (row i, column j, label alpha): fixed for the whole run, so the
+// sweep reads one streamed value per slot instead of gathering the neighbour's degree twice per iteration.
+__global__ void k_lsbm_dd(long long K, int G, const int* __restrict__ erow, const int* __restrict__ col,
+                          const unsigned char* __restrict__ lab, const double* __restrict__ deg, double N,
+                          double* __restrict__ dd) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < K; e += (long long)gridDim.x * blockDim.x) {
+    const int a = lab[e];
+    dd[e] = deg[(size_t)erow[e] * G + a] * deg[(size_t)col[e] * G + a] * N;
+  }
+}
+
 // ---- the sweep ----------------------------------------------------------------------------------------------------
 // LPV lanes per vertex (1 for large graphs, else 8, 16 or 32 from the mean degree), one lane per incoming link (rounds of LPV for
 // larger degrees): the lanes read the vertex's contiguous run of messages coalesced, each computes the log term of its
@@ -151,7 +162,8 @@ template <int MODE, int QT, int LPV>
 __global__ void __launch_bounds__(256) k_lsbm_vertex(int n, int qrt, int G, const int* __restrict__ rowptr,
                                                      const int* __restrict__ col, const int* __restrict__ rev,
                                                      const unsigned char* __restrict__ lab, const double* __restrict__ deg,
-                                                     const double* __restrict__ cur, double* __restrict__ nxt,
+                                                     const double* __restrict__ ddN, const double* __restrict__ cur,
+                                                     double* __restrict__ nxt,
                                                      double* __restrict__ PSI, LParams* P, double N, double damping,
                                                      int it) {
   __shared__ double red[256];
@@ -173,7 +185,7 @@ __global__ void __launch_bounds__(256) k_lsbm_vertex(int n, int qrt, int G, cons
       const int e = base + lane;
       if (e < e1) {
         const int a = lab[e];
-        const double dd = deg[(size_t)i * G + a] * deg[(size_t)col[e] * G + a];
+        const double dd = ddN[e];
         double psi[QA];
         row_load<QT, QA>(cur, e, q, psi);
         const double* A = P->aff[a];
@@ -184,7 +196,7 @@ __global__ void __launch_bounds__(256) k_lsbm_vertex(int n, int qrt, int G, cons
 #pragma unroll
             for (int r = 0; r < QA; ++r)
               if (r < q) s += psi[r] * A[r * q + t];
-            term[t] = log(dd * s * N);
+            term[t] = log(dd * s);
             x[t] += term[t];
           }
         }
@@ -222,7 +234,7 @@ __global__ void __launch_bounds__(256) k_lsbm_vertex(int n, int qrt, int G, cons
         if (e < e1) {
           if (!single) {
             const int a = lab[e];
-            const double dd = deg[(size_t)i * G + a] * deg[(size_t)col[e] * G + a];
+            const double dd = ddN[e];
             double psi[QA];
             row_load<QT, QA>(cur, e, q, psi);
             const double* A = P->aff[a];
@@ -233,7 +245,7 @@ __global__ void __launch_bounds__(256) k_lsbm_vertex(int n, int qrt, int G, cons
 #pragma unroll
                 for (int r = 0; r < QA; ++r)
                   if (r < q) s += psi[r] * A[r * q + t];
-                term[t] = log(dd * s * N);
+                term[t] = log(dd * s);
               }
             }
           }
@@ -488,7 +500,7 @@ struct gbx_lsbm {
   int q = 0, G = 0;
   gbx_lsbm_options opt{};
   unsigned char* lab = nullptr;
-  double *deg = nullptr, *msg[2] = {nullptr, nullptr}, *PSI = nullptr;
+  double *deg = nullptr, *dd = nullptr, *msg[2] = {nullptr, nullptr}, *PSI = nullptr;
   LParams* P = nullptr;
   LParams* hP = nullptr;     // pinned mirror
   int cur = 0;
@@ -527,7 +539,7 @@ int l_vertex_ql(gbx_lsbm* h) {
   const int gpb = 256 / LPV;
   const int grid = (int)std::min<int64_t>(std::max<int64_t>(1, (h->g.n + gpb - 1) / gpb), (int64_t)h->g.num_sms * 8);
   k_lsbm_vertex<MODE, QT, LPV><<<grid, 256, 0, h->g.stream>>>((int)h->g.n, h->q, h->G, h->g.rowptr, h->g.col, h->g.rev,
-                                                              h->lab, h->deg, h->msg[h->cur], h->msg[h->cur ^ 1], h->PSI,
+                                                              h->lab, h->deg, h->dd, h->msg[h->cur], h->msg[h->cur ^ 1], h->PSI,
                                                               h->P, (double)h->g.n, h->opt.damping, h->cur_it);
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
@@ -647,6 +659,7 @@ int gbx_lsbm_create(gbx_lsbm** out, int device, int64_t n, int64_t K, const int6
     const int dv = device;
     GBX_CUDA_TRY(dev_malloc(dv, (void**)&h->lab, std::max<size_t>((size_t)K, 1), true));
     GBX_CUDA_TRY(dev_malloc(dv, (void**)&h->deg, std::max<size_t>((size_t)n * h->G, 1) * sizeof(double), true));
+    GBX_CUDA_TRY(dev_malloc(dv, (void**)&h->dd, std::max<size_t>((size_t)K, 1) * sizeof(double), true));
     GBX_CUDA_TRY(dev_malloc(dv, (void**)&h->msg[0], std::max<size_t>((size_t)K * q, 1) * sizeof(double), true));
     GBX_CUDA_TRY(dev_malloc(dv, (void**)&h->msg[1], std::max<size_t>((size_t)K * q, 1) * sizeof(double), true));
     GBX_CUDA_TRY(dev_malloc(dv, (void**)&h->PSI, (size_t)n * q * sizeof(double), true));
@@ -697,6 +710,7 @@ int gbx_lsbm_destroy(gbx_lsbm* h) {
   dev_free(dv, h->g.slot_of_link);
   dev_free(dv, h->lab);
   dev_free(dv, h->deg);
+  dev_free(dv, h->dd);
   dev_free(dv, h->msg[0]);
   dev_free(dv, h->msg[1]);
   dev_free(dv, h->PSI);
@@ -743,7 +757,8 @@ int gbx_lsbm_init(gbx_lsbm* h, const double* gr, const double* affinity, const d
     h->launches++;
   }
   k_lsbm_degrees<<<h->grid_v, 256, 0, st>>>(h->g.rowptr, h->lab, (int)h->g.n, G, h->opt.dc, h->deg);
-  h->launches++;
+  if (K > 0) k_lsbm_dd<<<h->grid_e, 256, 0, st>>>((long long)K, G, h->g.erow, h->g.col, h->lab, h->deg, (double)h->g.n, h->dd);
+  h->launches += 2;
   GBX_CUDA_TRY(cudaGetLastError());
   // h = zeros(G,B); PSI = updatePSI(); h = update_h()   (notebook EM, "initial state")
   L_TRY(l_vertex<LMODE_MARGINAL>(h));
