@@ -31,3 +31,40 @@ def test_em_fixed_point_matches_oracle(gpu_required, path):
     np.testing.assert_allclose(eng.messages(), g["PSIcav"], rtol=0, atol=1e-6)
     np.testing.assert_allclose(eng.state()["theta"], g["theta"], rtol=1e-6)
     eng.close()
+
+
+@pytest.mark.parametrize("q,seed,prior", [(2, 1, True), (3, 2, True), (4, 3, False), (8, 4, False)])
+def test_cuda_marginals_are_exact_on_a_tree(gpu_required, q, seed, prior):
+    """Independent of the oracle: on a tree BP is exact, so the CUDA path's fixed point (affinity frozen, prior learning
+    on) must equal brute-force enumeration of prod_i gr e^{-h} prod_edges Crs, and its Bethe free energy -log Z."""
+    import math
+
+    from test_oracle_exact_tree import exact_marginals, random_tree
+    from graphbix_b200.engine import EM, SbmEngine
+    rng = np.random.default_rng(seed)
+    n = 9 if q < 8 else 6
+    links = random_tree(n, rng)
+    K = len(links)
+    A = rng.uniform(0.5, 3.0, size=(q, q))
+    C = 0.5 * (A + A.T) + 2.0 * np.eye(q)
+    gr0 = rng.dirichlet(np.ones(q) * 5)
+    psi0 = rng.random((K, q))
+    psi0 /= psi0.sum(axis=1, keepdims=True)
+    out, eng, res = EM(n, q, links, 1e9, (gr0, C), False, 3000, prior, 0.0, PSIcav0=psi0, BPconvthreshold=1e-14,
+                       return_engine=True)
+    gr, Crs, PSI, FE = out[0].ravel(), out[1], out[2], out[3]
+    assert out[13] and res.nonfinite == 0
+    np.testing.assert_allclose(Crs, C, rtol=1e-15)
+    if not prior:   # gr stays the mean of the initial marginals through the sweeps (sbm.jl:341): read it after init
+        e0 = SbmEngine(n, links, q)
+        e0.set_options(degreecorrection=0, priorlearning=0, learningrate=0.0)
+        e0.init(gr0, C, psi0)
+        gr = e0.state()["gr"]
+        e0.close()
+    h = PSI.sum(axis=0) @ C / n
+    marg, logZ = exact_marginals(n, q, links, gr, C, np.tile(h, (n, 1)))
+    assert np.abs(marg - PSI).max() < 1e-9
+    if prior:
+        bethe = -n * (FE + 0.5 * float(gr @ C @ gr)) - (K // 2) * math.log(n)
+        assert abs(bethe - logZ) < 1e-8
+    eng.close()
