@@ -100,3 +100,30 @@ def test_bp_is_exact_on_a_tree_with_degree_correction():
     h = (r.theta[:, None] * r.PSI).sum(axis=0) @ C / n                        # update_h, sbm.jl:70-73
     marg, _ = exact_marginals(n, q, links, r.gr, C, r.theta[:, None] * h[None, :])
     assert np.abs(marg - r.PSI).max() < 1e-9                                  # theta_i theta_j factors cancel in the marginals
+
+
+@pytest.mark.parametrize("q,dc,seed", [(2, False, 3), (3, False, 6), (4, False, 2)])
+def test_mod_oracle_bp_is_exact_on_a_tree(q, dc, seed):
+    """mod.jl's model on a tree: P(sigma) ~ prod_i gr[sigma_i] exp(-alpha beta d_i h[sigma_i]) prod_edges
+    (1 + (e^beta - 1) delta(sigma_i, sigma_j)) with d_i = 1 without degree correction (mod.jl:38-52); omegas frozen.
+    (With degree correction the hub's self-field alpha beta d_i h makes BP oscillate on a ten-vertex tree, for the
+    reference's schedule too, so only the uncorrected model is enumerated.)"""
+    from oracle import mod_oracle as M
+    rng = np.random.default_rng(seed)
+    n = 10
+    # a tree with a hub, so that the mean excess degree of mod.jl:185 is > 1 and beta is finite
+    und = [(1, v) for v in range(2, 7)] + [(int(rng.integers(2, v)), v) for v in range(7, n + 1)]
+    und = np.array(und, dtype=np.int64)
+    links = np.vstack([und, und[:, ::-1]])
+    K = len(links)
+    gr = rng.dirichlet(np.ones(q) * 5)
+    psi0 = rng.random((K, q))
+    psi0 /= psi0.sum(axis=1, keepdims=True)
+    r = M.EM(gr, n, q, links, 1, 3000, 0.0, False, False, dc, 0.3, rng=rng, PSIcav0=psi0, BPconvthreshold=1e-14)
+    assert r.cnv and np.isfinite(r.beta)
+    deg = np.bincount(links[:, 0] - 1, minlength=n).astype(np.float64)
+    d = deg if dc else np.ones(n)
+    h = d @ r.PSI                                                              # update_h, mod.jl:22-24
+    C = np.ones((q, q)) + (math.exp(r.beta) - 1) * np.eye(q)
+    marg, _ = exact_marginals(n, q, links, gr, C, r.alpha * r.beta * d[:, None] * h[None, :])
+    assert np.abs(marg - r.PSI).max() < 1e-9
