@@ -4,7 +4,8 @@ alpha, beta; EM + belief propagation + leave-one-out cross-validation errors).
 
 PARITY UNPINNED: as for oracle/sbm_oracle.py -- no Julia toolchain, no golden vectors upstream; this is a
 statement-by-statement transcription (each function cites the mod.jl lines it follows), checked against the
-independent synchronous formulation (tests/sync_model_mod.py).
+independent synchronous formulation (tests/sync_model_mod.py) and, because belief propagation is exact on trees,
+against brute-force enumeration of the model's labelings on small trees (tests/test_oracle_exact_tree.py).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
 """
