@@ -58,3 +58,32 @@ def test_mod_em_fixed_point_matches_oracle(gpu_required, path):
     np.testing.assert_allclose(eng.state()["gr"], g["gr"], rtol=1e-6)
     assert np.array_equal(eng.assignment(), np.argmax(g["PSI"], axis=1) + 1)
     eng.close()
+
+
+@pytest.mark.parametrize("q,seed", [(2, 3), (3, 6), (4, 2)])
+def test_mod_cuda_marginals_are_exact_on_a_tree(gpu_required, q, seed):
+    """Independent of the oracle: on a tree BP is exact, so the CUDA fixed point of mod.jl's model (omegas frozen, no
+    degree correction) equals brute-force enumeration of prod_i gr e^{-alpha beta h} prod_edges (1 + (e^beta - 1) delta)."""
+    import math
+
+    from test_oracle_exact_tree import exact_marginals
+    from graphbix_b200.engine import EM_mod
+    rng = np.random.default_rng(seed)
+    n = 10
+    und = [(1, v) for v in range(2, 7)] + [(int(rng.integers(2, v)), v) for v in range(7, n + 1)]
+    und = np.array(und, dtype=np.int64)
+    links = np.vstack([und, und[:, ::-1]])
+    K = len(links)
+    gr = rng.dirichlet(np.ones(q) * 5)
+    psi0 = rng.random((K, q))
+    psi0 /= psi0.sum(axis=1, keepdims=True)
+    # ten vertices and a global field: the synchronous schedule needs damping here (same fixed point)
+    out = EM_mod(gr, n, q, links, 1, 5000, 0.0, False, False, False, 0.3, PSIcav0=psi0, BPconvthreshold=1e-14, damping=0.5)
+    alpha, beta, PSI = out[1], out[2], out[5]
+    if not out[15]:
+        pytest.skip("synchronous BP oscillates on this ten-vertex tree even with damping 0.5")
+    assert math.isfinite(beta)
+    h = PSI.sum(axis=0)
+    C = np.ones((q, q)) + (math.exp(beta) - 1) * np.eye(q)
+    marg, _ = exact_marginals(n, q, links, gr, C, alpha * beta * np.tile(h, (n, 1)))
+    assert np.abs(marg - PSI).max() < 1e-9
