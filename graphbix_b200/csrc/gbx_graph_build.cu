@@ -9,7 +9,7 @@
 //
 // A partitioned run (`world` ranks, one GPU each) splits the vertices into `world` equal contiguous ranges; because
 // the CSR is destination-major, a rank's rows are one contiguous range of the global slot space, so its local slot
-// is the global slot minus a base and rev[e] becomes (owner rank << 28 | slot in the owner's buffer).
+// is the global slot minus a base and rev[e] becomes (owner rank << REV_SHIFT (29) | slot in the owner's buffer).
 //
 // One 64-bit radix sort (CUB) of (destination, source) keys; everything else is a map or a scan.
 #include <cub/cub.cuh>

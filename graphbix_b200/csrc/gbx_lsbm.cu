@@ -408,13 +408,18 @@ __global__ void k_lsbm_pre(LParams* P, int q, int G, int it) {
   }
 }
 
-// gr = lr * update_gr(PSI) + (1 - lr) * gr; affinity = lr * update_affinity() + (1 - lr) * affinity   (EM main loop)
+// gr = lr * update_gr(PSI) + (1 - lr) * gr; affinity = lr * update_affinity() + (1 - lr) * affinity   (EM main loop).
+// In the notebook update_gr rebinds EM()'s `gr` before the blend reads it and update_affinity mutates and returns the
+// same Dict, so both blends mix the new value with itself: the learning rate does not act (kept bit for bit).
 __global__ void k_lsbm_post(LParams* P, int q, int G, double N, double K, double lr, int prior, int learning, int red,
                             int it, double thr) {
   const int tid = threadIdx.x;
   if (l_skip(P, it)) return;
   if (tid == 0 && it != 0 && P->done_at == 0 && P->conv < thr) P->done_at = it;   // acted on from iteration it + 1
-  if (prior && tid < q) P->gr[tid] = lr * (P->sumPSI[tid] / N) + (1.0 - lr) * P->gr[tid];
+  if (prior && tid < q) {
+    const double g = P->sumPSI[tid] / N;
+    P->gr[tid] = lr * g + (1.0 - lr) * g;
+  }
   if (learning) {
     for (int k = tid; k < G * q * q; k += blockDim.x) {
       const int a = k / (q * q), r = (k % (q * q)) / q, s = k % q;
@@ -423,7 +428,7 @@ __global__ void k_lsbm_post(LParams* P, int q, int G, double N, double K, double
       if (red && a == G - 1) v = 1.0 / K;                // RED edges: fixed flat matrix
       if (!(v == v)) P->status |= 1;
       // Gnew / denom are read by every thread of this single block before anybody writes aff: aff has its own slot k
-      P->aff[a][r * q + s] = lr * v + (1.0 - lr) * P->aff[a][r * q + s];
+      P->aff[a][r * q + s] = lr * v + (1.0 - lr) * v;
     }
   }
 }

@@ -7,8 +7,8 @@
 //     incoming messages as one contiguous run; rev[e] = slot of the opposite message i -> col[e];
 //   * two message buffers (ping-pong): a sweep reads `cur` and scatters the new messages to `nxt` at rev[e]
 //     with 256-bit stores -- a synchronous (Jacobi) sweep, deterministic by construction;
-//   * PSI (N x q), theta (N); tiles = runs of consecutive vertices with <= 256 edge slots (one CTA iteration
-//     each, one thread per slot); vertices with more than 256 edges ("hubs") get a CTA each.
+//   * PSI (N x q), theta (N); tiles = runs of consecutive vertices with <= TILE_E = 128 edge slots (one CTA
+//     iteration each, one thread per slot); vertices with more than 128 edges ("hubs") get a CTA each.
 #include <algorithm>
 #include <chrono>
 #include <mutex>
@@ -486,6 +486,7 @@ int gbx_sbm_destroy(gbx_sbm* h) {
   if (!h) return GBX_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);  // blocks go back to the cache: nothing of this handle may still be running
+  if (h->ops && h->ops->release) h->ops->release(h);
   for (int k = 1; k < MAXPEER; ++k)
     if (h->peer_stream[k]) cudaStreamSynchronize(h->peer_stream[k]);
   for (int b = 0; b < 2; ++b)
@@ -720,11 +721,15 @@ int64_t gbx_sbm_device_bytes(const gbx_sbm* h) { return h ? h->dev_bytes : 0; }
 double gbx_sbm_sweep_bytes(const gbx_sbm* h) {
   if (!h) return 0.0;
   const double q = h->q, K = (double)h->K, n = (double)h->n;
-  double per_edge = 2.0 * q * 8.0 + 4.0;               // message in, message out, rev
-  if (h->opt.degreecorrection) per_edge += 4.0 + 8.0;  // col + theta of the neighbour
-  if (h->opt.damping != 1.0) per_edge += q * 8.0;      // old outgoing message
-  double per_vertex = 2.0 * q * 8.0 + 4.0 + 4.0;       // PSI read + write, rowptr, processing order
-  if (h->opt.degreecorrection) per_vertex += 8.0;
+  // what the sweep kernel streams: per directed edge the message read and the message written, rev and,
+  // with degree correction, one staged theta_row * theta_col scale; per vertex the marginal read and written, the
+  // row pointer and the row of the prior table
+  const bool dc = h->model == 1 ? false : h->opt.degreecorrection != 0;
+  const double damping = h->model == 1 ? h->mopt.damping : h->opt.damping;
+  double per_edge = 2.0 * q * 8.0 + 4.0;
+  if (dc) per_edge += 8.0;
+  if (damping != 1.0) per_edge += q * 8.0;             // old outgoing message
+  const double per_vertex = 2.0 * q * 8.0 + 4.0 + 4.0;
   return K * per_edge + n * per_vertex;
 }
 
@@ -943,13 +948,14 @@ int gbx_sbm_ipc_import(gbx_sbm* h, int which, int rank, const unsigned char* han
 
 int gbx_sbm_part_set_buffers(gbx_sbm* h, void* totals_dev, void* theta_dev) {
   if (!h) return fail_invalid("handle is NULL");
+  GBX_TRY(set_device(h));
   if (totals_dev) {
-    if (h->totals_owned) cudaFree(h->totals);
+    if (h->totals_owned) dev_free(h->device, h->totals);   // came from dev_malloc (possibly the block cache)
     h->totals = (double*)totals_dev;
     h->totals_owned = false;
   }
   if (theta_dev) {
-    if (h->theta_owned) cudaFree(h->theta);
+    if (h->theta_owned) dev_free(h->device, h->theta);
     h->theta = (double*)theta_dev;
     h->theta_owned = false;
   }

@@ -174,6 +174,7 @@ struct SbmOps {
   int (*occupancy)(int variant, int* vertex_occ, int* mstep_occ);
   int (*init_model)(gbx_sbm* h);  // per-vertex prior-table rows of the initial state
   int (*unpack)(gbx_sbm* h);      // packed exchange: received rows -> message buffer
+  int (*release)(gbx_sbm* h);     // the handle is going away: give up the shared __constant__ parameter block
 };
 
 }  // namespace gbx

@@ -18,6 +18,7 @@
 #error "compile with -DGBX_Q=<number of groups>"
 #endif
 #include <algorithm>
+#include <mutex>
 
 #include "gbx_sbm_internal.h"
 
@@ -44,6 +45,45 @@ constexpr double LN2 = 0.6931471805599453;
 constexpr double EXP_M500 = 7.124576406741286e-218;  // e^-500, sbm.jl:33-35
 
 __constant__ SbmParams c_P;
+
+// c_P is ONE object per (q, model, device): the handles that share it take turns.  A handle that launches a kernel
+// reading c_P first makes sure the object holds ITS parameters: if another handle (or this handle on another stream)
+// used it last, this handle's stream waits for that user's queued kernels and reloads h->params.  With one handle
+// per (q, model, device) -- the q sweep -- this is a pointer compare.  Host threads: handles of equal (q, model) on
+// one device must be driven from one thread at a time (include/graphbix_cuda.h).
+struct ParamOwner {
+  const gbx_sbm* h = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev = nullptr;
+};
+ParamOwner g_owner[64];
+std::mutex g_owner_mu;
+
+int acquire_params(gbx_sbm* h, bool reload) {
+  std::lock_guard<std::mutex> lock(g_owner_mu);
+  ParamOwner& o = g_owner[h->device & 63];
+  if (o.h == h && o.stream == h->stream) return GBX_OK;
+  if (o.h != nullptr && o.stream != h->stream) {  // the previous user's kernels may still be reading c_P
+    if (!o.ev) GBX_CUDA_TRY(cudaEventCreateWithFlags(&o.ev, cudaEventDisableTiming));
+    GBX_CUDA_TRY(cudaEventRecord(o.ev, o.stream));
+    GBX_CUDA_TRY(cudaStreamWaitEvent(h->stream, o.ev, 0));
+  }
+  if (reload)
+    GBX_CUDA_TRY(cudaMemcpyToSymbolAsync(c_P, h->params, sizeof(SbmParams), 0, cudaMemcpyDeviceToDevice, h->stream));
+  o.h = h;
+  o.stream = h->stream;
+  return GBX_OK;
+}
+
+int op_release(gbx_sbm* h) {  // gbx_sbm_destroy: the handle's stream has been synchronised
+  std::lock_guard<std::mutex> lock(g_owner_mu);
+  ParamOwner& o = g_owner[h->device & 63];
+  if (o.h == h) {
+    o.h = nullptr;
+    o.stream = nullptr;
+  }
+  return GBX_OK;
+}
 
 // rev[e] packs (owner rank, slot inside the owner's buffer); one rank: owner 0.
 __device__ __forceinline__ int rev_owner(int rv) { return (int)((unsigned)rv >> REV_SHIFT); }
@@ -453,7 +493,7 @@ __device__ __forceinline__ void store_partials(const LaneAcc& acc, double* scrat
 }
 
 // ---------------------------------------------------------------------------------------------
-// BP sweep over the tiled (degree <= 256) vertices.  Persistent CTAs; the messages of tile k+1 are staged into
+// BP sweep over the tiled (degree <= TILE_E = 128) vertices.  Persistent CTAs; the messages of tile k+1 are staged into
 // shared memory with cp.async (LDGSTS) while tile k is computed, so the HBM latency is covered by bytes in
 // flight in shared memory rather than by registers or occupancy (double buffer, 2 CTA barriers per tile).
 //   stage 1  one thread per incoming edge slot: psi row from smem, T = theta theta psi*Crs, rescaled   -> smem
@@ -815,7 +855,7 @@ __global__ void __launch_bounds__(NT, ((Q <= 8) ? 3 : 2) * (256 / NT)) sbm_verte
 }
 
 // ---------------------------------------------------------------------------------------------
-// Hubs (degree > 256): one CTA per vertex, two passes over its incoming messages; the per-component
+// Hubs (degree > TILE_E = 128): one CTA per vertex, two passes over its incoming messages; the per-component
 // product is carried as (mantissa in [1,2), exponent) so any degree is safe.
 template <int MODE>
 __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base) {
@@ -1409,6 +1449,7 @@ VertexArgs vertex_args(gbx_sbm* h) {
 
 template <int MODE>
 int launch_vertex_pass_t(gbx_sbm* h) {
+  { const int rc = acquire_params(h, true); if (rc != GBX_OK) return rc; }
   VertexArgs a = vertex_args(h);
   if (h->ntiles > 0) {
     sbm_vertex_kernel<MODE><<<h->grid_vertex, NT, SweepSmem::total, h->stream>>>(a);
@@ -1428,6 +1469,7 @@ int launch_vertex_pass_t(gbx_sbm* h) {
 // (rev_pack holds the positions), hubs first, then the tiles in `nchunks` pieces; when a piece is done its part of
 // every run is pushed to the owner's receive buffer by the copy engine while the next piece computes.
 int launch_packed_sweep(gbx_sbm* h) {
+  { const int rc = acquire_params(h, true); if (rc != GBX_OK) return rc; }
   VertexArgs a = vertex_args(h);
   a.rev = h->rev_pack;
   for (int o = 0; o < h->world; ++o)
@@ -1548,6 +1590,7 @@ int op_prepare(gbx_sbm* h, int zero_h, int gr_from_sum) {
                                        (double)h->max_degree, h->cur_it);
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
+  { const int rc = acquire_params(h, false); if (rc != GBX_OK) return rc; }
   GBX_CUDA_TRY(cudaMemcpyToSymbolAsync(c_P, h->params, sizeof(SbmParams), 0, cudaMemcpyDeviceToDevice, h->stream));
   {
     const int nrows = dc_tab ? 1 + (TILE_E + 1) * Q : 1;
@@ -1591,6 +1634,7 @@ PeerCur peer_cur(const gbx_sbm* h) {
 }
 
 int op_fe_local(gbx_sbm* h, int pass) {
+  { const int rc = acquire_params(h, true); if (rc != GBX_OK) return rc; }
   if (pass == 0)
     sbm_fe_kernel<0><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->rev, h->col, h->erow, (long long)h->K, h->msg[h->cur],
                                                        peer_cur(h), h->theta, h->opt.degreecorrection, h->rank, h->part_fe);
@@ -1704,8 +1748,10 @@ __global__ void mod_apply_totals(SbmState* st, const double* __restrict__ tot, c
       if (oin > maxomega) oin = maxomega;                             // mod.jl:97-103
       else if (oin < 0.0) oin = 0.0;
       else if (oout < 0.0) oout = 0.0;
-      st->omegain = lr * oin + (1.0 - lr) * st->omegain;              // mod.jl:226-227
-      st->omegaout = lr * oout + (1.0 - lr) * st->omegaout;
+      // mod.jl:226-227.  update_omega() has already assigned EM()'s own omegain / omegaout (closure write-through,
+      // mod.jl:90-94), so the reference blends the new value with itself: the learning rate does not act here.
+      st->omegain = lr * oin + (1.0 - lr) * oin;
+      st->omegaout = lr * oout + (1.0 - lr) * oout;
       st->beta = log(st->omegain / st->omegaout);                     // update_alphabeta, mod.jl:108-112
       st->alpha = (st->omegain - st->omegaout) / st->beta;
       if (!(st->beta == st->beta) || !(st->alpha == st->alpha)) st->status |= 1;
@@ -1829,6 +1875,7 @@ int mop_prepare(gbx_sbm* h, int zero_h, int) {
   mod_prepare<<<1, 32, 0, h->stream>>>(h->st, h->params, (double)h->n_global, zero_h, h->cur_it);
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
+  { const int rc = acquire_params(h, false); if (rc != GBX_OK) return rc; }
   GBX_CUDA_TRY(cudaMemcpyToSymbolAsync(c_P, h->params, sizeof(SbmParams), 0, cudaMemcpyDeviceToDevice, h->stream));
   const int dc_tab = h->mopt.dc;
   const int nrows = dc_tab ? 1 + (TILE_E + 1) * Q : 1;
@@ -1847,6 +1894,7 @@ PeerCur peer_cur(const gbx_sbm* h) {
 }
 
 int mop_fe_local(gbx_sbm* h, int pass) {
+  { const int rc = acquire_params(h, true); if (rc != GBX_OK) return rc; }
   if (pass == 0)
     mod_fe_kernel<0><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->rev, h->col, h->erow, h->deg_global, (long long)h->K,
                                                        h->msg[h->cur], peer_cur(h), h->mopt.dc, h->rank, h->part_fe);
@@ -1877,11 +1925,11 @@ int mop_fe_final(gbx_sbm* h) {
 
 const SbmOps kOps = {Q,          op_vertex_pass, op_local_totals, mop_apply_totals,   mop_prepare,   mop_noop,     mop_noop,
                      mop_noop,   mop_fe_local,   mop_fe_apply,    mop_fe_final,       op_permute,    op_random_messages,
-                     op_assignment, op_occupancy, op_init_model, op_unpack};
+                     op_assignment, op_occupancy, op_init_model, op_unpack, op_release};
 #else
 const SbmOps kOps = {Q,          op_vertex_pass, op_local_totals, op_apply_totals,    op_prepare,    op_theta_local, op_theta_apply,
                      op_escale,  op_fe_local,    op_fe_apply,     op_fe_final,        op_permute,    op_random_messages,
-                     op_assignment, op_occupancy, op_init_model, op_unpack};
+                     op_assignment, op_occupancy, op_init_model, op_unpack, op_release};
 #endif
 
 }  // namespace

@@ -128,7 +128,9 @@ typedef struct gbx_mod_options {
   int dc;                   /* mod.jl:189  --dc            (default 1)                          */
   int learning;             /* mod.jl:224  --learning      (default 1)                          */
   int priorlearning;        /* mod.jl:221  --prior         (default 0)                          */
-  double learningrate;      /* mod.jl:226  --learningrate  (default 0.3)                        */
+  double learningrate;      /* mod.jl:226  --learningrate  (default 0.3).  No effect, as in the reference:
+                               update_omega() rebinds EM()'s omegain/omegaout (mod.jl:90-94) before the
+                               blend of mod.jl:226-227 reads them, so new is mixed with new.        */
   double maxomega;          /* mod.jl:810  maxomega = 1                                         */
   int itrmax;               /* mod.jl:219  --itrmax        (default 256)                        */
   double betafrac;          /* mod.jl:194  position between beta* and beta0 (driver: 0, +0.1 per retry) */
@@ -179,7 +181,7 @@ typedef struct gbx_lsbm_options {
   int dc;                   /* degree correction: degrees[i,alpha] = alpha-labelled links at i, else all ones (default 1) */
   int learning;             /* update the affinity matrices (default 1)                                                   */
   int priorlearning;        /* update gr (default 1)                                                                      */
-  double learningrate;      /* default 0.3                                                                                */
+  double learningrate;      /* default 0.3; as in the notebook the blends mix the new gr / affinity with themselves (no effect) */
   int itrmax;               /* default 512                                                                                */
   double bp_conv_threshold; /* default 1e-6                                                                               */
   double REDfrac;           /* != 0: the last label holds the randomly discarded edges, its matrix stays flat at 1/K      */

@@ -197,10 +197,16 @@ def EM(Ntot, Larray, B, G, links, itrmax, BPconvthreshold, learning, priorlearni
         perm = perms[itr - 1] if perms is not None else rng.permutation(Ntot)
         BPconv = BP(perm)
         itrs_done = itr
+        # Closure write-through of the notebook: `update_gr` rebinds EM()'s `gr` before the right operand of
+        # `gr = learningrate*update_gr(PSI) + (1 - learningrate)*gr` is read (Julia evaluates left to right), and
+        # `update_affinity` mutates and returns the SAME Dict, so both blends mix the new value with itself:
+        # the learning rate has no effect on the notebook's trajectory.
         if priorlearning:
-            st["gr"] = learningrate * PSI.mean(axis=0) + (1 - learningrate) * st["gr"]
+            st["gr"] = PSI.mean(axis=0)                                          # update_gr: gr = mean(PSI,1)
+            st["gr"] = learningrate * st["gr"] + (1 - learningrate) * st["gr"]
         if learning:
-            st["aff"] = learningrate * update_affinity() + (1 - learningrate) * st["aff"]
+            st["aff"] = update_affinity()                                        # affinity[alpha] = ... in place
+            st["aff"] = learningrate * st["aff"] + (1 - learningrate) * st["aff"]
         if BPconv < BPconvthreshold:
             cnv, itrnum = True, itr
             break

@@ -3,7 +3,9 @@
 alpha, beta; EM + belief propagation + leave-one-out cross-validation errors).
 
 PARITY UNPINNED: as for oracle/sbm_oracle.py -- no Julia toolchain, no golden vectors upstream; this is a
-statement-by-statement transcription (each function cites the mod.jl lines it follows), checked against the
+statement-by-statement transcription (each function cites the mod.jl lines it follows) INCLUDING the reference's
+closure semantics (nested functions that assign a variable of the enclosing EM() rebind it: `h` in update_h,
+`gr` in update_gr, `omegain`/`omegaout` in update_omega, `alpha`/`beta` in update_alphabeta), checked against the
 independent synchronous formulation (tests/sync_model_mod.py) and, because belief propagation is exact on trees,
 against brute-force enumeration of the model's labelings on small trees (tests/test_oracle_exact_tree.py).
 
@@ -177,9 +179,14 @@ def EM(gr, Ntot, B, links, maxomega, itrmax, betafrac, learning, priorlearning, 
         if priorlearning:
             st["gr"] = PSI.mean(axis=0)                   # mod.jl:221-223
         if learning:                                      # mod.jl:224-229
+            # Closure write-through of the reference: update_omega() assigns the ENCLOSING EM() locals
+            # `omegain` / `omegaout` (mod.jl:90-94 -- it reads them at mod.jl:87, so they are not new locals), hence
+            # when the caller blends at mod.jl:226-227 the "old" value already is the new one:
+            # learningrate*new + (1-learningrate)*new.  --learningrate has no effect on mod.jl's trajectory.
             oin_new, oout_new = update_omega()
-            st["omegain"] = learningrate * oin_new + (1 - learningrate) * st["omegain"]
-            st["omegaout"] = learningrate * oout_new + (1 - learningrate) * st["omegaout"]
+            st["omegain"], st["omegaout"] = oin_new, oout_new                  # the write-through, mod.jl:90-103
+            st["omegain"] = learningrate * oin_new + (1 - learningrate) * st["omegain"]       # mod.jl:226
+            st["omegaout"] = learningrate * oout_new + (1 - learningrate) * st["omegaout"]    # mod.jl:227
             st["beta"] = math.log(st["omegain"] / st["omegaout"])          # update_alphabeta, mod.jl:108-112
             st["alpha"] = (st["omegain"] - st["omegaout"]) / st["beta"]
         itrs_done = itr

@@ -112,8 +112,115 @@ def main():
                                              r.varCVGT, r.varCVMAP]), itrnum=r.itrnum)
 
 
+BIG_CASES = [
+    # name, n, q, deg, eps, seed, dc, prior  -- the headline q = 8 through the C oracle (same schedule as sbm_oracle.py)
+    ("q8_nodc_prior", 6000, 8, 14.0, 0.05, 71, False, True),
+    ("q8_dc_prior", 6000, 8, 14.0, 0.05, 72, True, True),
+    ("q8_dc_noprior", 6000, 8, 14.0, 0.05, 74, True, False),
+]
+
+
+def digest(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def main_big():
+    """q = 8 fixed points (n = 6000) from the C oracle.  Inputs are regenerated from the seed by the tests
+    (helpers.planted_case); their SHA-256 is stored so that a drifting generator fails loudly instead of silently."""
+    from oracle import sbm_oracle_c as OC
+    for name, n, q, deg, eps, seed, dc, prior in BIG_CASES:
+        n2, links, psi0, lab = planted_case(n, q, deg, eps, seed)
+        gr0, C0 = assortative_init(q)
+        r = OC.EM(n2, q, links, n2, (gr0, C0), dc, 4000, prior, 0.3, PSIcav0=psi0, BPconvthreshold=1e-12,
+                  float32_logbiprob=True)
+        print("big", name, "n", n2, "K", links.shape[0], "cnv", r.cnv, "itr", r.itrs_done, "FE", r.FE)
+        assert r.cnv
+        np.savez_compressed(
+            os.path.join(HERE, f"sbmbig_em_{name}.npz"), n_req=n, n=n2, q=q, deg=deg, eps=eps, seed=seed, dc=dc,
+            prior=prior, lr=0.3, tol=1e-12, links_sha=digest(links), psi0_sha=digest(psi0), gr0=gr0, C0=C0,
+            gr=r.gr, Crs=r.Crs, PSI=r.PSI, theta=r.theta,
+            scalars=np.array([r.FE, r.CVBayes, r.CVGP, r.CVGT, r.CVMAP, r.varCVBayes, r.varCVGP, r.varCVGT,
+                              r.varCVMAP]), itrnum=r.itrnum)
+
+
+DEFAULT_SEEDS = [81, 82, 83, 84, 85, 86]
+
+
+def default_messages(K, q, seed):
+    """rand(1,B) rows normalised to 1, sbm.jl:319-323."""
+    psi0 = np.random.default_rng(seed).random((K, q))
+    return psi0 / psi0.sum(axis=1, keepdims=True)
+
+
+def main_default():
+    """The reference's default conditions (sbm.jl:293-295 `uniformAssortative`, sbm.jl:319-323 uniform random messages,
+    BPconvthreshold = 1e-6, itrmax = 256, no degree correction) on a planted 4-group graph, one run per seed, plus one
+    run of the first seed to 1e-12.  A label-symmetric start lets every schedule (and every randperm of the reference)
+    break the symmetry its own way, so what is comparable is what the reference's driver compares: the free energies
+    of the `initnum` samples and the best of them (sbm.jl:912-943)."""
+    from oracle import sbm_oracle_c as OC
+    n, q, deg, eps = 3000, 4, 10.0, 0.05
+    gr0, C0 = assortative_init(q)
+    n2, links, _, lab = planted_case(n, q, deg, eps, 81, informative=False)       # ONE graph ...
+    K = links.shape[0]
+    FE, CVB, cnv, itr, PSIs, shas = [], [], [], [], [], []
+    for seed in DEFAULT_SEEDS:                                                      # ... several random starts
+        psi0 = default_messages(K, q, seed)
+        r = OC.EM(n2, q, links, n2, (gr0, C0), False, 256, True, 0.3, PSIcav0=psi0, BPconvthreshold=1e-6,
+                  float32_logbiprob=True, seed=seed)
+        print("default", seed, "n", n2, "cnv", r.cnv, "itr", r.itrs_done, "FE", r.FE)
+        FE.append(r.FE); CVB.append(r.CVBayes); cnv.append(r.cnv); itr.append(r.itrnum)
+        PSIs.append(r.PSI.astype(np.float32)); shas.append(digest(psi0))
+    psi0 = default_messages(K, q, DEFAULT_SEEDS[0])
+    r = OC.EM(n2, q, links, n2, (gr0, C0), False, 4000, True, 0.3, PSIcav0=psi0, BPconvthreshold=1e-12,
+              float32_logbiprob=True, seed=DEFAULT_SEEDS[0])
+    print("default tight", "cnv", r.cnv, "itr", r.itrs_done, "FE", r.FE)
+    assert r.cnv
+    np.savez_compressed(
+        os.path.join(HERE, "sbmdefault_q4.npz"), n_req=n, n=n2, q=q, deg=deg, eps=eps, graph_seed=81,
+        seeds=np.array(DEFAULT_SEEDS), links_sha=digest(links), gr0=gr0, C0=C0, FE=np.array(FE), CVBayes=np.array(CVB),
+        cnv=np.array(cnv), itrnum=np.array(itr), PSI32=np.stack(PSIs), shas=np.array(shas),
+        tight_PSI=r.PSI, tight_gr=r.gr, tight_Crs=r.Crs,
+        tight_scalars=np.array([r.FE, r.CVBayes, r.CVGP, r.CVGT, r.CVMAP, r.varCVBayes, r.varCVGP, r.varCVGT,
+                                r.varCVMAP]))
+
+
+def main_fixture():
+    """The one data set the reference ships: src/labeled_sbm/labeledSBMedgelist_Nblock=[300,300,300]_c=[5,3]_X=[0.1,0.9]_1.txt
+    (900 vertices, three planted blocks of 300, label 1 disassortative, label 2 assortative), copied verbatim to
+    tests/golden/reference_labeledSBMedgelist_900.txt.  Oracle fixed point for B = 3 with the notebook's settings
+    (dc, learning, priorlearning, assortativity ["d","a"], Omega = 1/B, no random edge discarding) from uniform
+    random messages, run to 1e-12."""
+    from graphbix_b200.labeled import initial_affinity, labeledsimplegraph
+    from graphbix_b200.labeled_main import edges_per_label, read_labeled_edgelist
+    from oracle import labeled_oracle as L
+    links, ids = read_labeled_edgelist(os.path.join(HERE, "reference_labeledSBMedgelist_900.txt"))
+    s = labeledsimplegraph(links)
+    n, K, B, G = len(ids), len(s), 3, 2
+    Larray = edges_per_label(s)
+    rng = np.random.default_rng(0)
+    psi0 = rng.random((K, B))
+    psi0 /= psi0.sum(1, keepdims=True)
+    aff0 = initial_affinity(n, K, Larray, B, G, True, 0, ["d", "a"], 1 / B)
+    r = L.EM(n, Larray, B, G, s, 4000, 1e-12, True, True, True, 0.3, 0, ["d", "a"], 1 / B, rng=rng, PSIcav0=psi0)
+    print("fixture B=3", "n", n, "K", K, "cnv", r.cnv, "itr", r.itrs_done, "FE", r.FE, "CVBayes", r.CVBayes)
+    assert r.cnv
+    np.savez_compressed(
+        os.path.join(HERE, "lsbm_reference_fixture_B3.npz"), n=n, B=B, G=G, Larray=np.array(Larray), ids=np.array(ids),
+        psi0_sha=digest(psi0), links_sha=digest(s), gr=r.gr, affinity=r.affinity, PSI=r.PSI,
+        scalars=np.array([r.FE, r.CVBayes, r.CVGP, r.CVGT, r.CVMAP, r.varCVBayes, r.varCVGP, r.varCVGT, r.varCVMAP]),
+        itrnum=r.itrnum)
+
+
 if __name__ == "__main__":
-    if "labeled" in sys.argv[1:]:
+    if "fixture" in sys.argv[1:]:
+        main_fixture()
+    elif "big" in sys.argv[1:]:
+        main_big()
+    elif "default" in sys.argv[1:]:
+        main_default()
+    elif "labeled" in sys.argv[1:]:
         main_labeled()
     elif "mod" in sys.argv[1:]:
         main_mod()
@@ -122,3 +229,7 @@ if __name__ == "__main__":
     else:
         main()
         main_mod()
+        main_labeled()
+        main_big()
+        main_default()
+        main_fixture()

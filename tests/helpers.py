@@ -23,3 +23,23 @@ def planted_case(n, q, deg, eps, seed, informative=True):
 
 def assortative_init(q, cin=20.0, cout=0.01):
     return np.ones(q) / q, cin * np.eye(q) + cout * np.ones((q, q))
+
+
+def sha(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def best_permutation(P_ref, P):
+    """Column permutation `perm` of P that matches P_ref best (Hungarian on the overlap): P[:, perm] ~ P_ref."""
+    from scipy.optimize import linear_sum_assignment
+    _, c = linear_sum_assignment(-(P_ref.T @ P))
+    return c
+
+
+def big_case(g):
+    """Regenerates the inputs of a tests/golden/sbmbig_em_*.npz fixture from its seed and checks their digests."""
+    n, links, psi0, lab = planted_case(int(g["n_req"]), int(g["q"]), float(g["deg"]), float(g["eps"]), int(g["seed"]))
+    assert n == int(g["n"]) and sha(links) == str(g["links_sha"]) and sha(psi0) == str(g["psi0_sha"]), \
+        "the synthetic-graph generator drifted: regenerate tests/golden (make_golden.py big)"
+    return n, links, psi0, lab

@@ -2,7 +2,7 @@
 the notebook's EM() with a Jacobi sweep in place of the asynchronous BP().  Test helper only.
 
 One iteration:  h = update_h();  for all i at once from the old messages: cavity messages and marginals;
-conv = sum |PSI' - PSI| / N;  gr = lr mean(PSI') + (1 - lr) gr;  affinity = lr update_affinity() + (1 - lr) affinity."""
+conv = sum |PSI' - PSI| / N;  gr = mean(PSI');  affinity = update_affinity()  (the notebook's learning-rate blends mix the new value with itself)."""
 import math
 
 import numpy as np
@@ -64,9 +64,11 @@ class SyncLabeled:
         self.conv = float(np.abs(PSI - self.PSI).sum() / self.n)
         self.PSI = PSI
         if self.prior:
-            self.gr = self.lr * self.PSI.mean(axis=0) + (1 - self.lr) * self.gr
+            g = self.PSI.mean(axis=0)                       # update_gr rebinds gr: the blend mixes new with new
+            self.gr = self.lr * g + (1 - self.lr) * g
         if self.learning:
-            self.aff = self.lr * self.update_affinity() + (1 - self.lr) * self.aff
+            a = self.update_affinity()                      # mutates and returns the same Dict in the notebook
+            self.aff = self.lr * a + (1 - self.lr) * a
         return self.conv
 
     def update_affinity(self):

@@ -8,7 +8,7 @@ One EM iteration:
         psi'_{i->j} = normalize_logprob(logPSI_i - log(1 + psi_{j->i}(e^beta - 1)))        mod.jl:62-63
         PSI'_i = normalize_logprob(logPSI_i)                                              mod.jl:68-69
     conv = sum |PSI' - PSI| / N ; gr <- mean(PSI') if priorlearning                  mod.jl:72, 221-223
-    (omega_in, omega_out) <- lr * update_omega() + (1 - lr) * old ; (alpha, beta)      mod.jl:224-229
+    (omega_in, omega_out) <- update_omega() (the blend of mod.jl:226-227 mixes new with new) ; (alpha, beta)  mod.jl:224-229
 """
 from __future__ import annotations
 
@@ -89,8 +89,9 @@ class SyncMOD:
                 oin_n = 0
             elif oout_n < 0:
                 oout_n = 0
-            self.omegain = self.lr * oin_n + (1 - self.lr) * oin
-            self.omegaout = self.lr * oout_n + (1 - self.lr) * oout
+            # mod.jl:226-227 after the closure write-through of update_omega (mod.jl:90-94): new blended with itself
+            self.omegain = self.lr * oin_n + (1 - self.lr) * oin_n
+            self.omegaout = self.lr * oout_n + (1 - self.lr) * oout_n
             self.beta = math.log(self.omegain / self.omegaout)
             self.alpha = (self.omegain - self.omegaout) / self.beta
         self.itr += 1

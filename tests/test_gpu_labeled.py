@@ -119,3 +119,43 @@ def test_labeled_main_program_mirror(gpu_required, tmp_path):
     ids, block2 = a[:, 0], a[:, 1]
     agree = (block2 - 1 == lab[ids - 1]).mean()
     assert max(agree, 1 - agree) > 0.9
+
+
+def test_reference_fixture_three_blocks_and_qstar(gpu_required):
+    """The data set the reference ships with its notebook (tests/golden/reference_labeledSBMedgelist_900.txt): with the
+    notebook's settings EM_labeled lands on the oracle's fixed point for B = 3, recovers the three planted blocks of 300,
+    and the Bayes prediction error picks q* = 3 (a clear drop from B = 2, no significant gain at B = 4)."""
+    from helpers import best_permutation
+    from test_oracle_labeled import _reference_fixture
+    from graphbix_b200.labeled import EM_labeled
+    s, n, Larray, truth, g, initial_affinity = _reference_fixture()
+    K = len(s)
+    L = K // 2
+    cv, se = {}, {}
+    for B in (2, 3, 4):
+        best = None
+        for seed in range(3):                                  # notebook: `samples` runs, lowest free energy wins
+            rng = np.random.default_rng(seed)
+            psi0 = rng.random((K, B))
+            psi0 /= psi0.sum(1, keepdims=True)
+            tol = 1e-12 if (B == 3 and seed == 0) else 1e-6
+            out = EM_labeled(n, Larray, B, 2, s, 4000 if tol < 1e-9 else 512, tol, True, True, True, 0.3, 0, ["d", "a"],
+                             1 / B, PSIcav0=psi0)
+            if B == 3 and seed == 0:
+                assert out[12]
+                perm = best_permutation(g["PSI"], out[2])
+                assert np.abs(out[2][:, perm] - g["PSI"]).max() < 1e-6
+                np.testing.assert_allclose(out[0].ravel()[perm], g["gr"].ravel(), rtol=1e-6)
+                np.testing.assert_allclose(out[1][:, perm][:, :, perm], g["affinity"], rtol=1e-6, atol=1e-14)
+                np.testing.assert_allclose(np.array(out[3:12]), g["scalars"], rtol=1e-5)
+                blk = np.argmax(out[2], axis=1)
+                conf = np.zeros((3, 3))
+                np.add.at(conf, (truth, blk), 1)
+                assert conf.max(axis=1).sum() / n > 0.94           # the three blocks of 300
+                assert sorted(np.bincount(blk, minlength=3)) [0] > 250
+            if out[12] and (best is None or out[3] < best[3]):
+                best = out
+        assert best is not None
+        cv[B], se[B] = best[4], np.sqrt(best[8] / L)
+    assert cv[3] < cv[2] - 2 * se[2]                               # B = 3 is clearly better than B = 2 ...
+    assert cv[4] > cv[3] - 2 * se[3]                               # ... and B = 4 is no significant improvement: q* = 3

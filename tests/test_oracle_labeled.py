@@ -76,3 +76,43 @@ def test_labeled_golden_fixtures_reproduce():
     assert np.abs(r.PSI - g["PSI"]).max() < 1e-8
     np.testing.assert_allclose(r.affinity, g["affinity"], rtol=1e-7)
     np.testing.assert_allclose([r.FE, r.CVBayes, r.CVGP, r.CVGT, r.CVMAP], g["scalars"][:5], rtol=1e-8)
+
+
+def _reference_fixture():
+    """The edge list the reference ships (src/labeled_sbm/labeledSBMedgelist_Nblock=[300,300,300]_c=[5,3]_X=[0.1,0.9]_1.txt,
+    copied verbatim): 900 vertices, planted blocks 1-300 / 301-600 / 601-900, label 1 disassortative, label 2 assortative."""
+    import os
+    from graphbix_b200.labeled import initial_affinity, labeledsimplegraph
+    from graphbix_b200.labeled_main import edges_per_label, read_labeled_edgelist
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    links, ids = read_labeled_edgelist(os.path.join(here, "reference_labeledSBMedgelist_900.txt"))
+    s = labeledsimplegraph(links)
+    truth = (np.asarray(ids) - 1) // 300
+    return s, len(ids), edges_per_label(s), truth, np.load(os.path.join(here, "lsbm_reference_fixture_B3.npz")), initial_affinity
+
+
+def test_reference_fixture_oracle_golden_and_sync_schedule():
+    from helpers import best_permutation, sha
+    from sync_model_labeled import SyncLabeled
+    s, n, Larray, truth, g, initial_affinity = _reference_fixture()
+    assert n == 900 and list(np.bincount(truth)) == [300, 300, 300] and sha(s) == str(g["links_sha"])
+    assert Larray == list(g["Larray"]) == [2246, 1358]
+    # the oracle's fixed point recovers the planted blocks
+    blk = np.argmax(g["PSI"], axis=1)
+    conf = np.zeros((3, 3))
+    np.add.at(conf, (truth, blk), 1)
+    assert conf.max(axis=1).sum() / n > 0.94
+    # and the synchronous schedule (what gbx_lsbm.cu runs) reaches it from the same random start
+    K, B = len(s), 3
+    rng = np.random.default_rng(0)
+    psi0 = rng.random((K, B))
+    psi0 /= psi0.sum(1, keepdims=True)
+    assert sha(psi0) == str(g["psi0_sha"])
+    m = SyncLabeled(n, s, B, 2, np.ones(B) / B, initial_affinity(n, K, Larray, B, 2, True, 0, ["d", "a"], 1 / B), psi0)
+    for _ in range(600):
+        if m.iterate() < 1e-12:
+            break
+    perm = best_permutation(g["PSI"], m.PSI)
+    assert np.abs(m.PSI[:, perm] - g["PSI"]).max() < 1e-6
+    f = m.finalize()
+    np.testing.assert_allclose([f["FE"], f["CVBayes"], f["CVGP"], f["CVGT"], f["CVMAP"]], g["scalars"][:5], rtol=1e-5)
