@@ -83,6 +83,7 @@ SIGNATURES = {
     "gbx_sbm_num_links": (C.c_int64, [_P]),
     "gbx_sbm_device_bytes": (C.c_int64, [_P]),
     "gbx_sbm_sweep_bytes": (C.c_double, [_P]),
+    "gbx_sbm_sweep_kind": (C.c_int, [_P]),
     "gbx_mod_default_options": (None, [C.POINTER(ModOptions)]),
     "gbx_mod_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.c_int]),
     "gbx_mod_destroy": (C.c_int, [_P]),

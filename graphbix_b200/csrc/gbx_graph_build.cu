@@ -200,7 +200,7 @@ int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* 
     }
   auto keep = [&](void** p, size_t bytes) -> cudaError_t {
     h->dev_bytes += (int64_t)bytes;
-    return dev_malloc(dv, p, bytes ? bytes : 1, pooled);
+    return dev_malloc(dv, p, bytes + 64, pooled);   // slack: the pull kernel's bulk copies round their windows outwards
   };
   GBX_C(keep((void**)&h->rowptr, (size_t)(h->n + 1) * sizeof(int)));
   GBX_C(keep((void**)&h->col, (size_t)h->K * sizeof(int)));

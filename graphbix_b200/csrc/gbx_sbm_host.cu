@@ -74,7 +74,8 @@ int fail_state() {
 
 template <typename T>
 int dev_alloc(gbx_sbm* h, T** p, size_t count) {
-  const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  // 64 bytes of slack: the pull kernel's bulk copies round their (16-byte aligned) windows outwards
+  const size_t bytes = std::max<size_t>(count, 1) * sizeof(T) + 64;
   GBX_CUDA_TRY(dev_malloc(h->device, (void**)p, bytes, h->world == 1));
   h->dev_bytes += (int64_t)bytes;
   return GBX_OK;
@@ -97,23 +98,38 @@ int read_state(gbx_sbm* h) {
   return GBX_OK;
 }
 
-// Initial messages into buffer 0: from the caller's K_global x q array in `links` order, or drawn on the device.
+// Initial messages: from the caller's K_global x q array in `links` order, or drawn on the device.  Push layout:
+// buffer 0 holds the incoming messages of every row; pull layout: buffer 0 outgoing, buffer 1 incoming.
 int load_messages(gbx_sbm* h, const double* psicav, uint64_t seed) {
-  if (!psicav) return h->ops->random_messages(h, seed);
+  if (!psicav) return h->pull ? h->ops->pull_load(h, nullptr, seed) : h->ops->random_messages(h, seed);
   const size_t bytes = (size_t)h->K_global * h->q * sizeof(double);
   double* tmp = h->msg[1];  // scratch before the first sweep (large enough on a single rank)
   bool own = false;
-  if (h->world > 1) {
-    GBX_CUDA_TRY(cudaMalloc((void**)&tmp, bytes ? bytes : 1));
+  if (h->world > 1 || h->pull) {
+    GBX_CUDA_TRY(dev_malloc(h->device, (void**)&tmp, bytes ? bytes : 1, h->world == 1));
     own = true;
   }
   cudaError_t e = cudaMemcpyAsync(tmp, psicav, bytes, cudaMemcpyHostToDevice, h->stream);
   int rc = GBX_OK;
-  if (e == cudaSuccess) rc = h->ops->permute(h, tmp, h->msg[0], 1);
+  if (e == cudaSuccess) rc = h->pull ? h->ops->pull_load(h, tmp, 0) : h->ops->permute(h, tmp, h->msg[0], 1);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  if (own) cudaFree(tmp);
+  if (own) dev_free(h->device, tmp);
   GBX_CUDA_TRY(e);
   return rc;
+}
+
+// Which sweep kernels this EM run uses (decided at init, when the options are known).  Pull: message rows of 32 / 64 /
+// 128 bytes, no damping (a damped message cannot be rebuilt from the sender's record), one rank.  GBX_PULL=0 forces push.
+int choose_layout(gbx_sbm* h, double damping) {
+  int pull = h->ops->pull_ok && damping == 1.0 && h->world == 1 && !h->stepped && h->rec[0] != nullptr &&
+             h->theta_pp[0] != nullptr && h->theta_pp[1] != nullptr;
+  if (const char* e = getenv("GBX_PULL")) pull = pull && atoi(e) != 0;
+  h->pull = pull;
+  h->gen = 0;
+  h->thcur = h->th_used = 0;
+  h->theta = h->theta_pp[0] ? h->theta_pp[0] : h->theta;
+  if (pull && !h->tmap_ok) GBX_TRY(h->ops->pull_setup(h));
+  return GBX_OK;
 }
 
 // freeenergy(): sum_i log Z_i, then two passes over the undirected edges (sums, then squared deviations).
@@ -201,6 +217,15 @@ int em_loop(gbx_sbm* h, int itrmax, int check_every, double thr, bool mod, int* 
     if (done_at != 0) {
       const int extra = itr0 + itr - done_at;   // queued iterations that found the flag set and did nothing
       if (extra & 1) h->cur ^= 1;               // ... but the host flipped the message buffers for each of them
+      if (h->pull) {
+        h->gen -= extra;
+        const bool dc = !mod && h->opt.degreecorrection;
+        if (dc && extra > 0) {                  // ... and the theta generations (update_theta ran once per iteration)
+          if (extra & 1) h->thcur ^= 1;
+          h->th_used = h->thcur ^ 1;
+          h->theta = h->theta_pp[h->thcur];
+        }
+      }
       h->itr = done_at;
       *cnv = 1;
       *itrnum = done_at - itr0;
@@ -422,6 +447,16 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
     GBX_TRY(dev_alloc(h, &h->msg[1], (size_t)K * h->qm));
     GBX_TRY(dev_alloc(h, &h->PSI, (size_t)n * q));
     GBX_TRY(dev_alloc(h, &h->theta, (size_t)h->n_global + MAXPEER));
+    h->theta_pp[0] = h->theta;
+    if (ops->pull_ok && world == 1) {  // pull sweeps: per-vertex records (two generations), a second theta generation,
+                                       // the degree of every slot's neighbour
+      GBX_TRY(dev_alloc(h, &h->theta_pp[1], (size_t)h->n_global + MAXPEER));
+      GBX_TRY(dev_alloc(h, &h->rec[0], (size_t)h->n_global * h->qm));
+      GBX_TRY(dev_alloc(h, &h->rec[1], (size_t)h->n_global * h->qm));
+      GBX_TRY(dev_alloc(h, &h->coldeg, (size_t)K));
+      GBX_CUDA_TRY(cudaMemsetAsync(h->rec[0], 0, (size_t)h->n_global * h->qm * sizeof(double), h->stream));
+      GBX_CUDA_TRY(cudaMemsetAsync(h->rec[1], 0, (size_t)h->n_global * h->qm * sizeof(double), h->stream));
+    }
     GBX_TRY(dev_alloc(h, &h->totals, (size_t)TOT_MAX));
     GBX_TRY(dev_alloc(h, &h->maxd_dev, 1));
     if (model == 1) {  // degree of every vertex by global id: the field of mod.jl's sweep and free energy
@@ -433,7 +468,7 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
     h->msgp[0][h->rank] = h->msg[0];
     h->msgp[1][h->rank] = h->msg[1];
     GBX_TRY(dev_alloc(h, &h->pidx, (size_t)n));
-    GBX_TRY(dev_alloc(h, &h->prior_tab, (size_t)(1 + (TILE_E + 1) * q) * (q + 3)));
+    GBX_TRY(dev_alloc(h, &h->prior_tab, (size_t)(1 + (TILE_E + 1) * q) * (q + 4)));
     GBX_CUDA_TRY(cudaMemset(h->pidx, 0, (size_t)n * sizeof(int)));
     GBX_TRY(dev_alloc(h, &h->st, 1));
     GBX_TRY(dev_alloc(h, &h->params, 1));
@@ -448,11 +483,13 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
     occ = std::max(occ, 1);
     occm = std::max(occm, 1);
     h->grid_vertex = std::max(1, std::min(h->ntiles, h->num_sms * occ));
+    if (const char* e = getenv("GBX_PULL_OCC")) occm = std::max(1, std::min(occm, atoi(e)));   // CTAs per SM (tuning)
+    h->grid_pull = std::max(1, std::min(h->ntiles, h->num_sms * std::max(occm, 1)));
     const int64_t eblocks = std::max<int64_t>(1, (K / 2 + NT - 1) / NT);
     h->grid_mstep = h->grid_vertex + h->nhubs;  // M-step statistics: one row per sweep CTA
     h->grid_fe = (int)std::min<int64_t>(eblocks, (int64_t)h->num_sms * 2);
     h->grid_theta = (int)std::min<int64_t>(std::max<int64_t>(1, (n + NT - 1) / NT), (int64_t)h->num_sms * 4);
-    h->grid_mstep = h->grid_vertex * h->nchunks + h->nhubs;  // one row per sweep CTA of every piece
+    h->grid_mstep = std::max(h->grid_vertex * h->nchunks, h->grid_pull) + h->nhubs;  // one row per sweep CTA of every piece
     GBX_TRY(dev_alloc(h, &h->part_vertex, (size_t)h->grid_mstep * PSTRIDE));
     GBX_TRY(dev_alloc(h, &h->part_mstep, (size_t)h->grid_mstep * q * q));
     GBX_TRY(dev_alloc(h, &h->part_theta, (size_t)h->grid_theta * MAXQ));
@@ -520,7 +557,11 @@ int gbx_sbm_destroy(gbx_sbm* h) {
   dev_free(h->device, h->msg[0]);
   dev_free(h->device, h->msg[1]);
   dev_free(h->device, h->PSI);
-  if (h->theta_owned) dev_free(h->device, h->theta);
+  if (h->theta_owned) dev_free(h->device, h->theta_pp[0] ? h->theta_pp[0] : h->theta);
+  dev_free(h->device, h->theta_pp[1]);
+  dev_free(h->device, h->rec[0]);
+  dev_free(h->device, h->rec[1]);
+  dev_free(h->device, h->coldeg);
   if (h->totals_owned) dev_free(h->device, h->totals);
   dev_free(h->device, h->maxd_dev);
   dev_free(h->device, h->deg_global);
@@ -569,6 +610,7 @@ int gbx_sbm_init(gbx_sbm* h, const double* gr_init, const double* Crs_init, cons
       if (std::isnan(c) || std::isinf(c)) h->fail = 1;
       else if (c < 1e-6) c = 1e-6;
       s.C[r * q + t] = c;
+      s.Cused[r * q + t] = c;
     }
   for (int r = 0; r < q; ++r) s.gr[r] = h->opt.priorlearning ? gr_init[r] : 1.0 / q;  // sbm.jl:304-306
   GBX_CUDA_TRY(cudaMemcpyAsync(h->st, &s, sizeof s, cudaMemcpyHostToDevice, h->stream));
@@ -576,10 +618,12 @@ int gbx_sbm_init(gbx_sbm* h, const double* gr_init, const double* Crs_init, cons
   h->cur = 0;
   h->itr = 0;
   h->theta_valid = false;
+  GBX_TRY(choose_layout(h, h->opt.damping));
   GBX_TRY(h->ops->init_model(h));  // theta = 1: row 0 of the prior table
   GBX_TRY(load_messages(h, psicav, seed));
   {
     GBX_TRY(fill_async(h, h->theta, h->n_global, 1.0));  // theta = ones(Ntot,1), sbm.jl:277
+    if (h->theta_pp[1]) GBX_TRY(fill_async(h, h->theta_pp[1], h->n_global, 1.0));
     GBX_TRY(fill_async(h, h->escale, h->K, 1.0));
   }
   if (!h->fail && !h->stepped) {
@@ -614,8 +658,13 @@ int gbx_sbm_bp_sweeps(gbx_sbm* h, int n_sweeps) {
   GBX_TRY(set_device(h));
   GBX_TRY(h->ops->prepare(h, 0, 0));
   for (int i = 0; i < n_sweeps; ++i) {
+    if (h->pull && i > 0) GBX_TRY(h->ops->prepare(h, 0, 0));   // refresh "the parameters of the previous sweep"
     GBX_TRY(h->ops->vertex_pass(h, MODE_SWEEP));
     h->cur ^= 1;
+    if (h->pull) {  // no M-step follows that would note what this sweep ran with (sbm_apply_totals / mod_apply_totals)
+      GBX_CUDA_TRY(cudaMemcpyAsync(h->st->Cused, h->st->C, sizeof(h->st->C), cudaMemcpyDeviceToDevice, h->stream));
+      GBX_CUDA_TRY(cudaMemcpyAsync(&h->st->eb1_used, &h->st->eb1_cur, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
   }
   return GBX_OK;
 }
@@ -681,17 +730,17 @@ int gbx_sbm_get_messages(gbx_sbm* h, double* psicav) {
   GBX_TRY(set_device(h));
   // link order, K_global rows; on a partitioned run the rows of links owned by other ranks come back as zeros
   const size_t bytes = (size_t)h->K_global * h->q * sizeof(double);
-  double* tmp = h->msg[h->cur ^ 1];  // the other buffer is scratch between sweeps (single rank)
+  double* tmp = h->msg[h->cur ^ 1];  // the other buffer is scratch between sweeps (single rank, push layout)
   bool own = false;
-  if (h->world > 1) {
-    GBX_CUDA_TRY(cudaMalloc((void**)&tmp, bytes ? bytes : 1));
+  if (h->world > 1 || h->pull) {
+    GBX_CUDA_TRY(dev_malloc(h->device, (void**)&tmp, bytes ? bytes : 1, h->world == 1));
     own = true;
   }
-  int rc = h->ops->permute(h, h->msg[h->cur], tmp, 0);
+  int rc = h->pull ? h->ops->pull_export(h, tmp) : h->ops->permute(h, h->msg[h->cur], tmp, 0);
   cudaError_t e = cudaSuccess;
   if (rc == GBX_OK) e = cudaMemcpyAsync(psicav, tmp, bytes, cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  if (own) cudaFree(tmp);
+  if (own) dev_free(h->device, tmp);
   if (rc != GBX_OK) return rc;
   GBX_CUDA_TRY(e);
   return GBX_OK;
@@ -718,6 +767,8 @@ int64_t gbx_sbm_launch_count(const gbx_sbm* h) { return h ? h->launches : 0; }
 int64_t gbx_sbm_num_links(const gbx_sbm* h) { return h ? h->K : 0; }
 int64_t gbx_sbm_device_bytes(const gbx_sbm* h) { return h ? h->dev_bytes : 0; }
 
+int gbx_sbm_sweep_kind(const gbx_sbm* h) { return h ? h->pull : 0; }
+
 double gbx_sbm_sweep_bytes(const gbx_sbm* h) {
   if (!h) return 0.0;
   const double q = h->q, K = (double)h->K, n = (double)h->n;
@@ -726,6 +777,14 @@ double gbx_sbm_sweep_bytes(const gbx_sbm* h) {
   // row pointer and the row of the prior table
   const bool dc = h->model == 1 ? false : h->opt.degreecorrection != 0;
   const double damping = h->model == 1 ? h->mopt.damping : h->opt.damping;
+  if (h->pull) {
+    // pull sweep: per directed edge its own message read and rewritten in place, the neighbour's id and (degree
+    // correction) degree; per vertex the marginal read and written, its record written once and fetched from HBM once
+    // (the other deg - 1 gathers of it are L2 hits), row pointer, prior-table row, two theta generations
+    const double pe = 2.0 * q * 8.0 + 4.0 + (dc ? 4.0 : 0.0);
+    const double pv = 2.0 * q * 8.0 + 2.0 * q * 8.0 + 4.0 + 4.0 + (dc ? 16.0 : 0.0);
+    return K * pe + n * pv;
+  }
   double per_edge = 2.0 * q * 8.0 + 4.0;
   if (dc) per_edge += 8.0;
   if (damping != 1.0) per_edge += q * 8.0;             // old outgoing message
@@ -787,6 +846,7 @@ int gbx_mod_init(gbx_mod* h, const double* gr, const double* psicav, uint64_t se
   h->cur = 0;
   h->itr = 0;
   h->fail = 0;
+  GBX_TRY(choose_layout(h, h->mopt.damping));
   GBX_TRY(h->ops->init_model(h));  // prior-table row per vertex: by degree when degree corrected
   GBX_TRY(load_messages(h, psicav, seed));
   if (!h->stepped) {
@@ -956,6 +1016,7 @@ int gbx_sbm_part_set_buffers(gbx_sbm* h, void* totals_dev, void* theta_dev) {
   }
   if (theta_dev) {
     if (h->theta_owned) dev_free(h->device, h->theta);
+    h->theta_pp[0] = nullptr;
     h->theta = (double*)theta_dev;
     h->theta_owned = false;
   }

@@ -18,6 +18,11 @@ struct SbmParams {
   double logN;
   double eb1;                // e^beta - 1 (mod.jl)
   double oin, oout;          // omega_in, omega_out (mod.jl)
+  // pull sweeps (gbx_sbm_pull.cuh) rebuild the message a neighbour emitted in the PREVIOUS sweep: the parameters that
+  // sweep ran with, and the reciprocal block degree means that turn a neighbour's (degree, MAP block) into its theta
+  double Cprev[MAXQ * MAXQ];
+  double eb1_prev;
+  double invdr[MAXQ];
   int safe_deg;              // largest degree whose plain product of edge factors cannot leave the double range
   int pad_;
 };
@@ -30,6 +35,9 @@ struct SbmState {
   double sumPSI[MAXQ];   // sum_i PSI_i of the marginals currently in PSI
   double Stheta[MAXQ];   // sum_i theta_i PSI_i
   double drmean[MAXQ];   // mean degree of each MAP block (update_theta, sbm.jl:47-58)
+  double invdr[MAXQ];    // 1 / drmean: theta_i = degree_i * invdr[MAP block of i] wherever a theta is formed
+  double Cused[MAXQ * MAXQ];  // Crs the last sweep ran with (pull sweeps rebuild that sweep's messages)
+  double eb1_cur, eb1_used;   // e^beta - 1 of the current parameters / of the last sweep (mod.jl)
   double conv, maxd, sumlogZi;
   double cvsum[4], cvmean[4], cvss[4];
   double result[12];
@@ -117,7 +125,7 @@ struct gbx_sbm {
   gbx::SbmState* st = nullptr;
   gbx::SbmParams* params = nullptr;
   double *part_vertex = nullptr, *part_mstep = nullptr, *part_theta = nullptr, *part_fe = nullptr;
-  int grid_vertex = 0, grid_mstep = 0, grid_theta = 0, grid_fe = 0;
+  int grid_vertex = 0, grid_mstep = 0, grid_theta = 0, grid_fe = 0, grid_pull = 0;
   gbx::SbmState* h_state = nullptr;  // pinned mirror
   int cur_it = 0;                    // iteration the launchers stamp their kernels with (0: never skip)
   double cur_thr = -1.0;             // residual threshold sbm_apply_totals tests (< 0: never converged)
@@ -151,6 +159,16 @@ struct gbx_sbm {
   int sweep_rows = 0, sweep_row0 = 0;  // partial rows written by the last vertex pass (count, first row)
   int xparity = 0;                     // receive buffer the next sweep pushes into
   bool pending_unpack = false;         // the last sweep was packed and its rows have not been scattered yet
+  // ---- pull sweeps (gbx_sbm_pull.cuh): a vertex keeps its OUTGOING messages and rebuilds the incoming ones ------
+  int pull = 0;                        // this EM run sweeps with the pull kernels (chosen by gbx_*_init)
+  int gen = 0;                         // sweeps since init: the outgoing messages of generation g live in msg[g & 1];
+                                       // at g = 0 msg[1] holds the incoming messages (the layout of the push path)
+  double* rec[2] = {nullptr, nullptr}; // per-vertex records [n_global][qm] of generation g in rec[g & 1]
+  float* coldeg = nullptr;             // degree of col[e]
+  double* theta_pp[2] = {nullptr, nullptr};  // [n] theta of this rank's vertices, two generations
+  int thcur = 0, th_used = 0;          // theta_pp[thcur]: current; theta_pp[th_used]: what the last sweep ran with
+  alignas(64) unsigned char tmap[2][128] = {};  // CUtensorMap of msg[0] / msg[1] (rows of qm doubles, box of 32 rows)
+  bool tmap_ok = false;
 };
 
 namespace gbx {
@@ -175,6 +193,10 @@ struct SbmOps {
   int (*init_model)(gbx_sbm* h);  // per-vertex prior-table rows of the initial state
   int (*unpack)(gbx_sbm* h);      // packed exchange: received rows -> message buffer
   int (*release)(gbx_sbm* h);     // the handle is going away: give up the shared __constant__ parameter block
+  int pull_ok;                    // this q has pull kernels (message rows of 32, 64 or 128 bytes)
+  int (*pull_setup)(gbx_sbm* h);  // tensor maps, neighbour degrees
+  int (*pull_load)(gbx_sbm* h, const double* src_dev, uint64_t seed);   // initial messages into both layouts
+  int (*pull_export)(gbx_sbm* h, double* dst_dev);                      // current messages in `links` order
 };
 
 }  // namespace gbx

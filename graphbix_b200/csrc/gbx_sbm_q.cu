@@ -18,7 +18,9 @@
 #error "compile with -DGBX_Q=<number of groups>"
 #endif
 #include <algorithm>
+#include <cstring>
 #include <mutex>
+#include <string>
 
 #include "gbx_sbm_internal.h"
 
@@ -112,6 +114,7 @@ struct VertexArgs {
   int it;
   double damping;
   int dc;
+  int dc_model;   // == dc here (the pull kernel separates "degree correction on" from "thetas live")
 };
 
 // ---- small device helpers ---------------------------------------------------------------------
@@ -209,8 +212,8 @@ __device__ __forceinline__ void edge_transform(const double (&psi)[Q], double sc
 
 // Cavity message i -> j (sbm.jl:108-109) from the vertex product u and this edge's factor T, the absolute
 // clamp of normalize_logprob (sbm.jl:42) at 2^(ffrac + n) in the scaled domain, damping, scatter to rev slot.
-__device__ __forceinline__ void emit_message(const VertexArgs& a, const double* __restrict__ u, const double (&T)[Q],
-                                             double ffrac, int n, int rv, double (&w)[Q]) {
+__device__ __forceinline__ void emit_message_local(const double* __restrict__ u, const double (&T)[Q], double ffrac, int n,
+                                                   double (&w)[Q]) {
   double S = 0.0;
   bool low = false;
   const double thr = pow2c(n + 1);
@@ -232,6 +235,10 @@ __device__ __forceinline__ void emit_message(const VertexArgs& a, const double* 
   const double inv = fast_rcp(S);
 #pragma unroll
   for (int t = 0; t < Q; ++t) w[t] *= inv;
+}
+__device__ __forceinline__ void emit_message(const VertexArgs& a, const double* __restrict__ u, const double (&T)[Q],
+                                             double ffrac, int n, int rv, double (&w)[Q]) {
+  emit_message_local(u, T, ffrac, n, w);
   const int owner = rev_owner(rv), slot = rev_slot(rv);
   if (a.damping != 1.0) {
     double old[Q];
@@ -291,12 +298,21 @@ __device__ __forceinline__ void mstep_accumulate(MstepAcc& g, const double* arow
   else if (nrows > 0) mstep_accumulate_impl<false>(g, arow, bget, nrows);
 }
 
+// Barrier over the NT threads that carry vertex / edge work: the whole CTA in the push kernels, the consumer warps
+// (named barrier 1) in the pull kernel, whose producer warp has left by then.
+template <bool NAMED>
+__device__ __forceinline__ void cta_sync() {
+  if constexpr (NAMED) asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+  else __syncthreads();
+}
+
 // Fixed-order reduction of the per-warp q x q accumulators into this CTA's row of the M-step partials.
+template <bool NAMED = false>
 __device__ __forceinline__ void store_mstep_partials(const MstepAcc& g, double* scratch /* smem, >= 64 * MB * MB */,
                                                      double* mrow) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int w = 0; w < NT / 32; ++w) {
-    __syncthreads();
+    cta_sync<NAMED>();
     if (warp == w) {
 #pragma unroll
       for (int m = 0; m < MB; ++m)
@@ -310,7 +326,7 @@ __device__ __forceinline__ void store_mstep_partials(const MstepAcc& g, double* 
           }
     }
   }
-  __syncthreads();
+  cta_sync<NAMED>();
   for (int i = threadIdx.x; i < Q * Q; i += NT) mrow[i] = scratch[(i / Q) * (8 * MB) + (i % Q)];
 }
 
@@ -335,9 +351,10 @@ __device__ __forceinline__ unsigned group_bits(unsigned ballot) {
 //   x_t = log gr_t - theta h_t, xmax = max_t x_t, E = exp(x_t - xmax), 2^(fi + ffrac) = 1e-8 / e^xmax.
 // It depends on the vertex only through theta = degree / <degree of its MAP block>, so it is tabulated once per
 // EM iteration per (degree, block) by sbm_prior_table and read here as one coalesced row.
-constexpr int QT = Q + 3;
+constexpr int QT = Q + 4;
 struct Prior {
   double E, ffrac, xmax, fi;  // fi is an integer kept as a double so that loading it does not stall on a conversion
+  double ifrac;               // 2^-ffrac (pull sweeps fold the floor into the vertex's record)
 };
 
 __device__ __forceinline__ void prior_row(double th, double* row /* QT */) {
@@ -354,6 +371,7 @@ __device__ __forceinline__ void prior_row(double th, double* row /* QT */) {
   row[Q] = f - floor(f);
   row[Q + 1] = fi;
   row[Q + 2] = xmax;
+  row[Q + 3] = exp2(-row[Q]);
 }
 
 __global__ void sbm_prior_table(const SbmState* st, double* tab, int dc, int it) {
@@ -365,31 +383,32 @@ __global__ void sbm_prior_table(const SbmState* st, double* tab, int dc, int it)
   if (r > 0) {
     const int d = (r - 1) / Q, blk = (r - 1) % Q;
     if constexpr (MODEL == MODEL_MOD) th = (double)d;  // mod.jl:48: the field is alpha beta d_i h
-    else th = (double)d / st->drmean[blk];             // the expression of sbm_theta_kernel: bit-identical theta
+    else th = (double)d * st->invdr[blk];              // the expression of sbm_theta_kernel: bit-identical theta
   }
   double row[QT];
   prior_row(th, row);
   for (int k = 0; k < QT; ++k) tab[(size_t)r * QT + k] = row[k];
 }
 
-template <int MODE>
-__device__ __forceinline__ Prior load_prior(const VertexArgs& a, int r, int t) {
+template <int MODE, typename Args>
+__device__ __forceinline__ Prior load_prior(const Args& a, int r, int t) {
   Prior pr;
   const double* row = a.prior_tab + (size_t)r * QT;
   pr.E = (t < Q) ? row[t] : 0.0;
   pr.ffrac = row[Q];
   pr.fi = row[Q + 1];
   pr.xmax = (MODE == MODE_LOGZ) ? row[Q + 2] : 0.0;
+  pr.ifrac = row[Q + 3];
   return pr;
 }
 
 // Everything a vertex needs once lane t holds prod_t = product of its (scaled) edge factors and K = the exponent
 // taken out of it:  true unnormalised value v_t = u_t 2^K e^xmax,  u_t = E_t prod_t;  clamp floor 2^(fn + ffrac).
 // Runs on the QP lanes of a group (all lanes of the warp execute it; `valid` gates the side effects).
-template <int MODE>
-__device__ __forceinline__ void vertex_finish(const VertexArgs& a, bool valid, int gv, int deg, int t, const Prior& pr,
+template <int MODE, typename Args>
+__device__ __forceinline__ void vertex_finish(const Args& a, bool valid, int gv, int deg, int t, const Prior& pr,
                                               double old, double prod, int K, double& u_out, int& fn,
-                                              LaneAcc& acc, unsigned long long* s_dr, int* s_nr) {
+                                              LaneAcc& acc, unsigned long long* s_dr, int* s_nr, int* best_out = nullptr) {
   const bool tl = t < Q;
   const double u = tl ? pr.E * prod : 0.0;
   u_out = u;
@@ -413,6 +432,7 @@ __device__ __forceinline__ void vertex_finish(const VertexArgs& a, bool valid, i
     if constexpr (MODE == MODE_SWEEP) res = group_sum(tl ? fabs(p - old) : 0.0);
     const double pm = group_max(tl ? p : -1.0);
     const unsigned eq = group_bits(__ballot_sync(0xffffffffu, tl && (p == pm)));
+    if (best_out) *best_out = eq ? __ffs(eq) - 1 : 0;   // MAP block: findmax, first maximum (sbm.jl:49)
     if (valid) {
       if (tl) {
         a.PSI[(size_t)gv * Q + t] = p;
@@ -422,7 +442,7 @@ __device__ __forceinline__ void vertex_finish(const VertexArgs& a, bool valid, i
       if (t == 0) {
         acc.res += res;
         acc.vmax = fmax(acc.vmax, res);
-        if (MODEL == MODEL_SBM && a.dc && eq) {  // update_theta statistics: findmax, first maximum (sbm.jl:49)
+        if (MODEL == MODEL_SBM && a.dc_model && eq) {  // update_theta statistics: findmax, first maximum (sbm.jl:49)
           const int best = __ffs(eq) - 1;
           atomicAdd(&s_dr[best], (unsigned long long)deg);
           atomicAdd(&s_nr[best], 1);
@@ -433,36 +453,37 @@ __device__ __forceinline__ void vertex_finish(const VertexArgs& a, bool valid, i
 }
 
 // Deterministic CTA reduction of the lane accumulators into this CTA's partial row.
+template <bool NAMED = false>
 __device__ __forceinline__ void store_partials(const LaneAcc& acc, double* scratch /* smem, NT doubles */,
                                                double* prow, const unsigned long long* s_dr, const int* s_nr) {
   const int tid = threadIdx.x;
-  __syncthreads();
+  cta_sync<NAMED>();
   scratch[tid] = acc.psi;
-  __syncthreads();
+  cta_sync<NAMED>();
   if (tid < Q) {  // sumPSI[t]: lanes holding component t, in thread order
     double s = 0.0;
     for (int k = tid; k < NT; k += LV) s += scratch[k];
     prow[2 + tid] = s;
   }
-  __syncthreads();
+  cta_sync<NAMED>();
   scratch[tid] = acc.res;
-  __syncthreads();
+  cta_sync<NAMED>();
   if (tid == 0) {
     double s = 0.0;
     for (int k = 0; k < NT; k += LV) s += scratch[k];
     prow[0] = s;
   }
-  __syncthreads();
+  cta_sync<NAMED>();
   scratch[tid] = acc.logz;
-  __syncthreads();
+  cta_sync<NAMED>();
   if (tid == 0) {
     double s = 0.0;
     for (int k = 0; k < NT; k += LV) s += scratch[k];
     prow[1] = s;
   }
-  __syncthreads();
+  cta_sync<NAMED>();
   scratch[tid] = acc.vmax;
-  __syncthreads();
+  cta_sync<NAMED>();
   if (tid == 0) {
     double m = 0.0;
     for (int k = 0; k < NT; k += LV) m = fmax(m, scratch[k]);
@@ -473,17 +494,17 @@ __device__ __forceinline__ void store_partials(const LaneAcc& acc, double* scrat
     prow[2 + 2 * Q + tid] = (double)s_nr[tid];
   }
   if constexpr (MODEL == MODEL_MOD) {
-    __syncthreads();
+    cta_sync<NAMED>();
     scratch[tid] = acc.dpsi;
-    __syncthreads();
+    cta_sync<NAMED>();
     if (tid < Q) {
       double s = 0.0;
       for (int k = tid; k < NT; k += LV) s += scratch[k];
       prow[3 + 3 * Q + tid] = s;
     }
-    __syncthreads();
+    cta_sync<NAMED>();
     scratch[tid] = acc.mod;
-    __syncthreads();
+    cta_sync<NAMED>();
     if (tid == 0) {
       double s = 0.0;
       for (int k = 0; k < NT; ++k) s += scratch[k];
@@ -956,6 +977,7 @@ __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base
     pr.ffrac = row[Q];
     pr.fi = row[Q + 1];
     pr.xmax = row[Q + 2];
+    pr.ifrac = row[Q + 3];
     double u;
     int fn;
     vertex_finish<MODE>(a, writer, gv, e1 - e0, t, pr, old, prod, Ks + kcc, u, fn, acc, s_dr, s_nr);
@@ -1112,6 +1134,7 @@ __global__ void sbm_apply_totals(SbmState* st, const double* __restrict__ tot, c
     g[tid] = gnew;
     st->sumPSI[tid] = snew;
     st->drmean[tid] = tot[2 + Q + tid] / tot[2 + 2 * Q + tid];  // sbm.jl:54-58 (NaN for an empty block, unused)
+    st->invdr[tid] = 1.0 / st->drmean[tid];
   }
   if (tid == 0 && mode == MODE_SWEEP) {
     st->conv = tot[0] / N;  // sbm.jl:123
@@ -1125,6 +1148,7 @@ __global__ void sbm_apply_totals(SbmState* st, const double* __restrict__ tot, c
     const int s = tid / Q, t = tid - s * Q;
     const double* G = tot + TOT_G;
     const double Cold = st->C[tid];
+    st->Cused[tid] = Cold;                                         // what the sweep just ran with (pull sweeps)
     const double Cn = Cold * 0.5 * (G[s * Q + t] + G[t * Q + s]);  // Crsnew is symmetric (both directions of a link)
     double c = lr * Cn / (N * (g[s] * g[t])) + (1.0 - lr) * Cold;  // sbm.jl:137; (g g) first: bitwise symmetric in s, t
     if (c > maxCrs) c = maxCrs; else if (c < 0.0) c = 0.0;          // sbm.jl:138-146
@@ -1155,7 +1179,7 @@ __global__ void __launch_bounds__(NT) sbm_theta_kernel(const SbmState* st, const
         bv = p[t];
         best = t;
       }
-    const double th = (double)(rowptr[i + 1] - rowptr[i]) / st->drmean[best];
+    const double th = (double)(rowptr[i + 1] - rowptr[i]) * st->invdr[best];   // degrees[i] / drmean[block[i]], sbm.jl:61
     theta[i] = th;
     const int deg = rowptr[i + 1] - rowptr[i];
     pidx[i] = (deg <= TILE_E) ? 1 + deg * Q + best : 0;  // row of the prior table (hubs evaluate the prior in place)
@@ -1215,7 +1239,9 @@ __global__ void sbm_prepare(SbmState* st, SbmParams* out, double N, int zero_h, 
   for (int k = tid; k < Q * Q; k += blockDim.x) {
     out->C[k] = st->C[k];
     out->logC[k] = log(st->C[k]);
+    out->Cprev[k] = st->Cused[k];
   }
+  if (tid < Q) out->invdr[tid] = st->invdr[tid];
   if (tid == 0) {
     // Largest degree for which a plain product of edge factors provably stays inside the double range:
     // factor in [thmin^2 Cmin, thmax^2 Cmax] with theta = degree / <degree of the block> in [1/dmax, maxdeg/dmin].
@@ -1254,6 +1280,50 @@ struct PeerCur {
   const double* p[MAXPEER];
 };
 
+// Per undirected edge (a = psi_{i->j}, b = psi_{j->i}, lc = log theta_i + log theta_j - log N): log Z_ij and the three
+// Gibbs / MAP terms of freeenergy(), sbm.jl:162-200.
+__device__ __forceinline__ void fe_terms_sbm(const double (&a)[Q], const double (&b)[Q], double lc, double* x) {
+  double Z0 = 0.0, W = 0.0, L1 = 0.0, G1 = 0.0;
+  int sa = 0, sb = 0;
+  double ma = -1.0, mb = -1.0;
+#pragma unroll
+  for (int s = 0; s < Q; ++s) {
+    if (a[s] > ma) { ma = a[s]; sa = s; }
+    if (b[s] > mb) { mb = b[s]; sb = s; }
+#pragma unroll
+    for (int t = 0; t < Q; ++t) {
+      const double w = a[s] * b[t];
+      const double wc = w * c_P.C[s * Q + t];
+      W += w;
+      Z0 += wc;
+      L1 += w * c_P.logC[s * Q + t];
+      G1 += wc * c_P.logC[s * Q + t];
+    }
+  }
+  x[0] = log(Z0) + lc;                // logZijs, sbm.jl:176
+  x[1] = W * lc + L1;                 // CVGPs,   sbm.jl:178-184
+  x[2] = (Z0 * lc + G1) / Z0;         // CVGTs,   sbm.jl:186-192
+  x[3] = lc + c_P.logC[sa * Q + sb];  // CVMAPs,  sbm.jl:194-198
+}
+
+// freeenergy(), mod.jl:127-153, per undirected edge: x0 = logZij, x1 = CVBP, x2 = CVGP, x3 = CVGT, x4 = CVMAP.
+__device__ __forceinline__ void fe_terms_mod(const double (&a)[Q], const double (&b)[Q], double di, double dj, double oin,
+                                             double oout, double beta, double loin, double loout, double* x) {
+  double s = 0.0;
+  int sa = 0, sb = 0;
+#pragma unroll
+  for (int t = 0; t < Q; ++t) {
+    s = fma(a[t], b[t], s);
+    if (a[t] > a[sa]) sa = t;
+    if (b[t] > b[sb]) sb = t;
+  }
+  x[0] = log(1.0 + c_P.eb1 * s);
+  x[1] = x[0] + log(di) + loout + log(dj);
+  x[2] = beta * s;
+  x[3] = di * dj * (oout * loout + (oin * loin - oout * loout) * s) / exp(x[1]);
+  x[4] = (sa == sb) ? loin : loout;
+}
+
 template <int PASS>
 __global__ void __launch_bounds__(NT) sbm_fe_kernel(const SbmState* st, const int* __restrict__ rev,
                                                     const int* __restrict__ col, const int* __restrict__ erow,
@@ -1274,28 +1344,8 @@ __global__ void __launch_bounds__(NT) sbm_fe_kernel(const SbmState* st, const in
       load_msg<Q, QM>(peers.p[rev_owner(r)], rev_slot(r), a);   // i -> j   (in the row of j, possibly on a peer)
       double lc = -c_P.logN;
       if (dc) lc += log(theta[erow[e]]) + log(theta[col[e]]);
-      double Z0 = 0.0, W = 0.0, L1 = 0.0, G1 = 0.0;
-      int sa = 0, sb = 0;
-      double ma = -1.0, mb = -1.0;
-#pragma unroll
-      for (int s = 0; s < Q; ++s) {
-        if (a[s] > ma) { ma = a[s]; sa = s; }
-        if (b[s] > mb) { mb = b[s]; sb = s; }
-#pragma unroll
-        for (int t = 0; t < Q; ++t) {
-          const double w = a[s] * b[t];
-          const double wc = w * c_P.C[s * Q + t];
-          W += w;
-          Z0 += wc;
-          L1 += w * c_P.logC[s * Q + t];
-          G1 += wc * c_P.logC[s * Q + t];
-        }
-      }
       double x[4];
-      x[0] = log(Z0) + lc;                // logZijs, sbm.jl:176
-      x[1] = W * lc + L1;                 // CVGPs,   sbm.jl:178-184
-      x[2] = (Z0 * lc + G1) / Z0;         // CVGTs,   sbm.jl:186-192
-      x[3] = lc + c_P.logC[sa * Q + sb];  // CVMAPs,  sbm.jl:194-198
+      fe_terms_sbm(a, b, lc, x);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (PASS == 0) acc[k] += x[k];
@@ -1411,6 +1461,8 @@ __global__ void k_init_pidx(const int* __restrict__ rowptr, int n, int by_degree
   }
 }
 
+#include "gbx_sbm_pull.cuh"
+
 // =============================================================================================
 // Launchers (host)
 // =============================================================================================
@@ -1444,6 +1496,7 @@ VertexArgs vertex_args(gbx_sbm* h) {
   a.it = h->cur_it;
   a.damping = (MODEL == MODEL_MOD) ? h->mopt.damping : h->opt.damping;
   a.dc = (MODEL == MODEL_MOD) ? h->mopt.dc : h->opt.degreecorrection;
+  a.dc_model = a.dc;
   return a;
 }
 
@@ -1553,7 +1606,11 @@ int op_unpack(gbx_sbm* h) {
   return GBX_OK;
 }
 
+int pull_vertex_pass(gbx_sbm* h, int mode);
+int pull_fe_local(gbx_sbm* h, int pass);
+
 int op_vertex_pass(gbx_sbm* h, int mode) {
+  if (h->pull) return pull_vertex_pass(h, mode);
   if (mode == MODE_SWEEP) {
     const double damping = (MODEL == MODEL_MOD) ? h->mopt.damping : h->opt.damping;
     if (h->world > 1 && h->exchange == 1 && damping == 1.0) return launch_packed_sweep(h);
@@ -1602,6 +1659,10 @@ int op_prepare(gbx_sbm* h, int zero_h, int gr_from_sum) {
 }
 
 int op_theta_local(gbx_sbm* h) {
+  if (h->pull) {  // keep the thetas the last sweep ran with: the next sweep rebuilds that sweep's messages
+    h->thcur ^= 1;
+    h->theta = h->theta_pp[h->thcur];
+  }
   sbm_theta_kernel<<<h->grid_theta, NT, 0, h->stream>>>(h->st, h->rowptr, (int)h->n, h->PSI, h->theta + h->vbeg, h->pidx,
                                                         h->part_theta, h->cur_it);
   h->theta_valid = true;
@@ -1619,6 +1680,7 @@ int op_theta_apply(gbx_sbm* h) {
 }
 
 int op_escale(gbx_sbm* h) {
+  if (h->pull) return GBX_OK;  // the pull sweep forms theta_i theta_j per edge from the records
   if (h->K > 0) {
     sbm_escale_kernel<<<grid_for(h, h->K), 256, 0, h->stream>>>(h->erow, h->col, (long long)h->K, h->theta, h->escale, h->st, h->cur_it);
     h->launches++;
@@ -1634,6 +1696,7 @@ PeerCur peer_cur(const gbx_sbm* h) {
 }
 
 int op_fe_local(gbx_sbm* h, int pass) {
+  if (h->pull) return pull_fe_local(h, pass);
   { const int rc = acquire_params(h, true); if (rc != GBX_OK) return rc; }
   if (pass == 0)
     sbm_fe_kernel<0><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->rev, h->col, h->erow, (long long)h->K, h->msg[h->cur],
@@ -1693,6 +1756,201 @@ int op_init_model(gbx_sbm* h) {
   return GBX_OK;
 }
 
+#define GBX_TRY_RC(expr)         \
+  do {                           \
+    const int _rc = (expr);      \
+    if (_rc != GBX_OK) return _rc; \
+  } while (0)
+
+// ---- pull launchers ---------------------------------------------------------------------------------------------------
+int pull_set_attributes() {
+  if constexpr (PULL_OK) {
+    const int sm = (int)PullSmem::total;
+    GBX_CUDA_TRY(cudaFuncSetAttribute(sbm_pull_kernel<MODE_SWEEP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    GBX_CUDA_TRY(cudaFuncSetAttribute(sbm_pull_kernel<MODE_SWEEP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    GBX_CUDA_TRY(cudaFuncSetAttribute(sbm_pull_kernel<MODE_MARGINAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    GBX_CUDA_TRY(cudaFuncSetAttribute(sbm_pull_kernel<MODE_MARGINAL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    GBX_CUDA_TRY(cudaFuncSetAttribute(sbm_pull_kernel<MODE_LOGZ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    GBX_CUDA_TRY(cudaFuncSetAttribute(sbm_pull_kernel<MODE_LOGZ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  }
+  return GBX_OK;
+}
+
+PullArgs pull_args(gbx_sbm* h, int mode) {
+  PullArgs a;
+  a.tiles = h->tiles;
+  a.ntiles = h->ntiles;
+  a.rowptr = h->rowptr;
+  a.col = h->col;
+  a.coldeg = h->coldeg;
+  a.pidx = h->pidx;
+  a.prior_tab = h->prior_tab;
+  a.theta_cur = h->theta_pp[h->thcur];
+  a.theta_prev = h->theta_pp[h->th_used];
+  a.PSI = h->PSI;
+  // Generation g = h->gen.  A sweep reads the outgoing messages of generation g - 1 and overwrites them with those of
+  // generation g + 1: buffer (g + 1) & 1; at g = 0 that buffer holds the incoming messages of generation 0 instead.
+  // A marginal / log Z pass reads the same buffer without writing.
+  a.msg = h->msg[(h->gen + 1) & 1];
+  a.rec_old = h->rec[h->gen & 1];
+  a.rec_new = h->rec[(h->gen + 1) & 1];
+  a.vbeg = h->vbeg;
+  a.partials = h->part_vertex;
+  a.mpart = h->part_mstep;
+  a.st = h->st;
+  a.it = h->cur_it;
+  a.dc_model = (MODEL == MODEL_MOD) ? h->mopt.dc : h->opt.degreecorrection;
+  a.dc = (MODEL == MODEL_MOD) ? a.dc_model : (a.dc_model && h->theta_valid);
+  a.hubs = h->hubs;
+  (void)mode;
+  return a;
+}
+
+template <int MODE, bool RECON>
+int launch_pull_t(gbx_sbm* h) {
+  if constexpr (PULL_OK) {
+    GBX_TRY_RC(acquire_params(h, true));
+    PullArgs a = pull_args(h, MODE);
+    const int G = h->grid_pull;
+    if (h->ntiles > 0) {
+      const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(h->tmap[(h->gen + 1) & 1]);
+      sbm_pull_kernel<MODE, RECON><<<G, P_NT, PullSmem::total, h->stream>>>(*tm, a);
+      h->launches++;
+    }
+    if (h->nhubs > 0) {
+      sbm_pull_hub_kernel<MODE, RECON><<<h->nhubs, NT, 0, h->stream>>>(a, G);
+      h->launches++;
+    }
+    h->sweep_rows = (h->ntiles > 0 ? G : 0) + h->nhubs;
+    h->sweep_row0 = h->ntiles > 0 ? 0 : G;
+    GBX_CUDA_TRY(cudaGetLastError());
+    if (MODE == MODE_SWEEP) {
+      h->gen++;
+      h->th_used = h->thcur;
+    }
+    return GBX_OK;
+  } else {
+    last_error() = "no pull kernels for this q";
+    return GBX_ERR_STATE;
+  }
+}
+
+int pull_vertex_pass(gbx_sbm* h, int mode) {
+  const bool recon = h->gen > 0;
+  if (mode == MODE_SWEEP) return recon ? launch_pull_t<MODE_SWEEP, true>(h) : launch_pull_t<MODE_SWEEP, false>(h);
+  if (mode == MODE_MARGINAL) return recon ? launch_pull_t<MODE_MARGINAL, true>(h) : launch_pull_t<MODE_MARGINAL, false>(h);
+  return recon ? launch_pull_t<MODE_LOGZ, true>(h) : launch_pull_t<MODE_LOGZ, false>(h);
+}
+
+int pull_fe_local(gbx_sbm* h, int pass) {
+  if constexpr (PULL_OK) {
+    GBX_TRY_RC(acquire_params(h, true));
+    PullFeArgs f;
+    f.col = h->col;
+    f.erow = h->erow;
+    f.coldeg = h->coldeg;
+    f.msg_out = h->msg[h->gen & 1];
+    f.msg_other = h->msg[(h->gen + 1) & 1];
+    f.rec = h->rec[h->gen & 1];
+    f.theta_cur = h->theta_pp[h->thcur];
+    f.theta_prev = h->theta_pp[h->th_used];
+    f.degs = h->deg_global;
+    f.vbeg = h->vbeg;
+    f.K = h->K;
+    f.dc_model = (MODEL == MODEL_MOD) ? h->mopt.dc : h->opt.degreecorrection;
+    f.dc = (MODEL == MODEL_MOD) ? f.dc_model : (f.dc_model && h->theta_valid);
+    const bool recon = h->gen > 0;
+    if (pass == 0) {
+      if (recon) pull_fe_kernel<0, true><<<h->grid_fe, NT, 0, h->stream>>>(h->st, f, h->part_fe);
+      else pull_fe_kernel<0, false><<<h->grid_fe, NT, 0, h->stream>>>(h->st, f, h->part_fe);
+    } else {
+      if (recon) pull_fe_kernel<1, true><<<h->grid_fe, NT, 0, h->stream>>>(h->st, f, h->part_fe);
+      else pull_fe_kernel<1, false><<<h->grid_fe, NT, 0, h->stream>>>(h->st, f, h->part_fe);
+    }
+    constexpr int NX = (MODEL == MODEL_MOD) ? 5 : 4;
+    k_local_columns<<<1, 32 * NX, 0, h->stream>>>(h->part_fe, h->grid_fe, NX, h->totals);
+    h->launches += 2;
+    GBX_CUDA_TRY(cudaGetLastError());
+    return GBX_OK;
+  } else {
+    (void)pass;
+    last_error() = "no pull kernels for this q";
+    return GBX_ERR_STATE;
+  }
+}
+
+// Tensor maps of the two message buffers (rows of QM doubles, boxes of 32 rows, hardware swizzle of the row size) and
+// the neighbour degrees.  The driver entry point is looked up at run time: the library links no libcuda.
+int op_pull_setup(gbx_sbm* h) {
+  if constexpr (PULL_OK) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      GBX_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+      if (!fn || qres != cudaDriverEntryPointSuccess) {
+        last_error() = "cuTensorMapEncodeTiled is not available in this driver";
+        return GBX_ERR_CUDA;
+      }
+      encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const cuuint64_t rows = (cuuint64_t)std::max<int64_t>(h->K, 1);
+    for (int b = 0; b < 2; ++b) {
+      const cuuint64_t gdim[2] = {(cuuint64_t)QM, rows};
+      const cuuint64_t gstr[1] = {(cuuint64_t)ROWB};
+      const cuuint32_t box[2] = {(cuuint32_t)QM, 32u};
+      const cuuint32_t estr[2] = {1u, 1u};
+      const CUtensorMapSwizzle sw = (ROWB == 32) ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                 : (ROWB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+      const CUresult r = encode(reinterpret_cast<CUtensorMap*>(h->tmap[b]), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, h->msg[b], gdim,
+                                gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        last_error() = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")";
+        return GBX_ERR_CUDA;
+      }
+    }
+    if (h->K > 0) {
+      k_coldeg<<<grid_for(h, h->K), 256, 0, h->stream>>>(h->col, h->rowptr, (long long)h->K, h->coldeg);
+      h->launches++;
+      GBX_CUDA_TRY(cudaGetLastError());
+    }
+    h->tmap_ok = true;
+    return GBX_OK;
+  } else {
+    return GBX_OK;
+  }
+}
+
+// Initial messages (K x q in `links` order on the device, or drawn from `seed`) into both layouts: msg[0] outgoing,
+// msg[1] incoming.
+int op_pull_load(gbx_sbm* h, const double* src_dev, uint64_t seed) {
+  if (h->K > 0) {
+    if (src_dev)
+      k_pull_permute<<<grid_for(h, h->K), 256, 0, h->stream>>>(src_dev, nullptr, h->msg[1], h->msg[0], h->slot_of_link, h->rev,
+                                                              (long long)h->K, 1);
+    else
+      k_pull_random_messages<<<grid_for(h, h->K), 256, 0, h->stream>>>(h->msg[1], h->msg[0], h->slot_of_link, h->rev,
+                                                                      (long long)h->K, seed);
+    h->launches++;
+    GBX_CUDA_TRY(cudaGetLastError());
+  }
+  return GBX_OK;
+}
+
+int op_pull_export(gbx_sbm* h, double* dst_dev) {
+  if (h->K > 0) {
+    k_pull_permute<<<grid_for(h, h->K), 256, 0, h->stream>>>(nullptr, dst_dev, nullptr, h->msg[h->gen & 1], h->slot_of_link,
+                                                            h->rev, (long long)h->K, 0);
+    h->launches++;
+    GBX_CUDA_TRY(cudaGetLastError());
+  }
+  return GBX_OK;
+}
+
 int op_occupancy(int variant, int* vertex_occ, int* mstep_occ) {
   (void)variant;
   {
@@ -1701,7 +1959,11 @@ int op_occupancy(int variant, int* vertex_occ, int* mstep_occ) {
     GBX_CUDA_TRY(cudaFuncSetAttribute(sbm_vertex_kernel<MODE_LOGZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepSmem::total));
     GBX_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(vertex_occ, sbm_vertex_kernel<MODE_SWEEP>, NT, SweepSmem::total));
   }
-  *mstep_occ = 1;
+  *mstep_occ = 0;
+  if constexpr (PULL_OK) {
+    GBX_TRY_RC(pull_set_attributes());
+    GBX_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(mstep_occ, sbm_pull_kernel<MODE_SWEEP, true>, P_NT, PullSmem::total));
+  }
   return GBX_OK;
 }
 
@@ -1737,6 +1999,7 @@ __global__ void mod_apply_totals(SbmState* st, const double* __restrict__ tot, c
     if (it != 0 && st->done_at == 0 && st->conv < thr) st->done_at = it;   // mod.jl:230-234, acted on from it + 1
     st->maxd = *maxd;
     if (!(tot[0] == tot[0]) || !(tot[0] < INFINITY)) st->status |= 1;
+    st->eb1_used = st->eb1_cur;                                     // what the sweep just ran with (pull sweeps)
     if (learning) {
       // The statistic sum_e omega_in s_e / ((omega_in - omega_out) s_e + omega_out) (mod.jl:86-87) was accumulated by
       // the sweep over ALL directed slots (new outgoing message . previous incoming one): twice per undirected edge.
@@ -1772,6 +2035,9 @@ __global__ void mod_prepare(SbmState* st, SbmParams* out, double N, int zero_h, 
     out->logN = log(N);
     const double eb1 = exp(st->beta) - 1.0;             // written as in mod.jl:42
     out->eb1 = eb1;
+    st->eb1_cur = eb1;
+    if (zero_h) st->eb1_used = eb1;                     // init: no sweep has run yet
+    out->eb1_prev = st->eb1_used;
     out->oin = st->omegain;
     out->oout = st->omegaout;
     double hn2 = 0.0;
@@ -1811,20 +2077,8 @@ __global__ void __launch_bounds__(NT) mod_fe_kernel(const SbmState* st, const in
       di = degs[erow[er.x]];
       dj = degs[col[er.x]];
     }
-    double s = 0.0;
-    int sa = 0, sb = 0;
-#pragma unroll
-    for (int t = 0; t < Q; ++t) {
-      s = fma(a[t], b[t], s);
-      if (a[t] > a[sa]) sa = t;
-      if (b[t] > b[sb]) sb = t;
-    }
     double x[5];
-    x[0] = log(1.0 + c_P.eb1 * s);
-    x[1] = x[0] + log(di) + loout + log(dj);
-    x[2] = beta * s;
-    x[3] = di * dj * (oout * loout + (oin * loin - oout * loout) * s) / exp(x[1]);
-    x[4] = (sa == sb) ? loin : loout;
+    fe_terms_mod(a, b, di, dj, oin, oout, beta, loin, loout, x);
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
       if (PASS == 0) acc[k] += x[k];
@@ -1894,6 +2148,7 @@ PeerCur peer_cur(const gbx_sbm* h) {
 }
 
 int mop_fe_local(gbx_sbm* h, int pass) {
+  if (h->pull) return pull_fe_local(h, pass);
   { const int rc = acquire_params(h, true); if (rc != GBX_OK) return rc; }
   if (pass == 0)
     mod_fe_kernel<0><<<h->grid_fe, NT, 0, h->stream>>>(h->st, h->rev, h->col, h->erow, h->deg_global, (long long)h->K,
@@ -1925,11 +2180,13 @@ int mop_fe_final(gbx_sbm* h) {
 
 const SbmOps kOps = {Q,          op_vertex_pass, op_local_totals, mop_apply_totals,   mop_prepare,   mop_noop,     mop_noop,
                      mop_noop,   mop_fe_local,   mop_fe_apply,    mop_fe_final,       op_permute,    op_random_messages,
-                     op_assignment, op_occupancy, op_init_model, op_unpack, op_release};
+                     op_assignment, op_occupancy, op_init_model, op_unpack, op_release,
+                     PULL_OK ? 1 : 0, op_pull_setup, op_pull_load, op_pull_export};
 #else
 const SbmOps kOps = {Q,          op_vertex_pass, op_local_totals, op_apply_totals,    op_prepare,    op_theta_local, op_theta_apply,
                      op_escale,  op_fe_local,    op_fe_apply,     op_fe_final,        op_permute,    op_random_messages,
-                     op_assignment, op_occupancy, op_init_model, op_unpack, op_release};
+                     op_assignment, op_occupancy, op_init_model, op_unpack, op_release,
+                     PULL_OK ? 1 : 0, op_pull_setup, op_pull_load, op_pull_export};
 #endif
 
 }  // namespace

@@ -145,6 +145,11 @@ class SbmEngine:
     def sweep_bytes(self):
         return float(self.lib.gbx_sbm_sweep_bytes(self._h))
 
+    @property
+    def sweep_kind(self):
+        """'pull' or 'push': which sweep kernels the current EM run uses (decided by init)."""
+        return "pull" if self.lib.gbx_sbm_sweep_kind(self._h) else "push"
+
 
 def initial_parameters(initial: str, B: int, rng: np.random.Generator):
     """Hyper-parameter initial conditions of sbm.jl:283-302 (the spectral one lives in graphbix_b200.spectral)."""

@@ -115,6 +115,11 @@ int64_t gbx_sbm_num_links(const gbx_sbm* h);
 int64_t gbx_sbm_device_bytes(const gbx_sbm* h);
 /* Algorithmic HBM bytes one BP sweep moves (DESIGN.md "bytes per unit"). */
 double gbx_sbm_sweep_bytes(const gbx_sbm* h);
+/* Which sweep kernels the current EM run uses (decided by gbx_*_init): 0 = push (new messages scattered into the
+ * receiver's rows), 1 = pull (a vertex keeps its outgoing messages and rebuilds the incoming ones from per-vertex
+ * records; the default whenever a message row is 32, 64 or 128 bytes, damping == 1 and the handle is not partitioned;
+ * GBX_PULL=0 in the environment forces push).  Results agree to rounding; DESIGN.md "Sweep kernels". */
+int gbx_sbm_sweep_kind(const gbx_sbm* h);
 
 /* ------------------------------------------------------------------------------------------------
  * mod.jl: SBM restricted to community structure (omega_in / omega_out).
