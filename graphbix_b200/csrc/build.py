@@ -20,7 +20,7 @@ OUT = os.path.join(PKG, "libgraphbix_cuda.so")
 OBJ = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"] + ARCH
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"] + ARCH + os.environ.get("GBX_EXTRA_FLAGS", "").split()
 ALL_Q = list(range(1, 17))
 
 

@@ -70,6 +70,17 @@ __global__ void k_rev(const int* __restrict__ rowptr, const int* __restrict__ co
   }
 }
 
+// Pull layout (gbx_sbm_pull.cuh): local slot e (row i, column j) keeps the OUTGOING message i -> j and, before the first
+// sweep, the incoming one j -> i.  in_link[e] / out_link[e] = index in `links` of (j -> i) / (i -> j); link_of_slot is the
+// sorted value array of the build (global slot -> link).
+__global__ void k_link_maps(const int* __restrict__ link_of_slot, const int* __restrict__ grev, long long sbeg, long long Kl,
+                            int* __restrict__ in_link, int* __restrict__ out_link) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < Kl; e += (long long)gridDim.x * blockDim.x) {
+    in_link[e] = link_of_slot[sbeg + e];
+    out_link[e] = link_of_slot[grev[sbeg + e]];
+  }
+}
+
 struct PartBases {
   long long sbeg[MAXPEER + 1];
 };
@@ -169,10 +180,6 @@ int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* 
   GBX_C(cudaMemcpyAsync(rowptr_global->data(), g_rowptr, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
   GBX_C(cudaStreamSynchronize(st));
   GBX_C(cudaGetLastError());
-  // the sort workspace is the peak of the build: give it back before the per-rank arrays are allocated
-  dev_free(dv, d_links); dev_free(dv, keys); dev_free(dv, keys2); dev_free(dv, vals); dev_free(dv, vals2);
-  dev_free(dv, deg); dev_free(dv, tmp);
-  d_links = nullptr; keys = keys2 = nullptr; vals = vals2 = deg = nullptr; tmp = nullptr;
   if (herr & ERR_RANGE) { last_error() = "links: vertex id out of 1..n"; return fail(GBX_ERR_INVALID); }
   if (herr & ERR_SELF) { last_error() = "links: self loop (run simplegraph first)"; return fail(GBX_ERR_INVALID); }
   if (herr & ERR_DUP) { last_error() = "links: duplicate link (run simplegraph first)"; return fail(GBX_ERR_INVALID); }
@@ -198,6 +205,17 @@ int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* 
       last_error() = "too many edge slots on one rank (limit 2^29)";
       return fail(GBX_ERR_INVALID);
     }
+  if (h->ops && h->ops->pull_ok) {  // link <-> slot maps of the pull layout, while the sorted values are still around
+    GBX_C(dev_malloc(dv, (void**)&h->in_link, (size_t)std::max<long long>(h->K, 1) * sizeof(int), pooled));
+    GBX_C(dev_malloc(dv, (void**)&h->out_link, (size_t)std::max<long long>(h->K, 1) * sizeof(int), pooled));
+    h->dev_bytes += 2 * (int64_t)h->K * sizeof(int);
+    if (h->K > 0) k_link_maps<<<grid, 256, 0, st>>>(vals2, g_rev, h->sbeg, h->K, h->in_link, h->out_link);
+    GBX_C(cudaStreamSynchronize(st));
+  }
+  // the sort workspace is the peak of the build: give it back before the per-rank arrays are allocated
+  dev_free(dv, d_links); dev_free(dv, keys); dev_free(dv, keys2); dev_free(dv, vals); dev_free(dv, vals2);
+  dev_free(dv, deg); dev_free(dv, tmp);
+  d_links = nullptr; keys = keys2 = nullptr; vals = vals2 = deg = nullptr; tmp = nullptr;
   auto keep = [&](void** p, size_t bytes) -> cudaError_t {
     h->dev_bytes += (int64_t)bytes;
     return dev_malloc(dv, p, bytes + 64, pooled);   // slack: the pull kernel's bulk copies round their windows outwards

@@ -118,16 +118,21 @@ int load_messages(gbx_sbm* h, const double* psicav, uint64_t seed) {
   return rc;
 }
 
-// Which sweep kernels this EM run uses (decided at init, when the options are known).  Pull: message rows of 32 / 64 /
-// 128 bytes, no damping (a damped message cannot be rebuilt from the sender's record), one rank.  GBX_PULL=0 forces push.
+// Which sweep kernels this EM run uses (decided at init, when the options are known).
+//   push: new messages scattered into the receiver's rows (sbm_vertex_kernel); the faster sweep on one GPU today.
+//   pull: a vertex keeps its outgoing messages and rebuilds the incoming ones from per-vertex records
+//         (gbx_sbm_pull.cuh); needs message rows of 32 / 64 / 128 bytes and no damping (a damped message cannot be
+//         rebuilt from the sender's record).  What crosses NVLink in a partitioned run is then one record per vertex
+//         instead of one message per cut edge, so partitioned handles (world > 1) sweep with it by default.
+// GBX_PULL=1 / GBX_PULL=0 in the environment force one or the other where possible.
 int choose_layout(gbx_sbm* h, double damping) {
-  int pull = h->ops->pull_ok && damping == 1.0 && h->world == 1 && !h->stepped && h->rec[0] != nullptr &&
-             h->theta_pp[0] != nullptr && h->theta_pp[1] != nullptr;
+  int pull = h->ops->pull_ok && damping == 1.0 && h->rec[0] != nullptr && h->theta_pp[0] != nullptr;
+  for (int r = 0; r < h->world; ++r) pull = pull && h->recp[0][r] != nullptr && h->recp[1][r] != nullptr;   // peers mapped
   if (const char* e = getenv("GBX_PULL")) pull = pull && atoi(e) != 0;
+  else pull = pull && h->world > 1;
   h->pull = pull;
   h->gen = 0;
   h->thcur = h->th_used = 0;
-  h->theta = h->theta_pp[0] ? h->theta_pp[0] : h->theta;
   if (pull && !h->tmap_ok) GBX_TRY(h->ops->pull_setup(h));
   return GBX_OK;
 }
@@ -223,7 +228,6 @@ int em_loop(gbx_sbm* h, int itrmax, int check_every, double thr, bool mod, int* 
         if (dc && extra > 0) {                  // ... and the theta generations (update_theta ran once per iteration)
           if (extra & 1) h->thcur ^= 1;
           h->th_used = h->thcur ^ 1;
-          h->theta = h->theta_pp[h->thcur];
         }
       }
       h->itr = done_at;
@@ -411,7 +415,14 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
     // copies run slower through the switch than a few large ones (measured: 2 GPUs best with 8, 8 GPUs with 2)
     h->nchunks = std::max(2, std::min((int)MAXCHUNK, 16 / world));
     if (const char* e = getenv("GBX_EXCHANGE_PIECES")) h->nchunks = atoi(e);
-    const int rcp = build_exchange_plan(h, gg, tiles);
+    // Pull sweeps exchange per-vertex records, not messages: no send / receive runs are needed for them.  The packed
+    // message exchange of the push sweep is planned only where push is what will run (no pull kernels for this q, or
+    // GBX_PULL=0); a damped run on a pull-capable q falls back to direct peer stores (exchange mode 0).
+    const char* ep = getenv("GBX_PULL");
+    const bool want_push_plan = !ops->pull_ok || (ep && atoi(ep) == 0);   // (world > 1 here: pull is the default)
+    int rcp = GBX_OK;
+    if (want_push_plan) rcp = build_exchange_plan(h, gg, tiles);
+    else h->nchunks = 1;
     free_global(&gg);
     if (rcp != GBX_OK) {
       const std::string keep = last_error();
@@ -419,7 +430,7 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
       last_error() = keep;
       return rcp;
     }
-    h->exchange = 1;
+    h->exchange = want_push_plan ? 1 : 0;
   }
   for (int64_t v = 0; v < h->n_global; ++v) h->max_degree = std::max(h->max_degree, rowptr_g[(size_t)v + 1] - rowptr_g[(size_t)v]);
   h->model = model;
@@ -447,19 +458,31 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
     GBX_TRY(dev_alloc(h, &h->msg[1], (size_t)K * h->qm));
     GBX_TRY(dev_alloc(h, &h->PSI, (size_t)n * q));
     GBX_TRY(dev_alloc(h, &h->theta, (size_t)h->n_global + MAXPEER));
-    h->theta_pp[0] = h->theta;
-    if (ops->pull_ok && world == 1) {  // pull sweeps: per-vertex records (two generations), a second theta generation,
-                                       // the degree of every slot's neighbour
-      GBX_TRY(dev_alloc(h, &h->theta_pp[1], (size_t)h->n_global + MAXPEER));
+    if (ops->pull_ok) {  // pull sweeps: per-vertex records of ALL vertices (two generations; in a partitioned run every
+                         // rank stores its vertices' records into every rank's copy), two theta generations of this rank's
+                         // vertices, the degree of every slot's neighbour
+      GBX_TRY(dev_alloc(h, &h->theta_pp[0], (size_t)n + 2));
+      GBX_TRY(dev_alloc(h, &h->theta_pp[1], (size_t)n + 2));
       GBX_TRY(dev_alloc(h, &h->rec[0], (size_t)h->n_global * h->qm));
       GBX_TRY(dev_alloc(h, &h->rec[1], (size_t)h->n_global * h->qm));
       GBX_TRY(dev_alloc(h, &h->coldeg, (size_t)K));
+      GBX_TRY(dev_alloc(h, &h->slot_lv, (size_t)K));
+      {
+        std::vector<unsigned char> lv((size_t)std::max<int64_t>(K, 1), 0);
+        for (const int4& t : tiles)
+          for (int v = 0; v < t.y; ++v)
+            for (int e = rowptr[(size_t)t.x + v]; e < rowptr[(size_t)t.x + v + 1]; ++e) lv[(size_t)e] = (unsigned char)v;
+        GBX_CUDA_TRY(cudaMemcpy(h->slot_lv, lv.data(), (size_t)K, cudaMemcpyHostToDevice));
+      }
       GBX_CUDA_TRY(cudaMemsetAsync(h->rec[0], 0, (size_t)h->n_global * h->qm * sizeof(double), h->stream));
       GBX_CUDA_TRY(cudaMemsetAsync(h->rec[1], 0, (size_t)h->n_global * h->qm * sizeof(double), h->stream));
+      h->recp[0][h->rank] = h->rec[0];
+      h->recp[1][h->rank] = h->rec[1];
     }
     GBX_TRY(dev_alloc(h, &h->totals, (size_t)TOT_MAX));
     GBX_TRY(dev_alloc(h, &h->maxd_dev, 1));
-    if (model == 1) {  // degree of every vertex by global id: the field of mod.jl's sweep and free energy
+    if (model == 1 || (ops->pull_ok && world > 1)) {  // degree of every vertex by global id: the field of mod.jl's sweep
+                                                       // and free energy; the neighbour degrees of a partitioned pull run
       GBX_TRY(dev_alloc(h, &h->deg_global, (size_t)h->n_global));
       std::vector<double> dg((size_t)h->n_global);
       for (int64_t v = 0; v < h->n_global; ++v) dg[(size_t)v] = (double)(rowptr_g[(size_t)v + 1] - rowptr_g[(size_t)v]);
@@ -530,6 +553,7 @@ int gbx_sbm_destroy(gbx_sbm* h) {
     for (int r = 0; r < MAXPEER; ++r) {
       if (h->ipc_open[b][r]) cudaIpcCloseMemHandle(h->msgp[b][r]);
       if (h->ipc_open_recv[b][r]) cudaIpcCloseMemHandle(h->recvp[b][r]);
+      if (h->ipc_open_rec[b][r]) cudaIpcCloseMemHandle(h->recp[b][r]);
     }
   dev_free(h->device, h->rev_pack);
   dev_free(h->device, h->unpack_slot);
@@ -557,11 +581,15 @@ int gbx_sbm_destroy(gbx_sbm* h) {
   dev_free(h->device, h->msg[0]);
   dev_free(h->device, h->msg[1]);
   dev_free(h->device, h->PSI);
-  if (h->theta_owned) dev_free(h->device, h->theta_pp[0] ? h->theta_pp[0] : h->theta);
+  if (h->theta_owned) dev_free(h->device, h->theta);
+  dev_free(h->device, h->theta_pp[0]);
   dev_free(h->device, h->theta_pp[1]);
+  dev_free(h->device, h->in_link);
+  dev_free(h->device, h->out_link);
   dev_free(h->device, h->rec[0]);
   dev_free(h->device, h->rec[1]);
   dev_free(h->device, h->coldeg);
+  dev_free(h->device, h->slot_lv);
   if (h->totals_owned) dev_free(h->device, h->totals);
   dev_free(h->device, h->maxd_dev);
   dev_free(h->device, h->deg_global);
@@ -623,7 +651,8 @@ int gbx_sbm_init(gbx_sbm* h, const double* gr_init, const double* Crs_init, cons
   GBX_TRY(load_messages(h, psicav, seed));
   {
     GBX_TRY(fill_async(h, h->theta, h->n_global, 1.0));  // theta = ones(Ntot,1), sbm.jl:277
-    if (h->theta_pp[1]) GBX_TRY(fill_async(h, h->theta_pp[1], h->n_global, 1.0));
+    if (h->theta_pp[0]) GBX_TRY(fill_async(h, h->theta_pp[0], h->n, 1.0));
+    if (h->theta_pp[1]) GBX_TRY(fill_async(h, h->theta_pp[1], h->n, 1.0));
     GBX_TRY(fill_async(h, h->escale, h->K, 1.0));
   }
   if (!h->fail && !h->stepped) {
@@ -720,7 +749,10 @@ int gbx_sbm_get_state(gbx_sbm* h, double* gr, double* Crs, double* PSI, double* 
   if (Crs) memcpy(Crs, h->h_state->C, (size_t)q * q * sizeof(double));
   if (hfield) memcpy(hfield, h->h_state->h, q * sizeof(double));
   if (PSI) GBX_CUDA_TRY(cudaMemcpyAsync(PSI, h->PSI, (size_t)h->n * q * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  if (theta) GBX_CUDA_TRY(cudaMemcpyAsync(theta, h->theta + h->vbeg, (size_t)h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (theta) {
+    const double* src = h->pull ? h->theta_pp[h->thcur] : h->theta + h->vbeg;
+    GBX_CUDA_TRY(cudaMemcpyAsync(theta, src, (size_t)h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
   GBX_CUDA_TRY(cudaStreamSynchronize(h->stream));
   return GBX_OK;
 }
@@ -978,18 +1010,19 @@ int gbx_sbm_part_info(const gbx_sbm* h, int64_t* info) {
 }
 
 int gbx_sbm_ipc_export(gbx_sbm* h, int which, unsigned char* handle64) {
-  if (!h || !handle64 || which < 0 || which > 3) return fail_invalid("bad arguments");
-  if (which >= 2 && !h->recvbuf[which - 2]) return fail_invalid("no receive buffers (single-rank handle)");
+  if (!h || !handle64 || which < 0 || which > 5) return fail_invalid("bad arguments");
+  if (which >= 2 && which < 4 && !h->recvbuf[which - 2]) return fail_invalid("no receive buffers (single-rank handle)");
+  if (which >= 4 && !h->rec[which - 4]) return fail_invalid("no record buffers (this q has no pull kernels)");
   GBX_TRY(set_device(h));
   cudaIpcMemHandle_t mh;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-  GBX_CUDA_TRY(cudaIpcGetMemHandle(&mh, which < 2 ? h->msg[which] : h->recvbuf[which - 2]));
+  GBX_CUDA_TRY(cudaIpcGetMemHandle(&mh, which < 2 ? (void*)h->msg[which] : which < 4 ? (void*)h->recvbuf[which - 2] : (void*)h->rec[which - 4]));
   memcpy(handle64, &mh, 64);
   return GBX_OK;
 }
 
 int gbx_sbm_ipc_import(gbx_sbm* h, int which, int rank, const unsigned char* handle64) {
-  if (!h || !handle64 || which < 0 || which > 3 || rank < 0 || rank >= h->world) return fail_invalid("bad arguments");
+  if (!h || !handle64 || which < 0 || which > 5 || rank < 0 || rank >= h->world) return fail_invalid("bad arguments");
   if (rank == h->rank) return GBX_OK;
   GBX_TRY(set_device(h));
   cudaIpcMemHandle_t mh;
@@ -999,9 +1032,12 @@ int gbx_sbm_ipc_import(gbx_sbm* h, int which, int rank, const unsigned char* han
   if (which < 2) {
     h->msgp[which][rank] = (double*)p;
     h->ipc_open[which][rank] = true;
-  } else {
+  } else if (which < 4) {
     h->recvp[which - 2][rank] = (double*)p;
     h->ipc_open_recv[which - 2][rank] = true;
+  } else {
+    h->recp[which - 4][rank] = (double*)p;
+    h->ipc_open_rec[which - 4][rank] = true;
   }
   return GBX_OK;
 }
@@ -1016,7 +1052,6 @@ int gbx_sbm_part_set_buffers(gbx_sbm* h, void* totals_dev, void* theta_dev) {
   }
   if (theta_dev) {
     if (h->theta_owned) dev_free(h->device, h->theta);
-    h->theta_pp[0] = nullptr;
     h->theta = (double*)theta_dev;
     h->theta_owned = false;
   }
@@ -1026,7 +1061,10 @@ int gbx_sbm_part_set_buffers(gbx_sbm* h, void* totals_dev, void* theta_dev) {
 int gbx_sbm_part_set_exchange(gbx_sbm* h, int mode) {
   if (!h) return fail_invalid("handle is NULL");
   if (mode != 0 && mode != 1) return fail_invalid("exchange mode must be 0 (direct peer stores) or 1 (packed)");
-  if (mode == 1 && h->world > 1 && !h->rev_pack) return fail_invalid("no exchange plan");
+  if (mode == 1 && h->world > 1 && !h->rev_pack) {
+    if (!h->ops->pull_ok) return fail_invalid("no exchange plan");
+    mode = 0;  // the packed exchange was not planned because this q sweeps with the pull kernels (records, not messages)
+  }
   if (h->pending_unpack) return fail_state();
   h->exchange = h->world > 1 ? mode : 0;
   return GBX_OK;

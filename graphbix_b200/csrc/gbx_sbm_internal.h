@@ -165,6 +165,10 @@ struct gbx_sbm {
                                        // at g = 0 msg[1] holds the incoming messages (the layout of the push path)
   double* rec[2] = {nullptr, nullptr}; // per-vertex records [n_global][qm] of generation g in rec[g & 1]
   float* coldeg = nullptr;             // degree of col[e]
+  unsigned char* slot_lv = nullptr;    // vertex (inside its tile) of every slot
+  int *in_link = nullptr, *out_link = nullptr;   // per local slot: index in `links` of the incoming / outgoing message
+  double* recp[2][gbx::MAXPEER] = {};  // rec[b] of every rank (peer-mapped): a sweep stores a vertex's record everywhere
+  bool ipc_open_rec[2][gbx::MAXPEER] = {};
   double* theta_pp[2] = {nullptr, nullptr};  // [n] theta of this rank's vertices, two generations
   int thcur = 0, th_used = 0;          // theta_pp[thcur]: current; theta_pp[th_used]: what the last sweep ran with
   alignas(64) unsigned char tmap[2][128] = {};  // CUtensorMap of msg[0] / msg[1] (rows of qm doubles, box of 32 rows)

@@ -35,8 +35,15 @@
 constexpr bool PULL_OK = (QM == 4 || QM == 8 || QM == 16);     // rows of 32 / 64 / 128 bytes: a hardware swizzle fits
 constexpr int SWZ_MASK = (ROWB <= 32) ? 1 : (ROWB <= 64 ? 3 : 7);
 constexpr int NB_BLK = (Q <= 1) ? 0 : (Q <= 2 ? 1 : (Q <= 4 ? 2 : (Q <= 8 ? 3 : 4)));   // sign bits that carry the MAP block
-constexpr int P_S = 3;                  // stages of the streamed ring
-constexpr int P_R = 2;                  // stages of the gathered ring
+#ifndef GBX_PS
+#define GBX_PS 3
+#endif
+#ifndef GBX_PR
+#define GBX_PR 2
+#endif
+constexpr int P_S = GBX_PS;             // stages of the streamed ring: the producer runs P_S - 1 tiles ahead
+constexpr int P_R = GBX_PR;             // stages of the gathered ring: records are fetched P_R - 1 tiles ahead
+static_assert(P_S > P_R, "a tile's neighbour ids must have been streamed before its records can be gathered");
 constexpr int P_NT = NT + 32;           // threads of a pull CTA: NT consumers + one producer warp
 constexpr int QTP = Q + 4;              // prior-table row: E_0..E_{Q-1}, ffrac, fi, xmax, 2^-ffrac
 
@@ -53,19 +60,28 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
+// Wait for the phase of parity `parity` to complete.  try_wait suspends the thread in hardware for up to the hinted
+// time; a thread that still finds the phase open backs off with nanosleep so that its polling does not take issue
+// slots from the warps that have work (ncu: an un-throttled poll loop was 30% of the executed instructions).
+template <int SLEEP_NS>
+__device__ __forceinline__ void mbar_wait_t(unsigned long long* bar, unsigned parity) {
+  const unsigned addr = smem_u32(bar);
+  for (;;) {
+    unsigned done;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"(20000u)
+        : "memory");
+    if (done) break;
+    if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+  }
 }
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) { mbar_wait_t<20>(bar, parity); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // 1-D bulk copy global -> shared (UBLKCP); dst, src and bytes are multiples of 16
@@ -107,8 +123,8 @@ struct PStage {  // one stage of the streamed ring (bytes; every piece 16-byte a
   static constexpr size_t thc_off = old_off + (size_t)(TV * Q + 2) * 8;      // TV + 2 current thetas
   static constexpr size_t thp_off = thc_off + (size_t)(TV + 2) * 8;          // TV + 2 thetas of the previous sweep
   static constexpr size_t desc_off = thp_off + (size_t)(TV + 2) * 8;         // the tile descriptor (int4)
-  static constexpr size_t lv_off = desc_off + 16;                            // TILE_E: vertex (inside the tile) of a slot
-  static constexpr size_t bytes = ((lv_off + (size_t)TILE_E + 1023) / 1024) * 1024;
+  static constexpr size_t lv_off = desc_off + 16;                            // TILE_E + 16: vertex (inside the tile) of a slot
+  static constexpr size_t bytes = ((lv_off + (size_t)TILE_E + 16 + 1023) / 1024) * 1024;
 };
 struct PullSmem {
   static constexpr size_t gat_off = P_S * PStage::bytes;                              // P_R x TILE_E gathered records
@@ -119,15 +135,22 @@ struct PullSmem {
   static constexpr size_t dr_off = scratch_off + (size_t)(NT > 64 * MB * MB ? NT : 64 * MB * MB) * 8;
   static constexpr size_t nr_off = dr_off + (size_t)Q * 8;
   static constexpr size_t fn_off = nr_off + (size_t)((Q + 1) / 2 * 2) * 4;
-  static constexpr size_t bar_off = ((fn_off + (size_t)TV * 4 + 7) / 8) * 8;          // 2 P_S + 2 P_R mbarriers
-  static constexpr size_t total = ((bar_off + (size_t)(2 * P_S + 2 * P_R) * 8 + 127) / 128) * 128 + 1024;  // + alignment slack
+  static constexpr size_t bar_off = ((fn_off + (size_t)TV * 4 + 7) / 8) * 8;          // 2 P_S + P_R mbarriers
+  static constexpr size_t total = ((bar_off + (size_t)(2 * P_S + P_R) * 8 + 127) / 128) * 128 + 1024;  // + alignment slack
 };
+
+#ifdef GBX_FORCE_CTAS
+constexpr int PULL_MIN_CTAS = GBX_FORCE_CTAS;
+#else
+constexpr int PULL_MIN_CTAS = (PullSmem::total + 1024 <= 75 * 1024) ? 3 : ((PullSmem::total + 1024 <= 113 * 1024) ? 2 : 1);
+#endif
 
 struct PullArgs {
   const int4* tiles;   // (first vertex, #vertices, first edge slot, #edge slots)
   int ntiles;
   const int* rowptr;
   const int* col;        // neighbour of every slot (global vertex id)
+  const unsigned char* slot_lv;   // vertex (inside its tile) of every slot
   const float* coldeg;   // its degree (degree-corrected sbm.jl runs)
   const int* pidx;
   const double* prior_tab;
@@ -135,8 +158,10 @@ struct PullArgs {
   const double* theta_prev;
   double* PSI;
   double* msg;             // the message buffer this pass streams (a sweep rewrites it in place)
-  const double* rec_old;   // records of the previous sweep, by global vertex id
-  double* rec_new;
+  const double* rec_old;   // records of the previous sweep, by global vertex id (all ranks' vertices)
+  double* rec_new;         // this rank's copy of the new records ...
+  double* rec_peer[MAXPEER];   // ... and every other rank's (peer-mapped over NVLink): a vertex's record is stored
+  int npeer;                   //     into all of them, so the next sweep gathers locally
   long long vbeg;
   double* partials;
   double* mpart;
@@ -212,7 +237,7 @@ __device__ __forceinline__ double record_component(double u, int fn, double ifra
 // RECON: the incoming messages are rebuilt from records (any pass after the first sweep); otherwise `msg` holds the
 // incoming messages themselves (the state right after init) and a sweep overwrites them with the outgoing ones.
 template <int MODE, bool RECON>
-__global__ void __launch_bounds__(P_NT, (Q <= 8) ? 3 : 2)
+__global__ void __launch_bounds__(P_NT, PULL_MIN_CTAS)
     sbm_pull_kernel(const __grid_constant__ CUtensorMap tmap, PullArgs a) {
   extern __shared__ __align__(1024) char smem_raw[];
   // 1024-byte alignment (swizzle atoms) by an offset, not through an integer cast: the pointer keeps its shared-memory
@@ -228,8 +253,7 @@ __global__ void __launch_bounds__(P_NT, (Q <= 8) ? 3 : 2)
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + PullSmem::bar_off);
   unsigned long long* full_s = bars;                    // [P_S] streamed stage has landed
   unsigned long long* empty_s = bars + P_S;             // [P_S] consumers are done with it
-  unsigned long long* full_g = bars + 2 * P_S;          // [P_R] gathered records have landed, slot owners are filled in
-  unsigned long long* empty_g = bars + 2 * P_S + P_R;   // [P_R]
+  unsigned long long* full_g = bars + 2 * P_S;          // [P_R] gathered records have landed
 
   const int tid = threadIdx.x;
   if (MODE == MODE_SWEEP && skip_iteration(a.st, a.it)) return;
@@ -243,10 +267,7 @@ __global__ void __launch_bounds__(P_NT, (Q <= 8) ? 3 : 2)
       mbar_init(&full_s[s], 1);
       mbar_init(&empty_s[s], NT / 32);
     }
-    for (int r = 0; r < P_R; ++r) {
-      mbar_init(&full_g[r], RECON ? 64 : 32);
-      mbar_init(&empty_g[r], NT / 32);
-    }
+    for (int r = 0; r < P_R; ++r) mbar_init(&full_g[r], NT);   // one cp.async arrival per consumer thread
     fence_barrier_init();
   }
   if (tid < Q) {
@@ -262,7 +283,7 @@ __global__ void __launch_bounds__(P_NT, (Q <= 8) ? 3 : 2)
       const int s = j % P_S;
       __syncwarp();
       if (lane == 0) {   // one lane waits for the stage and issues its copies; the others meet it at the __syncwarp below
-        if (j >= P_S) mbar_wait(&empty_s[s], ((j / P_S) & 1) ^ 1);
+        if (j >= P_S) mbar_wait_t<200>(&empty_s[s], ((j / P_S) & 1) ^ 1);
         const int4 td = a.tiles[bid + j * G];
         char* sb = smem + (size_t)s * PStage::bytes;
         *reinterpret_cast<int4*>(sb + PStage::desc_off) = td;
@@ -278,10 +299,13 @@ __global__ void __launch_bounds__(P_NT, (Q <= 8) ? 3 : 2)
         const unsigned nb_pi = (unsigned)(((nv + (v0 - va0)) * 4 + 15) & ~15);
         const unsigned nb_old = (MODE == MODE_SWEEP) ? (unsigned)((((long long)nv * Q + (d0 - da0)) * 8 + 15) & ~15ll) : 0u;
         const unsigned nb_th = (THETA && a.dc_model) ? (unsigned)(((nv + (v0 - ta0)) * 8 + 15) & ~15) : 0u;
-        mbar_arrive_expect_tx(bar, nbox * 32u * ROWB + nb_col + nb_deg + nb_rp + nb_pi + nb_old + nb_th + (RECON ? nb_th : 0u));
+        const int la0 = e0 & ~15;
+        const unsigned nb_lv = ne > 0 ? (unsigned)((ne + (e0 - la0) + 15) & ~15) : 0u;
+        mbar_arrive_expect_tx(bar, nbox * 32u * ROWB + nb_col + nb_deg + nb_rp + nb_pi + nb_old + nb_th + (RECON ? nb_th : 0u) + nb_lv);
         for (unsigned b = 0; b < nbox; ++b)   // message rows, 32 at a time (rows past the buffer's end read as zeros)
           tma_load_2d(sb + PStage::msg_off + (size_t)b * 32 * ROWB, &tmap, bar, 0, e0 + (int)b * 32);
         if (nb_col) bulk_load(sb + PStage::col_off, a.col + ea0, nb_col, bar);
+        if (nb_lv) bulk_load(sb + PStage::lv_off, a.slot_lv + la0, nb_lv, bar);
         if (nb_deg) bulk_load(sb + PStage::deg_off, a.coldeg + ea0, nb_deg, bar);
         bulk_load(sb + PStage::rp_off, a.rowptr + va0, nb_rp, bar);
         bulk_load(sb + PStage::pi_off, a.pidx + va0, nb_pi, bar);
@@ -293,41 +317,10 @@ __global__ void __launch_bounds__(P_NT, (Q <= 8) ? 3 : 2)
       }
       __syncwarp();
     };
-    auto gather = [&](int j) {
-      const int s = j % P_S, r = j % P_R;
-      mbar_wait(&full_s[s], (j / P_S) & 1);   // the neighbour ids and row pointers of tile j have landed
-      if (j >= P_R) mbar_wait(&empty_g[r], ((j / P_R) & 1) ^ 1);
-      __syncwarp();
-      char* sb = smem + (size_t)s * PStage::bytes;
-      const int4 td = *reinterpret_cast<const int4*>(sb + PStage::desc_off);
-      const int v0 = td.x, nv = td.y, e0 = td.z, ne = td.w;
-      if constexpr (RECON) {
-        const int* colS = reinterpret_cast<const int*>(sb + PStage::col_off) + (e0 & 3);
-        char* gb = smem + PullSmem::gat_off + (size_t)r * TILE_E * ROWB;
-        const char* rec = reinterpret_cast<const char*>(a.rec_old);
-        for (int u = lane; u < ne * CH; u += 32) {
-          const int row = u / CH, c = u % CH;
-          cp_async_16(gb + swz(row * ROWB + c * 16), rec + ((size_t)colS[row] * ROWB + (size_t)c * 16));
-        }
-        cp_async_mbar_arrive_noinc(&full_g[r]);
-      }
-      // vertex (inside the tile) of every slot, for the per-edge phases
-      unsigned char* lvS = reinterpret_cast<unsigned char*>(sb + PStage::lv_off);
-      const int* rpS = reinterpret_cast<const int*>(sb + PStage::rp_off) + (v0 & 3);
-      for (int v = lane; v < nv; v += 32) {
-        const int b = rpS[v] - e0, e = rpS[v + 1] - e0;
-        for (int k = b; k < e; ++k) lvS[k] = (unsigned char)v;
-      }
-      mbar_arrive(&full_g[r]);
-      __syncwarp();
-    };
-    if (nt > 0) load_stream(0);
-    if (nt > 1) load_stream(1);
-    if (nt > 0) gather(0);
-    for (int j = 0; j < nt; ++j) {
-      if (j + 2 < nt) load_stream(j + 2);
-      if (j + 1 < nt) gather(j + 1);
-    }
+    // stream stages run two tiles ahead of the consumers; the consumers themselves issue the record gathers of the
+    // tile after the one they work on (128 threads share that work; one warp could not keep up)
+    for (int j = 0; j < P_S - 1 && j < nt; ++j) load_stream(j);
+    for (int j = 0; j + P_S - 1 < nt; ++j) load_stream(j + P_S - 1);
     return;
   }
 
@@ -343,12 +336,39 @@ __global__ void __launch_bounds__(P_NT, (Q <= 8) ? 3 : 2)
   const int vwarp = (tid & ~31) / LV;
   const int lane = tid & 31;
 
+  // Gathers of tile jj's records into gather stage jj % P_R, by all consumer threads: unit u = tid + NT i of the tile's
+  // ne * CH 16-byte units (CH consecutive lanes fetch one record).  The stage was last read in phase A of tile jj - 2,
+  // which every consumer warp has left (two consumer barriers ago) when this is called at the top of tile jj - 1.
+  auto issue_gather = [&](int jj) {
+    if constexpr (RECON) {
+      const int sg = jj % P_S, rg = jj % P_R;
+      mbar_wait(&full_s[sg], (jj / P_S) & 1);   // its neighbour ids have landed
+      const char* sbg = smem + (size_t)sg * PStage::bytes;
+      const int4 tg = *reinterpret_cast<const int4*>(sbg + PStage::desc_off);
+      const int* colS = reinterpret_cast<const int*>(sbg + PStage::col_off) + (tg.z & 3);
+      char* gbg = smem + PullSmem::gat_off + (size_t)rg * TILE_E * ROWB;
+      const char* rec = reinterpret_cast<const char*>(a.rec_old);
+      const int nu = tg.w * CH;
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        const int u = tid + NT * i;
+        if (u < nu) {
+          const int row = u / CH, c = u % CH;
+          cp_async_16(gbg + swz(row * ROWB + c * 16), rec + ((size_t)colS[row] * ROWB + (size_t)c * 16));
+        }
+      }
+      cp_async_mbar_arrive_noinc(&full_g[rg]);
+    }
+  };
+  for (int j = 0; j < P_R - 1 && j < nt; ++j) issue_gather(j);
+
   for (int j = 0; j < nt; ++j) {
     const int s = j % P_S, r = j % P_R;
     char* sb = smem + (size_t)s * PStage::bytes;
     char* gb = smem + PullSmem::gat_off + (size_t)r * TILE_E * ROWB;
+    if (j + P_R - 1 < nt) issue_gather(j + P_R - 1);
     mbar_wait(&full_s[s], (j / P_S) & 1);
-    mbar_wait(&full_g[r], (j / P_R) & 1);
+    if constexpr (RECON) mbar_wait(&full_g[r], (j / P_R) & 1);
     const int4 td = *reinterpret_cast<const int4*>(sb + PStage::desc_off);
     const int v0 = td.x, nv = td.y, e0 = td.z, ne = td.w;
     const int* rpS = reinterpret_cast<const int*>(sb + PStage::rp_off) + (v0 & 3);
@@ -356,7 +376,7 @@ __global__ void __launch_bounds__(P_NT, (Q <= 8) ? 3 : 2)
     const double* oldS = reinterpret_cast<const double*>(sb + PStage::old_off) + (((long long)v0 * Q) & 1);
     const double* thcS = reinterpret_cast<const double*>(sb + PStage::thc_off) + (v0 & 1);
     const double* thpS = reinterpret_cast<const double*>(sb + PStage::thp_off) + (v0 & 1);
-    const unsigned char* lvS = reinterpret_cast<const unsigned char*>(sb + PStage::lv_off);
+    const unsigned char* lvS = reinterpret_cast<const unsigned char*>(sb + PStage::lv_off) + (e0 & 15);
     char* msgS = sb + PStage::msg_off;
 
     // prior factors of this tile's first round of vertices (an L2-resident table row per vertex)
@@ -452,7 +472,9 @@ __global__ void __launch_bounds__(P_NT, (Q <= 8) ? 3 : 2)
           const double invth = (THETA && a.dc) ? fast_rcp(thcS[v]) : 1.0;
           if (t < QM) {
             const double x = tl ? record_component(u, fn, pr.ifrac, invth, eumax, t < NB_BLK && ((best >> t) & 1)) : 0.0;
-            a.rec_new[(size_t)(a.vbeg + v0 + v) * QM + t] = x;
+            const size_t ri = (size_t)(a.vbeg + v0 + v) * QM + t;
+            a.rec_new[ri] = x;
+            for (int p = 0; p < a.npeer; ++p) a.rec_peer[p][ri] = x;   // QP lanes write one contiguous row
           }
         }
       }
@@ -500,10 +522,7 @@ __global__ void __launch_bounds__(P_NT, (Q <= 8) ? 3 : 2)
     // ---- hand the stages back to the producer ----
     fence_proxy_async();   // this thread's plain stores into the message stage precede the next TMA write there
     __syncwarp();
-    if (lane == 0) {
-      mbar_arrive(&empty_s[s]);
-      mbar_arrive(&empty_g[r]);
-    }
+    if (lane == 0) mbar_arrive(&empty_s[s]);
   }
   // CTA-wide reductions of the consumers (the producer warp has left): barrier 1 over NT threads
   store_partials<true>(acc, scratch, a.partials + (size_t)blockIdx.x * PSTRIDE, s_dr, s_nr);
@@ -641,9 +660,12 @@ __global__ void __launch_bounds__(NT) sbm_pull_hub_kernel(PullArgs a, int part_b
           fnSh = fn;
         }
         const double invth = (MODEL == MODEL_SBM && a.dc) ? fast_rcp(thj) : 1.0;
-        if (t < QM)
-          a.rec_new[(size_t)(a.vbeg + gv) * QM + t] =
-              tl ? record_component(u, fn, pr.ifrac, invth, eumax, t < NB_BLK && ((best >> t) & 1)) : 0.0;
+        if (t < QM) {
+          const double x = tl ? record_component(u, fn, pr.ifrac, invth, eumax, t < NB_BLK && ((best >> t) & 1)) : 0.0;
+          const size_t ri = (size_t)(a.vbeg + gv) * QM + t;
+          a.rec_new[ri] = x;
+          for (int p = 0; p < a.npeer; ++p) a.rec_peer[p][ri] = x;
+        }
       }
     }
   }
@@ -774,42 +796,50 @@ __global__ void k_coldeg(const int* __restrict__ col, const int* __restrict__ ro
     out[e] = (float)(rowptr_global[j + 1] - rowptr_global[j]);
   }
 }
-// Messages between `links` order and the pull layout.  Link k = (a -> b) is slot s = slot_of_link[k] of the incoming
-// layout (row b) and slot rev[s] of the outgoing layout (row a).
-//   to_slots: out_buf[rev[s]] = in_buf[s] = src[k];  otherwise dst[k] = out_buf[rev[s]]
+// Messages between `links` order and the pull layout of this rank's slots: slot e keeps the outgoing message
+// out_link[e] and (before the first sweep) the incoming message in_link[e].
+//   to_slots: in_buf[e] = src[in_link[e]], out_buf[e] = src[out_link[e]];  otherwise dst[out_link[e]] = out_buf[e]
 __global__ void k_pull_permute(const double* __restrict__ src, double* __restrict__ dst, double* __restrict__ in_buf,
-                               double* __restrict__ out_buf, const int* __restrict__ slot_of_link, const int* __restrict__ rev,
-                               long long K, int to_slots) {
-  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < K; k += (long long)gridDim.x * blockDim.x) {
-    const long long s = slot_of_link[k];
-    const long long o = rev_slot(rev[s]);
+                               double* __restrict__ out_buf, const int* __restrict__ in_link, const int* __restrict__ out_link,
+                               long long Kl, int to_slots) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < Kl; e += (long long)gridDim.x * blockDim.x) {
     double m[Q];
     if (to_slots) {
-      load_vec<Q>(src, k, m);
-      store_msg<Q, QM>(in_buf, s, m);
-      store_msg<Q, QM>(out_buf, o, m);
+      load_vec<Q>(src, in_link[e], m);
+      store_msg<Q, QM>(in_buf, e, m);
+      load_vec<Q>(src, out_link[e], m);
+      store_msg<Q, QM>(out_buf, e, m);
     } else {
-      load_msg<Q, QM>(out_buf, o, m);
-      store_vec<Q>(dst, k, m);
+      load_msg<Q, QM>(out_buf, e, m);
+      store_vec<Q>(dst, out_link[e], m);
     }
   }
 }
-__global__ void k_pull_random_messages(double* __restrict__ in_buf, double* __restrict__ out_buf,
-                                       const int* __restrict__ slot_of_link, const int* __restrict__ rev, long long K,
-                                       uint64_t seed) {
-  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < K; k += (long long)gridDim.x * blockDim.x) {
-    const long long s = slot_of_link[k];
-    double m[Q];
-    double sum = 0.0;
+__device__ __forceinline__ void random_message(uint64_t seed, long long k, double (&m)[Q]) {
+  double sum = 0.0;
 #pragma unroll
-    for (int t = 0; t < Q; ++t) {
-      const uint64_t r = splitmix64(seed ^ splitmix64((uint64_t)k * Q + t));   // the draw of k_random_messages
-      m[t] = ((double)(r >> 11) + 0.5) * (1.0 / 9007199254740992.0);
-      sum += m[t];
-    }
-#pragma unroll
-    for (int t = 0; t < Q; ++t) m[t] /= sum;
-    store_msg<Q, QM>(in_buf, s, m);
-    store_msg<Q, QM>(out_buf, (long long)rev_slot(rev[s]), m);
+  for (int t = 0; t < Q; ++t) {
+    const uint64_t r = splitmix64(seed ^ splitmix64((uint64_t)k * Q + t));   // the draw of k_random_messages
+    m[t] = ((double)(r >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    sum += m[t];
   }
+#pragma unroll
+  for (int t = 0; t < Q; ++t) m[t] /= sum;
+}
+__global__ void k_pull_random_messages(double* __restrict__ in_buf, double* __restrict__ out_buf,
+                                       const int* __restrict__ in_link, const int* __restrict__ out_link, long long Kl,
+                                       uint64_t seed) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < Kl; e += (long long)gridDim.x * blockDim.x) {
+    double m[Q];
+    random_message(seed, in_link[e], m);
+    store_msg<Q, QM>(in_buf, e, m);
+    random_message(seed, out_link[e], m);
+    store_msg<Q, QM>(out_buf, e, m);
+  }
+}
+// degree of the neighbour of every slot, from the degrees by global vertex id
+__global__ void k_coldeg_global(const int* __restrict__ col, const double* __restrict__ deg_global, long long K,
+                                float* __restrict__ out) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < K; e += (long long)gridDim.x * blockDim.x)
+    out[e] = (float)deg_global[col[e]];
 }

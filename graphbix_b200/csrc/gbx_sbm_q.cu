@@ -1659,11 +1659,9 @@ int op_prepare(gbx_sbm* h, int zero_h, int gr_from_sum) {
 }
 
 int op_theta_local(gbx_sbm* h) {
-  if (h->pull) {  // keep the thetas the last sweep ran with: the next sweep rebuilds that sweep's messages
-    h->thcur ^= 1;
-    h->theta = h->theta_pp[h->thcur];
-  }
-  sbm_theta_kernel<<<h->grid_theta, NT, 0, h->stream>>>(h->st, h->rowptr, (int)h->n, h->PSI, h->theta + h->vbeg, h->pidx,
+  if (h->pull) h->thcur ^= 1;  // keep the thetas the last sweep ran with: the next sweep rebuilds that sweep's messages
+  sbm_theta_kernel<<<h->grid_theta, NT, 0, h->stream>>>(h->st, h->rowptr, (int)h->n, h->PSI,
+                                                        h->pull ? h->theta_pp[h->thcur] : h->theta + h->vbeg, h->pidx,
                                                         h->part_theta, h->cur_it);
   h->theta_valid = true;
   k_local_columns<<<1, 256, 0, h->stream>>>(h->part_theta, h->grid_theta, Q, h->totals, h->st, h->cur_it);
@@ -1783,6 +1781,7 @@ PullArgs pull_args(gbx_sbm* h, int mode) {
   a.rowptr = h->rowptr;
   a.col = h->col;
   a.coldeg = h->coldeg;
+  a.slot_lv = h->slot_lv;
   a.pidx = h->pidx;
   a.prior_tab = h->prior_tab;
   a.theta_cur = h->theta_pp[h->thcur];
@@ -1794,6 +1793,10 @@ PullArgs pull_args(gbx_sbm* h, int mode) {
   a.msg = h->msg[(h->gen + 1) & 1];
   a.rec_old = h->rec[h->gen & 1];
   a.rec_new = h->rec[(h->gen + 1) & 1];
+  a.npeer = 0;
+  for (int r = 0; r < h->world; ++r)
+    if (r != h->rank) a.rec_peer[a.npeer++] = h->recp[(h->gen + 1) & 1][r];
+  for (int p = a.npeer; p < MAXPEER; ++p) a.rec_peer[p] = nullptr;
   a.vbeg = h->vbeg;
   a.partials = h->part_vertex;
   a.mpart = h->part_mstep;
@@ -1914,7 +1917,8 @@ int op_pull_setup(gbx_sbm* h) {
       }
     }
     if (h->K > 0) {
-      k_coldeg<<<grid_for(h, h->K), 256, 0, h->stream>>>(h->col, h->rowptr, (long long)h->K, h->coldeg);
+      if (h->world > 1) k_coldeg_global<<<grid_for(h, h->K), 256, 0, h->stream>>>(h->col, h->deg_global, (long long)h->K, h->coldeg);
+      else k_coldeg<<<grid_for(h, h->K), 256, 0, h->stream>>>(h->col, h->rowptr, (long long)h->K, h->coldeg);
       h->launches++;
       GBX_CUDA_TRY(cudaGetLastError());
     }
@@ -1930,10 +1934,10 @@ int op_pull_setup(gbx_sbm* h) {
 int op_pull_load(gbx_sbm* h, const double* src_dev, uint64_t seed) {
   if (h->K > 0) {
     if (src_dev)
-      k_pull_permute<<<grid_for(h, h->K), 256, 0, h->stream>>>(src_dev, nullptr, h->msg[1], h->msg[0], h->slot_of_link, h->rev,
+      k_pull_permute<<<grid_for(h, h->K), 256, 0, h->stream>>>(src_dev, nullptr, h->msg[1], h->msg[0], h->in_link, h->out_link,
                                                               (long long)h->K, 1);
     else
-      k_pull_random_messages<<<grid_for(h, h->K), 256, 0, h->stream>>>(h->msg[1], h->msg[0], h->slot_of_link, h->rev,
+      k_pull_random_messages<<<grid_for(h, h->K), 256, 0, h->stream>>>(h->msg[1], h->msg[0], h->in_link, h->out_link,
                                                                       (long long)h->K, seed);
     h->launches++;
     GBX_CUDA_TRY(cudaGetLastError());
@@ -1942,9 +1946,11 @@ int op_pull_load(gbx_sbm* h, const double* src_dev, uint64_t seed) {
 }
 
 int op_pull_export(gbx_sbm* h, double* dst_dev) {
+  // rows of links whose source vertex another rank owns come back as zeros (as on the push layout)
+  if (h->world > 1) GBX_CUDA_TRY(cudaMemsetAsync(dst_dev, 0, (size_t)h->K_global * Q * sizeof(double), h->stream));
   if (h->K > 0) {
-    k_pull_permute<<<grid_for(h, h->K), 256, 0, h->stream>>>(nullptr, dst_dev, nullptr, h->msg[h->gen & 1], h->slot_of_link,
-                                                            h->rev, (long long)h->K, 0);
+    k_pull_permute<<<grid_for(h, h->K), 256, 0, h->stream>>>(nullptr, dst_dev, nullptr, h->msg[h->gen & 1], h->in_link,
+                                                            h->out_link, (long long)h->K, 0);
     h->launches++;
     GBX_CUDA_TRY(cudaGetLastError());
   }

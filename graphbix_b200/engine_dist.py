@@ -65,10 +65,16 @@ class PartEngine:
         check(self.lib.gbx_sbm_part_set_buffers(self._h, C.c_void_p(self.totals.data_ptr()),
                                                 C.c_void_p(self.theta.data_ptr())))
         check(self.lib.gbx_sbm_set_stream(self._h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        # peer pointers of both message buffers and both receive buffers of every rank
-        for which in ((0, 1, 2, 3) if self.world > 1 else ()):
+        # peer pointers: both message buffers (push sweeps store into the owner's rows), both receive buffers (packed
+        # exchange of the push sweep, when it was planned) and both per-vertex record buffers (pull sweeps store a
+        # vertex's record into every rank's copy) of every rank
+        for which in ((0, 1, 2, 3, 4, 5) if self.world > 1 else ()):
             buf = (C.c_ubyte * 64)()
-            check(self.lib.gbx_sbm_ipc_export(self._h, which, buf))
+            rc = self.lib.gbx_sbm_ipc_export(self._h, which, buf)
+            have = [None] * self.world
+            dist.all_gather_object(have, int(rc))
+            if any(r != 0 for r in have):       # no such buffer on this kind of handle (the same on every rank)
+                continue
             handles = [None] * self.world
             dist.all_gather_object(handles, bytes(buf))
             for r, hb in enumerate(handles):
@@ -138,11 +144,17 @@ class PartEngine:
         0: stored one by one into the owner's buffer from the sweep kernel."""
         check(self.lib.gbx_sbm_part_set_exchange(self._h, int(mode)))
 
+    @property
+    def pull(self):
+        """True when the run sweeps with the pull kernels (decided by init): what crosses NVLink is then one record per
+        vertex and rank, stored by the sweep kernel itself; no unpack, no theta all-gather, no per-slot theta scales."""
+        return bool(self.lib.gbx_sbm_sweep_kind(self._h))
+
     def _pass(self, mode):
         self._step(STEP_VERTEX_PASS, mode)
         self._step(STEP_LOCAL_TOTALS, mode)
-        self._allreduce()                   # also the barrier after which every rank's boundary rows have arrived
-        if mode == MODE_SWEEP:
+        self._allreduce()                   # also the barrier after which every rank's peer stores have landed
+        if mode == MODE_SWEEP and not self.pull:
             self._step(STEP_UNPACK)
         self._step(STEP_APPLY_TOTALS, mode)
 
@@ -171,10 +183,11 @@ class PartEngine:
                 self._step(STEP_THETA_LOCAL)
                 self._allreduce(q)
                 self._step(STEP_THETA_APPLY)
-                # in place: this rank's slice of the output is its input (NCCL's in-place all-gather layout)
-                self.dist.all_gather_into_tensor(self.theta, self.theta[r * c:(r + 1) * c])
-                self._sync("all_gather(theta)")
-                self._step(STEP_ESCALE)
+                if not self.pull:
+                    # in place: this rank's slice of the output is its input (NCCL's in-place all-gather layout)
+                    self.dist.all_gather_into_tensor(self.theta, self.theta[r * c:(r + 1) * c])
+                    self._sync("all_gather(theta)")
+                    self._step(STEP_ESCALE)
             self._step(STEP_COUNT_ITERATION)
             self._tick("iteration end")
 

@@ -116,9 +116,10 @@ int64_t gbx_sbm_device_bytes(const gbx_sbm* h);
 /* Algorithmic HBM bytes one BP sweep moves (DESIGN.md "bytes per unit"). */
 double gbx_sbm_sweep_bytes(const gbx_sbm* h);
 /* Which sweep kernels the current EM run uses (decided by gbx_*_init): 0 = push (new messages scattered into the
- * receiver's rows), 1 = pull (a vertex keeps its outgoing messages and rebuilds the incoming ones from per-vertex
- * records; the default whenever a message row is 32, 64 or 128 bytes, damping == 1 and the handle is not partitioned;
- * GBX_PULL=0 in the environment forces push).  Results agree to rounding; DESIGN.md "Sweep kernels". */
+ * receiver's rows; the default on one GPU), 1 = pull (a vertex keeps its outgoing messages and rebuilds the incoming
+ * ones from per-vertex records; needs message rows of 32, 64 or 128 bytes and damping == 1; the default of partitioned
+ * handles, where it sends one record per vertex over NVLink instead of one message per cut edge).  GBX_PULL=1 / 0 in
+ * the environment forces pull / push where possible.  Results agree to rounding; DESIGN.md "Sweep kernels". */
 int gbx_sbm_sweep_kind(const gbx_sbm* h);
 
 /* ------------------------------------------------------------------------------------------------
@@ -248,8 +249,9 @@ int gbx_mod_create_part(gbx_mod** out, int device, int64_t n_vertices, int64_t n
 /* info[0..8) = first owned vertex, owned vertices, first owned slot, owned slots, length of the totals vector,
  * vertices per rank c, rank, world */
 int gbx_sbm_part_info(const gbx_sbm* h, int64_t* info);
-/* cudaIpcMemHandle_t (64 bytes) of message buffer `which` (0/1) or receive buffer `which - 2` (2/3); every rank
- * imports every other rank's four. */
+/* cudaIpcMemHandle_t (64 bytes) of message buffer `which` (0/1), receive buffer `which - 2` (2/3) or per-vertex record
+ * buffer `which - 4` (4/5; pull sweeps: a rank stores the records of its vertices into every rank's copy, so only these
+ * two have to be mapped for a pull run); every rank imports every other rank's. */
 int gbx_sbm_ipc_export(gbx_sbm* h, int which, unsigned char* handle64);
 int gbx_sbm_ipc_import(gbx_sbm* h, int which, int rank, const unsigned char* handle64);
 /* Device buffers owned by the caller that the collectives run on: totals (info[4] doubles) and theta

@@ -10,6 +10,14 @@ from sync_model import SyncSBM
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["push", "pull"])
+def sweep_kind(request, monkeypatch):
+    """Every test of this file runs with both sweep kernels (push: GBX_PULL=0, pull: GBX_PULL=1; where a run cannot use
+    the pull kernels -- damping, q = 9..12 -- the library falls back to push)."""
+    monkeypatch.setenv("GBX_PULL", "1" if request.param == "pull" else "0")
+    return request.param
+
+
 def _create(lib, n, links, q):
     h = C.c_void_p()
     links = np.asfortranarray(np.asarray(links, dtype=np.int64).reshape(-1, 2))

@@ -11,6 +11,14 @@ from sync_model_mod import SyncMOD
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["push", "pull"])
+def sweep_kind(request, monkeypatch):
+    """Every test of this file runs with both sweep kernels (push: GBX_PULL=0, pull: GBX_PULL=1; where a run cannot use
+    the pull kernels -- damping, q = 9..12 -- the library falls back to push)."""
+    monkeypatch.setenv("GBX_PULL", "1" if request.param == "pull" else "0")
+    return request.param
+
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "mod_em_*.npz")))
 
 

@@ -8,6 +8,14 @@ from sync_model import SyncSBM
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["push", "pull"])
+def sweep_kind(request, monkeypatch):
+    """Every test of this file runs with both sweep kernels (push: GBX_PULL=0, pull: GBX_PULL=1; where a run cannot use
+    the pull kernels -- damping, q = 9..12 -- the library falls back to push)."""
+    monkeypatch.setenv("GBX_PULL", "1" if request.param == "pull" else "0")
+    return request.param
+
+
 def _run_pair(n, links, q, psi0, gr0, C0, iters, **opt):
     from graphbix_b200.engine import SbmEngine
     dc = opt.get("dc", True)
@@ -136,16 +144,15 @@ def test_several_tiles_per_cta(gpu_required, q, dc):
 
 @pytest.mark.parametrize("q,dc", [(2, True), (4, False), (8, True), (8, False), (16, True)])
 def test_pull_and_push_sweeps_agree(gpu_required, monkeypatch, q, dc):
-    """The default sweep kernels are the pull kernels (a vertex keeps its outgoing messages and rebuilds the incoming ones
-    from per-vertex records, gbx_sbm_pull.cuh); GBX_PULL=0 forces the push kernels.  Same schedule, same formulas: the two
-    agree to rounding sweep after sweep, and so do free energy and CV errors."""
+    """Two sweep kernels: push (new messages scattered into the receiver's rows; GBX_PULL=0) and pull (a vertex keeps its
+    outgoing messages and rebuilds the incoming ones from per-vertex records, gbx_sbm_pull.cuh; GBX_PULL=1).  Same
+    schedule, same formulas: the two agree to rounding sweep after sweep, and so do free energy and CV errors."""
     from graphbix_b200.engine import SbmEngine
     n, links, psi0, _ = planted_case(3000, q, 12.0, 0.1, seed=90 + q)
     gr0, C0 = assortative_init(q)
     eng = {}
     for kind in ("pull", "push"):
-        if kind == "push":
-            monkeypatch.setenv("GBX_PULL", "0")
+        monkeypatch.setenv("GBX_PULL", "1" if kind == "pull" else "0")
         e = SbmEngine(n, links, q)
         e.set_options(degreecorrection=int(dc))
         e.init(gr0, C0, psi0)
