@@ -50,9 +50,10 @@ def parse_args():
     ap.add_argument("--dc", type=int, default=1)
     ap.add_argument("--cpu-n", type=int, default=0, help="vertices of the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="independent", choices=["independent", "partitioned"],
-                    help="N > 1: one independent graph per GPU (default; a partitioned leg is reported beside it), or "
-                         "ONE graph vertex-partitioned over the GPUs as the headline")
+    ap.add_argument("--mode", default="auto", choices=["auto", "independent", "partitioned"],
+                    help="N > 1: ONE graph of N x n vertices vertex-partitioned over the GPUs is the headline (auto / "
+                         "partitioned; the independent-replica number is reported beside it), or one independent graph "
+                         "per GPU (independent)")
     ap.add_argument("--part-n", type=int, default=0, help="vertices of the partitioned graph (0 = gpus * n)")
     ap.add_argument("--part-deg", type=float, default=0.0, help="average degree of the partitioned graph (0 = deg)")
     ap.add_argument("--part-shuffle", type=int, default=1,
@@ -61,6 +62,11 @@ def parse_args():
     ap.add_argument("--part-exchange", type=int, default=1,
                     help="1: packed boundary exchange (copy engine pushes, unpack); 0: 64-B peer stores from the sweep")
     ap.add_argument("--no-partitioned-leg", action="store_true")
+    ap.add_argument("--no-configs3-leg", action="store_true",
+                    help="skip the BASELINE configs[3] leg (N = 50M, degree 20, q = 8 partitioned over the GPUs; N >= 2)")
+    ap.add_argument("--configs3-n", type=int, default=50_000_000)
+    ap.add_argument("--configs3-deg", type=float, default=20.0)
+    ap.add_argument("--configs3-steps", type=int, default=10)
     ap.add_argument("--no-convergence-leg", action="store_true")
     ap.add_argument("--no-batch-leg", action="store_true")
     ap.add_argument("--no-labeled-leg", action="store_true")
@@ -194,14 +200,57 @@ def run_reference(a):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_partitioned(a, torch, dist, world, rank, local):
-    """ONE graph, vertex-partitioned over the ranks (BASELINE.json configs[3]): every sweep stores the messages for
-    vertices of other ranks into their HBM over NVLink; totals all-reduced, theta all-gathered (NCCL) per iteration."""
+def partition_parity(a, torch, dist, world, rank, local):
+    """Driver-visible correctness of the partitioned path: a small graph run partitioned over ALL ranks against rank 0's
+    single-GPU engine from the same initial messages -- marginals (max abs), Crs / gr (max relative), free energy and
+    Bayes CV error (relative) after a few EM iterations.  Returned on every rank (the collectives need all of them)."""
+    from graphbix_b200.engine import SbmEngine
+    from graphbix_b200.engine_dist import PartEngine
+    from graphbix_b200.synth import planted_partition, random_messages
+    n, q, its = 20_000, a.q, 6
+    links, _ = planted_partition(n, q, 12.0, a.eps, seed=777, connected_only=True)
+    n = int(links.max())
+    psi0 = random_messages(links.shape[0], q, seed=778)
+    gr0 = np.ones(q) / q
+    C0 = 20 * np.eye(q) + 0.01 * np.ones((q, q))
+    part = PartEngine(n, links, q)
+    part.set_options(degreecorrection=a.dc, priorlearning=1, learningrate=0.3)
+    part.init(gr0, C0, psi0)
+    part.iterate(its)
+    PSI_p = part.marginals_all()
+    sp = part.state()
+    rp = part.finalize()
+    kind = "pull" if part.pull else "push"
+    part.close()
+    out = {"n_vertices": n, "q": q, "iterations": its, "ranks": world, "sweep_kernels": kind}
+    if rank == 0:
+        ref = SbmEngine(n, links, q, device=local)
+        ref.set_options(degreecorrection=a.dc, priorlearning=1, learningrate=0.3)
+        ref.init(gr0, C0, psi0)
+        ref.iterate(its, read_conv=False)
+        sr = ref.state()
+        rr = ref.finalize()
+        ref.close()
+        out.update({"parity_max_abs": float(np.abs(PSI_p - sr["PSI"]).max()),
+                    "crs_max_rel": float(np.abs(sp["Crs"] / sr["Crs"] - 1).max()),
+                    "gr_max_rel": float(np.abs(sp["gr"] / sr["gr"] - 1).max()),
+                    "fe_rel": abs(rp.FE / rr.FE - 1), "cvbayes_rel": abs(rp.CVBayes / rr.CVBayes - 1),
+                    "reference": "single-GPU engine on rank 0 (push sweep kernels unless GBX_PULL=1)"})
+    return out
+
+
+def run_partitioned(a, torch, dist, world, rank, local, n=None, deg=None, steps=None, warmup=None):
+    """ONE graph, vertex-partitioned over the ranks (BASELINE.json configs[3]).  With the pull sweep kernels (default)
+    every rank stores the per-vertex records of its vertices into every rank's copy over NVLink from inside the sweep
+    kernel and the next sweep gathers locally; the per-iteration collectives are two small NCCL all-reduces (totals,
+    S_theta).  GBX_PULL=0: push kernels, boundary MESSAGES packed / copied / unpacked, theta all-gathered."""
     from graphbix_b200.engine_dist import PartEngine
     from graphbix_b200.synth import planted_partition_device
     dev = torch.device("cuda", local)
-    n = a.part_n or world * a.n
-    deg = a.part_deg or a.deg
+    n = n or a.part_n or world * a.n
+    deg = deg or a.part_deg or a.deg
+    steps = steps or a.steps
+    warmup = a.warmup if warmup is None else warmup
     t0 = time.perf_counter()
     if rank == 0:
         links, _ = planted_partition_device(n, a.q, deg, a.eps, seed=4242, device=dev, shuffle=bool(a.part_shuffle))
@@ -229,18 +278,19 @@ def run_partitioned(a, torch, dist, world, rank, local):
     del links
     torch.cuda.empty_cache()
     t_build = time.perf_counter() - t0
-    eng.set_options(degreecorrection=a.dc, priorlearning=1, learningrate=0.3, itrmax=a.steps)
+    eng.set_options(degreecorrection=a.dc, priorlearning=1, learningrate=0.3, itrmax=steps)
     eng.set_exchange(a.part_exchange)
     gr0 = np.ones(a.q) / a.q
     C0 = 20 * np.eye(a.q) + 0.01 * np.ones((a.q, a.q))
     eng.init(gr0, C0, None, seed=99)
-    eng.iterate(a.warmup)
+    pull = eng.pull
+    eng.iterate(warmup)
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    eng.iterate(a.steps)
+    eng.iterate(steps)
     ev1.record()
     torch.cuda.synchronize()
     dist.barrier()
@@ -253,23 +303,30 @@ def run_partitioned(a, torch, dist, world, rank, local):
     prof = eng.profile_summary()
     if prof and rank == 0:
         print("partitioned step profile (ms per iteration, incl. warm-up iterations):",
-              {k: round(v / (a.steps + a.warmup), 4) for k, v in prof.items()}, file=sys.stderr)
+              {k: round(v / (steps + warmup), 4) for k, v in prof.items()}, file=sys.stderr)
     eng.close()
-    qm = (a.q + 3) // 4 * 4                      # message rows are padded to whole 32-B sectors
-    boundary = cut * K / world * qm * 8          # bytes that leave (and enter) each GPU per sweep, on average
-    return {"value": K * a.steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / a.steps, "n_vertices": n,
-            "boundary_bytes_per_gpu_per_step": boundary,
-            "nvlink_egress_gbs_if_exchange_alone": boundary / (ms / a.steps * 1e-3) / 1e9,
-            "nvlink_note": ("lower bound of the link rate the exchange sustains (whole iteration time in the denominator); "
-                            "NCCL all-to-all alone moves this volume at 586 GB/s per GPU on 8 B200 "
-                            "(profiles/r01_a2a_probe_8gpu.txt)"),
+    qm = (a.q + 3) // 4 * 4                      # message / record rows are padded to whole 32-B sectors
+    if pull:
+        # every vertex's record goes to every other rank once per sweep
+        boundary = (world - 1) * (n / world) * qm * 8
+        exchange = "per-vertex records stored into every rank's copy by the sweep kernel (peer stores over NVLink)"
+        what = ("one graph vertex-partitioned over the GPUs, pull sweep kernels: one record per vertex and peer rank crosses "
+                "NVLink every sweep; two small NCCL all-reduces (totals, S_theta) per iteration")
+    else:
+        boundary = cut * K / world * qm * 8      # one message per cut edge and direction
+        exchange = ("packed runs pushed by the copy engine, unpacked by the owner" if a.part_exchange else
+                    "64-B peer stores from the sweep kernel")
+        what = ("one graph vertex-partitioned over the GPUs, push sweep kernels: boundary messages cross NVLink every "
+                "sweep, NCCL all-reduce of the totals and all-gather of theta per iteration")
+    return {"value": K * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "n_vertices": n,
+            "sweep_kernels": "pull" if pull else "push",
+            "nvlink_bytes_per_gpu_per_step": boundary,
+            "nvlink_egress_gbs_lower_bound": boundary / (ms / steps * 1e-3) / 1e9,
+            "nvlink_note": ("bytes that leave each GPU per sweep / whole iteration time: a lower bound of the link rate the "
+                            "exchange sustains (peer copy 770 GB/s per direction, B200_PROFILING.md)"),
             "avg_degree": deg, "directed_edges": K, "directed_edges_rank0": slots, "cut_fraction": cut,
             "vertex_numbering": "random" if a.part_shuffle else "by planted group",
-            "exchange": "packed runs pushed by the copy engine, unpacked by the owner" if a.part_exchange else
-                        "64-B peer stores from the sweep kernel",
-            "generate_s": t_gen, "build_s": t_build, "residual_after": resid,
-            "what": ("one graph vertex-partitioned over the GPUs: boundary messages cross NVLink every sweep, NCCL "
-                     "all-reduce of the totals and all-gather of theta per iteration")}
+            "exchange": exchange, "generate_s": t_gen, "build_s": t_build, "residual_after": resid, "what": what}
 
 
 def run_convergence(a, torch, dist, world, rank, local):
@@ -439,6 +496,8 @@ def run_ours(a):
     from graphbix_b200.synth import planted_partition, random_messages
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.mode == "auto":
+        a.mode = "partitioned" if world > 1 else "independent"
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
@@ -495,6 +554,7 @@ def run_ours(a):
     sampler.stop()
     sweep_bytes = eng.sweep_bytes
     dev_bytes = eng.device_bytes
+    sweep_kind = eng.sweep_kind
     eng.close()
 
     # ---- end to end through EM() with host buffers ----
@@ -513,19 +573,40 @@ def run_ours(a):
     t_e2e = time.perf_counter() - t0
     e2e_parts = dict(eng2.timings)
     eng2.close()
+    # the same call with `links` in ordinary pageable memory, which is what a Julia `ccall` hands over
+    links_page = np.asfortranarray(links).copy(order="F")
+    barrier()
+    t0 = time.perf_counter()
+    EM(n, a.q, links_page, n, (gr0, C0), bool(a.dc), a.steps, True, 0.3, seed=55 + rank, BPconvthreshold=0.0, device=local)
+    torch.cuda.synchronize()
+    t_e2e_page = time.perf_counter() - t0
     h2d = links.nbytes
     d2h = out[2].nbytes + out[1].nbytes + out[0].nbytes
 
-    t = torch.tensor([ms, sweep_ms, t_e2e], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, sweep_ms, t_e2e, t_e2e_page], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, sweep_ms, t_e2e = (float(x) for x in t.tolist())
+    ms, sweep_ms, t_e2e, t_e2e_page = (float(x) for x in t.tolist())
     value = world * K * a.steps / (ms * 1e-3)
     e2e_value = world * K * a.steps / t_e2e
     peak, peak_src = measured_peak_gbs()
     achieved = sweep_bytes / (sweep_ms * 1e-3) / 1e9
-    traffic, traffic_src = recorded_traffic(a)
+    traffic, traffic_src = recorded_traffic(a) if sweep_kind == "push" else (None, None)
     part = None
+    parity = None
+    configs3 = None
+    if world > 1 and not a.no_partitioned_leg:
+        try:
+            parity = partition_parity(a, torch, dist, world, rank, local)
+        except Exception as e:  # noqa: BLE001
+            parity = {"error": f"{type(e).__name__}: {e}"[:400]}
+        if not a.no_configs3_leg:
+            try:   # BASELINE configs[3]: N = 50M, degree 20, q = 8 over the GPUs of the box (strong scaling in N_gpus)
+                configs3 = run_partitioned(a, torch, dist, world, rank, local, n=a.configs3_n, deg=a.configs3_deg,
+                                           steps=a.configs3_steps, warmup=2)
+            except Exception as e:  # noqa: BLE001
+                configs3 = {"error": f"{type(e).__name__}: {e}"[:400]}
+            torch.cuda.empty_cache()
     if (world > 1 and not a.no_partitioned_leg) or a.mode == "partitioned":
         if a.mode == "partitioned":
             part = run_partitioned(a, torch, dist, world, rank, local)
@@ -569,9 +650,13 @@ def run_ours(a):
                            "step": "one EM iteration = BP sweep + update_Crs + update_theta"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / a.steps,
                         "d2h_bytes_per_step": d2h / a.steps, "seconds": t_e2e, "breakdown_s": e2e_parts,
+                        "pageable_value": world * K * a.steps / t_e2e_page, "pageable_seconds": t_e2e_page,
+                        "pageable_note": "the same EM() call with `links` in ordinary (unpinned) host memory",
                         "what": "EM() with host buffers: H2D of links, CSR build, random initial messages (device), steps iterations, free energy + CV, D2H of PSI / gr / Crs"},
                 "gpu_launches": launches, "clocks": sampler.summary(),
-                "roofline": {"bound": "hbm", "kernel": "sbm_vertex_kernel<8,SWEEP> (BP sweep)", "achieved": achieved,
+                "roofline": {"bound": "hbm",
+                             "kernel": (f"sbm_vertex_kernel<q={a.q},SWEEP> (push BP sweep)" if sweep_kind == "push" else
+                                        f"sbm_pull_kernel<q={a.q},SWEEP> (pull BP sweep)"), "achieved": achieved,
                              "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                              "traffic_source": traffic_src, "peak_source": peak_src, "ms_per_launch": sweep_ms, "algorithmic_bytes": sweep_bytes,
                              "sweep_updates_per_sec": K / (sweep_ms * 1e-3)}}
@@ -581,7 +666,13 @@ def run_ours(a):
             line["batched_graphs"] = batch
         if labeled is not None:
             line["labeled_graphs"] = labeled
+        if parity is not None:
+            line["partition_parity"] = parity
+        if configs3 is not None:
+            line["configs3_50M"] = configs3
         if part is not None:
+            if parity is not None:
+                part["parity_max_abs"] = parity.get("parity_max_abs")
             line["partitioned"] = part
             if a.mode == "partitioned":
                 line["independent"] = {"value": value, "ms_per_step": ms / a.steps}
