@@ -113,23 +113,26 @@ __device__ __forceinline__ double mul_pow2(double x, int n) {
 }
 
 // ---- shared memory of a pull CTA -------------------------------------------------------------------------------------
-struct PStage {  // one stage of the streamed ring (bytes; every piece 16-byte aligned, the messages 1024-byte aligned)
-  static constexpr size_t msg_off = 0;                                        // TILE_E own message rows, swizzled
-  static constexpr size_t col_off = msg_off + (size_t)TILE_E * ROWB;         // TILE_E + 4 neighbour ids
+// Shared memory of a pull CTA (bytes).  Message stages first (1024-byte aligned: swizzle atoms), then the small per-tile
+// arrays of every stage (16-byte aligned pieces), the gathered records (P_R stages; after phase A a slot's row holds its
+// factor T, later its M-step operand: the record is dead by then), per-vertex scratch and the mbarriers.
+struct PStage {  // the small arrays of one streamed stage
+  static constexpr size_t col_off = 0;                                        // TILE_E + 4 neighbour ids
   static constexpr size_t deg_off = col_off + (size_t)(TILE_E + 4) * 4;      // TILE_E + 4 neighbour degrees (float)
   static constexpr size_t rp_off = deg_off + (size_t)(TILE_E + 4) * 4;       // TV + 8 row pointers
   static constexpr size_t pi_off = rp_off + (size_t)(TV + 8) * 4;            // TV + 4 prior-table rows
-  static constexpr size_t old_off = pi_off + (size_t)(TV + 4) * 4;           // TV * Q + 2 old marginals
-  static constexpr size_t thc_off = old_off + (size_t)(TV * Q + 2) * 8;      // TV + 2 current thetas
+  static constexpr size_t thc_off = pi_off + (size_t)(TV + 4) * 4;           // TV + 2 current thetas
   static constexpr size_t thp_off = thc_off + (size_t)(TV + 2) * 8;          // TV + 2 thetas of the previous sweep
   static constexpr size_t desc_off = thp_off + (size_t)(TV + 2) * 8;         // the tile descriptor (int4)
   static constexpr size_t lv_off = desc_off + 16;                            // TILE_E + 16: vertex (inside the tile) of a slot
-  static constexpr size_t bytes = ((lv_off + (size_t)TILE_E + 16 + 1023) / 1024) * 1024;
+  static constexpr size_t bytes = ((lv_off + (size_t)TILE_E + 16 + 15) / 16) * 16;
 };
 struct PullSmem {
-  static constexpr size_t gat_off = P_S * PStage::bytes;                              // P_R x TILE_E gathered records
-  static constexpr size_t t_off = gat_off + (size_t)P_R * TILE_E * ROWB;             // per-slot factors T
-  static constexpr size_t u_off = t_off + (size_t)TILE_E * QS * 8;
+  static constexpr size_t msg_bytes = (size_t)TILE_E * ROWB;                         // one stage of message rows
+  static constexpr size_t msg_off = 0;                                                // P_S stages
+  static constexpr size_t gat_off = msg_off + P_S * msg_bytes;                       // P_R x TILE_E gathered records
+  static constexpr size_t small_off = gat_off + (size_t)P_R * msg_bytes;             // P_S x PStage
+  static constexpr size_t u_off = ((small_off + P_S * PStage::bytes + 15) / 16) * 16;
   static constexpr size_t ff_off = u_off + (size_t)TV * Q * 8;
   static constexpr size_t scratch_off = ff_off + (size_t)TV * 8;
   static constexpr size_t dr_off = scratch_off + (size_t)(NT > 64 * MB * MB ? NT : 64 * MB * MB) * 8;
@@ -142,7 +145,7 @@ struct PullSmem {
 #ifdef GBX_FORCE_CTAS
 constexpr int PULL_MIN_CTAS = GBX_FORCE_CTAS;
 #else
-constexpr int PULL_MIN_CTAS = (PullSmem::total + 1024 <= 75 * 1024) ? 3 : ((PullSmem::total + 1024 <= 113 * 1024) ? 2 : 1);
+constexpr int PULL_MIN_CTAS = (PullSmem::total + 1024 <= 56 * 1024) ? 4 : (PullSmem::total + 1024 <= 75 * 1024) ? 3 : ((PullSmem::total + 1024 <= 113 * 1024) ? 2 : 1);
 #endif
 
 struct PullArgs {
@@ -185,6 +188,10 @@ __device__ __forceinline__ void write_swz(char* base, int row, const double (&m)
 #pragma unroll
   for (int c = 0; c < (Q + 1) / 2; ++c)
     *reinterpret_cast<double2*>(base + swz(row * ROWB + c * 16)) = make_double2(m[2 * c], (2 * c + 1 < Q) ? m[2 * c + 1] : 0.0);
+}
+
+__device__ __forceinline__ double* swz_elem(char* base, int row, int t) {
+  return reinterpret_cast<double*>(base + swz(row * ROWB + (t >> 1) * 16) + (t & 1) * 8);
 }
 
 // The message i -> j of the previous sweep, rebuilt from the record of i and the message j sent to i one sweep earlier:
@@ -243,7 +250,6 @@ __global__ void __launch_bounds__(P_NT, PULL_MIN_CTAS)
   // 1024-byte alignment (swizzle atoms) by an offset, not through an integer cast: the pointer keeps its shared-memory
   // address space and the accesses below compile to LDS / STS rather than generic loads and stores
   char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  double* Tsm = reinterpret_cast<double*>(smem + PullSmem::t_off);
   double* Usm = reinterpret_cast<double*>(smem + PullSmem::u_off);
   double* ffS = reinterpret_cast<double*>(smem + PullSmem::ff_off);
   double* scratch = reinterpret_cast<double*>(smem + PullSmem::scratch_off);
@@ -285,31 +291,29 @@ __global__ void __launch_bounds__(P_NT, PULL_MIN_CTAS)
       if (lane == 0) {   // one lane waits for the stage and issues its copies; the others meet it at the __syncwarp below
         if (j >= P_S) mbar_wait_t<200>(&empty_s[s], ((j / P_S) & 1) ^ 1);
         const int4 td = a.tiles[bid + j * G];
-        char* sb = smem + (size_t)s * PStage::bytes;
+        char* sb = smem + PullSmem::small_off + (size_t)s * PStage::bytes;
+        char* mb = smem + PullSmem::msg_off + (size_t)s * PullSmem::msg_bytes;
         *reinterpret_cast<int4*>(sb + PStage::desc_off) = td;
         const int v0 = td.x, nv = td.y, e0 = td.z, ne = td.w;
         unsigned long long* bar = &full_s[s];
         // sizes of the copies (16-byte windows rounded outwards), announced to the barrier before any copy is issued
         const int ea0 = e0 & ~3, va0 = v0 & ~3, ta0 = v0 & ~1;
-        const long long d0 = (long long)v0 * Q, da0 = d0 & ~1ll;
         const unsigned nbox = (unsigned)((ne + 31) / 32);
         const unsigned nb_col = ne > 0 ? (unsigned)(((ne + (e0 - ea0)) * 4 + 15) & ~15) : 0u;
         const unsigned nb_deg = (MODEL == MODEL_SBM && a.dc_model) ? nb_col : 0u;
         const unsigned nb_rp = (unsigned)(((nv + 1 + (v0 - va0)) * 4 + 15) & ~15);
         const unsigned nb_pi = (unsigned)(((nv + (v0 - va0)) * 4 + 15) & ~15);
-        const unsigned nb_old = (MODE == MODE_SWEEP) ? (unsigned)((((long long)nv * Q + (d0 - da0)) * 8 + 15) & ~15ll) : 0u;
         const unsigned nb_th = (THETA && a.dc_model) ? (unsigned)(((nv + (v0 - ta0)) * 8 + 15) & ~15) : 0u;
         const int la0 = e0 & ~15;
         const unsigned nb_lv = ne > 0 ? (unsigned)((ne + (e0 - la0) + 15) & ~15) : 0u;
-        mbar_arrive_expect_tx(bar, nbox * 32u * ROWB + nb_col + nb_deg + nb_rp + nb_pi + nb_old + nb_th + (RECON ? nb_th : 0u) + nb_lv);
+        mbar_arrive_expect_tx(bar, nbox * 32u * ROWB + nb_col + nb_deg + nb_rp + nb_pi + nb_th + (RECON ? nb_th : 0u) + nb_lv);
         for (unsigned b = 0; b < nbox; ++b)   // message rows, 32 at a time (rows past the buffer's end read as zeros)
-          tma_load_2d(sb + PStage::msg_off + (size_t)b * 32 * ROWB, &tmap, bar, 0, e0 + (int)b * 32);
+          tma_load_2d(mb + (size_t)b * 32 * ROWB, &tmap, bar, 0, e0 + (int)b * 32);
         if (nb_col) bulk_load(sb + PStage::col_off, a.col + ea0, nb_col, bar);
         if (nb_lv) bulk_load(sb + PStage::lv_off, a.slot_lv + la0, nb_lv, bar);
         if (nb_deg) bulk_load(sb + PStage::deg_off, a.coldeg + ea0, nb_deg, bar);
         bulk_load(sb + PStage::rp_off, a.rowptr + va0, nb_rp, bar);
         bulk_load(sb + PStage::pi_off, a.pidx + va0, nb_pi, bar);
-        if (nb_old) bulk_load(sb + PStage::old_off, a.PSI + da0, nb_old, bar);
         if (nb_th) {
           bulk_load(sb + PStage::thc_off, a.theta_cur + ta0, nb_th, bar);
           if (RECON) bulk_load(sb + PStage::thp_off, a.theta_prev + ta0, nb_th, bar);
@@ -336,26 +340,25 @@ __global__ void __launch_bounds__(P_NT, PULL_MIN_CTAS)
   const int vwarp = (tid & ~31) / LV;
   const int lane = tid & 31;
 
-  // Gathers of tile jj's records into gather stage jj % P_R, by all consumer threads: unit u = tid + NT i of the tile's
-  // ne * CH 16-byte units (CH consecutive lanes fetch one record).  The stage was last read in phase A of tile jj - 2,
-  // which every consumer warp has left (two consumer barriers ago) when this is called at the top of tile jj - 1.
+  // Gathers of tile jj's records into gather stage jj % P_R.  Every warp fetches the rows of its own 32 slots (CH
+  // consecutive lanes one record): a stage's rows double as the slot's factor / M-step operand until the end of phase C
+  // of tile jj - P_R, and with warp-private rows the overwrite is ordered by the warp's own program order (the other
+  // warps read a row only in phase B, two consumer barriers earlier).
   auto issue_gather = [&](int jj) {
     if constexpr (RECON) {
       const int sg = jj % P_S, rg = jj % P_R;
       mbar_wait(&full_s[sg], (jj / P_S) & 1);   // its neighbour ids have landed
-      const char* sbg = smem + (size_t)sg * PStage::bytes;
+      const char* sbg = smem + PullSmem::small_off + (size_t)sg * PStage::bytes;
       const int4 tg = *reinterpret_cast<const int4*>(sbg + PStage::desc_off);
       const int* colS = reinterpret_cast<const int*>(sbg + PStage::col_off) + (tg.z & 3);
-      char* gbg = smem + PullSmem::gat_off + (size_t)rg * TILE_E * ROWB;
+      char* gbg = smem + PullSmem::gat_off + (size_t)rg * PullSmem::msg_bytes;
       const char* rec = reinterpret_cast<const char*>(a.rec_old);
-      const int nu = tg.w * CH;
+      const int wrow = tid & ~31, ln = tid & 31;
 #pragma unroll
       for (int i = 0; i < CH; ++i) {
-        const int u = tid + NT * i;
-        if (u < nu) {
-          const int row = u / CH, c = u % CH;
-          cp_async_16(gbg + swz(row * ROWB + c * 16), rec + ((size_t)colS[row] * ROWB + (size_t)c * 16));
-        }
+        const int ul = ln + 32 * i;
+        const int row = wrow + ul / CH, c = ul % CH;
+        if (row < tg.w) cp_async_16(gbg + swz(row * ROWB + c * 16), rec + ((size_t)colS[row] * ROWB + (size_t)c * 16));
       }
       cp_async_mbar_arrive_noinc(&full_g[rg]);
     }
@@ -364,8 +367,8 @@ __global__ void __launch_bounds__(P_NT, PULL_MIN_CTAS)
 
   for (int j = 0; j < nt; ++j) {
     const int s = j % P_S, r = j % P_R;
-    char* sb = smem + (size_t)s * PStage::bytes;
-    char* gb = smem + PullSmem::gat_off + (size_t)r * TILE_E * ROWB;
+    char* sb = smem + PullSmem::small_off + (size_t)s * PStage::bytes;
+    char* gb = smem + PullSmem::gat_off + (size_t)r * PullSmem::msg_bytes;   // records, then factors T, then M-step rows
     if (j + P_R - 1 < nt) issue_gather(j + P_R - 1);
     mbar_wait(&full_s[s], (j / P_S) & 1);
     if constexpr (RECON) mbar_wait(&full_g[r], (j / P_R) & 1);
@@ -373,14 +376,16 @@ __global__ void __launch_bounds__(P_NT, PULL_MIN_CTAS)
     const int v0 = td.x, nv = td.y, e0 = td.z, ne = td.w;
     const int* rpS = reinterpret_cast<const int*>(sb + PStage::rp_off) + (v0 & 3);
     const int* piS = reinterpret_cast<const int*>(sb + PStage::pi_off) + (v0 & 3);
-    const double* oldS = reinterpret_cast<const double*>(sb + PStage::old_off) + (((long long)v0 * Q) & 1);
     const double* thcS = reinterpret_cast<const double*>(sb + PStage::thc_off) + (v0 & 1);
     const double* thpS = reinterpret_cast<const double*>(sb + PStage::thp_off) + (v0 & 1);
     const unsigned char* lvS = reinterpret_cast<const unsigned char*>(sb + PStage::lv_off) + (e0 & 15);
-    char* msgS = sb + PStage::msg_off;
+    char* msgS = smem + PullSmem::msg_off + (size_t)s * PullSmem::msg_bytes;
 
-    // prior factors of this tile's first round of vertices (an L2-resident table row per vertex)
+    // prior factors of this tile's first round of vertices (an L2-resident table row per vertex) and their old marginals:
+    // both loads are in flight through phase A
     Prior pr = load_prior<MODE>(a, (vlane < nv) ? piS[vlane] : 0, t);
+    double old0 = 0.0;
+    if (MODE == MODE_SWEEP && vlane < nv && tl) old0 = a.PSI[(size_t)(v0 + vlane) * Q + t];
 
     // ---- phase A: one thread per edge slot -- incoming message, its factor T ----
     double T[Q];
@@ -406,8 +411,7 @@ __global__ void __launch_bounds__(P_NT, PULL_MIN_CTAS)
         }
       }
       edge_factor(psi, sc, T);
-#pragma unroll
-      for (int k = 0; k < Q; ++k) Tsm[tid * QS + k] = T[k];
+      write_swz(gb, tid, T);   // over the record it was rebuilt from
     }
     consumer_sync();
 
@@ -418,37 +422,38 @@ __global__ void __launch_bounds__(P_NT, PULL_MIN_CTAS)
       const bool valid = v < nv;
       if (vb > 0) pr = load_prior<MODE>(a, valid ? piS[v] : 0, t);
       const int b = valid ? rpS[v] - e0 : 0, e = valid ? rpS[v + 1] - e0 : 0;
-      const double old = (MODE == MODE_SWEEP && valid && tl) ? oldS[v * Q + t] : 0.0;
-      const double* p = &Tsm[b * QS + tt];
-      const double* pe = &Tsm[e * QS + tt];
+      double old = old0;
+      if (vb > 0) old = (MODE == MODE_SWEEP && valid && tl) ? a.PSI[(size_t)(v0 + v) * Q + t] : 0.0;
+      auto Tat = [&](int k) { return *swz_elem(gb, k, tt); };   // factor of slot k, this lane's component
+      int k = b;
       double m1 = 1.0, m2 = 1.0;
       int K = 0;
       if (!__any_sync(0xffffffffu, e - b > c_P.safe_deg)) {
-        for (; p + QS < pe; p += 2 * QS) {
-          m1 *= p[0];
-          m2 *= p[QS];
+        for (; k + 1 < e; k += 2) {
+          m1 *= Tat(k);
+          m2 *= Tat(k + 1);
         }
-        if (p < pe) m1 *= p[0];
+        if (k < e) m1 *= Tat(k);
         m1 *= m2;
       } else {
-        while (p + 7 * QS < pe) {
-          m1 *= p[0];
-          m2 *= p[QS];
-          m1 *= p[2 * QS];
-          m2 *= p[3 * QS];
-          m1 *= p[4 * QS];
-          m2 *= p[5 * QS];
-          m1 *= p[6 * QS];
-          m2 *= p[7 * QS];
-          p += 8 * QS;
+        while (k + 7 < e) {
+          m1 *= Tat(k);
+          m2 *= Tat(k + 1);
+          m1 *= Tat(k + 2);
+          m2 *= Tat(k + 3);
+          m1 *= Tat(k + 4);
+          m2 *= Tat(k + 5);
+          m1 *= Tat(k + 6);
+          m2 *= Tat(k + 7);
+          k += 8;
           renorm(m1, K);
           renorm(m2, K);
         }
-        for (; p + QS < pe; p += 2 * QS) {
-          m1 *= p[0];
-          m2 *= p[QS];
+        for (; k + 1 < e; k += 2) {
+          m1 *= Tat(k);
+          m2 *= Tat(k + 1);
         }
-        if (p < pe) m1 *= p[0];
+        if (k < e) m1 *= Tat(k);
         renorm(m1, K);
         renorm(m2, K);
         m1 *= m2;
@@ -494,8 +499,10 @@ __global__ void __launch_bounds__(P_NT, PULL_MIN_CTAS)
 #pragma unroll
           for (int k = 0; k < Q; ++k) z = fma(w[k], T[k], z);
           const double kz = sc * fast_rcp(z);
+          double ar[Q];
 #pragma unroll
-          for (int k = 0; k < Q; ++k) Tsm[tid * QS + k] = w[k] * kz;
+          for (int k = 0; k < Q; ++k) ar[k] = w[k] * kz;
+          write_swz(gb, tid, ar);   // the slot's row once more: a / Z for the M-step
         } else {
           double psi[Q];
           read_swz(msgS, tid, psi);
@@ -508,12 +515,8 @@ __global__ void __launch_bounds__(P_NT, PULL_MIN_CTAS)
       if constexpr (MODEL == MODEL_SBM) {
         __syncwarp();
         const int wbase = tid & ~31;
-        mstep_accumulate(macc, &Tsm[wbase * QS],
-                         [&](int grp, int k, int comp) {
-                           const int row = wbase + 4 * grp + k;
-                           return *reinterpret_cast<const double*>(msgS + swz(row * ROWB + (comp >> 1) * 16) + (comp & 1) * 8);
-                         },
-                         ne - wbase);
+        mstep_accumulate_ab(macc, [&](int grp, int k, int comp) { return *swz_elem(gb, wbase + 4 * grp + k, comp); },
+                            [&](int grp, int k, int comp) { return *swz_elem(msgS, wbase + 4 * grp + k, comp); }, ne - wbase);
         __syncwarp();
       } else {
         acc.mod += mod_term;

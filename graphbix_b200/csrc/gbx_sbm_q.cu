@@ -292,6 +292,33 @@ __device__ __forceinline__ void mstep_accumulate_impl(MstepAcc& g, const double*
       for (int n = 0; n < MB; ++n) dmma884(g.c[(m * MB + n) * 2], g.c[(m * MB + n) * 2 + 1], av[m], bv[n]);
   }
 }
+// The same with both operands fetched through callables (the pull kernel keeps them in swizzled tiles).
+template <bool FULL, typename AGet, typename BGet>
+__device__ __forceinline__ void mstep_accumulate_ab_impl(MstepAcc& g, AGet aget, BGet bget, int nrows) {
+  const int lane = threadIdx.x & 31;
+  const int k = lane & 3, cidx = lane >> 2;
+#pragma unroll
+  for (int grp = 0; grp < 8; ++grp) {
+    const bool live = FULL || (4 * grp + k < nrows);
+    double av[MB], bv[MB];
+#pragma unroll
+    for (int m = 0; m < MB; ++m) {
+      const int comp = m * 8 + cidx;
+      const bool ok = live && (Q % 8 == 0 || comp < Q);
+      av[m] = ok ? aget(grp, k, comp) : 0.0;
+      bv[m] = ok ? bget(grp, k, comp) : 0.0;
+    }
+#pragma unroll
+    for (int m = 0; m < MB; ++m)
+#pragma unroll
+      for (int n = 0; n < MB; ++n) dmma884(g.c[(m * MB + n) * 2], g.c[(m * MB + n) * 2 + 1], av[m], bv[n]);
+  }
+}
+template <typename AGet, typename BGet>
+__device__ __forceinline__ void mstep_accumulate_ab(MstepAcc& g, AGet aget, BGet bget, int nrows) {
+  if (nrows >= 32) mstep_accumulate_ab_impl<true>(g, aget, bget, 32);
+  else if (nrows > 0) mstep_accumulate_ab_impl<false>(g, aget, bget, nrows);
+}
 template <typename BGet>
 __device__ __forceinline__ void mstep_accumulate(MstepAcc& g, const double* arow, BGet bget, int nrows) {
   if (nrows >= 32) mstep_accumulate_impl<true>(g, arow, bget, 32);
