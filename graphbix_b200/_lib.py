@@ -22,7 +22,7 @@ class GbxError(RuntimeError):
 class SbmOptions(C.Structure):
     _fields_ = [("degreecorrection", C.c_int), ("priorlearning", C.c_int), ("learningrate", C.c_double),
                 ("maxCrs", C.c_double), ("itrmax", C.c_int), ("bp_conv_threshold", C.c_double),
-                ("damping", C.c_double), ("check_every", C.c_int)]
+                ("damping", C.c_double), ("check_every", C.c_int), ("mstep_exact", C.c_int)]
 
 
 class SbmResult(C.Structure):

@@ -170,6 +170,7 @@ int em_iteration(gbx_sbm* h, bool want_residual = false) {
   GBX_TRY(op->prepare(h, 0, 0));              // gr clamp, h = update_h()                        sbm.jl:102
   GBX_TRY(op->vertex_pass(h, MODE_SWEEP));    // messages, marginals, residual, M-step statistics sbm.jl:103-136
   h->cur ^= 1;
+  if (h->opt.mstep_exact) GBX_TRY(op->mstep_exact(h));   // statistics from the new messages of both directions
   GBX_TRY(op->local_totals(h, MODE_SWEEP));
   GBX_TRY(op->apply_totals(h, MODE_SWEEP));   // BPconv, gr, Crs = update_Crs()                  sbm.jl:120-123, 137-147
   if (want_residual) GBX_TRY(queue_residual(h));
@@ -268,6 +269,7 @@ void gbx_sbm_default_options(gbx_sbm_options* opt) {
   opt->bp_conv_threshold = 0.000001;
   opt->damping = 1.0;
   opt->check_every = 1;
+  opt->mstep_exact = 0;
 }
 
 // Pinned mirrors of SbmState are recycled too (cudaMallocHost costs about a millisecond).
@@ -617,6 +619,7 @@ int gbx_sbm_set_options(gbx_sbm* h, const gbx_sbm_options* opt) {
   if (!(opt->damping > 0.0 && opt->damping <= 1.0)) return fail_invalid("damping must be in (0,1]");
   if (!(opt->learningrate >= 0.0 && opt->learningrate <= 1.0)) return fail_invalid("learningrate must be in [0,1]");
   if (opt->itrmax < 0) return fail_invalid("itrmax must be >= 0");
+  if (opt->mstep_exact && h->stepped) return fail_invalid("mstep_exact is not available on partitioned handles");
   h->opt = *opt;
   if (h->opt.check_every < 1) h->opt.check_every = 1;
   return GBX_OK;

@@ -197,6 +197,7 @@ struct SbmOps {
   int (*init_model)(gbx_sbm* h);  // per-vertex prior-table rows of the initial state
   int (*unpack)(gbx_sbm* h);      // packed exchange: received rows -> message buffer
   int (*release)(gbx_sbm* h);     // the handle is going away: give up the shared __constant__ parameter block
+  int (*mstep_exact)(gbx_sbm* h); // M-step statistics from the current messages of both directions (after a sweep)
   int pull_ok;                    // this q has pull kernels (message rows of 32, 64 or 128 bytes)
   int (*pull_setup)(gbx_sbm* h);  // tensor maps, neighbour degrees
   int (*pull_load)(gbx_sbm* h, const double* src_dev, uint64_t seed);   // initial messages into both layouts

@@ -1488,6 +1488,53 @@ __global__ void k_init_pidx(const int* __restrict__ rowptr, int n, int by_degree
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// update_Crs statistics (sbm.jl:128-136) from the CURRENT messages of both directions, for runs that ask for the
+// reference's pairing (gbx_sbm_options::mstep_exact): G += (x_e / Z) (x) x_rev(e) over all directed slots, where
+// x_e is the message stored at slot e and Z = x_e' Crs x_rev(e) (the theta factors cancel).  Works on either
+// layout: both keep a message and its reverse at slots e and rev[e] of one buffer.
+__global__ void __launch_bounds__(NT) sbm_mstep_exact_kernel(const double* __restrict__ msg, const int* __restrict__ rev,
+                                                             long long K, double* mpart, const SbmState* st, int it) {
+  __shared__ double rowA[NT * QS];
+  __shared__ double rowB[NT * QS];
+  __shared__ double scratch[(NT > 64 * MB * MB) ? NT : 64 * MB * MB];
+  if (skip_iteration(st, it)) return;
+  const int tid = threadIdx.x;
+  MstepAcc macc;
+#pragma unroll
+  for (int k = 0; k < MB * MB * 2; ++k) macc.c[k] = 0.0;
+  for (long long base = (long long)blockIdx.x * NT; base < K; base += (long long)gridDim.x * NT) {
+    const long long e = base + tid;
+    if (e < K) {
+      double a[Q], b[Q];
+      load_msg<Q, QM>(msg, e, a);
+      load_msg<Q, QM>(msg, (long long)rev_slot(rev[e]), b);
+      double z = 0.0;
+#pragma unroll
+      for (int t = 0; t < Q; ++t) {
+        double acc = 0.0;
+#pragma unroll
+        for (int s = 0; s < Q; ++s) acc = fma(a[s], c_P.C[s * Q + t], acc);
+        z = fma(acc, b[t], z);
+      }
+      const double kz = fast_rcp(z);
+#pragma unroll
+      for (int k = 0; k < Q; ++k) {
+        rowA[tid * QS + k] = a[k] * kz;
+        rowB[tid * QS + k] = b[k];
+      }
+    }
+    __syncwarp();
+    const int wbase = tid & ~31;
+    const double* bb = &rowB[wbase * QS];
+    const long long left = K - base - wbase;
+    mstep_accumulate(macc, &rowA[wbase * QS], [&](int grp, int k, int comp) { return bb[(4 * grp + k) * QS + comp]; },
+                     (int)(left > 32 ? 32 : (left < 0 ? 0 : left)));
+    __syncwarp();
+  }
+  store_mstep_partials(macc, scratch, mpart + (size_t)blockIdx.x * Q * Q);
+}
+
 #include "gbx_sbm_pull.cuh"
 
 // =============================================================================================
@@ -1984,6 +2031,22 @@ int op_pull_export(gbx_sbm* h, double* dst_dev) {
   return GBX_OK;
 }
 
+// Replaces the rows of M-step partials the sweep just wrote (one per sweep CTA and hub) by statistics paired the
+// reference's way; sbm_local_totals sums whatever is there.
+int op_mstep_exact(gbx_sbm* h) {
+  if (MODEL != MODEL_SBM || h->world > 1) return GBX_OK;
+  GBX_TRY_RC(acquire_params(h, true));
+  const double* cur = h->pull ? h->msg[h->gen & 1] : h->msg[h->cur];
+  const int rows = h->sweep_rows;
+  if (rows > 0) {
+    sbm_mstep_exact_kernel<<<rows, NT, 0, h->stream>>>(cur, h->rev, (long long)h->K,
+                                                     h->part_mstep + (size_t)h->sweep_row0 * Q * Q, h->st, h->cur_it);
+    h->launches++;
+    GBX_CUDA_TRY(cudaGetLastError());
+  }
+  return GBX_OK;
+}
+
 int op_occupancy(int variant, int* vertex_occ, int* mstep_occ) {
   (void)variant;
   {
@@ -2213,12 +2276,12 @@ int mop_fe_final(gbx_sbm* h) {
 
 const SbmOps kOps = {Q,          op_vertex_pass, op_local_totals, mop_apply_totals,   mop_prepare,   mop_noop,     mop_noop,
                      mop_noop,   mop_fe_local,   mop_fe_apply,    mop_fe_final,       op_permute,    op_random_messages,
-                     op_assignment, op_occupancy, op_init_model, op_unpack, op_release,
+                     op_assignment, op_occupancy, op_init_model, op_unpack, op_release, op_mstep_exact,
                      PULL_OK ? 1 : 0, op_pull_setup, op_pull_load, op_pull_export};
 #else
 const SbmOps kOps = {Q,          op_vertex_pass, op_local_totals, op_apply_totals,    op_prepare,    op_theta_local, op_theta_apply,
                      op_escale,  op_fe_local,    op_fe_apply,     op_fe_final,        op_permute,    op_random_messages,
-                     op_assignment, op_occupancy, op_init_model, op_unpack, op_release,
+                     op_assignment, op_occupancy, op_init_model, op_unpack, op_release, op_mstep_exact,
                      PULL_OK ? 1 : 0, op_pull_setup, op_pull_load, op_pull_export};
 #endif
 

@@ -52,6 +52,13 @@ typedef struct gbx_sbm_options {
   double damping;           /* weight of the new message in the synchronous update, (0,1];
                                1 = undamped (default). Not in the reference (asynchronous sweep). */
   int check_every;          /* read the residual back every n iterations (default 1)              */
+  int mstep_exact;          /* update_Crs pairing (sbm.jl:128-136).  0 (default): the statistics are accumulated
+                               inside the sweep, pairing each NEW outgoing message with the incoming message it
+                               was computed from -- identical at the fixed point, 24 % faster per iteration.
+                               1: a separate pass after the sweep pairs the new messages of both directions, as
+                               update_Crs does when it runs after BP(); use it when a run may stop at itrmax
+                               (sbm.jl:354-359) and its parameters are to be compared with the reference's.
+                               Single-GPU handles only.                                                         */
 } gbx_sbm_options;
 
 /* What EM() returns besides the arrays (sbm.jl:369). */

@@ -108,10 +108,11 @@ def update_theta(PSI, degrees):
 
 class SyncSBM:
     def __init__(self, n, links, q, gr0, Crs0, psi0_links, *, dc=True, prior=True, lr=0.3,
-                 maxCrs=None, damping=1.0):
+                 maxCrs=None, damping=1.0, mstep_exact=False):
         self.g = build_csr(n, links)
         self.n, self.q = n, q
         self.dc, self.prior, self.lr, self.damping = dc, prior, lr, damping
+        self.mstep_exact = mstep_exact       # gbx_sbm_options::mstep_exact: pair the NEW messages of both directions
         self.maxCrs = float(n if maxCrs is None else maxCrs)
         self.degrees = np.diff(self.g["rowptr"]).astype(np.float64)
         self.theta = np.ones(n)
@@ -137,7 +138,8 @@ class SyncSBM:
             self.gr = self.gr + (PSI.mean(axis=0) - self.PSI.mean(axis=0))
         old = self.psi
         self.psi, self.PSI = psi, PSI
-        self.C = update_Crs(self.g, self.psi, old, self.theta, self.C, self.gr, self.n, self.maxCrs, self.lr)
+        self.C = update_Crs(self.g, self.psi, self.psi if self.mstep_exact else old, self.theta, self.C, self.gr, self.n,
+                            self.maxCrs, self.lr)
         if self.dc:
             self.theta = update_theta(self.PSI, self.degrees)
         self.itr += 1

@@ -172,3 +172,47 @@ def test_pull_and_push_sweeps_agree(gpu_required, monkeypatch, q, dc):
         np.testing.assert_allclose(getattr(ra, k), getattr(rb, k), rtol=1e-10, err_msg=k)
     for e in eng.values():
         e.close()
+
+
+@pytest.mark.parametrize("q,dc", [(3, True), (8, False), (8, True)])
+def test_exact_mstep_pairing(gpu_required, q, dc):
+    """gbx_sbm_options::mstep_exact = 1: update_Crs pairs the NEW messages of both directions (what sbm.jl:128-136 sees
+    when it runs after BP()), sweep by sweep equal to the numpy statement of that schedule; and at an itrmax exit of a
+    run that has not converged the default (statistics fused into the sweep: new outgoing x consumed incoming) differs
+    from it by no more than a few residuals -- at the fixed point the two coincide."""
+    from graphbix_b200.engine import SbmEngine
+    n, links, psi0, _ = planted_case(2000, q, 9.0, 0.15, seed=30 + q, informative=False)
+    gr0, C0 = assortative_init(q)
+    ref = SyncSBM(n, links, q, gr0, C0, psi0, dc=dc, prior=True, lr=0.3, mstep_exact=True)
+    exact, fused = SbmEngine(n, links, q), SbmEngine(n, links, q)
+    exact.set_options(degreecorrection=int(dc), mstep_exact=1)
+    fused.set_options(degreecorrection=int(dc), mstep_exact=0)
+    exact.init(gr0, C0, psi0)
+    fused.init(gr0, C0, psi0)
+    its = 14
+    for it in range(its):
+        ref.iterate()
+        ce, cf = exact.iterate(1), fused.iterate(1)
+        st = exact.state()
+        np.testing.assert_allclose(st["PSI"], ref.PSI, rtol=0, atol=1e-11, err_msg=f"PSI it={it}")
+        np.testing.assert_allclose(st["Crs"], ref.C, rtol=1e-10, err_msg=f"Crs it={it}")
+    assert max(ce, cf) > 1e-6                                    # an itrmax exit: neither run has converged
+    Ce, Cf = exact.state()["Crs"], fused.state()["Crs"]
+    assert np.abs(Ce - Cf).max() / np.abs(Ce).max() <= 3.0 * max(ce, cf)
+    exact.close()
+    fused.close()
+    # ... and from a start that leans to the planted labels (one basin for both) they converge to the same parameters
+    n, links, psi0, _ = planted_case(2000, q, 9.0, 0.15, seed=30 + q, informative=True)
+    out = []
+    for flag in (1, 0):
+        eng = SbmEngine(n, links, q)
+        eng.set_options(degreecorrection=int(dc), mstep_exact=flag, itrmax=3000, bp_conv_threshold=1e-12)
+        eng.init(gr0, C0, psi0)
+        res = eng.em()
+        out.append((res, eng.state()["Crs"]))
+        eng.close()
+    if out[0][0].cnv and out[1][0].cnv:
+        np.testing.assert_allclose(out[0][1], out[1][1], rtol=1e-6, atol=1e-12)
+        np.testing.assert_allclose(out[0][0].FE, out[1][0].FE, rtol=1e-8)
+    else:
+        assert dc                   # only the degree-corrected theta cycle (update_theta's argmax) keeps a run from converging
