@@ -70,7 +70,7 @@ def parse_args():
     ap.add_argument("--no-convergence-leg", action="store_true")
     ap.add_argument("--no-batch-leg", action="store_true")
     ap.add_argument("--no-labeled-leg", action="store_true")
-    ap.add_argument("--labeled-graphs", type=int, default=32, help="graphs per GPU of the labeled-SBM leg")
+    ap.add_argument("--labeled-graphs", type=int, default=128, help="graphs per GPU of the labeled-SBM leg")
     ap.add_argument("--batch-graphs", type=int, default=128, help="graphs per GPU of the batched-graphs leg")
     return ap.parse_args()
 
@@ -424,7 +424,7 @@ def run_labeled(a, torch, dist, world, rank, local):
     the GPUs round-robin, one EM() per graph through graphbix_b200.labeled.EM_labeled.  The CUDA path of this model is
     the first correct one (log domain, thread per vertex), so this is a baseline to improve, not a tuned number.  Also
     times the sweep on one large labeled graph (N = 1M, two labels of mean degree 8 each, q = 8)."""
-    from graphbix_b200.labeled import EM_labeled, LabeledEngine, initial_affinity
+    from graphbix_b200.labeled import EM_labeled, EM_labeled_batch, LabeledEngine, initial_affinity
     from graphbix_b200.parallel import my_share
     from graphbix_b200.synth import labeled_planted_partition
     n, B, G = 10_000, 2, 2
@@ -439,15 +439,27 @@ def run_labeled(a, torch, dist, world, rank, local):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    # one at a time (round 1's way), on a few graphs, for the comparison
     t0 = time.perf_counter()
-    res = []
-    for pos, eps, links, lab, Larray in graphs:
-        out = EM_labeled(n, Larray, B, G, links, 512, 1e-6, True, True, True, 0.3, 0, ["a", "d"], 1 / B,
-                         rng=np.random.default_rng(pos), device=local)
-        agree = float((np.argmax(out[2], axis=1) == lab).mean())
-        res.append((eps, (max(agree, 1 - agree) - 0.5) / 0.5, int(out[13]), bool(out[12])))
+    sample = graphs[::max(1, len(graphs) // 8)]          # a spread over epsilon: easy and hard graphs alike
+    for pos, eps, links, lab, Larray in sample:
+        EM_labeled(n, Larray, B, G, links, 512, 1e-6, True, True, True, 0.3, 0, ["a", "d"], 1 / B,
+                   rng=np.random.default_rng(pos), device=local)
+    torch.cuda.synchronize()
+    serial_rate = len(sample) / (time.perf_counter() - t0)
+    if world > 1:
+        dist.barrier()
+    # side by side: gbx_lsbm_em_batch (a stream per running graph, iterations of all of them queued before any is
+    # waited for); graph construction, initial messages, EM to convergence, free energy / CV errors, read-back of PSI
+    t0 = time.perf_counter()
+    outs = EM_labeled_batch([(n, Larray, B, G, links) for _, _, links, _, Larray in graphs], 512, 1e-6, True, True, True,
+                            0.3, 0, ["a", "d"], rngs=[np.random.default_rng(pos) for pos, *_ in graphs], device=local)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    res = []
+    for (pos, eps, links, lab, Larray), out in zip(graphs, outs):
+        agree = float((np.argmax(out[2], axis=1) == lab).mean())
+        res.append((eps, (max(agree, 1 - agree) - 0.5) / 0.5, int(out[13]), bool(out[12])))
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -461,6 +473,8 @@ def run_labeled(a, torch, dist, world, rank, local):
     out = {"workload": f"{len(tasks)} independent labeled graphs N={n}, labels: assortative c=5 + disassortative c=3, "
                        f"q={B}, EM_labeled() with degree correction, itrmax 512, epsilon 0.05..0.75, {world} GPU(s)",
            "graphs": len(tasks), "seconds": dt, "graphs_per_sec": len(tasks) / dt,
+           "how": "gbx_lsbm_em_batch: up to 16 graphs side by side per GPU, one stream each",
+           "graphs_per_sec_one_at_a_time_per_gpu": serial_rate,
            "overlap_by_epsilon": {str(k): round(float(np.mean(v)), 3) for k, v in sorted(by_eps.items())},
            "converged_fraction": float(np.mean([x[3] for x in res])),
            "mean_iterations": float(np.mean([x[2] if x[3] else 512 for x in res]))}

@@ -113,6 +113,7 @@ SIGNATURES = {
     "gbx_lsbm_set_options": (C.c_int, [_P, C.POINTER(LsbmOptions)]),
     "gbx_lsbm_init": (C.c_int, [_P, _D, _D, _D]),
     "gbx_lsbm_em": (C.c_int, [_P, C.POINTER(LsbmResult)]),
+    "gbx_lsbm_em_batch": (C.c_int, [C.POINTER(_P), C.c_int, C.POINTER(LsbmResult), C.c_int]),
     "gbx_lsbm_iterate": (C.c_int, [_P, C.c_int, _D]),
     "gbx_lsbm_finalize": (C.c_int, [_P, C.POINTER(LsbmResult)]),
     "gbx_lsbm_get_state": (C.c_int, [_P, _D, _D, _D, _D]),

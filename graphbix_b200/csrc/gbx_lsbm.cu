@@ -831,6 +831,81 @@ int gbx_lsbm_finalize(gbx_lsbm* h, gbx_lsbm_result* res) {
   return GBX_OK;
 }
 
+}  // extern "C"
+
+namespace {
+
+// The main loop of the notebook's EM() as a small state machine, so that many handles can be driven side by side:
+// queue a batch of iterations on the handle's stream (plus the 4-byte read-back of the iteration at which the device
+// found BPconv < threshold), later look at it.  Small graphs are launch bound: `batch` iterations are queued before
+// the host looks; kernels of iterations after the converged one return at once (l_skip), so the state is the one
+// the notebook's `break` leaves.
+struct LsbmRun {
+  gbx_lsbm* h = nullptr;
+  int batch = 1, itr0 = 0, done = 0, cnv = 0, itrnum = 0;
+  bool finished = false;
+  cudaEvent_t ev = nullptr;
+};
+
+int lrun_begin(LsbmRun& r, gbx_lsbm* h) {
+  r.h = h;
+  r.batch = h->g.K < (int64_t)2000000 ? 8 : 1;
+  if (const char* e = getenv("GBX_EM_BATCH")) r.batch = std::max(1, atoi(e));
+  GBX_CUDA_TRY(cudaMemsetAsync(&h->P->done_at, 0, sizeof(int), h->g.stream));
+  r.itr0 = h->itr;
+  r.done = r.cnv = r.itrnum = 0;
+  r.finished = h->opt.itrmax <= 0;
+  h->cur_thr = h->opt.bp_conv_threshold;
+  if (!r.ev) GBX_CUDA_TRY(cudaEventCreateWithFlags(&r.ev, cudaEventDisableTiming));
+  return GBX_OK;
+}
+int lrun_queue(LsbmRun& r) {  // queue the next batch of iterations and the read-back
+  gbx_lsbm* h = r.h;
+  const int nb = std::min(r.batch, h->opt.itrmax - r.done);
+  for (int b = 1; b <= nb; ++b) {
+    h->cur_it = r.itr0 + r.done + b;
+    L_TRY(l_iteration(h));
+  }
+  r.done += nb;
+  GBX_CUDA_TRY(cudaMemcpyAsync(&h->hP->done_at, &h->P->done_at, sizeof(int), cudaMemcpyDeviceToHost, h->g.stream));
+  GBX_CUDA_TRY(cudaEventRecord(r.ev, h->g.stream));
+  return GBX_OK;
+}
+int lrun_poll(LsbmRun& r) {  // wait for the queued batch; decide whether the run is over
+  gbx_lsbm* h = r.h;
+  cudaError_t ce = cudaEventSynchronize(r.ev);
+  if (ce != cudaSuccess) {
+    last_error() = std::string("gbx_lsbm_em: ") + cudaGetErrorString(ce);
+    return GBX_ERR_CUDA;
+  }
+  const int done_at = h->hP->done_at;
+  if (done_at != 0) {
+    if ((r.itr0 + r.done - done_at) & 1) h->cur ^= 1;   // queued passes that did nothing still flipped the buffers
+    h->itr = done_at;
+    r.cnv = 1;
+    r.itrnum = done_at - r.itr0;
+    r.done = r.itrnum;
+    r.finished = true;
+  } else if (r.done >= h->opt.itrmax) {
+    r.finished = true;
+  }
+  return GBX_OK;
+}
+int lrun_end(LsbmRun& r, gbx_lsbm_result* res) {
+  gbx_lsbm* h = r.h;
+  h->cur_it = 0;
+  h->cur_thr = -1.0;
+  L_TRY(gbx_lsbm_finalize(h, res));
+  res->cnv = r.cnv;
+  res->itrnum = r.itrnum;
+  res->itrs_done = r.done;
+  return GBX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 int gbx_lsbm_em(gbx_lsbm* h, gbx_lsbm_result* res) {
   if (!h || !res) return l_invalid("handle/result is NULL");
   if (!h->initialised) {
@@ -838,48 +913,85 @@ int gbx_lsbm_em(gbx_lsbm* h, gbx_lsbm_result* res) {
     return GBX_ERR_STATE;
   }
   GBX_CUDA_TRY(cudaSetDevice(h->g.device));
-  // Small graphs are launch bound: queue `batch` iterations, then read the iteration k_lsbm_post recorded as converged
-  // (kernels of later iterations returned at once, so the state is the one the notebook's `break` leaves).
-  int cnv = 0, itrnum = 0, done = 0;
-  int batch = h->g.K < (int64_t)2000000 ? 8 : 1;
-  if (const char* e = getenv("GBX_EM_BATCH")) batch = std::max(1, atoi(e));
-  GBX_CUDA_TRY(cudaMemsetAsync(&h->P->done_at, 0, sizeof(int), h->g.stream));
-  const int itr0 = h->itr;
-  h->cur_thr = h->opt.bp_conv_threshold;
-  int rc = GBX_OK;
-  while (done < h->opt.itrmax && rc == GBX_OK) {
-    const int nb = std::min(batch, h->opt.itrmax - done);
-    for (int b = 1; b <= nb && rc == GBX_OK; ++b) {
-      h->cur_it = itr0 + done + b;
-      rc = l_iteration(h);
-    }
-    if (rc != GBX_OK) break;
-    done += nb;
-    cudaError_t ce = cudaMemcpyAsync(&h->hP->done_at, &h->P->done_at, sizeof(int), cudaMemcpyDeviceToHost, h->g.stream);
-    if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->g.stream);
-    if (ce != cudaSuccess) {
-      last_error() = std::string("gbx_lsbm_em: ") + cudaGetErrorString(ce);
-      rc = GBX_ERR_CUDA;
-      break;
-    }
-    const int done_at = h->hP->done_at;
-    if (done_at != 0) {
-      if ((itr0 + done - done_at) & 1) h->cur ^= 1;   // queued passes that did nothing still flipped the buffers
-      h->itr = done_at;
-      cnv = 1;
-      itrnum = done_at - itr0;
-      done = itrnum;
-      break;
-    }
+  LsbmRun r;
+  int rc = lrun_begin(r, h);
+  while (rc == GBX_OK && !r.finished) {
+    rc = lrun_queue(r);
+    if (rc == GBX_OK) rc = lrun_poll(r);
   }
+  if (rc == GBX_OK) rc = lrun_end(r, res);
+  if (r.ev) cudaEventDestroy(r.ev);
   h->cur_it = 0;
   h->cur_thr = -1.0;
-  L_TRY(rc);
-  L_TRY(gbx_lsbm_finalize(h, res));
-  res->cnv = cnv;
-  res->itrnum = itrnum;
-  res->itrs_done = done;
-  return GBX_OK;
+  return rc;
+}
+
+// EM() of `count` initialised handles of ONE device, side by side: every handle gets a stream of its own for the call
+// (up to `max_concurrent` run at a time, 0 = 16), batches of iterations of all running handles are queued before any is
+// waited for, and a finished handle hands its stream to the next one.  The graphs of a detectability sweep (BASELINE
+// configs[4]: thousands of N = 10k graphs) are launch bound one at a time; side by side their kernels overlap on the GPU
+// and the host's launch latency is hidden.  Results are those of gbx_lsbm_em on each handle (same kernels, same order).
+int gbx_lsbm_em_batch(gbx_lsbm** hs, int count, gbx_lsbm_result* res, int max_concurrent) {
+  if (count < 0 || (count > 0 && (!hs || !res))) return l_invalid("handles/results is NULL");
+  if (count == 0) return GBX_OK;
+  const int dev = hs[0] ? hs[0]->g.device : 0;
+  for (int i = 0; i < count; ++i) {
+    if (!hs[i]) return l_invalid("a handle is NULL");
+    if (!hs[i]->initialised) {
+      last_error() = "gbx_lsbm_init has not been called on every handle";
+      return GBX_ERR_STATE;
+    }
+    if (hs[i]->g.device != dev) return l_invalid("the handles of a batch must live on one device");
+  }
+  GBX_CUDA_TRY(cudaSetDevice(dev));
+  const int W = std::max(1, std::min(count, max_concurrent > 0 ? max_concurrent : 16));
+  std::vector<cudaStream_t> streams((size_t)W, nullptr);
+  std::vector<cudaStream_t> saved((size_t)count, nullptr);
+  std::vector<LsbmRun> run((size_t)W);
+  std::vector<int> who((size_t)W, -1);
+  int rc = GBX_OK, next = 0, live = 0;
+  for (int w = 0; w < W && rc == GBX_OK; ++w)
+    if (cudaStreamCreateWithFlags(&streams[(size_t)w], cudaStreamNonBlocking) != cudaSuccess) rc = GBX_ERR_CUDA;
+  auto start = [&](int w) -> int {
+    const int i = next++;
+    who[(size_t)w] = i;
+    saved[(size_t)i] = hs[i]->g.stream;
+    cudaStreamSynchronize(hs[i]->g.stream);   // whatever init queued on the handle's own stream
+    hs[i]->g.stream = streams[(size_t)w];
+    ++live;
+    return lrun_begin(run[(size_t)w], hs[i]);
+  };
+  for (int w = 0; w < W && next < count && rc == GBX_OK; ++w) rc = start(w);
+  while (live > 0 && rc == GBX_OK) {
+    for (int w = 0; w < W && rc == GBX_OK; ++w)
+      if (who[(size_t)w] >= 0 && !run[(size_t)w].finished) rc = lrun_queue(run[(size_t)w]);
+    for (int w = 0; w < W && rc == GBX_OK; ++w) {
+      if (who[(size_t)w] < 0) continue;
+      if (!run[(size_t)w].finished) rc = lrun_poll(run[(size_t)w]);
+      if (rc == GBX_OK && run[(size_t)w].finished) {
+        const int i = who[(size_t)w];
+        rc = lrun_end(run[(size_t)w], &res[i]);
+        hs[i]->g.stream = saved[(size_t)i];
+        who[(size_t)w] = -1;
+        --live;
+        if (rc == GBX_OK && next < count) rc = start(w);
+      }
+    }
+  }
+  for (int w = 0; w < W; ++w) {   // on an error path: give the handles their streams back
+    if (who[(size_t)w] >= 0) {
+      cudaStreamSynchronize(streams[(size_t)w]);
+      hs[who[(size_t)w]]->g.stream = saved[(size_t)who[(size_t)w]];
+      hs[who[(size_t)w]]->cur_it = 0;
+      hs[who[(size_t)w]]->cur_thr = -1.0;
+    }
+    if (run[(size_t)w].ev) cudaEventDestroy(run[(size_t)w].ev);
+    if (streams[(size_t)w]) {
+      cudaStreamSynchronize(streams[(size_t)w]);
+      cudaStreamDestroy(streams[(size_t)w]);
+    }
+  }
+  return rc;
 }
 
 int gbx_lsbm_get_state(gbx_lsbm* h, double* gr, double* affinity, double* PSI, double* hfield) {

@@ -145,3 +145,38 @@ def EM_labeled(Ntot, Larray, B, G, links, itrmax, BPconvthreshold, learning, pri
         return out, eng, r
     eng.close()
     return out
+
+
+def EM_labeled_batch(graphs, itrmax, BPconvthreshold, learning, priorlearning, dc, learningrate, REDfrac, assortativity, *,
+                     rngs=None, device=0, max_concurrent=0):
+    """The notebook's EM() on many graphs side by side on one GPU (gbx_lsbm_em_batch; BASELINE configs[4]: a
+    detectability sweep over thousands of N = 10k graphs).  `graphs` is a list of (Ntot, Larray, B, G, links); Omega is
+    1 / B as in the notebook's MAIN.  Returns the list of EM()'s 14-tuples, in order; each equals what EM_labeled returns
+    for that graph from the same initial messages."""
+    lib = _lib.load()
+    engines, outs = [], []
+    try:
+        for k, (Ntot, Larray, B, G, links) in enumerate(graphs):
+            links = np.asarray(links, dtype=np.int64)
+            K = links.shape[0]
+            eng = LabeledEngine(Ntot, links, B, G, device=device)
+            eng.set_options(dc=int(bool(dc)), learning=int(bool(learning)), priorlearning=int(bool(priorlearning)),
+                            learningrate=float(learningrate), itrmax=int(itrmax),
+                            bp_conv_threshold=float(BPconvthreshold), REDfrac=float(REDfrac))
+            rng = rngs[k] if rngs is not None else np.random.default_rng()
+            psi0 = rng.random((K, B))
+            psi0 /= psi0.sum(axis=1, keepdims=True)
+            eng.init(np.ones(B) / B, initial_affinity(Ntot, K, Larray, B, G, dc, REDfrac, assortativity, 1 / B), psi0)
+            engines.append(eng)
+        n = len(engines)
+        hs = (C.c_void_p * n)(*[e._h for e in engines])
+        res = (LsbmResult * n)()
+        check(lib.gbx_lsbm_em_batch(hs, n, res, int(max_concurrent)))
+        for eng, r in zip(engines, res):
+            st = eng.state()
+            outs.append((st["gr"], st["affinity"], st["PSI"], r.FE, r.CVBayes, r.CVGP, r.CVGT, r.CVMAP, r.varCVBayes,
+                         r.varCVGP, r.varCVGT, r.varCVMAP, bool(r.cnv), int(r.itrnum)))
+    finally:
+        for eng in engines:
+            eng.close()
+    return outs

@@ -217,6 +217,11 @@ int gbx_lsbm_set_options(gbx_lsbm* h, const gbx_lsbm_options* opt);
 /* gr[q], affinity[n_labels][q][q], psicav[K][q] (rows in `links3` order); then PSI = updatePSI(), h = update_h(). */
 int gbx_lsbm_init(gbx_lsbm* h, const double* gr, const double* affinity, const double* psicav);
 int gbx_lsbm_em(gbx_lsbm* h, gbx_lsbm_result* res);                  /* the main loop + freeenergy()          */
+/* EM() of `count` initialised handles of one device side by side (BASELINE configs[4]: a detectability sweep over
+ * thousands of N = 10k graphs): each handle runs on a stream of its own for the call, up to `max_concurrent` (0 = 16) at
+ * a time, so the kernels of different graphs overlap and the launch latency is hidden.  res[i] is what gbx_lsbm_em
+ * returns for hs[i] (same kernels in the same order).                                                              */
+int gbx_lsbm_em_batch(gbx_lsbm** hs, int count, gbx_lsbm_result* res, int max_concurrent);
 int gbx_lsbm_iterate(gbx_lsbm* h, int n_iters, double* bpconv_out);  /* n x (update_h, BP sweep, gr, affinity) */
 int gbx_lsbm_finalize(gbx_lsbm* h, gbx_lsbm_result* res);            /* freeenergy()                          */
 /* gr[q], affinity[n_labels][q][q], PSI[N][q], hfield[n_labels][q]; any may be NULL */

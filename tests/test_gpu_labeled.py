@@ -159,3 +159,27 @@ def test_reference_fixture_three_blocks_and_qstar(gpu_required):
         cv[B], se[B] = best[4], np.sqrt(best[8] / L)
     assert cv[3] < cv[2] - 2 * se[2]                               # B = 3 is clearly better than B = 2 ...
     assert cv[4] > cv[3] - 2 * se[3]                               # ... and B = 4 is no significant improvement: q* = 3
+
+
+def test_labeled_batch_equals_one_at_a_time(gpu_required):
+    """gbx_lsbm_em_batch: several graphs side by side (more graphs than concurrent streams, so streams are handed on) give
+    what gbx_lsbm_em gives one at a time: same itrnum, same state up to the rounding of the atomics."""
+    from graphbix_b200.labeled import EM_labeled, EM_labeled_batch
+    from graphbix_b200.synth import labeled_planted_partition
+    graphs, singles = [], []
+    for k in range(7):
+        n, B = 600 + 100 * k, 2 + (k % 2)
+        links, _ = labeled_planted_partition(n, B, [5.0, 3.0], ["a", "d"], 0.1, seed=40 + k)
+        und = links[links[:, 0] < links[:, 1]]
+        Larray = [int((und[:, 2] == a + 1).sum()) for a in range(2)]
+        graphs.append((n, Larray, B, 2, links))
+        singles.append(EM_labeled(n, Larray, B, 2, links, 512, 1e-8, True, True, True, 0.3, 0, ["a", "d"], 1 / B,
+                                  rng=np.random.default_rng(k)))
+    batch = EM_labeled_batch(graphs, 512, 1e-8, True, True, True, 0.3, 0, ["a", "d"],
+                             rngs=[np.random.default_rng(k) for k in range(7)], max_concurrent=3)
+    assert len(batch) == 7
+    for s, b in zip(singles, batch):
+        assert s[12] == b[12] and s[13] == b[13]
+        np.testing.assert_allclose(b[2], s[2], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(b[1], s[1], rtol=1e-10)
+        np.testing.assert_allclose(b[3:12], s[3:12], rtol=1e-9)
