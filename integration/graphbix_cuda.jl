@@ -8,6 +8,8 @@
 #                    EM_cuda(Ntot,B,links,maxCrs,gr0,Crs0,degreecorrection,itrmax,priorlearning,learningrate)
 #   mod.jl:817   (excm,alpha,beta,omegain,omegaout,PSI,FE,CVBayes,CVGP,CVGT,CVMAP,varCVBayes,varCVGP,varCVGT,varCVMAP,cnv,itrnum) =
 #                    EM_mod_cuda(gr,Ntot,B,links,maxomega,itrmax,betafrac,learning,priorlearning,dc,learningrate)
+# integration/sbm.jl.patch and integration/mod.jl.patch are the diffs against the reference's src/ that make exactly
+# these two replacements (`patch -p1` in the reference's root; copy this file next to sbm.jl / mod.jl).
 
 const libgbx = "libgraphbix_cuda"
 
@@ -20,6 +22,7 @@ mutable struct GbxSbmOptions               # struct gbx_sbm_options
     bp_conv_threshold::Cdouble
     damping::Cdouble
     check_every::Cint
+    mstep_exact::Cint
     GbxSbmOptions() = new()
 end
 
