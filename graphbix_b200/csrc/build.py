@@ -43,7 +43,7 @@ def build(qs=None, force=False, verbose=False):
     qs = sorted(set(qs or ALL_Q))
     os.makedirs(OBJ, exist_ok=True)
     srcs = [os.path.join(HERE, f) for f in ("gbx_sbm_q.cu", "gbx_sbm_host.cu", "gbx_graph_build.cu", "gbx_pool.cu", "gbx_lsbm.cu", "gbx_common.cuh",
-                                            "gbx_sbm_internal.h")]
+                                            "gbx_sbm_internal.h", "gbx_sbm_pull.cuh")]
     srcs.append(os.path.join(os.path.dirname(PKG), "include", "graphbix_cuda.h"))
     stamp = os.path.join(OBJ, "stamp.txt")
     want = _digest(srcs, extra=",".join(map(str, qs)) + " ".join(FLAGS))
