@@ -70,7 +70,7 @@ def parse_args():
     ap.add_argument("--no-convergence-leg", action="store_true")
     ap.add_argument("--no-batch-leg", action="store_true")
     ap.add_argument("--no-labeled-leg", action="store_true")
-    ap.add_argument("--labeled-graphs", type=int, default=128, help="graphs per GPU of the labeled-SBM leg")
+    ap.add_argument("--labeled-graphs", type=int, default=512, help="graphs per GPU of the labeled-SBM leg (configs[4]: 4096 over 8 GPUs)")
     ap.add_argument("--batch-graphs", type=int, default=128, help="graphs per GPU of the batched-graphs leg")
     return ap.parse_args()
 
@@ -421,9 +421,9 @@ def run_batch(a, torch, dist, world, rank, local):
 def run_labeled(a, torch, dist, world, rank, local):
     """BASELINE.json configs[4]: the labeled SBM of the reference's notebook on independent N = 10k graphs (two labels:
     one assortative with mean degree 5, one disassortative with mean degree 3; 2 groups), a sweep over epsilon, dealt to
-    the GPUs round-robin, one EM() per graph through graphbix_b200.labeled.EM_labeled.  The CUDA path of this model is
-    the first correct one (log domain, thread per vertex), so this is a baseline to improve, not a tuned number.  Also
-    times the sweep on one large labeled graph (N = 1M, two labels of mean degree 8 each, q = 8)."""
+    the GPUs round-robin; the graphs of a GPU run in ONE handle (gbx_lsbm_create_batch: one launch set per EM iteration
+    for all of them, graphs drop out as they converge).  Also times the sweep on one large labeled graph (N = 1M, two
+    labels of mean degree 8 each, q = 8)."""
     from graphbix_b200.labeled import EM_labeled, EM_labeled_batch, LabeledEngine, initial_affinity
     from graphbix_b200.parallel import my_share
     from graphbix_b200.synth import labeled_planted_partition
@@ -439,21 +439,20 @@ def run_labeled(a, torch, dist, world, rank, local):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    # one at a time (round 1's way), on a few graphs, for the comparison
+    # one at a time (a handle per graph), on a few graphs, for the comparison
     t0 = time.perf_counter()
     sample = graphs[::max(1, len(graphs) // 8)]          # a spread over epsilon: easy and hard graphs alike
     for pos, eps, links, lab, Larray in sample:
-        EM_labeled(n, Larray, B, G, links, 512, 1e-6, True, True, True, 0.3, 0, ["a", "d"], 1 / B,
-                   rng=np.random.default_rng(pos), device=local)
+        EM_labeled(n, Larray, B, G, links, 512, 1e-6, True, True, True, 0.3, 0, ["a", "d"], 1 / B, seed=pos, device=local)
     torch.cuda.synchronize()
     serial_rate = len(sample) / (time.perf_counter() - t0)
     if world > 1:
         dist.barrier()
-    # side by side: gbx_lsbm_em_batch (a stream per running graph, iterations of all of them queued before any is
-    # waited for); graph construction, initial messages, EM to convergence, free energy / CV errors, read-back of PSI
+    # all graphs of this GPU in one handle; timed: union + CSR build from host edge lists, initial messages (drawn on the
+    # device), EM to convergence of every graph, free energy / CV errors, read-back of gr / affinity / PSI of every graph
     t0 = time.perf_counter()
     outs = EM_labeled_batch([(n, Larray, B, G, links) for _, _, links, _, Larray in graphs], 512, 1e-6, True, True, True,
-                            0.3, 0, ["a", "d"], rngs=[np.random.default_rng(pos) for pos, *_ in graphs], device=local)
+                            0.3, 0, ["a", "d"], seeds=[pos for pos, *_ in graphs], device=local)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     res = []
@@ -473,7 +472,8 @@ def run_labeled(a, torch, dist, world, rank, local):
     out = {"workload": f"{len(tasks)} independent labeled graphs N={n}, labels: assortative c=5 + disassortative c=3, "
                        f"q={B}, EM_labeled() with degree correction, itrmax 512, epsilon 0.05..0.75, {world} GPU(s)",
            "graphs": len(tasks), "seconds": dt, "graphs_per_sec": len(tasks) / dt,
-           "how": "gbx_lsbm_em_batch: up to 16 graphs side by side per GPU, one stream each",
+           "how": "gbx_lsbm_create_batch: the graphs of a GPU in one handle (disjoint union, grid y = graph), one launch "
+                  "set per EM iteration for all live graphs; time includes graph build from host edge lists and read-back",
            "graphs_per_sec_one_at_a_time_per_gpu": serial_rate,
            "overlap_by_epsilon": {str(k): round(float(np.mean(v)), 3) for k, v in sorted(by_eps.items())},
            "converged_fraction": float(np.mean([x[3] for x in res])),

@@ -108,6 +108,13 @@ SIGNATURES = {
     "gbx_sbm_part_set_exchange": (C.c_int, [_P, C.c_int]),
     "gbx_lsbm_default_options": (None, [C.POINTER(LsbmOptions)]),
     "gbx_lsbm_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.c_int, C.c_int]),
+    "gbx_lsbm_create_batch": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                        C.POINTER(C.POINTER(C.c_int64)), C.c_int, C.c_int]),
+    "gbx_lsbm_count": (C.c_int, [_P]),
+    "gbx_lsbm_init_batch": (C.c_int, [_P, _D, _D, C.POINTER(_D)]),
+    "gbx_lsbm_init_random": (C.c_int, [_P, _D, _D, C.POINTER(C.c_uint64)]),
+    "gbx_lsbm_get_state_of": (C.c_int, [_P, C.c_int, _D, _D, _D, _D]),
+    "gbx_lsbm_get_messages_of": (C.c_int, [_P, C.c_int, _D]),
     "gbx_lsbm_destroy": (C.c_int, [_P]),
     "gbx_lsbm_set_stream": (C.c_int, [_P, C.c_void_p]),
     "gbx_lsbm_set_options": (C.c_int, [_P, C.POINTER(LsbmOptions)]),

@@ -81,9 +81,14 @@ class LabeledEngine:
             setattr(self.opt, k, v)
         check(self.lib.gbx_lsbm_set_options(self._h, C.byref(self.opt)))
 
-    def init(self, gr, affinity, psicav):
+    def init(self, gr, affinity, psicav=None, seed=None):
+        """psicav: K x q initial messages (rows in the order of links3), or None: drawn on the device from `seed`."""
         gr = np.ascontiguousarray(gr, dtype=np.float64).ravel()
         affinity = np.ascontiguousarray(affinity, dtype=np.float64).reshape(self.G, self.q, self.q)
+        if psicav is None:
+            sd = (C.c_uint64 * 1)(int(seed or 0))
+            check(self.lib.gbx_lsbm_init_random(self._h, _dp(gr), _dp(affinity), sd))
+            return
         psicav = np.ascontiguousarray(psicav, dtype=np.float64).reshape(self.K, self.q)
         check(self.lib.gbx_lsbm_init(self._h, _dp(gr), _dp(affinity), _dp(psicav)))
 
@@ -120,7 +125,7 @@ class LabeledEngine:
 
 def EM_labeled(Ntot, Larray, B, G, links, itrmax, BPconvthreshold, learning, priorlearning, dc, learningrate, REDfrac,
                assortativity, Omega, *, rng=None, PSIcav0=None, affinity0=None, gr0=None, damping=1.0, device=0,
-               return_engine=False):
+               return_engine=False, seed=None):
     """Drop-in for the notebook's EM(); returns its 14-tuple
     (gr, affinity, PSI, FE, CVBayes, CVGP, CVGT, CVMAP, varCVBayes, varCVGP, varCVGT, varCVMAP, cnv, itrnum) with
     `affinity` as a (G, B, B) array."""
@@ -133,10 +138,10 @@ def EM_labeled(Ntot, Larray, B, G, links, itrmax, BPconvthreshold, learning, pri
                     REDfrac=float(REDfrac), damping=float(damping))
     aff = affinity0 if affinity0 is not None else initial_affinity(Ntot, K, Larray, B, G, dc, REDfrac, assortativity, Omega)
     gr = np.ones(B) / B if gr0 is None else gr0
-    if PSIcav0 is None:                      # rand(1,B) normalised, one row per link
+    if PSIcav0 is None and seed is None:     # rand(1,B) normalised, one row per link
         PSIcav0 = rng.random((K, B))
         PSIcav0 /= PSIcav0.sum(axis=1, keepdims=True)
-    eng.init(gr, aff, PSIcav0)
+    eng.init(gr, aff, PSIcav0, seed=seed)    # seed given: the same draw on the device
     r = eng.em()
     st = eng.state()
     out = (st["gr"], st["affinity"], st["PSI"], r.FE, r.CVBayes, r.CVGP, r.CVGT, r.CVMAP, r.varCVBayes, r.varCVGP,
@@ -147,36 +152,116 @@ def EM_labeled(Ntot, Larray, B, G, links, itrmax, BPconvthreshold, learning, pri
     return out
 
 
+class LabeledBatch:
+    """Many labeled graphs in ONE handle on one GPU (gbx_lsbm_create_batch): every kernel launch serves all of them, each
+    graph keeps its own parameters and converges on its own (BASELINE configs[4])."""
+
+    def __init__(self, graphs, B: int, G: int, device: int = 0, stream=None):
+        """graphs: list of (Ntot, links3) with links3 K x 3 (i, j, label), vertices 1..Ntot of that graph."""
+        self.lib = _lib.load()
+        self.q, self.G, self.count = int(B), int(G), len(graphs)
+        self.n = [int(n) for n, _ in graphs]
+        self._links = [np.asfortranarray(np.asarray(l), dtype=np.int64) for _, l in graphs]   # kept alive for the call
+        self.K = [int(l.shape[0]) for l in self._links]
+        ns = (C.c_int64 * self.count)(*self.n)
+        Ks = (C.c_int64 * self.count)(*self.K)
+        ptrs = (C.POINTER(C.c_int64) * self.count)(*[l.ctypes.data_as(C.POINTER(C.c_int64)) for l in self._links])
+        self._h = C.c_void_p()
+        check(self.lib.gbx_lsbm_create_batch(C.byref(self._h), int(device), self.count, ns, Ks, ptrs, self.q, self.G))
+        self._links = None
+        self.opt = LsbmOptions()
+        self.lib.gbx_lsbm_default_options(C.byref(self.opt))
+        if stream is not None:
+            ptr = getattr(stream, "cuda_stream", stream)
+            check(self.lib.gbx_lsbm_set_stream(self._h, C.c_void_p(int(ptr) if ptr else 0)))
+
+    close = LabeledEngine.close
+    __del__ = LabeledEngine.__del__
+    set_options = LabeledEngine.set_options
+
+    def init(self, gr, affinity, psicav=None, seeds=None):
+        """gr: count x q, affinity: count x G x q x q, psicav: list of K_g x q arrays (rows in the order of links3), or
+        None: the messages of graph g are drawn on the device from seeds[g]."""
+        gr = np.ascontiguousarray(gr, dtype=np.float64).reshape(self.count, self.q)
+        affinity = np.ascontiguousarray(affinity, dtype=np.float64).reshape(self.count, self.G, self.q, self.q)
+        if psicav is None:
+            sd = (C.c_uint64 * self.count)(*[int(x) for x in (seeds if seeds is not None else range(self.count))])
+            check(self.lib.gbx_lsbm_init_random(self._h, _dp(gr), _dp(affinity), sd))
+            return
+        rows = [np.ascontiguousarray(m, dtype=np.float64).reshape(k, self.q) for m, k in zip(psicav, self.K)]
+        ptrs = (C.POINTER(C.c_double) * self.count)(*[_dp(m) for m in rows])
+        check(self.lib.gbx_lsbm_init_batch(self._h, _dp(gr), _dp(affinity), ptrs))
+
+    def iterate(self, n: int = 1):
+        check(self.lib.gbx_lsbm_iterate(self._h, int(n), None))
+
+    def em(self):
+        res = (LsbmResult * self.count)()
+        check(self.lib.gbx_lsbm_em(self._h, res))
+        return list(res)
+
+    def finalize(self):
+        res = (LsbmResult * self.count)()
+        check(self.lib.gbx_lsbm_finalize(self._h, res))
+        return list(res)
+
+    def state(self, g: int):
+        q, G = self.q, self.G
+        gr, aff, P, h = np.empty(q), np.empty((G, q, q)), np.empty((self.n[g], q)), np.empty((G, q))
+        check(self.lib.gbx_lsbm_get_state_of(self._h, int(g), _dp(gr), _dp(aff), _dp(P), _dp(h)))
+        return dict(gr=gr, affinity=aff, PSI=P, h=h)
+
+    def messages(self, g: int):
+        m = np.empty((self.K[g], self.q))
+        check(self.lib.gbx_lsbm_get_messages_of(self._h, int(g), _dp(m)))
+        return m
+
+    @property
+    def launch_count(self):
+        return int(self.lib.gbx_lsbm_launch_count(self._h))
+
+
 def EM_labeled_batch(graphs, itrmax, BPconvthreshold, learning, priorlearning, dc, learningrate, REDfrac, assortativity, *,
-                     rngs=None, device=0, max_concurrent=0):
-    """The notebook's EM() on many graphs side by side on one GPU (gbx_lsbm_em_batch; BASELINE configs[4]: a
-    detectability sweep over thousands of N = 10k graphs).  `graphs` is a list of (Ntot, Larray, B, G, links); Omega is
-    1 / B as in the notebook's MAIN.  Returns the list of EM()'s 14-tuples, in order; each equals what EM_labeled returns
-    for that graph from the same initial messages."""
-    lib = _lib.load()
-    engines, outs = [], []
+                     rngs=None, device=0, max_concurrent=0, PSIcav0=None, seeds=None, return_engine=False):
+    """The notebook's EM() on many graphs at once on one GPU (one handle for all of them, gbx_lsbm_create_batch; BASELINE
+    configs[4]: a detectability sweep over thousands of N = 10k graphs).  `graphs` is a list of (Ntot, Larray, B, G, links)
+    with equal B and G; Omega is 1 / B as in the notebook's MAIN.  Returns the list of EM()'s 14-tuples, in order; each
+    equals what EM_labeled returns for that graph from the same initial messages (to the rounding of the sums).
+    Initial messages: PSIcav0[k] if given, else drawn on the device from seeds[k] if `seeds` is given, else from rngs[k]."""
+    if not graphs:
+        return []
+    B, G = int(graphs[0][2]), int(graphs[0][3])
+    if any(int(g[2]) != B or int(g[3]) != G for g in graphs):
+        raise ValueError("the graphs of a batch must share B and G")
+    links = [np.asarray(g[4], dtype=np.int64) for g in graphs]
+    eng = LabeledBatch([(g[0], l) for g, l in zip(graphs, links)], B, G, device=device)
+    outs = []
     try:
-        for k, (Ntot, Larray, B, G, links) in enumerate(graphs):
-            links = np.asarray(links, dtype=np.int64)
-            K = links.shape[0]
-            eng = LabeledEngine(Ntot, links, B, G, device=device)
-            eng.set_options(dc=int(bool(dc)), learning=int(bool(learning)), priorlearning=int(bool(priorlearning)),
-                            learningrate=float(learningrate), itrmax=int(itrmax),
-                            bp_conv_threshold=float(BPconvthreshold), REDfrac=float(REDfrac))
-            rng = rngs[k] if rngs is not None else np.random.default_rng()
-            psi0 = rng.random((K, B))
-            psi0 /= psi0.sum(axis=1, keepdims=True)
-            eng.init(np.ones(B) / B, initial_affinity(Ntot, K, Larray, B, G, dc, REDfrac, assortativity, 1 / B), psi0)
-            engines.append(eng)
-        n = len(engines)
-        hs = (C.c_void_p * n)(*[e._h for e in engines])
-        res = (LsbmResult * n)()
-        check(lib.gbx_lsbm_em_batch(hs, n, res, int(max_concurrent)))
-        for eng, r in zip(engines, res):
-            st = eng.state()
+        eng.set_options(dc=int(bool(dc)), learning=int(bool(learning)), priorlearning=int(bool(priorlearning)),
+                        learningrate=float(learningrate), itrmax=int(itrmax), bp_conv_threshold=float(BPconvthreshold),
+                        REDfrac=float(REDfrac))
+        psi, aff = [], []
+        for k, (Ntot, Larray, _, _, _) in enumerate(graphs):
+            K = links[k].shape[0]
+            aff.append(initial_affinity(Ntot, K, Larray, B, G, dc, REDfrac, assortativity, 1 / B))
+            if PSIcav0 is None and seeds is not None:
+                continue
+            if PSIcav0 is not None:
+                m = np.asarray(PSIcav0[k], dtype=np.float64)
+            else:
+                rng = rngs[k] if rngs is not None else np.random.default_rng()
+                m = rng.random((K, B))
+                m /= m.sum(axis=1, keepdims=True)
+            psi.append(m)
+        eng.init(np.tile(np.ones(B) / B, (len(graphs), 1)), np.stack(aff), psi if psi else None, seeds=seeds)
+        res = eng.em()
+        for g, r in enumerate(res):
+            st = eng.state(g)
             outs.append((st["gr"], st["affinity"], st["PSI"], r.FE, r.CVBayes, r.CVGP, r.CVGT, r.CVMAP, r.varCVBayes,
                          r.varCVGP, r.varCVGT, r.varCVMAP, bool(r.cnv), int(r.itrnum)))
+        if return_engine:
+            return outs, eng, res
     finally:
-        for eng in engines:
+        if not return_engine:
             eng.close()
     return outs

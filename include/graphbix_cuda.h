@@ -185,7 +185,12 @@ int64_t gbx_mod_launch_count(const gbx_mod* h);
  * `links3` is the notebook's K x 3 Int64 matrix (i, j, label) in column-major order, both directions of every edge with
  * the same label (`labeledsimplegraph`).  The initial affinity matrices (notebook EM, "initial state": from Larray,
  * assortativity and Omega) and the random initial messages are computed by the host and handed over; affinity is
- * double[n_labels][q][q].  First CUDA path of this model: correct and parity-tested, not yet tuned (gbx_lsbm.cu).
+ * double[n_labels][q][q].
+ * A handle holds one graph (gbx_lsbm_create) or many (gbx_lsbm_create_batch: BASELINE configs[4], a detectability sweep
+ * over thousands of N = 10k graphs).  The graphs of a batch share q, the number of labels and the options; every kernel
+ * launch serves all of them (grid y index = graph), each graph keeps its own parameters, residual and convergence
+ * stamp, and what gbx_lsbm_em returns for graph g is what a handle of its own would return (same kernels; sums are
+ * accumulated with floating-point atomics, so to rounding).
  * ------------------------------------------------------------------------------------------------ */
 #define GBX_MAX_LABELS 4
 typedef struct gbx_lsbm gbx_lsbm;
@@ -211,22 +216,32 @@ typedef struct gbx_lsbm_result {
 void gbx_lsbm_default_options(gbx_lsbm_options* opt);
 int gbx_lsbm_create(gbx_lsbm** out, int device, int64_t n_vertices, int64_t n_links, const int64_t* links3, int q,
                     int n_labels);
+/* `count` graphs in one handle: n_vertices[g], n_links[g], links3[g] (K_g x 3, column-major, vertices 1..n_vertices[g]) */
+int gbx_lsbm_create_batch(gbx_lsbm** out, int device, int count, const int64_t* n_vertices, const int64_t* n_links,
+                          const int64_t* const* links3, int q, int n_labels);
+int gbx_lsbm_count(const gbx_lsbm* h);                               /* graphs in the handle                  */
 int gbx_lsbm_destroy(gbx_lsbm* h);
 int gbx_lsbm_set_stream(gbx_lsbm* h, void* cuda_stream);
 int gbx_lsbm_set_options(gbx_lsbm* h, const gbx_lsbm_options* opt);
 /* gr[q], affinity[n_labels][q][q], psicav[K][q] (rows in `links3` order); then PSI = updatePSI(), h = update_h(). */
 int gbx_lsbm_init(gbx_lsbm* h, const double* gr, const double* affinity, const double* psicav);
-int gbx_lsbm_em(gbx_lsbm* h, gbx_lsbm_result* res);                  /* the main loop + freeenergy()          */
-/* EM() of `count` initialised handles of one device side by side (BASELINE configs[4]: a detectability sweep over
- * thousands of N = 10k graphs): each handle runs on a stream of its own for the call, up to `max_concurrent` (0 = 16) at
- * a time, so the kernels of different graphs overlap and the launch latency is hidden.  res[i] is what gbx_lsbm_em
- * returns for hs[i] (same kernels in the same order).                                                              */
+/* the same for every graph of a batch: gr[count][q], affinity[count][n_labels][q][q], psicav[g] -> K_g x q */
+int gbx_lsbm_init_batch(gbx_lsbm* h, const double* gr, const double* affinity, const double* const* psicav);
+/* the same with the initial messages (rand(1,B) per link, normalised) drawn on the device: row k of graph g from
+ * (seeds[g], k), so a graph starts from the same messages alone and inside a batch; seeds[gbx_lsbm_count(h)] */
+int gbx_lsbm_init_random(gbx_lsbm* h, const double* gr, const double* affinity, const uint64_t* seeds);
+/* the main loop + freeenergy() of every graph of the handle; res[gbx_lsbm_count(h)] */
+int gbx_lsbm_em(gbx_lsbm* h, gbx_lsbm_result* res);
+/* gbx_lsbm_em on `count` initialised handles one after the other (res: one entry per graph, handle by handle); many
+ * graphs run faster in ONE handle (gbx_lsbm_create_batch).  `max_concurrent` is ignored.                          */
 int gbx_lsbm_em_batch(gbx_lsbm** hs, int count, gbx_lsbm_result* res, int max_concurrent);
-int gbx_lsbm_iterate(gbx_lsbm* h, int n_iters, double* bpconv_out);  /* n x (update_h, BP sweep, gr, affinity) */
-int gbx_lsbm_finalize(gbx_lsbm* h, gbx_lsbm_result* res);            /* freeenergy()                          */
-/* gr[q], affinity[n_labels][q][q], PSI[N][q], hfield[n_labels][q]; any may be NULL */
+int gbx_lsbm_iterate(gbx_lsbm* h, int n_iters, double* bpconv_out);  /* n x (update_h, BP sweep, gr, affinity); residual of graph 0 */
+int gbx_lsbm_finalize(gbx_lsbm* h, gbx_lsbm_result* res);            /* freeenergy() of every graph           */
+/* gr[q], affinity[n_labels][q][q], PSI[N][q], hfield[n_labels][q]; any may be NULL.  _of: graph g of a batch */
 int gbx_lsbm_get_state(gbx_lsbm* h, double* gr, double* affinity, double* PSI, double* hfield);
+int gbx_lsbm_get_state_of(gbx_lsbm* h, int g, double* gr, double* affinity, double* PSI, double* hfield);
 int gbx_lsbm_get_messages(gbx_lsbm* h, double* psicav);
+int gbx_lsbm_get_messages_of(gbx_lsbm* h, int g, double* psicav);
 int64_t gbx_lsbm_launch_count(const gbx_lsbm* h);
 
 /* ------------------------------------------------------------------------------------------------

@@ -161,25 +161,61 @@ def test_reference_fixture_three_blocks_and_qstar(gpu_required):
     assert cv[4] > cv[3] - 2 * se[3]                               # ... and B = 4 is no significant improvement: q* = 3
 
 
-def test_labeled_batch_equals_one_at_a_time(gpu_required):
-    """gbx_lsbm_em_batch: several graphs side by side (more graphs than concurrent streams, so streams are handed on) give
-    what gbx_lsbm_em gives one at a time: same itrnum, same state up to the rounding of the atomics."""
+@pytest.mark.parametrize("B", [2, 3])
+def test_labeled_batch_equals_one_at_a_time(gpu_required, B):
+    """gbx_lsbm_create_batch: several graphs of different sizes in ONE handle (one launch set per EM iteration for all of
+    them; graphs converge at different iterations and drop out of the live list) give what a handle of their own gives:
+    same itrnum, same state and messages up to the rounding of the atomics."""
     from graphbix_b200.labeled import EM_labeled, EM_labeled_batch
     from graphbix_b200.synth import labeled_planted_partition
-    graphs, singles = [], []
+    graphs, singles, psi0 = [], [], []
     for k in range(7):
-        n, B = 600 + 100 * k, 2 + (k % 2)
-        links, _ = labeled_planted_partition(n, B, [5.0, 3.0], ["a", "d"], 0.1, seed=40 + k)
+        n = 600 + 100 * k
+        links, _ = labeled_planted_partition(n, B, [5.0, 3.0], ["a", "d"], 0.05 + 0.1 * k, seed=40 + k)
         und = links[links[:, 0] < links[:, 1]]
         Larray = [int((und[:, 2] == a + 1).sum()) for a in range(2)]
         graphs.append((n, Larray, B, 2, links))
-        singles.append(EM_labeled(n, Larray, B, 2, links, 512, 1e-8, True, True, True, 0.3, 0, ["a", "d"], 1 / B,
-                                  rng=np.random.default_rng(k)))
-    batch = EM_labeled_batch(graphs, 512, 1e-8, True, True, True, 0.3, 0, ["a", "d"],
-                             rngs=[np.random.default_rng(k) for k in range(7)], max_concurrent=3)
-    assert len(batch) == 7
-    for s, b in zip(singles, batch):
+        m = np.random.default_rng(k).random((links.shape[0], B))
+        psi0.append(m / m.sum(axis=1, keepdims=True))
+        singles.append(EM_labeled(n, Larray, B, 2, links, 300, 1e-8, True, True, True, 0.3, 0, ["a", "d"], 1 / B,
+                                  PSIcav0=psi0[-1], return_engine=True))
+    batch, eng, res = EM_labeled_batch(graphs, 300, 1e-8, True, True, True, 0.3, 0, ["a", "d"], PSIcav0=psi0,
+                                       return_engine=True)
+    assert len(batch) == 7 and eng.count == 7
+    assert len({b[13] for b in batch}) > 1                         # they did not all stop at the same iteration
+    for g, ((s, seng, sres), b) in enumerate(zip(singles, batch)):
         assert s[12] == b[12] and s[13] == b[13]
-        np.testing.assert_allclose(b[2], s[2], rtol=0, atol=1e-12)
-        np.testing.assert_allclose(b[1], s[1], rtol=1e-10)
-        np.testing.assert_allclose(b[3:12], s[3:12], rtol=1e-9)
+        assert sres.itrs_done == res[g].itrs_done
+        np.testing.assert_allclose(b[2], s[2], rtol=0, atol=1e-11)
+        np.testing.assert_allclose(b[1], s[1], rtol=1e-9)
+        np.testing.assert_allclose(b[3:12], s[3:12], rtol=1e-8)
+        np.testing.assert_allclose(eng.messages(g), seng.messages(), rtol=0, atol=1e-11)
+        seng.close()
+    eng.close()
+
+
+def test_labeled_batch_rejects_bad_input(gpu_required):
+    from graphbix_b200.labeled import LabeledBatch
+    from graphbix_b200._lib import GbxError
+    links = np.array([[1, 2, 1], [2, 1, 1]], dtype=np.int64)
+    with pytest.raises(GbxError):
+        LabeledBatch([(2, links), (2, np.array([[1, 3, 1], [3, 1, 1]], dtype=np.int64))], 2, 1)   # vertex 3 of a 2-vertex graph
+    with pytest.raises(GbxError):
+        LabeledBatch([(2, links), (2, np.array([[1, 2, 1], [2, 1, 2]], dtype=np.int64))], 2, 2)   # directions disagree in label
+
+
+def test_labeled_device_random_messages_same_alone_and_in_batch(gpu_required):
+    """gbx_lsbm_init_random: a graph starts from the same device-drawn messages in a handle of its own and inside a batch."""
+    from graphbix_b200.labeled import EM_labeled, EM_labeled_batch
+    from graphbix_b200.synth import labeled_planted_partition
+    graphs = []
+    for k in range(3):
+        links, _ = labeled_planted_partition(500 + 50 * k, 2, [5.0, 3.0], ["a", "d"], 0.1, seed=7 + k)
+        und = links[links[:, 0] < links[:, 1]]
+        graphs.append((500 + 50 * k, [int((und[:, 2] == a + 1).sum()) for a in range(2)], 2, 2, links))
+    batch = EM_labeled_batch(graphs, 200, 1e-8, True, True, True, 0.3, 0, ["a", "d"], seeds=[11, 12, 13])
+    for k, g in enumerate(graphs):
+        s = EM_labeled(*g[:4], g[4], 200, 1e-8, True, True, True, 0.3, 0, ["a", "d"], 0.5, seed=11 + k)
+        assert s[13] == batch[k][13] and s[12] == batch[k][12]
+        np.testing.assert_allclose(batch[k][2], s[2], rtol=0, atol=1e-11)
+        assert abs(s[2].sum(axis=1) - 1).max() < 1e-12
