@@ -205,7 +205,7 @@ int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* 
       last_error() = "too many edge slots on one rank (limit 2^29)";
       return fail(GBX_ERR_INVALID);
     }
-  if (h->ops && h->ops->pull_ok) {  // link <-> slot maps of the pull layout, while the sorted values are still around
+  if (want_pull_layout(h->ops, h->world)) {  // link <-> slot maps of the pull layout, while the sorted values are still around
     GBX_C(dev_malloc(dv, (void**)&h->in_link, (size_t)std::max<long long>(h->K, 1) * sizeof(int), pooled));
     GBX_C(dev_malloc(dv, (void**)&h->out_link, (size_t)std::max<long long>(h->K, 1) * sizeof(int), pooled));
     h->dev_bytes += 2 * (int64_t)h->K * sizeof(int);

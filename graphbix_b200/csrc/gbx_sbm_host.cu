@@ -460,7 +460,7 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
     GBX_TRY(dev_alloc(h, &h->msg[1], (size_t)K * h->qm));
     GBX_TRY(dev_alloc(h, &h->PSI, (size_t)n * q));
     GBX_TRY(dev_alloc(h, &h->theta, (size_t)h->n_global + MAXPEER));
-    if (ops->pull_ok) {  // pull sweeps: per-vertex records of ALL vertices (two generations; in a partitioned run every
+    if (want_pull_layout(ops, world)) {  // pull sweeps: per-vertex records of ALL vertices (two generations; in a partitioned run every
                          // rank stores its vertices' records into every rank's copy), two theta generations of this rank's
                          // vertices, the degree of every slot's neighbour
       GBX_TRY(dev_alloc(h, &h->theta_pp[0], (size_t)n + 2));

@@ -204,4 +204,16 @@ struct SbmOps {
   int (*pull_export)(gbx_sbm* h, double* dst_dev);                      // current messages in `links` order
 };
 
+// The pull layout (records, neighbour degrees, link <-> slot maps) is built only for handles that may sweep with the pull
+// kernels: partitioned runs (their default) and single-GPU handles created under GBX_PULL=1.
+inline bool want_pull_layout(const SbmOps* ops, int world);
+
 }  // namespace gbx
+
+#include <cstdlib>
+inline bool gbx::want_pull_layout(const gbx::SbmOps* ops, int world) {
+  if (!ops || !ops->pull_ok) return false;
+  if (world > 1) return true;
+  const char* e = getenv("GBX_PULL");
+  return e && atoi(e) != 0;
+}
