@@ -416,9 +416,82 @@ __global__ void __launch_bounds__(MSTEP_THREADS) k_lsbm_mstep(const LGraph* __re
   __shared__ unsigned char labS[MSTEP_THREADS];
   const int q = QT > 0 ? QT : qrt;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, qq = q * q;
-  double* rows = dyn + (size_t)warp * 32 * 2 * q;
   for (int k = threadIdx.x; k < G * qq; k += blockDim.x) sh[k] = 0.0;
   __syncthreads();
+  if constexpr (QT > 0 && QT <= 8) {
+    // q <= 8: the sum of outer products of a warp's 32 links is a (q x 32)(32 x q) product -> FP64 DMMA m8n8k4 over
+    // groups of 4 links, one accumulator (two registers per lane) per label; operands of other labels are zeroed.
+    constexpr int RS = 9;                                 // row stride (doubles): conflict-free for rows and fragments
+    double* ra = dyn + (size_t)warp * 32 * 2 * RS;        // a / Z of the warp's 32 links
+    double* rb = ra + 32 * RS;                            // the message of the other direction
+    double c0[LMAXG], c1[LMAXG];
+#pragma unroll
+    for (int g = 0; g < LMAXG; ++g) c0[g] = c1[g] = 0.0;
+    const int kq = lane & 3, cidx = lane >> 2;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long chunks = (gg.K + 31) / 32;
+    for (long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < chunks; c += nwarps) {
+      const long long k = c * 32 + lane;
+      const long long e = gg.sbeg + k;
+      unsigned char L = 255;
+      if (k < gg.K && erow[e] < col[e]) {                 // row i < column j: every undirected link once
+        L = lab[e];
+        const double* A = P->aff[L];
+        double mij[QT], mji[QT];
+        load_vec<QT>(cur, rev[e], mij);                   // i -> j
+        load_vec<QT>(cur, e, mji);                        // j -> i
+        double Z = 0.0;
+#pragma unroll
+        for (int r = 0; r < QT; ++r) {
+          double t = 0.0;
+#pragma unroll
+          for (int s2 = 0; s2 < QT; ++s2) t += mji[s2] * A[r * QT + s2];
+          Z += mij[r] * t;
+        }
+        const double inv = 1.0 / Z;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          ra[lane * RS + r] = r < QT ? mij[r] * inv : 0.0;
+          rb[lane * RS + r] = r < QT ? mji[r] : 0.0;
+        }
+      }
+      labS[threadIdx.x] = L;
+      __syncwarp();
+#pragma unroll
+      for (int grp = 0; grp < 8; ++grp) {
+        const int row = 4 * grp + kq;
+        const unsigned char Lr = labS[(warp << 5) + row];
+        const double av = ra[row * RS + cidx], bv = rb[row * RS + cidx];
+#pragma unroll
+        for (int g = 0; g < LMAXG; ++g) {
+          if (g < G) {   // warp-uniform
+            const bool on = Lr == g;
+            const double a = on ? av : 0.0, b = on ? bv : 0.0;
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c0[g]), "+d"(c1[g])
+                         : "d"(a), "d"(b));
+          }
+        }
+      }
+      __syncwarp();
+    }
+    // accumulator layout: lane holds (row = lane / 4, columns 2 (lane % 4), + 1)
+#pragma unroll
+    for (int g = 0; g < LMAXG; ++g) {
+      const int r = lane >> 2, s0 = 2 * (lane & 3);
+      if (g < G && r < QT) {
+        if (s0 < QT && c0[g] != 0.0) atomicAdd(&sh[g * qq + r * QT + s0], c0[g]);
+        if (s0 + 1 < QT && c1[g] != 0.0) atomicAdd(&sh[g * qq + r * QT + s0 + 1], c1[g]);
+      }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < G * qq; k += blockDim.x) {
+      const int g = k / qq, rs = k % qq;
+      if (sh[k] != 0.0) atomicAdd(&P->Gnew[g][rs], sh[k] * P->aff[g][rs]);
+    }
+    return;
+  }
+  double* rows = dyn + (size_t)warp * 32 * 2 * q;
   constexpr int EPL = ((QT > 0 ? QT * QT : MAXQ * MAXQ) + 31) / 32;         // entries (r,s) a lane may own
   double acc[LMAXG][EPL];
 #pragma unroll
@@ -768,7 +841,7 @@ int l_iteration(gbx_lsbm* h) {
   L_TRY(l_denom(h));                                            // from the new marginals
   if (h->opt.learning && h->g.K > 0) {
     const dim3 mg = l_grid(h, h->Kmax, MSTEP_THREADS, ng);
-    const size_t msm = (size_t)(MSTEP_THREADS / 32) * 32 * 2 * h->q * sizeof(double);
+    const size_t msm = (size_t)(MSTEP_THREADS / 32) * 32 * 2 * std::max(h->q, 9) * sizeof(double);
 #define GBX_LSBM_MSTEP(QT)                                                                                                  \
   k_lsbm_mstep<QT><<<mg, MSTEP_THREADS, msm, st>>>(h->gt, l_live(h), h->q, h->G, h->g.erow, h->g.col, h->g.rev, h->lab, \
                                                    h->msg[0], h->msg[1], h->P, it)

@@ -170,8 +170,9 @@ def initial_parameters(initial: str, B: int, rng: np.random.Generator):
 
 def EM(Ntot, B, links, maxCrs, initial, degreecorrection, itrmax, priorlearning, learningrate, *,
        rng=None, PSIcav0=None, seed=0, BPconvthreshold=0.000001, damping=1.0, device=0, engine=None,
-       return_engine=False):
-    """Drop-in for the reference's EM(), sbm.jl:28.  `initial` is a name or a `(gr, Crs)` pair."""
+       return_engine=False, stream=None):
+    """Drop-in for the reference's EM(), sbm.jl:28.  `initial` is a name or a `(gr, Crs)` pair.  `stream`: CUDA stream of
+    the run (runs of DIFFERENT q on streams of their own overlap on one GPU, see parallel.threaded_sweep)."""
     rng = rng if rng is not None else np.random.default_rng(seed)
     if isinstance(initial, str):
         if initial == "normalizedLaplacian":
@@ -181,7 +182,7 @@ def EM(Ntot, B, links, maxCrs, initial, degreecorrection, itrmax, priorlearning,
             gr0, Crs0 = initial_parameters(initial, B, rng)
     else:
         gr0, Crs0 = initial
-    eng = engine if engine is not None else SbmEngine(Ntot, links, B, device=device)
+    eng = engine if engine is not None else SbmEngine(Ntot, links, B, device=device, stream=stream)
     eng.set_options(degreecorrection=int(bool(degreecorrection)), priorlearning=int(bool(priorlearning)),
                     learningrate=float(learningrate), maxCrs=float(maxCrs), itrmax=int(itrmax),
                     bp_conv_threshold=float(BPconvthreshold), damping=float(damping))
@@ -288,10 +289,10 @@ class ModEngine:
 
 
 def EM_mod(gr, Ntot, B, links, maxomega, itrmax, betafrac, learning, priorlearning, dc, learningrate, *,
-           PSIcav0=None, seed=0, BPconvthreshold=0.000001, damping=1.0, device=0, return_engine=False):
+           PSIcav0=None, seed=0, BPconvthreshold=0.000001, damping=1.0, device=0, return_engine=False, stream=None):
     """Drop-in for mod.jl's EM(), mod.jl:3.  Returns the reference's 17-tuple
     (excm,alpha,beta,omegain,omegaout,PSI,FE,CVBayes,CVGP,CVGT,CVMAP,varCVBayes,varCVGP,varCVGT,varCVMAP,cnv,itrnum)."""
-    eng = ModEngine(Ntot, links, B, device=device)
+    eng = ModEngine(Ntot, links, B, device=device, stream=stream)
     eng.set_options(dc=int(bool(dc)), learning=int(bool(learning)), priorlearning=int(bool(priorlearning)),
                     learningrate=float(learningrate), maxomega=float(maxomega), itrmax=int(itrmax),
                     betafrac=float(betafrac), bp_conv_threshold=float(BPconvthreshold), damping=float(damping))

@@ -42,6 +42,31 @@ def sweep(tasks: Iterable, run_task: Callable[[object, int], object], *, backend
     return out
 
 
+def threaded_sweep(tasks: Iterable, run_task: Callable[[object, object], object], *, device: int = 0, max_workers: int = 0):
+    """The q values of a sweep that land on ONE GPU, side by side: a host thread and a CUDA stream per task (ctypes
+    releases the GIL inside libgraphbix_cuda, so the launches of the runs interleave and their kernels overlap on the
+    GPU; every q has its own parameter block in constant memory).  `run_task(task, stream)` must pass `stream` on to
+    EM(..., stream=stream) / EM_mod(..., stream=stream).  Tasks of EQUAL q must not run concurrently on one device
+    (include/graphbix_cuda.h): give each q one task, or loop over the samples of a q inside the task.  Returns the
+    results in task order."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    tasks = list(tasks)
+    if not tasks:
+        return []
+    workers = max_workers or len(tasks)
+
+    def one(t):
+        torch.cuda.set_device(device)
+        st = torch.cuda.Stream(device=device)
+        out = run_task(t, st)
+        st.synchronize()
+        return out
+
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        return list(ex.map(one, tasks))
+
+
 def _has_cuda() -> bool:
     try:
         import torch
