@@ -19,6 +19,7 @@
 //   k_lsbm_pre / k_lsbm_post   h = update_h(); gr and affinity updates with the learning rate
 //   k_lsbm_fe<PASS>       log Z^{ij}, Gibbs / MAP errors per edge                     (freeenergy)
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -37,6 +38,7 @@ enum { LMODE_SWEEP = 0, LMODE_MARGINAL = 1, LMODE_LOGZ = 2 };
 
 struct LParams {
   double gr[MAXQ];
+  double lgr[MAXQ];                  // log(gr), refreshed whenever gr changes (k_lsbm_post; gbx_lsbm_init)
   double aff[LMAXG][MAXQ * MAXQ];   // row-major B x B per label
   double h[LMAXG][MAXQ];
   double denom[LMAXG][MAXQ];
@@ -97,23 +99,6 @@ __device__ __forceinline__ double l_rcp(double x) {
   e = fma(-x, r, 1.0);
   r = fma(r, e, r);
   return r;
-}
-// normalize_logprob (notebook): clamp at log(1e-8), then exp(x - logsumexp(x)) with logsumexp's 500 cut-off.
-__device__ __forceinline__ void normalize_logprob(const double* x, int q, double* p) {
-  double m = -INFINITY;
-  for (int t = 0; t < q; ++t) {
-    const double y = x[t] < LOG1EM8 ? LOG1EM8 : x[t];
-    p[t] = y;
-    m = fmax(m, y);
-  }
-  double s = 0.0;
-  for (int t = 0; t < q; ++t) {
-    const double y = (m - p[t] > 500.0) ? m - 500.0 : p[t];
-    p[t] = exp(y - m);
-    s += p[t];
-  }
-  const double inv = 1.0 / s;
-  for (int t = 0; t < q; ++t) p[t] *= inv;
 }
 __device__ __forceinline__ double logsumexp_dev(const double* x, int q) {
   double m = -INFINITY;
@@ -281,15 +266,40 @@ __global__ void __launch_bounds__(256) k_lsbm_vertex(const LGraph* __restrict__ 
         if (valid)
           for (int a = 0; a < G; ++a) ext += deg[(size_t)i * G + a] * P->h[a][t];
         // sum of the log terms, then prior and field as logunnormalizedMessage adds them
-        x[t] = (log(m) + (double)k * 0.6931471805599453) + (log(P->gr[t]) - ext);
+        x[t] = (log(m) + (double)k * 0.6931471805599453) + (P->lgr[t] - ext);
       }
     }
     if (MODE == LMODE_LOGZ) {
       if (valid && lane == 0) acc += logsumexp_dev(x, q);
       continue;
     }
-    double w[QA];
-    normalize_logprob(x, q, w);
+    // normalize_logprob(x): weights in the scale of the largest component, the clamp at log(1e-8) as a floor in that
+    // scale (the 500 cut-off of logsumexp cannot bind above the floor by more than e^-500)
+    double M = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < QA; ++t)
+      if (t < q) M = fmax(M, x[t]);
+    const double lfl = LOG1EM8 - M;
+    const bool all_floor = lfl > 700.0;          // every component is below 1e-8: flat
+    const double fl = all_floor ? 1.0 : exp(lfl);
+    double y[QA], w[QA];
+    {
+      double S = 0.0;
+#pragma unroll
+      for (int t = 0; t < QA; ++t) {
+        if (t < q) {
+          y[t] = exp(x[t] - M);
+          double c = (y[t] < fl) ? fl : y[t];
+          if (all_floor) c = 1.0;
+          w[t] = c;
+          S += c;
+        }
+      }
+      const double inv = 1.0 / S;
+#pragma unroll
+      for (int t = 0; t < QA; ++t)
+        if (t < q) w[t] *= inv;
+    }
     if (valid && lane == 0) {
       for (int t = 0; t < q; ++t) {
         if (MODE == LMODE_SWEEP) acc += fabs(w[t] - PSI[(size_t)i * q + t]) / N;
@@ -298,18 +308,7 @@ __global__ void __launch_bounds__(256) k_lsbm_vertex(const LGraph* __restrict__ 
     }
     __syncwarp();   // lane 0 has read the old marginal
     if (MODE == LMODE_SWEEP) {
-      // weights of the vertex in the scale of its largest component, and the clamp floor 1e-8 in that scale
-      double M = -INFINITY;
-#pragma unroll
-      for (int t = 0; t < QA; ++t)
-        if (t < q) M = fmax(M, x[t]);
-      double y[QA];
-#pragma unroll
-      for (int t = 0; t < QA; ++t)
-        if (t < q) y[t] = exp(x[t] - M);
-      const double lfl = LOG1EM8 - M;
-      const bool all_floor = lfl > 700.0;          // every cavity component is below 1e-8: the message is flat
-      const double fl = all_floor ? 1.0 : exp(lfl);
+      // cavities: the vertex's weights y (scale of its largest component) over the link's term, same floor
       for (int base = e0; base < e1; base += LPV) {
         const int e = base + lane;
         if (e < e1) {
@@ -604,6 +603,7 @@ __global__ void k_lsbm_post(const LGraph* __restrict__ gt, const int* __restrict
   if (prior && tid < q) {
     const double g = P->sumPSI[tid] / N;
     P->gr[tid] = lr * g + (1.0 - lr) * g;
+    P->lgr[tid] = log(P->gr[tid]);
   }
   if (learning) {
     for (int k = tid; k < G * q * q; k += blockDim.x) {
@@ -1067,7 +1067,10 @@ int l_init(gbx_lsbm* h, const double* gr, const double* affinity, const double* 
   memset(h->hP, 0, sizeof(LParams) * (size_t)h->count);
   for (int g = 0; g < h->count; ++g) {
     LParams* s = h->hP + g;
-    for (int t = 0; t < q; ++t) s->gr[t] = gr[(size_t)g * q + t];
+    for (int t = 0; t < q; ++t) {
+      s->gr[t] = gr[(size_t)g * q + t];
+      s->lgr[t] = std::log(s->gr[t]);
+    }
     for (int a = 0; a < G; ++a)
       for (int k = 0; k < q * q; ++k) s->aff[a][k] = affinity[((size_t)g * G + a) * q * q + k];
   }

@@ -10,7 +10,7 @@ pins this transcription: with one label, no degree correction and learning switc
 cross-validation errors equal those of oracle/sbm_oracle.py for Crs = Ntot * affinity (tests/test_oracle_labeled.py),
 which is itself cross-checked against a C transcription, exact enumeration on trees and the q = 1 closed form.
 
-This is the oracle for DESIGN.md row (f'): the CUDA path of this model is not built yet.  Only tests/ may import it.
+This is the oracle for DESIGN.md row (f') (CUDA path: graphbix_b200/csrc/gbx_lsbm.cu).  Only tests/, smoke() and the CPU-baseline leg of bench.py may import it.
 
 Conventions kept from the notebook
   * `links` is K x 3 (i, j, label), 1-based vertices, labels 1..G, BOTH directions of every undirected edge with the
