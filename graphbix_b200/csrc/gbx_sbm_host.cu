@@ -306,6 +306,21 @@ static int fill_async(gbx_sbm* h, double* p, int64_t n, double v) {
 }
 
 // GBX_TIMING=1: host wall time of the phases of gbx_*_create on stderr.
+// slot -> vertex inside its tile (one block per tile, a thread per vertex of the tile)
+__global__ void k_slot_lv(const int4* __restrict__ tiles, const int* __restrict__ rowptr, unsigned char* __restrict__ lv) {
+  const int4 t = tiles[blockIdx.x];
+  for (int v = threadIdx.x; v < t.y; v += blockDim.x)
+    for (int e = rowptr[t.x + v]; e < rowptr[t.x + v + 1]; ++e) lv[e] = (unsigned char)v;
+}
+// degree of the neighbour of every slot: from the local row pointers (one rank) or the degrees by global id
+__global__ void k_neighbour_degree(const int* __restrict__ col, const int* __restrict__ rowptr, const double* __restrict__ deg_global,
+                                   long long K, float* __restrict__ out) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < K; e += (long long)gridDim.x * blockDim.x) {
+    const int j = col[e];
+    out[e] = rowptr ? (float)(rowptr[j + 1] - rowptr[j]) : (float)deg_global[j];
+  }
+}
+
 struct PhaseTimer {
   bool on = getenv("GBX_TIMING") != nullptr;
   std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
@@ -453,7 +468,10 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
   pt.lap("degree statistics (host)");
   gbx_sbm_default_options(&h->opt);
   auto body = [&]() -> int {
-    GBX_TRY(dev_alloc(h, &h->escale, (size_t)K));
+    // static per-slot data of the sweeps: the vertex (inside its tile) of every slot, and for sbm.jl the degree of every
+    // slot's neighbour (theta_neighbour = degree / <degree of its MAP block>: the block arrives with the message)
+    GBX_TRY(dev_alloc(h, &h->slot_lv, (size_t)K + 16));
+    if (model == 0) GBX_TRY(dev_alloc(h, &h->coldeg, (size_t)K + 4));
     GBX_TRY(dev_alloc(h, &h->tiles, tiles.size()));
     GBX_TRY(dev_alloc(h, &h->hubs, hubs.size()));
     GBX_TRY(dev_alloc(h, &h->msg[0], (size_t)K * h->qm));
@@ -467,15 +485,7 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
       GBX_TRY(dev_alloc(h, &h->theta_pp[1], (size_t)n + 2));
       GBX_TRY(dev_alloc(h, &h->rec[0], (size_t)h->n_global * h->qm));
       GBX_TRY(dev_alloc(h, &h->rec[1], (size_t)h->n_global * h->qm));
-      GBX_TRY(dev_alloc(h, &h->coldeg, (size_t)K));
-      GBX_TRY(dev_alloc(h, &h->slot_lv, (size_t)K));
-      {
-        std::vector<unsigned char> lv((size_t)std::max<int64_t>(K, 1), 0);
-        for (const int4& t : tiles)
-          for (int v = 0; v < t.y; ++v)
-            for (int e = rowptr[(size_t)t.x + v]; e < rowptr[(size_t)t.x + v + 1]; ++e) lv[(size_t)e] = (unsigned char)v;
-        GBX_CUDA_TRY(cudaMemcpy(h->slot_lv, lv.data(), (size_t)K, cudaMemcpyHostToDevice));
-      }
+      if (!h->coldeg) GBX_TRY(dev_alloc(h, &h->coldeg, (size_t)K + 4));
       GBX_CUDA_TRY(cudaMemsetAsync(h->rec[0], 0, (size_t)h->n_global * h->qm * sizeof(double), h->stream));
       GBX_CUDA_TRY(cudaMemsetAsync(h->rec[1], 0, (size_t)h->n_global * h->qm * sizeof(double), h->stream));
       h->recp[0][h->rank] = h->rec[0];
@@ -483,8 +493,8 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
     }
     GBX_TRY(dev_alloc(h, &h->totals, (size_t)TOT_MAX));
     GBX_TRY(dev_alloc(h, &h->maxd_dev, 1));
-    if (model == 1 || (ops->pull_ok && world > 1)) {  // degree of every vertex by global id: the field of mod.jl's sweep
-                                                       // and free energy; the neighbour degrees of a partitioned pull run
+    if (model == 1 || world > 1) {  // degree of every vertex by global id: the field of mod.jl's sweep and free energy;
+                                    // the neighbour degrees of a partitioned run
       GBX_TRY(dev_alloc(h, &h->deg_global, (size_t)h->n_global));
       std::vector<double> dg((size_t)h->n_global);
       for (int64_t v = 0; v < h->n_global; ++v) dg[(size_t)v] = (double)(rowptr_g[(size_t)v + 1] - rowptr_g[(size_t)v]);
@@ -498,6 +508,11 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
     GBX_TRY(dev_alloc(h, &h->st, 1));
     GBX_TRY(dev_alloc(h, &h->params, 1));
     GBX_CUDA_TRY(cudaMemcpy(h->tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    if (!tiles.empty()) k_slot_lv<<<(unsigned)tiles.size(), 64, 0, h->stream>>>(h->tiles, h->rowptr, h->slot_lv);
+    if (h->coldeg && K > 0)
+      k_neighbour_degree<<<(unsigned)std::min<int64_t>((K + 255) / 256, (int64_t)h->num_sms * 8), 256, 0, h->stream>>>(
+          h->col, world > 1 ? nullptr : h->rowptr, h->deg_global, (long long)K, h->coldeg);
+    GBX_CUDA_TRY(cudaGetLastError());
     GBX_CUDA_TRY(cudaMemcpy(h->hubs, hubs.data(), hubs.size() * sizeof(int), cudaMemcpyHostToDevice));
     GBX_CUDA_TRY(cudaMemset(h->st, 0, sizeof(SbmState)));
     GBX_CUDA_TRY(pinned_state_alloc(&h->h_state));
@@ -576,7 +591,6 @@ int gbx_sbm_destroy(gbx_sbm* h) {
   dev_free(h->device, h->col);
   dev_free(h->device, h->rev);
   dev_free(h->device, h->erow);
-  dev_free(h->device, h->escale);
   dev_free(h->device, h->slot_of_link);
   dev_free(h->device, h->tiles);
   dev_free(h->device, h->hubs);
@@ -656,7 +670,6 @@ int gbx_sbm_init(gbx_sbm* h, const double* gr_init, const double* Crs_init, cons
     GBX_TRY(fill_async(h, h->theta, h->n_global, 1.0));  // theta = ones(Ntot,1), sbm.jl:277
     if (h->theta_pp[0]) GBX_TRY(fill_async(h, h->theta_pp[0], h->n, 1.0));
     if (h->theta_pp[1]) GBX_TRY(fill_async(h, h->theta_pp[1], h->n, 1.0));
-    GBX_TRY(fill_async(h, h->escale, h->K, 1.0));
   }
   if (!h->fail && !h->stepped) {
     // PSI = updatePSI() with h = 0, then gr = update_gr(PSI): sbm.jl:340-341
@@ -820,10 +833,10 @@ double gbx_sbm_sweep_bytes(const gbx_sbm* h) {
     const double pv = 2.0 * q * 8.0 + 2.0 * q * 8.0 + 4.0 + 4.0 + (dc ? 16.0 : 0.0);
     return K * pe + n * pv;
   }
-  double per_edge = 2.0 * q * 8.0 + 4.0;
-  if (dc) per_edge += 8.0;
+  double per_edge = 2.0 * q * 8.0 + 4.0 + 1.0;          // message read, message written, rev, slot -> vertex byte
+  if (dc) per_edge += 4.0;                              // degree of the neighbour
   if (damping != 1.0) per_edge += q * 8.0;             // old outgoing message
-  const double per_vertex = 2.0 * q * 8.0 + 4.0 + 4.0;
+  const double per_vertex = 2.0 * q * 8.0 + 4.0 + 4.0 + (dc ? 8.0 : 0.0);   // marginal r/w, row pointer, prior row, theta
   return K * per_edge + n * per_vertex;
 }
 

@@ -106,7 +106,6 @@ struct gbx_sbm {
   int *rowptr = nullptr, *col = nullptr, *rev = nullptr, *slot_of_link = nullptr, *hubs = nullptr;
   int* erow = nullptr;            // per edge slot: its row (destination vertex)
   int4* tiles = nullptr;          // (first vertex, #vertices, first edge slot, #edge slots)
-  double* escale = nullptr;       // per edge slot theta_row * theta_col (all ones until update_theta runs)
   int ntiles = 0, nhubs = 0, max_degree = 1;
   double* deg_global = nullptr;   // degree of every vertex, by global id
   // state (device)

@@ -8,7 +8,7 @@
 //   sbm_local_totals         per-CTA partial rows -> this rank's totals vector (one block per column, fixed order)
 //   sbm_apply_totals         residual, gr, block degree means, Crs update + clamp sbm.jl:120-123, 47-58, 137-147
 //   sbm_theta_kernel         update_theta, S_theta for update_h                  sbm.jl:47-64, 70-73
-//   sbm_escale_kernel        theta_row * theta_col per edge slot
+//   (theta_row * theta_col per edge slot is formed inside the sweeps: sender block in the message sign bits)
 //   sbm_prepare / sbm_prior_table   gr clamp, h, logs -> __constant__; prior factors per (degree, block) sbm.jl:89-96, 70-73
 //   sbm_fe_kernel<PASS>      log Z_ij, CV errors per edge                        sbm.jl:162-200
 //   sbm_finalize             FE, CV errors, variances                            sbm.jl:201-212
@@ -95,7 +95,8 @@ struct VertexArgs {
   const int* rowptr;
   const int* col;
   const int* rev;
-  const double* escale;  // per edge slot: theta_row * theta_col (degree-corrected runs), refreshed with theta
+  const float* coldeg;             // per edge slot: degree of the slot's neighbour (static; degree-corrected sbm.jl runs)
+  const unsigned char* slot_lv;    // per edge slot: its vertex inside its tile (static)
   const int4* tiles;     // [ntiles] (first vertex, #vertices, first edge slot, #edge slots)
   int ntiles;
   const int* hubs;    // vertex ids with degree > TILE_E
@@ -113,8 +114,8 @@ struct VertexArgs {
   const SbmState* st;   // for skip_iteration
   int it;
   double damping;
-  int dc;
-  int dc_model;   // == dc here (the pull kernel separates "degree correction on" from "thetas live")
+  int dc;         // sbm.jl: degree correction with live thetas (update_theta has run); mod.jl: degree correction
+  int dc_model;   // degree correction switched on at all
 };
 
 // ---- small device helpers ---------------------------------------------------------------------
@@ -142,6 +143,25 @@ __device__ __forceinline__ double fast_rcp(double x) {
   r = fma(r, e, r);
   return r;
 }
+// Degree-corrected sbm.jl runs: a message carries the MAP block of its SENDER in the sign bits of its first
+// ceil(log2 q) components (messages are positive).  The receiver needs theta_sender = degree_sender / <degree of that
+// block> for the edge factor (sbm.jl:87); the degree is a static per-slot value and the block means are q parameters, so
+// nothing per edge has to be recomputed when update_theta moves the thetas (no theta_row * theta_col pass over the slots).
+constexpr int NB_SIGN = (MODEL != 0 || Q <= 1) ? 0 : (Q <= 2 ? 1 : (Q <= 4 ? 2 : (Q <= 8 ? 3 : 4)));
+__device__ __forceinline__ int take_block_bits(double (&m)[Q]) {   // strips the bits, returns the block
+  int blk = 0;
+#pragma unroll
+  for (int b = 0; b < NB_SIGN; ++b) blk |= (int)((unsigned)__double2hiint(m[b]) >> 31) << b;
+#pragma unroll
+  for (int b = 0; b < NB_SIGN; ++b) m[b] = fabs(m[b]);
+  return blk;
+}
+__device__ __forceinline__ void put_block_bits(double (&m)[Q], int blk) {
+#pragma unroll
+  for (int b = 0; b < NB_SIGN; ++b)
+    if ((blk >> b) & 1) m[b] = __hiloint2double(__double2hiint(m[b]) | (int)0x80000000, __double2loint(m[b]));
+}
+
 // Reductions over the QP lanes that share a vertex.  They name all 32 lanes, so every call site must be reached by
 // the whole warp (the aggregation stage keeps its branches warp-uniform with a vote for that reason).
 template <typename T>
@@ -237,17 +257,26 @@ __device__ __forceinline__ void emit_message_local(const double* __restrict__ u,
   for (int t = 0; t < Q; ++t) w[t] *= inv;
 }
 __device__ __forceinline__ void emit_message(const VertexArgs& a, const double* __restrict__ u, const double (&T)[Q],
-                                             double ffrac, int n, int rv, double (&w)[Q]) {
+                                             double ffrac, int n, int rv, double (&w)[Q], int blk) {
   emit_message_local(u, T, ffrac, n, w);
   const int owner = rev_owner(rv), slot = rev_slot(rv);
   if (a.damping != 1.0) {
     double old[Q];
     load_msg<Q, QM>(a.curp[owner], slot, old);
+    take_block_bits(old);
     const double al = a.damping, be = 1.0 - a.damping;
 #pragma unroll
     for (int t = 0; t < Q; ++t) w[t] = be * old[t] + al * w[t];
   }
-  store_msg<Q, QM>(a.nxtp[owner], slot, w);
+  if constexpr (NB_SIGN > 0) {
+    double ws[Q];
+#pragma unroll
+    for (int t = 0; t < Q; ++t) ws[t] = w[t];
+    put_block_bits(ws, blk);   // the sender's MAP block travels with the message
+    store_msg<Q, QM>(a.nxtp[owner], slot, ws);
+  } else {
+    store_msg<Q, QM>(a.nxtp[owner], slot, w);
+  }
 }
 
 // ---- M-step statistics fused into the sweep ------------------------------------------------------------
@@ -579,12 +608,14 @@ __device__ __forceinline__ void edge_factor(const double (&psi)[Q], double sc, d
 // Per-tile inputs staged by cp.async, double buffered: nothing in the tile loop waits on a global load.
 struct StageBuf {
   static constexpr size_t psi_off = 0;                                   // ne messages (rotated units)
-  static constexpr size_t sc_off = psi_off + (size_t)TILE_E * ROWB;      // ne theta scales
-  static constexpr size_t rev_off = sc_off + (size_t)TILE_E * 8;         // ne reverse slots
+  static constexpr size_t th_off = psi_off + (size_t)TILE_E * ROWB;      // nv thetas of the tile's vertices
+  static constexpr size_t cd_off = th_off + (size_t)TV * 8;              // ne neighbour degrees (float)
+  static constexpr size_t rev_off = cd_off + (size_t)TILE_E * 4;         // ne reverse slots
   static constexpr size_t old_off = rev_off + (size_t)TILE_E * 4;        // nv old marginals
   static constexpr size_t rp_off = old_off + (size_t)TV * ROWB;          // nv + 1 row pointers
   static constexpr size_t pi_off = rp_off + (size_t)(TV + 4) * 4;        // nv prior-table rows
-  static constexpr size_t bytes = ((pi_off + (size_t)TV * 4 + 15) / 16) * 16;
+  static constexpr size_t lv_off = pi_off + (size_t)TV * 4;              // ne + 3 bytes: vertex (inside the tile) of a slot
+  static constexpr size_t bytes = ((lv_off + (size_t)TILE_E + 4 + 15) / 16) * 16;
 };
 struct SweepSmem {
   static constexpr size_t t_off = 2 * StageBuf::bytes;
@@ -594,8 +625,9 @@ struct SweepSmem {
   static constexpr size_t dr_off = scratch_off + (size_t)(NT > 64 * MB * MB ? NT : 64 * MB * MB) * 8;
   static constexpr size_t nr_off = dr_off + (size_t)Q * 8;
   static constexpr size_t fn_off = nr_off + (size_t)Q * 4;
-  static constexpr size_t lv_off = fn_off + (size_t)TV * 4;
-  static constexpr size_t total = ((lv_off + (size_t)TILE_E + 127) / 128) * 128;
+  static constexpr size_t best_off = fn_off + (size_t)TV * 4;            // MAP block of the tile's vertices
+  static constexpr size_t inv_off = ((best_off + (size_t)TV * 4 + 7) / 8) * 8;   // 1 / <degree of a block>
+  static constexpr size_t total = ((inv_off + (size_t)Q * 8 + 127) / 128) * 128;
 };
 
 __device__ __forceinline__ void cp_async_unit(void* smem_dst, const void* gsrc) {
@@ -659,11 +691,16 @@ __device__ __forceinline__ void stage_tile(const VertexArgs& a, const int4& td, 
     }
   }
   if (tid < ne) {
-    if (MODEL == MODEL_SBM && a.dc) cp_async_8(buf + StageBuf::sc_off + tid * 8, a.escale + e0 + tid);
+    if (MODEL == MODEL_SBM && a.dc) cp_async_4(buf + StageBuf::cd_off + tid * 4, a.coldeg + e0 + tid);
     if (MODE == MODE_SWEEP) cp_async_4(buf + StageBuf::rev_off + tid * 4, a.rev + e0 + tid);
+  }
+  if (ne > 0 && (MODE == MODE_SWEEP || (MODEL == MODEL_SBM && a.dc))) {   // slot -> vertex bytes: a 4-byte window rounded outwards
+    const int la0 = e0 & ~3;
+    if (tid * 4 < ne + (e0 - la0)) cp_async_4(buf + StageBuf::lv_off + tid * 4, a.slot_lv + la0 + tid * 4);
   }
   if (tid <= nv) cp_async_4(buf + StageBuf::rp_off + tid * 4, a.rowptr + v0 + tid);
   if (tid < nv) cp_async_4(buf + StageBuf::pi_off + tid * 4, a.pidx + v0 + tid);
+  if (MODEL == MODEL_SBM && a.dc && tid < nv) cp_async_8(buf + StageBuf::th_off + tid * 8, a.theta + a.vbeg + v0 + tid);
   if (MODE == MODE_SWEEP) {
     const char* osrc = reinterpret_cast<const char*>(a.PSI) + (size_t)v0 * PROWB;
     for (int g = tid; g < nv * PCH; g += NT) cp_async_punit(buf + StageBuf::old_off + g * PCHB, osrc + (size_t)g * PCHB);
@@ -707,13 +744,15 @@ __global__ void __launch_bounds__(NT, ((Q <= 8) ? 3 : 2) * (256 / NT)) sbm_verte
   unsigned long long* s_dr = reinterpret_cast<unsigned long long*>(smem + SweepSmem::dr_off);
   int* s_nr = reinterpret_cast<int*>(smem + SweepSmem::nr_off);
   int* fnS = reinterpret_cast<int*>(smem + SweepSmem::fn_off);
-  unsigned char* lvS = reinterpret_cast<unsigned char*>(smem + SweepSmem::lv_off);
+  int* bestS = reinterpret_cast<int*>(smem + SweepSmem::best_off);
+  double* invS = reinterpret_cast<double*>(smem + SweepSmem::inv_off);
 
   const int tid = threadIdx.x;
   if (MODE == MODE_SWEEP && skip_iteration(a.st, a.it)) return;
   if (tid < Q) {
     s_dr[tid] = 0ull;
     s_nr[tid] = 0;
+    invS[tid] = (MODEL == MODEL_SBM) ? c_P.invdr[tid] : 0.0;   // read by the barrier that publishes the first tile
   }
   LaneAcc acc;
   MstepAcc macc;
@@ -742,6 +781,7 @@ __global__ void __launch_bounds__(NT, ((Q <= 8) ? 3 : 2) * (256 / NT)) sbm_verte
     const int* rpS = reinterpret_cast<const int*>(cb + StageBuf::rp_off);
     const int* piS = reinterpret_cast<const int*>(cb + StageBuf::pi_off);
     const double* oldS = reinterpret_cast<const double*>(cb + StageBuf::old_off);
+    const unsigned char* lvS = reinterpret_cast<const unsigned char*>(cb + StageBuf::lv_off) + (e0 & 3);
     // ---- copies of tile k+1 into the other buffer, then the descriptor of tile k+2 into the same registers ----
     {
       int4 tn = tdN;
@@ -756,10 +796,14 @@ __global__ void __launch_bounds__(NT, ((Q <= 8) ? 3 : 2) * (256 / NT)) sbm_verte
 
     // ---- stage 1 ----
     double T[Q];
+    double sc = 1.0;
     if (tid < ne) {
       double psi[Q];
       read_staged(cb, tid, psi);
-      const double sc = (MODEL == MODEL_SBM && a.dc) ? reinterpret_cast<const double*>(cb + StageBuf::sc_off)[tid] : 1.0;
+      const int blk = take_block_bits(psi);   // MAP block of the sender (degree-corrected sbm.jl runs)
+      if (MODEL == MODEL_SBM && a.dc)         // theta_row theta_col, sbm.jl:87
+        sc = reinterpret_cast<const double*>(cb + StageBuf::th_off)[lvS[tid]] *
+             ((double)reinterpret_cast<const float*>(cb + StageBuf::cd_off)[tid] * invS[blk]);
       edge_factor(psi, sc, T);
 #pragma unroll
       for (int k = 0; k < Q; ++k) Tsm[tid * QS + k] = T[k];
@@ -774,9 +818,6 @@ __global__ void __launch_bounds__(NT, ((Q <= 8) ? 3 : 2) * (256 / NT)) sbm_verte
       if (vb > 0) pr = load_prior<MODE>(a, valid ? piS[v] : 0, t);  // tiles with more than VPR vertices
       const int b = valid ? rpS[v] - e0 : 0, e = valid ? rpS[v + 1] - e0 : 0;
       const double old = (MODE == MODE_SWEEP && valid && tl) ? oldS[v * Q + t] : 0.0;
-      if constexpr (MODE == MODE_SWEEP) {
-        for (int k = b + t; k < e; k += LV) lvS[k] = (unsigned char)v;  // owner of every edge slot, for stage 3
-      }
       const double* p = &Tsm[b * QS + tt];
       const double* pe = &Tsm[e * QS + tt];
       double m1 = 1.0, m2 = 1.0;
@@ -820,14 +861,15 @@ __global__ void __launch_bounds__(NT, ((Q <= 8) ? 3 : 2) * (256 / NT)) sbm_verte
         K = Kcc;
       }
       double u;
-      int fn;
-      vertex_finish<MODE>(a, valid, v0 + v, e - b, t, pr, old, m1, K, u, fn, acc, s_dr, s_nr);
+      int fn, best = 0;
+      vertex_finish<MODE>(a, valid, v0 + v, e - b, t, pr, old, m1, K, u, fn, acc, s_dr, s_nr, &best);
       if constexpr (MODE == MODE_SWEEP) {
         if (valid) {
           if (tl) Usm[v * Q + t] = u;
           if (t == 0) {
             ffS[v] = pr.ffrac;
             fnS[v] = fn;
+            bestS[v] = best;
           }
         }
       }
@@ -842,10 +884,9 @@ __global__ void __launch_bounds__(NT, ((Q <= 8) ? 3 : 2) * (256 / NT)) sbm_verte
         const int lv = lvS[tid];
         const int rv = reinterpret_cast<const int*>(cb + StageBuf::rev_off)[tid];
         double w[Q];
-        emit_message(a, &Usm[lv * Q], T, ffS[lv], fnS[lv], rv, w);
+        emit_message(a, &Usm[lv * Q], T, ffS[lv], fnS[lv], rv, w, bestS[lv]);
         if constexpr (MODEL == MODEL_SBM) {
           // a / Z for the M-step: Z = sum_s a_s (Crs b)_s = sum_s w_s T_s / sc
-          const double sc = a.dc ? reinterpret_cast<const double*>(cb + StageBuf::sc_off)[tid] : 1.0;
           double z = 0.0;
 #pragma unroll
           for (int k = 0; k < Q; ++k) z = fma(w[k], T[k], z);
@@ -873,8 +914,8 @@ __global__ void __launch_bounds__(NT, ((Q <= 8) ? 3 : 2) * (256 / NT)) sbm_verte
           const int p0 = ((cc >> 1) + (kk >> 1)) & 3;
           const int off0 = kk * ROWB + p0 * 16 + (cc & 1) * 8, off1 = kk * ROWB + (p0 ^ 2) * 16 + (cc & 1) * 8;
           mstep_accumulate(macc, &Tsm[wbase * QS],
-                           [&](int grp, int, int) {
-                             return *reinterpret_cast<const double*>(pw + grp * 4 * ROWB + ((grp & 1) ? off1 : off0));
+                           [&](int grp, int, int) {   // fabs: the first components carry the sender's block in their sign
+                             return fabs(*reinterpret_cast<const double*>(pw + grp * 4 * ROWB + ((grp & 1) ? off1 : off0)));
                            },
                            ne - wbase);
         } else {
@@ -882,10 +923,10 @@ __global__ void __launch_bounds__(NT, ((Q <= 8) ? 3 : 2) * (256 / NT)) sbm_verte
                            [&](int grp, int k, int comp) {
                              const int row = wbase + 4 * grp + k;
                              if constexpr (CHB == 16)
-                               return *reinterpret_cast<const double*>(pb + row * ROWB + swz_unit(row, comp >> 1) * 16 +
-                                                                       (comp & 1) * 8);
+                               return fabs(*reinterpret_cast<const double*>(pb + row * ROWB + swz_unit(row, comp >> 1) * 16 +
+                                                                            (comp & 1) * 8));
                              else
-                               return *reinterpret_cast<const double*>(pb + row * ROWB + comp * 8);
+                               return fabs(*reinterpret_cast<const double*>(pb + row * ROWB + comp * 8));
                            },
                            ne - wbase);
         }
@@ -915,7 +956,7 @@ __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base
   __shared__ double rowA[(MODEL == MODEL_SBM && MODE == MODE_SWEEP) ? NT * QS : 1];   // a / Z of the warp's 32 slots
   __shared__ double rowB[(MODEL == MODEL_SBM && MODE == MODE_SWEEP) ? NT * QS : 1];   // consumed messages
   __shared__ double ffSh;
-  __shared__ int fnSh;
+  __shared__ int fnSh, bestSh;
   __shared__ unsigned long long s_dr[Q];
   __shared__ int s_nr[Q];
 
@@ -943,6 +984,7 @@ __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base
     double psi[Q], T[Q];
     int ke;
     load_msg<Q, QM>(a.cur, e, psi);
+    take_block_bits(psi);   // hubs gather the neighbour's theta itself (they are rare)
     const double sc = (MODEL == MODEL_SBM && a.dc) ? th * a.theta[a.col[e]] : 1.0;
     edge_transform(psi, sc, T, ke);
     ksum += ke;
@@ -1006,14 +1048,15 @@ __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base
     pr.xmax = row[Q + 2];
     pr.ifrac = row[Q + 3];
     double u;
-    int fn;
-    vertex_finish<MODE>(a, writer, gv, e1 - e0, t, pr, old, prod, Ks + kcc, u, fn, acc, s_dr, s_nr);
+    int fn, best = 0;
+    vertex_finish<MODE>(a, writer, gv, e1 - e0, t, pr, old, prod, Ks + kcc, u, fn, acc, s_dr, s_nr, &best);
     const double ffrac = pr.ffrac;
     if (writer) {
       if (tl) Ush[t] = u;
       if (t == 0) {
         ffSh = ffrac;
         fnSh = fn;
+        bestSh = best;
       }
     }
   }
@@ -1030,9 +1073,10 @@ __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base
         double psi[Q], T[Q], w[Q];
         int ke;
         load_msg<Q, QM>(a.cur, e, psi);
+        take_block_bits(psi);
         const double sc = (MODEL == MODEL_SBM && a.dc) ? th * a.theta[a.col[e]] : 1.0;
         edge_transform(psi, sc, T, ke);
-        emit_message(a, Ush, T, ffSh, fnSh + ke, a.rev[e], w);
+        emit_message(a, Ush, T, ffSh, fnSh + ke, a.rev[e], w, bestSh);
         if constexpr (MODEL == MODEL_SBM) {
           double z = 0.0;
 #pragma unroll
@@ -1067,16 +1111,6 @@ __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base
   store_partials(acc, scratch, a.partials + (size_t)(part_base + blockIdx.x) * PSTRIDE, s_dr, s_nr);
   if constexpr (MODE == MODE_SWEEP && MODEL == MODEL_SBM)
     store_mstep_partials(macc, scratch, a.mpart + (size_t)(part_base + blockIdx.x) * Q * Q);
-}
-
-// theta_row * theta_col per edge slot, refreshed after update_theta (degree-corrected runs): keeps the random
-// theta gather out of the sweep (one staged 8-byte value per slot there instead of col + a dependent gather).
-__global__ void __launch_bounds__(256) sbm_escale_kernel(const int* __restrict__ erow, const int* __restrict__ col,
-                                                         long long K, const double* __restrict__ theta,
-                                                         double* __restrict__ escale, const SbmState* st, int it) {
-  if (skip_iteration(st, it)) return;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < K; e += (long long)gridDim.x * blockDim.x)
-    escale[e] = theta[erow[e]] * theta[col[e]];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1369,6 +1403,8 @@ __global__ void __launch_bounds__(NT) sbm_fe_kernel(const SbmState* st, const in
       double a[Q], b[Q];
       load_msg<Q, QM>(psi, e, b);                               // j -> i   (i = row of e, j = col[e])
       load_msg<Q, QM>(peers.p[rev_owner(r)], rev_slot(r), a);   // i -> j   (in the row of j, possibly on a peer)
+      take_block_bits(a);
+      take_block_bits(b);
       double lc = -c_P.logN;
       if (dc) lc += log(theta[erow[e]]) + log(theta[col[e]]);
       double x[4];
@@ -1426,6 +1462,7 @@ __global__ void k_permute_rows(const double* __restrict__ src, double* __restric
     } else {
       if (local) {
         load_msg<Q, QM>(src, s, m);
+        take_block_bits(m);   // messages leave without the sender's block in their signs
       } else {
 #pragma unroll
         for (int t = 0; t < Q; ++t) m[t] = 0.0;
@@ -1509,6 +1546,8 @@ __global__ void __launch_bounds__(NT) sbm_mstep_exact_kernel(const double* __res
       double a[Q], b[Q];
       load_msg<Q, QM>(msg, e, a);
       load_msg<Q, QM>(msg, (long long)rev_slot(rev[e]), b);
+      take_block_bits(a);   // no-ops on the pull layout, whose messages carry no bits
+      take_block_bits(b);
       double z = 0.0;
 #pragma unroll
       for (int t = 0; t < Q; ++t) {
@@ -1549,7 +1588,8 @@ VertexArgs vertex_args(gbx_sbm* h) {
   a.rowptr = h->rowptr;
   a.col = h->col;
   a.rev = h->rev;
-  a.escale = h->escale;
+  a.coldeg = h->coldeg;
+  a.slot_lv = h->slot_lv;
   a.tiles = h->tiles;
   a.ntiles = h->ntiles;
   a.hubs = h->hubs;
@@ -1569,8 +1609,8 @@ VertexArgs vertex_args(gbx_sbm* h) {
   a.st = h->st;
   a.it = h->cur_it;
   a.damping = (MODEL == MODEL_MOD) ? h->mopt.damping : h->opt.damping;
-  a.dc = (MODEL == MODEL_MOD) ? h->mopt.dc : h->opt.degreecorrection;
-  a.dc_model = a.dc;
+  a.dc_model = (MODEL == MODEL_MOD) ? h->mopt.dc : h->opt.degreecorrection;
+  a.dc = (MODEL == MODEL_MOD) ? a.dc_model : (a.dc_model && h->theta_valid);   // before update_theta every theta is 1
   return a;
 }
 
@@ -1751,13 +1791,11 @@ int op_theta_apply(gbx_sbm* h) {
   return GBX_OK;
 }
 
+// theta_row * theta_col per edge slot used to be refreshed here after every update_theta (one pass over the slots);
+// both sweeps now form it per edge from the sender's block (message sign bits / records), its static degree and the
+// block degree means, so there is nothing to do.  Kept as a step of the partitioned sequence (GBX_STEP_ESCALE).
 int op_escale(gbx_sbm* h) {
-  if (h->pull) return GBX_OK;  // the pull sweep forms theta_i theta_j per edge from the records
-  if (h->K > 0) {
-    sbm_escale_kernel<<<grid_for(h, h->K), 256, 0, h->stream>>>(h->erow, h->col, (long long)h->K, h->theta, h->escale, h->st, h->cur_it);
-    h->launches++;
-    GBX_CUDA_TRY(cudaGetLastError());
-  }
+  (void)h;
   return GBX_OK;
 }
 
