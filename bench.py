@@ -359,21 +359,6 @@ def run_convergence(a, torch, dist, world, rank, local):
                      "seconds_graph_build": eng.timings.get("create"), "CVBayes": float(out[7]), "FE": float(out[6])})
         eng.close()
     wall = time.perf_counter() - t_all
-    # the same q values of this GPU side by side: a host thread and a stream per q (parallel.threaded_sweep)
-    from graphbix_b200.parallel import threaded_sweep
-    my_qs = [q for _, q in my_share(qs, rank, world)]
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    side = threaded_sweep(my_qs, lambda q, st: EM_mod(np.ones(q) / q, n, q, links, 1, 256, 0.0, True, True, False, 0.3,
-                                                      seed=5 + q, device=local, stream=st), device=local)
-    torch.cuda.synchronize()
-    wall_side = time.perf_counter() - t0
-    for rec, out in zip(mine, side):
-        rec["iterations_side_by_side"] = int(out[16])
-    if world > 1:
-        t = torch.tensor([wall_side], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        wall_side = float(t.item())
     if world > 1:
         gathered = [None] * world
         dist.all_gather_object(gathered, mine)
@@ -383,10 +368,7 @@ def run_convergence(a, torch, dist, world, rank, local):
         wall = float(t.item())
     return {"workload": f"mod.jl EM() to BPconv < 1e-6, planted partition N={n} (giant component of 100000), avg degree "
                         f"{deg:g}, 4 planted groups, q = 2..10, one q per GPU round-robin",
-            "seconds_total": wall, "seconds_q_sweep_one_after_another": sum(r["seconds"] for r in mine) if world == 1 else None,
-            "seconds_q_sweep_side_by_side": wall_side,
-            "side_by_side_note": "all q of a GPU at once: a host thread and a CUDA stream per q (parallel.threaded_sweep); "
-                                 "graph build, initial messages, EM to convergence, free energy, read-back of every q",
+            "seconds_total": wall, "seconds_q_sweep": sum(r["seconds"] for r in mine) if world == 1 else None,
             "directed_edges": int(links.shape[0]), "runs": mine}
 
 

@@ -235,7 +235,27 @@ __global__ void __launch_bounds__(256) k_lsbm_vertex(const LGraph* __restrict__ 
       pk[t] = 0;
       term[t] = 1.0;
     }
-    for (int base = e0; base < e1; base += LPV) {
+    // thread-per-vertex launches with few groups keep the terms of a vertex's first NC links in registers: the second
+    // pass (cavities) then reads neither the messages nor the per-slot scales again for vertices of degree <= NC
+    constexpr int NC = (LPV == 1 && QT > 0 && QT <= 4 && MODE == LMODE_SWEEP) ? (QT <= 2 ? 12 : (QT == 3 ? 8 : 6)) : 0;
+    double tc[NC > 0 ? NC : 1][QA];
+#pragma unroll
+    for (int r = 0; r < NC; ++r) {
+      const int e = e0 + r + lane;   // LPV == 1: lane == 0
+      if (e < e1) {
+        double psi[QA];
+        row_load<QT, QA>(cur, e, q, psi);
+        l_term<QT, QA>(psi, P->aff[lab[e]], ddN[e], q, tc[r]);
+#pragma unroll
+        for (int t = 0; t < QA; ++t) {
+          if (t < q) {
+            pm[t] *= tc[r][t];
+            l_renorm(pm[t], pk[t]);
+          }
+        }
+      }
+    }
+    for (int base = e0 + NC * LPV; base < e1; base += LPV) {
       const int e = base + lane;
       if (e < e1) {
         double psi[QA];
@@ -309,7 +329,37 @@ __global__ void __launch_bounds__(256) k_lsbm_vertex(const LGraph* __restrict__ 
     __syncwarp();   // lane 0 has read the old marginal
     if (MODE == LMODE_SWEEP) {
       // cavities: the vertex's weights y (scale of its largest component) over the link's term, same floor
-      for (int base = e0; base < e1; base += LPV) {
+      auto emit = [&](int e, const double (&tm)[QA]) {
+        double m[QA];
+        double S = 0.0;
+#pragma unroll
+        for (int t = 0; t < QA; ++t) {
+          if (t < q) {
+            double c = y[t] * l_rcp(tm[t]);
+            c = (c < fl) ? fl : c;               // normalize_logprob: array[r] < log(1e-8) -> log(1e-8)
+            if (all_floor) c = 1.0;
+            m[t] = c;
+            S += c;
+          }
+        }
+        const double inv = 1.0 / S;
+#pragma unroll
+        for (int t = 0; t < QA; ++t)
+          if (t < q) m[t] *= inv;
+        const long long rv = rev[e];
+        if (damping != 1.0) {
+          double old[QA];
+          row_load<QT, QA>(cur, rv, q, old);
+          for (int t = 0; t < q; ++t) m[t] = (1.0 - damping) * old[t] + damping * m[t];
+        }
+        row_store<QT, QA>(nxt, rv, q, m);
+      };
+#pragma unroll
+      for (int r = 0; r < NC; ++r) {
+        const int e = e0 + r + lane;
+        if (e < e1) emit(e, tc[r]);
+      }
+      for (int base = e0 + NC * LPV; base < e1; base += LPV) {
         const int e = base + lane;
         if (e < e1) {
           if (!single) {
@@ -317,29 +367,7 @@ __global__ void __launch_bounds__(256) k_lsbm_vertex(const LGraph* __restrict__ 
             row_load<QT, QA>(cur, e, q, psi);
             l_term<QT, QA>(psi, P->aff[lab[e]], ddN[e], q, term);
           }
-          double m[QA];
-          double S = 0.0;
-#pragma unroll
-          for (int t = 0; t < QA; ++t) {
-            if (t < q) {
-              double c = y[t] * l_rcp(term[t]);
-              c = (c < fl) ? fl : c;               // normalize_logprob: array[r] < log(1e-8) -> log(1e-8)
-              if (all_floor) c = 1.0;
-              m[t] = c;
-              S += c;
-            }
-          }
-          const double inv = 1.0 / S;
-#pragma unroll
-          for (int t = 0; t < QA; ++t)
-            if (t < q) m[t] *= inv;
-          const long long rv = rev[e];
-          if (damping != 1.0) {
-            double old[QA];
-            row_load<QT, QA>(cur, rv, q, old);
-            for (int t = 0; t < q; ++t) m[t] = (1.0 - damping) * old[t] + damping * m[t];
-          }
-          row_store<QT, QA>(nxt, rv, q, m);
+          emit(e, term);
         }
       }
     }

@@ -13,8 +13,6 @@ c = d.get("em_convergence")
 if c and "error" in c:
     print("convergence leg failed:", c["error"])
 elif c:
-    if "seconds_q_sweep_side_by_side" in c:
-        print(f"q sweep on one GPU: one after another {c.get('seconds_q_sweep_one_after_another')} s, side by side {c['seconds_q_sweep_side_by_side']:.4f} s")
     print(f"em_convergence: total {c['seconds_total']:.2f}s :", " ".join(f"q{r['q']}:{r['iterations']}it/{r['seconds']*1e3:.0f}ms{'' if r['converged'] else '(!)'}" for r in c["runs"]))
 b = d.get("batched_graphs")
 if b and "error" in b:
