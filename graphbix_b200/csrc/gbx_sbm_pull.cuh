@@ -45,6 +45,15 @@ constexpr int P_S = GBX_PS;             // stages of the streamed ring: the prod
 constexpr int P_R = GBX_PR;             // stages of the gathered ring: records are fetched P_R - 1 tiles ahead
 static_assert(P_S > P_R, "a tile's neighbour ids must have been streamed before its records can be gathered");
 constexpr int P_NT = NT + 32;           // threads of a pull CTA: NT consumers + one producer warp
+#ifndef GBX_GATHER_LATE
+#define GBX_GATHER_LATE 1
+#endif
+// The record gathers of the next tile are issued by the upper half of the consumer warps between phase A and phase B:
+// with ~8 vertices per tile only the lower warps have vertex work in phase B, so the gathers leave the critical path
+// (0: every warp gathers its own rows at the top of a tile, as in the first version).
+constexpr bool GATHER_LATE = GBX_GATHER_LATE != 0;
+constexpr int G_T0 = GATHER_LATE ? NT / 2 : 0;        // first gathering thread
+constexpr int G_NT = NT - G_T0;                       // gathering threads
 constexpr int QTP = Q + 4;              // prior-table row: E_0..E_{Q-1}, ffrac, fi, xmax, 2^-ffrac
 
 __device__ __forceinline__ int swz(int off) { return off ^ (((off >> 7) & SWZ_MASK) << 4); }
@@ -273,7 +282,7 @@ __global__ void __launch_bounds__(P_NT, PULL_MIN_CTAS)
       mbar_init(&full_s[s], 1);
       mbar_init(&empty_s[s], NT / 32);
     }
-    for (int r = 0; r < P_R; ++r) mbar_init(&full_g[r], NT);   // one cp.async arrival per consumer thread
+    for (int r = 0; r < P_R; ++r) mbar_init(&full_g[r], G_NT);   // one cp.async arrival per gathering thread
     fence_barrier_init();
   }
   if (tid < Q) {
@@ -353,23 +362,36 @@ __global__ void __launch_bounds__(P_NT, PULL_MIN_CTAS)
       const int* colS = reinterpret_cast<const int*>(sbg + PStage::col_off) + (tg.z & 3);
       char* gbg = smem + PullSmem::gat_off + (size_t)rg * PullSmem::msg_bytes;
       const char* rec = reinterpret_cast<const char*>(a.rec_old);
-      const int wrow = tid & ~31, ln = tid & 31;
+      if constexpr (GATHER_LATE) {
+        // all rows of the tile, CH consecutive threads one record; every consumer warp is past phase C of the tile that
+        // used this gather stage last (they met at the barrier after phase A), so any thread may write any row
+        const int gt = tid - G_T0;
 #pragma unroll
-      for (int i = 0; i < CH; ++i) {
-        const int ul = ln + 32 * i;
-        const int row = wrow + ul / CH, c = ul % CH;
-        if (row < tg.w) cp_async_16(gbg + swz(row * ROWB + c * 16), rec + ((size_t)colS[row] * ROWB + (size_t)c * 16));
+        for (int i = 0; i < TILE_E * CH / G_NT; ++i) {
+          const int ul = gt + G_NT * i;
+          const int row = ul / CH, c = ul % CH;
+          if (row < tg.w) cp_async_16(gbg + swz(row * ROWB + c * 16), rec + ((size_t)colS[row] * ROWB + (size_t)c * 16));
+        }
+      } else {
+        const int wrow = tid & ~31, ln = tid & 31;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          const int ul = ln + 32 * i;
+          const int row = wrow + ul / CH, c = ul % CH;
+          if (row < tg.w) cp_async_16(gbg + swz(row * ROWB + c * 16), rec + ((size_t)colS[row] * ROWB + (size_t)c * 16));
+        }
       }
       cp_async_mbar_arrive_noinc(&full_g[rg]);
     }
   };
-  for (int j = 0; j < P_R - 1 && j < nt; ++j) issue_gather(j);
+  if (tid >= G_T0)
+    for (int j = 0; j < P_R - 1 && j < nt; ++j) issue_gather(j);
 
   for (int j = 0; j < nt; ++j) {
     const int s = j % P_S, r = j % P_R;
     char* sb = smem + PullSmem::small_off + (size_t)s * PStage::bytes;
     char* gb = smem + PullSmem::gat_off + (size_t)r * PullSmem::msg_bytes;   // records, then factors T, then M-step rows
-    if (j + P_R - 1 < nt) issue_gather(j + P_R - 1);
+    if (!GATHER_LATE && j + P_R - 1 < nt) issue_gather(j + P_R - 1);
     mbar_wait(&full_s[s], (j / P_S) & 1);
     if constexpr (RECON) mbar_wait(&full_g[r], (j / P_R) & 1);
     const int4 td = *reinterpret_cast<const int4*>(sb + PStage::desc_off);
@@ -414,6 +436,7 @@ __global__ void __launch_bounds__(P_NT, PULL_MIN_CTAS)
       write_swz(gb, tid, T);   // over the record it was rebuilt from
     }
     consumer_sync();
+    if (GATHER_LATE && tid >= G_T0 && j + P_R - 1 < nt) issue_gather(j + P_R - 1);
 
     // ---- phase B: QP lanes per vertex -- product, prior, clamp floor, marginal, residual, the vertex's record ----
     for (int vb = 0; vb < nv; vb += VPR) {
