@@ -43,7 +43,6 @@ constexpr int NB_BLK = (Q <= 1) ? 0 : (Q <= 2 ? 1 : (Q <= 4 ? 2 : (Q <= 8 ? 3 : 
 #endif
 constexpr int P_S = GBX_PS;             // stages of the streamed ring: the producer runs P_S - 1 tiles ahead
 constexpr int P_R = GBX_PR;             // stages of the gathered ring: records are fetched P_R - 1 tiles ahead
-static_assert(P_S > P_R, "a tile's neighbour ids must have been streamed before its records can be gathered");
 constexpr int P_NT = NT + 32;           // threads of a pull CTA: NT consumers + one producer warp
 #ifndef GBX_GATHER_LATE
 #define GBX_GATHER_LATE 1
@@ -52,6 +51,7 @@ constexpr int P_NT = NT + 32;           // threads of a pull CTA: NT consumers +
 // with ~8 vertices per tile only the lower warps have vertex work in phase B, so the gathers leave the critical path
 // (0: every warp gathers its own rows at the top of a tile, as in the first version).
 constexpr bool GATHER_LATE = GBX_GATHER_LATE != 0;
+static_assert(P_S > P_R || (GATHER_LATE && P_S == P_R), "a tile's neighbour ids must have been streamed before its records can be gathered");
 constexpr int G_T0 = GATHER_LATE ? NT / 2 : 0;        // first gathering thread
 constexpr int G_NT = NT - G_T0;                       // gathering threads
 constexpr int QTP = Q + 4;              // prior-table row: E_0..E_{Q-1}, ffrac, fi, xmax, 2^-ffrac
