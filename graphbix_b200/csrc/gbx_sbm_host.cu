@@ -397,12 +397,17 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
   }
   n = h->n;  // from here on: this rank's vertices and slots
   K = h->K;
-  rowptr.resize((size_t)n + 1);
-  for (int64_t i = 0; i <= n; ++i) rowptr[(size_t)i] = rowptr_g[(size_t)(h->vbeg + i)] - (int)h->sbeg;
+  if (h->vbeg == 0 && h->sbeg == 0 && (int64_t)rowptr_g.size() == n + 1) {
+    rowptr = rowptr_g;   // one rank: the global row pointers are the local ones (rowptr_g is still read below)
+  } else {
+    rowptr.resize((size_t)n + 1);
+    for (int64_t i = 0; i <= n; ++i) rowptr[(size_t)i] = rowptr_g[(size_t)(h->vbeg + i)] - (int)h->sbeg;
+  }
   // ---- tile schedule: runs of consecutive vertices with <= TILE_E slots and <= TV vertices; hubs apart ----
   const int TV = tile_vertices(q);
   std::vector<int4> tiles;
   std::vector<int> hubs;
+  tiles.reserve((size_t)(K / (TILE_E / 2) + n / TV + 16));
   {
     int64_t v = 0;
     while (v < n) {
