@@ -14,6 +14,7 @@
 // One 64-bit radix sort (CUB) of (destination, source) keys; everything else is a map or a scan.
 #include <cub/cub.cuh>
 
+#include <functional>
 #include <vector>
 
 #include "gbx_sbm_internal.h"
@@ -103,7 +104,11 @@ __global__ void k_slice(const int* __restrict__ gcol, const int* __restrict__ gr
 // Builds the global structure on the device, then keeps this rank's slice in the handle: h->rowptr (local, rebased),
 // h->col / h->erow (global vertex ids), h->rev (packed owner/slot), h->slot_of_link (global slot of every link) and
 // the partition bases.  rowptr_global receives the global row pointers.  Sets h->n, h->K, h->vbeg, h->sbeg.
-int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* rowptr_global, GlobalGraph* keep_global) {
+// `while_sorting` (optional) is called once the global row pointers and this rank's bases (h->vbeg, h->sbeg, h->n, h->K)
+// are on the host, while the GPU is still sorting the links: host work that needs only the degrees (the tile schedule)
+// overlaps the sort.  It must not touch the device.
+int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* rowptr_global, GlobalGraph* keep_global,
+                       const std::function<void()>* while_sorting) {
   const long long n = h->n_global, K = h->K_global;
   cudaStream_t st = h->stream;
   int *g_rowptr = nullptr, *g_col = nullptr, *g_rev = nullptr, *g_erow = nullptr;
@@ -111,12 +116,15 @@ int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* 
   unsigned long long *keys = nullptr, *keys2 = nullptr;
   int *vals = nullptr, *vals2 = nullptr, *deg = nullptr, *err = nullptr;
   void* tmp = nullptr;
+  cudaEvent_t ev_rowptr = nullptr;
   const int dv = h->device;
   const bool pooled = h->world == 1;
   auto cleanup = [&]() {
     dev_free(dv, g_rowptr); dev_free(dv, g_col); dev_free(dv, g_rev); dev_free(dv, g_erow);
     dev_free(dv, d_links); dev_free(dv, keys); dev_free(dv, keys2); dev_free(dv, vals); dev_free(dv, vals2);
     dev_free(dv, deg); dev_free(dv, err); dev_free(dv, tmp);
+    if (ev_rowptr) cudaEventDestroy(ev_rowptr);
+    ev_rowptr = nullptr;
   };
   auto fail = [&](int rc) { cleanup(); return rc; };
 #define GBX_C(expr)                                                                      \
@@ -168,6 +176,11 @@ int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* 
   GBX_C(dev_malloc(dv, &tmp, tb ? tb : 1, pooled));
   size_t t = tb;
   GBX_C(cub::DeviceScan::ExclusiveSum(tmp, t, deg, g_rowptr, (int)(n + 1), st));
+  // the row pointers go to the host now: everything the host derives from the degrees overlaps the sort below
+  rowptr_global->resize((size_t)n + 1);
+  GBX_C(cudaEventCreateWithFlags(&ev_rowptr, cudaEventDisableTiming));
+  GBX_C(cudaMemcpyAsync(rowptr_global->data(), g_rowptr, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+  GBX_C(cudaEventRecord(ev_rowptr, st));
   if (K > 0) {
     t = tb;
     GBX_C(cub::DeviceRadixSort::SortPairs(tmp, t, keys, keys2, vals, vals2, (int)K, 0, bits, st));
@@ -175,19 +188,8 @@ int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* 
     k_rev<<<grid, 256, 0, st>>>(g_rowptr, g_col, g_erow, K, g_rev, err);
   }
   int herr = 0;
-  rowptr_global->resize((size_t)n + 1);
-  GBX_C(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
-  GBX_C(cudaMemcpyAsync(rowptr_global->data(), g_rowptr, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
-  GBX_C(cudaStreamSynchronize(st));
-  GBX_C(cudaGetLastError());
-  if (herr & ERR_RANGE) { last_error() = "links: vertex id out of 1..n"; return fail(GBX_ERR_INVALID); }
-  if (herr & ERR_SELF) { last_error() = "links: self loop (run simplegraph first)"; return fail(GBX_ERR_INVALID); }
-  if (herr & ERR_DUP) { last_error() = "links: duplicate link (run simplegraph first)"; return fail(GBX_ERR_INVALID); }
-  if (herr & ERR_NOREV) {
-    last_error() = "links: reverse link missing (graph must be bidirected)";
-    return fail(GBX_ERR_INVALID);
-  }
-  // ---- this rank's slice ----
+  GBX_C(cudaEventSynchronize(ev_rowptr));
+  // ---- this rank's slice (host arithmetic on the row pointers), then the caller's host work, then wait for the sort ----
   const long long chunk = (n + h->world - 1) / h->world;
   PartBases pb;
   for (int r = 0; r <= MAXPEER; ++r) {
@@ -200,6 +202,17 @@ int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* 
   h->sbeg = h->sbeg_all[h->rank];
   h->n = h->vbeg_all[h->rank + 1] - h->vbeg;
   h->K = h->sbeg_all[h->rank + 1] - h->sbeg;
+  if (while_sorting && *while_sorting) (*while_sorting)();
+  GBX_C(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));   // (a copy into pageable memory waits for the stream)
+  GBX_C(cudaStreamSynchronize(st));
+  GBX_C(cudaGetLastError());
+  if (herr & ERR_RANGE) { last_error() = "links: vertex id out of 1..n"; return fail(GBX_ERR_INVALID); }
+  if (herr & ERR_SELF) { last_error() = "links: self loop (run simplegraph first)"; return fail(GBX_ERR_INVALID); }
+  if (herr & ERR_DUP) { last_error() = "links: duplicate link (run simplegraph first)"; return fail(GBX_ERR_INVALID); }
+  if (herr & ERR_NOREV) {
+    last_error() = "links: reverse link missing (graph must be bidirected)";
+    return fail(GBX_ERR_INVALID);
+  }
   for (int r = 0; r < h->world; ++r)
     if (h->sbeg_all[r + 1] - h->sbeg_all[r] > (long long)REV_MASK) {
       last_error() = "too many edge slots on one rank (limit 2^29)";

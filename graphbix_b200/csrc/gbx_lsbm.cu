@@ -21,12 +21,14 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <vector>
 
 #include "gbx_sbm_internal.h"
 
 namespace gbx {
-int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* rowptr_host, GlobalGraph* keep_global);
+int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* rowptr_host, GlobalGraph* keep_global,
+                       const std::function<void()>* while_sorting = nullptr);
 }
 using namespace gbx;
 

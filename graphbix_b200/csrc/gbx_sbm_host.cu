@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <functional>
 #include <vector>
 
 #include "gbx_sbm_internal.h"
@@ -47,7 +48,8 @@ static const SbmOps* ops_for(int model, int q) {
 }  // namespace gbx
 
 namespace gbx {
-int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* rowptr_host, GlobalGraph* keep_global);
+int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* rowptr_host, GlobalGraph* keep_global,
+                       const std::function<void()>* while_sorting = nullptr);
 void free_global(GlobalGraph* g);
 int build_exchange_plan(gbx_sbm* h, const GlobalGraph& g, const std::vector<int4>& tiles);
 }
@@ -369,46 +371,20 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
   std::vector<int> rowptr_g;   // global row pointers
   std::vector<int> rowptr;     // this rank's (rebased)
   GlobalGraph gg;              // global columns / reverse slots, alive until the exchange plan is built
-  {
-    int major = 0, sms = 0;
-    cudaError_t ce = cudaSetDevice(device);
-    if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
-    if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    if (ce != cudaSuccess) {
-      last_error() = std::string("cudaSetDevice/cudaDeviceGetAttribute: ") + cudaGetErrorString(ce);
-      delete h;
-      return GBX_ERR_CUDA;
-    }
-    if (major < 10) {
-      last_error() = "libgraphbix_cuda is built for sm_100a (B200) only";
-      delete h;
-      return GBX_ERR_CUDA;
-    }
-    h->num_sms = sms;
-    pt.lap("device properties");
-    const int rcb = build_graph_device(h, links, &rowptr_g, &gg);
-    pt.lap("build_graph_device");
-    if (rcb != GBX_OK) {
-      const std::string keep = last_error();
-      gbx_sbm_destroy(h);
-      last_error() = keep;
-      return rcb;
-    }
-  }
-  n = h->n;  // from here on: this rank's vertices and slots
-  K = h->K;
-  if (h->vbeg == 0 && h->sbeg == 0 && (int64_t)rowptr_g.size() == n + 1) {
-    rowptr = rowptr_g;   // one rank: the global row pointers are the local ones (rowptr_g is still read below)
-  } else {
-    rowptr.resize((size_t)n + 1);
-    for (int64_t i = 0; i <= n; ++i) rowptr[(size_t)i] = rowptr_g[(size_t)(h->vbeg + i)] - (int)h->sbeg;
-  }
-  // ---- tile schedule: runs of consecutive vertices with <= TILE_E slots and <= TV vertices; hubs apart ----
+  // ---- tile schedule: runs of consecutive vertices with <= TILE_E slots and <= TV vertices; hubs apart.  Host work on
+  // the row pointers alone: build_graph_device runs it while the GPU sorts the links. ----
   const int TV = tile_vertices(q);
   std::vector<int4> tiles;
   std::vector<int> hubs;
-  tiles.reserve((size_t)(K / (TILE_E / 2) + n / TV + 16));
-  {
+  const std::function<void()> schedule = [&]() {
+    const int64_t n = h->n, K = h->K;   // this rank's vertices and slots
+    if (h->vbeg == 0 && h->sbeg == 0 && (int64_t)rowptr_g.size() == n + 1) {
+      rowptr = rowptr_g;   // one rank: the global row pointers are the local ones (rowptr_g is still read below)
+    } else {
+      rowptr.resize((size_t)n + 1);
+      for (int64_t i = 0; i <= n; ++i) rowptr[(size_t)i] = rowptr_g[(size_t)(h->vbeg + i)] - (int)h->sbeg;
+    }
+    tiles.reserve((size_t)(K / (TILE_E / 2) + n / TV + 16));
     int64_t v = 0;
     while (v < n) {
       const int deg = rowptr[(size_t)v + 1] - rowptr[(size_t)v];
@@ -428,10 +404,53 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
       tiles.push_back(make_int4((int)v, (int)(w - v), rowptr[(size_t)v], ne));
       v = w;
     }
+    // degree statistics of the whole graph: the largest degree; for mod.jl handles constshift = sum_i d_i log d_i / L
+    // (mod.jl:155) and the mean excess degree excm (mod.jl:185)
+    double sdl = 0.0, sd2 = 0.0, sd = 0.0;
+    for (int64_t u = 0; u < h->n_global; ++u) {
+      const int di = rowptr_g[(size_t)u + 1] - rowptr_g[(size_t)u];
+      h->max_degree = std::max(h->max_degree, di);
+      if (model == 1) {
+        const double d = (double)di;
+        if (d > 0) sdl += d * std::log(d);
+        sd2 += d * d;
+        sd += d;
+      }
+    }
+    h->constshift = h->K_global > 0 ? sdl / (0.5 * (double)h->K_global) : 0.0;
+    h->excm = sd > 0 ? sd2 / sd - 1.0 : 0.0;  // (d'd)/(N mean(d)) - 1
+  };
+  {
+    int major = 0, sms = 0;
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (ce != cudaSuccess) {
+      last_error() = std::string("cudaSetDevice/cudaDeviceGetAttribute: ") + cudaGetErrorString(ce);
+      delete h;
+      return GBX_ERR_CUDA;
+    }
+    if (major < 10) {
+      last_error() = "libgraphbix_cuda is built for sm_100a (B200) only";
+      delete h;
+      return GBX_ERR_CUDA;
+    }
+    h->num_sms = sms;
+    pt.lap("device properties");
+    const int rcb = build_graph_device(h, links, &rowptr_g, &gg, &schedule);
+    pt.lap("build_graph_device");
+    if (rcb != GBX_OK) {
+      const std::string keep = last_error();
+      gbx_sbm_destroy(h);
+      last_error() = keep;
+      return rcb;
+    }
   }
+  n = h->n;  // from here on: this rank's vertices and slots
+  K = h->K;
 
   h->ntiles = (int)tiles.size();
-  pt.lap("tile schedule (host)");
+  pt.lap("(tile schedule ran during the sort)");
   if (world > 1) {
     // pieces of a packed sweep: the exposed copy tail is 1/pieces of the boundary traffic, but many small all-to-all
     // copies run slower through the switch than a few large ones (measured: 2 GPUs best with 8, 8 GPUs with 2)
@@ -454,23 +473,9 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
     }
     h->exchange = want_push_plan ? 1 : 0;
   }
-  for (int64_t v = 0; v < h->n_global; ++v) h->max_degree = std::max(h->max_degree, rowptr_g[(size_t)v + 1] - rowptr_g[(size_t)v]);
   h->model = model;
   gbx_mod_default_options(&h->mopt);
-  {
-    // mod.jl:155 constshift = sum_i d_i log d_i / L and mod.jl:185 excm, from the true degrees (mod.jl handles only)
-    double sdl = 0.0, sd2 = 0.0, sd = 0.0;
-    for (int64_t v = 0; model == 1 && v < h->n_global; ++v) {
-      const double d = (double)(rowptr_g[(size_t)v + 1] - rowptr_g[(size_t)v]);
-      if (d > 0) sdl += d * std::log(d);
-      sd2 += d * d;
-      sd += d;
-    }
-    h->constshift = h->K_global > 0 ? sdl / (0.5 * (double)h->K_global) : 0.0;
-    h->excm = sd > 0 ? sd2 / sd - 1.0 : 0.0;  // (d'd)/(N mean(d)) - 1
-  }
   h->nhubs = (int)hubs.size();
-  pt.lap("degree statistics (host)");
   gbx_sbm_default_options(&h->opt);
   auto body = [&]() -> int {
     // static per-slot data of the sweeps: the vertex (inside its tile) of every slot, and for sbm.jl the degree of every
