@@ -797,12 +797,17 @@ __global__ void __launch_bounds__(NT, ((Q <= 8) ? 3 : 2) * (256 / NT)) sbm_verte
     // ---- stage 1 ----
     double T[Q];
     double sc = 1.0;
+    // The slot's vertex is read NOW and kept for stage 3: the bytes were staged by other threads, and a faster warp starts
+    // overwriting this buffer (copies of the tile after next) while slower warps are still in stage 3 -- no barrier lies
+    // in between.  (Everything else stage 3 reads from the stage buffer was staged by the reading thread or its warp.)
+    int lv = 0;
+    if ((MODE == MODE_SWEEP || (MODEL == MODEL_SBM && a.dc)) && tid < ne) lv = lvS[tid];
     if (tid < ne) {
       double psi[Q];
       read_staged(cb, tid, psi);
       const int blk = take_block_bits(psi);   // MAP block of the sender (degree-corrected sbm.jl runs)
       if (MODEL == MODEL_SBM && a.dc)         // theta_row theta_col, sbm.jl:87
-        sc = reinterpret_cast<const double*>(cb + StageBuf::th_off)[lvS[tid]] *
+        sc = reinterpret_cast<const double*>(cb + StageBuf::th_off)[lv] *
              ((double)reinterpret_cast<const float*>(cb + StageBuf::cd_off)[tid] * invS[blk]);
       edge_factor(psi, sc, T);
 #pragma unroll
@@ -881,7 +886,6 @@ __global__ void __launch_bounds__(NT, ((Q <= 8) ? 3 : 2) * (256 / NT)) sbm_verte
     if constexpr (MODE == MODE_SWEEP) {
       double mod_term = 0.0;
       if (tid < ne) {
-        const int lv = lvS[tid];
         const int rv = reinterpret_cast<const int*>(cb + StageBuf::rev_off)[tid];
         double w[Q];
         emit_message(a, &Usm[lv * Q], T, ffS[lv], fnS[lv], rv, w, bestS[lv]);
