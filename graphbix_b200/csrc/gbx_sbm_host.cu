@@ -199,11 +199,70 @@ int em_loop(gbx_sbm* h, int itrmax, int check_every, double thr, bool mod, int* 
   const int itr0 = h->itr;  // iterations run before this call (gbx_sbm_iterate): stamps keep growing
   h->cur_thr = thr;
   int rc = GBX_OK, itr = 0;
+  // Small graphs (batch > 1) are launch bound: after the first batch (update_theta has run, every launch argument is
+  // settled) two consecutive iterations -- one per message buffer parity -- are captured into a CUDA graph and replayed.
+  // The replayed kernels carry the stamp -1 and read their iteration number from SbmState::it_now.
+  cudaGraphExec_t gexec = nullptr;
+  bool graph_ok = batch > 1 && (batch % 2) == 0 && h->world == 1 && !h->pull && !h->opt.mstep_exact &&
+                  !(getenv("GBX_GRAPH") && atoi(getenv("GBX_GRAPH")) == 0);
+  auto drop_graph = [&]() {
+    if (gexec) cudaGraphExecDestroy(gexec);
+    gexec = nullptr;
+  };
   while (itr < itrmax && rc == GBX_OK) {
     const int nb = std::min(batch, itrmax - itr);
-    for (int b = 1; b <= nb && rc == GBX_OK; ++b) {
-      h->cur_it = itr0 + itr + b;
-      rc = mod ? mod_iteration(h, nb == 1) : em_iteration(h, nb == 1);
+    if (graph_ok && itr > 0 && nb == batch) {
+      if (!gexec) {   // record two iterations (nothing runs during a capture)
+        cudaGraph_t graph = nullptr;
+        const int itr_host = h->itr;
+        const int64_t launches_host = h->launches;
+        // The recording happens on a stream of the handle's own (the caller's stream may be the legacy default stream,
+        // which cannot be captured); the graph is then launched into the caller's stream.  The shared parameter block
+        // is released first so that taking it inside the capture involves no event of another stream.
+        cudaStream_t user = h->stream;
+        cudaError_t ce = cudaSuccess;
+        if (!h->cap_stream) ce = cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking);
+        if (ce == cudaSuccess) {
+          h->ops->release(h);
+          h->stream = h->cap_stream;
+          ce = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+          if (ce == cudaSuccess) {
+            h->cur_it = -1;
+            for (int b = 0; b < 2 && rc == GBX_OK; ++b) rc = mod ? mod_iteration(h, false) : em_iteration(h, false);
+            ce = cudaStreamEndCapture(h->stream, &graph);
+            if (ce == cudaSuccess && rc == GBX_OK) ce = cudaGraphInstantiate(&gexec, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+          }
+          h->ops->release(h);
+          h->stream = user;
+        }
+        h->itr = itr_host;             // nothing ran yet
+        h->launches = launches_host;
+        if (ce != cudaSuccess || rc != GBX_OK || !gexec) {   // no graphs on this system / for this handle: plain launches
+          cudaGetLastError();
+          drop_graph();
+          graph_ok = false;
+          rc = GBX_OK;
+        }
+      }
+    }
+    if (graph_ok && gexec && itr > 0 && nb == batch) {
+      const int start = itr0 + itr;    // the replayed iterations are start + 1 ... start + nb
+      h->h_state->it_now = start;
+      cudaError_t ce = cudaMemcpyAsync(&h->st->it_now, &h->h_state->it_now, sizeof(int), cudaMemcpyHostToDevice, h->stream);
+      for (int b = 0; b < nb / 2 && ce == cudaSuccess; ++b) ce = cudaGraphLaunch(gexec, h->stream);
+      if (ce != cudaSuccess) {
+        last_error() = std::string("gbx em_loop (graph replay): ") + cudaGetErrorString(ce);
+        rc = GBX_ERR_CUDA;
+        break;
+      }
+      h->itr += nb;
+      h->launches += nb / 2;
+    } else {
+      for (int b = 1; b <= nb && rc == GBX_OK; ++b) {
+        h->cur_it = itr0 + itr + b;
+        rc = mod ? mod_iteration(h, nb == 1) : em_iteration(h, nb == 1);
+      }
     }
     if (rc != GBX_OK) break;
     itr += nb;
@@ -239,6 +298,7 @@ int em_loop(gbx_sbm* h, int itrmax, int check_every, double thr, bool mod, int* 
       break;
     }
   }
+  drop_graph();
   h->cur_it = 0;
   h->cur_thr = -1.0;
   return rc;
@@ -544,7 +604,10 @@ static int graph_create(int model, gbx_sbm** out, int device, int64_t n, int64_t
     GBX_TRY(dev_alloc(h, &h->part_mstep, (size_t)h->grid_mstep * q * q));
     GBX_TRY(dev_alloc(h, &h->part_theta, (size_t)h->grid_theta * MAXQ));
     GBX_TRY(dev_alloc(h, &h->part_fe, (size_t)h->grid_fe * 8));
-    GBX_CUDA_TRY(cudaDeviceSynchronize());
+    // everything above went into this handle's stream (the legacy stream at this point): wait for that, not for the
+    // whole device -- another host thread may be recording a CUDA graph (em_loop), during which a device-wide
+    // synchronisation is an error
+    GBX_CUDA_TRY(cudaStreamSynchronize(h->stream));
     return GBX_OK;
   };
   const int rc = body();
@@ -592,6 +655,7 @@ int gbx_sbm_destroy(gbx_sbm* h) {
   for (int k = 0; k < MAXPEER; ++k)
     if (h->ev_peer[k]) cudaEventDestroy(h->ev_peer[k]);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   for (int c = 0; c < MAXCHUNK; ++c)
     if (h->ev_piece[c]) cudaEventDestroy(h->ev_piece[c]);
   if (h->ev_copied) cudaEventDestroy(h->ev_copied);

@@ -45,6 +45,7 @@ struct SbmState {
   double omegain, omegaout, alpha, beta, hn2, omegainnew2;
   double cv5sum[5], cv5mean[5], cv5ss[5];
   int status;  // bit 0: non-finite / non-positive value met in a kernel
+  int it_now;  // iteration counter of launches replayed from a captured CUDA graph (stamp -1), see skip_iteration
   int done_at; // EM iteration whose residual fell below the threshold (0: not yet).  The kernels of LATER iterations
                // return at once, so the host may queue several iterations before it reads the residual back and the
                // state still is exactly that of the converged iteration (sbm.jl:348-353 breaks after update_theta).
@@ -149,6 +150,7 @@ struct gbx_sbm {
   int nchunks = 1;
   int chunk_tile[gbx::MAXCHUNK + 1] = {0};
   int64_t chunk_send[gbx::MAXCHUNK + 1][gbx::MAXPEER] = {};  // rows of the run for o written by pieces < c
+  cudaStream_t cap_stream = nullptr;                  // recording stream of the EM loop's CUDA graph (small graphs)
   cudaStream_t copy_stream = nullptr;                 // unpack + the copies to rank (me + 1) % world
   cudaStream_t peer_stream[gbx::MAXPEER] = {};        // [k]: copies to rank (me + k) % world, k >= 2 (own copy engine queue)
   cudaEvent_t ev_peer[gbx::MAXPEER] = {};

@@ -121,10 +121,24 @@ struct VertexArgs {
 // ---- small device helpers ---------------------------------------------------------------------
 // True when an earlier EM iteration has already converged (SbmState::done_at): this launch belongs to an iteration the
 // host queued ahead of reading the residual and must not touch anything.  it == 0: unconditional launch.
+// it < 0: the launch sits in a captured CUDA graph that is replayed for many iterations; its iteration number is the
+// device counter SbmState::it_now, advanced by the first kernel of every iteration (next_iteration in the prepare kernels).
+__device__ __forceinline__ int stamp_of(const SbmState* st, int it) {
+  return it < 0 ? *reinterpret_cast<const volatile int*>(&st->it_now) : it;
+}
 __device__ __forceinline__ bool skip_iteration(const SbmState* st, int it) {
   if (it == 0) return false;
   const int d = *reinterpret_cast<const volatile int*>(&st->done_at);
-  return d != 0 && d < it;
+  return d != 0 && d < stamp_of(st, it);
+}
+// First kernel of an EM iteration (one block): under graph replay advance the device's iteration counter, then decide.
+__device__ __forceinline__ bool next_iteration_skips(SbmState* st, int it) {
+  if (it >= 0) return skip_iteration(st, it);
+  const int now = *reinterpret_cast<const volatile int*>(&st->it_now) + 1;
+  __syncthreads();   // every thread has read the old value
+  if (threadIdx.x == 0) st->it_now = now;
+  const int d = *reinterpret_cast<const volatile int*>(&st->done_at);
+  return d != 0 && d < now;
 }
 
 // 2^n with saturation: 0 below the normal range, +inf above.
@@ -1203,7 +1217,7 @@ __global__ void sbm_apply_totals(SbmState* st, const double* __restrict__ tot, c
   }
   if (tid == 0 && mode == MODE_SWEEP) {
     st->conv = tot[0] / N;  // sbm.jl:123
-    if (it != 0 && st->done_at == 0 && st->conv < thr) st->done_at = it;   // sbm.jl:348-353, acted on from it + 1
+    if (it != 0 && st->done_at == 0 && st->conv < thr) st->done_at = stamp_of(st, it);   // sbm.jl:348-353, acted on from it + 1
     st->maxd = *maxd;
     if (!(tot[0] == tot[0]) || !(tot[0] < INFINITY)) st->status |= 1;  // NaN/Inf reached the marginals
   }
@@ -1274,7 +1288,7 @@ __global__ void sbm_apply_theta(SbmState* st, const double* __restrict__ totals,
 // global staging struct that the host copies device->constant in stream order.
 __global__ void sbm_prepare(SbmState* st, SbmParams* out, double N, int zero_h, int gr_from_sum, int dc_range,
                             double maxdeg, int it) {
-  if (skip_iteration(st, it)) return;
+  if (next_iteration_skips(st, it)) return;
   __shared__ double g[Q];
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -2134,7 +2148,7 @@ __global__ void mod_apply_totals(SbmState* st, const double* __restrict__ tot, c
   __syncthreads();
   if (tid == 0 && mode == MODE_SWEEP) {
     st->conv = tot[0] / N;  // mod.jl:72
-    if (it != 0 && st->done_at == 0 && st->conv < thr) st->done_at = it;   // mod.jl:230-234, acted on from it + 1
+    if (it != 0 && st->done_at == 0 && st->conv < thr) st->done_at = stamp_of(st, it);   // mod.jl:230-234, acted on from it + 1
     st->maxd = *maxd;
     if (!(tot[0] == tot[0]) || !(tot[0] < INFINITY)) st->status |= 1;
     st->eb1_used = st->eb1_cur;                                     // what the sweep just ran with (pull sweeps)
@@ -2161,7 +2175,7 @@ __global__ void mod_apply_totals(SbmState* st, const double* __restrict__ tot, c
 }
 
 __global__ void mod_prepare(SbmState* st, SbmParams* out, double N, int zero_h, int it) {
-  if (skip_iteration(st, it)) return;
+  if (next_iteration_skips(st, it)) return;
   const int tid = threadIdx.x;
   if (tid < Q) {
     out->lgr[tid] = log(st->gr[tid]);
