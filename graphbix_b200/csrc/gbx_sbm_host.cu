@@ -203,6 +203,7 @@ int em_loop(gbx_sbm* h, int itrmax, int check_every, double thr, bool mod, int* 
   // settled) two consecutive iterations -- one per message buffer parity -- are captured into a CUDA graph and replayed.
   // The replayed kernels carry the stamp -1 and read their iteration number from SbmState::it_now.
   cudaGraphExec_t gexec = nullptr;
+  int64_t graph_kernels = 0;   // kernel launches recorded in the graph (two iterations)
   bool graph_ok = batch > 1 && (batch % 2) == 0 && h->world == 1 && !h->pull && !h->opt.mstep_exact &&
                   !(getenv("GBX_GRAPH") && atoi(getenv("GBX_GRAPH")) == 0);
   auto drop_graph = [&]() {
@@ -236,6 +237,7 @@ int em_loop(gbx_sbm* h, int itrmax, int check_every, double thr, bool mod, int* 
           h->ops->release(h);
           h->stream = user;
         }
+        graph_kernels = h->launches - launches_host;
         h->itr = itr_host;             // nothing ran yet
         h->launches = launches_host;
         if (ce != cudaSuccess || rc != GBX_OK || !gexec) {   // no graphs on this system / for this handle: plain launches
@@ -257,7 +259,7 @@ int em_loop(gbx_sbm* h, int itrmax, int check_every, double thr, bool mod, int* 
         break;
       }
       h->itr += nb;
-      h->launches += nb / 2;
+      h->launches += (nb / 2) * graph_kernels;   // the kernels the replays ran
     } else {
       for (int b = 1; b <= nb && rc == GBX_OK; ++b) {
         h->cur_it = itr0 + itr + b;
