@@ -203,7 +203,10 @@ __device__ __forceinline__ void l_term(const double (&psi)[QA], const double* __
 }
 
 template <int MODE, int QT, int LPV>
-__global__ void __launch_bounds__(256) k_lsbm_vertex(const LGraph* __restrict__ gt, const int* __restrict__ live, int qrt, int G,
+#ifndef GBX_LSBM_MINB
+#define GBX_LSBM_MINB 1
+#endif
+__global__ void __launch_bounds__(256, GBX_LSBM_MINB) k_lsbm_vertex(const LGraph* __restrict__ gt, const int* __restrict__ live, int qrt, int G,
                                                      const int* __restrict__ rowptr, const int* __restrict__ rev,
                                                      const unsigned char* __restrict__ lab, const double* __restrict__ deg,
                                                      const double* __restrict__ ddN, double* __restrict__ msg0,
