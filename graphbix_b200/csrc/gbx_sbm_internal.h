@@ -121,6 +121,7 @@ struct gbx_sbm {
   int* pidx = nullptr;            // per vertex: row of the prior table (1 + degree * q + MAP block; 0: theta = 1)
   double* prior_tab = nullptr;    // prior factors per (degree, block), rebuilt every EM iteration
   bool theta_valid = false;       // update_theta has run since init
+  bool theta_applied = false;     // theta_local has written S_theta itself (one rank): theta_apply has nothing to do
   int cur = 0;
   gbx::SbmState* st = nullptr;
   gbx::SbmParams* params = nullptr;

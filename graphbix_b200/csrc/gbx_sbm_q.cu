@@ -1278,6 +1278,16 @@ __global__ void k_local_columns(const double* __restrict__ partials, int nrows, 
   }
 }
 
+// One rank: the column sums of the update_theta partials go straight into S_theta (k_local_columns + sbm_apply_theta in
+// one launch; a partitioned run all-reduces the totals in between and keeps the two steps).
+__global__ void k_theta_columns_apply(const double* __restrict__ partials, int nrows, SbmState* st, int it) {
+  if (skip_iteration(st, it)) return;
+  for (int c = threadIdx.x >> 5; c < Q; c += blockDim.x >> 5) {
+    const double v = warp_column_reduce(partials, nrows, Q, c);
+    if ((threadIdx.x & 31) == 0) st->Stheta[c] = v;
+  }
+}
+
 __global__ void sbm_apply_theta(SbmState* st, const double* __restrict__ totals, int it) {
   if (skip_iteration(st, it)) return;
   if (threadIdx.x < Q) st->Stheta[threadIdx.x] = totals[threadIdx.x];
@@ -1796,13 +1806,23 @@ int op_theta_local(gbx_sbm* h) {
                                                         h->pull ? h->theta_pp[h->thcur] : h->theta + h->vbeg, h->pidx,
                                                         h->part_theta, h->cur_it);
   h->theta_valid = true;
-  k_local_columns<<<1, 256, 0, h->stream>>>(h->part_theta, h->grid_theta, Q, h->totals, h->st, h->cur_it);
+  if (h->world == 1 && !h->stepped) {   // nobody reduces the totals across ranks: sum and apply in one launch
+    k_theta_columns_apply<<<1, 256, 0, h->stream>>>(h->part_theta, h->grid_theta, h->st, h->cur_it);
+    h->theta_applied = true;
+  } else {
+    k_local_columns<<<1, 256, 0, h->stream>>>(h->part_theta, h->grid_theta, Q, h->totals, h->st, h->cur_it);
+    h->theta_applied = false;
+  }
   h->launches += 2;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
 }
 
 int op_theta_apply(gbx_sbm* h) {
+  if (h->theta_applied) {   // op_theta_local has already written S_theta
+    h->theta_applied = false;
+    return GBX_OK;
+  }
   sbm_apply_theta<<<1, 32, 0, h->stream>>>(h->st, h->totals, h->cur_it);
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
