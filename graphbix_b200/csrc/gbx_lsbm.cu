@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256, GBX_LSBM_MINB) k_lsbm_vertex(const LGraph
                                                      const unsigned char* __restrict__ lab, const double* __restrict__ deg,
                                                      const double* __restrict__ ddN, double* __restrict__ msg0,
                                                      double* __restrict__ msg1, double* __restrict__ PSI, LParams* Pall,
-                                                     double damping, int it) {
+                                                     double damping, int it, double* __restrict__ pv, int xcap) {
   __shared__ double red[256];
   const int gi = l_graph(live);
   LParams* P = Pall + gi;
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(256, GBX_LSBM_MINB) k_lsbm_vertex(const LGraph
   }
   if (MODE != LMODE_MARGINAL) {
     const double s = block_sum(acc, red);
-    if (threadIdx.x == 0) atomicAdd(MODE == LMODE_SWEEP ? &P->conv : &P->sumlogZi, s);
+    if (threadIdx.x == 0) pv[(size_t)gi * xcap + blockIdx.x] = s;   // residual / sum log Z_i of this block (k_lsbm_reduce)
   }
 }
 
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(256, GBX_LSBM_MINB) k_lsbm_vertex(const LGraph
 // the threads of equal t in a fixed order: one atomic per (alpha, t) and block.
 __global__ void __launch_bounds__(256) k_lsbm_denom(const LGraph* __restrict__ gt, const int* __restrict__ live, int q, int G,
                                                     const double* __restrict__ deg, const double* __restrict__ PSI,
-                                                    LParams* Pall, int it) {
+                                                    LParams* Pall, int it, double* __restrict__ pd, int xcap) {
   __shared__ double sh[LMAXG + 1][256];
   const int gi = l_graph(live);
   LParams* P = Pall + gi;
@@ -417,11 +417,10 @@ __global__ void __launch_bounds__(256) k_lsbm_denom(const LGraph* __restrict__ g
   __syncthreads();
   if (tid < (LMAXG + 1) * q) {
     const int a = tid / q, tt = tid % q;
-    if (a == LMAXG || a < G) {
-      double s = 0.0;
+    double s = 0.0;
+    if (a == LMAXG || a < G)
       for (int k = tt; k < vpb * q; k += q) s += sh[a][k];
-      if (s != 0.0) atomicAdd(a == LMAXG ? &P->sumPSI[tt] : &P->denom[a][tt], s);
-    }
+    pd[((size_t)gi * xcap + blockIdx.x) * (LMAXG + 1) * q + a * q + tt] = s;   // summed over the blocks by k_lsbm_reduce
   }
 }
 
@@ -437,19 +436,21 @@ __global__ void __launch_bounds__(MSTEP_THREADS) k_lsbm_mstep(const LGraph* __re
                                                               int G, const int* __restrict__ erow, const int* __restrict__ col,
                                                               const int* __restrict__ rev, const unsigned char* __restrict__ lab,
                                                               const double* __restrict__ msg0, const double* __restrict__ msg1,
-                                                              LParams* Pall, int it) {
+                                                              LParams* Pall, int it, double* __restrict__ pm, int xcap) {
   extern __shared__ double dyn[];
   const int gi = l_graph(live);
   LParams* P = Pall + gi;
   if (l_skip(P, it)) return;                       // [warps][32][2 q]
   const LGraph gg = gt[gi];
   const double* __restrict__ cur = P->parity ? msg0 : msg1;
-  __shared__ double sh[LMAXG * MAXQ * MAXQ];
+  __shared__ double sh[(MSTEP_THREADS / 32) * LMAXG * (QT > 0 ? QT * QT : MAXQ * MAXQ)];   // one slab per warp
   __shared__ unsigned char labS[MSTEP_THREADS];
+  constexpr int WSL = LMAXG * (QT > 0 ? QT * QT : MAXQ * MAXQ);
   const int q = QT > 0 ? QT : qrt;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, qq = q * q;
-  for (int k = threadIdx.x; k < G * qq; k += blockDim.x) sh[k] = 0.0;
+  for (int k = threadIdx.x; k < (MSTEP_THREADS / 32) * WSL; k += blockDim.x) sh[k] = 0.0;
   __syncthreads();
+  double* pmrow = pm + ((size_t)gi * xcap + blockIdx.x) * G * qq;   // this block's partial sums (k_lsbm_reduce adds the blocks)
   if constexpr (QT > 0 && QT <= 8) {
     // q <= 8: the sum of outer products of a warp's 32 links is a (q x 32)(32 x q) product -> FP64 DMMA m8n8k4 over
     // groups of 4 links, one accumulator (two registers per lane) per label; operands of other labels are zeroed.
@@ -511,15 +512,17 @@ __global__ void __launch_bounds__(MSTEP_THREADS) k_lsbm_mstep(const LGraph* __re
 #pragma unroll
     for (int g = 0; g < LMAXG; ++g) {
       const int r = lane >> 2, s0 = 2 * (lane & 3);
-      if (g < G && r < QT) {
-        if (s0 < QT && c0[g] != 0.0) atomicAdd(&sh[g * qq + r * QT + s0], c0[g]);
-        if (s0 + 1 < QT && c1[g] != 0.0) atomicAdd(&sh[g * qq + r * QT + s0 + 1], c1[g]);
+      if (g < G && r < QT) {   // every entry of a warp's slab has one owner lane
+        if (s0 < QT) sh[warp * WSL + g * qq + r * QT + s0] = c0[g];
+        if (s0 + 1 < QT) sh[warp * WSL + g * qq + r * QT + s0 + 1] = c1[g];
       }
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < G * qq; k += blockDim.x) {
-      const int g = k / qq, rs = k % qq;
-      if (sh[k] != 0.0) atomicAdd(&P->Gnew[g][rs], sh[k] * P->aff[g][rs]);
+    for (int k = threadIdx.x; k < G * qq; k += blockDim.x) {   // the warps in a fixed order
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < MSTEP_THREADS / 32; ++w) v += sh[w * WSL + k];
+      pmrow[k] = v;
     }
     return;
   }
@@ -578,29 +581,63 @@ __global__ void __launch_bounds__(MSTEP_THREADS) k_lsbm_mstep(const LGraph* __re
 #pragma unroll
     for (int m = 0; m < EPL; ++m) {
       const int kk = lane + 32 * m;
-      if (g < G && kk < qq && acc[g][m] != 0.0) atomicAdd(&sh[g * qq + kk], acc[g][m]);
+      if (g < G && kk < qq) sh[warp * WSL + g * qq + kk] = acc[g][m];   // one owner lane per entry of the warp's slab
     }
   __syncthreads();
-  for (int k = threadIdx.x; k < G * qq; k += blockDim.x) {
-    const int g = k / qq, rs = k % qq;
-    if (sh[k] != 0.0) atomicAdd(&P->Gnew[g][rs], sh[k] * P->aff[g][rs]);
+  for (int k = threadIdx.x; k < G * qq; k += blockDim.x) {   // the warps in a fixed order
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < MSTEP_THREADS / 32; ++w) v += sh[w * WSL + k];
+    pmrow[k] = v;
   }
 }
 
-// what bit 0: denom / sumPSI / Gnew, bit 1: conv, bit 2: free energy sums
-__global__ void k_lsbm_zero(const int* __restrict__ live, LParams* Pall, int what, int it) {
-  const int tid = threadIdx.x;
-  LParams* P = Pall + l_graph(live);
+// Per-block partial sums -> the graph's parameter block, in a fixed order (no floating-point atomics anywhere: a run is
+// bit-reproducible, and a graph gives the same bits alone and inside a batch as long as the launch shapes agree).
+// One block per graph; a warp per column, lanes strided over the blocks, then a shuffle tree.
+//   what bit 0: residual (pv -> conv)   bit 1: sum log Z_i (pv -> sumlogZi)   bit 2: denom / sumPSI (pd)   bit 3: Gnew (pm)
+__device__ __forceinline__ double l_column(const double* __restrict__ base, int nrows, size_t stride) {
+  const int lane = threadIdx.x & 31;
+  double s = 0.0;
+  for (int r = lane; r < nrows; r += 32) s += base[(size_t)r * stride];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+__global__ void __launch_bounds__(256) k_lsbm_reduce(const int* __restrict__ live, LParams* Pall, int q, int G, int xcap, int what,
+                                                     const double* __restrict__ pv, int nv, const double* __restrict__ pd, int nd,
+                                                     const double* __restrict__ pm, int nm, int it) {
+  const int gi = l_graph(live);
+  LParams* P = Pall + gi;
   if (l_skip(P, it)) return;
-  if (what & 1) {
-    for (int k = tid; k < LMAXG * MAXQ; k += blockDim.x) P->denom[k / MAXQ][k % MAXQ] = 0.0;
-    for (int k = tid; k < MAXQ; k += blockDim.x) P->sumPSI[k] = 0.0;
-    for (int k = tid; k < LMAXG * MAXQ * MAXQ; k += blockDim.x) P->Gnew[k / (MAXQ * MAXQ)][k % (MAXQ * MAXQ)] = 0.0;
+  // the graph's columns are dealt to the warps of its blocks (grid x: several blocks per graph when few graphs are live)
+  const int lane = threadIdx.x & 31, nw = (blockDim.x >> 5) * gridDim.x;
+  const int warp = (threadIdx.x >> 5) + (blockDim.x >> 5) * blockIdx.x;
+  if ((what & 3) && warp == 0) {
+    const double v = l_column(pv + (size_t)gi * xcap, nv, 1);
+    if (lane == 0) {
+      if (what & 1) P->conv = v;
+      else P->sumlogZi = v;
+    }
   }
-  if ((what & 2) && tid == 0) P->conv = 0.0;
-  if ((what & 4) && tid == 0) {
-    P->sumlogZi = 0.0;
-    for (int k = 0; k < 4; ++k) P->fesum[k] = P->femean[k] = P->fess[k] = 0.0;
+  if (what & 4) {
+    const int ncol = (LMAXG + 1) * q;
+    for (int c = warp; c < ncol; c += nw) {
+      const int a = c / q, t = c % q;
+      if (a < LMAXG && a >= G) continue;
+      const double v = l_column(pd + (size_t)gi * xcap * ncol + c, nd, (size_t)ncol);
+      if (lane == 0) {
+        if (a == LMAXG) P->sumPSI[t] = v;
+        else P->denom[a][t] = v;
+      }
+    }
+  }
+  if (what & 8) {
+    const int qq = q * q, ncol = G * qq;
+    for (int c = warp; c < ncol; c += nw) {
+      const double v = l_column(pm + (size_t)gi * xcap * ncol + c, nm, (size_t)ncol);
+      if (lane == 0) P->Gnew[c / qq][c % qq] = v * P->aff[c / qq][c % qq];
+    }
   }
 }
 
@@ -657,7 +694,7 @@ __global__ void __launch_bounds__(256) k_lsbm_fe(const LGraph* __restrict__ gt, 
                                                  const int* __restrict__ col, const int* __restrict__ rev,
                                                  const unsigned char* __restrict__ lab, const double* __restrict__ deg,
                                                  const double* __restrict__ msg0, const double* __restrict__ msg1,
-                                                 LParams* Pall) {
+                                                 LParams* Pall, double* __restrict__ pf, int xcap) {
   __shared__ double red[256];
   LParams* P = Pall + blockIdx.y;
   const LGraph gg = gt[blockIdx.y];
@@ -692,13 +729,24 @@ __global__ void __launch_bounds__(256) k_lsbm_fe(const LGraph* __restrict__ gt, 
   }
   for (int k = 0; k < 4; ++k) {
     const double s = block_sum(v[k], red);
-    if (threadIdx.x == 0 && s != 0.0) atomicAdd(PASS == 0 ? &P->fesum[k] : &P->fess[k], s);
+    if (threadIdx.x == 0) pf[((size_t)blockIdx.y * xcap + blockIdx.x) * 4 + k] = s;
   }
 }
-__global__ void k_lsbm_fe_mean(const LGraph* __restrict__ gt, LParams* Pall) {
+// sums (pass 0) or sums of squared deviations (pass 1) of the four edge terms over the blocks, fixed order; 128 threads
+__global__ void k_lsbm_fe_sum(const LGraph* __restrict__ gt, LParams* Pall, const double* __restrict__ pf, int nf, int xcap,
+                              int pass) {
   LParams* P = Pall + blockIdx.y;
-  const double L = 0.5 * (double)gt[blockIdx.y].K;
-  if (threadIdx.x < 4) P->femean[threadIdx.x] = P->fesum[threadIdx.x] / L;
+  const int k = threadIdx.x >> 5;
+  if (k >= 4) return;
+  const double v = gt[blockIdx.y].K > 0 ? l_column(pf + (size_t)blockIdx.y * xcap * 4 + k, nf, 4) : 0.0;
+  if ((threadIdx.x & 31) == 0) {
+    if (pass == 0) {
+      P->fesum[k] = v;
+      P->femean[k] = v / (0.5 * (double)gt[blockIdx.y].K);
+    } else {
+      P->fess[k] = v;
+    }
+  }
 }
 __global__ void k_lsbm_finalize(const LGraph* __restrict__ gt, LParams* Pall) {
   if (threadIdx.x != 0) return;
@@ -782,6 +830,10 @@ struct gbx_lsbm {
   LParams* P = nullptr;      // [count]
   LParams* hP = nullptr;     // pinned mirror, [count]
   int* h_done = nullptr;     // pinned, [count]: done_at of every graph
+  int xcap = 1;              // most blocks (grid x) any launch gives one graph: rows of the partial-sum arrays
+  double *pv = nullptr, *pd = nullptr, *pm = nullptr, *pf = nullptr;   // per graph and block: residual / log Z, denominators,
+                                                                       // M-step sums, free-energy terms (k_lsbm_reduce)
+  int nbv = 0, nbd = 0, nbm = 0;   // blocks per graph of the last vertex / denominator / M-step launch
   LSpan* spans = nullptr;    // device, [count]: link range and vertex shift of every graph
   uint64_t* seeds = nullptr; // device, [count]
   bool initialised = false;
@@ -809,18 +861,25 @@ int l_read_conv(gbx_lsbm* h) {  // the residual of graph 0 alone: 8 bytes instea
 // the largest graph, but no more than ~8 blocks per SM over all the graphs of the launch
 dim3 l_grid(const gbx_lsbm* h, int64_t items, int per_block, int ngraphs) {
   const int64_t want = std::max<int64_t>(1, (items + per_block - 1) / per_block);
-  const int64_t cap = std::max<int64_t>(1, ((int64_t)h->g.num_sms * 8 + ngraphs - 1) / ngraphs);
+  const int64_t cap = std::min<int64_t>(h->xcap, std::max<int64_t>(1, ((int64_t)h->g.num_sms * 8 + ngraphs - 1) / ngraphs));
   return dim3((unsigned)std::min(want, cap), (unsigned)ngraphs, 1);
 }
 int l_ngraphs(const gbx_lsbm* h) { return h->nlive > 0 ? h->nlive : h->count; }
+// blocks per graph of k_lsbm_reduce: a warp per column of the partial sums, but no more blocks than the GPU holds
+dim3 l_reduce_grid(const gbx_lsbm* h, int ngraphs) {
+  const int ncol = 1 + (LMAXG + 1) * h->q + h->G * h->q * h->q;
+  const int want = (ncol + 7) / 8;
+  const int cap = std::max(1, h->g.num_sms * 8 / std::max(ngraphs, 1));
+  return dim3((unsigned)std::max(1, std::min(want, cap)), (unsigned)ngraphs, 1);
+}
 const int* l_live(const gbx_lsbm* h) { return h->nlive > 0 ? h->live : nullptr; }
 
 int l_denom(gbx_lsbm* h) {
   const int ng = l_ngraphs(h);
-  k_lsbm_zero<<<dim3(1, ng), 256, 0, h->g.stream>>>(l_live(h), h->P, 1, h->cur_it);
-  k_lsbm_denom<<<l_grid(h, h->nmax, 256, ng), 256, 0, h->g.stream>>>(h->gt, l_live(h), h->q, h->G, h->deg, h->PSI, h->P,
-                                                                     h->cur_it);
-  h->launches += 2;
+  const dim3 gd = l_grid(h, h->nmax, 256 / h->q, ng);
+  k_lsbm_denom<<<gd, 256, 0, h->g.stream>>>(h->gt, l_live(h), h->q, h->G, h->deg, h->PSI, h->P, h->cur_it, h->pd, h->xcap);
+  h->nbd = (int)gd.x;
+  h->launches += 1;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
 }
@@ -828,9 +887,11 @@ int l_denom(gbx_lsbm* h) {
 template <int MODE, int QT, int LPV>
 int l_vertex_ql(gbx_lsbm* h) {
   const int ng = l_ngraphs(h);
-  k_lsbm_vertex<MODE, QT, LPV><<<l_grid(h, h->nmax, 256 / LPV, ng), 256, 0, h->g.stream>>>(
+  const dim3 gv = l_grid(h, h->nmax, 256 / LPV, ng);
+  k_lsbm_vertex<MODE, QT, LPV><<<gv, 256, 0, h->g.stream>>>(
       h->gt, l_live(h), h->q, h->G, h->g.rowptr, h->g.rev, h->lab, h->deg, h->dd, h->msg[0], h->msg[1], h->PSI, h->P,
-      h->opt.damping, h->cur_it);
+      h->opt.damping, h->cur_it, h->pv, h->xcap);
+  h->nbv = (int)gv.x;
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
@@ -877,7 +938,7 @@ int l_iteration(gbx_lsbm* h) {
     const size_t msm = (size_t)(MSTEP_THREADS / 32) * 32 * 2 * std::max(h->q, 9) * sizeof(double);
 #define GBX_LSBM_MSTEP(QT)                                                                                                  \
   k_lsbm_mstep<QT><<<mg, MSTEP_THREADS, msm, st>>>(h->gt, l_live(h), h->q, h->G, h->g.erow, h->g.col, h->g.rev, h->lab, \
-                                                   h->msg[0], h->msg[1], h->P, it)
+                                                   h->msg[0], h->msg[1], h->P, it, h->pm, h->xcap)
     switch (h->q) {
       case 2: GBX_LSBM_MSTEP(2); break;
       case 3: GBX_LSBM_MSTEP(3); break;
@@ -888,8 +949,14 @@ int l_iteration(gbx_lsbm* h) {
       default: GBX_LSBM_MSTEP(0); break;
     }
 #undef GBX_LSBM_MSTEP
+    h->nbm = (int)mg.x;
     h->launches++;
   }
+  // the blocks' partial sums -> residual, denominators, M-step statistics of every live graph (fixed order)
+  const bool mstep = h->opt.learning && h->g.K > 0;
+  k_lsbm_reduce<<<l_reduce_grid(h, ng), 256, 0, st>>>(l_live(h), h->P, h->q, h->G, h->xcap, 1 | 4 | (mstep ? 8 : 0), h->pv, h->nbv,
+                                                      h->pd, h->nbd, h->pm, mstep ? h->nbm : 0, it);
+  h->launches++;
   k_lsbm_post<<<dim3(1, ng), 256, 0, st>>>(h->gt, l_live(h), h->P, h->q, h->G, h->opt.learningrate, h->opt.priorlearning,
                                            h->opt.learning, h->opt.REDfrac != 0.0, it, h->cur_thr);
   h->launches++;
@@ -1037,6 +1104,16 @@ int l_create(gbx_lsbm** out, int device, int count, const int64_t* n_vertices, c
     GBX_CUDA_TRY(dev_malloc(dv, (void**)&h->P, sizeof(LParams) * (size_t)count, true));
     GBX_CUDA_TRY(dev_malloc(dv, (void**)&h->gt, sizeof(LGraph) * (size_t)count, true));
     GBX_CUDA_TRY(dev_malloc(dv, (void**)&h->live, sizeof(int) * (size_t)count, true));
+    // partial sums per graph and block: a launch gives one graph at most xcap blocks
+    // (at least 32, so that the last live graphs of a batch still get a fair share of the GPU, unless the M-step
+    // partials of a batch with large q would exceed 256 MB)
+    h->xcap = (int)std::max<int64_t>(32, ((int64_t)sms * 8 + count - 1) / count);
+    while (h->xcap > 8 && (size_t)count * h->xcap * h->G * q * q * sizeof(double) > ((size_t)256 << 20)) h->xcap /= 2;
+    const size_t rows = (size_t)count * (size_t)h->xcap;
+    GBX_CUDA_TRY(dev_malloc(dv, (void**)&h->pv, rows * sizeof(double), true));
+    GBX_CUDA_TRY(dev_malloc(dv, (void**)&h->pd, rows * (size_t)(LMAXG + 1) * q * sizeof(double), true));
+    GBX_CUDA_TRY(dev_malloc(dv, (void**)&h->pm, rows * (size_t)h->G * q * q * sizeof(double), true));
+    GBX_CUDA_TRY(dev_malloc(dv, (void**)&h->pf, rows * 4 * sizeof(double), true));
     GBX_CUDA_TRY(cudaMallocHost((void**)&h->hP, sizeof(LParams) * (size_t)count));
     GBX_CUDA_TRY(cudaMallocHost((void**)&h->h_done, sizeof(int) * (size_t)count));
     GBX_CUDA_TRY(cudaMemset(h->P, 0, sizeof(LParams) * (size_t)count));
@@ -1140,8 +1217,9 @@ int l_init(gbx_lsbm* h, const double* gr, const double* affinity, const double* 
   h->cur_it = 0;
   L_TRY(l_vertex<LMODE_MARGINAL>(h));
   L_TRY(l_denom(h));
+  k_lsbm_reduce<<<dim3(1, h->count), 256, 0, st>>>(nullptr, h->P, q, G, h->xcap, 4, h->pv, 0, h->pd, h->nbd, h->pm, 0, 0);
   k_lsbm_pre<<<dim3(1, h->count), 64, 0, st>>>(nullptr, h->P, q, G, 0);
-  h->launches++;
+  h->launches += 2;
   GBX_CUDA_TRY(cudaGetLastError());
   GBX_CUDA_TRY(cudaStreamSynchronize(st));
   h->initialised = true;
@@ -1156,18 +1234,21 @@ int l_finalize(gbx_lsbm* h, gbx_lsbm_result* res) {
   h->nlive = 0;   // every graph
   h->cur_it = 0;
   const dim3 one(1, (unsigned)h->count);
-  k_lsbm_zero<<<one, 32, 0, st>>>(nullptr, h->P, 4, 0);
-  h->launches++;
   int rc = l_vertex<LMODE_LOGZ>(h);
   h->nlive = saved_live;
   h->cur_it = saved_it;
   L_TRY(rc);
+  k_lsbm_reduce<<<one, 256, 0, st>>>(nullptr, h->P, h->q, h->G, h->xcap, 2, h->pv, h->nbv, h->pd, 0, h->pm, 0, 0);
+  h->launches++;
   if (h->g.K > 0) {
     const dim3 ge = l_grid(h, h->Kmax, 256, h->count);
-    k_lsbm_fe<0><<<ge, 256, 0, st>>>(h->gt, h->q, h->G, h->g.erow, h->g.col, h->g.rev, h->lab, h->deg, h->msg[0], h->msg[1], h->P);
-    k_lsbm_fe_mean<<<one, 32, 0, st>>>(h->gt, h->P);
-    k_lsbm_fe<1><<<ge, 256, 0, st>>>(h->gt, h->q, h->G, h->g.erow, h->g.col, h->g.rev, h->lab, h->deg, h->msg[0], h->msg[1], h->P);
-    h->launches += 3;
+    k_lsbm_fe<0><<<ge, 256, 0, st>>>(h->gt, h->q, h->G, h->g.erow, h->g.col, h->g.rev, h->lab, h->deg, h->msg[0], h->msg[1], h->P,
+                                     h->pf, h->xcap);
+    k_lsbm_fe_sum<<<one, 128, 0, st>>>(h->gt, h->P, h->pf, (int)ge.x, h->xcap, 0);
+    k_lsbm_fe<1><<<ge, 256, 0, st>>>(h->gt, h->q, h->G, h->g.erow, h->g.col, h->g.rev, h->lab, h->deg, h->msg[0], h->msg[1], h->P,
+                                     h->pf, h->xcap);
+    k_lsbm_fe_sum<<<one, 128, 0, st>>>(h->gt, h->P, h->pf, (int)ge.x, h->xcap, 1);
+    h->launches += 4;
   }
   k_lsbm_finalize<<<one, 32, 0, st>>>(h->gt, h->P);
   h->launches++;
@@ -1306,6 +1387,10 @@ int gbx_lsbm_destroy(gbx_lsbm* h) {
   dev_free(dv, h->live);
   dev_free(dv, h->spans);
   dev_free(dv, h->seeds);
+  dev_free(dv, h->pv);
+  dev_free(dv, h->pd);
+  dev_free(dv, h->pm);
+  dev_free(dv, h->pf);
   if (h->hP) cudaFreeHost(h->hP);
   if (h->h_done) cudaFreeHost(h->h_done);
   delete h;

@@ -189,8 +189,8 @@ int64_t gbx_mod_launch_count(const gbx_mod* h);
  * A handle holds one graph (gbx_lsbm_create) or many (gbx_lsbm_create_batch: BASELINE configs[4], a detectability sweep
  * over thousands of N = 10k graphs).  The graphs of a batch share q, the number of labels and the options; every kernel
  * launch serves all of them (grid y index = graph), each graph keeps its own parameters, residual and convergence
- * stamp, and what gbx_lsbm_em returns for graph g is what a handle of its own would return (same kernels; sums are
- * accumulated with floating-point atomics, so to rounding).
+ * stamp, and what gbx_lsbm_em returns for graph g is what a handle of its own would return (same kernels; the launch
+ * shapes differ, so to rounding -- a given handle is bit-reproducible from run to run).
  * ------------------------------------------------------------------------------------------------ */
 #define GBX_MAX_LABELS 4
 typedef struct gbx_lsbm gbx_lsbm;

@@ -219,3 +219,19 @@ def test_labeled_device_random_messages_same_alone_and_in_batch(gpu_required):
         assert s[13] == batch[k][13] and s[12] == batch[k][12]
         np.testing.assert_allclose(batch[k][2], s[2], rtol=0, atol=1e-11)
         assert abs(s[2].sum(axis=1) - 1).max() < 1e-12
+
+
+def test_labeled_runs_are_bit_reproducible(gpu_required):
+    """No floating-point atomics on the labeled path (per-block partial sums, fixed-order reductions): the same batch run
+    twice gives identical bits."""
+    from graphbix_b200.labeled import EM_labeled_batch
+    from graphbix_b200.synth import labeled_planted_partition
+    graphs = []
+    for k in range(5):
+        links, _ = labeled_planted_partition(2000 + 300 * k, 3, [5.0, 3.0], ["a", "d"], 0.15, seed=70 + k)
+        und = links[links[:, 0] < links[:, 1]]
+        graphs.append((2000 + 300 * k, [int((und[:, 2] == a + 1).sum()) for a in range(2)], 3, 2, links))
+    runs = [EM_labeled_batch(graphs, 60, 1e-9, True, True, True, 0.3, 0, ["a", "d"], seeds=[1, 2, 3, 4, 5]) for _ in range(2)]
+    for a, b in zip(*runs):
+        assert np.array_equal(a[2], b[2]) and np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0])
+        assert a[3:12] == b[3:12] and a[13] == b[13]
