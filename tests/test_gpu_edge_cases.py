@@ -134,3 +134,27 @@ def test_queued_iterations_stop_exactly_where_the_one_by_one_loop_stops(gpu_requ
     for o in outs[1:]:
         assert o[0] == outs[0][0] and o[1] == outs[0][1]
         assert np.array_equal(o[2], outs[0][2]) and np.array_equal(o[3], outs[0][3]) and np.array_equal(o[4], outs[0][4])
+
+
+@pytest.mark.parametrize("model", ["sbm", "mod"])
+def test_graph_replay_equals_plain_launches(gpu_required, monkeypatch, model):
+    """Small graphs: from the second batch of eight iterations on the EM loop replays a CUDA graph of two iterations whose
+    kernels read their iteration number from the device (SbmState::it_now).  Same results, bit for bit, as plain launches
+    (GBX_GRAPH=0): the iteration at which the loop stops, the marginals and the free energy."""
+    from graphbix_b200.engine import EM, EM_mod
+    from graphbix_b200.synth import planted_partition
+    links, _ = planted_partition(4000, 3, 9.0, 0.15, seed=17, connected_only=True)
+    n = int(links.max())
+    outs = []
+    for graph in ("1", "0"):
+        monkeypatch.setenv("GBX_GRAPH", graph)
+        if model == "sbm":
+            o = EM(n, 3, links, n, "uniformAssortative", True, 200, True, 0.3, seed=4)
+            outs.append((o[2], o[1], o[3], o[13], o[14]))
+        else:
+            o = EM_mod(np.ones(3) / 3, n, 3, links, 1, 200, 0.0, True, True, True, 0.3, seed=4)
+            outs.append((o[5], np.array(o[1:5]), o[6], o[15], o[16]))
+    a, b = outs
+    assert a[3] == b[3] and a[4] == b[4]
+    assert a[4] == 0 or a[4] > 16 or not a[3]          # (the run is long enough for the replay to have been used)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
