@@ -45,6 +45,7 @@ struct SbmState {
   double omegain, omegaout, alpha, beta, hn2, omegainnew2;
   double cv5sum[5], cv5mean[5], cv5ss[5];
   int status;  // bit 0: non-finite / non-positive value met in a kernel
+  int tot_count; // blocks of sbm_local_totals that have delivered their total (the last one applies the totals)
   int it_now;  // iteration counter of launches replayed from a captured CUDA graph (stamp -1), see skip_iteration
   int done_at; // EM iteration whose residual fell below the threshold (0: not yet).  The kernels of LATER iterations
                // return at once, so the host may queue several iterations before it reads the residual back and the
@@ -121,6 +122,7 @@ struct gbx_sbm {
   int* pidx = nullptr;            // per vertex: row of the prior table (1 + degree * q + MAP block; 0: theta = 1)
   double* prior_tab = nullptr;    // prior factors per (degree, block), rebuilt every EM iteration
   bool theta_valid = false;       // update_theta has run since init
+  bool totals_applied = false;    // local_totals has applied the totals itself (one rank): apply_totals has nothing to do
   bool theta_applied = false;     // theta_local has written S_theta itself (one rank): theta_apply has nothing to do
   int cur = 0;
   gbx::SbmState* st = nullptr;

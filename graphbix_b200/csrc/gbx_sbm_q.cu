@@ -1140,10 +1140,26 @@ __global__ void __launch_bounds__(NT) sbm_hub_kernel(VertexArgs a, int part_base
 constexpr int TOT_G = 4 + 4 * Q;
 constexpr int TOT_LEN = TOT_G + Q * Q;
 
+// One rank: nothing sits between the totals and their application (a partitioned run all-reduces them), so the block that
+// finishes last applies them right away -- one launch less per pass.
+struct ApplyArgs {
+  int fuse;       // 0: only the totals (partitioned runs; the apply kernel follows the all-reduce)
+  int mode, prior, dc, learning;
+  double N, K, lr, cap, thr;
+};
+#if GBX_MODEL == 0
+__device__ __forceinline__ void sbm_apply_totals_body(SbmState* st, const double* __restrict__ tot, const double* maxd, int mode,
+                                                      int prior, int dc, double N, double lr, double maxCrs, int it, double thr);
+#else
+__device__ __forceinline__ void mod_apply_totals_body(SbmState* st, const double* __restrict__ tot, const double* maxd, int mode,
+                                                      int prior, int dc, int learning, double N, double K, double lr,
+                                                      double maxomega, int it, double thr);
+#endif
+
 __global__ void __launch_bounds__(256) sbm_local_totals(const double* __restrict__ pv, int nrows,
                                                         const double* __restrict__ pm, int with_g,
                                                         double* __restrict__ totals, double* __restrict__ maxd_out,
-                                                        const SbmState* st, int it) {
+                                                        SbmState* st, int it, ApplyArgs aa) {
   // One block per column of the totals vector (the last block: the max column); fixed summation order.
   if (skip_iteration(st, it)) return;
   __shared__ double red[256];
@@ -1183,12 +1199,34 @@ __global__ void __launch_bounds__(256) sbm_local_totals(const double* __restrict
     if (is_max) *maxd_out = red[0];
     else totals[c] = red[0];
   }
+  if (!aa.fuse) return;
+  // ---- the last block to get here applies the totals ----
+  __shared__ int s_last;
+  __shared__ double s_tot[TOT_G + Q * Q + 1];
+  if (tid == 0) {
+    __threadfence();                                                 // this block's total is visible device-wide ...
+    s_last = (atomicAdd(&st->tot_count, 1) == (int)gridDim.x - 1);   // ... before it is counted
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if (tid == 0) st->tot_count = 0;   // for the next pass (the next kernel starts after this one has ended)
+  __threadfence();
+  for (int k = tid; k < ncol; k += 256) s_tot[k] = __ldcg(&totals[k]);
+  if (tid == 0) s_tot[TOT_G + Q * Q] = __ldcg(maxd_out);
+  __syncthreads();
+#if GBX_MODEL == 0
+  sbm_apply_totals_body(st, s_tot, &s_tot[TOT_G + Q * Q], aa.mode, aa.prior, aa.dc, aa.N, aa.lr, aa.cap, it, aa.thr);
+#else
+  mod_apply_totals_body(st, s_tot, &s_tot[TOT_G + Q * Q], aa.mode, aa.prior, aa.dc, aa.learning, aa.N, aa.K, aa.lr, aa.cap, it,
+                        aa.thr);
+#endif
 }
 
 #if GBX_MODEL == 0
 // sbm.jl:120-123 (residual, gr), 47-58 (block degree means), 137-147 (update_Crs) from the global totals.
-__global__ void sbm_apply_totals(SbmState* st, const double* __restrict__ tot, const double* maxd, int mode, int prior,
-                                 int dc, double N, double lr, double maxCrs, int it, double thr) {
+// (a __device__ body so that, on one rank, the last block of sbm_local_totals can run it right away: one launch less)
+__device__ __forceinline__ void sbm_apply_totals_body(SbmState* st, const double* __restrict__ tot, const double* maxd, int mode,
+                                                      int prior, int dc, double N, double lr, double maxCrs, int it, double thr) {
   const int tid = threadIdx.x;
   if (skip_iteration(st, it)) return;
   if (mode == MODE_LOGZ) {
@@ -1234,6 +1272,10 @@ __global__ void sbm_apply_totals(SbmState* st, const double* __restrict__ tot, c
     if (!(c == c)) st->status |= 1;
     st->C[tid] = c;
   }
+}
+__global__ void sbm_apply_totals(SbmState* st, const double* __restrict__ tot, const double* maxd, int mode, int prior,
+                                 int dc, double N, double lr, double maxCrs, int it, double thr) {
+  sbm_apply_totals_body(st, tot, maxd, mode, prior, dc, N, lr, maxCrs, it, thr);
 }
 #endif
 
@@ -1765,8 +1807,29 @@ int op_vertex_pass(gbx_sbm* h, int mode) {
 int op_local_totals(gbx_sbm* h, int mode) {
   const size_t skip = (size_t)h->sweep_row0;  // rows of the last vertex pass (a packed sweep has one set per piece)
   const int with_g = (MODEL == MODEL_SBM && mode == MODE_SWEEP) ? 1 : 0;
+  ApplyArgs aa{};
+  aa.fuse = (h->world == 1 && !h->stepped) ? 1 : 0;   // one rank: the last block applies the totals (op_apply_totals skips)
+  aa.mode = mode;
+  aa.thr = h->cur_thr;
+  if (MODEL == MODEL_MOD) {
+    aa.prior = h->mopt.priorlearning;
+    aa.dc = h->mopt.dc;
+    aa.learning = h->mopt.learning;
+    aa.N = (double)h->n_global;
+    aa.K = (double)h->K_global;
+    aa.lr = h->mopt.learningrate;
+    aa.cap = h->mopt.maxomega;
+  } else {
+    aa.prior = h->opt.priorlearning;
+    aa.dc = h->opt.degreecorrection;
+    aa.N = (double)h->n_global;
+    aa.lr = h->opt.learningrate;
+    aa.cap = h->opt.maxCrs > 0 ? h->opt.maxCrs : (double)h->n_global;
+  }
   sbm_local_totals<<<4 * Q + 4 + (with_g ? Q * Q : 0) + 1, 256, 0, h->stream>>>(
-      h->part_vertex + skip * PSTRIDE, h->sweep_rows, h->part_mstep + skip * Q * Q, with_g, h->totals, h->maxd_dev, h->st, h->cur_it);
+      h->part_vertex + skip * PSTRIDE, h->sweep_rows, h->part_mstep + skip * Q * Q, with_g, h->totals, h->maxd_dev, h->st, h->cur_it,
+      aa);
+  h->totals_applied = aa.fuse != 0;
   h->launches++;
   GBX_CUDA_TRY(cudaGetLastError());
   return GBX_OK;
@@ -1774,6 +1837,10 @@ int op_local_totals(gbx_sbm* h, int mode) {
 
 #if GBX_MODEL == 0
 int op_apply_totals(gbx_sbm* h, int mode) {
+  if (h->totals_applied) {   // the last block of sbm_local_totals has done it
+    h->totals_applied = false;
+    return GBX_OK;
+  }
   const double maxCrs = h->opt.maxCrs > 0 ? h->opt.maxCrs : (double)h->n_global;
   sbm_apply_totals<<<1, 256, 0, h->stream>>>(h->st, h->totals, h->maxd_dev, mode, h->opt.priorlearning,
                                              h->opt.degreecorrection, (double)h->n_global, h->opt.learningrate, maxCrs, h->cur_it,
@@ -2146,8 +2213,9 @@ int op_occupancy(int variant, int* vertex_occ, int* mstep_occ) {
 // alpha beta d_i h); below are the scalar bookkeeping, the omega M-step and the free energy of that model.
 // =============================================================================================
 // mod.jl:72 (residual), 22-24 (h numerator), 221-223 (gr), 77-112 and 224-229 (omegas, alpha, beta) from the totals.
-__global__ void mod_apply_totals(SbmState* st, const double* __restrict__ tot, const double* maxd, int mode, int prior,
-                                 int dc, int learning, double N, double K, double lr, double maxomega, int it, double thr) {
+__device__ __forceinline__ void mod_apply_totals_body(SbmState* st, const double* __restrict__ tot, const double* maxd, int mode,
+                                                      int prior, int dc, int learning, double N, double K, double lr,
+                                                      double maxomega, int it, double thr) {
   const int tid = threadIdx.x;
   if (skip_iteration(st, it)) return;
   if (mode == MODE_LOGZ) {
@@ -2192,6 +2260,10 @@ __global__ void mod_apply_totals(SbmState* st, const double* __restrict__ tot, c
       if (!(st->beta == st->beta) || !(st->alpha == st->alpha)) st->status |= 1;
     }
   }
+}
+__global__ void mod_apply_totals(SbmState* st, const double* __restrict__ tot, const double* maxd, int mode, int prior,
+                                 int dc, int learning, double N, double K, double lr, double maxomega, int it, double thr) {
+  mod_apply_totals_body(st, tot, maxd, mode, prior, dc, learning, N, K, lr, maxomega, it, thr);
 }
 
 __global__ void mod_prepare(SbmState* st, SbmParams* out, double N, int zero_h, int it) {
@@ -2289,6 +2361,10 @@ __global__ void mod_finalize(SbmState* st, double N, double L, double constshift
 }
 
 int mop_apply_totals(gbx_sbm* h, int mode) {
+  if (h->totals_applied) {   // the last block of sbm_local_totals has done it
+    h->totals_applied = false;
+    return GBX_OK;
+  }
   mod_apply_totals<<<1, 64, 0, h->stream>>>(h->st, h->totals, h->maxd_dev, mode, h->mopt.priorlearning, h->mopt.dc,
                                             h->mopt.learning, (double)h->n_global, (double)h->K_global,
                                             h->mopt.learningrate, h->mopt.maxomega, h->cur_it, h->cur_thr);
