@@ -261,7 +261,7 @@ enum {
   GBX_STEP_APPLY_TOTALS = 3,     /* after the all-reduce (sum) of the totals vector                           */
   GBX_STEP_THETA_LOCAL = 4,      /* update_theta on this rank's vertices; S_theta partial -> totals[0..q)      */
   GBX_STEP_THETA_APPLY = 5,      /* after the all-reduce of totals[0..q)                                      */
-  GBX_STEP_ESCALE = 6,           /* after the all-gather of theta                                             */
+  GBX_STEP_ESCALE = 6,           /* no-op since round 2 (theta_i theta_j is formed inside the sweeps); kept for callers */
   GBX_STEP_FE_LOCAL = 7,         /* arg = pass (0 sums, 1 squared deviations) -> totals[0..5)                 */
   GBX_STEP_FE_APPLY = 8,
   GBX_STEP_FE_FINAL = 9,
