@@ -373,7 +373,7 @@ def run_convergence(a, torch, dist, world, rank, local):
 
 
 def run_batch(a, torch, dist, world, rank, local):
-    """The shape of BASELINE.json configs[4] with the sbm.jl model (the labeled model of the notebook is not built): a
+    """The shape of BASELINE.json configs[4] with the sbm.jl model (the labeled model itself is the `labeled_graphs` leg): a
     detectability sweep over epsilon = c_out / c_in on independent planted-partition graphs of N = 10k, average degree 8,
     2 groups, dealt to the GPUs round-robin, one EM() per graph through the public call (host links in, PSI out).
     Reports graphs per second and the mean overlap with the planted groups per epsilon."""
