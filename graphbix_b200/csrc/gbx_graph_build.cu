@@ -163,7 +163,7 @@ int build_graph_device(gbx_sbm* h, const int64_t* links_host, std::vector<int>* 
   GBX_T(err, 1);
   const int grid = h->num_sms * 8;
   if (links == d_links)
-    GBX_C(cudaMemcpyAsync(d_links, links_host, (size_t)2 * K * sizeof(int64_t), cudaMemcpyDefault, st));
+    GBX_C(upload_async(h->device, d_links, links_host, (size_t)2 * K * sizeof(int64_t), st));
   GBX_C(cudaMemsetAsync(deg, 0, (size_t)(n + 1) * sizeof(int), st));
   GBX_C(cudaMemsetAsync(err, 0, sizeof(int), st));
   if (K > 0) k_keys<<<grid, 256, 0, st>>>(links, K, n, keys, vals, deg, err);

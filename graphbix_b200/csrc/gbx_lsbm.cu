@@ -1132,7 +1132,7 @@ int l_create(gbx_lsbm** out, int device, int count, const int64_t* n_vertices, c
     const int grid_e = (int)std::min<int64_t>(std::max<int64_t>(1, (K + 255) / 256), (int64_t)sms * 8);
     cudaError_t e = cudaMemsetAsync(err, 0, sizeof(int), h->g.stream);
     if (e == cudaSuccess && K > 0 && !d_uni)
-      e = cudaMemcpyAsync(d_lab, labels_all, (size_t)K * sizeof(int64_t), cudaMemcpyDefault, h->g.stream);
+      e = upload_async(dv, d_lab, labels_all, (size_t)K * sizeof(int64_t), h->g.stream);
     if (d_uni) {   // the labels of a batch are already on the device, behind the links
       d_lab = d_uni + 2 * K;
     }

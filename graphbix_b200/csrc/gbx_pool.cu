@@ -3,9 +3,14 @@
 // cudaFree of the ~40 buffers of a handle cost 4-25 ms per call.  Freed blocks are kept (up to a cap) and handed to
 // the next handle.  Blocks of partitioned handles are never cached (their buffers are mapped by other processes).
 //   GBX_POOL=0      disable          GBX_POOL_MB=<n>   cap of cached bytes (default: a quarter of the device memory)
+#include <algorithm>
+#include <atomic>
+#include <cstring>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
+#include <vector>
 
 #include "gbx_sbm_internal.h"
 
@@ -117,6 +122,202 @@ int64_t pool_cached_bytes(int device) {
   Pool& P = pool();
   std::lock_guard<std::mutex> g(P.m);
   return (device >= 0 && device < MAXDEV) ? (int64_t)P.cached[device] : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Upload of a large PAGEABLE host array.  A Julia `ccall` hands over ordinary Arrays: cudaMemcpyAsync from pageable
+// memory goes through the driver's single staging buffer at ~5 GB/s (the 256 MB Int64 edge list of N = 1M, degree 16:
+// 49 ms, more than the 20 EM iterations that follow).  Here a few host threads copy alternate chunks into their own
+// pinned buffers and queue the DMA of each chunk on their own streams, so the host copies run in parallel with each
+// other and with the transfers; `st` then waits for all of them.  Pinned or small sources take one cudaMemcpyAsync.
+// On return the source has been read completely (as with cudaMemcpyAsync from pageable memory).
+//   GBX_STAGE_THREADS=<n>  host threads (default 4, 0: always the plain copy)   GBX_STAGE_MIN_MB=<n>  smallest staged upload (16)
+namespace {
+constexpr size_t STAGE_CHUNK = size_t(2) << 20;   // 2 buffers per thread: 16 MB of pinned memory with 4 threads
+constexpr size_t STAGE_MIN = size_t(16) << 20;
+constexpr int STAGE_MAXT = 8;
+struct Stager {
+  std::mutex m;  // one staged upload at a time per process (the buffers are shared)
+  int device = -1;
+  int nt = 0;
+  char* buf[STAGE_MAXT][2] = {};
+  cudaEvent_t ev[STAGE_MAXT][2] = {};
+  cudaEvent_t done[STAGE_MAXT] = {};
+  cudaStream_t s[STAGE_MAXT] = {};
+  cudaEvent_t start = nullptr;
+};
+Stager& stager() {
+  static Stager* p = new Stager();  // leaked on purpose, like the pool
+  return *p;
+}
+int stage_threads() {  // read per call: tests switch it
+  int t = 4;
+  if (const char* e = getenv("GBX_STAGE_THREADS")) t = atoi(e);
+  const int hc = (int)std::thread::hardware_concurrency();
+  if (hc > 0) t = std::min(t, std::max(1, hc - 1));
+  return std::max(0, std::min(t, STAGE_MAXT));
+}
+size_t stage_min_bytes() {
+  if (const char* e = getenv("GBX_STAGE_MIN_MB")) return (size_t)std::max(0ll, atoll(e)) << 20;
+  return STAGE_MIN;
+}
+void stager_release(Stager& S) {
+  for (int t = 0; t < STAGE_MAXT; ++t) {
+    for (int b = 0; b < 2; ++b) {
+      if (S.buf[t][b]) cudaFreeHost(S.buf[t][b]);
+      if (S.ev[t][b]) cudaEventDestroy(S.ev[t][b]);
+      S.buf[t][b] = nullptr;
+      S.ev[t][b] = nullptr;
+    }
+    if (S.done[t]) cudaEventDestroy(S.done[t]);
+    if (S.s[t]) cudaStreamDestroy(S.s[t]);
+    S.done[t] = nullptr;
+    S.s[t] = nullptr;
+  }
+  if (S.start) cudaEventDestroy(S.start);
+  S.start = nullptr;
+  S.device = -1;
+  S.nt = 0;
+}
+cudaError_t stager_prepare(Stager& S, int device, int nt) {
+  if (S.device == device && S.nt == nt) return cudaSuccess;
+  stager_release(S);  // (buffers of another device: pinned memory is portable, streams and events are not)
+  cudaError_t e = cudaSuccess;
+  for (int t = 0; t < nt && e == cudaSuccess; ++t) {
+    e = cudaStreamCreateWithFlags(&S.s[t], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.done[t], cudaEventDisableTiming);
+    for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+      e = cudaHostAlloc((void**)&S.buf[t][b], STAGE_CHUNK, cudaHostAllocDefault);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.ev[t][b], cudaEventDisableTiming);
+    }
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.start, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    stager_release(S);
+    return e;
+  }
+  S.device = device;
+  S.nt = nt;
+  return cudaSuccess;
+}
+}  // namespace
+
+cudaError_t upload_async(int device, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return cudaSuccess;
+  const int nt = stage_threads();
+  bool pageable = false;
+  if (nt > 0 && bytes >= stage_min_bytes()) {
+    cudaPointerAttributes at;
+    const cudaError_t e = cudaPointerGetAttributes(&at, src);
+    pageable = (e == cudaSuccess && at.type == cudaMemoryTypeUnregistered);
+    if (e != cudaSuccess) cudaGetLastError();
+  }
+  if (!pageable) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, st);
+  Stager& S = stager();
+  std::lock_guard<std::mutex> g(S.m);
+  cudaError_t e = stager_prepare(S, device, nt);
+  if (e != cudaSuccess) {  // no pinned memory to be had: the plain copy still works
+    cudaGetLastError();
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, st);
+  }
+  // the chunks land in dst only after what `st` holds so far (dst may be a recycled block)
+  e = cudaEventRecord(S.start, st);
+  if (e != cudaSuccess) return e;
+  const size_t nchunks = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
+  std::atomic<int> first_err{(int)cudaSuccess};
+  auto work = [&](int t) {
+    cudaError_t r = cudaSetDevice(device);
+    if (r == cudaSuccess) r = cudaStreamWaitEvent(S.s[t], S.start, 0);
+    int b = 0;
+    for (size_t c = (size_t)t; c < nchunks && r == cudaSuccess; c += (size_t)nt, b ^= 1) {
+      const size_t off = c * STAGE_CHUNK, len = std::min(STAGE_CHUNK, bytes - off);
+      r = cudaEventSynchronize(S.ev[t][b]);  // the transfer that last used this buffer (a fresh event is complete)
+      if (r != cudaSuccess) break;
+      memcpy(S.buf[t][b], (const char*)src + off, len);
+      r = cudaMemcpyAsync((char*)dst + off, S.buf[t][b], len, cudaMemcpyHostToDevice, S.s[t]);
+      if (r == cudaSuccess) r = cudaEventRecord(S.ev[t][b], S.s[t]);
+    }
+    if (r == cudaSuccess) r = cudaEventRecord(S.done[t], S.s[t]);
+    if (r != cudaSuccess) {
+      int ok = (int)cudaSuccess;
+      first_err.compare_exchange_strong(ok, (int)r);
+    }
+  };
+  std::vector<std::thread> th;
+  th.reserve(nt > 0 ? nt - 1 : 0);
+  for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto& x : th) x.join();
+  e = (cudaError_t)first_err.load();
+  for (int t = 0; t < nt && e == cudaSuccess; ++t) e = cudaStreamWaitEvent(st, S.done[t], 0);
+  if (e != cudaSuccess) {  // leave nothing of ours in flight behind an error
+    for (int t = 0; t < nt; ++t) cudaStreamSynchronize(S.s[t]);
+  }
+  return e;
+}
+
+// The other direction, for results read into pageable arrays (PSI is n x q doubles): the threads' DMAs land in their
+// pinned buffers and are copied out while the next chunk is in flight.  Returns when dst holds the data.
+cudaError_t download_sync(int device, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return cudaStreamSynchronize(st);
+  const int nt = stage_threads();
+  bool pageable = false;
+  if (nt > 0 && bytes >= stage_min_bytes()) {
+    cudaPointerAttributes at;
+    const cudaError_t e = cudaPointerGetAttributes(&at, dst);
+    pageable = (e == cudaSuccess && at.type == cudaMemoryTypeUnregistered);
+    if (e != cudaSuccess) cudaGetLastError();
+  }
+  cudaError_t e = cudaSuccess;
+  if (pageable) {
+    Stager& S = stager();
+    std::lock_guard<std::mutex> g(S.m);
+    e = stager_prepare(S, device, nt);
+    if (e == cudaSuccess) {
+      e = cudaEventRecord(S.start, st);  // the source is final once what `st` holds so far has run
+      if (e != cudaSuccess) return e;
+      const size_t nchunks = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
+      std::atomic<int> first_err{(int)cudaSuccess};
+      auto work = [&](int t) {
+        cudaError_t r = cudaSetDevice(device);
+        if (r == cudaSuccess) r = cudaStreamWaitEvent(S.s[t], S.start, 0);
+        int b = 0, pb = -1;
+        size_t poff = 0, plen = 0;
+        for (size_t c = (size_t)t; c < nchunks && r == cudaSuccess; c += (size_t)nt, b ^= 1) {
+          const size_t off = c * STAGE_CHUNK, len = std::min(STAGE_CHUNK, bytes - off);
+          r = cudaMemcpyAsync(S.buf[t][b], (const char*)src + off, len, cudaMemcpyDeviceToHost, S.s[t]);
+          if (r == cudaSuccess) r = cudaEventRecord(S.ev[t][b], S.s[t]);
+          if (r == cudaSuccess && pb >= 0) {
+            r = cudaEventSynchronize(S.ev[t][pb]);
+            if (r == cudaSuccess) memcpy((char*)dst + poff, S.buf[t][pb], plen);
+          }
+          pb = b;
+          poff = off;
+          plen = len;
+        }
+        if (r == cudaSuccess && pb >= 0) {
+          r = cudaEventSynchronize(S.ev[t][pb]);
+          if (r == cudaSuccess) memcpy((char*)dst + poff, S.buf[t][pb], plen);
+        }
+        if (r != cudaSuccess) {
+          cudaStreamSynchronize(S.s[t]);
+          int ok = (int)cudaSuccess;
+          first_err.compare_exchange_strong(ok, (int)r);
+        }
+      };
+      std::vector<std::thread> th;
+      for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+      work(0);
+      for (auto& x : th) x.join();
+      e = (cudaError_t)first_err.load();
+      if (e != cudaSuccess) return e;
+      return cudaStreamSynchronize(st);
+    }
+    cudaGetLastError();  // no pinned memory: the plain copy
+  }
+  e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  return e;
 }
 
 }  // namespace gbx

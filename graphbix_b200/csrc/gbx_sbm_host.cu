@@ -111,7 +111,7 @@ int load_messages(gbx_sbm* h, const double* psicav, uint64_t seed) {
     GBX_CUDA_TRY(dev_malloc(h->device, (void**)&tmp, bytes ? bytes : 1, h->world == 1));
     own = true;
   }
-  cudaError_t e = cudaMemcpyAsync(tmp, psicav, bytes, cudaMemcpyHostToDevice, h->stream);
+  cudaError_t e = upload_async(h->device, tmp, psicav, bytes, h->stream);   // initial messages: K x q doubles
   int rc = GBX_OK;
   if (e == cudaSuccess) rc = h->pull ? h->ops->pull_load(h, tmp, 0) : h->ops->permute(h, tmp, h->msg[0], 1);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
@@ -840,12 +840,13 @@ int gbx_sbm_get_state(gbx_sbm* h, double* gr, double* Crs, double* PSI, double* 
   if (gr) memcpy(gr, h->h_state->gr, q * sizeof(double));
   if (Crs) memcpy(Crs, h->h_state->C, (size_t)q * q * sizeof(double));
   if (hfield) memcpy(hfield, h->h_state->h, q * sizeof(double));
-  if (PSI) GBX_CUDA_TRY(cudaMemcpyAsync(PSI, h->PSI, (size_t)h->n * q * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (theta) {
     const double* src = h->pull ? h->theta_pp[h->thcur] : h->theta + h->vbeg;
     GBX_CUDA_TRY(cudaMemcpyAsync(theta, src, (size_t)h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   }
-  GBX_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  // the big one last: a pageable PSI (a Julia Array) is filled through pinned chunks by several host threads
+  if (PSI) GBX_CUDA_TRY(download_sync(h->device, PSI, h->PSI, (size_t)h->n * q * sizeof(double), h->stream));
+  else GBX_CUDA_TRY(cudaStreamSynchronize(h->stream));
   return GBX_OK;
 }
 
@@ -862,8 +863,8 @@ int gbx_sbm_get_messages(gbx_sbm* h, double* psicav) {
   }
   int rc = h->pull ? h->ops->pull_export(h, tmp) : h->ops->permute(h, h->msg[h->cur], tmp, 0);
   cudaError_t e = cudaSuccess;
-  if (rc == GBX_OK) e = cudaMemcpyAsync(psicav, tmp, bytes, cudaMemcpyDeviceToHost, h->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (rc == GBX_OK) e = download_sync(h->device, psicav, tmp, bytes, h->stream);
+  else e = cudaStreamSynchronize(h->stream);
   if (own) dev_free(h->device, tmp);
   if (rc != GBX_OK) return rc;
   GBX_CUDA_TRY(e);

@@ -75,6 +75,10 @@ cudaError_t dev_malloc(int device, void** p, size_t bytes, bool pooled);
 void dev_free(int device, void* p);
 void pool_trim(int device);              // device < 0: every device
 int64_t pool_cached_bytes(int device);
+// Host -> device copy ordered on `st`; large pageable sources go through pinned chunks filled by several host threads.
+cudaError_t upload_async(int device, void* dst, const void* src, size_t bytes, cudaStream_t st);
+// Device -> host copy after what `st` holds; returns when dst is filled (and `st` is idle).  Same staging for pageable dst.
+cudaError_t download_sync(int device, void* dst, const void* src, size_t bytes, cudaStream_t st);
 
 // Device copies of the global columns / reverse slots, kept between the graph build and the exchange plan.
 struct GlobalGraph {
