@@ -1040,12 +1040,16 @@ int l_create(gbx_lsbm** out, int device, int count, const int64_t* n_vertices, c
     if (e == cudaSuccess) e = dev_malloc(device, (void**)&d_err, sizeof(int), true);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_err, 0, sizeof(int), h->g.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_sp, spans.data(), sizeof(LSpan) * (size_t)count, cudaMemcpyHostToDevice, h->g.stream);
-    for (int g = 0; g < count && e == cudaSuccess; ++g) {
-      const int64_t Kg = n_links[g], k0 = spans[(size_t)g].k0;
-      if (Kg == 0) continue;
-      for (int c = 0; c < 3 && e == cudaSuccess; ++c)
-        e = cudaMemcpyAsync(d_uni + (size_t)c * K + k0, links3[g] + (size_t)c * Kg, (size_t)Kg * sizeof(int64_t),
-                            cudaMemcpyHostToDevice, h->g.stream);
+    if (e == cudaSuccess) {   // three columns per graph; pageable sources are staged by host threads (gbx_pool.cu)
+      std::vector<UploadSeg> segs;
+      segs.reserve((size_t)3 * (size_t)count);
+      for (int g = 0; g < count; ++g) {
+        const int64_t Kg = n_links[g], k0 = spans[(size_t)g].k0;
+        if (Kg == 0) continue;
+        for (int c = 0; c < 3; ++c)
+          segs.push_back(UploadSeg{d_uni + (size_t)c * K + k0, links3[g] + (size_t)c * Kg, (size_t)Kg * sizeof(int64_t)});
+      }
+      e = upload_segments_async(device, segs.data(), segs.size(), h->g.stream);
     }
     if (e == cudaSuccess) {
       int64_t Kmax = 0;

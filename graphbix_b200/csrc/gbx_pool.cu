@@ -202,39 +202,55 @@ cudaError_t stager_prepare(Stager& S, int device, int nt) {
 }
 }  // namespace
 
-cudaError_t upload_async(int device, void* dst, const void* src, size_t bytes, cudaStream_t st) {
-  if (bytes == 0) return cudaSuccess;
+cudaError_t upload_segments_async(int device, const UploadSeg* segs, size_t nseg, cudaStream_t st) {
+  size_t total = 0;
+  const void* first = nullptr;
+  for (size_t i = 0; i < nseg; ++i) {
+    if (segs[i].bytes && !first) first = segs[i].src;
+    total += segs[i].bytes;
+  }
+  if (total == 0) return cudaSuccess;
   const int nt = stage_threads();
   bool pageable = false;
-  if (nt > 0 && bytes >= stage_min_bytes()) {
+  if (nt > 0 && total >= stage_min_bytes()) {  // (the segments of a call are of one kind: the first one is asked)
     cudaPointerAttributes at;
-    const cudaError_t e = cudaPointerGetAttributes(&at, src);
+    const cudaError_t e = cudaPointerGetAttributes(&at, first);
     pageable = (e == cudaSuccess && at.type == cudaMemoryTypeUnregistered);
     if (e != cudaSuccess) cudaGetLastError();
   }
-  if (!pageable) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, st);
+  auto plain = [&]() {
+    cudaError_t e = cudaSuccess;
+    for (size_t i = 0; i < nseg && e == cudaSuccess; ++i)
+      if (segs[i].bytes) e = cudaMemcpyAsync(segs[i].dst, segs[i].src, segs[i].bytes, cudaMemcpyDefault, st);
+    return e;
+  };
+  if (!pageable) return plain();
   Stager& S = stager();
   std::lock_guard<std::mutex> g(S.m);
   cudaError_t e = stager_prepare(S, device, nt);
-  if (e != cudaSuccess) {  // no pinned memory to be had: the plain copy still works
+  if (e != cudaSuccess) {  // no pinned memory to be had: the plain copies still work
     cudaGetLastError();
-    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, st);
+    return plain();
   }
-  // the chunks land in dst only after what `st` holds so far (dst may be a recycled block)
+  // pieces of at most one chunk, dealt to the threads in turn
+  std::vector<UploadSeg> pieces;
+  pieces.reserve(nseg + total / STAGE_CHUNK + 1);
+  for (size_t i = 0; i < nseg; ++i)
+    for (size_t off = 0; off < segs[i].bytes; off += STAGE_CHUNK)
+      pieces.push_back(UploadSeg{(char*)segs[i].dst + off, (const char*)segs[i].src + off, std::min(STAGE_CHUNK, segs[i].bytes - off)});
+  // the pieces land only after what `st` holds so far (a destination may be a recycled block)
   e = cudaEventRecord(S.start, st);
   if (e != cudaSuccess) return e;
-  const size_t nchunks = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
   std::atomic<int> first_err{(int)cudaSuccess};
   auto work = [&](int t) {
     cudaError_t r = cudaSetDevice(device);
     if (r == cudaSuccess) r = cudaStreamWaitEvent(S.s[t], S.start, 0);
     int b = 0;
-    for (size_t c = (size_t)t; c < nchunks && r == cudaSuccess; c += (size_t)nt, b ^= 1) {
-      const size_t off = c * STAGE_CHUNK, len = std::min(STAGE_CHUNK, bytes - off);
+    for (size_t c = (size_t)t; c < pieces.size() && r == cudaSuccess; c += (size_t)nt, b ^= 1) {
       r = cudaEventSynchronize(S.ev[t][b]);  // the transfer that last used this buffer (a fresh event is complete)
       if (r != cudaSuccess) break;
-      memcpy(S.buf[t][b], (const char*)src + off, len);
-      r = cudaMemcpyAsync((char*)dst + off, S.buf[t][b], len, cudaMemcpyHostToDevice, S.s[t]);
+      memcpy(S.buf[t][b], pieces[c].src, pieces[c].bytes);
+      r = cudaMemcpyAsync(pieces[c].dst, S.buf[t][b], pieces[c].bytes, cudaMemcpyHostToDevice, S.s[t]);
       if (r == cudaSuccess) r = cudaEventRecord(S.ev[t][b], S.s[t]);
     }
     if (r == cudaSuccess) r = cudaEventRecord(S.done[t], S.s[t]);
@@ -254,6 +270,11 @@ cudaError_t upload_async(int device, void* dst, const void* src, size_t bytes, c
     for (int t = 0; t < nt; ++t) cudaStreamSynchronize(S.s[t]);
   }
   return e;
+}
+
+cudaError_t upload_async(int device, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  const UploadSeg seg{dst, src, bytes};
+  return upload_segments_async(device, &seg, 1, st);
 }
 
 // The other direction, for results read into pageable arrays (PSI is n x q doubles): the threads' DMAs land in their

@@ -77,6 +77,13 @@ void pool_trim(int device);              // device < 0: every device
 int64_t pool_cached_bytes(int device);
 // Host -> device copy ordered on `st`; large pageable sources go through pinned chunks filled by several host threads.
 cudaError_t upload_async(int device, void* dst, const void* src, size_t bytes, cudaStream_t st);
+// ... and many pieces at once (the edge lists of a batch of graphs: each too small to be worth staging on its own).
+struct UploadSeg {
+  void* dst;
+  const void* src;
+  size_t bytes;
+};
+cudaError_t upload_segments_async(int device, const UploadSeg* segs, size_t nseg, cudaStream_t st);
 // Device -> host copy after what `st` holds; returns when dst is filled (and `st` is idle).  Same staging for pageable dst.
 cudaError_t download_sync(int device, void* dst, const void* src, size_t bytes, cudaStream_t st);
 

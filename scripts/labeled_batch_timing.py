@@ -11,9 +11,10 @@ graphs = []
 for k in range(ng):
     eps = eps_list[k % 8]
     links, lab = labeled_planted_partition(n, B, [5.0, 3.0], ["a", "d"], eps, seed=977 * (k // 8) + int(eps * 100))
+    links = np.asfortranarray(links)   # column-major, as the Julia host holds it
     und = links[links[:, 0] < links[:, 1]]
     graphs.append((n, [int((und[:, 2] == a + 1).sum()) for a in range(G)], B, G, links))
-for rep in range(2):
+for rep in range(3):
     torch.cuda.synchronize(); t = [time.perf_counter()]
     eng = LabeledBatch([(g[0], g[4]) for g in graphs], B, G)
     t.append(time.perf_counter())

@@ -24,4 +24,4 @@ if l and "error" in l:
     print("labeled leg failed:", l["error"])
 elif l:
     lg = l.get("large_graph", {})
-    print(f"labeled_graphs: {l['graphs']} graphs in {l['seconds']:.2f}s = {l['graphs_per_sec']:.1f} graphs/s  converged {l['converged_fraction']:.2f}  mean it {l['mean_iterations']:.0f}  overlap {l['overlap_by_epsilon']}  large: {lg.get('ms_per_em_iteration', 0):.2f} ms/iter = {lg.get('updates_per_sec', 0)/1e9:.2f} G upd/s")
+    print(f"labeled_graphs: {l['graphs']} graphs in {l['seconds']:.2f}s = {l['graphs_per_sec']:.1f} graphs/s (second batch {l.get('graphs_per_sec_second_batch', 0):.1f})  converged {l['converged_fraction']:.2f}  mean it {l['mean_iterations']:.0f}  overlap {l['overlap_by_epsilon']}  large: {lg.get('ms_per_em_iteration', 0):.2f} ms/iter = {lg.get('updates_per_sec', 0)/1e9:.2f} G upd/s")
