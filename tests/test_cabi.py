@@ -63,3 +63,47 @@ def test_product_does_not_import_the_oracle():
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)
                 assert "oracle/" not in src and "sbm_oracle" not in src, os.path.join(dirpath, f)
+
+
+def _header_structs():
+    """{struct name: [(ctype, field), ...]} of the typedef'd structs of include/graphbix_cuda.h, in declaration order."""
+    text = open(os.path.join(ROOT, "include", "graphbix_cuda.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = {}
+    for body, name in re.findall(r"typedef\s+struct\s+\w+\s*\{(.*?)\}\s*(\w+)\s*;", text, flags=re.S):
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            m = re.match(r"(unsigned long long|uint64_t|int64_t|double|int)\s+(.*)$", decl, flags=re.S)
+            assert m, f"unparsed declaration in {name}: {decl!r}"
+            fields += [(m.group(1), f.strip()) for f in m.group(2).split(",")]
+        out[name] = fields
+    return out
+
+
+def _julia_structs():
+    """{struct name: [(type, field), ...]} of integration/graphbix_cuda.jl."""
+    text = open(os.path.join(ROOT, "integration", "graphbix_cuda.jl")).read()
+    out = {}
+    for name, body in re.findall(r"^(?:mutable\s+)?struct\s+(\w+)[^\n]*\n(.*?)\nend", text, flags=re.S | re.M):
+        body = re.sub(r"#[^\n]*", "", body)
+        out[name] = [(t, f) for f, t in re.findall(r"(\w+)::(\w+)", body)]
+    return out
+
+
+def test_julia_binding_matches_header():
+    """integration/graphbix_cuda.jl cannot be run here (no Julia): at least its struct layouts and the symbols it
+    `ccall`s must be the header's."""
+    hs, js = _header_structs(), _julia_structs()
+    ctype = {"Cint": "int", "Cdouble": "double", "Int64": "int64_t", "UInt64": "uint64_t"}
+    pairs = {"GbxSbmOptions": "gbx_sbm_options", "GbxSbmResult": "gbx_sbm_result", "GbxModOptions": "gbx_mod_options",
+             "GbxModResult": "gbx_mod_result", "GbxLsbmOptions": "gbx_lsbm_options", "GbxLsbmResult": "gbx_lsbm_result"}
+    for jl, c in pairs.items():
+        assert jl in js and c in hs, (jl, c)
+        assert [(ctype[t], f) for t, f in js[jl]] == hs[c], f"{jl} and struct {c} differ"
+    text = open(os.path.join(ROOT, "integration", "graphbix_cuda.jl")).read()
+    called = set(re.findall(r"ccall\(\(:(\w+),\s*libgbx\)", text))
+    assert {"gbx_sbm_create", "gbx_sbm_em", "gbx_mod_em", "gbx_lsbm_create_batch", "gbx_lsbm_em"} <= called
+    assert called <= set(_header_symbols()), called - set(_header_symbols())
