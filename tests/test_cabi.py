@@ -107,3 +107,29 @@ def test_julia_binding_matches_header():
     called = set(re.findall(r"ccall\(\(:(\w+),\s*libgbx\)", text))
     assert {"gbx_sbm_create", "gbx_sbm_em", "gbx_mod_em", "gbx_lsbm_create_batch", "gbx_lsbm_em"} <= called
     assert called <= set(_header_symbols()), called - set(_header_symbols())
+
+
+def test_julia_ccall_argument_counts_match_header():
+    """Every `ccall` of the Julia binding passes as many arguments as the header's prototype takes, and pointer
+    arguments where the prototype has pointers."""
+    htext = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "graphbix_cuda.h")).read(), flags=re.S)
+    protos = {}
+    for name, args in re.findall(r"\b(gbx_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", htext):
+        args = " ".join(args.split())
+        protos[name] = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+    jtext = open(os.path.join(ROOT, "integration", "graphbix_cuda.jl")).read()
+    calls = []
+    for m in re.finditer(r"ccall\(\(:(\w+),\s*libgbx\),\s*\w+,\s*\(", jtext):
+        depth, i = 1, m.end()
+        while depth:                      # the balanced end of the argument-type tuple
+            depth += {"(": 1, ")": -1}.get(jtext[i], 0)
+            i += 1
+        calls.append((m.group(1), jtext[m.end():i - 1]))
+    assert len(calls) >= 20
+    for name, tup in calls:
+        jargs = [a.strip() for a in " ".join(tup.split()).split(",") if a.strip()]
+        assert name in protos, name
+        assert len(jargs) == len(protos[name]), f"{name}: ccall passes {len(jargs)} arguments, the header takes {len(protos[name])}"
+        for ja, ha in zip(jargs, protos[name]):
+            is_ptr = ja.startswith(("Ptr{", "Ref{")) or ja == "Cstring"
+            assert is_ptr == ("*" in ha), f"{name}: {ja} against `{ha}`"
