@@ -126,8 +126,8 @@ int64_t pool_cached_bytes(int device) {
 
 // ---------------------------------------------------------------------------------------------
 // Upload of a large PAGEABLE host array.  A Julia `ccall` hands over ordinary Arrays: cudaMemcpyAsync from pageable
-// memory goes through the driver's single staging buffer at ~5 GB/s (the 256 MB Int64 edge list of N = 1M, degree 16:
-// 49 ms, more than the 20 EM iterations that follow).  Here a few host threads copy alternate chunks into their own
+// memory goes through the driver's single staging buffer at ~6 GB/s (creating a handle from the 256 MB Int64 edge list
+// of N = 1M, degree 16: 28 ms against 9-10 ms from pinned memory).  Here a few host threads copy alternate chunks into their own
 // pinned buffers and queue the DMA of each chunk on their own streams, so the host copies run in parallel with each
 // other and with the transfers; `st` then waits for all of them.  Pinned or small sources take one cudaMemcpyAsync.
 // On return the source has been read completely (as with cudaMemcpyAsync from pageable memory).
